@@ -1,0 +1,179 @@
+"""CPU oracle for the polar encode / SC / SCL hot path -- TEST INFRASTRUCTURE ONLY.
+
+`oracle/` is the checker, never the product: only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / `--impl reference` legs may import it.  polarcub_b200/ never does.
+
+The arithmetic lives in oracle/polar_oracle*.c (a restatement of the reference's float64
+probability-domain recursion, cited line by line there); this module is the ctypes loader plus
+numpy-typed wrappers.  Parity is PINNED against golden vectors generated from the live reference
+(oracle/gen_golden.py -> tests/golden/*.npz, checked by tests/test_oracle_golden.py).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_f64p = ctypes.POINTER(ctypes.c_double)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+
+
+def build(force=False):
+    """Compile oracle/libpolar_oracle.so with gcc (Makefile in this directory)."""
+    so = os.path.join(_HERE, "libpolar_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".c")]
+    stale = (not os.path.isfile(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "libpolar_oracle.so"], check=True, capture_output=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libpolar_oracle.so")
+        if not os.path.isfile(so):
+            build()
+        _LIB = ctypes.CDLL(so)
+    return _LIB
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def frozen_mask(N, frozenSet):
+    m = np.zeros(N, dtype=np.uint8)
+    if len(frozenSet):
+        m[np.fromiter(frozenSet, dtype=np.int64)] = 1
+    return m
+
+
+def common_randomness(N, seed):
+    """randomlyGeneratedNumbers, BinaryPolarEncoderDecoder.py:33-44 (CPython MT19937 via the stdlib)."""
+    import random
+    if seed == -1:
+        return np.ones(N, dtype=np.float64)
+    rng = random.Random()
+    rng.seed(seed)
+    return np.array([rng.random() for _ in range(N)], dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------------------------------
+def bin_encode(N, fmask, r, xprobs, info, want_marg=False):
+    fmask, r, xprobs, info = _c(fmask, np.uint8), _c(r, np.float64), _c(xprobs, np.float64), _c(info, np.int64)
+    cw = np.empty(N, dtype=np.int64)
+    marg = np.empty((N, 2), dtype=np.float64) if want_marg else None
+    rc = lib().po_bin_encode(ctypes.c_int(N), _p(fmask, _u8p), _p(r, _f64p), _p(xprobs, _f64p), _p(info, _i64p),
+                             _p(cw, _i64p), _p(marg, _f64p))
+    assert rc == 0, rc
+    return (cw, marg) if want_marg else cw
+
+
+def bin_decode(N, fmask, r, xprobs, xyprobs, want_marg=False, want_lvl1=False):
+    fmask, r = _c(fmask, np.uint8), _c(r, np.float64)
+    xprobs, xyprobs = _c(xprobs, np.float64), _c(xyprobs, np.float64)
+    k = int(N - fmask.sum())
+    cw = np.empty(N, dtype=np.int64)
+    info = np.full(k, -1, dtype=np.int64)
+    marg = np.empty((N, 2), dtype=np.float64) if want_marg else None
+    l1m = np.empty((N // 2, 2), dtype=np.float64) if want_lvl1 and N > 1 else None
+    l1p = np.empty((N // 2, 2), dtype=np.float64) if want_lvl1 and N > 1 else None
+    rc = lib().po_bin_decode(ctypes.c_int(N), _p(fmask, _u8p), _p(r, _f64p), _p(xprobs, _f64p), _p(xyprobs, _f64p),
+                             _p(cw, _i64p), _p(info, _i64p), _p(marg, _f64p), _p(l1m, _f64p), _p(l1p, _f64p))
+    assert rc == 0, rc
+    out = [cw, info]
+    if want_marg:
+        out.append(marg)
+    if want_lvl1:
+        out += [l1m, l1p]
+    return tuple(out)
+
+
+def bin_decode_batch(N, fmask, r, xprobs, xyprobs):
+    fmask, r = _c(fmask, np.uint8), _c(r, np.float64)
+    xprobs, xyprobs = _c(xprobs, np.float64), _c(xyprobs, np.float64)
+    B = xyprobs.shape[0]
+    k = int(N - fmask.sum())
+    cw = np.empty((B, N), dtype=np.int64)
+    info = np.full((B, k), -1, dtype=np.int64)
+    rc = lib().po_bin_decode_batch(ctypes.c_int(B), ctypes.c_int(N), ctypes.c_int(k), _p(fmask, _u8p), _p(r, _f64p),
+                                   _p(xprobs, _f64p), _p(xyprobs, _f64p), _p(cw, _i64p), _p(info, _i64p))
+    assert rc == 0, rc
+    return cw, info
+
+
+def bin_encode_batch(N, fmask, r, xprobs, info):
+    fmask, r, xprobs, info = _c(fmask, np.uint8), _c(r, np.float64), _c(xprobs, np.float64), _c(info, np.int64)
+    B, k = info.shape
+    cw = np.empty((B, N), dtype=np.int64)
+    rc = lib().po_bin_encode_batch(ctypes.c_int(B), ctypes.c_int(N), ctypes.c_int(k), _p(fmask, _u8p), _p(r, _f64p),
+                                   _p(xprobs, _f64p), _p(info, _i64p), _p(cw, _i64p))
+    assert rc == 0, rc
+    return cw
+
+
+def polar_transform_bits(x):
+    x = _c(x, np.int64)
+    u = np.empty_like(x)
+    rc = lib().po_polar_transform_bits(ctypes.c_int(x.shape[0]), _p(x, _i64p), _p(u, _i64p))
+    assert rc == 0, rc
+    return u
+
+
+# ---------------------------------------------------------------------------------------------------
+def q_encode(q, N, fmask, xprobs, info):
+    fmask, xprobs, info = _c(fmask, np.uint8), _c(xprobs, np.float64), _c(info, np.int64)
+    cw = np.empty(N, dtype=np.int64)
+    rc = lib().po_q_encode(ctypes.c_int(q), ctypes.c_int(N), _p(fmask, _u8p), _p(xprobs, _f64p), _p(info, _i64p),
+                           _p(cw, _i64p))
+    assert rc == 0, rc
+    return cw
+
+
+def q_decode(q, N, fmask, xprobs, xyprobs, want_marg=False, want_lvl1=False):
+    fmask, xprobs, xyprobs = _c(fmask, np.uint8), _c(xprobs, np.float64), _c(xyprobs, np.float64)
+    k = int(N - fmask.sum())
+    cw = np.empty(N, dtype=np.int64)
+    info = np.full(k, -1, dtype=np.int64)
+    marg = np.empty((N, q), dtype=np.float64) if want_marg else None
+    l1m = np.empty((N // 2, q), dtype=np.float64) if want_lvl1 and N > 1 else None
+    l1p = np.empty((N // 2, q), dtype=np.float64) if want_lvl1 and N > 1 else None
+    rc = lib().po_q_decode(ctypes.c_int(q), ctypes.c_int(N), _p(fmask, _u8p), _p(xprobs, _f64p), _p(xyprobs, _f64p),
+                           _p(cw, _i64p), _p(info, _i64p), _p(marg, _f64p), _p(l1m, _f64p), _p(l1p, _f64p))
+    assert rc == 0, rc
+    out = [cw, info]
+    if want_marg:
+        out.append(marg)
+    if want_lvl1:
+        out += [l1m, l1p]
+    return tuple(out)
+
+
+def q_decode_batch(q, N, fmask, xprobs, xyprobs):
+    fmask, xprobs, xyprobs = _c(fmask, np.uint8), _c(xprobs, np.float64), _c(xyprobs, np.float64)
+    B = xyprobs.shape[0]
+    k = int(N - fmask.sum())
+    cw = np.empty((B, N), dtype=np.int64)
+    info = np.full((B, k), -1, dtype=np.int64)
+    rc = lib().po_q_decode_batch(ctypes.c_int(B), ctypes.c_int(q), ctypes.c_int(N), ctypes.c_int(k), _p(fmask, _u8p),
+                                 _p(xprobs, _f64p), _p(xyprobs, _f64p), _p(cw, _i64p), _p(info, _i64p))
+    assert rc == 0, rc
+    return cw, info
+
+
+def polar_transform_qudits(q, x):
+    x = _c(x, np.int64)
+    u = np.empty_like(x)
+    rc = lib().po_polar_transform_qudits(ctypes.c_int(q), ctypes.c_int(x.shape[0]), _p(x, _i64p), _p(u, _i64p))
+    assert rc == 0, rc
+    return u
