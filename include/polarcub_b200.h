@@ -1,0 +1,109 @@
+/*
+ * polarcub_b200.h -- C-ABI of the B200-native batched polar-code engine.
+ *
+ * Drop-in boundary for the encode / decode hot path of benjilieber/polarcub.  Every entry point takes
+ * plain pointers and sizes (no torch / C++ types), returns 0 on success or a negative pc_status, never
+ * throws, and launches on the CUDA stream passed as `stream` (a cudaStream_t cast to void*).
+ * All `d_*` pointers are DEVICE pointers owned by the caller; `h_*` pointers are host pointers read
+ * before the call returns.  A plan is immutable after creation and may be shared between threads.
+ *
+ * Bit packing: bit i of a frame lives in word i/32, bit position i%32 (LSB first).  Codewords are in
+ * the reference's index order (x = u B_N F^{(x)n}, BinaryPolarEncoderDecoder.py:321-323).
+ *
+ * Reference interface replaced by each entry point (paths relative to the reference root):
+ *   pc_plan_create            BinaryPolarEncoderDecoder.__init__ / initializeFrozenOrInformation...
+ *                             (BinaryPolarEncoderDecoder.py:16-44), QaryPolarEncoderDecoder.__init__
+ *                             (QaryPolarEncoderDecoder.py:27-63)
+ *   pc_encode_bits            BinaryPolarEncoderDecoder.encode            (BinaryPolarEncoderDecoder.py:46-69)
+ *                             with a uniform prior; polarTransformOfBits is its inverse (:494-516)
+ *   pc_sc_decode_probs        BinaryPolarEncoderDecoder.decode            (BinaryPolarEncoderDecoder.py:71-99,
+ *                             recursion :223-325, arithmetic BinaryMemorylessVectorDistribution.py:15-87)
+ *   pc_sc_decode_symbols      same, fused with makeBinaryMemorylessVectorDistribution(length, yvec)
+ *                             (ScalarDistributions/BinaryMemorylessDistribution.py:245-258)
+ *   pc_qsc_encode             QaryPolarEncoderDecoder.encode              (QaryPolarEncoderDecoder.py:65-88)
+ *   pc_qsc_decode_probs       QaryPolarEncoderDecoder.decode              (QaryPolarEncoderDecoder.py:90-116,
+ *                             recursion :318-401, arithmetic QaryMemorylessVectorDistribution.py:26-118)
+ *   pc_scl_decode_probs       QaryPolarEncoderDecoder.listDecode          (QaryPolarEncoderDecoder.py:118-227,
+ *                             recursion :403-757, helpers :759-820, :867-872)
+ *   pc_trellis_decode         BinaryPolarEncoderDecoder.decode over CollectionOfBinaryTrellises
+ *                             (VectorDistributions/BinaryTrellis.py:206-306, CollectionOfBinaryTrellises.py:55-103)
+ */
+#ifndef POLARCUB_B200_H
+#define POLARCUB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pc_plan pc_plan;
+
+enum pc_status {
+    PC_OK = 0,
+    PC_ERR_INVALID = -1,   /* bad argument (null pointer, unsupported q / n / L, ...) */
+    PC_ERR_NOMEM = -2,     /* host or device allocation failed, or the workspace is too small */
+    PC_ERR_CUDA = -3,      /* a CUDA runtime call failed; see pc_last_error() */
+    PC_ERR_UNSUPPORTED = -4
+};
+
+/* library / build identification */
+int pc_version(void);
+/* thread-local text of the last error returned on this thread ("" if none) */
+const char *pc_last_error(void);
+/* number of kernels launched by this library since load (all threads); used by bench.py's gpu_launches */
+unsigned long long pc_kernel_launch_count(void);
+
+/* ---- plans -------------------------------------------------------------------------------------- */
+/* q: alphabet size (2 = binary path).  n: log2 of the block length, 0 <= n <= 24.
+ * h_frozen_mask[N]: 1 = frozen u index.  h_frozen_vals[N]: the value every frozen u_i takes
+ * (binary: (0.5 >= r_i) ? 0 : 1 for a uniform prior, BinaryPolarEncoderDecoder.py:258-262; q-ary: 0,
+ * QaryPolarEncoderDecoder.py:351); entries at information positions are ignored.
+ * The plan is bound to the CUDA device current at creation. */
+int pc_plan_create(int q, int n, const uint8_t *h_frozen_mask, const uint8_t *h_frozen_vals, pc_plan **out);
+void pc_plan_destroy(pc_plan *plan);
+int pc_plan_k(const pc_plan *plan);      /* number of information symbols */
+int pc_plan_length(const pc_plan *plan); /* N */
+/* number of schedule nodes after rate-0 pruning (diagnostic) */
+int pc_plan_schedule_len(const pc_plan *plan);
+
+/* ---- binary encode ------------------------------------------------------------------------------ */
+/* d_info_packed [B][ceil(k/32)] -> d_cw_packed [B][ceil(N/32)].  Frozen bits come from the plan. */
+int pc_encode_bits(const pc_plan *plan, const uint32_t *d_info_packed, uint32_t *d_cw_packed, int64_t B,
+                   void *stream);
+/* inverse map x -> u (polarTransformOfBits): d_cw_packed [B][ceil(N/32)] -> d_u_packed [B][ceil(N/32)] */
+int pc_polar_transform_bits(int n, const uint32_t *d_cw_packed, uint32_t *d_u_packed, int64_t B, void *stream);
+
+/* ---- binary SC decode --------------------------------------------------------------------------- */
+#define PC_INPUT_SYMBOLS 0
+#define PC_INPUT_PROBS 1
+/* bytes of device scratch the decoders want for a batch of B frames (they accept less and then work in
+ * smaller chunks, down to 32 frames; PC_ERR_NOMEM below that) */
+size_t pc_sc_workspace_bytes(const pc_plan *plan, int64_t B, int input_kind);
+
+/* d_xy [B][N][2] float64: entry i holds P(X=0,Y=y_i), P(X=1,Y=y_i) exactly as the reference's
+ * xyVectorDistribution.probs.  Outputs: d_cw_packed [B][ceil(N/32)] (re-encoded codeword) and
+ * d_info_packed [B][ceil(k/32)].  Arithmetic is float64 and BIT-IDENTICAL to the reference (same
+ * products, sums, max-normalisation and tie rule). */
+int pc_sc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint32_t *d_cw_packed,
+                       uint32_t *d_info_packed, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* d_y [B][N] uint8 channel output symbols; h_table [Y][2] float64 = the channel's joint probabilities
+ * (BinaryMemorylessDistribution.probs), 1 <= Y <= 16. */
+int pc_sc_decode_symbols(const pc_plan *plan, const uint8_t *d_y, int64_t B, const double *h_table, int Y,
+                         uint32_t *d_cw_packed, uint32_t *d_info_packed, void *d_workspace, size_t workspace_bytes,
+                         void *stream);
+
+/* ---- q-ary SC ------------------------------------------------------------------------------------ */
+/* symbols are uint8 in [0, q).  d_info [B][k] -> d_cw [B][N] */
+int pc_qsc_encode(const pc_plan *plan, const uint8_t *d_info, uint8_t *d_cw, int64_t B, void *stream);
+size_t pc_qsc_workspace_bytes(const pc_plan *plan, int64_t B);
+/* d_xy [B][N][q] float64 (linear domain).  Outputs d_cw [B][N], d_info [B][k] uint8. */
+int pc_qsc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint8_t *d_cw, uint8_t *d_info,
+                        void *d_workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLARCUB_B200_H */

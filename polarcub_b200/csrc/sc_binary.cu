@@ -1,0 +1,441 @@
+// sc_binary.cu -- batched binary successive-cancellation decoding, float64, bit-identical to the reference.
+//
+// Replaces BinaryPolarEncoderDecoder.decode / recursiveEncodeDecode (BinaryPolarEncoderDecoder.py:71-99, :223-325)
+// and the arithmetic of BinaryMemorylessVectorDistribution (minusTransform :15-29, plusTransform :31-47,
+// calcNormalizationVector / normalize :71-87, calcMarginalizedProbabilities :52-69) for a uniform prior.
+//
+// Design (B200-first, not a port of the recursion):
+//  * one FRAME PER LANE: all frames share the frozen set, so the tree walk is identical for every lane
+//    of a warp (no divergence, no lane idles in the small stages that dominate SC) and every node vector
+//    is laid out [element][lane] so loads and stores are fully coalesced 256-byte rows;
+//  * the walk is a host-flattened schedule (plan.cu) with maximal rate-0 sub-trees pruned;
+//  * node state is ONE float64 per element: after the reference's max-normalisation a probability pair is
+//    (1, r) or (r, 1) with r = min/max, or (0, 0) after contradicting hard knowledge.  We store r with the
+//    sign bit saying which side is 1, and NaN for (0, 0).  Every product / sum / quotient the reference
+//    performs on the pair is reproduced on r with the same IEEE-754 roundings (multiplications by exactly
+//    1.0 are dropped -- they are exact), so decisions and probabilities are bit-identical;
+//  * levels 0..LS of the tree live in shared memory (one private column per thread), the larger levels in
+//    an L2-resident global scratch private to the warp; partial sums are bit-packed, the low five levels in
+//    a register;
+//  * the channel level is read through a transposed, bit-reversed copy made by the ingest kernel, and the
+//    decoded words are transposed back (codeword bit-reversed to the reference order) by the egress kernel.
+#include "common.cuh"
+
+namespace pc {
+
+constexpr int LS = 4;            // levels 0..LS in shared memory: 2^(LS+1)-1 doubles per thread
+constexpr int SC_THREADS = 256;  // 8 warps = 256 frames per block
+constexpr int SMEM_VALS = (1 << (LS + 1)) - 1;
+constexpr int SC_BLOCKS_PER_SM = 3;
+constexpr int SC_MAX_N = 16;     // frame-per-lane kernel; larger blocks use the streamed decoder
+
+struct ScParams {
+    int n, k, n_sched, Y;
+    int64_t frames;  // frames in this chunk
+    int64_t Bpad;    // row pitch (frames, multiple of 32) of the transposed buffers
+    const SchedEntry *sched;
+    const uint32_t *r0_words;
+    const void *in_t;   // [N][Bpad] uint8 symbols or double2 probability pairs, natural (bit-reversed) order
+    double *vals;       // [warps][N - 2^(LS+1)][32] scratch for levels > LS
+    uint32_t *cw_t;     // [Nw][Bpad] natural-order codeword words (also the partial-sum store)
+    uint32_t *info_t;   // [Kw][Bpad]
+    double table[32];   // symbols: [Y][2] joint probabilities
+};
+
+__device__ __forceinline__ double d_abs(double x) { return __longlong_as_double(__double_as_longlong(x) & 0x7fffffffffffffffLL); }
+__device__ __forceinline__ uint32_t d_sign(double x) { return (uint32_t)(__double2hiint(x)) >> 31; }
+__device__ __forceinline__ double d_pack(double r, uint32_t side) {
+    return __hiloint2double((__double2hiint(r) & 0x7fffffff) | (int)(side << 31), __double2loint(r));
+}
+
+// normalise a raw pair by its maximum (BinaryMemorylessVectorDistribution.py:71-87) and pack it.
+// 0/0 -> NaN encodes the (0,0) state the reference keeps when the maximum is 0.
+__device__ __forceinline__ double pack_pair(double o0, double o1) {
+    const bool gt = o1 > o0;
+    const double mx = gt ? o1 : o0, mn = gt ? o0 : o1;
+    return d_pack(mn / mx, gt ? 1u : 0u);
+}
+
+// f on raw pairs (channel level), BinaryMemorylessVectorDistribution.py:21-26
+__device__ __forceinline__ double f_raw(double a0, double a1, double b0, double b1) {
+    const double o0 = __dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1));
+    const double o1 = __dadd_rn(__dmul_rn(a0, b1), __dmul_rn(a1, b0));
+    return pack_pair(o0, o1);
+}
+// g on raw pairs, BinaryMemorylessVectorDistribution.py:37-44
+__device__ __forceinline__ double g_raw(double a0, double a1, double b0, double b1, uint32_t u) {
+    const double o0 = __dmul_rn(u ? a1 : a0, b0);
+    const double o1 = __dmul_rn(u ? a0 : a1, b1);
+    return pack_pair(o0, o1);
+}
+// f on packed normalised values: (o0,o1) is (1 + ra*rb, ra + rb), or swapped when the sides differ
+__device__ __forceinline__ double f_packed(double a, double b) {
+    const double ra = d_abs(a), rb = d_abs(b);
+    const uint32_t s = d_sign(a) ^ d_sign(b);
+    const double A = __dadd_rn(1.0, __dmul_rn(ra, rb));
+    const double Bv = __dadd_rn(ra, rb);
+    const bool c = Bv > A, d = A > Bv;
+    const double mx = c ? Bv : A, mn = c ? A : Bv;
+    return d_pack(mn / mx, (s ? d : c) ? 1u : 0u);
+}
+// g on packed normalised values
+__device__ __forceinline__ double g_packed(double a, double b, uint32_t u) {
+    const double ra = d_abs(a), rb = d_abs(b);
+    const uint32_t sa = d_sign(a) ^ u, sb = d_sign(b);
+    if (sa == sb) {  // (1*1, ra*rb): already normalised (division by 1.0 is exact)
+        const double r = __dmul_rn(ra, rb);
+        return d_pack(r, (sb && r < 1.0) ? 1u : 0u);
+    }
+    // out[sb] = ra, out[1-sb] = rb
+    const bool c = ra > rb;
+    const double mx = c ? ra : rb, mn = c ? rb : ra;
+    const bool gt = sb ? (ra > rb) : (rb > ra);
+    return d_pack(mn / mx, gt ? 1u : 0u);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel(const ScParams p) {
+    extern __shared__ double sm_vals[];  // [SMEM_VALS][SC_THREADS]
+    __shared__ double s_table[32];
+    if (threadIdx.x < 32) s_table[threadIdx.x] = p.table[threadIdx.x];
+    __syncthreads();
+    const int n = p.n, N = 1 << n;
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * (SC_THREADS / 32) + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * (SC_THREADS / 32);
+    const int64_t groups = (p.frames + 31) / 32;
+    const int64_t gvals = N > (1 << (LS + 1)) ? (int64_t)N - (1 << (LS + 1)) : 0;
+    double *gv = p.vals + (int64_t)warp_global * gvals * 32 + lane;
+    double *sv = sm_vals + threadIdx.x;
+
+    auto ld = [&](int lev, int h) -> double {
+        return lev <= LS ? sv[(((1 << lev) - 1) + h) * SC_THREADS] : gv[(int64_t)(((1 << lev) - (1 << (LS + 1))) + h) * 32];
+    };
+    auto st = [&](int lev, int h, double v) {
+        if (lev <= LS)
+            sv[(((1 << lev) - 1) + h) * SC_THREADS] = v;
+        else
+            gv[(int64_t)(((1 << lev) - (1 << (LS + 1))) + h) * 32] = v;
+    };
+
+    for (int64_t grp = warp_global; grp < groups; grp += warps_total) {
+        const int64_t col = grp * 32 + lane;  // always < Bpad; columns >= frames hold padding
+        auto root = [&](int h, double &v0, double &v1) {
+            if (KIND == PC_INPUT_SYMBOLS) {
+                const uint32_t y = ((const uint8_t *)p.in_t)[(int64_t)h * p.Bpad + col];
+                v0 = s_table[2 * y];
+                v1 = s_table[2 * y + 1];
+            } else {
+                const double2 t = ((const double2 *)p.in_t)[(int64_t)h * p.Bpad + col];
+                v0 = t.x;
+                v1 = t.y;
+            }
+        };
+        uint32_t *xw = p.cw_t + col;  // word w at xw[w * Bpad]
+        uint32_t *iw = p.info_t + col;
+        uint32_t cwreg = 0, infoacc = 0;
+        int icount = 0;
+
+        if (n == 0) {  // no transform: leaf rule on the raw pair (BinaryPolarEncoderDecoder.py:250-252)
+            const SchedEntry e = p.sched[0];
+            uint32_t bit = e.bits & 1u;
+            if (e.kind == NODE_INFO) {
+                double p0, p1;
+                root(0, p0, p1);
+                const double s = __dadd_rn(__dadd_rn(0.0, p0), p1);
+                bit = 0;
+                if (s > 0.0) bit = (p0 / s >= p1 / s) ? 0u : 1u;
+                iw[0] = bit;
+            }
+            xw[0] = bit;
+            continue;
+        }
+
+        for (int ei = 0; ei < p.n_sched; ++ei) {
+            const SchedEntry e = p.sched[ei];
+            const int i = e.i, l = e.l, top = e.top;
+            const int stop = e.kind == NODE_RATE0 ? l + 1 : l;
+            int lev;
+            if (i == 0) {
+                lev = n - 1;
+            } else if (top >= stop) {
+                // ---- g at level `top` with the sibling's partial sums x[i - 2^top, i) ----------------
+                const int size = 1 << top;
+                if (top < 5) {
+                    const uint32_t ub = cwreg >> ((i - size) & 31);
+                    if (top + 1 == n) {
+                        for (int h = 0; h < size; ++h) {
+                            double a0, a1, b0, b1;
+                            root(h, a0, a1);
+                            root(h + size, b0, b1);
+                            st(top, h, g_raw(a0, a1, b0, b1, (ub >> h) & 1u));
+                        }
+                    } else {
+#pragma unroll 2
+                        for (int h = 0; h < size; ++h)
+                            st(top, h, g_packed(ld(top + 1, h), ld(top + 1, h + size), (ub >> h) & 1u));
+                    }
+                } else {
+                    const uint32_t *uw = xw + (int64_t)((i - size) >> 5) * p.Bpad;
+                    for (int w = 0; w < (size >> 5); ++w) {
+                        const uint32_t ub = uw[(int64_t)w * p.Bpad];
+                        if (top + 1 == n) {
+                            for (int b = 0; b < 32; ++b) {
+                                const int h = 32 * w + b;
+                                double a0, a1, b0, b1;
+                                root(h, a0, a1);
+                                root(h + size, b0, b1);
+                                st(top, h, g_raw(a0, a1, b0, b1, (ub >> b) & 1u));
+                            }
+                        } else {
+#pragma unroll 2
+                            for (int b = 0; b < 32; ++b) {
+                                const int h = 32 * w + b;
+                                st(top, h, g_packed(ld(top + 1, h), ld(top + 1, h + size), (ub >> b) & 1u));
+                            }
+                        }
+                    }
+                }
+                lev = top - 1;
+            } else {
+                lev = -1;  // a rate-0 node that is the whole plus child: nothing to compute
+            }
+            // ---- f down to the node ------------------------------------------------------------------
+            for (; lev >= stop; --lev) {
+                const int size = 1 << lev;
+                if (lev + 1 == n) {
+                    for (int h = 0; h < size; ++h) {
+                        double a0, a1, b0, b1;
+                        root(h, a0, a1);
+                        root(h + size, b0, b1);
+                        st(lev, h, f_raw(a0, a1, b0, b1));
+                    }
+                } else {
+#pragma unroll 2
+                    for (int h = 0; h < size; ++h) st(lev, h, f_packed(ld(lev + 1, h), ld(lev + 1, h + size)));
+                }
+            }
+            // ---- the node itself -----------------------------------------------------------------------
+            if (e.kind == NODE_INFO) {
+                const uint32_t bit = d_sign(ld(0, 0));  // p0 >= p1 -> 0 (ties and (0,0) -> 0), :252
+                infoacc |= bit << (icount & 31);
+                if ((++icount & 31) == 0) {
+                    iw[(int64_t)((icount >> 5) - 1) * p.Bpad] = infoacc;
+                    infoacc = 0;
+                }
+                cwreg |= bit << (i & 31);
+            } else if (l < 5) {
+                cwreg |= e.bits << (i & 31);
+            } else {
+                for (int w = 0; w < (1 << (l - 5)); ++w) xw[(int64_t)((i >> 5) + w) * p.Bpad] = p.r0_words[e.bits + w];
+            }
+            // ---- partial sums: x[lo, lo+s) ^= x[lo+s, lo+2s) whenever a plus child completes -----------
+            int lv = l, ii = i;
+            while (lv < 5 && lv < n && ((ii >> lv) & 1)) {  // inside the register word
+                const int s = 1 << lv;
+                const int sh = (ii - s) & 31;
+                cwreg ^= ((cwreg >> (sh + s)) & ((1u << s) - 1u)) << sh;
+                ii -= s;
+                ++lv;
+            }
+            const int end = i + (1 << l);
+            if (l < 5 && ((end & 31) == 0 || end == N)) {  // the register word is complete
+                xw[(int64_t)((end - 1) >> 5) * p.Bpad] = cwreg;
+                cwreg = 0;
+            }
+            while (lv < n && ((ii >> lv) & 1)) {  // whole words (lv >= 5 here)
+                const int s = 1 << lv;
+                uint32_t *lo = xw + (int64_t)((ii - s) >> 5) * p.Bpad;
+                for (int w = 0; w < (s >> 5); ++w) lo[(int64_t)w * p.Bpad] ^= lo[(int64_t)(w + (s >> 5)) * p.Bpad];
+                ii -= s;
+                ++lv;
+            }
+        }
+        if (icount & 31) iw[(int64_t)(icount >> 5) * p.Bpad] = infoacc;
+    }
+}
+
+// ---- ingest: caller layout [frames][N] -> transposed, bit-reversed [N][Bpad] --------------------------
+template <class T>
+__global__ void __launch_bounds__(256) ingest_kernel(int n, int64_t frames, int64_t Bpad, const T *__restrict__ in,
+                                                     T *__restrict__ out, T pad_value) {
+    __shared__ T tile[32][33];
+    const int N = 1 << n;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t f0 = (int64_t)blockIdx.x * 32;
+    const int ptiles = (N + 31) / 32;
+    for (int pt = blockIdx.y; pt < ptiles; pt += gridDim.y) {
+        const int i0 = pt * 32;
+        for (int r = ty; r < 32; r += 8) {
+            const int64_t f = f0 + r;
+            const int pos = i0 + tx;
+            tile[r][tx] = (f < frames && pos < N) ? in[f * N + pos] : pad_value;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int pos = i0 + r;
+            if (pos < N) out[(int64_t)bitrev_n((uint32_t)pos, n) * Bpad + f0 + tx] = tile[tx][r];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- egress: [W][Bpad] words -> [frames][W], optionally applying the bit-reversal permutation ---------
+template <bool BITREV>
+__global__ void __launch_bounds__(256) egress_kernel(int n, int W, int64_t frames, int64_t Bpad,
+                                                     const uint32_t *__restrict__ in_t, uint32_t *__restrict__ out) {
+    __shared__ uint32_t tile[8][32][33];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int64_t f0 = (int64_t)blockIdx.x * 32;
+    const int jtiles = (W + 31) / 32;
+    for (int jt = blockIdx.y * 8 + wrp; jt < jtiles; jt += gridDim.y * 8) {
+        const int j0 = jt * 32;
+        const int64_t col = f0 + lane;
+        for (int t = 0; t < 32; ++t) {
+            const int j = j0 + t;
+            uint32_t v = 0;
+            if (j < W) {
+                if (BITREV)
+                    v = bitrev_gather_word([&](uint32_t wi) { return in_t[(int64_t)wi * Bpad + col]; }, n, (uint32_t)j);
+                else
+                    v = in_t[(int64_t)j * Bpad + col];
+            }
+            tile[wrp][lane][t] = v;
+        }
+        __syncwarp();
+        for (int r = 0; r < 32; ++r) {
+            const int64_t f = f0 + r;
+            if (f < frames && j0 + lane < W) out[f * W + j0 + lane] = tile[wrp][r][lane];
+        }
+        __syncwarp();
+    }
+}
+
+struct ScLayout {
+    int64_t chunk, Bpad;
+    size_t off_in, off_cw, off_info, off_vals, total;
+    int grid;
+};
+
+static int sc_grid_max() { return num_sms() * SC_BLOCKS_PER_SM; }
+
+static ScLayout sc_layout(const pc_plan *plan, int64_t chunk, int kind) {
+    ScLayout L;
+    const int64_t N = plan->N, Nw = (N + 31) / 32, Kw = (plan->k + 31) / 32 > 0 ? (plan->k + 31) / 32 : 1;
+    L.chunk = chunk;
+    L.Bpad = round_up(chunk, 32);
+    const int64_t blocks = (L.Bpad + SC_THREADS - 1) / SC_THREADS;
+    L.grid = (int)(blocks < sc_grid_max() ? blocks : sc_grid_max());
+    const int64_t gvals = N > (1 << (LS + 1)) ? N - (1 << (LS + 1)) : 0;
+    size_t o = 0;
+    L.off_in = o;
+    o += align256((size_t)N * L.Bpad * (kind == PC_INPUT_SYMBOLS ? 1 : 16));
+    L.off_cw = o;
+    o += align256((size_t)Nw * L.Bpad * 4);
+    L.off_info = o;
+    o += align256((size_t)Kw * L.Bpad * 4);
+    L.off_vals = o;
+    o += align256((size_t)L.grid * (SC_THREADS / 32) * gvals * 32 * 8 + 256);
+    L.total = o;
+    return L;
+}
+
+static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int64_t B, const double *h_table, int Y,
+                            uint32_t *d_cw, uint32_t *d_info, void *ws, size_t ws_bytes, cudaStream_t st) {
+    PC_REQUIRE(plan && plan->q == 2, "binary plan required");
+    PC_REQUIRE(plan->n <= SC_MAX_N, "block length too large for the frame-per-lane SC decoder");
+    PC_REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return PC_OK;
+    PC_REQUIRE(d_in && d_cw && (d_info || plan->k == 0) && ws, "null buffer");
+    PC_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+    if (kind == PC_INPUT_SYMBOLS) PC_REQUIRE(h_table && Y >= 1 && Y <= 16, "symbol table must have 1..16 rows");
+    // largest chunk (multiple of 32 frames) that fits the workspace
+    int64_t chunk = round_up(B, 32);
+    const int64_t cap = 1 << 17;
+    if (chunk > cap) chunk = cap;
+    while (chunk > 32 && sc_layout(plan, chunk, kind).total > ws_bytes) chunk = round_up(chunk / 2, 32);
+    ScLayout L = sc_layout(plan, chunk, kind);
+    if (L.total > ws_bytes) {
+        set_error("workspace too small: %zu bytes given, %zu needed for a 32-frame chunk", ws_bytes, L.total);
+        return PC_ERR_NOMEM;
+    }
+    const int N = plan->N, Nw = (N + 31) / 32, Kw = (plan->k + 31) / 32;
+    char *base = (char *)ws;
+    ScParams p{};
+    p.n = plan->n;
+    p.k = plan->k;
+    p.n_sched = (int)plan->sched.size();
+    p.Y = Y;
+    p.Bpad = L.Bpad;
+    p.sched = plan->d_sched;
+    p.r0_words = plan->d_r0_words;
+    p.in_t = base + L.off_in;
+    p.vals = (double *)(base + L.off_vals);
+    p.cw_t = (uint32_t *)(base + L.off_cw);
+    p.info_t = (uint32_t *)(base + L.off_info);
+    for (int i = 0; i < 32; ++i) p.table[i] = (kind == PC_INPUT_SYMBOLS && i < 2 * Y) ? h_table[i] : 0.0;
+    const size_t smem = (size_t)SMEM_VALS * SC_THREADS * sizeof(double);
+    if (kind == PC_INPUT_SYMBOLS)
+        PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<PC_INPUT_SYMBOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+        PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<PC_INPUT_PROBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t f0 = 0; f0 < B; f0 += chunk) {
+        const int64_t frames = (B - f0) < chunk ? (B - f0) : chunk;
+        const int64_t tiles = (frames + 31) / 32;
+        p.frames = frames;
+        const int ptiles = (N + 31) / 32;
+        dim3 ig((unsigned)tiles, (unsigned)(ptiles < 64 ? ptiles : 64));
+        if (kind == PC_INPUT_SYMBOLS) {
+            ingest_kernel<uint8_t><<<ig, 256, 0, st>>>(plan->n, frames, L.Bpad, (const uint8_t *)d_in + f0 * N,
+                                                       (uint8_t *)p.in_t, (uint8_t)0);
+        } else {
+            ingest_kernel<double2><<<ig, 256, 0, st>>>(plan->n, frames, L.Bpad, (const double2 *)d_in + f0 * N,
+                                                       (double2 *)p.in_t, make_double2(0.5, 0.5));
+        }
+        PC_LAUNCH_CHECK();
+        const int64_t blocks = (tiles * 32 + SC_THREADS - 1) / SC_THREADS;
+        const int grid = (int)(blocks < L.grid ? blocks : L.grid);
+        if (kind == PC_INPUT_SYMBOLS)
+            sc_decode_kernel<PC_INPUT_SYMBOLS><<<grid, SC_THREADS, smem, st>>>(p);
+        else
+            sc_decode_kernel<PC_INPUT_PROBS><<<grid, SC_THREADS, smem, st>>>(p);
+        PC_LAUNCH_CHECK();
+        const int jt_cw = (Nw + 255) / 256;
+        egress_kernel<true><<<dim3((unsigned)tiles, (unsigned)jt_cw), 256, 0, st>>>(plan->n, Nw, frames, L.Bpad, p.cw_t,
+                                                                                     d_cw + f0 * Nw);
+        PC_LAUNCH_CHECK();
+        if (Kw > 0) {
+            const int jt_i = (Kw + 255) / 256;
+            egress_kernel<false><<<dim3((unsigned)tiles, (unsigned)jt_i), 256, 0, st>>>(plan->n, Kw, frames, L.Bpad,
+                                                                                         p.info_t, d_info + f0 * Kw);
+            PC_LAUNCH_CHECK();
+        }
+    }
+    return PC_OK;
+}
+
+}  // namespace pc
+
+extern "C" {
+
+size_t pc_sc_workspace_bytes(const pc_plan *plan, int64_t B, int input_kind) {
+    if (!plan || B <= 0) return 256;
+    int64_t chunk = pc::round_up(B, 32);
+    if (chunk > (1 << 16)) chunk = 1 << 16;
+    return pc::sc_layout(plan, chunk, input_kind).total;
+}
+
+int pc_sc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint32_t *d_cw_packed, uint32_t *d_info_packed,
+                       void *d_workspace, size_t workspace_bytes, void *stream) {
+    return pc::sc_decode_common(plan, PC_INPUT_PROBS, d_xy, B, nullptr, 0, d_cw_packed, d_info_packed, d_workspace,
+                                workspace_bytes, (cudaStream_t)stream);
+}
+
+int pc_sc_decode_symbols(const pc_plan *plan, const uint8_t *d_y, int64_t B, const double *h_table, int Y,
+                         uint32_t *d_cw_packed, uint32_t *d_info_packed, void *d_workspace, size_t workspace_bytes,
+                         void *stream) {
+    return pc::sc_decode_common(plan, PC_INPUT_SYMBOLS, d_y, B, h_table, Y, d_cw_packed, d_info_packed, d_workspace,
+                                workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+"""Batched array entry points over the C-ABI (torch tensors own the device memory, nothing else).
+
+All functions launch on torch's current CUDA stream and return device tensors; packed bit tensors are
+int32 views of the uint32 words described in include/polarcub_b200.h (bit i -> word i//32, bit i%32).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+INPUT_SYMBOLS = 0
+INPUT_PROBS = 1
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
+
+
+def pack_bits(bits):
+    """[..., n] array of 0/1 -> uint32 [..., ceil(n/32)] (LSB first)."""
+    bits = np.ascontiguousarray(bits, dtype=np.uint8)
+    n = bits.shape[-1]
+    W = (n + 31) // 32
+    pad = W * 32 - n
+    if pad:
+        bits = np.concatenate([bits, np.zeros(bits.shape[:-1] + (pad,), dtype=np.uint8)], axis=-1)
+    by = np.packbits(bits, axis=-1, bitorder="little")
+    return np.ascontiguousarray(by).view("<u4").reshape(bits.shape[:-1] + (W,))
+
+
+def unpack_bits(words, n):
+    """uint32 [..., W] -> uint8 [..., n]."""
+    words = np.ascontiguousarray(words).view(np.uint32)
+    by = words.view(np.uint8).reshape(words.shape[:-1] + (words.shape[-1] * 4,))
+    return np.unpackbits(by, axis=-1, bitorder="little")[..., :n]
+
+
+class Plan:
+    """Immutable (q, N, frozen set, frozen values) plan bound to one CUDA device (pc_plan_create)."""
+
+    def __init__(self, q, n, frozen_mask, frozen_vals=None, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.PolarcubError("polarcub_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.q, self.n, self.N = int(q), int(n), 1 << int(n)
+        fm = np.ascontiguousarray(frozen_mask, dtype=np.uint8)
+        assert fm.shape == (self.N,)
+        fv = np.zeros(self.N, dtype=np.uint8) if frozen_vals is None else np.ascontiguousarray(frozen_vals, dtype=np.uint8)
+        assert fv.shape == (self.N,)
+        self.frozen_mask, self.frozen_vals = fm, fv
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._h = ctypes.c_void_p(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().pc_plan_create(self.q, self.n, fm.ctypes.data_as(ctypes.c_void_p),
+                                                 fv.ctypes.data_as(ctypes.c_void_p), ctypes.byref(self._h)),
+                       "pc_plan_create")
+        self.k = _lib.lib().pc_plan_k(self._h)
+        self.Nw = (self.N + 31) // 32
+        self.Kw = (self.k + 31) // 32
+        self._ws = None
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _lib.lib().pc_plan_destroy(self._h)
+            self._h = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def schedule_len(self):
+        return _lib.lib().pc_plan_schedule_len(self._h)
+
+    def workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+
+def encode_bits(plan, info_packed):
+    """info_packed int32 [B, Kw] (device) -> codewords int32 [B, Nw] (BinaryPolarEncoderDecoder.encode, uniform prior)."""
+    B = info_packed.shape[0]
+    assert info_packed.is_cuda and info_packed.dtype == torch.int32 and info_packed.is_contiguous()
+    assert info_packed.shape[1] == plan.Kw
+    cw = torch.empty((B, plan.Nw), dtype=torch.int32, device=info_packed.device)
+    _lib.check(_lib.lib().pc_encode_bits(plan._h, _ptr(info_packed), _ptr(cw), B, _stream()), "pc_encode_bits")
+    return cw
+
+
+def polar_transform_bits(n, cw_packed):
+    """x -> u (polarTransformOfBits) on packed words."""
+    B = cw_packed.shape[0]
+    assert cw_packed.is_cuda and cw_packed.dtype == torch.int32 and cw_packed.is_contiguous()
+    u = torch.empty_like(cw_packed)
+    _lib.check(_lib.lib().pc_polar_transform_bits(int(n), _ptr(cw_packed), _ptr(u), B, _stream()),
+               "pc_polar_transform_bits")
+    return u
+
+
+def sc_decode_probs(plan, xy, out=None):
+    """xy float64 [B, N, 2] (device) -> (cw_packed int32 [B, Nw], info_packed int32 [B, Kw])."""
+    assert xy.is_cuda and xy.dtype == torch.float64 and xy.is_contiguous() and xy.shape[1:] == (plan.N, 2)
+    B = xy.shape[0]
+    cw, info = out if out is not None else (torch.empty((B, plan.Nw), dtype=torch.int32, device=xy.device),
+                                            torch.empty((B, max(plan.Kw, 1)), dtype=torch.int32, device=xy.device))
+    need = _lib.lib().pc_sc_workspace_bytes(plan._h, B, INPUT_PROBS)
+    ws = plan.workspace(need)
+    _lib.check(_lib.lib().pc_sc_decode_probs(plan._h, _ptr(xy), B, _ptr(cw), _ptr(info), _ptr(ws), ws.numel(),
+                                             _stream()), "pc_sc_decode_probs")
+    return cw, info[:, :plan.Kw]
+
+
+def sc_decode_symbols(plan, y, table, out=None):
+    """y uint8 [B, N] channel output symbols (device), table float64 [Y, 2] joint probabilities (host)."""
+    assert y.is_cuda and y.dtype == torch.uint8 and y.is_contiguous() and y.shape[1] == plan.N
+    table = np.ascontiguousarray(table, dtype=np.float64)
+    assert table.ndim == 2 and table.shape[1] == 2 and 1 <= table.shape[0] <= 16
+    B = y.shape[0]
+    cw, info = out if out is not None else (torch.empty((B, plan.Nw), dtype=torch.int32, device=y.device),
+                                            torch.empty((B, max(plan.Kw, 1)), dtype=torch.int32, device=y.device))
+    need = _lib.lib().pc_sc_workspace_bytes(plan._h, B, INPUT_SYMBOLS)
+    ws = plan.workspace(need)
+    _lib.check(_lib.lib().pc_sc_decode_symbols(plan._h, _ptr(y), B, table.ctypes.data_as(ctypes.c_void_p),
+                                               table.shape[0], _ptr(cw), _ptr(info), _ptr(ws), ws.numel(), _stream()),
+               "pc_sc_decode_symbols")
+    return cw, info[:, :plan.Kw]
+
+
+def qsc_encode(plan, info):
+    """info uint8 [B, k] (device) -> codeword symbols uint8 [B, N] (QaryPolarEncoderDecoder.encode)."""
+    assert info.is_cuda and info.dtype == torch.uint8 and info.is_contiguous() and info.shape[1] == plan.k
+    B = info.shape[0]
+    cw = torch.empty((B, plan.N), dtype=torch.uint8, device=info.device)
+    _lib.check(_lib.lib().pc_qsc_encode(plan._h, _ptr(info), _ptr(cw), B, _stream()), "pc_qsc_encode")
+    return cw
+
+
+def qsc_decode_probs(plan, xy):
+    """xy float64 [B, N, q] (device) -> (cw uint8 [B, N], info uint8 [B, k])."""
+    assert xy.is_cuda and xy.dtype == torch.float64 and xy.is_contiguous() and xy.shape[1:] == (plan.N, plan.q)
+    B = xy.shape[0]
+    cw = torch.empty((B, plan.N), dtype=torch.uint8, device=xy.device)
+    info = torch.empty((B, max(plan.k, 1)), dtype=torch.uint8, device=xy.device)
+    need = _lib.lib().pc_qsc_workspace_bytes(plan._h, B)
+    ws = plan.workspace(need)
+    _lib.check(_lib.lib().pc_qsc_decode_probs(plan._h, _ptr(xy), B, _ptr(cw), _ptr(info), _ptr(ws), ws.numel(),
+                                              _stream()), "pc_qsc_decode_probs")
+    return cw, info[:, :plan.k]
+
+
+def kernel_launch_count():
+    return int(_lib.lib().pc_kernel_launch_count())
