@@ -103,6 +103,17 @@ size_t pc_qsc_workspace_bytes(const pc_plan *plan, int64_t B);
 int pc_qsc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint8_t *d_cw, uint8_t *d_info,
                         void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---- Monte-Carlo counters and measurement hooks ---------------------------------------------------- */
+/* d_out3[0..2] += {B, frames whose first nbits differ, differing bits} over packed rows of ceil(nbits/32) words.
+ * Replaces the serial comparison loop BinaryPolarEncoderDecoder.py:374-385 / QaryPolarEncoderDecoder.py:907-909;
+ * the caller all-reduces the three counters across ranks (NCCL). */
+int pc_count_errors(const uint32_t *d_a, const uint32_t *d_b, int64_t B, int nbits, unsigned long long *d_out3,
+                    void *stream);
+/* When enabled, the library records CUDA events on the launching stream around every launch of the dominant
+ * decode kernel; pc_profile_read returns their summed duration (ms) and the number of launches. */
+int pc_profile_enable(int on);
+int pc_profile_read(double *total_ms, unsigned long long *launches);
+
 #ifdef __cplusplus
 }
 #endif

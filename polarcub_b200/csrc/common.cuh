@@ -46,6 +46,7 @@ static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * 
 static inline size_t align256(size_t a) { return (a + 255) & ~(size_t)255; }
 
 int num_sms();  // SM count of the current device (cached)
+void prof_mark(cudaStream_t st);  // bench.py timing hook: call before and after the dominant kernel launch
 
 // ---- schedule of the SC tree walk -------------------------------------------------------------------
 // The decoder never recurses: the host flattens the tree walk of

@@ -137,7 +137,7 @@ extern "C" {
 
 int pc_encode_bits(const pc_plan *plan, const uint32_t *d_info_packed, uint32_t *d_cw_packed, int64_t B, void *stream) {
     PC_REQUIRE(plan && plan->q == 2, "binary plan required");
-    PC_REQUIRE(B >= 0 && d_cw_packed && (d_info_packed || plan->k == 0 || B == 0), "null buffer");
+    PC_REQUIRE(B >= 0 && (d_cw_packed || B == 0) && (d_info_packed || plan->k == 0 || B == 0), "null buffer");
     return pc::launch_bits(pc::SRC_INFO, plan->n, plan->k, B, d_info_packed, plan->d_src, plan->d_frozen_words,
                            d_cw_packed, (cudaStream_t)stream);
 }

@@ -395,10 +395,12 @@ static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int
         PC_LAUNCH_CHECK();
         const int64_t blocks = (tiles * 32 + SC_THREADS - 1) / SC_THREADS;
         const int grid = (int)(blocks < L.grid ? blocks : L.grid);
+        prof_mark(st);
         if (kind == PC_INPUT_SYMBOLS)
             sc_decode_kernel<PC_INPUT_SYMBOLS><<<grid, SC_THREADS, smem, st>>>(p);
         else
             sc_decode_kernel<PC_INPUT_PROBS><<<grid, SC_THREADS, smem, st>>>(p);
+        prof_mark(st);
         PC_LAUNCH_CHECK();
         const int jt_cw = (Nw + 255) / 256;
         egress_kernel<true><<<dim3((unsigned)tiles, (unsigned)jt_cw), 256, 0, st>>>(plan->n, Nw, frames, L.Bpad, p.cw_t,

@@ -159,3 +159,24 @@ def qsc_decode_probs(plan, xy):
 
 def kernel_launch_count():
     return int(_lib.lib().pc_kernel_launch_count())
+
+
+def count_errors(a_packed, b_packed, nbits, out=None):
+    """Accumulate {frames, frame errors, bit errors} (int64[3], device) over two packed-bit tensors."""
+    assert a_packed.shape == b_packed.shape and a_packed.is_cuda and b_packed.is_cuda
+    assert a_packed.is_contiguous() and b_packed.is_contiguous()
+    if out is None:
+        out = torch.zeros(3, dtype=torch.int64, device=a_packed.device)
+    _lib.check(_lib.lib().pc_count_errors(_ptr(a_packed), _ptr(b_packed), a_packed.shape[0], int(nbits), _ptr(out),
+                                          _stream()), "pc_count_errors")
+    return out
+
+
+def profile_enable(on=True):
+    _lib.check(_lib.lib().pc_profile_enable(1 if on else 0), "pc_profile_enable")
+
+
+def profile_read():
+    ms, cnt = ctypes.c_double(0), ctypes.c_ulonglong(0)
+    _lib.check(_lib.lib().pc_profile_read(ctypes.byref(ms), ctypes.byref(cnt)), "pc_profile_read")
+    return ms.value, cnt.value
