@@ -118,6 +118,45 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
             gv[(int64_t)(((1 << lev) - (1 << (LS + 1))) + h) * 32] = v;
     };
 
+    // one tree level, UNR elements per batch: every load of the batch is issued before the first division
+    constexpr int UNR = 4;
+    auto f_level = [&](int lev) {
+        const int size = 1 << lev;
+        if (size >= UNR) {
+            for (int h0 = 0; h0 < size; h0 += UNR) {
+                double a[UNR], b[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    a[u] = ld(lev + 1, h0 + u);
+                    b[u] = ld(lev + 1, h0 + u + size);
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) st(lev, h0 + u, f_packed(a[u], b[u]));
+            }
+        } else {
+            for (int h = 0; h < size; ++h) st(lev, h, f_packed(ld(lev + 1, h), ld(lev + 1, h + size)));
+        }
+    };
+    // elements [h0, h0+cnt) of level lev, decision bits in `ub` starting at bit 0 for element h0
+    auto g_level = [&](int lev, int h0, int cnt, uint32_t ub) {
+        const int size = 1 << lev;
+        if (cnt >= UNR) {
+            for (int hh = 0; hh < cnt; hh += UNR) {
+                double a[UNR], b[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    a[u] = ld(lev + 1, h0 + hh + u);
+                    b[u] = ld(lev + 1, h0 + hh + u + size);
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) st(lev, h0 + hh + u, g_packed(a[u], b[u], (ub >> (hh + u)) & 1u));
+            }
+        } else {
+            for (int hh = 0; hh < cnt; ++hh)
+                st(lev, h0 + hh, g_packed(ld(lev + 1, h0 + hh), ld(lev + 1, h0 + hh + size), (ub >> hh) & 1u));
+        }
+    };
+
     for (int64_t grp = warp_global; grp < groups; grp += warps_total) {
         const int64_t col = grp * 32 + lane;  // always < Bpad; columns >= frames hold padding
         auto root = [&](int h, double &v0, double &v1) {
@@ -171,9 +210,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                             st(top, h, g_raw(a0, a1, b0, b1, (ub >> h) & 1u));
                         }
                     } else {
-#pragma unroll 2
-                        for (int h = 0; h < size; ++h)
-                            st(top, h, g_packed(ld(top + 1, h), ld(top + 1, h + size), (ub >> h) & 1u));
+                        g_level(top, 0, size, ub);
                     }
                 } else {
                     const uint32_t *uw = xw + (int64_t)((i - size) >> 5) * p.Bpad;
@@ -188,11 +225,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                                 st(top, h, g_raw(a0, a1, b0, b1, (ub >> b) & 1u));
                             }
                         } else {
-#pragma unroll 2
-                            for (int b = 0; b < 32; ++b) {
-                                const int h = 32 * w + b;
-                                st(top, h, g_packed(ld(top + 1, h), ld(top + 1, h + size), (ub >> b) & 1u));
-                            }
+                            g_level(top, 32 * w, 32, ub);
                         }
                     }
                 }
@@ -211,8 +244,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                         st(lev, h, f_raw(a0, a1, b0, b1));
                     }
                 } else {
-#pragma unroll 2
-                    for (int h = 0; h < size; ++h) st(lev, h, f_packed(ld(lev + 1, h), ld(lev + 1, h + size)));
+                    f_level(lev);
                 }
             }
             // ---- the node itself -----------------------------------------------------------------------
@@ -340,6 +372,16 @@ static ScLayout sc_layout(const pc_plan *plan, int64_t chunk, int kind) {
     return L;
 }
 
+// Frames per launch: a whole multiple of the resident lane count (so every persistent warp walks the same
+// number of 32-frame groups), capped so that the transposed input stays around 1-4 GiB.
+static int64_t sc_pick_chunk(int64_t B, int kind) {
+    const int64_t wave = (int64_t)sc_grid_max() * SC_THREADS;
+    const int64_t cap = kind == PC_INPUT_SYMBOLS ? (1 << 20) : (1 << 18);
+    int64_t chunk = round_up(B, 32);
+    if (chunk > cap + cap / 2) chunk = cap >= wave ? cap / wave * wave : cap;  // up to 1.5 cap goes in one launch
+    return chunk;
+}
+
 static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int64_t B, const double *h_table, int Y,
                             uint32_t *d_cw, uint32_t *d_info, void *ws, size_t ws_bytes, cudaStream_t st) {
     PC_REQUIRE(plan && plan->q == 2, "binary plan required");
@@ -350,9 +392,7 @@ static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int
     PC_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
     if (kind == PC_INPUT_SYMBOLS) PC_REQUIRE(h_table && Y >= 1 && Y <= 16, "symbol table must have 1..16 rows");
     // largest chunk (multiple of 32 frames) that fits the workspace
-    int64_t chunk = round_up(B, 32);
-    const int64_t cap = 1 << 17;
-    if (chunk > cap) chunk = cap;
+    int64_t chunk = sc_pick_chunk(B, kind);
     while (chunk > 32 && sc_layout(plan, chunk, kind).total > ws_bytes) chunk = round_up(chunk / 2, 32);
     ScLayout L = sc_layout(plan, chunk, kind);
     if (L.total > ws_bytes) {
@@ -422,9 +462,7 @@ extern "C" {
 
 size_t pc_sc_workspace_bytes(const pc_plan *plan, int64_t B, int input_kind) {
     if (!plan || B <= 0) return 256;
-    int64_t chunk = pc::round_up(B, 32);
-    if (chunk > (1 << 16)) chunk = 1 << 16;
-    return pc::sc_layout(plan, chunk, input_kind).total;
+    return pc::sc_layout(plan, pc::sc_pick_chunk(B, input_kind), input_kind).total;
 }
 
 int pc_sc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint32_t *d_cw_packed, uint32_t *d_info_packed,
