@@ -177,3 +177,38 @@ def polar_transform_qudits(q, x):
     rc = lib().po_polar_transform_qudits(ctypes.c_int(q), ctypes.c_int(x.shape[0]), _p(x, _i64p), _p(u, _i64p))
     assert rc == 0, rc
     return u
+
+
+# ---------------------------------------------------------------------------------------------------
+def list_decode(q, N, L, fmask, xyprobs, frozen_values, actual_info, want_list=False):
+    """QaryPolarEncoderDecoder.listDecode with actualInformation (genie selection).
+    Returns (information[k], ProbResult value) and, with want_list, (list_size, list_info[L,k], list_prob[L], actual_prob)."""
+    fmask, xyprobs = _c(fmask, np.uint8), _c(xyprobs, np.float64)
+    fv, ai = _c(frozen_values, np.int64), _c(actual_info, np.int64)
+    k = int(N - fmask.sum())
+    info = np.empty(k, dtype=np.int64)
+    pr = ctypes.c_int(-1)
+    ls = ctypes.c_int(0)
+    linfo = np.full((L, k), -1, dtype=np.int64)
+    lprob = np.zeros(L, dtype=np.float64)
+    ap = ctypes.c_double(0)
+    rc = lib().po_list_decode(ctypes.c_int(q), ctypes.c_int(N), ctypes.c_int(L), _p(fmask, _u8p), _p(xyprobs, _f64p),
+                              _p(fv, _i64p), _p(ai, _i64p), _p(info, _i64p), ctypes.byref(pr), ctypes.byref(ls),
+                              _p(linfo, _i64p), _p(lprob, _f64p), ctypes.byref(ap))
+    assert rc == 0, rc
+    if want_list:
+        return info, pr.value, ls.value, linfo, lprob, ap.value
+    return info, pr.value
+
+
+def list_decode_batch(q, N, L, fmask, xyprobs, frozen_values, actual_info):
+    fmask, xyprobs = _c(fmask, np.uint8), _c(xyprobs, np.float64)
+    fv, ai = _c(frozen_values, np.int64), _c(actual_info, np.int64)
+    B = xyprobs.shape[0]
+    k = int(N - fmask.sum())
+    info = np.empty((B, k), dtype=np.int64)
+    pr = np.empty(B, dtype=np.int32)
+    rc = lib().po_list_decode_batch(ctypes.c_int(B), ctypes.c_int(q), ctypes.c_int(N), ctypes.c_int(L), _p(fmask, _u8p),
+                                    _p(xyprobs, _f64p), _p(fv, _i64p), _p(ai, _i64p), _p(info, _i64p), _p(pr, _i32p))
+    assert rc == 0, rc
+    return info, pr
