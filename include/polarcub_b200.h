@@ -103,6 +103,20 @@ size_t pc_qsc_workspace_bytes(const pc_plan *plan, int64_t B);
 int pc_qsc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint8_t *d_cw, uint8_t *d_info,
                         void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---- SC-list decoding (any q in {2,3,4,5}; binary SCL is q = 2) --------------------------------------- */
+/* QaryPolarEncoderDecoder.listDecode with actualInformation (genie selection, the form ir() uses,
+ * QaryPolarEncoderDecoder.py:856).  d_xy [B][N][q] float64 (linear domain); d_frozen_values [B][N-k] uint8 (the
+ * explicit frozen values, consumed in u order like frozenValuesIterator); d_actual_info [B][k] uint8.
+ * Outputs: d_info [B][k] uint8 (the word listDecode returns) and d_prob_result [B] int32 (ProbResult value,
+ * QaryPolarEncoderDecoder.py:18-24).  Optional (all null, or the first three non-null): the final list --
+ * d_list_size [B] int32, d_list_prob [B][L] float64 (normalised metrics, list order), d_actual_prob [B] float64,
+ * d_list_info [B][L][k] uint8 (may be null on its own).  1 <= L <= 32 (q <= 3) or L <= 8 (q = 4, 5); N >= 2. */
+size_t pc_scl_workspace_bytes(const pc_plan *plan, int L, int64_t B, int want_list);
+int pc_scl_decode_probs(const pc_plan *plan, int L, const double *d_xy, const uint8_t *d_frozen_values,
+                        const uint8_t *d_actual_info, int64_t B, uint8_t *d_info, int32_t *d_prob_result,
+                        int32_t *d_list_size, double *d_list_prob, double *d_actual_prob, uint8_t *d_list_info,
+                        void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* ---- Monte-Carlo counters and measurement hooks ---------------------------------------------------- */
 /* d_out3[0..2] += {B, frames whose first nbits differ, differing bits} over packed rows of ceil(nbits/32) words.
  * Replaces the serial comparison loop BinaryPolarEncoderDecoder.py:374-385 / QaryPolarEncoderDecoder.py:907-909;

@@ -96,6 +96,79 @@ class QaryPolarEncoderDecoder:
         return self.decode_batch(xy)[0]
 
 
+    # ---- SC-list decoding --------------------------------------------------------------------------
+    def listDecode_batch(self, xyProbs, frozenValues, maxListSize, actualInformation, return_list=False):
+        """Batched listDecode with genie selection.  xyProbs [B,N,q] float64, frozenValues [B,N-k],
+        actualInformation [B,k].  Returns (information int64 [B,k], ProbResult values int32 [B]) and, with
+        return_list, a dict with the final list (sizes, normalised metrics, genie metric, per-path information)."""
+        self._require_linear()
+        dev = self.plan.device
+        xy = xyProbs if torch.is_tensor(xyProbs) else torch.from_numpy(np.ascontiguousarray(xyProbs, dtype=np.float64))
+        B = xy.shape[0]
+        fv = torch.from_numpy(np.ascontiguousarray(frozenValues, dtype=np.uint8).reshape(B, self.length - self.k))
+        ai = torch.from_numpy(np.ascontiguousarray(actualInformation, dtype=np.uint8).reshape(B, self.k))
+        out = engine.scl_decode_probs(self.plan, int(maxListSize), xy.to(dev).contiguous(), fv.to(dev).contiguous(),
+                                      ai.to(dev).contiguous(), want_list=return_list, want_list_info=return_list)
+        info = out["info"].cpu().numpy().astype(np.int64)
+        res = out["prob_result"].cpu().numpy()
+        if not return_list:
+            return info, res
+        lst = {"list_size": out["list_size"].cpu().numpy(), "list_prob": out["list_prob"].cpu().numpy(),
+               "actual_prob": out["actual_prob"].cpu().numpy(),
+               "list_info": out["list_info"].cpu().numpy().astype(np.int64)}
+        return info, res, lst
+
+    def listDecode(self, xyVectorDistribution, frozenValues, maxListSize, check_matrix, check_value,
+                   actualInformation=None, verbosity=0):
+        """QaryPolarEncoderDecoder.py:118-227 -> (information int64 [k], ProbResult or None).
+
+        With actualInformation (the form ir() uses, :856) the genie selection of :172-213 applies.  Without it the
+        reference crashes inside the fast nodes (:569, :608 index self.actualInformation), so that form is not
+        reproduced; the first list entry passing `info @ check_matrix % q == check_value` (:215-227) is selected
+        from the final list instead, with a dummy genie path."""
+        assert len(xyVectorDistribution) == self.length
+        xy = _probs_of(xyVectorDistribution, self.length, self.q).reshape(1, self.length, self.q)
+        fv = np.asarray(frozenValues, dtype=np.int64).reshape(1, -1)
+        if actualInformation is not None:
+            info, res = self.listDecode_batch(xy, fv, maxListSize, np.asarray(actualInformation).reshape(1, self.k))
+            return info[0], ProbResult(int(res[0]))
+        _, _, lst = self.listDecode_batch(xy, fv, maxListSize, np.zeros((1, self.k), dtype=np.int64), return_list=True)
+        cands = lst["list_info"][0][:int(lst["list_size"][0])]
+        cm, cv = np.asarray(check_matrix), np.asarray(check_value)
+        for row in cands:
+            if np.array_equal(np.matmul(row, cm) % self.q, cv):
+                return row, None
+        return cands[0], None
+
+    def calculate_syndrome_and_complement(self, u_message):  # QaryPolarEncoderDecoder.py:822-833
+        y = np.asarray(polarTransformOfQudits(self.q, u_message), dtype=np.int64).copy()
+        w = np.copy(y)
+        w[list(self.infoSet)] = 0
+        w[list(self.frozenSet)] *= self.q - 1
+        w[list(self.frozenSet)] %= self.q
+        u = y
+        u[list(self.frozenSet)] = 0
+        return w, u
+
+    def get_message_info_bits(self, u_message):
+        return u_message[list(self.infoSet)]
+
+    def get_message_frozen_bits(self, u_message):
+        return u_message[list(self.frozenSet)]
+
+    def ir(self, a, b, make_xyVectorDistribution, list_size=1, check_size=0, verbosity=0):
+        """Information reconciliation wrapper, QaryPolarEncoderDecoder.py:841-858."""
+        w, u = self.calculate_syndrome_and_complement(a)
+        a_key = self.get_message_info_bits(u)
+        frozen_values = (self.get_message_frozen_bits(w) * (self.q - 1)) % self.q
+        check_matrix = np.random.choice(range(self.q), (self.k, check_size))
+        check_value = np.matmul(a_key, check_matrix) % self.q
+        b_key, prob_result = self.listDecode(make_xyVectorDistribution(b), frozenValues=frozen_values,
+                                             maxListSize=list_size, check_matrix=check_matrix, check_value=check_value,
+                                             actualInformation=a_key, verbosity=verbosity)
+        return a_key, b_key, prob_result
+
+
 def polarTransformOfQudits(q, xvec):
     """QaryPolarEncoderDecoder.py:1136-1154 (x -> u).  Integer butterfly; computed with numpy on the host
     because callers use it on single short vectors (the batched inverse lives in the encoder kernel)."""

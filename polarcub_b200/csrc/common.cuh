@@ -9,6 +9,8 @@
 
 #include "../../include/polarcub_b200.h"
 
+struct pc_plan;
+
 namespace pc {
 
 // ---- error plumbing (no exceptions cross the C-ABI) ------------------------------------------------
@@ -62,6 +64,8 @@ struct SchedEntry {
     int8_t pad;
     uint32_t bits;  // rate-0, l < 5: the node codeword (natural order) in the low 2^l bits; l >= 5: word offset into r0_words
 };
+
+void scl_tables_release(const pc_plan *p);
 
 }  // namespace pc
 

@@ -157,6 +157,41 @@ def qsc_decode_probs(plan, xy):
     return cw, info[:, :plan.k]
 
 
+def scl_decode_probs(plan, L, xy, frozen_values, actual_info, want_list=False, want_list_info=False):
+    """SC-list decoding (QaryPolarEncoderDecoder.listDecode with genie selection) of a batch.
+
+    xy float64 [B, N, q]; frozen_values uint8 [B, N-k]; actual_info uint8 [B, k] (all on the device).
+    Returns dict(info uint8 [B,k], prob_result int32 [B]) plus, with want_list, list_size int32 [B],
+    list_prob float64 [B,L], actual_prob float64 [B] and (want_list_info) list_info uint8 [B,L,k]."""
+    assert xy.is_cuda and xy.dtype == torch.float64 and xy.is_contiguous() and xy.shape[1:] == (plan.N, plan.q)
+    B = xy.shape[0]
+    dev = xy.device
+    nf = plan.N - plan.k
+    assert frozen_values.dtype == torch.uint8 and frozen_values.shape == (B, nf) and frozen_values.is_contiguous()
+    assert actual_info.dtype == torch.uint8 and actual_info.shape == (B, plan.k) and actual_info.is_contiguous()
+    info = torch.empty((B, max(plan.k, 1)), dtype=torch.uint8, device=dev)
+    res = torch.empty((B,), dtype=torch.int32, device=dev)
+    ls = lp = ap = li = None
+    if want_list or want_list_info:
+        want_list = True
+        ls = torch.empty((B,), dtype=torch.int32, device=dev)
+        lp = torch.empty((B, L), dtype=torch.float64, device=dev)
+        ap = torch.empty((B,), dtype=torch.float64, device=dev)
+        if want_list_info:
+            li = torch.empty((B, L, max(plan.k, 1)), dtype=torch.uint8, device=dev)
+    need = _lib.lib().pc_scl_workspace_bytes(plan._h, int(L), B, 1 if want_list else 0)
+    ws = plan.workspace(need)
+    _lib.check(_lib.lib().pc_scl_decode_probs(plan._h, int(L), _ptr(xy), _ptr(frozen_values), _ptr(actual_info), B,
+                                              _ptr(info), _ptr(res), _ptr(ls), _ptr(lp), _ptr(ap), _ptr(li), _ptr(ws),
+                                              ws.numel(), _stream()), "pc_scl_decode_probs")
+    out = {"info": info[:, :plan.k], "prob_result": res}
+    if want_list:
+        out.update(list_size=ls, list_prob=lp, actual_prob=ap)
+        if want_list_info:
+            out["list_info"] = li[:, :, :plan.k]
+    return out
+
+
 def kernel_launch_count():
     return int(_lib.lib().pc_kernel_launch_count())
 
