@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- decoded info Gbit/s of the batched polar decoders on B200 (contract: see DESIGN.md "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sc1024|scl4096|qsc2048] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload scl4096|sc1024|qsc2048] [--impl ours|reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one pass of the decode hot path over one batch of synthetic channel outputs (frames are
 independent, so every rank decodes its own slice: weak scaling, no data-path collective; one NCCL
 all-reduce of the int64[3] error counters after the timed region).  Rank 0 prints ONE JSON line.
 
+Default workload = BASELINE.json configs[1]: binary SCL L=8, N=4096, R=1/2 over BI-AWGN (Eb/N0 = 2 dB).
+`--workload sc1024` is configs[0] (binary SC N=1024 K=512 over BSC(0.11)), `--workload qsc2048` configs[2].
+The default line also carries a short `secondary` object with the SC N=1024 device-resident throughput, since
+BASELINE.json's metric names both decoders.
+
   value     whole-job decoded information Gbit/s, inputs resident in HBM, CUDA events, max over ranks
-  e2e       same metric through the public batched API with HOST (pinned) buffers: H2D of the channel outputs
-            and D2H of the decoded words inside the timed region
+  e2e       same metric through the batched C-ABI call with HOST (pinned) buffers: H2D of the channel
+            probabilities / symbols and D2H of the decoded words inside the timed region
   roofline  dominant kernel (the SC/SCL decode kernel): algorithmic bytes per launch / its CUDA-event duration
-  cpu_baseline  the oracle port (oracle/polar_oracle.c, the reference's algorithm restated in C) on the host cores
+  cpu_baseline  the oracle port (oracle/polar_oracle*.c, the reference's algorithm restated in C) on the host cores
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -29,17 +35,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 P_BSC = 0.11
+EBN0_DB = 2.0
+P_QSC = 0.02
 
 
 def bsc_table(p=P_BSC):
     return np.array([[0.5 * (1 - p), 0.5 * p], [0.5 * p, 0.5 * (1 - p)]])  # makeBSC, BinaryMemorylessDistribution.py:485-490
 
 
-def c1_code():
-    """C1: N=1024, K=512, frozen set = 512 worst indices by Tal-Vardy Pe (reference degrade pass, L=100)."""
-    from polarcub_b200.construction import frozen_set_from_pe, load_pe
-    pe = load_pe("bsc_p0.11_n10_L100_pe.npy")
-    return 1024, 512, frozen_set_from_pe(pe, 512)
+def awgn_sigma(rate=0.5, ebn0_db=EBN0_DB):
+    return math.sqrt(1.0 / (2.0 * rate * 10.0 ** (ebn0_db / 10.0)))
+
+
+def common_randomness(N, seed):
+    import random as _random
+    rng = _random.Random()
+    rng.seed(seed)  # BinaryPolarEncoderDecoder.py:36-41
+    return np.array([rng.random() for _ in range(N)])
+
+
+def mask_of(N, fs):
+    fm = np.zeros(N, dtype=np.uint8)
+    fm[list(fs)] = 1
+    return fm
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -91,7 +109,8 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            out["sm_mhz"] = float(np.median(sm))
+            busy = [s for s in sm if s > 0]
+            out["sm_mhz"] = float(np.median(busy or sm))
             out["sm_max_mhz"] = float(max(mx))
             out["samples"] = len(sm)
         out["reasons"] = sorted(reasons)
@@ -106,111 +125,414 @@ def measured_peak_hbm():
         return 6650.0, "fallback"
 
 
-# ---------------------------------------------------------------------------------------------------
-def cpu_decode_sample(N, fm, r, xy_tab_idx, table, threads):
-    """Time the oracle port on `threads` host threads over a sample of frames (symbols -> table lookup -> decode)."""
-    import oracle
-    B = xy_tab_idx.shape[0]
-    xp = np.full((N, 2), 0.5)
-    parts = np.array_split(np.arange(B), threads)
-
-    def work(idx):
-        if len(idx) == 0:
-            return 0
-        xy = table[xy_tab_idx[idx]]  # makeBinaryMemorylessVectorDistribution, BinaryMemorylessDistribution.py:245-258
-        oracle.bin_decode_batch(N, fm, r, xp, xy)
-        return len(idx)
-
-    oracle.lib()
+def run_threads(work, parts, threads):
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
         done = sum(ex.map(work, parts))
-    dt = time.perf_counter() - t0
-    return done, dt
+    return done, time.perf_counter() - t0
 
 
+# ---------------------------------------------------------------------------------------------------
+# Workloads.  Each one owns: the code (N, K, frozen set), device-side synthetic inputs keyed by the GLOBAL frame
+# index (results do not depend on the rank count), the timed step, the e2e step and the CPU (oracle) leg.
+# ---------------------------------------------------------------------------------------------------
+class ScBinary1024:
+    """C1: binary SC, N=1024, K=512, BSC(0.11); frozen set = 512 worst indices by Tal-Vardy Pe (reference degrade pass)."""
+    name = "sc_n1024_k512_bsc0.11"
+    kernel = "sc_decode_kernel<symbols>"
+    dtype = "f64"
+    default_frames, default_e2e, default_cpu = 1 << 20, 1 << 18, 1 << 16
+    N, K, n = 1024, 512, 10
+    alg_bytes_frame = 4288  # SURVEY.md 8(d): 4 N bytes of soft input + (N + K)/8 bytes out
+    info_bits = 512
+
+    def code(self):
+        from polarcub_b200.construction import frozen_set_from_pe, load_pe
+        fs = frozen_set_from_pe(load_pe("bsc_p0.11_n10_L100_pe.npy"), self.K)
+        self.fm = mask_of(self.N, fs)
+        self.r = common_randomness(self.N, 1)
+        self.fv = np.where(0.5 >= self.r, 0, 1).astype(np.uint8)
+        self.tab = bsc_table()
+        self.construction = "Tal-Vardy degrade L=100 via the live reference (tests/golden/constructions/bsc_p0.11_n10_L100_pe.npy)"
+
+    def setup(self, dev, rank, B, Be):
+        import torch
+        from polarcub_b200 import engine
+        self.engine, self.torch = engine, torch
+        self.code()
+        N = self.N
+        self.plan = plan = engine.Plan(2, self.n, self.fm, self.fv, device=dev)
+        gen = torch.Generator(device=dev)
+        self.y = torch.empty((B, N), dtype=torch.uint8, device=dev)
+        self.info_tx = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
+        shifts = torch.arange(32, device=dev, dtype=torch.int32)
+        CH = 1 << 16
+        for c0 in range(0, B, CH):
+            c1 = min(B, c0 + CH)
+            gen.manual_seed(1234 + 7919 * ((rank * B + c0) // CH))
+            it = torch.randint(-2 ** 31, 2 ** 31 - 1, (c1 - c0, plan.Kw), dtype=torch.int64, device=dev, generator=gen).to(torch.int32)
+            self.info_tx[c0:c1] = it
+            cwp = engine.encode_bits(plan, it.contiguous())
+            bits = ((cwp.unsqueeze(-1) >> shifts) & 1).reshape(c1 - c0, N).to(torch.uint8)
+            flips = (torch.rand((c1 - c0, N), device=dev, generator=gen) < P_BSC).to(torch.uint8)
+            self.y[c0:c1] = bits ^ flips
+            del it, cwp, bits, flips
+        self.cw_out = torch.empty((B, plan.Nw), dtype=torch.int32, device=dev)
+        self.info_out = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
+        self.Be = Be
+        self.y_host = torch.empty((Be, N), dtype=torch.uint8).pin_memory()
+        self.y_host.copy_(self.y[:Be])
+        self.cw_host = torch.empty((Be, plan.Nw), dtype=torch.int32).pin_memory()
+        self.info_host = torch.empty((Be, plan.Kw), dtype=torch.int32).pin_memory()
+        self.y_e = torch.empty((Be, N), dtype=torch.uint8, device=dev)
+        self.h2d = int(Be * N)
+        self.d2h = int(Be * (plan.Nw + plan.Kw) * 4)
+        self.input_note = "uint8 channel symbols [B,N] (%.2f GiB per step per GPU, larger than L2: no flush needed)" % (B * N / 2 ** 30)
+
+    def step(self):
+        self.engine.sc_decode_symbols(self.plan, self.y, self.tab, out=(self.cw_out, self.info_out))
+
+    def e2e_step(self):
+        Be = self.Be
+        self.y_e.copy_(self.y_host, non_blocking=True)
+        c, i = self.engine.sc_decode_symbols(self.plan, self.y_e, self.tab, out=(self.cw_out[:Be], self.info_out[:Be]))
+        self.cw_host.copy_(c, non_blocking=True)
+        self.info_host.copy_(i, non_blocking=True)
+
+    def counters(self):
+        return self.engine.count_errors(self.info_out, self.info_tx, self.K)
+
+    # ---- CPU leg (oracle port) ----
+    def cpu_inputs_from_gpu(self, sample):
+        return self.y[:sample].cpu().numpy()
+
+    def cpu_inputs_synth(self, frames):
+        import oracle
+        self.code()
+        rng = np.random.default_rng(1234)
+        info = rng.integers(0, 2, size=(min(frames, 2048), self.K))
+        cw = oracle.bin_encode_batch(self.N, self.fm, self.r, np.full((self.N, 2), 0.5), info)
+        cw = np.tile(cw, ((frames + cw.shape[0] - 1) // cw.shape[0], 1))[:frames]
+        return (cw ^ (rng.random((frames, self.N)) < P_BSC)).astype(np.uint8)
+
+    def cpu_decode(self, ys, threads):
+        import oracle
+        oracle.lib()
+        xp = np.full((self.N, 2), 0.5)
+
+        def work(idx):
+            if len(idx) == 0:
+                return 0
+            xy = self.tab[ys[idx]]  # makeBinaryMemorylessVectorDistribution, BinaryMemorylessDistribution.py:245-258
+            oracle.bin_decode_batch(self.N, self.fm, self.r, xp, xy)
+            return len(idx)
+
+        return run_threads(work, np.array_split(np.arange(ys.shape[0]), threads), threads)
+
+    cpu_what = "oracle/polar_oracle.c (C restatement of the reference's float64 SC recursion, prior and posterior trees)"
+
+
+def awgn_frozen_set(n, K, allow_ga):
+    """C2 code: Pe vector of the reference's degrade pass over a 400-bin quantised BI-AWGN (oracle/gen_constructions.py)."""
+    from polarcub_b200.construction import frozen_set_from_pe, load_pe, ga_awgn_pe
+    name = "biawgn_ebn0%s_n%d_L100_pe.npy" % (EBN0_DB, n)
+    try:
+        return frozen_set_from_pe(load_pe(name), K), "Tal-Vardy degrade L=100 via the live reference on a 400-bin BI-AWGN (tests/golden/constructions/%s)" % name
+    except FileNotFoundError:
+        if not allow_ga:
+            raise
+        return frozen_set_from_pe(ga_awgn_pe(n, awgn_sigma()), K), "Gaussian approximation (Chung et al.), --construction ga"
+
+
+class SclBinary4096:
+    """C2: binary SCL L=8, N=4096, K=2048 over BI-AWGN at Eb/N0 = 2 dB, linear-domain float64 (listDecode with q=2)."""
+    name = "scl_l8_n4096_k2048_biawgn2dB"
+    kernel = "scl_decode_kernel<2>"
+    dtype = "f64"
+    default_frames, default_e2e, default_cpu = 1 << 15, 1 << 13, 1 << 9
+    N, K, n, L = 4096, 2048, 12, 8
+    alg_bytes_frame = 16640  # SURVEY.md 8(d): 4 N bytes of soft input + K/8 bytes out
+    info_bits = 2048
+    allow_ga = False
+
+    def code(self):
+        fs, self.construction = awgn_frozen_set(self.n, self.K, self.allow_ga)
+        self.fm = mask_of(self.N, fs)
+
+    def make_xy(self, torch, cw, gen):
+        sigma = awgn_sigma()
+        y = (1.0 - 2.0 * cw.to(torch.float64)) + sigma * torch.randn(cw.shape, dtype=torch.float64, device=cw.device, generator=gen)
+        l0 = -(y - 1.0) ** 2 / (2 * sigma * sigma)
+        l1 = -(y + 1.0) ** 2 / (2 * sigma * sigma)
+        m = torch.maximum(l0, l1)
+        return torch.stack([torch.exp(l0 - m), torch.exp(l1 - m)], dim=-1).contiguous()
+
+    def setup(self, dev, rank, B, Be):
+        import torch
+        from polarcub_b200 import engine
+        self.engine, self.torch = engine, torch
+        self.code()
+        N, K = self.N, self.K
+        self.plan = plan = engine.Plan(2, self.n, self.fm, None, device=dev)
+        gen = torch.Generator(device=dev)
+        self.xy = torch.empty((B, N, 2), dtype=torch.float64, device=dev)
+        self.info_tx = torch.empty((B, K), dtype=torch.uint8, device=dev)
+        self.fvals = torch.zeros((B, N - K), dtype=torch.uint8, device=dev)
+        CH = 1 << 12
+        for c0 in range(0, B, CH):
+            c1 = min(B, c0 + CH)
+            gen.manual_seed(4321 + 7919 * ((rank * B + c0) // CH))
+            it = torch.randint(0, 2, (c1 - c0, K), dtype=torch.uint8, device=dev, generator=gen)
+            self.info_tx[c0:c1] = it
+            cw = engine.qsc_encode(plan, it.contiguous())
+            self.xy[c0:c1] = self.make_xy(torch, cw, gen)
+            del it, cw
+        self.out = None
+        self.Be = Be
+        self.xy_host = torch.empty((Be, N, 2), dtype=torch.float64).pin_memory()
+        self.xy_host.copy_(self.xy[:Be])
+        self.ai_host = torch.empty((Be, K), dtype=torch.uint8).pin_memory()
+        self.ai_host.copy_(self.info_tx[:Be])
+        self.info_host = torch.empty((Be, K), dtype=torch.uint8).pin_memory()
+        self.res_host = torch.empty((Be,), dtype=torch.int32).pin_memory()
+        self.xy_e = torch.empty((Be, N, 2), dtype=torch.float64, device=dev)
+        self.ai_e = torch.empty((Be, K), dtype=torch.uint8, device=dev)
+        self.h2d = int(Be * (N * 16 + K))
+        self.d2h = int(Be * (K + 4))
+        self.input_note = ("float64 probability pairs [B,N,2] = xyVectorDistribution.probs (%.2f GiB per step per GPU, larger "
+                           "than L2: no flush needed)" % (B * N * 16 / 2 ** 30))
+
+    def step(self):
+        self.out = self.engine.scl_decode_probs(self.plan, self.L, self.xy, self.fvals, self.info_tx)
+
+    def e2e_step(self):
+        Be = self.Be
+        self.xy_e.copy_(self.xy_host, non_blocking=True)
+        self.ai_e.copy_(self.ai_host, non_blocking=True)
+        o = self.engine.scl_decode_probs(self.plan, self.L, self.xy_e, self.fvals[:Be], self.ai_e)
+        self.info_host.copy_(o["info"], non_blocking=True)
+        self.res_host.copy_(o["prob_result"], non_blocking=True)
+
+    def counters(self):
+        torch = self.torch
+        diff = (self.out["info"] != self.info_tx)
+        c = torch.zeros(3, dtype=torch.int64, device=diff.device)
+        c[0] = diff.shape[0]
+        c[1] = diff.any(dim=1).sum()
+        c[2] = diff.sum()
+        return c
+
+    def cpu_inputs_from_gpu(self, sample):
+        return (self.xy[:sample].cpu().numpy(), self.info_tx[:sample].cpu().numpy().astype(np.int64))
+
+    def cpu_inputs_synth(self, frames):
+        import oracle
+        self.code()
+        rng = np.random.default_rng(4321)
+        info = rng.integers(0, 2, size=(frames, self.K))
+        u = np.zeros((frames, self.N), dtype=np.int64)
+        u[:, self.fm == 0] = info
+        cw = np.stack([oracle.polar_transform_qudits(2, u[b]) for b in range(frames)])
+        sigma = awgn_sigma()
+        y = (1.0 - 2.0 * cw) + sigma * rng.standard_normal(cw.shape)
+        l0, l1 = -(y - 1) ** 2 / (2 * sigma ** 2), -(y + 1) ** 2 / (2 * sigma ** 2)
+        m = np.maximum(l0, l1)
+        return (np.stack([np.exp(l0 - m), np.exp(l1 - m)], axis=-1), info)
+
+    def cpu_decode(self, inputs, threads):
+        import oracle
+        oracle.lib()
+        xy, info = inputs
+        fv = np.zeros((xy.shape[0], self.N - self.K), dtype=np.int64)
+
+        def work(idx):
+            if len(idx) == 0:
+                return 0
+            oracle.list_decode_batch(2, self.N, self.L, self.fm, xy[idx], fv[idx], info[idx])
+            return len(idx)
+
+        return run_threads(work, np.array_split(np.arange(xy.shape[0]), threads), threads)
+
+    cpu_what = "oracle/polar_oracle_list.c (C restatement of the reference's float64 listDecode with fast nodes)"
+
+
+class ScQary2048:
+    """C3: q=3 SC, N=2048, K=1024 over the ternary symmetric channel QSC(p=0.02)."""
+    name = "qsc_q3_n2048_k1024_qsc0.02"
+    kernel = "qsc_decode_kernel<3>"
+    dtype = "f64"
+    default_frames, default_e2e, default_cpu = 1 << 16, 1 << 14, 1 << 11
+    N, K, n, q = 2048, 1024, 11, 3
+    alg_bytes_frame = 25344  # SURVEY.md 8(d)
+    info_bits = 1024 * math.log2(3)
+    allow_ga = False
+
+    def code(self):
+        from polarcub_b200.construction import frozen_set_from_pe, load_pe, bec_pe
+        name = "qsc_q3_p%s_n%d_L100_pe.npy" % (P_QSC, self.n)
+        try:
+            fs = frozen_set_from_pe(load_pe(name), self.K)
+            self.construction = "reference calcTVAndPe_degradingUpgrading L=100 (tests/golden/constructions/%s)" % name
+        except FileNotFoundError:
+            if not self.allow_ga:
+                raise
+            fs = frozen_set_from_pe(bec_pe(self.n, 0.15), self.K)
+            self.construction = "BEC(0.15) Bhattacharyya heuristic, --construction ga"
+        self.fm = mask_of(self.N, fs)
+
+    def setup(self, dev, rank, B, Be):
+        import torch
+        from polarcub_b200 import engine
+        self.engine, self.torch = engine, torch
+        self.code()
+        N, K, q = self.N, self.K, self.q
+        self.plan = plan = engine.Plan(q, self.n, self.fm, None, device=dev)
+        gen = torch.Generator(device=dev)
+        self.xy = torch.empty((B, N, q), dtype=torch.float64, device=dev)
+        self.info_tx = torch.empty((B, K), dtype=torch.uint8, device=dev)
+        tab = torch.full((q, q), P_QSC / (q - 1), dtype=torch.float64, device=dev)  # makeQSC, QaryMemorylessDistribution.py:780-784
+        tab.fill_diagonal_(1.0 - P_QSC)
+        CH = 1 << 13
+        for c0 in range(0, B, CH):
+            c1 = min(B, c0 + CH)
+            gen.manual_seed(777 + 7919 * ((rank * B + c0) // CH))
+            it = torch.randint(0, q, (c1 - c0, K), dtype=torch.uint8, device=dev, generator=gen)
+            self.info_tx[c0:c1] = it
+            cw = engine.qsc_encode(plan, it.contiguous()).to(torch.int64)
+            err = torch.rand(cw.shape, device=dev, generator=gen) < P_QSC
+            off = torch.randint(1, q, cw.shape, device=dev, generator=gen)
+            y = torch.where(err, (cw + off) % q, cw)
+            self.xy[c0:c1] = tab[y]
+            del it, cw, err, off, y
+        self.out = None
+        self.Be = Be
+        self.xy_host = torch.empty((Be, N, q), dtype=torch.float64).pin_memory()
+        self.xy_host.copy_(self.xy[:Be])
+        self.info_host = torch.empty((Be, K), dtype=torch.uint8).pin_memory()
+        self.xy_e = torch.empty((Be, N, q), dtype=torch.float64, device=dev)
+        self.h2d = int(Be * N * q * 8)
+        self.d2h = int(Be * K)
+        self.input_note = "float64 probability triples [B,N,3] (%.2f GiB per step per GPU, larger than L2)" % (B * N * q * 8 / 2 ** 30)
+
+    def step(self):
+        self.out = self.engine.qsc_decode_probs(self.plan, self.xy)
+
+    def e2e_step(self):
+        self.xy_e.copy_(self.xy_host, non_blocking=True)
+        _, i = self.engine.qsc_decode_probs(self.plan, self.xy_e)
+        self.info_host.copy_(i, non_blocking=True)
+
+    def counters(self):
+        torch = self.torch
+        diff = (self.out[1] != self.info_tx)
+        c = torch.zeros(3, dtype=torch.int64, device=diff.device)
+        c[0] = diff.shape[0]
+        c[1] = diff.any(dim=1).sum()
+        c[2] = diff.sum()
+        return c
+
+    def cpu_inputs_from_gpu(self, sample):
+        return self.xy[:sample].cpu().numpy()
+
+    def cpu_inputs_synth(self, frames):
+        import oracle
+        self.code()
+        q = self.q
+        rng = np.random.default_rng(777)
+        info = rng.integers(0, q, size=(frames, self.K))
+        u = np.zeros((frames, self.N), dtype=np.int64)
+        u[:, self.fm == 0] = info
+        cw = np.stack([oracle.polar_transform_qudits(q, u[b]) for b in range(frames)])
+        err = rng.random(cw.shape) < P_QSC
+        y = np.where(err, (cw + rng.integers(1, q, size=cw.shape)) % q, cw)
+        tab = np.full((q, q), P_QSC / (q - 1))
+        np.fill_diagonal(tab, 1 - P_QSC)
+        return tab[y]
+
+    def cpu_decode(self, xy, threads):
+        import oracle
+        oracle.lib()
+        xp = np.full((self.N, self.q), 1.0 / self.q)
+
+        def work(idx):
+            if len(idx) == 0:
+                return 0
+            oracle.q_decode_batch(self.q, self.N, self.fm, xp, xy[idx])
+            return len(idx)
+
+        return run_threads(work, np.array_split(np.arange(xy.shape[0]), threads), threads)
+
+    cpu_what = "oracle/polar_oracle.c (C restatement of the reference's float64 q-ary SC recursion)"
+
+
+WORKLOADS = {"scl4096": SclBinary4096, "sc1024": ScBinary1024, "qsc2048": ScQary2048}
+
+
+def nframes(x):
+    return x[0].shape[0] if isinstance(x, tuple) else x.shape[0]
+
+
+def head(x, m):
+    return tuple(a[:m] for a in x) if isinstance(x, tuple) else x[:m]
+
+
+# ---------------------------------------------------------------------------------------------------
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Python original cannot travel to the GPU box)."""
+    """--impl reference: the reference's CPU algorithm (the oracle port; the Python original cannot travel to the GPU box),
+    all host threads, bounded sample per step."""
     if rank != 0:
         return
     import oracle
-    N, K, fs = c1_code()
-    fm = oracle.frozen_mask(N, fs)
-    r = oracle.common_randomness(N, 1)
+    oracle.build()
+    w = WORKLOADS[args.workload]()
+    w.allow_ga = args.construction == "ga"
     cores = os.cpu_count() or 1
-    rng = np.random.default_rng(1234)
-    frames = args.ref_frames
-    info = rng.integers(0, 2, size=(frames, K))
-    cw = oracle.bin_encode_batch(N, fm, r, np.full((N, 2), 0.5), info[:min(frames, 2048)])
-    cw = np.tile(cw, ((frames + cw.shape[0] - 1) // cw.shape[0], 1))[:frames]
-    y = (cw ^ (rng.random((frames, N)) < P_BSC)).astype(np.uint8)
-    tab = bsc_table()
+    frames = args.ref_frames or w.default_cpu
+    inputs = w.cpu_inputs_synth(frames)
     for _ in range(args.warmup):
-        cpu_decode_sample(N, fm, r, y[:max(cores * 64, 256)], tab, cores)
-    t = 0.0
-    done = 0
+        w.cpu_decode(head(inputs, max(cores, frames // 8)), cores)
+    t, done = 0.0, 0
     for _ in range(args.steps):
-        d, dt = cpu_decode_sample(N, fm, r, y, tab, cores)
+        d, dt = w.cpu_decode(inputs, cores)
         t += dt
         done += d
-    val = done * K / t / 1e9
+    val = done * w.info_bits / t / 1e9
     line = {
         "impl": "reference", "metric": "decoded info Gbit/s", "value": val, "unit": "Gbit/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "sc_n1024_k512_bsc0.11", "frames_per_step": frames},
+        "scaling": "weak", "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
+        "config": {"workload": w.name, "frames_per_step": frames, "construction": w.construction},
         "frames_per_s": done / t,
         "cpu_baseline": {"value": val, "unit": "Gbit/s", "cores": cores, "kind": "port",
-                         "sample": "%d frames/step x %d steps, oracle/polar_oracle.c (C restatement of the reference's "
-                                   "float64 SC recursion, both prior and posterior trees), %d threads" % (frames, args.steps, cores)},
+                         "sample": "%d frames/step x %d steps, %s, %d threads" % (frames, args.steps, w.cpu_what, cores)},
         "e2e": {"value": val, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
+def time_steps(torch, fn, steps, barrier):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from polarcub_b200 import engine
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    N, K, fs = c1_code()
-    fm = np.zeros(N, dtype=np.uint8)
-    fm[list(fs)] = 1
-    import random as _random
-    rng_cr = _random.Random()
-    rng_cr.seed(1)  # commonRandomnessSeed=1, BinaryPolarEncoderDecoder.py:36-41
-    r = np.array([rng_cr.random() for _ in range(N)])
-    fv = np.where(0.5 >= r, 0, 1).astype(np.uint8)
-    plan = engine.Plan(2, 10, fm, fv, device=dev)
-    tab = bsc_table()
-    B = args.frames
-    Be = min(args.e2e_frames, B)
-
-    # ---- synthetic frames, generated on the device, keyed by the global frame index (rank-count invariant) ----
-    gen = torch.Generator(device=dev)
-    y = torch.empty((B, N), dtype=torch.uint8, device=dev)
-    info_tx = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
-    shifts = torch.arange(32, device=dev, dtype=torch.int32)
-    CH = 1 << 16
-    for c0 in range(0, B, CH):
-        c1 = min(B, c0 + CH)
-        gen.manual_seed(1234 + 7919 * ((rank * B + c0) // CH))
-        it = torch.randint(-2 ** 31, 2 ** 31 - 1, (c1 - c0, plan.Kw), dtype=torch.int64, device=dev, generator=gen).to(torch.int32)
-        info_tx[c0:c1] = it
-        cwp = engine.encode_bits(plan, it.contiguous())
-        bits = ((cwp.unsqueeze(-1) >> shifts) & 1).reshape(c1 - c0, N).to(torch.uint8)
-        flips = (torch.rand((c1 - c0, N), device=dev, generator=gen) < P_BSC).to(torch.uint8)
-        y[c0:c1] = bits ^ flips
-        del it, cwp, bits, flips
-    cw_out = torch.empty((B, plan.Nw), dtype=torch.int32, device=dev)
-    info_out = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
-    y_host = torch.empty((Be, N), dtype=torch.uint8).pin_memory()
-    y_host.copy_(y[:Be])
-    cw_host = torch.empty((Be, plan.Nw), dtype=torch.int32).pin_memory()
-    info_host = torch.empty((Be, plan.Kw), dtype=torch.int32).pin_memory()
-    y_e = torch.empty((Be, N), dtype=torch.uint8, device=dev)
+    w = WORKLOADS[args.workload]()
+    w.allow_ga = args.construction == "ga"
+    B = args.frames or w.default_frames
+    Be = min(args.e2e_frames or w.default_e2e, B)
+    w.setup(dev, rank, B, Be)
     torch.cuda.synchronize()
 
     def barrier():
@@ -218,31 +540,15 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        engine.sc_decode_symbols(plan, y, tab, out=(cw_out, info_out))
-
-    def e2e_step():
-        y_e.copy_(y_host, non_blocking=True)
-        c, i = engine.sc_decode_symbols(plan, y_e, tab, out=(cw_out[:Be], info_out[:Be]))
-        cw_host.copy_(c, non_blocking=True)
-        info_host.copy_(i, non_blocking=True)
-
     for _ in range(args.warmup):
-        step()
+        w.step()
     barrier()
     sampler = ClockSampler()
     if rank == 0:
         sampler.start()
     engine.profile_enable(True)
     l0 = engine.kernel_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = time_steps(torch, w.step, args.steps, barrier)
     launches = engine.kernel_launch_count() - l0
     k_ms, k_launches = engine.profile_read()
     engine.profile_enable(False)
@@ -250,18 +556,12 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through host buffers --------------------------------------------------------------
     for _ in range(max(1, min(args.warmup, 2))):
-        e2e_step()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
+        w.e2e_step()
+    ms_e2e = time_steps(torch, w.e2e_step, args.steps, barrier)
 
-    # ---- error counters: one kernel per rank + ONE all-reduce (the only collective of the run) ----------
-    counters = engine.count_errors(info_out, info_tx, K)
+    # ---- error counters: one reduction per rank + ONE all-reduce (the only collective of the run) --------
+    w.step()
+    counters = w.counters()
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -272,43 +572,56 @@ def run_ours(args, rank, world, local_rank):
         return
 
     frames_total = B * world * args.steps
-    value = frames_total * K / (ms * 1e-3) / 1e9
-    e2e_val = Be * world * args.steps * K / (ms_e2e * 1e-3) / 1e9
+    bits = w.info_bits
+    value = frames_total * bits / (ms * 1e-3) / 1e9
+    e2e_val = Be * world * args.steps * bits / (ms_e2e * 1e-3) / 1e9
     peak, peak_kind = measured_peak_hbm()
-    alg_bytes_frame = 4288  # 4 N bytes of soft input + (N + K)/8 bytes out
-    achieved = (B * args.steps * alg_bytes_frame) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+    achieved = (B * args.steps * w.alg_bytes_frame) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
     line = {
         "metric": "decoded info Gbit/s", "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "sc_n1024_k512_bsc0.11", "N": N, "K": K, "decoder": "SC", "frames_per_step_per_gpu": B,
-                   "input": "uint8 channel symbols [B,N] (1 GiB per step per GPU, larger than L2: no flush needed)",
-                   "parity": "bit-identical to the reference (float64 probability-pair arithmetic)"},
+        "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
+        "config": {"workload": w.name, "N": w.N, "K": w.K, "frames_per_step_per_gpu": B, "input": w.input_note,
+                   "construction": w.construction,
+                   "parity": "bit-identical to the reference (float64 probability arithmetic, same rounding order)"},
         "frames_per_s": frames_total / (ms * 1e-3),
-        "fer": float(cnt[1]) / max(1, int(cnt[0])), "ber": float(cnt[2]) / max(1, int(cnt[0]) * K),
-        "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": int(Be * N), "d2h_bytes_per_step": int(Be * (plan.Nw + plan.Kw) * 4),
+        "fer": float(cnt[1]) / max(1, int(cnt[0])), "ber": float(cnt[2]) / max(1, int(cnt[0]) * w.K),
+        "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h,
                 "frames_per_step_per_gpu": Be},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": None,
-                     "kernel": "sc_decode_kernel<symbols>", "kernel_ms_per_launch": k_ms / max(1, k_launches),
+                     "kernel": w.kernel, "kernel_ms_per_launch": k_ms / max(1, k_launches),
                      "kernel_launches": int(k_launches), "kernel_share_of_step": k_ms / ms,
-                     "algorithmic_bytes_per_frame": alg_bytes_frame, "peak_source": peak_kind,
-                     "note": "SC decoding is FP64-issue bound, not HBM bound (SURVEY.md 8d); see profiles/ for pipe utilisation"},
+                     "algorithmic_bytes_per_frame": w.alg_bytes_frame, "peak_source": peak_kind,
+                     "note": "SC/SCL decoding is FP64-issue bound, not HBM bound (SURVEY.md 8d); pipe utilisation in profiles/"},
     }
     if world == 1:
         import oracle
         cores = os.cpu_count() or 1
-        sample = min(B, args.cpu_frames)
-        ys = y[:sample].cpu().numpy()
+        sample = min(B, args.cpu_frames or w.default_cpu)
         oracle.build()
-        cpu_decode_sample(N, fm, r, ys[:256], tab, cores)
-        done, dt = cpu_decode_sample(N, fm, r, ys, tab, cores)
-        line["cpu_baseline"] = {"value": done * K / dt / 1e9, "unit": "Gbit/s", "cores": cores, "kind": "port",
+        inputs = w.cpu_inputs_from_gpu(sample)
+        w.cpu_decode(head(inputs, max(cores, sample // 8)), cores)
+        done, dt = w.cpu_decode(inputs, cores)
+        line["cpu_baseline"] = {"value": done * bits / dt / 1e9, "unit": "Gbit/s", "cores": cores, "kind": "port",
                                 "frames_per_s": done / dt,
-                                "sample": "first %d frames of the GPU batch, oracle/polar_oracle.c on %d threads "
-                                          "(%.1f s wall)" % (sample, cores, dt)}
+                                "sample": "first %d frames of the GPU batch, %s on %d threads (%.1f s wall)" % (
+                                    sample, w.cpu_what, cores, dt)}
+    if args.workload == "scl4096" and not args.no_secondary:
+        # BASELINE.json's metric also names SC N=1024: a short device-resident measurement of it rides along
+        del w
+        torch.cuda.empty_cache()
+        s = ScBinary1024()
+        Bs = 1 << 19
+        s.setup(dev, rank, Bs, 1 << 10)
+        for _ in range(2):
+            s.step()
+        ms_s = time_steps(torch, s.step, 3, barrier)
+        line["secondary"] = {"workload": s.name, "value": 3 * Bs * world * s.info_bits / (ms_s * 1e-3) / 1e9, "unit": "Gbit/s",
+                             "frames_per_s": 3 * Bs * world / (ms_s * 1e-3), "frames_per_step_per_gpu": Bs, "steps": 3,
+                             "note": "device-resident, this rank's clock only; full line: --workload sc1024"}
     print(json.dumps(line), flush=True)
 
 
@@ -318,11 +631,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sc1024")
-    ap.add_argument("--frames", type=int, default=1 << 20, help="frames per step per GPU")
-    ap.add_argument("--e2e-frames", type=int, default=1 << 18)
-    ap.add_argument("--cpu-frames", type=int, default=1 << 16)
-    ap.add_argument("--ref-frames", type=int, default=1 << 16)
+    ap.add_argument("--workload", default="scl4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--construction", default="reference", choices=["reference", "ga"],
+                    help="ga: allow a heuristic frozen set when the reference-derived Pe vector is not in tests/golden/constructions")
+    ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (0 = workload default)")
+    ap.add_argument("--e2e-frames", type=int, default=0)
+    ap.add_argument("--cpu-frames", type=int, default=0)
+    ap.add_argument("--ref-frames", type=int, default=0)
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

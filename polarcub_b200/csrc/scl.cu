@@ -22,37 +22,19 @@
 #include <map>
 #include <mutex>
 
-#include "common.cuh"
+#include "scl_tables.cuh"
 
 namespace pc {
 
 int qsc_ingest_launch(int n, int q, int64_t frames, int64_t Bpad, const double *in, double *out, cudaStream_t st);
 int byte_egress_launch(bool bitrev, int n, int R, int64_t frames, int64_t Bpad, const uint8_t *in_t, uint8_t *out,
                        cudaStream_t st);
-
-enum : int { OP_MINUS = 0, OP_PLUS = 1, OP_COMBINE = 2, OP_RATE0 = 3, OP_REP = 4, OP_RATE1 = 5, OP_SPC = 6 };
-constexpr int SCL_LMAX = 32;
-constexpr int SCL_THREADS = 64;
-
-struct SclOp {
-    int8_t kind, l, c, pad;
-    int32_t i;         // first u index of the node
-    int32_t info_idx;  // informationVectorIndex when the node starts
-    int32_t fv_idx;    // position of the frozen-values iterator when the node starts
-    int32_t kpos;      // Rep: offset of the single information index inside the segment
-    int32_t coef_off;  // Rep: offset into rep_coef (natural-order T(e_kpos) mod q)
-};
-
-struct SclTables {
-    std::vector<SclOp> ops;
-    std::vector<int32_t> a_src, f_src, info_src;
-    std::vector<int8_t> node_level;
-    std::vector<uint8_t> rep_coef;
-    SclOp *d_ops = nullptr;
-    int32_t *d_a_src = nullptr, *d_f_src = nullptr, *d_info_src = nullptr;
-    int8_t *d_node_level = nullptr;
-    uint8_t *d_rep_coef = nullptr;
-};
+// scl_bin.cu: frame-per-CTA binary decoder
+bool scl2_supported(const pc_plan *plan, int L);
+size_t scl2_workspace_bytes(const pc_plan *plan, int L, int64_t B);
+int scl2_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_xy, const uint8_t *d_fv, const uint8_t *d_ainfo,
+                int64_t B, uint8_t *d_info, int32_t *d_res, int32_t *d_lsize, double *d_lprob, double *d_aprob,
+                uint8_t *d_linfo, void *ws, size_t ws_bytes, cudaStream_t st);
 
 static std::mutex g_scl_mu;
 static std::map<const pc_plan *, SclTables *> g_scl_tables;
@@ -108,6 +90,20 @@ static void scl_build(const pc_plan *p, SclTables &T, int i, int l, int c, int &
                 }
         op.coef_off = (int32_t)T.rep_coef.size();
         for (int j = 0; j < size; ++j) T.rep_coef.push_back((uint8_t)cf[j]);
+        if (q == 2) {  // reference order: position j of the node is natural position bitrev(j, l)
+            op.coefw_off = (int32_t)T.rep_coef_words.size();
+            const int words = size >= 32 ? size / 32 : 1;
+            for (int w = 0; w < words; ++w) {
+                uint32_t v = 0;
+                for (int b = 0; b < 32 && 32 * w + b < size; ++b) {
+                    const int j = 32 * w + b;
+                    int r = 0;
+                    for (int t = 0; t < l; ++t) r |= ((j >> t) & 1) << (l - 1 - t);
+                    v |= (uint32_t)(cf[r] & 1) << b;
+                }
+                T.rep_coef_words.push_back(v);
+            }
+        }
         fv_idx += size - 1;
         info_idx += 1;
         mark();
@@ -157,7 +153,7 @@ static cudaError_t upload(T *&dst, const std::vector<T> &v) {
     return e;
 }
 
-static SclTables *scl_tables(const pc_plan *p) {
+SclTables *scl_tables(const pc_plan *p) {
     std::lock_guard<std::mutex> lk(g_scl_mu);
     auto it = g_scl_tables.find(p);
     if (it != g_scl_tables.end()) return it->second;
@@ -168,9 +164,25 @@ static SclTables *scl_tables(const pc_plan *p) {
     T->info_src.assign(p->k > 0 ? p->k : 1, 0);
     int ii = 0, fi = 0;
     scl_build(p, *T, 0, p->n, 0, ii, fi);
+    if (p->q == 2) {
+        const int N = p->N, NW = N >= 32 ? N / 32 : 1;
+        T->perm.assign(N, 0);
+        for (int i = 0; i < N; ++i) {
+            const int l = T->node_level[i], size = 1 << l, i0 = i & ~(size - 1), j = i - i0;
+            int r = 0;
+            for (int t = 0; t < l; ++t) r |= ((j >> t) & 1) << (l - 1 - t);
+            T->perm[i] = i0 + r;
+        }
+        T->stage_mask.assign((size_t)(p->n > 0 ? p->n : 1) * NW, 0u);
+        for (int t = 0; t < p->n; ++t)
+            for (int pos = 0; pos < N; ++pos)
+                if (!(pos & (1 << t)) && T->node_level[pos] > t) T->stage_mask[(size_t)t * NW + (pos >> 5)] |= 1u << (pos & 31);
+    }
     if (upload(T->d_ops, T->ops) != cudaSuccess || upload(T->d_a_src, T->a_src) != cudaSuccess ||
         upload(T->d_f_src, T->f_src) != cudaSuccess || upload(T->d_info_src, T->info_src) != cudaSuccess ||
-        upload(T->d_node_level, T->node_level) != cudaSuccess || upload(T->d_rep_coef, T->rep_coef) != cudaSuccess) {
+        upload(T->d_node_level, T->node_level) != cudaSuccess || upload(T->d_rep_coef, T->rep_coef) != cudaSuccess ||
+        upload(T->d_rep_coef_words, T->rep_coef_words) != cudaSuccess || upload(T->d_stage_mask, T->stage_mask) != cudaSuccess ||
+        upload(T->d_perm, T->perm) != cudaSuccess) {
         set_error("scl tables: device upload failed");
         return nullptr;
     }
@@ -185,6 +197,7 @@ void scl_tables_release(const pc_plan *p) {
     SclTables *T = it->second;
     cudaFree(T->d_ops), cudaFree(T->d_a_src), cudaFree(T->d_f_src), cudaFree(T->d_info_src);
     cudaFree(T->d_node_level), cudaFree(T->d_rep_coef);
+    cudaFree(T->d_rep_coef_words), cudaFree(T->d_stage_mask), cudaFree(T->d_perm);
     delete T;
     g_scl_tables.erase(it);
 }
@@ -687,6 +700,7 @@ extern "C" {
 
 size_t pc_scl_workspace_bytes(const pc_plan *plan, int L, int64_t B, int want_list) {
     if (!plan || B <= 0 || L < 1 || L > pc::SCL_LMAX) return 256;
+    if (pc::scl2_supported(plan, L)) return pc::scl2_workspace_bytes(plan, L, B);
     int64_t chunk = pc::round_up(B, 32);
     const int64_t cap = (int64_t)pc::num_sms() * 2 * pc::SCL_THREADS * 4;
     if (chunk > cap) chunk = cap;
@@ -714,6 +728,9 @@ int pc_scl_decode_probs(const pc_plan *plan, int L, const double *d_xy, const ui
     SclTables *T = scl_tables(plan);
     if (!T) return PC_ERR_CUDA;
     cudaStream_t st = (cudaStream_t)stream;
+    if (scl2_supported(plan, L))  // q = 2: one frame per CTA, state in shared memory (scl_bin.cu)
+        return scl2_decode(plan, T, L, d_xy, d_frozen_values, d_actual_info, B, d_info, d_prob_result, d_list_size,
+                           d_list_prob, d_actual_prob, d_list_info, d_workspace, workspace_bytes, st);
     int64_t chunk = round_up(B, 32);
     const int64_t cap = (int64_t)num_sms() * 2 * SCL_THREADS * 4;
     if (chunk > cap) chunk = cap;

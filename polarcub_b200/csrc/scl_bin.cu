@@ -1,0 +1,646 @@
+// scl_bin.cu -- binary (q = 2) SC-list decoding, ONE FRAME PER CTA, float64 linear domain, arithmetic and decisions
+// identical to QaryPolarEncoderDecoder.listDecode with q = 2 (the reference's only SCL; QaryPolarEncoderDecoder.py:118-227,
+// recursiveListDecode :403-757, helpers :759-820, normalize :867-872, QaryMemorylessVectorDistribution.py:26-118).
+//
+// Why a second SCL kernel: a list decoder's state is L path vectors per tree level (N L 16 bytes of float64 pairs,
+// 0.5 MB per frame at N = 4096, L = 8).  The frame-per-lane kernel of scl.cu keeps 32 such states per warp in global
+// memory and is DRAM-bound.  Here a CTA owns one frame:
+//  * path vectors of levels <= LSM live in shared memory, the larger levels in a per-CTA global scratch that the
+//    CTA writes and re-reads element-parallel (16-byte accesses, fully coalesced, L2-resident for the resident CTAs);
+//  * vectors stay in the REFERENCE's index order (children of a node are elements (2h, 2h+1)), so the channel
+//    probabilities are read in the caller's layout -- no ingest / transpose pass -- and the fast nodes' sequential
+//    products run over contiguous elements;
+//  * path codewords (partial sums) are bit-packed in shared memory; the combine step is a 16 -> 32 bit interleave;
+//  * lazy path copy: a pruned list is a permutation table per (level, child) (omap), never a copy of a vector;
+//  * f / g node updates run over (path, element) with all threads; the fast nodes' order-dependent float64 products
+//    (np.product is a left-to-right product) run one path per lane in warp 0; pruning follows the oracle's
+//    ascending (metric, index) order;
+//  * the genie ("actual") path that listDecode tracks is slot L of every array.
+#include "scl_tables.cuh"
+
+namespace pc {
+
+constexpr int SCL2_MAX_THREADS = 512;
+
+struct Scl2Params {
+    int n, k, L, n_ops, nfrozen, lsm;
+    int64_t frames;
+    const SclOp *ops;
+    const int32_t *a_src, *f_src, *info_src, *perm;
+    const uint32_t *stage_mask, *coef_words;
+    const double2 *xy;     // [frames][N] caller layout (reference order)
+    const uint8_t *fv;     // [frames][N-k]
+    const uint8_t *ainfo;  // [frames][k]
+    double2 *vg;           // [grid][vg_stride] scratch for levels > lsm
+    int64_t vg_stride;
+    uint8_t *info;         // [frames][k]
+    int32_t *result;       // [frames]
+    int32_t *list_size;    // optional, caller layouts
+    double *list_prob, *actual_prob;
+    uint8_t *list_info;
+};
+
+__host__ __device__ inline int scl2_W(int l) { return l <= 5 ? 1 : 1 << (l - 5); }
+__host__ __device__ inline int scl2_wsum(int l) { return l <= 6 ? l - 1 : 3 + (1 << (l - 5)); }  // sum of W(1..l-1)
+
+// shared-memory bytes of the kernel for (n, L, lsm); mirrors the carve-up at the top of the kernel
+static size_t scl2_smem_bytes(int n, int L, int lsm) {
+    const int S = L + 1, N = 1 << n, NW = N >= 32 ? N >> 5 : 1;
+    size_t b = (size_t)((2 << lsm) - 2) * S * 16;       // Vs
+    b += (size_t)(10 * L + 4) * 8;                      // prob, cand, newprob, misc
+    b += (size_t)2 * S * scl2_wsum(n + 1) * 4;          // Rw
+    b += (size_t)4 * NW * 4;                            // Abits, Fbits, T0, T1
+    b += (size_t)(3 * L + 3 * (n + 1) + 4) * 4;         // keep, selsrc, self, nl, nin, ivars
+    b += (size_t)4 * L * 2 + L + (size_t)(n + 1) * 2 * L + L;  // pick, delta, omap, eqf
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+// keep the min(#nonzero, L) largest candidates, ascending (metric, index) -- same rule as scl.cu / the oracle
+__device__ int scl2_prune(const double *m, int C, int L, int *keep) {
+    int nz = 0;
+    for (int c = 0; c < C; ++c) nz += (m[c] != 0.0);
+    const int ns = nz < L ? nz : L;
+    int cnt = 0;
+    for (int c = 0; c < C; ++c) {
+        if (cnt == ns) {
+            if (ns == 0 || !(m[c] >= m[keep[0]])) continue;
+            for (int t = 0; t + 1 < cnt; ++t) keep[t] = keep[t + 1];
+            --cnt;
+        }
+        int t = cnt - 1;
+        while (t >= 0 && m[keep[t]] > m[c]) {
+            keep[t + 1] = keep[t];
+            --t;
+        }
+        keep[t + 1] = c;
+        ++cnt;
+    }
+    return ns;
+}
+
+// one f / g node update, QaryMemorylessVectorDistribution.py:36-42 / :56-62 + sum-normalisation :104-118, q = 2
+__device__ __forceinline__ double2 node_update(const double2 a, const double2 b, const bool plus, const uint32_t u1) {
+    double d0, d1;
+    if (!plus) {
+        d0 = __dadd_rn(__dadd_rn(0.0, __dmul_rn(a.x, b.x)), __dmul_rn(a.y, b.y));
+        d1 = __dadd_rn(__dadd_rn(0.0, __dmul_rn(a.x, b.y)), __dmul_rn(a.y, b.x));
+    } else {
+        const double a0 = u1 ? a.y : a.x, a1 = u1 ? a.x : a.y;
+        d0 = __dadd_rn(0.0, __dmul_rn(a0, b.x));
+        d1 = __dadd_rn(0.0, __dmul_rn(a1, b.y));
+    }
+    const double ts = __dadd_rn(__dadd_rn(0.0, d0), d1);
+    if (ts != 0.0) {
+        d0 = d0 / ts;
+        d1 = d1 / ts;
+    }
+    return make_double2(d0, d1);
+}
+
+__global__ void __launch_bounds__(SCL2_MAX_THREADS) scl2_kernel(const Scl2Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n, N = 1 << n, L = p.L, S = L + 1, k = p.k, lsm = p.lsm;
+    const int NW = N >= 32 ? N >> 5 : 1;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    // ---- shared-memory carve-up (scl2_smem_bytes mirrors this) -----------------------------------------
+    const int VS = ((2 << lsm) - 2) * S;
+    double2 *Vs = (double2 *)smem_raw;
+    double *prob = (double *)(Vs + VS);
+    double *cand = prob + L;
+    double *newprob = cand + 8 * L;
+    double *misc = newprob + L;  // [0] genie product of the node, [1] actual_prob
+    uint32_t *Rw = (uint32_t *)(misc + 4);
+    uint32_t *Abits = Rw + 2 * S * scl2_wsum(n + 1);
+    uint32_t *Fbits = Abits + NW, *T0 = Fbits + NW, *T1 = T0 + NW;
+    int *keep = (int *)(T1 + NW);
+    int *selsrc = keep + L, *selfk = selsrc + L;
+    int *nl = selfk + L;          // [(n+1)][2]
+    int *nin = nl + 2 * (n + 1);  // [n+1]
+    int *ivars = nin + (n + 1);   // [4]
+    int16_t *pick = (int16_t *)(ivars + 4);  // [L][4]
+    uint8_t *delta = (uint8_t *)(pick + 4 * L);
+    uint8_t *omap = delta + L;               // [(n+1)][2][L]
+    uint8_t *eqf = omap + (n + 1) * 2 * L;   // [L]
+
+    double2 *vg = p.vg + (int64_t)blockIdx.x * p.vg_stride;
+    auto R = [&](int l, int c, int slot) -> uint32_t * { return Rw + 2 * S * scl2_wsum(l) + (c * S + slot) * scl2_W(l); };
+    auto OM = [&](int l, int c) -> uint8_t * { return omap + (l * 2 + c) * L; };
+
+    for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
+        const double2 *xyf = p.xy + f * N;
+        const uint8_t *fvf = p.fv ? p.fv + f * p.nfrozen : nullptr;
+        const uint8_t *aif = p.ainfo + f * k;
+        auto vsel = [&](int l, int slot) -> const double2 * {
+            if (l == n) return xyf;
+            const int off = ((1 << l) - 2) * S + (slot << l);
+            return l <= lsm ? Vs + off : vg + (off - VS);
+        };
+        auto vout = [&](int l, int slot) -> double2 * {
+            const int off = ((1 << l) - 2) * S + (slot << l);
+            return l <= lsm ? Vs + off : vg + (off - VS);
+        };
+        __syncthreads();
+        // ---- node-local codewords of the genie path (A) and of the frozen values (F) ------------------------
+        // u-domain bits in natural order, masked butterfly up to each fast node's size, then the per-node bit reversal
+        // that turns natural positions into the reference's order.
+        for (int w = warp; w < NW; w += nwarps) {
+            const int pos = 32 * w + lane;
+            uint32_t a = 0, fb = 0;
+            if (pos < N) {
+                const int sa = p.a_src[pos], sf = p.f_src[pos];
+                a = sa >= 0 ? aif[sa] : fvf[~sa];
+                fb = sf >= 0 ? fvf[sf] : 0u;
+            }
+            const uint32_t wa = __ballot_sync(0xffffffffu, a & 1u), wf = __ballot_sync(0xffffffffu, fb & 1u);
+            if (lane == 0) {
+                T0[w] = wa;
+                T1[w] = wf;
+            }
+        }
+        __syncthreads();
+        for (int t = 0; t < n; ++t) {
+            const int s = 1 << t;
+            for (int w = tid; w < NW; w += T) {
+                const uint32_t m = p.stage_mask[t * NW + w];
+                if (m) {
+                    if (s < 32) {
+                        T0[w] ^= (T0[w] >> s) & m;
+                        T1[w] ^= (T1[w] >> s) & m;
+                    } else {
+                        T0[w] ^= T0[w + (s >> 5)] & m;
+                        T1[w] ^= T1[w + (s >> 5)] & m;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        for (int w = warp; w < NW; w += nwarps) {
+            const int i = 32 * w + lane;
+            uint32_t a = 0, fb = 0;
+            if (i < N) {
+                const int src = p.perm[i];
+                a = (T0[src >> 5] >> (src & 31)) & 1u;
+                fb = (T1[src >> 5] >> (src & 31)) & 1u;
+            }
+            const uint32_t wa = __ballot_sync(0xffffffffu, a), wf = __ballot_sync(0xffffffffu, fb);
+            if (lane == 0) {
+                Abits[w] = wa;
+                Fbits[w] = wf;
+            }
+        }
+        if (tid == 0) {
+            prob[0] = 1.0;
+            misc[1] = 1.0;
+            nin[n] = 1;
+            nl[n * 2 + 0] = 1;
+        }
+        __syncthreads();
+
+        for (int oi = 0; oi < p.n_ops; ++oi) {
+            const SclOp op = p.ops[oi];
+            const int l = op.l, size = 1 << l, half = size >> 1, c = op.c;
+            if (op.kind == OP_MINUS || op.kind == OP_PLUS) {
+                const bool plus = op.kind == OP_PLUS;
+                const int cnt = plus ? nl[(l - 1) * 2 + 0] : nin[l];
+                const int total = (cnt + 1) << (l - 1);
+                const uint8_t *om = OM(l - 1, 0);
+                for (int idx = tid; idx < total; idx += T) {
+                    const int t = idx >> (l - 1), h = idx & (half - 1);
+                    const int slot = t == cnt ? L : t;
+                    const int src = t == cnt ? L : (plus ? (int)om[t] : t);
+                    const double2 *P = vsel(l, src);
+                    const double2 a = P[2 * h], b = P[2 * h + 1];
+                    uint32_t u1 = 0;
+                    if (plus) u1 = (R(l - 1, 0, slot)[h >> 5] >> (h & 31)) & 1u;
+                    vout(l - 1, slot)[h] = node_update(a, b, plus, u1);
+                }
+                if (tid == 0) nin[l - 1] = cnt;
+                __syncthreads();
+                continue;
+            }
+            if (op.kind == OP_COMBINE) {  // :726-754 in reference order: out[2h] = m[h] + p[h], out[2h+1] = -p[h]
+                const int cnt = nl[(l - 1) * 2 + 1];
+                const int Wo = scl2_W(l);
+                const uint8_t *om1 = OM(l - 1, 1), *om0 = OM(l - 1, 0);
+                for (int idx = tid; idx < (cnt + 1) * Wo; idx += T) {
+                    const int t = idx / Wo, w = idx - t * Wo;
+                    const int slot = t == cnt ? L : t;
+                    const int mi = t == cnt ? L : (int)om1[t];
+                    const int sh = (w & 1) * 16;
+                    const uint32_t m16 = (R(l - 1, 0, mi)[w >> 1] >> sh) & 0xffffu;
+                    const uint32_t p16 = (R(l - 1, 1, slot)[w >> 1] >> sh) & 0xffffu;
+                    R(l, c, slot)[w] = spread16(m16 ^ p16) | (spread16(p16) << 1);
+                }
+                if (tid < cnt) OM(l, c)[tid] = om0[om1[tid]];
+                if (tid == 0) nl[l * 2 + c] = cnt;
+                __syncthreads();
+                continue;
+            }
+            // ------------------------------- fast nodes ------------------------------------------------------
+            const int cnt = nin[l];
+            const int i0 = op.i;
+            const bool spc = op.kind == OP_SPC;
+            const int nfork = spc ? 3 : 2, npick = spc ? 4 : 2;
+            const int fs = op.kind == OP_REP ? 2 : (spc ? 8 : 4);
+            const uint32_t *coefw = p.coef_words + op.coefw_off;
+            auto abit = [&](int j) -> uint32_t { return (Abits[(i0 + j) >> 5] >> ((i0 + j) & 31)) & 1u; };
+            auto fbit = [&](int j) -> uint32_t { return (Fbits[(i0 + j) >> 5] >> ((i0 + j) & 31)) & 1u; };
+            if (warp == 0) {
+                // ---- phase 1: order-dependent products, one job per lane ------------------------------------
+                if (op.kind == OP_RATE0) {  // :495-518
+                    for (int job = lane; job <= cnt; job += 32) {
+                        const bool act = job == cnt;
+                        const double2 *P = vsel(l, act ? L : job);
+                        double pr = 1.0;
+                        for (int j = 0; j < size; ++j) {
+                            const double2 v2 = P[j];
+                            const double v = (act ? abit(j) : fbit(j)) ? v2.y : v2.x;
+                            pr = j == 0 ? v : __dmul_rn(pr, v);
+                        }
+                        if (act)
+                            misc[0] = pr;
+                        else
+                            newprob[job] = __dmul_rn(prob[job], pr);
+                    }
+                } else if (op.kind == OP_REP) {  // :521-578
+                    for (int job = lane; job <= 2 * cnt; job += 32) {
+                        const bool act = job == 2 * cnt;
+                        const int s = act ? 0 : job / cnt, t = act ? 0 : job - s * cnt;
+                        const double2 *P = vsel(l, act ? L : t);
+                        double pr = 1.0;
+                        for (int j = 0; j < size; ++j) {
+                            const double2 v2 = P[j];
+                            uint32_t b;
+                            if (act)
+                                b = abit(j);
+                            else
+                                b = fbit(j) ^ (s ? (coefw[j >> 5] >> (j & 31)) & 1u : 0u);
+                            const double v = b ? v2.y : v2.x;
+                            pr = j == 0 ? v : __dmul_rn(pr, v);
+                        }
+                        if (act)
+                            misc[0] = pr;
+                        else
+                            cand[s * cnt + t] = __dmul_rn(prob[t], pr);
+                    }
+                } else {  // Rate-1 :581-628 and SPC :631-682
+                    const int fval = spc ? fvf[op.fv_idx] : 0;
+                    for (int job = lane; job <= cnt; job += 32) {
+                        if (job == cnt) {
+                            const double2 *P = vsel(l, L);
+                            double pr = 1.0;
+                            for (int j = 0; j < size; ++j) {
+                                const double2 v2 = P[j];
+                                const double v = abit(j) ? v2.y : v2.x;
+                                pr = j == 0 ? v : __dmul_rn(pr, v);
+                            }
+                            misc[0] = pr;
+                            continue;
+                        }
+                        const int t = job;
+                        const double2 *P = vsel(l, t);
+                        // pickLeastReliableIndices (:759-768): the npick largest (score, j), ascending
+                        double sc[4] = {-1.0, -1.0, -1.0, -1.0};
+                        int sj[4] = {0, 0, 0, 0};
+                        for (int j = 0; j < size; ++j) {
+                            const double2 v2 = P[j];
+                            double m1 = -1.0, m2 = -1.0;
+                            if (v2.x > m1) {
+                                m2 = m1;
+                                m1 = v2.x;
+                            } else if (v2.x > m2) {
+                                m2 = v2.x;
+                            }
+                            if (v2.y > m1) {
+                                m2 = m1;
+                                m1 = v2.y;
+                            } else if (v2.y > m2) {
+                                m2 = v2.y;
+                            }
+                            const double s = m2 / m1;
+                            if (s >= sc[0]) {
+                                int w = 0;
+                                while (w + 1 < npick && s >= sc[w + 1]) {
+                                    sc[w] = sc[w + 1];
+                                    sj[w] = sj[w + 1];
+                                    ++w;
+                                }
+                                sc[w] = s;
+                                sj[w] = j;
+                            }
+                        }
+                        int sumconst = 0;
+                        bool first = true;
+                        double prodmax = 1.0;
+                        for (int j = 0; j < size; ++j) {
+                            bool forked = false;
+                            for (int w = 0; w < npick; ++w) forked |= (sj[w] == j);
+                            if (forked) continue;
+                            const double2 v2 = P[j];
+                            double mv = v2.x;
+                            int am = 0;
+                            if (v2.y > mv) {
+                                mv = v2.y;
+                                am = 1;
+                            }
+                            sumconst += am;
+                            prodmax = first ? mv : __dmul_rn(prodmax, mv);
+                            first = false;
+                        }
+                        const double base_prob = __dmul_rn(prob[t], prodmax);
+                        for (int w = 0; w < npick; ++w) pick[t * 4 + w] = (int16_t)sj[w];
+                        const int dl = (fval ^ sumconst) & 1;
+                        delta[t] = (uint8_t)dl;
+                        for (int fk = 0; fk < fs; ++fk) {
+                            double pf = 1.0;
+                            int sf = 0;
+                            for (int w = 0; w < nfork; ++w) {
+                                const int dg = (fk >> (nfork - 1 - w)) & 1;
+                                const double2 v2 = P[sj[w]];
+                                const double v = dg ? v2.y : v2.x;
+                                pf = w == 0 ? v : __dmul_rn(pf, v);
+                                sf += dg;
+                            }
+                            if (spc) {
+                                const int dep = (dl ^ sf) & 1;
+                                const double2 v2 = P[sj[3]];
+                                pf = __dmul_rn(pf, dep ? v2.y : v2.x);
+                            }
+                            cand[t * fs + fk] = __dmul_rn(pf, base_prob);
+                        }
+                    }
+                }
+                __syncwarp();
+                // ---- phase 2: prune, lazy copy (omap), normalise ---------------------------------------------
+                int nout = cnt;
+                if (op.kind == OP_RATE0) {
+                    for (int t = lane; t < cnt; t += 32) OM(l, c)[t] = (uint8_t)t;
+                } else {
+                    const int C = cnt * fs;
+                    if (lane == 0) {
+                        int no;
+                        if (C > L) {
+                            no = scl2_prune(cand, C, L, keep);
+                        } else {
+                            for (int cc = 0; cc < C; ++cc) keep[cc] = cc;
+                            no = C;
+                        }
+                        ivars[0] = no;
+                    }
+                    __syncwarp();
+                    nout = ivars[0];
+                    for (int t = lane; t < nout; t += 32) {
+                        const int cidx = keep[t];
+                        int src, sel;
+                        if (op.kind == OP_REP) {
+                            sel = cidx / cnt;
+                            src = cidx - sel * cnt;
+                        } else {
+                            src = cidx / fs;
+                            sel = cidx - src * fs;
+                        }
+                        newprob[t] = cand[cidx];
+                        selsrc[t] = src;
+                        selfk[t] = sel;
+                        OM(l, c)[t] = (uint8_t)src;
+                    }
+                }
+                __syncwarp();
+                double mx = newprob[0];
+                for (int t = 1; t < nout; ++t) {
+                    const double v = newprob[t];
+                    if (v > mx) mx = v;
+                }
+                for (int t = lane; t < nout; t += 32) prob[t] = newprob[t] / mx;
+                if (lane == 0) {
+                    misc[1] = __dmul_rn(misc[1], misc[0] / mx);
+                    nl[l * 2 + c] = nout;
+                }
+            }
+            __syncthreads();
+            // ---- phase 3: node codewords of the surviving paths and of the genie path ---------------------------
+            {
+                const int nout = nl[l * 2 + c];
+                const int Wl = scl2_W(l);
+                const uint32_t smask = size >= 32 ? 0xffffffffu : ((1u << size) - 1u);
+                auto slice = [&](const uint32_t *bits, int w) -> uint32_t {
+                    return size >= 32 ? bits[(i0 >> 5) + w] : ((bits[i0 >> 5] >> (i0 & 31)) & smask);
+                };
+                for (int w = tid; w < Wl; w += T) R(l, c, L)[w] = slice(Abits, w);
+                if (op.kind == OP_RATE0 || op.kind == OP_REP) {
+                    for (int idx = tid; idx < nout * Wl; idx += T) {
+                        const int t = idx / Wl, w = idx - t * Wl;
+                        uint32_t v = slice(Fbits, w);
+                        if (op.kind == OP_REP && selfk[t]) v ^= coefw[w];
+                        R(l, c, t)[w] = v;
+                    }
+                } else {
+                    auto sym = [&](int t, int j) -> uint32_t {
+                        const int src = selsrc[t], fk = selfk[t];
+                        const int16_t *pk = pick + src * 4;
+                        for (int w = 0; w < nfork; ++w)
+                            if (pk[w] == j) return (uint32_t)((fk >> (nfork - 1 - w)) & 1);
+                        if (spc && pk[3] == j) return (uint32_t)((delta[src] ^ __popc(fk)) & 1);
+                        const double2 v2 = vsel(l, src)[j];
+                        return v2.y > v2.x ? 1u : 0u;
+                    };
+                    if (size >= 32) {
+                        for (int base = warp * 32; base < nout * size; base += T) {
+                            const int idx = base + lane;
+                            const int t = idx >> l, j = idx & (size - 1);
+                            const uint32_t wv = __ballot_sync(0xffffffffu, sym(t, j));
+                            if (lane == 0) R(l, c, t)[j >> 5] = wv;
+                        }
+                    } else {
+                        for (int t = tid; t < nout; t += T) {
+                            uint32_t wv = 0;
+                            for (int j = 0; j < size; ++j) wv |= sym(t, j) << j;
+                            R(l, c, t)[0] = wv;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- final selection (listDecode :172-213): the genie path is in the list iff a root codeword equals it ----
+        const int cnt = nl[n * 2 + 0];
+        for (int t = warp; t < cnt; t += nwarps) {
+            const uint32_t *a = R(n, 0, t), *b = R(n, 0, L);
+            bool eq = true;
+            for (int w = lane; w < NW; w += 32) eq &= a[w] == b[w];
+            eq = __all_sync(0xffffffffu, eq);
+            if (lane == 0) eqf[t] = eq ? 1 : 0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int found = -1;
+            for (int t = 0; t < cnt && found < 0; ++t)
+                if (eqf[t]) found = t;
+            double maxp = prob[0], minp = prob[0];
+            for (int t = 1; t < cnt; ++t) {
+                maxp = prob[t] > maxp ? prob[t] : maxp;
+                minp = prob[t] < minp ? prob[t] : minp;
+            }
+            const double ap = misc[1];
+            int res;
+            if (found >= 0)
+                res = prob[found] == maxp ? 0 : 1;
+            else
+                res = ap > maxp ? 2 : (ap == maxp ? 3 : (ap >= minp ? 4 : 5));
+            ivars[1] = found >= 0 ? found : 0;
+            p.result[f] = res;
+            if (p.list_size) {
+                p.list_size[f] = cnt;
+                p.actual_prob[f] = ap;
+                for (int t = 0; t < L; ++t) p.list_prob[f * L + t] = t < cnt ? prob[t] : 0.0;
+            }
+        }
+        __syncthreads();
+        // information of a path = gather of T(root codeword): bit-reverse to natural order, butterfly, gather
+        const int sel = ivars[1];
+        const int npaths = p.list_info ? cnt : 1;
+        for (int pi = 0; pi < npaths; ++pi) {
+            const int t = p.list_info ? pi : sel;
+            const uint32_t *root = R(n, 0, t);
+            for (int w = warp; w < NW; w += nwarps) {
+                const int pos = 32 * w + lane;
+                uint32_t b = 0;
+                if (pos < N) {
+                    const uint32_t r = bitrev_n((uint32_t)pos, n);
+                    b = (root[r >> 5] >> (r & 31)) & 1u;
+                }
+                const uint32_t wv = __ballot_sync(0xffffffffu, b);
+                if (lane == 0) T0[w] = wv;
+            }
+            __syncthreads();
+            for (int st = 0; st < n; ++st) {
+                const int s = 1 << st;
+                for (int w = tid; w < NW; w += T) {
+                    if (s < 32) {
+                        const uint32_t m = s == 1 ? 0x55555555u : s == 2 ? 0x33333333u : s == 4 ? 0x0f0f0f0fu : s == 8 ? 0x00ff00ffu : 0x0000ffffu;
+                        T0[w] ^= (T0[w] >> s) & m;
+                    } else if (!(w & (s >> 5))) {
+                        T0[w] ^= T0[w + (s >> 5)];
+                    }
+                }
+                __syncthreads();
+            }
+            for (int j = tid; j < k; j += T) {
+                const int pos = p.info_src[j];
+                const uint8_t v = (uint8_t)((T0[pos >> 5] >> (pos & 31)) & 1u);
+                if (p.list_info) p.list_info[(f * L + pi) * k + j] = v;
+                if (t == sel) p.info[f * k + j] = v;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+struct Scl2Config {
+    int lsm, threads, grid;
+    size_t smem, vg_stride;  // vg_stride in double2 elements per CTA
+    bool ok;
+};
+
+static int env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+
+static Scl2Config scl2_config(const pc_plan *plan, int L, int64_t B) {
+    Scl2Config c{};
+    const int n = plan->n, S = L + 1;
+    c.ok = false;
+    if (plan->q != 2 || n < 1 || n > 13 || L > 32) return c;
+    const size_t budget = (size_t)env_int("PC_SCL_SMEM_KB", 74) * 1024;
+    int lsm = n - 1;
+    while (lsm > 0 && scl2_smem_bytes(n, L, lsm) > budget) --lsm;
+    const int forced = env_int("PC_SCL_LSM", -1);
+    if (forced >= 0 && forced <= n - 1) lsm = forced;
+    c.lsm = lsm;
+    c.smem = scl2_smem_bytes(n, L, lsm);
+    if (c.smem > 220 * 1024) return c;
+    c.threads = env_int("PC_SCL_THREADS", 256);
+    if (c.threads < 32 || c.threads > SCL2_MAX_THREADS || (c.threads & 31)) c.threads = 256;
+    int per_sm = (int)((227 * 1024) / (c.smem + 1024));
+    const int by_threads = 2048 / c.threads;
+    if (per_sm > by_threads) per_sm = by_threads;
+    const int forced_cps = env_int("PC_SCL_CTAS_PER_SM", 0);
+    if (forced_cps > 0 && forced_cps < per_sm) per_sm = forced_cps;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)num_sms() * per_sm;
+    if (grid > B) grid = B;
+    c.grid = (int)(grid > 0 ? grid : 1);
+    const int64_t vtot = (int64_t)((1 << n) - 2) * S, vs = (int64_t)((2 << lsm) - 2) * S;
+    c.vg_stride = (size_t)(vtot > vs ? vtot - vs : 0);
+    c.ok = true;
+    return c;
+}
+
+bool scl2_supported(const pc_plan *plan, int L) {
+    if (env_int("PC_SCL_GENERIC", 0)) return false;
+    return scl2_config(plan, L, 1).ok;
+}
+
+size_t scl2_workspace_bytes(const pc_plan *plan, int L, int64_t B) {
+    const Scl2Config c = scl2_config(plan, L, B);
+    return align256((size_t)c.grid * c.vg_stride * sizeof(double2) + 256);
+}
+
+int scl2_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_xy, const uint8_t *d_fv, const uint8_t *d_ainfo,
+                int64_t B, uint8_t *d_info, int32_t *d_res, int32_t *d_lsize, double *d_lprob, double *d_aprob,
+                uint8_t *d_linfo, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const Scl2Config c = scl2_config(plan, L, B);
+    if (!c.ok) {
+        set_error("scl2: unsupported configuration");
+        return PC_ERR_UNSUPPORTED;
+    }
+    if ((size_t)c.grid * c.vg_stride * sizeof(double2) > ws_bytes) {
+        set_error("workspace too small: %zu bytes given, %zu needed", ws_bytes, (size_t)c.grid * c.vg_stride * sizeof(double2));
+        return PC_ERR_NOMEM;
+    }
+    Scl2Params p{};
+    p.n = plan->n;
+    p.k = plan->k;
+    p.L = L;
+    p.n_ops = (int)T->ops.size();
+    p.nfrozen = plan->N - plan->k;
+    p.lsm = c.lsm;
+    p.frames = B;
+    p.ops = T->d_ops;
+    p.a_src = T->d_a_src;
+    p.f_src = T->d_f_src;
+    p.info_src = T->d_info_src;
+    p.perm = T->d_perm;
+    p.stage_mask = T->d_stage_mask;
+    p.coef_words = T->d_rep_coef_words;
+    p.xy = (const double2 *)d_xy;
+    p.fv = d_fv;
+    p.ainfo = d_ainfo;
+    p.vg = (double2 *)ws;
+    p.vg_stride = (int64_t)c.vg_stride;
+    p.info = d_info;
+    p.result = d_res;
+    p.list_size = d_lsize;
+    p.list_prob = d_lprob;
+    p.actual_prob = d_aprob;
+    p.list_info = d_linfo;
+    PC_CUDA(cudaFuncSetAttribute(scl2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    prof_mark(st);
+    scl2_kernel<<<c.grid, c.threads, c.smem, st>>>(p);
+    prof_mark(st);
+    PC_LAUNCH_CHECK();
+    return PC_OK;
+}
+
+}  // namespace pc
