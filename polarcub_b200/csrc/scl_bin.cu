@@ -63,25 +63,36 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {
     return x;
 }
 
-// keep the min(#nonzero, L) largest candidates, ascending (metric, index) -- same rule as scl.cu / the oracle
-__device__ int scl2_prune(const double *m, int C, int L, int *keep) {
+// Warp-parallel prune (:446-451 etc.): keep the ns = min(#nonzero, L) largest candidates under the total order
+// (metric, index) and list them ascending -- the same result as the streaming insertion of scl.cu / the oracle.
+// Each lane ranks the candidates c = lane, lane + 32, ... against all C (shared-memory broadcast reads).
+__device__ int scl2_prune_warp(const double *m, int C, int L, int *keep, int lane) {
     int nz = 0;
-    for (int c = 0; c < C; ++c) nz += (m[c] != 0.0);
+    for (int c = lane; c < C; c += 32) nz += (m[c] != 0.0);
+    nz = __reduce_add_sync(0xffffffffu, nz);
     const int ns = nz < L ? nz : L;
-    int cnt = 0;
-    for (int c = 0; c < C; ++c) {
-        if (cnt == ns) {
-            if (ns == 0 || !(m[c] >= m[keep[0]])) continue;
-            for (int t = 0; t + 1 < cnt; ++t) keep[t] = keep[t + 1];
-            --cnt;
+    for (int c0 = 0; c0 < C; c0 += 128) {  // four candidates per lane and pass
+        double mine[4];
+        int rank[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = c0 + lane + 32 * i;
+            mine[i] = c < C ? m[c] : 0.0;
+            rank[i] = 0;
         }
-        int t = cnt - 1;
-        while (t >= 0 && m[keep[t]] > m[c]) {
-            keep[t + 1] = keep[t];
-            --t;
+        for (int o = 0; o < C; ++o) {
+            const double v = m[o];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = c0 + lane + 32 * i;
+                rank[i] += (v > mine[i] || (v == mine[i] && o > c)) ? 1 : 0;
+            }
         }
-        keep[t + 1] = c;
-        ++cnt;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = c0 + lane + 32 * i;
+            if (c < C && rank[i] < ns) keep[ns - 1 - rank[i]] = c;
+        }
     }
     return ns;
 }
@@ -204,8 +215,10 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS) scl2_kernel(const Scl2Params
         }
         __syncthreads();
 
+        SclOp op_next = p.ops[0];
         for (int oi = 0; oi < p.n_ops; ++oi) {
-            const SclOp op = p.ops[oi];
+            const SclOp op = op_next;
+            if (oi + 1 < p.n_ops) op_next = p.ops[oi + 1];  // prefetch: the load is in flight while this op runs
             const int l = op.l, size = 1 << l, half = size >> 1, c = op.c;
             if (op.kind == OP_MINUS || op.kind == OP_PLUS) {
                 const bool plus = op.kind == OP_PLUS;
@@ -385,18 +398,13 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS) scl2_kernel(const Scl2Params
                     for (int t = lane; t < cnt; t += 32) OM(l, c)[t] = (uint8_t)t;
                 } else {
                     const int C = cnt * fs;
-                    if (lane == 0) {
-                        int no;
-                        if (C > L) {
-                            no = scl2_prune(cand, C, L, keep);
-                        } else {
-                            for (int cc = 0; cc < C; ++cc) keep[cc] = cc;
-                            no = C;
-                        }
-                        ivars[0] = no;
+                    if (C > L) {
+                        nout = scl2_prune_warp(cand, C, L, keep, lane);
+                    } else {
+                        for (int cc = lane; cc < C; cc += 32) keep[cc] = cc;
+                        nout = C;
                     }
                     __syncwarp();
-                    nout = ivars[0];
                     for (int t = lane; t < nout; t += 32) {
                         const int cidx = keep[t];
                         int src, sel;

@@ -11,13 +11,14 @@ enum : int { OP_MINUS = 0, OP_PLUS = 1, OP_COMBINE = 2, OP_RATE0 = 3, OP_REP = 4
 constexpr int SCL_LMAX = 32;
 constexpr int SCL_THREADS = 64;
 
-struct SclOp {
+struct alignas(16) SclOp {
     int8_t kind, l, c, pad;
     int32_t i;         // first u index of the node
     int32_t info_idx;  // informationVectorIndex when the node starts
     int32_t fv_idx;    // position of the frozen-values iterator when the node starts
     int32_t kpos;      // Rep: offset of the single information index inside the segment
     int32_t coef_off;  // Rep: offset into rep_coef (natural-order T(e_kpos) mod q)
+    int32_t pad2;      // 32-byte record: two 16-byte loads
     int32_t coefw_off; // Rep, q = 2: offset into rep_coef_words (REFERENCE-order T(e_kpos), bit-packed, max(1, size/32) words)
 };
 
