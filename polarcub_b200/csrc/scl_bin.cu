@@ -20,12 +20,12 @@
 
 namespace pc {
 
-constexpr int SCL2_MAX_THREADS = 512;
+constexpr int SCL2_MAX_THREADS = 256;
 
 struct Scl2Params {
     int n, k, L, n_ops, nfrozen, lsm;
     int64_t frames;
-    const SclOp *ops;
+    const uint2 *ops2;     // packed ops: x = kind | l << 3 | c << 7 | i << 8, y = fv_idx | coefw_off << 16
     const int32_t *a_src, *f_src, *info_src, *perm;
     const uint32_t *stage_mask, *coef_words;
     const double2 *xy;     // [frames][N] caller layout (reference order)
@@ -50,6 +50,7 @@ static size_t scl2_smem_bytes(int n, int L, int lsm) {
     b += (size_t)(10 * L + 4) * 8;                      // prob, cand, newprob, misc
     b += (size_t)2 * S * scl2_wsum(n + 1) * 4;          // Rw
     b += (size_t)4 * NW * 4;                            // Abits, Fbits, T0, T1
+    b += (size_t)2 * 64 * 8;                            // op window (double-buffered)
     b += (size_t)(3 * L + 3 * (n + 1) + 4) * 4;         // keep, selsrc, self, nl, nin, ivars
     b += (size_t)4 * L * 2 + L + (size_t)(n + 1) * 2 * L + L;  // pick, delta, omap, eqf
     return (b + 15) & ~(size_t)15;
@@ -71,11 +72,11 @@ __device__ int scl2_prune_warp(const double *m, int C, int L, int *keep, int lan
     for (int c = lane; c < C; c += 32) nz += (m[c] != 0.0);
     nz = __reduce_add_sync(0xffffffffu, nz);
     const int ns = nz < L ? nz : L;
-    for (int c0 = 0; c0 < C; c0 += 128) {  // four candidates per lane and pass
-        double mine[4];
-        int rank[4];
+    for (int c0 = 0; c0 < C; c0 += 64) {  // two candidates per lane and pass
+        double mine[2];
+        int rank[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
             const int c = c0 + lane + 32 * i;
             mine[i] = c < C ? m[c] : 0.0;
             rank[i] = 0;
@@ -83,13 +84,13 @@ __device__ int scl2_prune_warp(const double *m, int C, int L, int *keep, int lan
         for (int o = 0; o < C; ++o) {
             const double v = m[o];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 2; ++i) {
                 const int c = c0 + lane + 32 * i;
                 rank[i] += (v > mine[i] || (v == mine[i] && o > c)) ? 1 : 0;
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
             const int c = c0 + lane + 32 * i;
             if (c < C && rank[i] < ns) keep[ns - 1 - rank[i]] = c;
         }
@@ -97,26 +98,53 @@ __device__ int scl2_prune_warp(const double *m, int C, int L, int *keep, int lan
     return ns;
 }
 
+// d0 / ts and d1 / ts, IEEE-754 round-to-nearest, sharing the reciprocal refinement between the two quotients.
+// The instruction sequence is the one nvcc emits for a double-precision division (MUFU.RCP64H seed with low word 1,
+// two Newton steps, quotient, exact residual, final FMA), so on its validity range (tested below, a subset of the
+// compiler's own fast-path test) the results are bit-identical to `d / ts`; everything else takes the plain division.
+__device__ __forceinline__ void div2_shared(double &d0, double &d1, const double ts) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(ts));
+    y = __hiloint2double(__double2hiint(y), 1);
+    double e = __fma_rn(-ts, y, 1.0);
+    e = __fma_rn(e, e, e);
+    y = __fma_rn(y, e, y);
+    e = __fma_rn(-ts, y, 1.0);
+    y = __fma_rn(y, e, y);
+    double q0 = __dmul_rn(d0, y), q1 = __dmul_rn(d1, y);
+    q0 = __fma_rn(y, __fma_rn(-ts, q0, d0), q0);
+    q1 = __fma_rn(y, __fma_rn(-ts, q1, d1), q1);
+    const uint32_t ht = (uint32_t)__double2hiint(ts), h0 = (uint32_t)__double2hiint(d0), h1 = (uint32_t)__double2hiint(d1);
+    const uint32_t g0 = (uint32_t)__double2hiint(q0), g1 = (uint32_t)__double2hiint(q1);
+    // operands and quotients positive, finite, normal with margin (exponent fields in [0x036, 0x7fe], divisor [0x100, 0x6ff])
+    const bool ok = (ht - 0x10000000u) < 0x60000000u && (h0 - 0x03600000u) < 0x7c900000u && (h1 - 0x03600000u) < 0x7c900000u &&
+                    (g0 - 0x00200000u) < 0x7fc00000u && (g1 - 0x00200000u) < 0x7fc00000u;
+    if (ok) {
+        d0 = q0;
+        d1 = q1;
+    } else {
+        d0 = d0 / ts;
+        d1 = d1 / ts;
+    }
+}
+
 // one f / g node update, QaryMemorylessVectorDistribution.py:36-42 / :56-62 + sum-normalisation :104-118, q = 2
 __device__ __forceinline__ double2 node_update(const double2 a, const double2 b, const bool plus, const uint32_t u1) {
     double d0, d1;
     if (!plus) {
-        d0 = __dadd_rn(__dadd_rn(0.0, __dmul_rn(a.x, b.x)), __dmul_rn(a.y, b.y));
-        d1 = __dadd_rn(__dadd_rn(0.0, __dmul_rn(a.x, b.y)), __dmul_rn(a.y, b.x));
+        d0 = __dadd_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y));
+        d1 = __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x));
     } else {
         const double a0 = u1 ? a.y : a.x, a1 = u1 ? a.x : a.y;
-        d0 = __dadd_rn(0.0, __dmul_rn(a0, b.x));
-        d1 = __dadd_rn(0.0, __dmul_rn(a1, b.y));
+        d0 = __dmul_rn(a0, b.x);
+        d1 = __dmul_rn(a1, b.y);
     }
-    const double ts = __dadd_rn(__dadd_rn(0.0, d0), d1);
-    if (ts != 0.0) {
-        d0 = d0 / ts;
-        d1 = d1 / ts;
-    }
+    const double ts = __dadd_rn(d0, d1);
+    if (ts != 0.0) div2_shared(d0, d1, ts);
     return make_double2(d0, d1);
 }
 
-__global__ void __launch_bounds__(SCL2_MAX_THREADS) scl2_kernel(const Scl2Params p) {
+__global__ void __launch_bounds__(SCL2_MAX_THREADS, 3) scl2_kernel(const Scl2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, N = 1 << n, L = p.L, S = L + 1, k = p.k, lsm = p.lsm;
     const int NW = N >= 32 ? N >> 5 : 1;
@@ -131,7 +159,8 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS) scl2_kernel(const Scl2Params
     uint32_t *Rw = (uint32_t *)(misc + 4);
     uint32_t *Abits = Rw + 2 * S * scl2_wsum(n + 1);
     uint32_t *Fbits = Abits + NW, *T0 = Fbits + NW, *T1 = T0 + NW;
-    int *keep = (int *)(T1 + NW);
+    uint2 *opw = (uint2 *)(T1 + NW);  // [2][64]; 8-byte aligned: everything before is a multiple of 8 bytes
+    int *keep = (int *)(opw + 128);
     int *selsrc = keep + L, *selfk = selsrc + L;
     int *nl = selfk + L;          // [(n+1)][2]
     int *nin = nl + 2 * (n + 1);  // [n+1]
@@ -213,33 +242,60 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS) scl2_kernel(const Scl2Params
             nin[n] = 1;
             nl[n * 2 + 0] = 1;
         }
+        if (tid < 64 && tid < p.n_ops) opw[tid] = p.ops2[tid];
         __syncthreads();
 
-        SclOp op_next = p.ops[0];
+        uint2 op_pre = make_uint2(0u, 0u);
         for (int oi = 0; oi < p.n_ops; ++oi) {
-            const SclOp op = op_next;
-            if (oi + 1 < p.n_ops) op_next = p.ops[oi + 1];  // prefetch: the load is in flight while this op runs
-            const int l = op.l, size = 1 << l, half = size >> 1, c = op.c;
-            if (op.kind == OP_MINUS || op.kind == OP_PLUS) {
-                const bool plus = op.kind == OP_PLUS;
+            // ops stream through a double-buffered 64-entry shared-memory window; the next window's global load is
+            // issued at the start of the current one and lands in shared memory 63 ops later
+            const int wi = oi & 63, buf = (oi >> 6) & 1;
+            if (tid < 64) {
+                if (wi == 0 && oi + 64 + tid < p.n_ops) op_pre = p.ops2[oi + 64 + tid];
+                if (wi == 63) opw[(buf ^ 1) * 64 + tid] = op_pre;
+            }
+            const uint2 opk = opw[buf * 64 + wi];
+            const int kind = opk.x & 7, l = (opk.x >> 3) & 15, c = (opk.x >> 7) & 1, i0 = (int)(opk.x >> 8);
+            const int size = 1 << l, half = size >> 1;
+            if (kind == OP_MINUS || kind == OP_PLUS) {
+                const bool plus = kind == OP_PLUS;
                 const int cnt = plus ? nl[(l - 1) * 2 + 0] : nin[l];
                 const int total = (cnt + 1) << (l - 1);
                 const uint8_t *om = OM(l - 1, 0);
-                for (int idx = tid; idx < total; idx += T) {
+                const double2 *sbase = l == n ? xyf : (l <= lsm ? Vs : vg - VS) + ((1 << l) - 2) * S;
+                double2 *dbase = (l - 1 <= lsm ? Vs : vg - VS) + ((1 << (l - 1)) - 2) * S;
+                const uint32_t *rb = R(l - 1, 0, 0);
+                const int rw = scl2_W(l - 1);
+                auto item = [&](int idx, double2 &a, double2 &b, uint32_t &u1, double2 *&dst) {
                     const int t = idx >> (l - 1), h = idx & (half - 1);
                     const int slot = t == cnt ? L : t;
                     const int src = t == cnt ? L : (plus ? (int)om[t] : t);
-                    const double2 *P = vsel(l, src);
-                    const double2 a = P[2 * h], b = P[2 * h + 1];
-                    uint32_t u1 = 0;
-                    if (plus) u1 = (R(l - 1, 0, slot)[h >> 5] >> (h & 31)) & 1u;
-                    vout(l - 1, slot)[h] = node_update(a, b, plus, u1);
+                    const double2 *P = sbase + (l == n ? 0 : (src << l));  // the channel level is shared by all paths
+                    a = P[2 * h];
+                    b = P[2 * h + 1];
+                    u1 = plus ? (rb[slot * rw + (h >> 5)] >> (h & 31)) & 1u : 0u;
+                    dst = dbase + (slot << (l - 1)) + h;
+                };
+                int idx = tid;
+                for (; idx + T < total; idx += 2 * T) {  // two independent items in flight per thread
+                    double2 a0, b0, a1, b1, *o0, *o1;
+                    uint32_t u0, u1;
+                    item(idx, a0, b0, u0, o0);
+                    item(idx + T, a1, b1, u1, o1);
+                    *o0 = node_update(a0, b0, plus, u0);
+                    *o1 = node_update(a1, b1, plus, u1);
+                }
+                if (idx < total) {
+                    double2 a0, b0, *o0;
+                    uint32_t u0;
+                    item(idx, a0, b0, u0, o0);
+                    *o0 = node_update(a0, b0, plus, u0);
                 }
                 if (tid == 0) nin[l - 1] = cnt;
                 __syncthreads();
                 continue;
             }
-            if (op.kind == OP_COMBINE) {  // :726-754 in reference order: out[2h] = m[h] + p[h], out[2h+1] = -p[h]
+            if (kind == OP_COMBINE) {  // :726-754 in reference order: out[2h] = m[h] + p[h], out[2h+1] = -p[h]
                 const int cnt = nl[(l - 1) * 2 + 1];
                 const int Wo = scl2_W(l);
                 const uint8_t *om1 = OM(l - 1, 1), *om0 = OM(l - 1, 0);
@@ -259,16 +315,27 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS) scl2_kernel(const Scl2Params
             }
             // ------------------------------- fast nodes ------------------------------------------------------
             const int cnt = nin[l];
-            const int i0 = op.i;
-            const bool spc = op.kind == OP_SPC;
+            const bool spc = kind == OP_SPC;
             const int nfork = spc ? 3 : 2, npick = spc ? 4 : 2;
-            const int fs = op.kind == OP_REP ? 2 : (spc ? 8 : 4);
-            const uint32_t *coefw = p.coef_words + op.coefw_off;
+            const int fs = kind == OP_REP ? 2 : (spc ? 8 : 4);
+            const uint32_t *coefw = p.coef_words + (opk.y >> 16);
             auto abit = [&](int j) -> uint32_t { return (Abits[(i0 + j) >> 5] >> ((i0 + j) & 31)) & 1u; };
             auto fbit = [&](int j) -> uint32_t { return (Fbits[(i0 + j) >> 5] >> ((i0 + j) & 31)) & 1u; };
+            // Rate-1 / SPC: reliabilities (second-largest / largest, :763-768) of every (path, element) with all threads;
+            // they are parked in the dead level l-1 region of the path vectors (S 2^(l-1) float64 pairs >= cnt 2^l doubles)
+            double *scr = nullptr;
+            if ((kind == OP_RATE1 || spc) && l >= 2) {
+                scr = (double *)((l - 1 <= lsm ? Vs : vg - VS) + ((1 << (l - 1)) - 2) * S);
+                for (int idx = tid; idx < (cnt << l); idx += T) {
+                    const double2 v2 = vsel(l, idx >> l)[idx & (size - 1)];
+                    const double m1 = v2.y > v2.x ? v2.y : v2.x, m2 = v2.y > v2.x ? v2.x : v2.y;
+                    scr[idx] = m2 / m1;
+                }
+                __syncthreads();
+            }
             if (warp == 0) {
                 // ---- phase 1: order-dependent products, one job per lane ------------------------------------
-                if (op.kind == OP_RATE0) {  // :495-518
+                if (kind == OP_RATE0) {  // :495-518
                     for (int job = lane; job <= cnt; job += 32) {
                         const bool act = job == cnt;
                         const double2 *P = vsel(l, act ? L : job);
@@ -283,7 +350,7 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS) scl2_kernel(const Scl2Params
                         else
                             newprob[job] = __dmul_rn(prob[job], pr);
                     }
-                } else if (op.kind == OP_REP) {  // :521-578
+                } else if (kind == OP_REP) {  // :521-578
                     for (int job = lane; job <= 2 * cnt; job += 32) {
                         const bool act = job == 2 * cnt;
                         const int s = act ? 0 : job / cnt, t = act ? 0 : job - s * cnt;
@@ -305,7 +372,7 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS) scl2_kernel(const Scl2Params
                             cand[s * cnt + t] = __dmul_rn(prob[t], pr);
                     }
                 } else {  // Rate-1 :581-628 and SPC :631-682
-                    const int fval = spc ? fvf[op.fv_idx] : 0;
+                    const int fval = spc ? fvf[opk.y & 0xffffu] : 0;
                     for (int job = lane; job <= cnt; job += 32) {
                         if (job == cnt) {
                             const double2 *P = vsel(l, L);
@@ -321,35 +388,45 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS) scl2_kernel(const Scl2Params
                         const int t = job;
                         const double2 *P = vsel(l, t);
                         // pickLeastReliableIndices (:759-768): the npick largest (score, j), ascending
-                        double sc[4] = {-1.0, -1.0, -1.0, -1.0};
-                        int sj[4] = {0, 0, 0, 0};
+                        // sc0 <= sc1 (<= sc2 <= sc3): ascending; ties go to the later index (>=), as in the streaming form
+                        double sc0 = -1.0, sc1 = -1.0, sc2 = -1.0, sc3 = -1.0;
+                        int sj0 = 0, sj1 = 0, sj2 = 0, sj3 = 0;
                         for (int j = 0; j < size; ++j) {
-                            const double2 v2 = P[j];
-                            double m1 = -1.0, m2 = -1.0;
-                            if (v2.x > m1) {
-                                m2 = m1;
-                                m1 = v2.x;
-                            } else if (v2.x > m2) {
-                                m2 = v2.x;
+                            double s;
+                            if (scr) {
+                                s = scr[(t << l) + j];
+                            } else {
+                                const double2 v2 = P[j];
+                                const double m1 = v2.y > v2.x ? v2.y : v2.x, m2 = v2.y > v2.x ? v2.x : v2.y;
+                                s = m2 / m1;
                             }
-                            if (v2.y > m1) {
-                                m2 = m1;
-                                m1 = v2.y;
-                            } else if (v2.y > m2) {
-                                m2 = v2.y;
-                            }
-                            const double s = m2 / m1;
-                            if (s >= sc[0]) {
-                                int w = 0;
-                                while (w + 1 < npick && s >= sc[w + 1]) {
-                                    sc[w] = sc[w + 1];
-                                    sj[w] = sj[w + 1];
-                                    ++w;
+                            if (!spc) {
+                                if (s >= sc1) {
+                                    sc0 = sc1, sj0 = sj1;
+                                    sc1 = s, sj1 = j;
+                                } else if (s >= sc0) {
+                                    sc0 = s, sj0 = j;
                                 }
-                                sc[w] = s;
-                                sj[w] = j;
+                            } else if (s >= sc0) {
+                                if (s >= sc1) {
+                                    sc0 = sc1, sj0 = sj1;
+                                    if (s >= sc2) {
+                                        sc1 = sc2, sj1 = sj2;
+                                        if (s >= sc3) {
+                                            sc2 = sc3, sj2 = sj3;
+                                            sc3 = s, sj3 = j;
+                                        } else {
+                                            sc2 = s, sj2 = j;
+                                        }
+                                    } else {
+                                        sc1 = s, sj1 = j;
+                                    }
+                                } else {
+                                    sc0 = s, sj0 = j;
+                                }
                             }
                         }
+                        const int sj[4] = {sj0, sj1, sj2, sj3};
                         int sumconst = 0;
                         bool first = true;
                         double prodmax = 1.0;
@@ -394,7 +471,7 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS) scl2_kernel(const Scl2Params
                 __syncwarp();
                 // ---- phase 2: prune, lazy copy (omap), normalise ---------------------------------------------
                 int nout = cnt;
-                if (op.kind == OP_RATE0) {
+                if (kind == OP_RATE0) {
                     for (int t = lane; t < cnt; t += 32) OM(l, c)[t] = (uint8_t)t;
                 } else {
                     const int C = cnt * fs;
@@ -408,7 +485,7 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS) scl2_kernel(const Scl2Params
                     for (int t = lane; t < nout; t += 32) {
                         const int cidx = keep[t];
                         int src, sel;
-                        if (op.kind == OP_REP) {
+                        if (kind == OP_REP) {
                             sel = cidx / cnt;
                             src = cidx - sel * cnt;
                         } else {
@@ -443,11 +520,11 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS) scl2_kernel(const Scl2Params
                     return size >= 32 ? bits[(i0 >> 5) + w] : ((bits[i0 >> 5] >> (i0 & 31)) & smask);
                 };
                 for (int w = tid; w < Wl; w += T) R(l, c, L)[w] = slice(Abits, w);
-                if (op.kind == OP_RATE0 || op.kind == OP_REP) {
+                if (kind == OP_RATE0 || kind == OP_REP) {
                     for (int idx = tid; idx < nout * Wl; idx += T) {
                         const int t = idx / Wl, w = idx - t * Wl;
                         uint32_t v = slice(Fbits, w);
-                        if (op.kind == OP_REP && selfk[t]) v ^= coefw[w];
+                        if (kind == OP_REP && selfk[t]) v ^= coefw[w];
                         R(l, c, t)[w] = v;
                     }
                 } else {
@@ -625,7 +702,7 @@ int scl2_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_
     p.nfrozen = plan->N - plan->k;
     p.lsm = c.lsm;
     p.frames = B;
-    p.ops = T->d_ops;
+    p.ops2 = T->d_ops2;
     p.a_src = T->d_a_src;
     p.f_src = T->d_f_src;
     p.info_src = T->d_info_src;
