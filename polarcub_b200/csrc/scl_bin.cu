@@ -24,6 +24,7 @@ constexpr int SCL2_MAX_THREADS = 256;
 
 struct Scl2Params {
     int n, k, L, n_ops, nfrozen, lsm;
+    int rgl;               // path codewords of levels >= rgl live in the global scratch `rg`, smaller levels in shared memory
     int64_t frames;
     const uint2 *ops2;     // packed ops: x = kind | l << 3 | c << 7 | i << 8, y = fv_idx | coefw_off << 16
     const int32_t *a_src, *f_src, *info_src, *perm;
@@ -33,6 +34,8 @@ struct Scl2Params {
     const uint8_t *ainfo;  // [frames][k]
     double2 *vg;           // [grid][vg_stride] scratch for levels > lsm
     int64_t vg_stride;
+    uint32_t *rg;          // [grid][rg_stride]
+    int64_t rg_stride;
     uint8_t *info;         // [frames][k]
     int32_t *result;       // [frames]
     int32_t *list_size;    // optional, caller layouts
@@ -44,11 +47,11 @@ __host__ __device__ inline int scl2_W(int l) { return l <= 5 ? 1 : 1 << (l - 5);
 __host__ __device__ inline int scl2_wsum(int l) { return l <= 6 ? l - 1 : 3 + (1 << (l - 5)); }  // sum of W(1..l-1)
 
 // shared-memory bytes of the kernel for (n, L, lsm); mirrors the carve-up at the top of the kernel
-static size_t scl2_smem_bytes(int n, int L, int lsm) {
+static size_t scl2_smem_bytes(int n, int L, int lsm, int rgl) {
     const int S = L + 1, N = 1 << n, NW = N >= 32 ? N >> 5 : 1;
     size_t b = (size_t)((2 << lsm) - 2) * S * 16;       // Vs
-    b += (size_t)(10 * L + 4) * 8;                      // prob, cand, newprob, misc
-    b += (size_t)2 * S * scl2_wsum(n + 1) * 4;          // Rw
+    b += (size_t)(11 * L + 4) * 8;                      // prob, cand, newprob, misc, basep
+    b += (size_t)2 * S * scl2_wsum(rgl < n + 1 ? rgl : n + 1) * 4;  // Rw (levels < rgl)
     b += (size_t)4 * NW * 4;                            // Abits, Fbits, T0, T1
     b += (size_t)2 * 64 * 8;                            // op window (double-buffered)
     b += (size_t)(3 * L + 3 * (n + 1) + 4) * 4;         // keep, selsrc, self, nl, nin, ivars
@@ -62,40 +65,6 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {
     x = (x | (x << 2)) & 0x33333333u;
     x = (x | (x << 1)) & 0x55555555u;
     return x;
-}
-
-// Warp-parallel prune (:446-451 etc.): keep the ns = min(#nonzero, L) largest candidates under the total order
-// (metric, index) and list them ascending -- the same result as the streaming insertion of scl.cu / the oracle.
-// Each lane ranks the candidates c = lane, lane + 32, ... against all C (shared-memory broadcast reads).
-__device__ int scl2_prune_warp(const double *m, int C, int L, int *keep, int lane) {
-    int nz = 0;
-    for (int c = lane; c < C; c += 32) nz += (m[c] != 0.0);
-    nz = __reduce_add_sync(0xffffffffu, nz);
-    const int ns = nz < L ? nz : L;
-    for (int c0 = 0; c0 < C; c0 += 64) {  // two candidates per lane and pass
-        double mine[2];
-        int rank[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int c = c0 + lane + 32 * i;
-            mine[i] = c < C ? m[c] : 0.0;
-            rank[i] = 0;
-        }
-        for (int o = 0; o < C; ++o) {
-            const double v = m[o];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int c = c0 + lane + 32 * i;
-                rank[i] += (v > mine[i] || (v == mine[i] && o > c)) ? 1 : 0;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int c = c0 + lane + 32 * i;
-            if (c < C && rank[i] < ns) keep[ns - 1 - rank[i]] = c;
-        }
-    }
-    return ns;
 }
 
 // d0 / ts and d1 / ts, IEEE-754 round-to-nearest, sharing the reciprocal refinement between the two quotients.
@@ -156,8 +125,11 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS, 3) scl2_kernel(const Scl2Par
     double *cand = prob + L;
     double *newprob = cand + 8 * L;
     double *misc = newprob + L;  // [0] genie product of the node, [1] actual_prob
-    uint32_t *Rw = (uint32_t *)(misc + 4);
-    uint32_t *Abits = Rw + 2 * S * scl2_wsum(n + 1);
+    double *basep = misc + 4;    // [L] Rate-1 / SPC: prob[t] * product of the non-forked maxima
+    uint32_t *Rw = (uint32_t *)(basep + L);
+    const int rgl = p.rgl < n + 1 ? p.rgl : n + 1;
+    uint32_t *Abits = Rw + 2 * S * scl2_wsum(rgl);
+    uint32_t *rgc = p.rg + (int64_t)blockIdx.x * p.rg_stride - 2 * S * scl2_wsum(rgl);
     uint32_t *Fbits = Abits + NW, *T0 = Fbits + NW, *T1 = T0 + NW;
     uint2 *opw = (uint2 *)(T1 + NW);  // [2][64]; 8-byte aligned: everything before is a multiple of 8 bytes
     int *keep = (int *)(opw + 128);
@@ -171,7 +143,9 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS, 3) scl2_kernel(const Scl2Par
     uint8_t *eqf = omap + (n + 1) * 2 * L;   // [L]
 
     double2 *vg = p.vg + (int64_t)blockIdx.x * p.vg_stride;
-    auto R = [&](int l, int c, int slot) -> uint32_t * { return Rw + 2 * S * scl2_wsum(l) + (c * S + slot) * scl2_W(l); };
+    auto R = [&](int l, int c, int slot) -> uint32_t * {
+        return (l < rgl ? Rw : rgc) + 2 * S * scl2_wsum(l) + (c * S + slot) * scl2_W(l);
+    };
     auto OM = [&](int l, int c) -> uint8_t * { return omap + (l * 2 + c) * L; };
 
     for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
@@ -276,20 +250,41 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS, 3) scl2_kernel(const Scl2Par
                     u1 = plus ? (rb[slot * rw + (h >> 5)] >> (h & 31)) & 1u : 0u;
                     dst = dbase + (slot << (l - 1)) + h;
                 };
-                int idx = tid;
-                for (; idx + T < total; idx += 2 * T) {  // two independent items in flight per thread
-                    double2 a0, b0, a1, b1, *o0, *o1;
-                    uint32_t u0, u1;
-                    item(idx, a0, b0, u0, o0);
-                    item(idx + T, a1, b1, u1, o1);
-                    *o0 = node_update(a0, b0, plus, u0);
-                    *o1 = node_update(a1, b1, plus, u1);
-                }
-                if (idx < total) {
-                    double2 a0, b0, *o0;
-                    uint32_t u0;
-                    item(idx, a0, b0, u0, o0);
-                    *o0 = node_update(a0, b0, plus, u0);
+                if (half >= 2 * T) {
+                    // large level: path-major, per-path pointers hoisted, two independent elements in flight per thread
+                    for (int t = 0; t <= cnt; ++t) {
+                        const int slot = t == cnt ? L : t;
+                        const int src = t == cnt ? L : (plus ? (int)om[t] : t);
+                        const double2 *P = sbase + (l == n ? 0 : (src << l));
+                        double2 *D = dbase + (slot << (l - 1));
+                        const uint32_t *rp = rb + slot * rw;
+                        for (int h = tid; h < half; h += 2 * T) {
+                            const double2 a0 = P[2 * h], b0 = P[2 * h + 1], a1 = P[2 * (h + T)], b1 = P[2 * (h + T) + 1];
+                            uint32_t u0 = 0, u1 = 0;
+                            if (plus) {
+                                u0 = (rp[h >> 5] >> (h & 31)) & 1u;
+                                u1 = (rp[(h + T) >> 5] >> (h & 31)) & 1u;
+                            }
+                            D[h] = node_update(a0, b0, plus, u0);
+                            D[h + T] = node_update(a1, b1, plus, u1);
+                        }
+                    }
+                } else {
+                    int idx = tid;
+                    for (; idx + T < total; idx += 2 * T) {
+                        double2 a0, b0, a1, b1, *o0, *o1;
+                        uint32_t u0, u1;
+                        item(idx, a0, b0, u0, o0);
+                        item(idx + T, a1, b1, u1, o1);
+                        *o0 = node_update(a0, b0, plus, u0);
+                        *o1 = node_update(a1, b1, plus, u1);
+                    }
+                    if (idx < total) {
+                        double2 a0, b0, *o0;
+                        uint32_t u0;
+                        item(idx, a0, b0, u0, o0);
+                        *o0 = node_update(a0, b0, plus, u0);
+                    }
                 }
                 if (tid == 0) nin[l - 1] = cnt;
                 __syncthreads();
@@ -319,8 +314,24 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS, 3) scl2_kernel(const Scl2Par
             const int nfork = spc ? 3 : 2, npick = spc ? 4 : 2;
             const int fs = kind == OP_REP ? 2 : (spc ? 8 : 4);
             const uint32_t *coefw = p.coef_words + (opk.y >> 16);
-            auto abit = [&](int j) -> uint32_t { return (Abits[(i0 + j) >> 5] >> ((i0 + j) & 31)) & 1u; };
-            auto fbit = [&](int j) -> uint32_t { return (Fbits[(i0 + j) >> 5] >> ((i0 + j) & 31)) & 1u; };
+            // bits [32 w, 32 w + 32) of the node-local codeword slices (reference order; i0 is a multiple of the node size)
+            auto aword = [&](int w) -> uint32_t { return size >= 32 ? Abits[(i0 >> 5) + w] : (Abits[i0 >> 5] >> (i0 & 31)); };
+            auto fword = [&](int w) -> uint32_t { return size >= 32 ? Fbits[(i0 >> 5) + w] : (Fbits[i0 >> 5] >> (i0 & 31)); };
+            // left-to-right product of P[j].{x|y} selected by the bits of getw (np.product order, :503-509 etc.)
+            auto chain = [&](const double2 *P, auto getw) -> double {
+                double pr = 1.0;
+                for (int w0 = 0; w0 < size; w0 += 32) {
+                    const uint32_t bits = getw(w0 >> 5);
+                    const int m = size - w0 < 32 ? size - w0 : 32;
+#pragma unroll 4
+                    for (int b = 0; b < m; ++b) {
+                        const double2 v2 = P[w0 + b];
+                        const double v = (bits >> b) & 1u ? v2.y : v2.x;
+                        pr = (w0 + b) == 0 ? v : __dmul_rn(pr, v);
+                    }
+                }
+                return pr;
+            };
             // Rate-1 / SPC: reliabilities (second-largest / largest, :763-768) of every (path, element) with all threads;
             // they are parked in the dead level l-1 region of the path vectors (S 2^(l-1) float64 pairs >= cnt 2^l doubles)
             double *scr = nullptr;
@@ -333,18 +344,12 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS, 3) scl2_kernel(const Scl2Par
                 }
                 __syncthreads();
             }
+            // ---- phase 1 (warp 0, one job per lane): the order-dependent float64 products ---------------------------
             if (warp == 0) {
-                // ---- phase 1: order-dependent products, one job per lane ------------------------------------
                 if (kind == OP_RATE0) {  // :495-518
                     for (int job = lane; job <= cnt; job += 32) {
                         const bool act = job == cnt;
-                        const double2 *P = vsel(l, act ? L : job);
-                        double pr = 1.0;
-                        for (int j = 0; j < size; ++j) {
-                            const double2 v2 = P[j];
-                            const double v = (act ? abit(j) : fbit(j)) ? v2.y : v2.x;
-                            pr = j == 0 ? v : __dmul_rn(pr, v);
-                        }
+                        const double pr = act ? chain(vsel(l, L), aword) : chain(vsel(l, job), fword);
                         if (act)
                             misc[0] = pr;
                         else
@@ -354,18 +359,9 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS, 3) scl2_kernel(const Scl2Par
                     for (int job = lane; job <= 2 * cnt; job += 32) {
                         const bool act = job == 2 * cnt;
                         const int s = act ? 0 : job / cnt, t = act ? 0 : job - s * cnt;
-                        const double2 *P = vsel(l, act ? L : t);
-                        double pr = 1.0;
-                        for (int j = 0; j < size; ++j) {
-                            const double2 v2 = P[j];
-                            uint32_t b;
-                            if (act)
-                                b = abit(j);
-                            else
-                                b = fbit(j) ^ (s ? (coefw[j >> 5] >> (j & 31)) & 1u : 0u);
-                            const double v = b ? v2.y : v2.x;
-                            pr = j == 0 ? v : __dmul_rn(pr, v);
-                        }
+                        const uint32_t sm = s ? 0xffffffffu : 0u;
+                        const double pr = act ? chain(vsel(l, L), aword)
+                                              : chain(vsel(l, t), [&](int w) -> uint32_t { return fword(w) ^ (coefw[w] & sm); });
                         if (act)
                             misc[0] = pr;
                         else
@@ -375,20 +371,13 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS, 3) scl2_kernel(const Scl2Par
                     const int fval = spc ? fvf[opk.y & 0xffffu] : 0;
                     for (int job = lane; job <= cnt; job += 32) {
                         if (job == cnt) {
-                            const double2 *P = vsel(l, L);
-                            double pr = 1.0;
-                            for (int j = 0; j < size; ++j) {
-                                const double2 v2 = P[j];
-                                const double v = abit(j) ? v2.y : v2.x;
-                                pr = j == 0 ? v : __dmul_rn(pr, v);
-                            }
-                            misc[0] = pr;
+                            misc[0] = chain(vsel(l, L), aword);
                             continue;
                         }
                         const int t = job;
                         const double2 *P = vsel(l, t);
-                        // pickLeastReliableIndices (:759-768): the npick largest (score, j), ascending
-                        // sc0 <= sc1 (<= sc2 <= sc3): ascending; ties go to the later index (>=), as in the streaming form
+                        // pickLeastReliableIndices (:759-768): the npick largest (score, j), ascending;
+                        // sc0 <= sc1 (<= sc2 <= sc3), ties go to the later index (>=), as in the streaming form
                         double sc0 = -1.0, sc1 = -1.0, sc2 = -1.0, sc3 = -1.0;
                         int sj0 = 0, sj1 = 0, sj2 = 0, sj3 = 0;
                         for (int j = 0; j < size; ++j) {
@@ -426,64 +415,93 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS, 3) scl2_kernel(const Scl2Par
                                 }
                             }
                         }
-                        const int sj[4] = {sj0, sj1, sj2, sj3};
                         int sumconst = 0;
                         bool first = true;
                         double prodmax = 1.0;
                         for (int j = 0; j < size; ++j) {
-                            bool forked = false;
-                            for (int w = 0; w < npick; ++w) forked |= (sj[w] == j);
+                            bool forked = j == sj0 || j == sj1;
+                            if (spc) forked |= j == sj2 || j == sj3;
                             if (forked) continue;
                             const double2 v2 = P[j];
-                            double mv = v2.x;
-                            int am = 0;
-                            if (v2.y > mv) {
-                                mv = v2.y;
-                                am = 1;
-                            }
-                            sumconst += am;
+                            const bool one = v2.y > v2.x;
+                            const double mv = one ? v2.y : v2.x;
+                            sumconst += one ? 1 : 0;
                             prodmax = first ? mv : __dmul_rn(prodmax, mv);
                             first = false;
                         }
-                        const double base_prob = __dmul_rn(prob[t], prodmax);
-                        for (int w = 0; w < npick; ++w) pick[t * 4 + w] = (int16_t)sj[w];
-                        const int dl = (fval ^ sumconst) & 1;
-                        delta[t] = (uint8_t)dl;
-                        for (int fk = 0; fk < fs; ++fk) {
-                            double pf = 1.0;
-                            int sf = 0;
-                            for (int w = 0; w < nfork; ++w) {
-                                const int dg = (fk >> (nfork - 1 - w)) & 1;
-                                const double2 v2 = P[sj[w]];
-                                const double v = dg ? v2.y : v2.x;
-                                pf = w == 0 ? v : __dmul_rn(pf, v);
-                                sf += dg;
-                            }
-                            if (spc) {
-                                const int dep = (dl ^ sf) & 1;
-                                const double2 v2 = P[sj[3]];
-                                pf = __dmul_rn(pf, dep ? v2.y : v2.x);
-                            }
-                            cand[t * fs + fk] = __dmul_rn(pf, base_prob);
-                        }
+                        basep[t] = __dmul_rn(prob[t], prodmax);
+                        pick[t * 4 + 0] = (int16_t)sj0;
+                        pick[t * 4 + 1] = (int16_t)sj1;
+                        pick[t * 4 + 2] = (int16_t)sj2;
+                        pick[t * 4 + 3] = (int16_t)sj3;
+                        delta[t] = (uint8_t)((fval ^ sumconst) & 1);
                     }
                 }
-                __syncwarp();
-                // ---- phase 2: prune, lazy copy (omap), normalise ---------------------------------------------
+            }
+            __syncthreads();
+            const int C = kind == OP_RATE0 ? 0 : cnt * fs;
+            if (kind == OP_RATE1 || spc) {
+                // candidate metrics (forkIndices / forkIndicesSpc, :770-820), one (path, fork) per thread
+                for (int idx = tid; idx < C; idx += T) {
+                    const int t = idx / fs, fk = idx - t * fs;
+                    const double2 *P = vsel(l, t);
+                    const int16_t *pk = pick + t * 4;
+                    double pf = 1.0;
+                    int sf = 0;
+                    for (int w = 0; w < nfork; ++w) {
+                        const int dg = (fk >> (nfork - 1 - w)) & 1;
+                        const double2 v2 = P[pk[w]];
+                        const double v = dg ? v2.y : v2.x;
+                        pf = w == 0 ? v : __dmul_rn(pf, v);
+                        sf += dg;
+                    }
+                    if (spc) {
+                        const int dep = (delta[t] ^ sf) & 1;
+                        const double2 v2 = P[pk[3]];
+                        pf = __dmul_rn(pf, dep ? v2.y : v2.x);
+                    }
+                    cand[idx] = __dmul_rn(pf, basep[t]);
+                }
+                __syncthreads();
+            }
+            // ---- prune (:446-451 etc.): keep the ns = min(#nonzero, L) largest candidates under the total order
+            // (metric, index), listed ascending -- the same result as the streaming insertion of scl.cu / the oracle.
+            // All threads: a group of G consecutive lanes ranks one candidate against all C.
+            if (C > L) {
+                int G = 32;  // lanes per candidate: a power of two, so a group never straddles a warp
+                while (G > 1 && G * C > T) G >>= 1;
+                const int cpp = T / G;            // candidates per pass
+                const int per = (C + G - 1) / G;  // candidates scanned per lane
+                for (int c0 = 0; c0 < C; c0 += cpp) {  // uniform trip count (shuffles inside)
+                    const int c = c0 + tid / G, part = tid & (G - 1);
+                    const bool live = c < C;
+                    const double mine = live ? cand[c] : 0.0;
+                    int rank = 0, nz = 0;
+                    const int o1 = (part + 1) * per < C ? (part + 1) * per : C;
+                    for (int o = part * per; o < o1; ++o) {
+                        const double v = cand[o];
+                        rank += (v > mine || (v == mine && o > c)) ? 1 : 0;
+                        nz += v != 0.0 ? 1 : 0;
+                    }
+                    for (int sh = 1; sh < G; sh <<= 1) {
+                        rank += __shfl_xor_sync(0xffffffffu, rank, sh);
+                        nz += __shfl_xor_sync(0xffffffffu, nz, sh);
+                    }
+                    const int ns = nz < L ? nz : L;
+                    if (live && part == 0 && rank < ns) keep[ns - 1 - rank] = c;
+                    if (c == 0 && part == 0) ivars[0] = ns;
+                }
+                __syncthreads();
+            }
+            // ---- phase 2 (warp 0): lazy copy (omap), normalise (:867-872) ------------------------------------------
+            if (warp == 0) {
                 int nout = cnt;
                 if (kind == OP_RATE0) {
                     for (int t = lane; t < cnt; t += 32) OM(l, c)[t] = (uint8_t)t;
                 } else {
-                    const int C = cnt * fs;
-                    if (C > L) {
-                        nout = scl2_prune_warp(cand, C, L, keep, lane);
-                    } else {
-                        for (int cc = lane; cc < C; cc += 32) keep[cc] = cc;
-                        nout = C;
-                    }
-                    __syncwarp();
+                    nout = C > L ? ivars[0] : C;
                     for (int t = lane; t < nout; t += 32) {
-                        const int cidx = keep[t];
+                        const int cidx = C > L ? keep[t] : t;
                         int src, sel;
                         if (kind == OP_REP) {
                             sel = cidx / cnt;
@@ -499,10 +517,14 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS, 3) scl2_kernel(const Scl2Par
                     }
                 }
                 __syncwarp();
-                double mx = newprob[0];
-                for (int t = 1; t < nout; ++t) {
+                double mx = lane < nout ? newprob[lane] : newprob[0];
+                for (int t = lane + 32; t < nout; t += 32) {
                     const double v = newprob[t];
                     if (v > mx) mx = v;
+                }
+                for (int sh = 16; sh > 0; sh >>= 1) {
+                    const double o = __shfl_xor_sync(0xffffffffu, mx, sh);
+                    if (o > mx) mx = o;
                 }
                 for (int t = lane; t < nout; t += 32) prob[t] = newprob[t] / mx;
                 if (lane == 0) {
@@ -632,8 +654,8 @@ __global__ void __launch_bounds__(SCL2_MAX_THREADS, 3) scl2_kernel(const Scl2Par
 
 // ---- host side ------------------------------------------------------------------------------------------------
 struct Scl2Config {
-    int lsm, threads, grid;
-    size_t smem, vg_stride;  // vg_stride in double2 elements per CTA
+    int lsm, rgl, threads, grid;
+    size_t smem, vg_stride, rg_stride;  // vg_stride in double2 elements, rg_stride in words, per CTA
     bool ok;
 };
 
@@ -648,12 +670,16 @@ static Scl2Config scl2_config(const pc_plan *plan, int L, int64_t B) {
     c.ok = false;
     if (plan->q != 2 || n < 1 || n > 13 || L > 32) return c;
     const size_t budget = (size_t)env_int("PC_SCL_SMEM_KB", 74) * 1024;
+    int rgl = env_int("PC_SCL_RGL", 9);
+    if (rgl < 1) rgl = 1;
+    if (rgl > n + 1) rgl = n + 1;
+    c.rgl = rgl;
     int lsm = n - 1;
-    while (lsm > 0 && scl2_smem_bytes(n, L, lsm) > budget) --lsm;
+    while (lsm > 0 && scl2_smem_bytes(n, L, lsm, rgl) > budget) --lsm;
     const int forced = env_int("PC_SCL_LSM", -1);
     if (forced >= 0 && forced <= n - 1) lsm = forced;
     c.lsm = lsm;
-    c.smem = scl2_smem_bytes(n, L, lsm);
+    c.smem = scl2_smem_bytes(n, L, lsm, rgl);
     if (c.smem > 220 * 1024) return c;
     c.threads = env_int("PC_SCL_THREADS", 256);
     if (c.threads < 32 || c.threads > SCL2_MAX_THREADS || (c.threads & 31)) c.threads = 256;
@@ -668,6 +694,7 @@ static Scl2Config scl2_config(const pc_plan *plan, int L, int64_t B) {
     c.grid = (int)(grid > 0 ? grid : 1);
     const int64_t vtot = (int64_t)((1 << n) - 2) * S, vs = (int64_t)((2 << lsm) - 2) * S;
     c.vg_stride = (size_t)(vtot > vs ? vtot - vs : 0);
+    c.rg_stride = (size_t)2 * S * (scl2_wsum(n + 1) - scl2_wsum(rgl)) + 4;
     c.ok = true;
     return c;
 }
@@ -679,7 +706,7 @@ bool scl2_supported(const pc_plan *plan, int L) {
 
 size_t scl2_workspace_bytes(const pc_plan *plan, int L, int64_t B) {
     const Scl2Config c = scl2_config(plan, L, B);
-    return align256((size_t)c.grid * c.vg_stride * sizeof(double2) + 256);
+    return align256(align256((size_t)c.grid * c.vg_stride * sizeof(double2) + 256) + (size_t)c.grid * c.rg_stride * 4 + 256);
 }
 
 int scl2_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_xy, const uint8_t *d_fv, const uint8_t *d_ainfo,
@@ -690,8 +717,9 @@ int scl2_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_
         set_error("scl2: unsupported configuration");
         return PC_ERR_UNSUPPORTED;
     }
-    if ((size_t)c.grid * c.vg_stride * sizeof(double2) > ws_bytes) {
-        set_error("workspace too small: %zu bytes given, %zu needed", ws_bytes, (size_t)c.grid * c.vg_stride * sizeof(double2));
+    const size_t need = scl2_workspace_bytes(plan, L, B);
+    if (need > ws_bytes) {
+        set_error("workspace too small: %zu bytes given, %zu needed", ws_bytes, need);
         return PC_ERR_NOMEM;
     }
     Scl2Params p{};
@@ -701,6 +729,7 @@ int scl2_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_
     p.n_ops = (int)T->ops.size();
     p.nfrozen = plan->N - plan->k;
     p.lsm = c.lsm;
+    p.rgl = c.rgl;
     p.frames = B;
     p.ops2 = T->d_ops2;
     p.a_src = T->d_a_src;
@@ -714,6 +743,8 @@ int scl2_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_
     p.ainfo = d_ainfo;
     p.vg = (double2 *)ws;
     p.vg_stride = (int64_t)c.vg_stride;
+    p.rg = (uint32_t *)((char *)ws + align256((size_t)c.grid * c.vg_stride * sizeof(double2) + 256));
+    p.rg_stride = (int64_t)c.rg_stride;
     p.info = d_info;
     p.result = d_res;
     p.list_size = d_lsize;
