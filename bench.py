@@ -247,9 +247,9 @@ def awgn_frozen_set(n, K, allow_ga):
 class SclBinary4096:
     """C2: binary SCL L=8, N=4096, K=2048 over BI-AWGN at Eb/N0 = 2 dB, linear-domain float64 (listDecode with q=2)."""
     name = "scl_l8_n4096_k2048_biawgn2dB"
-    kernel = "scl_decode_kernel<2>"
+    kernel = "scl2_kernel (frame-per-CTA binary SCL)"
     dtype = "f64"
-    default_frames, default_e2e, default_cpu = 1 << 15, 1 << 13, 1 << 9
+    default_frames, default_e2e, default_cpu = 1 << 15, 1 << 13, 1 << 14
     N, K, n, L = 4096, 2048, 12, 8
     alg_bytes_frame = 16640  # SURVEY.md 8(d): 4 N bytes of soft input + K/8 bytes out
     info_bits = 2048
