@@ -66,6 +66,7 @@ struct SchedEntry {
 };
 
 void scl_tables_release(const pc_plan *p);
+void stream_tables_release(const pc_plan *p);
 
 }  // namespace pc
 

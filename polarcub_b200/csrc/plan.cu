@@ -160,6 +160,7 @@ int pc_plan_create(int q, int n, const uint8_t *h_frozen_mask, const uint8_t *h_
 void pc_plan_destroy(pc_plan *p) {
     if (!p) return;
     pc::scl_tables_release(p);
+    pc::stream_tables_release(p);
     cudaFree(p->d_sched);
     cudaFree(p->d_r0_words);
     cudaFree(p->d_src);

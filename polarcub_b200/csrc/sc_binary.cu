@@ -19,9 +19,15 @@
 //    a register;
 //  * the channel level is read through a transposed, bit-reversed copy made by the ingest kernel, and the
 //    decoded words are transposed back (codeword bit-reversed to the reference order) by the egress kernel.
-#include "common.cuh"
+#include "sc_arith.cuh"
 
 namespace pc {
+
+// sc_stream.cu: one frame per CTA, upper stages streamed through HBM (large blocks)
+bool sc_stream_supported(const pc_plan *plan);
+size_t sc_stream_workspace_bytes(const pc_plan *plan, int64_t B);
+int sc_stream_decode(const pc_plan *plan, int kind, const void *d_in, int64_t B, const double *h_table, int Y, uint32_t *d_cw,
+                     uint32_t *d_info, void *ws, size_t ws_bytes, cudaStream_t st);
 
 constexpr int LS = 4;            // levels 0..LS in shared memory: 2^(LS+1)-1 doubles per thread
 constexpr int SC_THREADS = 256;  // 8 warps = 256 frames per block
@@ -41,57 +47,6 @@ struct ScParams {
     uint32_t *info_t;   // [Kw][Bpad]
     double table[32];   // symbols: [Y][2] joint probabilities
 };
-
-__device__ __forceinline__ double d_abs(double x) { return __longlong_as_double(__double_as_longlong(x) & 0x7fffffffffffffffLL); }
-__device__ __forceinline__ uint32_t d_sign(double x) { return (uint32_t)(__double2hiint(x)) >> 31; }
-__device__ __forceinline__ double d_pack(double r, uint32_t side) {
-    return __hiloint2double((__double2hiint(r) & 0x7fffffff) | (int)(side << 31), __double2loint(r));
-}
-
-// normalise a raw pair by its maximum (BinaryMemorylessVectorDistribution.py:71-87) and pack it.
-// 0/0 -> NaN encodes the (0,0) state the reference keeps when the maximum is 0.
-__device__ __forceinline__ double pack_pair(double o0, double o1) {
-    const bool gt = o1 > o0;
-    const double mx = gt ? o1 : o0, mn = gt ? o0 : o1;
-    return d_pack(mn / mx, gt ? 1u : 0u);
-}
-
-// f on raw pairs (channel level), BinaryMemorylessVectorDistribution.py:21-26
-__device__ __forceinline__ double f_raw(double a0, double a1, double b0, double b1) {
-    const double o0 = __dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1));
-    const double o1 = __dadd_rn(__dmul_rn(a0, b1), __dmul_rn(a1, b0));
-    return pack_pair(o0, o1);
-}
-// g on raw pairs, BinaryMemorylessVectorDistribution.py:37-44
-__device__ __forceinline__ double g_raw(double a0, double a1, double b0, double b1, uint32_t u) {
-    const double o0 = __dmul_rn(u ? a1 : a0, b0);
-    const double o1 = __dmul_rn(u ? a0 : a1, b1);
-    return pack_pair(o0, o1);
-}
-// f on packed normalised values: (o0,o1) is (1 + ra*rb, ra + rb), or swapped when the sides differ
-__device__ __forceinline__ double f_packed(double a, double b) {
-    const double ra = d_abs(a), rb = d_abs(b);
-    const uint32_t s = d_sign(a) ^ d_sign(b);
-    const double A = __dadd_rn(1.0, __dmul_rn(ra, rb));
-    const double Bv = __dadd_rn(ra, rb);
-    const bool c = Bv > A, d = A > Bv;
-    const double mx = c ? Bv : A, mn = c ? A : Bv;
-    return d_pack(mn / mx, (s ? d : c) ? 1u : 0u);
-}
-// g on packed normalised values
-__device__ __forceinline__ double g_packed(double a, double b, uint32_t u) {
-    const double ra = d_abs(a), rb = d_abs(b);
-    const uint32_t sa = d_sign(a) ^ u, sb = d_sign(b);
-    if (sa == sb) {  // (1*1, ra*rb): already normalised (division by 1.0 is exact)
-        const double r = __dmul_rn(ra, rb);
-        return d_pack(r, (sb && r < 1.0) ? 1u : 0u);
-    }
-    // out[sb] = ra, out[1-sb] = rb
-    const bool c = ra > rb;
-    const double mx = c ? ra : rb, mn = c ? rb : ra;
-    const bool gt = sb ? (ra > rb) : (rb > ra);
-    return d_pack(mn / mx, gt ? 1u : 0u);
-}
 
 template <int KIND>
 __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel(const ScParams p) {
@@ -382,15 +337,26 @@ static int64_t sc_pick_chunk(int64_t B, int kind) {
     return chunk;
 }
 
+// Large blocks (and, on request, any block of at least 64 symbols) take the frame-per-CTA streamed decoder:
+// PC_SC_STREAM=1 forces it, PC_SC_STREAM=0 forbids it below the frame-per-lane limit.
+static bool sc_use_stream(const pc_plan *plan, int64_t B) {
+    if (!sc_stream_supported(plan)) return false;
+    if (plan->n > SC_MAX_N) return true;
+    const char *s = getenv("PC_SC_STREAM");
+    if (s && *s) return atoi(s) != 0;
+    return plan->n >= 14 && B < 2048;  // few long frames: not enough frames to fill 32-frame warps
+}
+
 static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int64_t B, const double *h_table, int Y,
                             uint32_t *d_cw, uint32_t *d_info, void *ws, size_t ws_bytes, cudaStream_t st) {
     PC_REQUIRE(plan && plan->q == 2, "binary plan required");
-    PC_REQUIRE(plan->n <= SC_MAX_N, "block length too large for the frame-per-lane SC decoder");
     PC_REQUIRE(B >= 0, "negative batch");
     if (B == 0) return PC_OK;
     PC_REQUIRE(d_in && d_cw && (d_info || plan->k == 0) && ws, "null buffer");
     PC_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
     if (kind == PC_INPUT_SYMBOLS) PC_REQUIRE(h_table && Y >= 1 && Y <= 16, "symbol table must have 1..16 rows");
+    if (sc_use_stream(plan, B)) return sc_stream_decode(plan, kind, d_in, B, h_table, Y, d_cw, d_info, ws, ws_bytes, st);
+    PC_REQUIRE(plan->n <= SC_MAX_N, "block length too large for the frame-per-lane SC decoder");
     // largest chunk (multiple of 32 frames) that fits the workspace
     int64_t chunk = sc_pick_chunk(B, kind);
     while (chunk > 32 && sc_layout(plan, chunk, kind).total > ws_bytes) chunk = round_up(chunk / 2, 32);
@@ -462,6 +428,7 @@ extern "C" {
 
 size_t pc_sc_workspace_bytes(const pc_plan *plan, int64_t B, int input_kind) {
     if (!plan || B <= 0) return 256;
+    if (pc::sc_use_stream(plan, B)) return pc::sc_stream_workspace_bytes(plan, B);
     return pc::sc_layout(plan, pc::sc_pick_chunk(B, input_kind), input_kind).total;
 }
 

@@ -1,0 +1,125 @@
+"""GPU parity: the frame-per-CTA streamed SC decoder (sc_stream.cu, the large-block path) vs the CPU oracle.
+
+PC_SC_STREAM=1 forces the streamed decoder for block lengths the frame-per-lane decoder also covers, so it is checked
+at sizes the oracle finishes in seconds (N = 64 .. 2^17) with several frozen-set shapes; the BASELINE N = 2^20 BEC
+configuration is checked on two frames against the oracle and through size-independent properties.
+Bar: BIT-EXACT decisions (codeword and information bits).
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _z(n, eps):
+    z = [eps]
+    for _ in range(n):
+        z = [v for zz in z for v in (2 * zz - zz * zz, zz * zz)]
+    return np.array(z)
+
+
+def _frozen(n, k, how, rng):
+    N = 1 << n
+    if how == "bec":
+        return set(int(i) for i in np.argsort(-_z(n, 0.5), kind="stable")[:N - k])
+    if how == "random":
+        return set(int(i) for i in rng.permutation(N)[:N - k])
+    if how == "blocks":  # long frozen and long free runs: rate-0 nodes of many sizes
+        m = np.zeros(N, dtype=bool)
+        pos = 0
+        while pos < N:
+            run = int(rng.choice([1, 2, 3, 8, 32, 33, 64, 100, 256]))
+            if rng.random() < 0.5:
+                m[pos:pos + run] = True
+            pos += run
+        return set(np.nonzero(m)[0].tolist())
+    raise ValueError(how)
+
+
+def _channel(kind, cw, rng):
+    B, N = cw.shape
+    if kind == "bsc":
+        p = 0.11
+        tab = np.array([[0.5 * (1 - p), 0.5 * p], [0.5 * p, 0.5 * (1 - p)]])
+        return tab, (cw ^ (rng.random((B, N)) < p)).astype(np.uint8)
+    if kind == "bec":
+        p = 0.35
+        tab = np.array([[0.5 * (1 - p), 0.0], [0.0, 0.5 * (1 - p)], [0.5 * p, 0.5 * p]])
+        return tab, np.where(rng.random((B, N)) < p, 2, cw).astype(np.uint8)
+    if kind == "bec_lossy":  # contradictions: (0,0) states appear
+        p = 0.3
+        tab = np.array([[0.5 * (1 - p), 0.0], [0.0, 0.5 * (1 - p)], [0.5 * p, 0.5 * p]])
+        return tab, np.where(rng.random((B, N)) < p, 2, cw ^ (rng.random((B, N)) < 0.03)).astype(np.uint8)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("n,how,kind,seed", [(6, "bec", "bsc", 1), (7, "random", "bec", -1), (8, "blocks", "bsc", 5),
+                                             (9, "bec", "bec_lossy", 1), (10, "bec", "bsc", 1), (11, "blocks", "bec", 2),
+                                             (12, "random", "bsc", 1), (13, "bec", "awgn", 1), (14, "blocks", "bsc", 9)])
+def test_stream_decoder_vs_oracle(n, how, kind, seed, monkeypatch):
+    monkeypatch.setenv("PC_SC_STREAM", "1")
+    import polarcub_b200 as pcb
+    N = 1 << n
+    rng = np.random.default_rng(4000 + 31 * n)
+    fs = _frozen(n, N // 2, how, rng)
+    ed = pcb.BinaryPolarEncoderDecoder(N, fs, seed)
+    B = 37 if n <= 11 else 9
+    info = rng.integers(0, 2, size=(B, ed.k))
+    cw = ed.encode_batch(info)
+    fm, r = ed.frozenMask, ed.randomlyGeneratedNumbers
+    xp = np.full((N, 2), 0.5)
+    if kind == "awgn":
+        sigma = 0.8
+        yv = (1.0 - 2.0 * cw) + sigma * rng.standard_normal((B, N))
+        l0, l1 = -(yv - 1) ** 2 / (2 * sigma ** 2), -(yv + 1) ** 2 / (2 * sigma ** 2)
+        m = np.maximum(l0, l1)
+        xy = np.stack([np.exp(l0 - m), np.exp(l1 - m)], axis=-1)
+        tab = None
+    else:
+        tab, y = _channel(kind, cw, rng)
+        xy = tab[y]
+    ocw, oinfo = oracle.bin_decode_batch(N, fm, r, xp, xy)
+    dcw, dinfo = ed.decode_batch(xy)
+    np.testing.assert_array_equal(dcw, ocw)
+    np.testing.assert_array_equal(dinfo, oinfo)
+    if tab is not None:
+        dcw_s, dinfo_s = ed.decode_symbols_batch(y, tab)
+        np.testing.assert_array_equal(dcw_s, ocw)
+        np.testing.assert_array_equal(dinfo_s, oinfo)
+    # the streamed and the frame-per-lane decoders agree
+    monkeypatch.setenv("PC_SC_STREAM", "0")
+    dcw2, dinfo2 = ed.decode_batch(xy)
+    np.testing.assert_array_equal(dcw2, dcw)
+    np.testing.assert_array_equal(dinfo2, dinfo)
+
+
+@pytest.mark.parametrize("n,frames", [(17, 3), (20, 2)])
+def test_large_block_bec(n, frames):
+    """BASELINE config 4 shape: BEC(0.1), R = 0.8, frozen set from the closed-form BEC recursion."""
+    import polarcub_b200 as pcb
+    N = 1 << n
+    K = int(0.8 * N)
+    order = np.argsort(_z(n, 0.1), kind="stable")  # ascending Z: best indices first
+    fs = set(int(i) for i in order[K:])
+    ed = pcb.BinaryPolarEncoderDecoder(N, fs, 1)
+    assert ed.k == K
+    rng = np.random.default_rng(77 + n)
+    info = rng.integers(0, 2, size=(frames, K))
+    cw = ed.encode_batch(info)
+    p = 0.1
+    tab = np.array([[0.5 * (1 - p), 0.0], [0.0, 0.5 * (1 - p)], [0.5 * p, 0.5 * p]])  # makeBEC, BinaryMemorylessDistribution.py:493-499
+    y = np.where(rng.random((frames, N)) < p, 2, cw).astype(np.uint8)
+    dcw, dinfo = ed.decode_symbols_batch(y, tab)
+    # size-independent properties: the decoded codeword is the encoding of the decoded information, and it agrees with
+    # every unerased channel output (the BEC never contradicts a correct decision)
+    np.testing.assert_array_equal(ed.encode_batch(dinfo), dcw)
+    known = y != 2
+    assert np.array_equal(dcw[known], cw[known])
+    # the oracle on the same frames
+    xp = np.full((N, 2), 0.5)
+    for f in range(frames):
+        ocw, oinfo = oracle.bin_decode(N, ed.frozenMask, ed.randomlyGeneratedNumbers, xp, tab[y[f]])
+        np.testing.assert_array_equal(dcw[f], ocw)
+        np.testing.assert_array_equal(dinfo[f], oinfo)
