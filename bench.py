@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- decoded info Gbit/s of the batched polar decoders on B200 (contract: see DESIGN.md "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload scl4096|sc1024|qsc2048] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload scl4096|sc1024|qsc2048|sc2p20] [--impl ours|reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one pass of the decode hot path over one batch of synthetic channel outputs (frames are
@@ -230,6 +230,84 @@ class ScBinary1024:
         return run_threads(work, np.array_split(np.arange(ys.shape[0]), threads), threads)
 
     cpu_what = "oracle/polar_oracle.c (C restatement of the reference's float64 SC recursion, prior and posterior trees)"
+
+
+class ScBinaryLarge:
+    """C4: large-block binary SC, N=2^20, R=0.8 over BEC(0.1); upper stages streamed through HBM (sc_stream.cu)."""
+    name = "sc_n2p%s_r0.8_bec0.1" % os.environ.get("PC_BENCH_LARGE_N", "20")
+    kernel = "sc_stream_kernel<symbols>"
+    dtype = "f64"
+    default_frames, default_e2e, default_cpu = 296, 64, 32
+    n = int(os.environ.get("PC_BENCH_LARGE_N", "20"))  # 20 is the BASELINE configuration; smaller values are for profiling runs
+    N, K = 1 << n, int(0.8 * (1 << n))
+    # SURVEY.md 8(d): stages above 2^13 stream 12 N bytes each + channel ingest 4 N + (N + K)/8 out (fp32 soft-input contract)
+    alg_bytes_frame = 4 * N * (1 + 3 * max(0, n - 13)) + (N + K) // 8
+    info_bits = K
+    P_BEC = 0.1
+
+    def code(self):
+        from polarcub_b200.construction import bec_pe
+        pe = bec_pe(self.n, self.P_BEC)
+        order = np.argsort(pe, kind="stable")
+        self.fm = np.zeros(self.N, dtype=np.uint8)
+        self.fm[order[self.K:]] = 1
+        self.r = common_randomness(self.N, 1)
+        self.fv = np.where(0.5 >= self.r, 0, 1).astype(np.uint8)
+        p = self.P_BEC
+        self.tab = np.array([[0.5 * (1 - p), 0.0], [0.0, 0.5 * (1 - p)], [0.5 * p, 0.5 * p]])  # makeBEC, BinaryMemorylessDistribution.py:493-499
+        self.construction = "closed-form BEC recursion z -> (2z - z^2, z^2), K = 0.8 N best indices (SURVEY.md 8d, C4)"
+
+    def setup(self, dev, rank, B, Be):
+        import torch
+        from polarcub_b200 import engine
+        self.engine, self.torch = engine, torch
+        self.code()
+        N = self.N
+        self.plan = plan = engine.Plan(2, self.n, self.fm, self.fv, device=dev)
+        gen = torch.Generator(device=dev)
+        self.y = torch.empty((B, N), dtype=torch.uint8, device=dev)
+        self.info_tx = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
+        shifts = torch.arange(32, device=dev, dtype=torch.int32)
+        CH = 8
+        for c0 in range(0, B, CH):
+            c1 = min(B, c0 + CH)
+            gen.manual_seed(2020 + 7919 * ((rank * B + c0) // CH))
+            it = torch.randint(-2 ** 31, 2 ** 31 - 1, (c1 - c0, plan.Kw), dtype=torch.int64, device=dev, generator=gen).to(torch.int32)
+            if self.K & 31:
+                it[:, -1] &= (1 << (self.K & 31)) - 1
+            self.info_tx[c0:c1] = it
+            cwp = engine.encode_bits(plan, it.contiguous())
+            bits = ((cwp.unsqueeze(-1) >> shifts) & 1).reshape(c1 - c0, N).to(torch.uint8)
+            erased = torch.rand((c1 - c0, N), device=dev, generator=gen) < self.P_BEC
+            self.y[c0:c1] = torch.where(erased, torch.full_like(bits, 2), bits)
+            del it, cwp, bits, erased
+        self.cw_out = torch.empty((B, plan.Nw), dtype=torch.int32, device=dev)
+        self.info_out = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
+        self.Be = Be
+        self.y_host = torch.empty((Be, N), dtype=torch.uint8).pin_memory()
+        self.y_host.copy_(self.y[:Be])
+        self.cw_host = torch.empty((Be, plan.Nw), dtype=torch.int32).pin_memory()
+        self.info_host = torch.empty((Be, plan.Kw), dtype=torch.int32).pin_memory()
+        self.y_e = torch.empty((Be, N), dtype=torch.uint8, device=dev)
+        self.h2d = int(Be * N)
+        self.d2h = int(Be * (plan.Nw + plan.Kw) * 4)
+        self.input_note = "uint8 channel symbols [B,N] (%.2f GiB per step per GPU, larger than L2)" % (B * N / 2 ** 30)
+
+    step = ScBinary1024.step
+    e2e_step = ScBinary1024.e2e_step
+    counters = ScBinary1024.counters
+    cpu_inputs_from_gpu = ScBinary1024.cpu_inputs_from_gpu
+    cpu_decode = ScBinary1024.cpu_decode
+    cpu_what = ScBinary1024.cpu_what
+
+    def cpu_inputs_synth(self, frames):
+        import oracle
+        self.code()
+        rng = np.random.default_rng(2020)
+        info = rng.integers(0, 2, size=(min(frames, 4), self.K))
+        cw = oracle.bin_encode_batch(self.N, self.fm, self.r, np.full((self.N, 2), 0.5), info)
+        cw = np.tile(cw, ((frames + cw.shape[0] - 1) // cw.shape[0], 1))[:frames]
+        return np.where(rng.random((frames, self.N)) < self.P_BEC, 2, cw).astype(np.uint8)
 
 
 def awgn_frozen_set(n, K, allow_ga):
@@ -465,7 +543,7 @@ class ScQary2048:
     cpu_what = "oracle/polar_oracle.c (C restatement of the reference's float64 q-ary SC recursion)"
 
 
-WORKLOADS = {"scl4096": SclBinary4096, "sc1024": ScBinary1024, "qsc2048": ScQary2048}
+WORKLOADS = {"scl4096": SclBinary4096, "sc1024": ScBinary1024, "qsc2048": ScQary2048, "sc2p20": ScBinaryLarge}
 
 
 def nframes(x):

@@ -61,4 +61,41 @@ __device__ __forceinline__ double g_packed(double a, double b, uint32_t u) {
     return d_pack(mn / mx, gt ? 1u : 0u);
 }
 
+
+// ---- exact shortcuts for hard / erased values --------------------------------------------------------------------
+// When both operands are r = 0 (hard knowledge) or r = 1 (erasure) -- every value of a BEC frame -- the reference's
+// products, sums and quotients are exact small integers, so the result is selected without the division.  Same
+// bits as f_packed / g_packed; anything else (including the 0/0 contradiction case) takes the general path.
+// out-of-line general paths: a real call keeps the compiler from evaluating the division speculatively
+static __device__ __noinline__ double f_packed_call(double a, double b) { return f_packed(a, b); }
+static __device__ __noinline__ double g_packed_call(double a, double b, uint32_t u) { return g_packed(a, b, u); }
+__device__ __forceinline__ bool d_is01(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x) & 0x7fffffffffffffffULL;
+    return b == 0ULL || b == 0x3ff0000000000000ULL;
+}
+__device__ __forceinline__ double f_packed01(double a, double b) {
+    if (d_is01(a) && d_is01(b)) {
+        const double ra = d_abs(a), rb = d_abs(b);
+        // (A, B) = (1 + ra rb, ra + rb) is (1,0), (1,1) or (2,2): min/max = 0, 1, 1; A > B only for ra = rb = 0
+        const bool both0 = ra == 0.0 && rb == 0.0;
+        return d_pack(both0 ? 0.0 : 1.0, ((d_sign(a) ^ d_sign(b)) && both0) ? 1u : 0u);
+    }
+    return f_packed_call(a, b);
+}
+__device__ __forceinline__ double g_packed01(double a, double b, uint32_t u) {
+    if (d_is01(a) && d_is01(b)) {
+        const double ra = d_abs(a), rb = d_abs(b);
+        const uint32_t sa = d_sign(a) ^ u, sb = d_sign(b);
+        if (sa == sb) {
+            const double r = (ra == 1.0 && rb == 1.0) ? 1.0 : 0.0;  // ra * rb
+            return d_pack(r, (sb && r < 1.0) ? 1u : 0u);
+        }
+        if (ra != 0.0 || rb != 0.0) {  // (ra, rb) = (0,0) with opposite sides is the 0/0 contradiction: general path
+            const bool gt = sb ? (ra > rb) : (rb > ra);
+            return d_pack(ra == rb ? 1.0 : 0.0, gt ? 1u : 0u);
+        }
+    }
+    return g_packed_call(a, b, u);
+}
+
 }  // namespace pc

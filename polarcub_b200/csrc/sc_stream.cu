@@ -164,8 +164,6 @@ __device__ __forceinline__ uint32_t st_spread16(uint32_t x) {
     return x;
 }
 
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
 template <int KIND>
 __global__ void __launch_bounds__(256) sc_stream_kernel(const StreamParams p) {
     extern __shared__ __align__(16) unsigned char st_smem[];
@@ -219,7 +217,7 @@ __global__ void __launch_bounds__(256) sc_stream_kernel(const StreamParams p) {
                     const double2 *src = (const double2 *)V(l + 1);
                     for (int h = tid; h < size; h += T) {
                         const double2 ab = src[h];
-                        dst[h] = kind == SOP_F ? f_packed(ab.x, ab.y) : g_packed(ab.x, ab.y, (ub[h >> 5] >> (h & 31)) & 1u);
+                        dst[h] = kind == SOP_F ? f_packed01(ab.x, ab.y) : g_packed01(ab.x, ab.y, (ub[h >> 5] >> (h & 31)) & 1u);
                     }
                 }
                 __syncthreads();
@@ -244,70 +242,65 @@ __global__ void __launch_bounds__(256) sc_stream_kernel(const StreamParams p) {
                 __syncthreads();
                 continue;
             }
-            // ---- SOP_BLOCK: 32 leaves in warp 0, level vectors in registers --------------------------------------
+            // ---- SOP_BLOCK: 32 leaves in warp 0; level vectors 0..5 in shared memory, warp-level barriers only ---------
             if (warp == 0) {
                 const int e0 = (int)opk.y, cnt = (opk.x >> 9) & 63;
-                double v[6];
-                v[5] = Vs[32 + lane];
-                v[0] = v[1] = v[2] = v[3] = v[4] = 0.0;
-                uint32_t x[5][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
+                // the block's schedule entries (<= 32) are fetched with one coalesced load and broadcast by shuffle
+                int my_i = 0;
+                uint32_t my_meta = 0, my_bits = 0;
+                if (lane < cnt) {
+                    const uint32_t *se = (const uint32_t *)(p.sched + e0 + lane);
+                    my_i = (int)se[0];
+                    my_meta = se[1];
+                    my_bits = se[2];
+                }
                 uint32_t x5 = 0, ubits = 0;
-                int i_block = 0;
-                const int s0 = (2 * lane) & 31, s1 = (2 * lane + 1) & 31;
+                const int i_block = __shfl_sync(0xffffffffu, my_i, 0);
                 for (int q = 0; q < cnt; ++q) {
-                    const SchedEntry e = p.sched[e0 + q];
-                    const int li = e.i & 31, el = e.l, top = e.top;
-                    if (q == 0) i_block = e.i;
-                    const int stop = e.kind == NODE_RATE0 ? el + 1 : el;
-                    int start;
+                    const int e_i = __shfl_sync(0xffffffffu, my_i, q);
+                    const uint32_t e_meta = __shfl_sync(0xffffffffu, my_meta, q), e_bits = __shfl_sync(0xffffffffu, my_bits, q);
+                    const int li = e_i & 31, el = (int)(e_meta & 0xff), e_kind = (int)((e_meta >> 8) & 0xff),
+                              top = (int)((e_meta >> 16) & 0xff);
+                    const int stop = e_kind == NODE_RATE0 ? el + 1 : el;
+                    int lev;
                     if (li == 0) {
-                        start = 4;
-                    } else if (top >= stop) {
-#pragma unroll
-                        for (int TL = 0; TL < 5; ++TL)
-                            if (top == TL) {
-                                const double a = shfl_d(v[TL + 1], s0), b = shfl_d(v[TL + 1], s1);
-                                v[TL] = g_packed(a, b, (x[TL][0] >> lane) & 1u);
-                            }
-                        start = top - 1;
-                    } else {
-                        start = -1;
-                    }
-#pragma unroll
-                    for (int TL = 4; TL >= 0; --TL)
-                        if (TL <= start && TL >= stop) {
-                            const double a = shfl_d(v[TL + 1], s0), b = shfl_d(v[TL + 1], s1);
-                            v[TL] = f_packed(a, b);
+                        lev = 4;
+                    } else if (top >= stop) {  // g at level top with the sibling's partial sums
+                        if (lane < (1 << top)) {
+                            const double2 ab = ((const double2 *)(Vs + (2 << top)))[lane];
+                            Vs[(1 << top) + lane] = g_packed01(ab.x, ab.y, (Xs[2 * top] >> lane) & 1u);
                         }
-                    if (e.kind == NODE_INFO) {  // p0 >= p1 -> 0 (ties and (0,0) -> 0), BinaryPolarEncoderDecoder.py:252
-                        const uint32_t bit = __shfl_sync(0xffffffffu, d_sign(v[0]), 0);
-                        ubits |= bit << li;
-                        x[0][0] = (li & 1) ? x[0][0] : bit;
-                        x[0][1] = (li & 1) ? bit : x[0][1];
+                        __syncwarp();
+                        lev = top - 1;
                     } else {
-                        const int cc = (li >> el) & 1;
-#pragma unroll
-                        for (int TL = 0; TL < 5; ++TL)
-                            if (el == TL) {
-                                x[TL][0] = cc ? x[TL][0] : e.bits;
-                                x[TL][1] = cc ? e.bits : x[TL][1];
-                            }
+                        lev = -1;
+                    }
+                    for (; lev >= stop; --lev) {
+                        if (lane < (1 << lev)) {
+                            const double2 ab = ((const double2 *)(Vs + (2 << lev)))[lane];
+                            Vs[(1 << lev) + lane] = f_packed01(ab.x, ab.y);
+                        }
+                        __syncwarp();
+                    }
+                    // every lane keeps the (warp-uniform) partial-sum words of the block: same value to the same address
+                    if (e_kind == NODE_INFO) {  // p0 >= p1 -> 0 (ties and (0,0) -> 0), BinaryPolarEncoderDecoder.py:252
+                        const uint32_t bit = d_sign(Vs[1]);
+                        ubits |= bit << li;
+                        Xs[li & 1] = bit;
+                    } else {
+                        Xs[2 * el + ((li >> el) & 1)] = e_bits;
                     }
                     int lv = el, ii = li;
-#pragma unroll
-                    for (int TL = 0; TL < 5; ++TL)
-                        if (lv == TL && ((ii >> TL) & 1)) {
-                            const uint32_t cw = st_spread16(x[TL][0] ^ x[TL][1]) | (st_spread16(x[TL][1]) << 1);
-                            ii -= 1 << TL;
-                            lv = TL + 1;
-                            if (TL + 1 == 5) {
-                                x5 = cw;
-                            } else {
-                                const int cc = (ii >> (TL + 1)) & 1;
-                                x[(TL + 1) % 5][0] = cc ? x[(TL + 1) % 5][0] : cw;
-                                x[(TL + 1) % 5][1] = cc ? cw : x[(TL + 1) % 5][1];
-                            }
-                        }
+                    while (lv < 5 && ((ii >> lv) & 1)) {  // a plus child completed: x[2h] = m[h] ^ p[h], x[2h+1] = p[h]
+                        const uint32_t m = Xs[2 * lv], pw = Xs[2 * lv + 1];
+                        const uint32_t cw = st_spread16(m ^ pw) | (st_spread16(pw) << 1);
+                        ii -= 1 << lv;
+                        ++lv;
+                        if (lv == 5)
+                            x5 = cw;
+                        else
+                            Xs[2 * lv + ((ii >> lv) & 1)] = cw;
+                    }
                 }
                 if (lane == 0) {
                     X(5, c)[0] = x5;
