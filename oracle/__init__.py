@@ -212,3 +212,45 @@ def list_decode_batch(q, N, L, fmask, xyprobs, frozen_values, actual_info):
                                     _p(xyprobs, _f64p), _p(fv, _i64p), _p(ai, _i64p), _p(info, _i64p), _p(pr, _i32p))
     assert rc == 0, rc
     return info, pr
+
+
+# ---------------------------------------------------------------------------------------------------
+# deletion channel: guard bands + trellis decoding (polar_oracle_trellis.c)
+def add_guard_bands(encoded, n, n0, xi, ones=0):
+    """Guardbands.addDeletionGuardBands (Guardbands.py:4-44) -> uint8 array."""
+    enc = _c(encoded, np.uint8)
+    assert enc.shape == (1 << n,)
+    out = np.zeros(8 * (1 << n) + 2 * ones * (1 << n) + 64, dtype=np.uint8)
+    m = lib().po_add_guard_bands(_p(enc, _u8p), ctypes.c_int(n), ctypes.c_int(n0), ctypes.c_double(xi), ctypes.c_int(ones),
+                                 _p(out, _u8p))
+    return out[:m].copy()
+
+
+def remove_guard_bands(received, n, n0, maxlen):
+    """Guardbands.removeDeletionGuardBands (Guardbands.py:47-63) -> (sub_bits uint8 [T, maxlen], sub_len int32 [T], overflow)."""
+    rw = _c(received, np.uint8)
+    T = 1 << (n - n0)
+    sub_bits = np.zeros((T, maxlen), dtype=np.uint8)
+    sub_len = np.zeros(T, dtype=np.int32)
+    ov = lib().po_remove_guard_bands(_p(rw, _u8p), ctypes.c_int(rw.shape[0]), ctypes.c_int(n), ctypes.c_int(n0),
+                                     _p(sub_bits, _u8p), _p(sub_len, _i32p), ctypes.c_int(maxlen))
+    return sub_bits, sub_len, bool(ov)
+
+
+def trellis_decode(n, n0, fmask, r, sub_bits, sub_len, deletion_prob, ones=0, want_collapse=False):
+    """BinaryPolarEncoderDecoder.decode over a CollectionOfBinaryTrellises built from the trimmed sub-words (uniform prior).
+    Returns (codeword int64[N], information int64[k]) and, with want_collapse, the collapsed unnormalised vectors
+    [2^n0, T, 2] in visiting order."""
+    fmask, r = _c(fmask, np.uint8), _c(r, np.float64)
+    sub_bits, sub_len = _c(sub_bits, np.uint8), _c(sub_len, np.int32)
+    N, T = 1 << n, 1 << (n - n0)
+    assert sub_bits.shape[0] == T and sub_len.shape == (T,)
+    k = int(N - fmask.sum())
+    cw = np.empty(N, dtype=np.int64)
+    info = np.full(max(k, 1), -1, dtype=np.int64)
+    col = np.zeros((1 << n0, T, 2), dtype=np.float64) if want_collapse else None
+    rc = lib().po_trellis_decode(ctypes.c_int(n), ctypes.c_int(n0), _p(fmask, _u8p), _p(r, _f64p), _p(sub_bits, _u8p),
+                                 _p(sub_len, _i32p), ctypes.c_int(sub_bits.shape[1]), ctypes.c_double(deletion_prob),
+                                 ctypes.c_int(ones), _p(cw, _i64p), _p(info, _i64p), _p(col, _f64p))
+    assert rc == 0, rc
+    return (cw, info[:k], col) if want_collapse else (cw, info[:k])
