@@ -25,8 +25,9 @@
  *                             recursion :318-401, arithmetic QaryMemorylessVectorDistribution.py:26-118)
  *   pc_scl_decode_probs       QaryPolarEncoderDecoder.listDecode          (QaryPolarEncoderDecoder.py:118-227,
  *                             recursion :403-757, helpers :759-820, :867-872)
- *   pc_trellis_decode         BinaryPolarEncoderDecoder.decode over CollectionOfBinaryTrellises
- *                             (VectorDistributions/BinaryTrellis.py:206-306, CollectionOfBinaryTrellises.py:55-103)
+ *   pc_trellis_decode         BinaryPolarEncoderDecoder.decode over CollectionOfBinaryTrellises (uniform prior), fused with
+ *                             buildCollectionOfBinaryTrellises_uniformInput_deletion's per-sub-word trellis construction
+ *                             (VectorDistributions/BinaryTrellis.py:206-438, CollectionOfBinaryTrellises.py:55-129)
  */
 #ifndef POLARCUB_B200_H
 #define POLARCUB_B200_H
@@ -116,6 +117,19 @@ int pc_scl_decode_probs(const pc_plan *plan, int L, const double *d_xy, const ui
                         const uint8_t *d_actual_info, int64_t B, uint8_t *d_info, int32_t *d_prob_result,
                         int32_t *d_list_size, double *d_list_prob, double *d_actual_prob, uint8_t *d_list_info,
                         void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---- deletion channel: SC decoding over a collection of trellises ---------------------------------------- */
+/* The received word is split by the caller into T = 2^(n-n0) trimmed sub-words (Guardbands.removeDeletionGuardBands,
+ * Guardbands.py:47-63): d_sub_bits [B][T][maxlen] uint8 (0/1), d_sub_len [B][T] int32 (lengths <= maxlen).  Each sub-word
+ * becomes a trellis of 2^n0 inputs exactly as buildTrellis_uniformInput_deletion(subword, 2^n0, deletion_prob, True,
+ * ones) builds it; the first n0 decoding levels transform trellises, the rest is memoryless SC decoding.
+ * Outputs as pc_sc_decode_probs.  d_first_collapse (optional, may be null) [B][T][2] float64 receives the unnormalised
+ * pairs of the first collapsed vector (all-minus descent), for parity checks.  1 <= n0 <= min(4, n), ones <= 16,
+ * maxlen <= 250. */
+size_t pc_trellis_workspace_bytes(const pc_plan *plan, int n0, int maxlen, int64_t B);
+int pc_trellis_decode(const pc_plan *plan, int n0, double deletion_prob, int ones, const uint8_t *d_sub_bits,
+                      const int32_t *d_sub_len, int maxlen, int64_t B, uint32_t *d_cw_packed, uint32_t *d_info_packed,
+                      double *d_first_collapse, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* ---- Monte-Carlo counters and measurement hooks ---------------------------------------------------- */
 /* d_out3[0..2] += {B, frames whose first nbits differ, differing bits} over packed rows of ceil(nbits/32) words.

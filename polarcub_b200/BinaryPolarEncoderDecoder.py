@@ -13,6 +13,7 @@ import torch
 
 from . import engine
 from ._lib import PolarcubError
+from .CollectionOfBinaryTrellises import CollectionOfBinaryTrellises
 
 
 def _probs_of(vd, length, cols):
@@ -102,6 +103,22 @@ class BinaryPolarEncoderDecoder:
         return (engine.unpack_bits(cw.cpu().numpy(), self.length).astype(np.int64),
                 engine.unpack_bits(info.cpu().numpy(), self.k).astype(np.int64))
 
+    def decode_trellis_batch(self, collection, want_collapse=False):
+        """Deletion channel: `collection` is the descriptor built by
+        CollectionOfBinaryTrellises.buildCollection[Batch]_uniformInput_deletion -> (codewords int64 [B, N],
+        information int64 [B, k]) (+ the first collapsed vector float64 [B, T, 2] with want_collapse)."""
+        assert isinstance(collection, CollectionOfBinaryTrellises) and len(collection) == self.length
+        if collection.n0 == 0:  # trellises of one symbol are not a reference use (main_deletion.py:74 takes n0 >= 1)
+            raise PolarcubError("n0 = 0 is not supported by the CUDA trellis path")
+        dev = self.plan.device
+        bits = torch.from_numpy(collection.sub_bits).to(dev)
+        lens = torch.from_numpy(collection.sub_len).to(dev)
+        out = engine.trellis_decode(self.plan, collection.n0, collection.deletionProb, collection.ones, bits, lens,
+                                    want_collapse=want_collapse)
+        res = (engine.unpack_bits(out[0].cpu().numpy(), self.length).astype(np.int64),
+               engine.unpack_bits(out[1].cpu().numpy(), self.k).astype(np.int64))
+        return res + (out[2].cpu().numpy(),) if want_collapse else res
+
     # ---- the reference's entry points -----------------------------------------------------------------
     def encode(self, xVectorDistribution, information):
         """BinaryPolarEncoderDecoder.py:46-69 -> encodedVector int64 [N]."""
@@ -115,6 +132,10 @@ class BinaryPolarEncoderDecoder:
         """BinaryPolarEncoderDecoder.py:71-99 -> (encodedVector int64 [N], information int64 [k])."""
         assert len(xVectorDistribution) == len(xyVectorDistribution) == self.length
         self._require_uniform(xVectorDistribution)
+        if isinstance(xyVectorDistribution, CollectionOfBinaryTrellises):  # main_deletion.py:52-59
+            assert xyVectorDistribution.frames == 1
+            cw, info = self.decode_trellis_batch(xyVectorDistribution)
+            return cw[0], info[0]
         xy = _probs_of(xyVectorDistribution, self.length, 2).reshape(1, self.length, 2)
         cw, info = self.decode_batch(xy)
         return cw[0], info[0]

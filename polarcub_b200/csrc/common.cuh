@@ -67,6 +67,7 @@ struct SchedEntry {
 
 void scl_tables_release(const pc_plan *p);
 void stream_tables_release(const pc_plan *p);
+void trellis_tables_release(const pc_plan *p);
 
 }  // namespace pc
 

@@ -192,6 +192,28 @@ def scl_decode_probs(plan, L, xy, frozen_values, actual_info, want_list=False, w
     return out
 
 
+def trellis_decode(plan, n0, deletion_prob, ones, sub_bits, sub_len, want_collapse=False):
+    """Deletion-channel SC decoding (BinaryPolarEncoderDecoder.decode over a CollectionOfBinaryTrellises).
+
+    sub_bits uint8 [B, T, maxlen], sub_len int32 [B, T] (device): the trimmed sub-words of each received word.
+    Returns (cw_packed int32 [B, Nw], info_packed int32 [B, Kw]) and, with want_collapse, the first collapsed
+    unnormalised vector float64 [B, T, 2]."""
+    assert sub_bits.is_cuda and sub_bits.dtype == torch.uint8 and sub_bits.is_contiguous() and sub_bits.dim() == 3
+    assert sub_len.is_cuda and sub_len.dtype == torch.int32 and sub_len.is_contiguous()
+    B, T, maxlen = sub_bits.shape
+    assert sub_len.shape == (B, T) and T == plan.N >> n0
+    dev = sub_bits.device
+    cw = torch.empty((B, plan.Nw), dtype=torch.int32, device=dev)
+    info = torch.empty((B, max(plan.Kw, 1)), dtype=torch.int32, device=dev)
+    col = torch.zeros((B, T, 2), dtype=torch.float64, device=dev) if want_collapse else None
+    need = _lib.lib().pc_trellis_workspace_bytes(plan._h, int(n0), int(maxlen), B)
+    ws = plan.workspace(need)
+    _lib.check(_lib.lib().pc_trellis_decode(plan._h, int(n0), float(deletion_prob), int(ones), _ptr(sub_bits), _ptr(sub_len),
+                                            int(maxlen), B, _ptr(cw), _ptr(info), _ptr(col), _ptr(ws), ws.numel(), _stream()),
+               "pc_trellis_decode")
+    return (cw, info[:, :plan.Kw], col) if want_collapse else (cw, info[:, :plan.Kw])
+
+
 def kernel_launch_count():
     return int(_lib.lib().pc_kernel_launch_count())
 
