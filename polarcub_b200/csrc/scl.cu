@@ -36,6 +36,13 @@ int scl2_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_
                 int64_t B, uint8_t *d_info, int32_t *d_res, int32_t *d_lsize, double *d_lprob, double *d_aprob,
                 uint8_t *d_linfo, void *ws, size_t ws_bytes, cudaStream_t st);
 
+// scl_warp.cu: frame-per-warp binary decoder (the default for q = 2)
+bool sclw_supported(const pc_plan *plan, int L);
+size_t sclw_workspace_bytes(const pc_plan *plan, int L, int64_t B);
+int sclw_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_xy, const uint8_t *d_fv, const uint8_t *d_ainfo,
+                int64_t B, uint8_t *d_info, int32_t *d_res, int32_t *d_lsize, double *d_lprob, double *d_aprob,
+                uint8_t *d_linfo, void *ws, size_t ws_bytes, cudaStream_t st);
+
 static std::mutex g_scl_mu;
 static std::map<const pc_plan *, SclTables *> g_scl_tables;
 
@@ -703,6 +710,7 @@ extern "C" {
 
 size_t pc_scl_workspace_bytes(const pc_plan *plan, int L, int64_t B, int want_list) {
     if (!plan || B <= 0 || L < 1 || L > pc::SCL_LMAX) return 256;
+    if (pc::sclw_supported(plan, L)) return pc::sclw_workspace_bytes(plan, L, B);
     if (pc::scl2_supported(plan, L)) return pc::scl2_workspace_bytes(plan, L, B);
     int64_t chunk = pc::round_up(B, 32);
     const int64_t cap = (int64_t)pc::num_sms() * 2 * pc::SCL_THREADS * 4;
@@ -731,6 +739,9 @@ int pc_scl_decode_probs(const pc_plan *plan, int L, const double *d_xy, const ui
     SclTables *T = scl_tables(plan);
     if (!T) return PC_ERR_CUDA;
     cudaStream_t st = (cudaStream_t)stream;
+    if (sclw_supported(plan, L))  // q = 2: one frame per warp, small state in shared memory (scl_warp.cu)
+        return sclw_decode(plan, T, L, d_xy, d_frozen_values, d_actual_info, B, d_info, d_prob_result, d_list_size,
+                           d_list_prob, d_actual_prob, d_list_info, d_workspace, workspace_bytes, st);
     if (scl2_supported(plan, L))  // q = 2: one frame per CTA, state in shared memory (scl_bin.cu)
         return scl2_decode(plan, T, L, d_xy, d_frozen_values, d_actual_info, B, d_info, d_prob_result, d_list_size,
                            d_list_prob, d_actual_prob, d_list_info, d_workspace, workspace_bytes, st);

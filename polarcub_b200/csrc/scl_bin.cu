@@ -16,7 +16,7 @@
 //    (np.product is a left-to-right product) run one path per lane in warp 0; pruning follows the oracle's
 //    ascending (metric, index) order;
 //  * the genie ("actual") path that listDecode tracks is slot L of every array.
-#include "scl_tables.cuh"
+#include "scl_arith.cuh"
 
 namespace pc {
 
@@ -43,9 +43,6 @@ struct Scl2Params {
     uint8_t *list_info;
 };
 
-__host__ __device__ inline int scl2_W(int l) { return l <= 5 ? 1 : 1 << (l - 5); }
-__host__ __device__ inline int scl2_wsum(int l) { return l <= 6 ? l - 1 : 3 + (1 << (l - 5)); }  // sum of W(1..l-1)
-
 // shared-memory bytes of the kernel for (n, L, lsm); mirrors the carve-up at the top of the kernel
 static size_t scl2_smem_bytes(int n, int L, int lsm, int rgl) {
     const int S = L + 1, N = 1 << n, NW = N >= 32 ? N >> 5 : 1;
@@ -57,60 +54,6 @@ static size_t scl2_smem_bytes(int n, int L, int lsm, int rgl) {
     b += (size_t)(3 * L + 3 * (n + 1) + 4) * 4;         // keep, selsrc, self, nl, nin, ivars
     b += (size_t)4 * L * 2 + L + (size_t)(n + 1) * 2 * L + L;  // pick, delta, omap, eqf
     return (b + 15) & ~(size_t)15;
-}
-
-__device__ __forceinline__ uint32_t spread16(uint32_t x) {
-    x = (x | (x << 8)) & 0x00FF00FFu;
-    x = (x | (x << 4)) & 0x0F0F0F0Fu;
-    x = (x | (x << 2)) & 0x33333333u;
-    x = (x | (x << 1)) & 0x55555555u;
-    return x;
-}
-
-// d0 / ts and d1 / ts, IEEE-754 round-to-nearest, sharing the reciprocal refinement between the two quotients.
-// The instruction sequence is the one nvcc emits for a double-precision division (MUFU.RCP64H seed with low word 1,
-// two Newton steps, quotient, exact residual, final FMA), so on its validity range (tested below, a subset of the
-// compiler's own fast-path test) the results are bit-identical to `d / ts`; everything else takes the plain division.
-__device__ __forceinline__ void div2_shared(double &d0, double &d1, const double ts) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(ts));
-    y = __hiloint2double(__double2hiint(y), 1);
-    double e = __fma_rn(-ts, y, 1.0);
-    e = __fma_rn(e, e, e);
-    y = __fma_rn(y, e, y);
-    e = __fma_rn(-ts, y, 1.0);
-    y = __fma_rn(y, e, y);
-    double q0 = __dmul_rn(d0, y), q1 = __dmul_rn(d1, y);
-    q0 = __fma_rn(y, __fma_rn(-ts, q0, d0), q0);
-    q1 = __fma_rn(y, __fma_rn(-ts, q1, d1), q1);
-    const uint32_t ht = (uint32_t)__double2hiint(ts), h0 = (uint32_t)__double2hiint(d0), h1 = (uint32_t)__double2hiint(d1);
-    const uint32_t g0 = (uint32_t)__double2hiint(q0), g1 = (uint32_t)__double2hiint(q1);
-    // operands and quotients positive, finite, normal with margin (exponent fields in [0x036, 0x7fe], divisor [0x100, 0x6ff])
-    const bool ok = (ht - 0x10000000u) < 0x60000000u && (h0 - 0x03600000u) < 0x7c900000u && (h1 - 0x03600000u) < 0x7c900000u &&
-                    (g0 - 0x00200000u) < 0x7fc00000u && (g1 - 0x00200000u) < 0x7fc00000u;
-    if (ok) {
-        d0 = q0;
-        d1 = q1;
-    } else {
-        d0 = d0 / ts;
-        d1 = d1 / ts;
-    }
-}
-
-// one f / g node update, QaryMemorylessVectorDistribution.py:36-42 / :56-62 + sum-normalisation :104-118, q = 2
-__device__ __forceinline__ double2 node_update(const double2 a, const double2 b, const bool plus, const uint32_t u1) {
-    double d0, d1;
-    if (!plus) {
-        d0 = __dadd_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y));
-        d1 = __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x));
-    } else {
-        const double a0 = u1 ? a.y : a.x, a1 = u1 ? a.x : a.y;
-        d0 = __dmul_rn(a0, b.x);
-        d1 = __dmul_rn(a1, b.y);
-    }
-    const double ts = __dadd_rn(d0, d1);
-    if (ts != 0.0) div2_shared(d0, d1, ts);
-    return make_double2(d0, d1);
 }
 
 __global__ void __launch_bounds__(SCL2_MAX_THREADS, 3) scl2_kernel(const Scl2Params p) {

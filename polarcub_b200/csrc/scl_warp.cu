@@ -1,0 +1,733 @@
+// scl_warp.cu -- binary (q = 2) SC-list decoding, ONE FRAME PER WARP, float64 linear domain, arithmetic and decisions
+// identical to QaryPolarEncoderDecoder.listDecode with q = 2 (QaryPolarEncoderDecoder.py:118-227, recursiveListDecode
+// :403-757, helpers :759-820, normalize :867-872, QaryMemorylessVectorDistribution.py:26-118).
+//
+// Why this mapping (profiles/r1_c_scl_ncu_summary.md): a list decoder walks ~1000 dependent ops per N = 4096 frame and most
+// of them touch fewer than 300 (path, element) items.  With a frame per CTA (scl_bin.cu) every op costs CTA barriers, every
+// warp re-decodes the op and re-derives the same addresses, the code footprint thrashes the instruction cache, and only
+// ~13 % of the issued instructions are node arithmetic.  Here a warp owns a frame:
+//  * no CTA barrier anywhere -- phases are separated by __syncwarp; a CTA is one warp, up to 32 resident per SM, each at its
+//    own point of its own frame, so the SM always has independent work to issue;
+//  * per-frame state is small enough for that residency: path vectors of levels <= lsm, the short path codewords, the genie
+//    / frozen codeword bits and the list bookkeeping live in ~8 KB of shared memory; the larger levels stream through a
+//    per-warp global scratch (written and re-read with 16-byte coalesced accesses, mostly L2 hits);
+//  * vectors stay in the REFERENCE's index order (children of a node are elements (2h, 2h+1)), so the channel
+//    probabilities are read in the caller's layout -- no ingest / transpose pass;
+//  * lazy path copy: a pruned list is a permutation table per (level, child) (omap), never a copy of a vector;
+//  * pruning is L rounds of a warp arg-max over the candidate metrics (three redux.sync per round on the order-preserving
+//    integer image of the non-negative float64 metrics), giving the oracle's ascending (metric, index) order;
+//  * the order-dependent float64 products of the fast nodes (np.product is a left-to-right product) run one path per lane;
+//  * the genie ("actual") path that listDecode tracks is slot L of every array.
+#include "scl_arith.cuh"
+
+namespace pc {
+
+struct SclwParams {
+    int n, k, L, n_ops, nfrozen, lsm;
+    int rgl;               // path codewords of levels >= rgl live in the global scratch `rg`, smaller levels in shared memory
+    int tx_words;          // extra shared words behind the path vectors so that the prologue's two N-bit temporaries fit
+    int64_t frames;
+    const uint2 *ops2;     // packed ops: x = kind | l << 3 | c << 7 | i << 8, y = fv_idx | coefw_off << 16
+    const int32_t *a_src, *f_src, *info_src, *perm;
+    const uint32_t *stage_mask, *coef_words;
+    const double2 *xy;     // [frames][N] caller layout (reference order)
+    const uint8_t *fv;     // [frames][N-k]
+    const uint8_t *ainfo;  // [frames][k]
+    double2 *vg;           // [grid][vg_stride] scratch for levels > lsm
+    int64_t vg_stride;
+    uint32_t *rg;          // [grid][rg_stride]
+    int64_t rg_stride;
+    uint8_t *info;         // [frames][k]
+    int32_t *result;       // [frames]
+    int32_t *list_size;    // optional, caller layouts
+    double *list_prob, *actual_prob;
+    uint8_t *list_info;
+};
+
+// level l of the path vectors starts at double2 index ((1 << l) - 1) * S; slot stride 1 << l; levels 0 .. n-1
+static size_t sclw_smem_bytes(int n, int L, int lsm, int rgl, int *tx_words) {
+    const int S = L + 1, N = 1 << n, NW = N >= 32 ? N >> 5 : 1;
+    size_t v = (size_t)((2 << lsm) - 1) * S * 16;
+    int tx = 0;
+    if (v < (size_t)2 * NW * 4) tx = (int)(((size_t)2 * NW * 4 - v + 15) / 16 * 4);
+    if (tx_words) *tx_words = tx;
+    size_t b = v + (size_t)tx * 4;
+    b += (size_t)(11 * L + 4) * 8;                                  // prob, newprob, basep, cand, misc
+    b += (size_t)2 * S * scl2_wsum(rgl < n + 1 ? rgl : n + 1) * 4;  // Rw (levels < rgl)
+    b += (size_t)2 * NW * 4;                                        // Abits, Fbits
+    b += (size_t)(3 * L + 3 * (n + 1) + 4) * 4;                     // keep, selsrc, selfk, nl, nin, ivars
+    b += (size_t)4 * L * 2 + L + (size_t)(n + 1) * 2 * L + L;       // pick, delta, omap, eqf
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ double warp_max_f64(double v) {
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, v, sh);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n, N = 1 << n, L = p.L, S = L + 1, k = p.k, lsm = p.lsm;
+    const int NW = N >= 32 ? N >> 5 : 1;
+    const int lane = threadIdx.x;
+    constexpr uint32_t FULL = 0xffffffffu;
+    // ---- shared-memory carve-up (sclw_smem_bytes mirrors this) -----------------------------------------
+    const int VS = ((2 << lsm) - 1) * S;
+    double2 *Vs = (double2 *)smem_raw;
+    double *prob = (double *)(Vs + VS) + p.tx_words / 2;
+    double *newprob = prob + L;
+    double *basep = newprob + L;   // Rate-1 / SPC: prob[t] * product of the non-forked maxima
+    double *cand = basep + L;      // [8 L]
+    double *misc = cand + 8 * L;   // [0] genie product of the node, [1] actual_prob
+    uint32_t *Rw = (uint32_t *)(misc + 4);
+    const int rgl = p.rgl < n + 1 ? p.rgl : n + 1;
+    uint32_t *Abits = Rw + 2 * S * scl2_wsum(rgl);
+    uint32_t *Fbits = Abits + NW;
+    int *keep = (int *)(Fbits + NW);
+    int *selsrc = keep + L, *selfk = selsrc + L;
+    int *nl = selfk + L;          // [(n+1)][2]
+    int *nin = nl + 2 * (n + 1);  // [n+1]
+    int *ivars = nin + (n + 1);   // [4]
+    int16_t *pick = (int16_t *)(ivars + 4);  // [L][4]
+    uint8_t *delta = (uint8_t *)(pick + 4 * L);
+    uint8_t *omap = delta + L;               // [(n+1)][2][L]
+    uint8_t *eqf = omap + (n + 1) * 2 * L;   // [L]
+    uint32_t *T0 = (uint32_t *)smem_raw, *T1 = T0 + NW;  // prologue / epilogue temporaries over the (then dead) path vectors
+
+    double2 *vg = p.vg + (int64_t)blockIdx.x * p.vg_stride - VS;
+    uint32_t *rgc = p.rg + (int64_t)blockIdx.x * p.rg_stride - 2 * S * scl2_wsum(rgl);
+    auto R = [&](int l, int c, int slot) -> uint32_t * {
+        return (l < rgl ? Rw : rgc) + 2 * S * scl2_wsum(l) + (c * S + slot) * scl2_W(l);
+    };
+    auto OM = [&](int l, int c) -> uint8_t * { return omap + (l * 2 + c) * L; };
+    auto Vlev = [&](int l) -> double2 * { return (l <= lsm ? Vs : vg) + ((1 << l) - 1) * S; };
+
+    #pragma unroll 1
+    for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
+        const double2 *xyf = p.xy + f * N;
+        const uint8_t *fvf = p.fv ? p.fv + f * p.nfrozen : nullptr;
+        const uint8_t *aif = p.ainfo + f * k;
+        __syncwarp();
+        // ---- node-local codewords of the genie path (A) and of the frozen values (F) ------------------------
+        // u-domain bits in natural order, masked butterfly up to each fast node's size, then the per-node bit reversal
+        // that turns natural positions into the reference's order.
+        #pragma unroll 1
+        for (int w = 0; w < NW; ++w) {
+            const int pos = 32 * w + lane;
+            uint32_t a = 0, fb = 0;
+            if (pos < N) {
+                const int sa = p.a_src[pos], sf = p.f_src[pos];
+                a = sa >= 0 ? aif[sa] : fvf[~sa];
+                fb = sf >= 0 ? fvf[sf] : 0u;
+            }
+            const uint32_t wa = __ballot_sync(FULL, a & 1u), wf = __ballot_sync(FULL, fb & 1u);
+            if (lane == 0) {
+                T0[w] = wa;
+                T1[w] = wf;
+            }
+        }
+        __syncwarp();
+        #pragma unroll 1
+        for (int t = 0; t < n; ++t) {
+            const int s = 1 << t;
+            #pragma unroll 1
+            for (int w = lane; w < NW; w += 32) {
+                const uint32_t m = p.stage_mask[t * NW + w];
+                if (m) {
+                    if (s < 32) {
+                        T0[w] ^= (T0[w] >> s) & m;
+                        T1[w] ^= (T1[w] >> s) & m;
+                    } else {
+                        T0[w] ^= T0[w + (s >> 5)] & m;
+                        T1[w] ^= T1[w + (s >> 5)] & m;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        #pragma unroll 1
+        for (int w = 0; w < NW; ++w) {
+            const int i = 32 * w + lane;
+            uint32_t a = 0, fb = 0;
+            if (i < N) {
+                const int src = p.perm[i];
+                a = (T0[src >> 5] >> (src & 31)) & 1u;
+                fb = (T1[src >> 5] >> (src & 31)) & 1u;
+            }
+            const uint32_t wa = __ballot_sync(FULL, a), wf = __ballot_sync(FULL, fb);
+            if (lane == 0) {
+                Abits[w] = wa;
+                Fbits[w] = wf;
+            }
+        }
+        if (lane == 0) {
+            prob[0] = 1.0;
+            misc[1] = 1.0;
+            nin[n] = 1;
+            nl[n * 2 + 0] = 1;
+        }
+        __syncwarp();
+
+        uint2 opn = p.ops2[0];
+        #pragma unroll 1
+        for (int oi = 0; oi < p.n_ops; ++oi) {
+            const uint2 opk = opn;
+            if (oi + 1 < p.n_ops) opn = p.ops2[oi + 1];  // the next op's load overlaps this op
+            const int kind = opk.x & 7, l = (opk.x >> 3) & 15, c = (opk.x >> 7) & 1, i0 = (int)(opk.x >> 8);
+            const int size = 1 << l, half = size >> 1;
+            if (kind == OP_MINUS || kind == OP_PLUS) {
+                const bool plus = kind == OP_PLUS;
+                const int cnt = plus ? nl[(l - 1) * 2 + 0] : nin[l];
+                const uint8_t *om = OM(l - 1, 0);
+                const double2 *sbase = l == n ? xyf : Vlev(l);
+                const size_t sstride = l == n ? 0 : (size_t)1 << l;  // the channel level is shared by all paths
+                double2 *dbase = Vlev(l - 1);
+                const uint32_t *rb = R(l - 1, 0, 0);
+                const int rw = scl2_W(l - 1);
+                if (half >= 64) {
+                    // large level: path-major, per-path pointers hoisted, two independent elements in flight per lane
+                    #pragma unroll 1
+                    for (int t = 0; t <= cnt; ++t) {
+                        const int slot = t == cnt ? L : t;
+                        const int src = t == cnt ? L : (plus ? (int)om[t] : t);
+                        const double2 *P = sbase + src * sstride;
+                        double2 *D = dbase + (slot << (l - 1));
+                        const uint32_t *rp = rb + slot * rw;
+                        #pragma unroll 1
+                        for (int h = lane; h < half; h += 64) {
+                            const double2 a0 = P[2 * h], b0 = P[2 * h + 1], a1 = P[2 * h + 64], b1 = P[2 * h + 65];
+                            uint32_t u0 = 0, u1 = 0;
+                            if (plus) {
+                                const uint32_t w0 = rp[h >> 5], w1 = rp[(h >> 5) + 1];
+                                u0 = (w0 >> lane) & 1u;
+                                u1 = (w1 >> lane) & 1u;
+                            }
+                            D[h] = node_update(a0, b0, plus, u0);
+                            D[h + 32] = node_update(a1, b1, plus, u1);
+                        }
+                    }
+                } else {
+                    const int total = (cnt + 1) << (l - 1);
+                    #pragma unroll 1
+                    for (int idx = lane; idx < total; idx += 32) {
+                        const int t = idx >> (l - 1), h = idx & (half - 1);
+                        const int slot = t == cnt ? L : t;
+                        const int src = t == cnt ? L : (plus ? (int)om[t] : t);
+                        const double2 *P = sbase + src * sstride;
+                        const double2 a = P[2 * h], b = P[2 * h + 1];
+                        const uint32_t u1 = plus ? (rb[slot * rw + (h >> 5)] >> (h & 31)) & 1u : 0u;
+                        dbase[(slot << (l - 1)) + h] = node_update(a, b, plus, u1);
+                    }
+                }
+                if (lane == 0) nin[l - 1] = cnt;
+                __syncwarp();
+                continue;
+            }
+            if (kind == OP_COMBINE) {  // :726-754 in reference order: out[2h] = m[h] + p[h], out[2h+1] = -p[h]
+                const int cnt = nl[(l - 1) * 2 + 1];
+                const int Wo = scl2_W(l);
+                const uint8_t *om1 = OM(l - 1, 1), *om0 = OM(l - 1, 0);
+                #pragma unroll 1
+                for (int idx = lane; idx < (cnt + 1) * Wo; idx += 32) {
+                    const int t = idx / Wo, w = idx - t * Wo;
+                    const int slot = t == cnt ? L : t;
+                    const int mi = t == cnt ? L : (int)om1[t];
+                    const int sh = (w & 1) * 16;
+                    const uint32_t m16 = (R(l - 1, 0, mi)[w >> 1] >> sh) & 0xffffu;
+                    const uint32_t p16 = (R(l - 1, 1, slot)[w >> 1] >> sh) & 0xffffu;
+                    R(l, c, slot)[w] = spread16(m16 ^ p16) | (spread16(p16) << 1);
+                }
+                #pragma unroll 1
+                for (int t = lane; t < cnt; t += 32) OM(l, c)[t] = om0[om1[t]];
+                if (lane == 0) nl[l * 2 + c] = cnt;
+                __syncwarp();
+                continue;
+            }
+            // ------------------------------- fast nodes ------------------------------------------------------
+            const int cnt = nin[l];
+            const bool spc = kind == OP_SPC;
+            const int nfork = spc ? 3 : 2;
+            const int fs = kind == OP_REP ? 2 : (spc ? 8 : 4);
+            const uint32_t *coefw = p.coef_words + (opk.y >> 16);
+            const double2 *Vl = l == n ? xyf : Vlev(l);
+            const size_t vstride = l == n ? 0 : (size_t)1 << l;
+            auto vsel = [&](int slot) -> const double2 * { return Vl + slot * vstride; };
+            // bits [32 w, 32 w + 32) of the node-local codeword slices (reference order; i0 is a multiple of the node size)
+            auto aword = [&](int w) -> uint32_t { return size >= 32 ? Abits[(i0 >> 5) + w] : (Abits[i0 >> 5] >> (i0 & 31)); };
+            auto fword = [&](int w) -> uint32_t { return size >= 32 ? Fbits[(i0 >> 5) + w] : (Fbits[i0 >> 5] >> (i0 & 31)); };
+            // left-to-right product of P[j].{x|y} selected by the bits of `bits ^ (cw & xm)` (np.product order, :503-509 etc.)
+            auto chain = [&](const double2 *P, const uint32_t *bw, int bsh, const uint32_t *cw, uint32_t xm) -> double {
+                double pr = 1.0;
+                #pragma unroll 1
+                for (int w0 = 0; w0 < size; w0 += 32) {
+                    const uint32_t bits = (bw[w0 >> 5] >> bsh) ^ (xm ? cw[w0 >> 5] : 0u);
+                    const int m = size - w0 < 32 ? size - w0 : 32;
+                    #pragma unroll 1
+                    for (int b = 0; b < m; ++b) {
+                        const double2 v2 = P[w0 + b];
+                        const double v = (bits >> b) & 1u ? v2.y : v2.x;
+                        pr = (w0 + b) == 0 ? v : __dmul_rn(pr, v);
+                    }
+                }
+                return pr;
+            };
+            const uint32_t *aw = Abits + (i0 >> 5), *fw = Fbits + (i0 >> 5);
+            const int bsh = size >= 32 ? 0 : (i0 & 31);
+            // Rate-1 / SPC: reliabilities (second-largest / largest, :763-768) of every (path, element) with all lanes;
+            // they are parked in the dead level l-1 region of the path vectors (S 2^(l-1) float64 pairs >= cnt 2^l doubles)
+            double *scr = nullptr;
+            if (kind == OP_RATE1 || spc) {
+                scr = (double *)Vlev(l - 1);
+                #pragma unroll 1
+                for (int idx = lane; idx < (cnt << l); idx += 32) {
+                    const double2 v2 = vsel(idx >> l)[idx & (size - 1)];
+                    const double m1 = v2.y > v2.x ? v2.y : v2.x, m2 = v2.y > v2.x ? v2.x : v2.y;
+                    scr[idx] = m2 / m1;
+                }
+                __syncwarp();
+            }
+            // ---- phase 1 (one job per lane): the order-dependent float64 products ---------------------------------
+            if (kind == OP_RATE0) {  // :495-518
+                #pragma unroll 1
+                for (int job = lane; job <= cnt; job += 32) {
+                    const bool act = job == cnt;
+                    const double pr = chain(vsel(act ? L : job), act ? aw : fw, bsh, coefw, 0u);
+                    if (act)
+                        misc[0] = pr;
+                    else
+                        newprob[job] = __dmul_rn(prob[job], pr);
+                }
+            } else if (kind == OP_REP) {  // :521-578
+                #pragma unroll 1
+                for (int job = lane; job <= 2 * cnt; job += 32) {
+                    const bool act = job == 2 * cnt;
+                    const int s = act ? 0 : job / cnt, t = act ? 0 : job - s * cnt;
+                    const double pr = chain(vsel(act ? L : t), act ? aw : fw, bsh, coefw, s ? FULL : 0u);
+                    if (act)
+                        misc[0] = pr;
+                    else
+                        cand[s * cnt + t] = __dmul_rn(prob[t], pr);
+                }
+            } else {  // Rate-1 :581-628 and SPC :631-682
+                const int fval = spc ? fvf[opk.y & 0xffffu] : 0;
+                #pragma unroll 1
+                for (int job = lane; job <= cnt; job += 32) {
+                    if (job == cnt) {
+                        misc[0] = chain(vsel(L), aw, bsh, coefw, 0u);
+                        continue;
+                    }
+                    const int t = job;
+                    const double2 *P = vsel(t);
+                    // pickLeastReliableIndices (:759-768): the npick largest (score, j), ascending;
+                    // sc0 <= sc1 (<= sc2 <= sc3), ties go to the later index (>=), as in the streaming form
+                    double sc0 = -1.0, sc1 = -1.0, sc2 = -1.0, sc3 = -1.0;
+                    int sj0 = 0, sj1 = 0, sj2 = 0, sj3 = 0;
+                    const double *sp = scr + (t << l);
+                    #pragma unroll 1
+                    for (int j = 0; j < size; ++j) {
+                        const double s = sp[j];
+                        if (!spc) {
+                            if (s >= sc1) {
+                                sc0 = sc1, sj0 = sj1;
+                                sc1 = s, sj1 = j;
+                            } else if (s >= sc0) {
+                                sc0 = s, sj0 = j;
+                            }
+                        } else if (s >= sc0) {
+                            if (s >= sc1) {
+                                sc0 = sc1, sj0 = sj1;
+                                if (s >= sc2) {
+                                    sc1 = sc2, sj1 = sj2;
+                                    if (s >= sc3) {
+                                        sc2 = sc3, sj2 = sj3;
+                                        sc3 = s, sj3 = j;
+                                    } else {
+                                        sc2 = s, sj2 = j;
+                                    }
+                                } else {
+                                    sc1 = s, sj1 = j;
+                                }
+                            } else {
+                                sc0 = s, sj0 = j;
+                            }
+                        }
+                    }
+                    int sumconst = 0;
+                    bool first = true;
+                    double prodmax = 1.0;
+                    #pragma unroll 1
+                    for (int j = 0; j < size; ++j) {
+                        bool forked = j == sj0 || j == sj1;
+                        if (spc) forked |= j == sj2 || j == sj3;
+                        if (forked) continue;
+                        const double2 v2 = P[j];
+                        const bool one = v2.y > v2.x;
+                        const double mv = one ? v2.y : v2.x;
+                        sumconst += one ? 1 : 0;
+                        prodmax = first ? mv : __dmul_rn(prodmax, mv);
+                        first = false;
+                    }
+                    basep[t] = __dmul_rn(prob[t], prodmax);
+                    pick[t * 4 + 0] = (int16_t)sj0;
+                    pick[t * 4 + 1] = (int16_t)sj1;
+                    pick[t * 4 + 2] = (int16_t)sj2;
+                    pick[t * 4 + 3] = (int16_t)sj3;
+                    delta[t] = (uint8_t)((fval ^ sumconst) & 1);
+                }
+            }
+            __syncwarp();
+            const int C = kind == OP_RATE0 ? 0 : cnt * fs;
+            if (kind == OP_RATE1 || spc) {
+                // candidate metrics (forkIndices / forkIndicesSpc, :770-820), one (path, fork) per lane
+                #pragma unroll 1
+                for (int idx = lane; idx < C; idx += 32) {
+                    const int t = idx / fs, fk = idx - t * fs;
+                    const double2 *P = vsel(t);
+                    const int16_t *pk = pick + t * 4;
+                    double pf = 1.0;
+                    int sf = 0;
+                    #pragma unroll 1
+                    for (int w = 0; w < nfork; ++w) {
+                        const int dg = (fk >> (nfork - 1 - w)) & 1;
+                        const double2 v2 = P[pk[w]];
+                        const double v = dg ? v2.y : v2.x;
+                        pf = w == 0 ? v : __dmul_rn(pf, v);
+                        sf += dg;
+                    }
+                    if (spc) {
+                        const int dep = (delta[t] ^ sf) & 1;
+                        const double2 v2 = P[pk[3]];
+                        pf = __dmul_rn(pf, dep ? v2.y : v2.x);
+                    }
+                    cand[idx] = __dmul_rn(pf, basep[t]);
+                }
+                __syncwarp();
+            }
+            // ---- prune (:446-451 etc.): keep the ns = min(#nonzero, L) largest candidates under the total order
+            // (metric, index), listed ascending.  Round r extracts the r-th largest: non-negative float64 compare like their
+            // bit patterns, so the arg-max is three integer redux.sync (high word, low word, index); a candidate that has
+            // been taken is zeroed in place (zeros are never taken: r < ns <= #nonzero).
+            int nout = cnt;
+            if (kind != OP_RATE0) {
+                nout = C;
+                if (C > L) {
+                    int nzc = 0;
+                    #pragma unroll 1
+                    for (int cc = lane; cc < C; cc += 32) nzc += cand[cc] != 0.0 ? 1 : 0;
+                    nzc = __reduce_add_sync(FULL, nzc);
+                    const int ns = nzc < L ? nzc : L;
+                    double v0 = lane < C ? cand[lane] : 0.0, v1 = lane + 32 < C ? cand[lane + 32] : 0.0;
+                    #pragma unroll 1
+                    for (int r = 0; r < ns; ++r) {
+                        // this lane's best candidate; among equals the later index wins
+                        double bv = v1 >= v0 ? v1 : v0;
+                        int bi = v1 >= v0 ? lane + 32 : lane;
+                        #pragma unroll 1
+                        for (int cc = lane + 64; cc < C; cc += 32) {
+                            const double v = cand[cc];
+                            if (v >= bv) bv = v, bi = cc;
+                        }
+                        const uint32_t hi = (uint32_t)__double2hiint(bv), lo = (uint32_t)__double2loint(bv);
+                        const uint32_t mh = __reduce_max_sync(FULL, hi);
+                        const uint32_t ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+                        const uint32_t mi = __reduce_max_sync(FULL, (hi == mh && lo == ml) ? (uint32_t)bi + 1u : 0u) - 1u;
+                        if ((mi & 31u) == (uint32_t)lane) {
+                            keep[ns - 1 - r] = (int)mi;
+                            newprob[ns - 1 - r] = bv;
+                            if (mi < 32u)
+                                v0 = 0.0;
+                            else if (mi < 64u)
+                                v1 = 0.0;
+                            else
+                                cand[mi] = 0.0;
+                        }
+                    }
+                    nout = ns;
+                } else {
+                    #pragma unroll 1
+                    for (int t = lane; t < C; t += 32) {
+                        keep[t] = t;
+                        newprob[t] = cand[t];
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- phase 2: lazy copy (omap), normalise (:867-872) ---------------------------------------------------
+            {
+                if (kind == OP_RATE0) {
+                    #pragma unroll 1
+                    for (int t = lane; t < cnt; t += 32) OM(l, c)[t] = (uint8_t)t;
+                } else {
+                    #pragma unroll 1
+                    for (int t = lane; t < nout; t += 32) {
+                        const int cidx = keep[t];
+                        int src, sel;
+                        if (kind == OP_REP) {
+                            sel = cidx / cnt;
+                            src = cidx - sel * cnt;
+                        } else {
+                            src = cidx / fs;
+                            sel = cidx - src * fs;
+                        }
+                        selsrc[t] = src;
+                        selfk[t] = sel;
+                        OM(l, c)[t] = (uint8_t)src;
+                    }
+                }
+                double mx = lane < nout ? newprob[lane] : newprob[0];
+                #pragma unroll 1
+                for (int t = lane + 32; t < nout; t += 32) {
+                    const double v = newprob[t];
+                    if (v > mx) mx = v;
+                }
+                mx = warp_max_f64(mx);
+                #pragma unroll 1
+                for (int t = lane; t < nout; t += 32) prob[t] = newprob[t] / mx;
+                if (lane == 0) {
+                    misc[1] = __dmul_rn(misc[1], misc[0] / mx);
+                    nl[l * 2 + c] = nout;
+                }
+            }
+            __syncwarp();
+            // ---- phase 3: node codewords of the surviving paths and of the genie path ---------------------------
+            {
+                const int Wl = scl2_W(l);
+                const uint32_t smask = size >= 32 ? 0xffffffffu : ((1u << size) - 1u);
+                #pragma unroll 1
+                for (int w = lane; w < Wl; w += 32) R(l, c, L)[w] = (aw[w] >> bsh) & smask;
+                if (kind == OP_RATE0 || kind == OP_REP) {
+                    #pragma unroll 1
+                    for (int idx = lane; idx < nout * Wl; idx += 32) {
+                        const int t = idx / Wl, w = idx - t * Wl;
+                        uint32_t v = (fw[w] >> bsh) & smask;
+                        if (kind == OP_REP && selfk[t]) v ^= coefw[w];
+                        R(l, c, t)[w] = v;
+                    }
+                } else {
+                    auto sym = [&](int t, int j) -> uint32_t {
+                        const int src = selsrc[t], fk = selfk[t];
+                        const int16_t *pk = pick + src * 4;
+                        #pragma unroll 1
+                        for (int w = 0; w < nfork; ++w)
+                            if (pk[w] == j) return (uint32_t)((fk >> (nfork - 1 - w)) & 1);
+                        if (spc && pk[3] == j) return (uint32_t)((delta[src] ^ __popc(fk)) & 1);
+                        const double2 v2 = vsel(src)[j];
+                        return v2.y > v2.x ? 1u : 0u;
+                    };
+                    if (size >= 32) {
+                        #pragma unroll 1
+                        for (int base = 0; base < nout * size; base += 32) {
+                            const int idx = base + lane;
+                            const int t = idx >> l, j = idx & (size - 1);
+                            const uint32_t wv = __ballot_sync(FULL, sym(t, j));
+                            if (lane == 0) R(l, c, t)[j >> 5] = wv;
+                        }
+                    } else {
+                        // 32 / size paths per round, one symbol per lane; a path's word is its slice of the ballot
+                        const int ppr = 32 >> l;
+                        #pragma unroll 1
+                        for (int t0 = 0; t0 < nout; t0 += ppr) {
+                            const int t = t0 + (lane >> l), j = lane & (size - 1);
+                            const uint32_t wv = __ballot_sync(FULL, t < nout ? sym(t, j) : 0u);
+                            if (j == 0 && t < nout) R(l, c, t)[0] = (wv >> (lane & ~(size - 1))) & smask;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- final selection (listDecode :172-213): the genie path is in the list iff a root codeword equals it ----
+        const int cnt = nl[n * 2 + 0];
+        #pragma unroll 1
+        for (int t = 0; t < cnt; ++t) {
+            const uint32_t *a = R(n, 0, t), *b = R(n, 0, L);
+            bool eq = true;
+            #pragma unroll 1
+            for (int w = lane; w < NW; w += 32) eq &= a[w] == b[w];
+            eq = __all_sync(FULL, eq);
+            if (lane == 0) eqf[t] = eq ? 1 : 0;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int found = -1;
+            #pragma unroll 1
+            for (int t = 0; t < cnt && found < 0; ++t)
+                if (eqf[t]) found = t;
+            double maxp = prob[0], minp = prob[0];
+            #pragma unroll 1
+            for (int t = 1; t < cnt; ++t) {
+                maxp = prob[t] > maxp ? prob[t] : maxp;
+                minp = prob[t] < minp ? prob[t] : minp;
+            }
+            const double ap = misc[1];
+            int res;
+            if (found >= 0)
+                res = prob[found] == maxp ? 0 : 1;
+            else
+                res = ap > maxp ? 2 : (ap == maxp ? 3 : (ap >= minp ? 4 : 5));
+            ivars[1] = found >= 0 ? found : 0;
+            p.result[f] = res;
+            if (p.list_size) {
+                p.list_size[f] = cnt;
+                p.actual_prob[f] = ap;
+                #pragma unroll 1
+                for (int t = 0; t < L; ++t) p.list_prob[f * L + t] = t < cnt ? prob[t] : 0.0;
+            }
+        }
+        __syncwarp();
+        // information of a path = gather of T(root codeword): bit-reverse to natural order, butterfly, gather
+        const int sel = ivars[1];
+        const int npaths = p.list_info ? cnt : 1;
+        #pragma unroll 1
+        for (int pi = 0; pi < npaths; ++pi) {
+            const int t = p.list_info ? pi : sel;
+            const uint32_t *root = R(n, 0, t);
+            #pragma unroll 1
+            for (int w = 0; w < NW; ++w) {
+                const int pos = 32 * w + lane;
+                uint32_t b = 0;
+                if (pos < N) {
+                    const uint32_t r = bitrev_n((uint32_t)pos, n);
+                    b = (root[r >> 5] >> (r & 31)) & 1u;
+                }
+                const uint32_t wv = __ballot_sync(FULL, b);
+                if (lane == 0) T0[w] = wv;
+            }
+            __syncwarp();
+            #pragma unroll 1
+            for (int st = 0; st < n; ++st) {
+                const int s = 1 << st;
+                #pragma unroll 1
+                for (int w = lane; w < NW; w += 32) {
+                    if (s < 32) {
+                        const uint32_t m = s == 1 ? 0x55555555u : s == 2 ? 0x33333333u : s == 4 ? 0x0f0f0f0fu : s == 8 ? 0x00ff00ffu : 0x0000ffffu;
+                        T0[w] ^= (T0[w] >> s) & m;
+                    } else if (!(w & (s >> 5))) {
+                        T0[w] ^= T0[w + (s >> 5)];
+                    }
+                }
+                __syncwarp();
+            }
+            #pragma unroll 1
+            for (int j = lane; j < k; j += 32) {
+                const int pos = p.info_src[j];
+                const uint8_t v = (uint8_t)((T0[pos >> 5] >> (pos & 31)) & 1u);
+                if (p.list_info) p.list_info[(f * L + pi) * k + j] = v;
+                if (t == sel) p.info[f * k + j] = v;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+struct SclwConfig {
+    int lsm, rgl, grid, tx_words;
+    size_t smem, vg_stride, rg_stride;  // vg_stride in double2 elements, rg_stride in words, per warp
+    bool ok;
+};
+
+static int envw_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+
+static SclwConfig sclw_config(const pc_plan *plan, int L, int64_t B) {
+    SclwConfig c{};
+    const int n = plan->n, S = L + 1;
+    c.ok = false;
+    if (plan->q != 2 || n < 1 || n > 13 || L > 32) return c;
+    int rgl = envw_int("PC_SCLW_RGL", 9);
+    if (rgl < 1) rgl = 1;
+    if (rgl > n + 1) rgl = n + 1;
+    c.rgl = rgl;
+    // shared-memory budget per warp: aim at `target` resident warps per SM
+    const int target = envw_int("PC_SCLW_WARPS_PER_SM", 24);
+    const size_t budget = (size_t)(227 * 1024) / (size_t)(target > 0 ? target : 1) - 1024;
+    int lsm = n - 1;
+    while (lsm > 0 && sclw_smem_bytes(n, L, lsm, rgl, nullptr) > budget) --lsm;
+    const int forced = envw_int("PC_SCLW_LSM", -1);
+    if (forced >= 0 && forced <= n - 1) lsm = forced;
+    c.lsm = lsm;
+    c.smem = sclw_smem_bytes(n, L, lsm, rgl, &c.tx_words);
+    if (c.smem > 220 * 1024) return c;
+    int per_sm = (int)((227 * 1024) / (c.smem + 1024));
+    if (per_sm > 32) per_sm = 32;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)num_sms() * per_sm;
+    if (grid > B) grid = B;
+    c.grid = (int)(grid > 0 ? grid : 1);
+    const int64_t vtot = (int64_t)((1 << n) - 1) * S, vs = (int64_t)((2 << lsm) - 1) * S;
+    c.vg_stride = (size_t)(vtot > vs ? vtot - vs : 0) + 2;
+    c.rg_stride = (size_t)2 * S * (scl2_wsum(n + 1) - scl2_wsum(rgl)) + 4;
+    c.ok = true;
+    return c;
+}
+
+bool sclw_supported(const pc_plan *plan, int L) {
+    if (envw_int("PC_SCL_GENERIC", 0) || envw_int("PC_SCL_CTA", 0)) return false;
+    return sclw_config(plan, L, 1).ok;
+}
+
+size_t sclw_workspace_bytes(const pc_plan *plan, int L, int64_t B) {
+    const SclwConfig c = sclw_config(plan, L, B);
+    return align256(align256((size_t)c.grid * c.vg_stride * sizeof(double2) + 256) + (size_t)c.grid * c.rg_stride * 4 + 256);
+}
+
+int sclw_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_xy, const uint8_t *d_fv, const uint8_t *d_ainfo,
+                int64_t B, uint8_t *d_info, int32_t *d_res, int32_t *d_lsize, double *d_lprob, double *d_aprob,
+                uint8_t *d_linfo, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const SclwConfig c = sclw_config(plan, L, B);
+    if (!c.ok) {
+        set_error("sclw: unsupported configuration");
+        return PC_ERR_UNSUPPORTED;
+    }
+    const size_t need = sclw_workspace_bytes(plan, L, B);
+    if (need > ws_bytes) {
+        set_error("workspace too small: %zu bytes given, %zu needed", ws_bytes, need);
+        return PC_ERR_NOMEM;
+    }
+    SclwParams p{};
+    p.n = plan->n;
+    p.k = plan->k;
+    p.L = L;
+    p.n_ops = (int)T->ops.size();
+    p.nfrozen = plan->N - plan->k;
+    p.lsm = c.lsm;
+    p.rgl = c.rgl;
+    p.tx_words = c.tx_words;
+    p.frames = B;
+    p.ops2 = T->d_ops2;
+    p.a_src = T->d_a_src;
+    p.f_src = T->d_f_src;
+    p.info_src = T->d_info_src;
+    p.perm = T->d_perm;
+    p.stage_mask = T->d_stage_mask;
+    p.coef_words = T->d_rep_coef_words;
+    p.xy = (const double2 *)d_xy;
+    p.fv = d_fv;
+    p.ainfo = d_ainfo;
+    p.vg = (double2 *)ws;
+    p.vg_stride = (int64_t)c.vg_stride;
+    p.rg = (uint32_t *)((char *)ws + align256((size_t)c.grid * c.vg_stride * sizeof(double2) + 256));
+    p.rg_stride = (int64_t)c.rg_stride;
+    p.info = d_info;
+    p.result = d_res;
+    p.list_size = d_lsize;
+    p.list_prob = d_lprob;
+    p.actual_prob = d_aprob;
+    p.list_info = d_linfo;
+    PC_CUDA(cudaFuncSetAttribute(sclw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    prof_mark(st);
+    sclw_kernel<<<c.grid, 32, c.smem, st>>>(p);
+    prof_mark(st);
+    PC_LAUNCH_CHECK();
+    return PC_OK;
+}
+
+}  // namespace pc

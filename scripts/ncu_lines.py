@@ -1,28 +1,43 @@
-#!/usr/bin/env python
-"""Summarise an `ncu --page source --csv --print-source cuda,sass` dump per CUDA source line:
-   python tools_ncu_lines.py dump.csv [top]"""
-import csv, sys
-rows = list(csv.reader(open(sys.argv[1])))
-top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-hdr = None
-out = []
+"""Per-source-line summary of an ncu report: python scripts/ncu_lines.py <report.ncu-rep> [min_pct]
+(reads `ncu --page source --print-source cuda,sass --csv`; needs -lineinfo and --import-source on)."""
+import csv, subprocess, sys
+rep = sys.argv[1]
+thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.8
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(txt.splitlines()))
 fname = ""
+hdr = None
+lines = []
 for r in rows:
-    if len(r) >= 2 and r[0] == "File Path":
-        fname = r[1].split("/")[-1]
-    if len(r) > 10 and r[0] == "Line No":
-        hdr = r
+    if not r:
         continue
-    if hdr and len(r) == len(hdr) and r[0] != "":
-        d = dict(zip(hdr[4:], r[4:]))
+    if r[0] == "File Path":
+        fname = r[1].split("/")[-1]
+        continue
+    if r[0] == "Line No":
+        hdr = r
+        ci, si, ti = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
+        continue
+    if hdr and r[0] not in ("", "Function Name") and len(r) > ci:
         try:
-            out.append((fname, int(r[0]), r[1].strip()[:90], int(d["# Samples"]), int(d["Instructions Executed"]),
-                        {k: int(v) for k, v in d.items() if k.startswith("stall_") and "Not Issued" not in k and v.isdigit() and int(v) > 0}))
-        except Exception:
+            lines.append((fname, int(r[0]), r[1].strip(), float(r[ci] or 0), float(r[si] or 0), float(r[ti] or 0)))
+        except ValueError:
             pass
-tot_s = sum(o[3] for o in out) or 1
-tot_i = sum(o[4] for o in out) or 1
-print("total samples", tot_s, "total warp instr", tot_i)
-for o in sorted(out, key=lambda o: -o[3])[:top]:
-    st = sorted(o[5].items(), key=lambda kv: -kv[1])[:3]
-    print("%s:%d  samp %.1f%%  inst %.1f%%  %s | %s" % (o[0], o[1], 100 * o[3] / tot_s, 100 * o[4] / tot_i, st, o[2]))
+ti_ = sum(l[3] for l in lines)
+ts_ = sum(l[4] for l in lines)
+print("total warp inst %.4g samples %.4g" % (ti_, ts_))
+for f, ln, src, i, s, t in lines:
+    if 100 * i / ti_ >= thr or 100 * s / ts_ >= thr:
+        print("%-14s %4d inst %5.1f%% samp %5.1f%% thr/inst %4.1f  %s" % (f, ln, 100 * i / ti_, 100 * s / ts_, t / i if i else 0, src[:100]))
+if len(sys.argv) > 3:  # line ranges "a-b,c-d,..." of the main .cu file
+    main = max(set(l[0] for l in lines), key=lambda f: sum(l[3] for l in lines if l[0] == f))
+    for rg in sys.argv[3].split(","):
+        a, b = (int(v) for v in rg.split("-"))
+        i = sum(l[3] for l in lines if l[0] == main and a <= l[1] <= b)
+        s = sum(l[4] for l in lines if l[0] == main and a <= l[1] <= b)
+        t = sum(l[5] for l in lines if l[0] == main and a <= l[1] <= b)
+        print("%s %4d-%4d inst %5.1f%% samp %5.1f%% thr/inst %4.1f" % (main, a, b, 100 * i / ti_, 100 * s / ts_, t / i if i else 0))
+    for f in sorted(set(l[0] for l in lines)):
+        if f != main:
+            i = sum(l[3] for l in lines if l[0] == f); s = sum(l[4] for l in lines if l[0] == f)
+            print("%s inst %5.1f%% samp %5.1f%%" % (f, 100 * i / ti_, 100 * s / ts_))
