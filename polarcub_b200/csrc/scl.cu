@@ -183,6 +183,18 @@ SclTables *scl_tables(const pc_plan *p) {
         for (const SclOp &o : T->ops)
             T->ops2.push_back(make_uint2((uint32_t)o.kind | (uint32_t)o.l << 3 | (uint32_t)o.c << 7 | (uint32_t)o.i << 8,
                                          (uint32_t)(o.fv_idx & 0xffff) | (uint32_t)(o.kind == OP_REP ? o.coefw_off : 0) << 16));
+        for (size_t a = 0; a < T->ops2.size(); ++a) {
+            uint2 o = T->ops2[a];
+            const int kind = o.x & 7, l = (o.x >> 3) & 15;
+            if ((kind == OP_MINUS || kind == OP_PLUS) && l >= 7 && a + 1 < T->ops2.size()) {
+                const uint2 nx = T->ops2[a + 1];
+                if ((nx.x & 7) == OP_MINUS && (int)((nx.x >> 3) & 15) == l - 1) {
+                    o.x |= 1u << 30;
+                    ++a;
+                }
+            }
+            T->ops3.push_back(o);
+        }
         T->stage_mask.assign((size_t)(p->n > 0 ? p->n : 1) * NW, 0u);
         for (int t = 0; t < p->n; ++t)
             for (int pos = 0; pos < N; ++pos)
@@ -192,7 +204,8 @@ SclTables *scl_tables(const pc_plan *p) {
         upload(T->d_f_src, T->f_src) != cudaSuccess || upload(T->d_info_src, T->info_src) != cudaSuccess ||
         upload(T->d_node_level, T->node_level) != cudaSuccess || upload(T->d_rep_coef, T->rep_coef) != cudaSuccess ||
         upload(T->d_rep_coef_words, T->rep_coef_words) != cudaSuccess || upload(T->d_stage_mask, T->stage_mask) != cudaSuccess ||
-        upload(T->d_perm, T->perm) != cudaSuccess || upload(T->d_ops2, T->ops2) != cudaSuccess) {
+        upload(T->d_perm, T->perm) != cudaSuccess || upload(T->d_ops2, T->ops2) != cudaSuccess ||
+        upload(T->d_ops3, T->ops3) != cudaSuccess) {
         set_error("scl tables: device upload failed");
         return nullptr;
     }
@@ -207,7 +220,7 @@ void scl_tables_release(const pc_plan *p) {
     SclTables *T = it->second;
     cudaFree(T->d_ops), cudaFree(T->d_a_src), cudaFree(T->d_f_src), cudaFree(T->d_info_src);
     cudaFree(T->d_node_level), cudaFree(T->d_rep_coef);
-    cudaFree(T->d_rep_coef_words), cudaFree(T->d_stage_mask), cudaFree(T->d_perm), cudaFree(T->d_ops2);
+    cudaFree(T->d_rep_coef_words), cudaFree(T->d_stage_mask), cudaFree(T->d_perm), cudaFree(T->d_ops2), cudaFree(T->d_ops3);
     delete T;
     g_scl_tables.erase(it);
 }

@@ -32,6 +32,7 @@ struct SclTables {
     std::vector<uint32_t> stage_mask;      // [n][max(1,N/32)] natural-order masked-butterfly masks: bit pos set iff
                                            // (pos & 2^t) == 0 and the fast node holding pos is larger than 2^t
     std::vector<uint2> ops2;               // packed ops: x = kind | l << 3 | c << 7 | i << 8, y = fv_idx | coefw_off << 16
+    std::vector<uint2> ops3;               // scl_warp.cu: ops2 with PLUS/MINUS (l >= 7) + MINUS (l-1) pairs fused (x bit 30)
     std::vector<int32_t> perm;             // [N] reference position -> natural position inside its fast node
     SclOp *d_ops = nullptr;
     int32_t *d_a_src = nullptr, *d_f_src = nullptr, *d_info_src = nullptr;
@@ -39,7 +40,7 @@ struct SclTables {
     uint8_t *d_rep_coef = nullptr;
     uint32_t *d_rep_coef_words = nullptr, *d_stage_mask = nullptr;
     int32_t *d_perm = nullptr;
-    uint2 *d_ops2 = nullptr;
+    uint2 *d_ops2 = nullptr, *d_ops3 = nullptr;
 };
 
 

@@ -27,7 +27,7 @@ struct SclwParams {
     int rgl;               // path codewords of levels >= rgl live in the global scratch `rg`, smaller levels in shared memory
     int tx_words;          // extra shared words behind the path vectors so that the prologue's two N-bit temporaries fit
     int64_t frames;
-    const uint2 *ops2;     // packed ops: x = kind | l << 3 | c << 7 | i << 8, y = fv_idx | coefw_off << 16
+    const uint2 *ops;      // packed ops (SclTables::ops3): x = kind | l << 3 | c << 7 | i << 8 | fused << 30, y = fv_idx | coefw_off << 16
     const int32_t *a_src, *f_src, *info_src, *perm;
     const uint32_t *stage_mask, *coef_words;
     const double2 *xy;     // [frames][N] caller layout (reference order)
@@ -53,9 +53,10 @@ static size_t sclw_smem_bytes(int n, int L, int lsm, int rgl, int *tx_words) {
     if (tx_words) *tx_words = tx;
     size_t b = v + (size_t)tx * 4;
     b += (size_t)(11 * L + 4) * 8;                                  // prob, newprob, basep, cand, misc
+    b += (size_t)2 * (n + 1) * 8;                                   // vptr, rptr
     b += (size_t)2 * S * scl2_wsum(rgl < n + 1 ? rgl : n + 1) * 4;  // Rw (levels < rgl)
     b += (size_t)2 * NW * 4;                                        // Abits, Fbits
-    b += (size_t)(3 * L + 3 * (n + 1) + 4) * 4;                     // keep, selsrc, selfk, nl, nin, ivars
+    b += (size_t)(4 * L + 3 * (n + 1) + 4) * 4;                     // keep, selsrc, selfk, hds, nl, nin, ivars
     b += (size_t)4 * L * 2 + L + (size_t)(n + 1) * 2 * L + L;       // pick, delta, omap, eqf
     return (b + 15) & ~(size_t)15;
 }
@@ -83,13 +84,16 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
     double *basep = newprob + L;   // Rate-1 / SPC: prob[t] * product of the non-forked maxima
     double *cand = basep + L;      // [8 L]
     double *misc = cand + 8 * L;   // [0] genie product of the node, [1] actual_prob
-    uint32_t *Rw = (uint32_t *)(misc + 4);
+    double2 **vptr = (double2 **)(misc + 4);        // [n+1] base of the level-l path vectors ([n]: the frame's channel input)
+    uint32_t **rptr = (uint32_t **)(vptr + n + 1);  // [n+1] base of the level-l path codewords
+    uint32_t *Rw = (uint32_t *)(rptr + n + 1);
     const int rgl = p.rgl < n + 1 ? p.rgl : n + 1;
     uint32_t *Abits = Rw + 2 * S * scl2_wsum(rgl);
     uint32_t *Fbits = Abits + NW;
     int *keep = (int *)(Fbits + NW);
     int *selsrc = keep + L, *selfk = selsrc + L;
-    int *nl = selfk + L;          // [(n+1)][2]
+    uint32_t *hds = (uint32_t *)(selfk + L);  // [L] hard-decision words of fast nodes smaller than 32
+    int *nl = (int *)(hds + L);   // [(n+1)][2]
     int *nin = nl + 2 * (n + 1);  // [n+1]
     int *ivars = nin + (n + 1);   // [4]
     int16_t *pick = (int16_t *)(ivars + 4);  // [L][4]
@@ -98,15 +102,18 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
     uint8_t *eqf = omap + (n + 1) * 2 * L;   // [L]
     uint32_t *T0 = (uint32_t *)smem_raw, *T1 = T0 + NW;  // prologue / epilogue temporaries over the (then dead) path vectors
 
-    double2 *vg = p.vg + (int64_t)blockIdx.x * p.vg_stride - VS;
-    uint32_t *rgc = p.rg + (int64_t)blockIdx.x * p.rg_stride - 2 * S * scl2_wsum(rgl);
-    auto R = [&](int l, int c, int slot) -> uint32_t * {
-        return (l < rgl ? Rw : rgc) + 2 * S * scl2_wsum(l) + (c * S + slot) * scl2_W(l);
-    };
+    {
+        double2 *vg = p.vg + (int64_t)blockIdx.x * p.vg_stride - VS;
+        uint32_t *rgc = p.rg + (int64_t)blockIdx.x * p.rg_stride - 2 * S * scl2_wsum(rgl);
+        for (int l = lane; l <= n; l += 32) {
+            vptr[l] = (l <= lsm ? Vs : vg) + ((1 << l) - 1) * S;
+            rptr[l] = (l < rgl ? Rw : rgc) + 2 * S * scl2_wsum(l);
+        }
+    }
+    auto R = [&](int l, int c, int slot) -> uint32_t * { return rptr[l] + (c * S + slot) * scl2_W(l); };
     auto OM = [&](int l, int c) -> uint8_t * { return omap + (l * 2 + c) * L; };
-    auto Vlev = [&](int l) -> double2 * { return (l <= lsm ? Vs : vg) + ((1 << l) - 1) * S; };
 
-    #pragma unroll 1
+#pragma unroll 1
     for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
         const double2 *xyf = p.xy + f * N;
         const uint8_t *fvf = p.fv ? p.fv + f * p.nfrozen : nullptr;
@@ -115,7 +122,7 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
         // ---- node-local codewords of the genie path (A) and of the frozen values (F) ------------------------
         // u-domain bits in natural order, masked butterfly up to each fast node's size, then the per-node bit reversal
         // that turns natural positions into the reference's order.
-        #pragma unroll 1
+#pragma unroll 1
         for (int w = 0; w < NW; ++w) {
             const int pos = 32 * w + lane;
             uint32_t a = 0, fb = 0;
@@ -131,10 +138,10 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
             }
         }
         __syncwarp();
-        #pragma unroll 1
+#pragma unroll 1
         for (int t = 0; t < n; ++t) {
             const int s = 1 << t;
-            #pragma unroll 1
+#pragma unroll 1
             for (int w = lane; w < NW; w += 32) {
                 const uint32_t m = p.stage_mask[t * NW + w];
                 if (m) {
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
             }
             __syncwarp();
         }
-        #pragma unroll 1
+#pragma unroll 1
         for (int w = 0; w < NW; ++w) {
             const int i = 32 * w + lane;
             uint32_t a = 0, fb = 0;
@@ -169,50 +176,80 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
             misc[1] = 1.0;
             nin[n] = 1;
             nl[n * 2 + 0] = 1;
+            vptr[n] = (double2 *)xyf;
         }
         __syncwarp();
 
-        uint2 opn = p.ops2[0];
-        #pragma unroll 1
+        uint2 opn = p.ops[0];
+#pragma unroll 1
         for (int oi = 0; oi < p.n_ops; ++oi) {
             const uint2 opk = opn;
-            if (oi + 1 < p.n_ops) opn = p.ops2[oi + 1];  // the next op's load overlaps this op
-            const int kind = opk.x & 7, l = (opk.x >> 3) & 15, c = (opk.x >> 7) & 1, i0 = (int)(opk.x >> 8);
-            const int size = 1 << l, half = size >> 1;
+            if (oi + 1 < p.n_ops) opn = p.ops[oi + 1];  // the next op's load overlaps this op
+            const int kind = opk.x & 7, l = (opk.x >> 3) & 15, c = (opk.x >> 7) & 1, i0 = (int)((opk.x >> 8) & 0x3fffffu);
+            const int size = 1 << l;
             if (kind == OP_MINUS || kind == OP_PLUS) {
                 const bool plus = kind == OP_PLUS;
                 const int cnt = plus ? nl[(l - 1) * 2 + 0] : nin[l];
                 const uint8_t *om = OM(l - 1, 0);
-                const double2 *sbase = l == n ? xyf : Vlev(l);
-                const size_t sstride = l == n ? 0 : (size_t)1 << l;  // the channel level is shared by all paths
-                double2 *dbase = Vlev(l - 1);
+                const double2 *sbase = vptr[l];
+                const int sstride = l == n ? 0 : size;  // the channel level is shared by all paths
+                double2 *dbase = vptr[l - 1];
                 const uint32_t *rb = R(l - 1, 0, 0);
                 const int rw = scl2_W(l - 1);
-                if (half >= 64) {
-                    // large level: path-major, per-path pointers hoisted, two independent elements in flight per lane
-                    #pragma unroll 1
-                    for (int t = 0; t <= cnt; ++t) {
-                        const int slot = t == cnt ? L : t;
+                const bool fused = (opk.x >> 30) & 1u;  // PLUS / MINUS (l) followed by MINUS (l-1): one pass, two levels out
+                if (l >= 7) {
+                    // large level: iteration `it` covers 128 consecutive source elements of one path; the loads of iteration
+                    // it+1 are issued before the arithmetic of iteration it.  Plain: lane h and h+32 of the 64 outputs.
+                    // Fused: the lane's 4 consecutive elements give 2 outputs of level l-1 and 1 of level l-2.
+                    const int bsh = l - 7, bmask = (1 << bsh) - 1;
+                    const int niter = (cnt + 1) << bsh;
+                    double2 *d2base = vptr[l - 2];
+                    const int o2 = fused ? 2 : 64;
+                    auto src_ptr = [&](int it) -> const double2 * {
+                        const int t = it >> bsh, blk = it & bmask;
                         const int src = t == cnt ? L : (plus ? (int)om[t] : t);
-                        const double2 *P = sbase + src * sstride;
-                        double2 *D = dbase + (slot << (l - 1));
-                        const uint32_t *rp = rb + slot * rw;
-                        #pragma unroll 1
-                        for (int h = lane; h < half; h += 64) {
-                            const double2 a0 = P[2 * h], b0 = P[2 * h + 1], a1 = P[2 * h + 64], b1 = P[2 * h + 65];
-                            uint32_t u0 = 0, u1 = 0;
-                            if (plus) {
-                                const uint32_t w0 = rp[h >> 5], w1 = rp[(h >> 5) + 1];
-                                u0 = (w0 >> lane) & 1u;
-                                u1 = (w1 >> lane) & 1u;
-                            }
-                            D[h] = node_update(a0, b0, plus, u0);
-                            D[h + 32] = node_update(a1, b1, plus, u1);
+                        return sbase + src * sstride + blk * 128 + (fused ? 4 * lane : 2 * lane);
+                    };
+                    const double2 *q = src_ptr(0);
+                    double2 e0 = q[0], e1 = q[1], e2 = q[o2], e3 = q[o2 + 1];
+#pragma unroll 1
+                    for (int it = 0; it < niter; ++it) {
+                        double2 f0 = e0, f1 = e1, f2 = e2, f3 = e3;
+                        if (it + 1 < niter) {
+                            q = src_ptr(it + 1);
+                            f0 = q[0], f1 = q[1], f2 = q[o2], f3 = q[o2 + 1];
                         }
+                        const int t = it >> bsh, blk = it & bmask;
+                        const int slot = t == cnt ? L : t;
+                        uint32_t u0 = 0, u1 = 0;
+                        if (plus) {
+                            const uint32_t *rp = rb + slot * rw + 2 * blk;
+                            if (fused) {
+                                const uint32_t w = rp[lane >> 4];
+                                u0 = (w >> ((2 * lane) & 31)) & 1u;
+                                u1 = (w >> ((2 * lane + 1) & 31)) & 1u;
+                            } else {
+                                u0 = (rp[0] >> lane) & 1u;
+                                u1 = (rp[1] >> lane) & 1u;
+                            }
+                        }
+                        const double2 y0 = node_update(e0, e1, plus, u0), y1 = node_update(e2, e3, plus, u1);
+                        double2 *D = dbase + (slot << (l - 1)) + blk * 64;
+                        if (fused) {
+                            D[2 * lane] = y0;
+                            D[2 * lane + 1] = y1;
+                            d2base[(slot << (l - 2)) + blk * 32 + lane] = node_update(y0, y1, false, 0u);
+                        } else {
+                            D[lane] = y0;
+                            D[lane + 32] = y1;
+                        }
+                        e0 = f0, e1 = f1, e2 = f2, e3 = f3;
                     }
+                    if (lane == 0 && fused) nin[l - 2] = cnt;
                 } else {
+                    const int half = size >> 1;
                     const int total = (cnt + 1) << (l - 1);
-                    #pragma unroll 1
+#pragma unroll 1
                     for (int idx = lane; idx < total; idx += 32) {
                         const int t = idx >> (l - 1), h = idx & (half - 1);
                         const int slot = t == cnt ? L : t;
@@ -229,19 +266,22 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
             }
             if (kind == OP_COMBINE) {  // :726-754 in reference order: out[2h] = m[h] + p[h], out[2h+1] = -p[h]
                 const int cnt = nl[(l - 1) * 2 + 1];
-                const int Wo = scl2_W(l);
+                const int Wo = scl2_W(l), wsh = l <= 5 ? 0 : l - 5;
                 const uint8_t *om1 = OM(l - 1, 1), *om0 = OM(l - 1, 0);
-                #pragma unroll 1
-                for (int idx = lane; idx < (cnt + 1) * Wo; idx += 32) {
-                    const int t = idx / Wo, w = idx - t * Wo;
+                const uint32_t *rm = R(l - 1, 0, 0), *rp = R(l - 1, 1, 0);
+                uint32_t *ro = R(l, c, 0);
+                const int Wc = scl2_W(l - 1);
+#pragma unroll 1
+                for (int idx = lane; idx < (cnt + 1) << wsh; idx += 32) {
+                    const int t = idx >> wsh, w = idx & (Wo - 1);
                     const int slot = t == cnt ? L : t;
                     const int mi = t == cnt ? L : (int)om1[t];
                     const int sh = (w & 1) * 16;
-                    const uint32_t m16 = (R(l - 1, 0, mi)[w >> 1] >> sh) & 0xffffu;
-                    const uint32_t p16 = (R(l - 1, 1, slot)[w >> 1] >> sh) & 0xffffu;
-                    R(l, c, slot)[w] = spread16(m16 ^ p16) | (spread16(p16) << 1);
+                    const uint32_t m16 = (rm[mi * Wc + (w >> 1)] >> sh) & 0xffffu;
+                    const uint32_t p16 = (rp[slot * Wc + (w >> 1)] >> sh) & 0xffffu;
+                    ro[slot * Wo + w] = spread16(m16 ^ p16) | (spread16(p16) << 1);
                 }
-                #pragma unroll 1
+#pragma unroll 1
                 for (int t = lane; t < cnt; t += 32) OM(l, c)[t] = om0[om1[t]];
                 if (lane == 0) nl[l * 2 + c] = cnt;
                 __syncwarp();
@@ -252,150 +292,166 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
             const bool spc = kind == OP_SPC;
             const int nfork = spc ? 3 : 2;
             const int fs = kind == OP_REP ? 2 : (spc ? 8 : 4);
+            const int Wl = scl2_W(l);
+            const uint32_t smask = size >= 32 ? 0xffffffffu : ((1u << size) - 1u);
             const uint32_t *coefw = p.coef_words + (opk.y >> 16);
-            const double2 *Vl = l == n ? xyf : Vlev(l);
-            const size_t vstride = l == n ? 0 : (size_t)1 << l;
-            auto vsel = [&](int slot) -> const double2 * { return Vl + slot * vstride; };
-            // bits [32 w, 32 w + 32) of the node-local codeword slices (reference order; i0 is a multiple of the node size)
-            auto aword = [&](int w) -> uint32_t { return size >= 32 ? Abits[(i0 >> 5) + w] : (Abits[i0 >> 5] >> (i0 & 31)); };
-            auto fword = [&](int w) -> uint32_t { return size >= 32 ? Fbits[(i0 >> 5) + w] : (Fbits[i0 >> 5] >> (i0 & 31)); };
-            // left-to-right product of P[j].{x|y} selected by the bits of `bits ^ (cw & xm)` (np.product order, :503-509 etc.)
-            auto chain = [&](const double2 *P, const uint32_t *bw, int bsh, const uint32_t *cw, uint32_t xm) -> double {
-                double pr = 1.0;
-                #pragma unroll 1
-                for (int w0 = 0; w0 < size; w0 += 32) {
-                    const uint32_t bits = (bw[w0 >> 5] >> bsh) ^ (xm ? cw[w0 >> 5] : 0u);
-                    const int m = size - w0 < 32 ? size - w0 : 32;
-                    #pragma unroll 1
-                    for (int b = 0; b < m; ++b) {
-                        const double2 v2 = P[w0 + b];
-                        const double v = (bits >> b) & 1u ? v2.y : v2.x;
-                        pr = (w0 + b) == 0 ? v : __dmul_rn(pr, v);
-                    }
-                }
-                return pr;
-            };
+            const double2 *Vl = vptr[l];
+            const int vstride = l == n ? 0 : size;
+            // node-local codeword slices (reference order; i0 is a multiple of the node size): bit j is word j/32, bit j%32 + bsh
             const uint32_t *aw = Abits + (i0 >> 5), *fw = Fbits + (i0 >> 5);
             const int bsh = size >= 32 ? 0 : (i0 & 31);
-            // Rate-1 / SPC: reliabilities (second-largest / largest, :763-768) of every (path, element) with all lanes;
-            // they are parked in the dead level l-1 region of the path vectors (S 2^(l-1) float64 pairs >= cnt 2^l doubles)
-            double *scr = nullptr;
-            if (kind == OP_RATE1 || spc) {
-                scr = (double *)Vlev(l - 1);
-                #pragma unroll 1
-                for (int idx = lane; idx < (cnt << l); idx += 32) {
-                    const double2 v2 = vsel(idx >> l)[idx & (size - 1)];
-                    const double m1 = v2.y > v2.x ? v2.y : v2.x, m2 = v2.y > v2.x ? v2.x : v2.y;
-                    scr[idx] = m2 / m1;
-                }
-                __syncwarp();
-            }
-            // ---- phase 1 (one job per lane): the order-dependent float64 products ---------------------------------
-            if (kind == OP_RATE0) {  // :495-518
-                #pragma unroll 1
-                for (int job = lane; job <= cnt; job += 32) {
-                    const bool act = job == cnt;
-                    const double pr = chain(vsel(act ? L : job), act ? aw : fw, bsh, coefw, 0u);
+            int nout = cnt;
+            if (kind == OP_RATE0 || kind == OP_REP) {
+                // one job per lane: left-to-right product of P[j].{x|y} selected by the candidate codeword's bits
+                // (np.product order; Rate-0 :495-518, Rep :521-578); job njobs-1 is the genie path
+                const int njobs = (kind == OP_REP ? 2 * cnt : cnt) + 1;
+#pragma unroll 1
+                for (int job = lane; job < njobs; job += 32) {
+                    const bool act = job == njobs - 1;
+                    const int s = (act || job < cnt) ? 0 : 1, t = act ? L : job - s * cnt;
+                    const double2 *P = Vl + t * vstride;
+                    const uint32_t *bw = act ? aw : fw;
+                    double pr = 1.0;
+#pragma unroll 1
+                    for (int w0 = 0; w0 < size; w0 += 32) {
+                        const uint32_t bits = (bw[w0 >> 5] >> bsh) ^ (s ? coefw[w0 >> 5] : 0u);
+                        const int m = size - w0 < 32 ? size - w0 : 32;
+#pragma unroll 1
+                        for (int b = 0; b < m; ++b) {
+                            const double2 v2 = P[w0 + b];
+                            pr = __dmul_rn(pr, (bits >> b) & 1u ? v2.y : v2.x);
+                        }
+                    }
                     if (act)
                         misc[0] = pr;
-                    else
-                        newprob[job] = __dmul_rn(prob[job], pr);
-                }
-            } else if (kind == OP_REP) {  // :521-578
-                #pragma unroll 1
-                for (int job = lane; job <= 2 * cnt; job += 32) {
-                    const bool act = job == 2 * cnt;
-                    const int s = act ? 0 : job / cnt, t = act ? 0 : job - s * cnt;
-                    const double pr = chain(vsel(act ? L : t), act ? aw : fw, bsh, coefw, s ? FULL : 0u);
-                    if (act)
-                        misc[0] = pr;
+                    else if (kind == OP_RATE0)
+                        newprob[t] = __dmul_rn(prob[t], pr);
                     else
                         cand[s * cnt + t] = __dmul_rn(prob[t], pr);
                 }
             } else {  // Rate-1 :581-628 and SPC :631-682
-                const int fval = spc ? fvf[opk.y & 0xffffu] : 0;
-                #pragma unroll 1
-                for (int job = lane; job <= cnt; job += 32) {
-                    if (job == cnt) {
-                        misc[0] = chain(vsel(L), aw, bsh, coefw, 0u);
-                        continue;
+                // phase 0, all lanes over (path, element): reliabilities (second-largest / largest, :763-768) and hard decisions.
+                // Both are parked in the dead level l-1 region of the path vectors (S 2^l doubles): reliabilities in the
+                // first cnt 2^l doubles, hard-decision words in the genie slot's share.
+                double *scr = (double *)vptr[l - 1];
+                uint32_t *hd = l >= 5 ? (uint32_t *)(scr + ((size_t)L << l)) : hds;
+                const int total = cnt << l;
+#pragma unroll 1
+                for (int base = 0; base < total; base += 32) {
+                    const int idx = base + lane;
+                    const bool valid = idx < total;
+                    const int t = idx >> l, j = idx & (size - 1);
+                    double2 v2 = make_double2(1.0, 1.0);
+                    if (valid) v2 = Vl[t * vstride + j];
+                    const bool one = v2.y > v2.x;
+                    const double m1 = one ? v2.y : v2.x, m2 = one ? v2.x : v2.y;
+                    const double s = m2 / m1;
+                    if (valid) scr[idx] = s;
+                    const uint32_t bal = __ballot_sync(FULL, valid && one);
+                    if (size >= 32) {
+                        if (lane == 0) hd[idx >> 5] = bal;
+                    } else if (valid && j == 0) {
+                        hd[t] = (bal >> (lane & ~(size - 1))) & smask;
                     }
-                    const int t = job;
-                    const double2 *P = vsel(t);
-                    // pickLeastReliableIndices (:759-768): the npick largest (score, j), ascending;
-                    // sc0 <= sc1 (<= sc2 <= sc3), ties go to the later index (>=), as in the streaming form
-                    double sc0 = -1.0, sc1 = -1.0, sc2 = -1.0, sc3 = -1.0;
-                    int sj0 = 0, sj1 = 0, sj2 = 0, sj3 = 0;
-                    const double *sp = scr + (t << l);
-                    #pragma unroll 1
-                    for (int j = 0; j < size; ++j) {
-                        const double s = sp[j];
-                        if (!spc) {
-                            if (s >= sc1) {
-                                sc0 = sc1, sj0 = sj1;
-                                sc1 = s, sj1 = j;
-                            } else if (s >= sc0) {
-                                sc0 = s, sj0 = j;
-                            }
-                        } else if (s >= sc0) {
-                            if (s >= sc1) {
-                                sc0 = sc1, sj0 = sj1;
-                                if (s >= sc2) {
-                                    sc1 = sc2, sj1 = sj2;
-                                    if (s >= sc3) {
-                                        sc2 = sc3, sj2 = sj3;
-                                        sc3 = s, sj3 = j;
-                                    } else {
-                                        sc2 = s, sj2 = j;
-                                    }
-                                } else {
-                                    sc1 = s, sj1 = j;
-                                }
-                            } else {
-                                sc0 = s, sj0 = j;
-                            }
+                }
+                __syncwarp();
+                // pickLeastReliableIndices (:759-768): per path the 2 (Rate-1) or 4 (SPC) largest (score, j), ties to the later
+                // index.  G lanes share a path: each keeps the top four of its strided elements (ascending s0 <= .. <= s3,
+                // branch-free insertion), then the lists are merged by arg-max rounds inside the lane group.
+                {
+                    int cl = 0;
+                    while ((1 << cl) < cnt) ++cl;
+                    const int gsh = 5 - cl, G = 1 << gsh;  // cnt <= 32
+                    const int t = lane >> gsh, qq = lane & (G - 1);
+                    double s0 = -1.0, s1 = -1.0, s2 = -1.0, s3 = -1.0;
+                    int j0 = 0, j1 = 0, j2 = 0, j3 = 0;
+                    if (t < cnt) {
+                        const double *sp = scr + (t << l);
+#pragma unroll 1
+                        for (int j = qq; j < size; j += G) {
+                            const double s = sp[j];
+                            const bool g0 = s >= s0, g1 = s >= s1, g2 = s >= s2, g3 = s >= s3;
+                            s0 = g1 ? s1 : (g0 ? s : s0), j0 = g1 ? j1 : (g0 ? j : j0);
+                            s1 = g2 ? s2 : (g1 ? s : s1), j1 = g2 ? j2 : (g1 ? j : j1);
+                            s2 = g3 ? s3 : (g2 ? s : s2), j2 = g3 ? j3 : (g2 ? j : j2);
+                            s3 = g3 ? s : s3, j3 = g3 ? j : j3;
                         }
                     }
-                    int sumconst = 0;
-                    bool first = true;
-                    double prodmax = 1.0;
-                    #pragma unroll 1
-                    for (int j = 0; j < size; ++j) {
-                        bool forked = j == sj0 || j == sj1;
-                        if (spc) forked |= j == sj2 || j == sj3;
-                        if (forked) continue;
-                        const double2 v2 = P[j];
-                        const bool one = v2.y > v2.x;
-                        const double mv = one ? v2.y : v2.x;
-                        sumconst += one ? 1 : 0;
-                        prodmax = first ? mv : __dmul_rn(prodmax, mv);
-                        first = false;
+                    const int npick = spc ? 4 : 2;
+#pragma unroll 1
+                    for (int r = 0; r < npick; ++r) {
+                        double bs = s3;
+                        int bj = j3;
+#pragma unroll 1
+                        for (int o = 1; o < G; o <<= 1) {
+                            const double os = __shfl_xor_sync(FULL, bs, o);
+                            const int oj = __shfl_xor_sync(FULL, bj, o);
+                            if (os > bs || (os == bs && oj > bj)) bs = os, bj = oj;
+                        }
+                        if (s3 == bs && j3 == bj) {  // this lane's head was taken
+                            s3 = s2, j3 = j2;
+                            s2 = s1, j2 = j1;
+                            s1 = s0, j1 = j0;
+                            s0 = -1.0, j0 = 0;
+                        }
+                        if (qq == 0 && t < cnt) pick[t * 4 + npick - 1 - r] = (int16_t)bj;
                     }
-                    basep[t] = __dmul_rn(prob[t], prodmax);
-                    pick[t * 4 + 0] = (int16_t)sj0;
-                    pick[t * 4 + 1] = (int16_t)sj1;
-                    pick[t * 4 + 2] = (int16_t)sj2;
-                    pick[t * 4 + 3] = (int16_t)sj3;
-                    delta[t] = (uint8_t)((fval ^ sumconst) & 1);
+                    if (!spc && qq == 0 && t < cnt) pick[t * 4 + 2] = pick[t * 4 + 3] = -1;
                 }
-            }
-            __syncwarp();
-            const int C = kind == OP_RATE0 ? 0 : cnt * fs;
-            if (kind == OP_RATE1 || spc) {
+                __syncwarp();
+                // per path, in element order: product of the non-forked maxima; the genie path's product runs in lane cnt
+                const int fval = spc ? fvf[opk.y & 0xffffu] : 0;
+#pragma unroll 1
+                for (int job = lane; job <= cnt; job += 32) {
+                    const bool act = job == cnt;
+                    const double2 *P = Vl + (act ? L : job) * vstride;
+                    int p0 = -1, p1 = -1, p2 = -1, p3 = -1;
+                    if (!act) p0 = pick[job * 4], p1 = pick[job * 4 + 1], p2 = pick[job * 4 + 2], p3 = pick[job * 4 + 3];
+                    double pr = 1.0;
+#pragma unroll 1
+                    for (int w0 = 0; w0 < size; w0 += 32) {
+                        const uint32_t abits = aw[w0 >> 5] >> bsh;
+                        const int m = size - w0 < 32 ? size - w0 : 32;
+#pragma unroll 1
+                        for (int b = 0; b < m; ++b) {
+                            const int j = w0 + b;
+                            const double2 v2 = P[j];
+                            const bool sely = act ? ((abits >> b) & 1u) != 0u : v2.y > v2.x;
+                            const double v = sely ? v2.y : v2.x;
+                            const bool forked = j == p0 || j == p1 || j == p2 || j == p3;
+                            pr = forked ? pr : __dmul_rn(pr, v);
+                        }
+                    }
+                    if (act) {
+                        misc[0] = pr;
+                    } else {
+                        basep[job] = __dmul_rn(prob[job], pr);
+                        // parity of the non-forked hard decisions
+                        uint32_t par = 0;
+                        const uint32_t *hw = hd + job * Wl;
+#pragma unroll 1
+                        for (int w = 0; w < Wl; ++w) par ^= hw[w];
+                        par = __popc(par);
+                        par ^= (hw[p0 >> 5] >> (p0 & 31)) ^ (hw[p1 >> 5] >> (p1 & 31));
+                        if (spc) par ^= (hw[p2 >> 5] >> (p2 & 31)) ^ (hw[p3 >> 5] >> (p3 & 31));
+                        delta[job] = (uint8_t)((fval ^ par) & 1);
+                    }
+                }
+                __syncwarp();
                 // candidate metrics (forkIndices / forkIndicesSpc, :770-820), one (path, fork) per lane
-                #pragma unroll 1
+                const int C = cnt * fs;
+#pragma unroll 1
                 for (int idx = lane; idx < C; idx += 32) {
                     const int t = idx / fs, fk = idx - t * fs;
-                    const double2 *P = vsel(t);
+                    const double2 *P = Vl + t * vstride;
                     const int16_t *pk = pick + t * 4;
                     double pf = 1.0;
                     int sf = 0;
-                    #pragma unroll 1
+#pragma unroll 1
                     for (int w = 0; w < nfork; ++w) {
                         const int dg = (fk >> (nfork - 1 - w)) & 1;
                         const double2 v2 = P[pk[w]];
-                        const double v = dg ? v2.y : v2.x;
-                        pf = w == 0 ? v : __dmul_rn(pf, v);
+                        pf = __dmul_rn(pf, dg ? v2.y : v2.x);
                         sf += dg;
                     }
                     if (spc) {
@@ -405,28 +461,28 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
                     }
                     cand[idx] = __dmul_rn(pf, basep[t]);
                 }
-                __syncwarp();
             }
+            __syncwarp();
             // ---- prune (:446-451 etc.): keep the ns = min(#nonzero, L) largest candidates under the total order
             // (metric, index), listed ascending.  Round r extracts the r-th largest: non-negative float64 compare like their
             // bit patterns, so the arg-max is three integer redux.sync (high word, low word, index); a candidate that has
             // been taken is zeroed in place (zeros are never taken: r < ns <= #nonzero).
-            int nout = cnt;
             if (kind != OP_RATE0) {
+                const int C = cnt * fs;
                 nout = C;
                 if (C > L) {
-                    int nzc = 0;
-                    #pragma unroll 1
-                    for (int cc = lane; cc < C; cc += 32) nzc += cand[cc] != 0.0 ? 1 : 0;
+                    double v0 = lane < C ? cand[lane] : 0.0, v1 = lane + 32 < C ? cand[lane + 32] : 0.0;
+                    int nzc = (v0 != 0.0 ? 1 : 0) + (v1 != 0.0 ? 1 : 0);
+#pragma unroll 1
+                    for (int cc = lane + 64; cc < C; cc += 32) nzc += cand[cc] != 0.0 ? 1 : 0;
                     nzc = __reduce_add_sync(FULL, nzc);
                     const int ns = nzc < L ? nzc : L;
-                    double v0 = lane < C ? cand[lane] : 0.0, v1 = lane + 32 < C ? cand[lane + 32] : 0.0;
-                    #pragma unroll 1
+#pragma unroll 1
                     for (int r = 0; r < ns; ++r) {
                         // this lane's best candidate; among equals the later index wins
                         double bv = v1 >= v0 ? v1 : v0;
                         int bi = v1 >= v0 ? lane + 32 : lane;
-                        #pragma unroll 1
+#pragma unroll 1
                         for (int cc = lane + 64; cc < C; cc += 32) {
                             const double v = cand[cc];
                             if (v >= bv) bv = v, bi = cc;
@@ -448,26 +504,26 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
                     }
                     nout = ns;
                 } else {
-                    #pragma unroll 1
+#pragma unroll 1
                     for (int t = lane; t < C; t += 32) {
                         keep[t] = t;
                         newprob[t] = cand[t];
                     }
                 }
+                __syncwarp();
             }
-            __syncwarp();
             // ---- phase 2: lazy copy (omap), normalise (:867-872) ---------------------------------------------------
             {
                 if (kind == OP_RATE0) {
-                    #pragma unroll 1
+#pragma unroll 1
                     for (int t = lane; t < cnt; t += 32) OM(l, c)[t] = (uint8_t)t;
                 } else {
-                    #pragma unroll 1
+#pragma unroll 1
                     for (int t = lane; t < nout; t += 32) {
                         const int cidx = keep[t];
                         int src, sel;
                         if (kind == OP_REP) {
-                            sel = cidx / cnt;
+                            sel = cidx >= cnt ? 1 : 0;
                             src = cidx - sel * cnt;
                         } else {
                             src = cidx / fs;
@@ -479,13 +535,13 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
                     }
                 }
                 double mx = lane < nout ? newprob[lane] : newprob[0];
-                #pragma unroll 1
+#pragma unroll 1
                 for (int t = lane + 32; t < nout; t += 32) {
                     const double v = newprob[t];
                     if (v > mx) mx = v;
                 }
                 mx = warp_max_f64(mx);
-                #pragma unroll 1
+#pragma unroll 1
                 for (int t = lane; t < nout; t += 32) prob[t] = newprob[t] / mx;
                 if (lane == 0) {
                     misc[1] = __dmul_rn(misc[1], misc[0] / mx);
@@ -495,47 +551,36 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
             __syncwarp();
             // ---- phase 3: node codewords of the surviving paths and of the genie path ---------------------------
             {
-                const int Wl = scl2_W(l);
-                const uint32_t smask = size >= 32 ? 0xffffffffu : ((1u << size) - 1u);
-                #pragma unroll 1
-                for (int w = lane; w < Wl; w += 32) R(l, c, L)[w] = (aw[w] >> bsh) & smask;
-                if (kind == OP_RATE0 || kind == OP_REP) {
-                    #pragma unroll 1
-                    for (int idx = lane; idx < nout * Wl; idx += 32) {
-                        const int t = idx / Wl, w = idx - t * Wl;
-                        uint32_t v = (fw[w] >> bsh) & smask;
-                        if (kind == OP_REP && selfk[t]) v ^= coefw[w];
-                        R(l, c, t)[w] = v;
+                uint32_t *ro = R(l, c, 0);
+                const int wsh = l <= 5 ? 0 : l - 5;
+#pragma unroll 1
+                for (int idx = lane; idx < (nout + 1) << wsh; idx += 32) {
+                    const int t = idx >> wsh, w = idx & (Wl - 1);
+                    uint32_t v;
+                    if (t == nout) {
+                        ro[L * Wl + w] = (aw[w] >> bsh) & smask;
+                        continue;
                     }
-                } else {
-                    auto sym = [&](int t, int j) -> uint32_t {
+                    if (kind == OP_RATE0 || kind == OP_REP) {
+                        v = (fw[w] >> bsh) & smask;
+                        if (kind == OP_REP && selfk[t]) v ^= coefw[w];
+                    } else {
+                        // the source path's hard decisions with the forked positions overwritten
+                        const uint32_t *hd = l >= 5 ? (uint32_t *)((double *)vptr[l - 1] + ((size_t)L << l)) : hds;
                         const int src = selsrc[t], fk = selfk[t];
                         const int16_t *pk = pick + src * 4;
-                        #pragma unroll 1
-                        for (int w = 0; w < nfork; ++w)
-                            if (pk[w] == j) return (uint32_t)((fk >> (nfork - 1 - w)) & 1);
-                        if (spc && pk[3] == j) return (uint32_t)((delta[src] ^ __popc(fk)) & 1);
-                        const double2 v2 = vsel(src)[j];
-                        return v2.y > v2.x ? 1u : 0u;
-                    };
-                    if (size >= 32) {
-                        #pragma unroll 1
-                        for (int base = 0; base < nout * size; base += 32) {
-                            const int idx = base + lane;
-                            const int t = idx >> l, j = idx & (size - 1);
-                            const uint32_t wv = __ballot_sync(FULL, sym(t, j));
-                            if (lane == 0) R(l, c, t)[j >> 5] = wv;
+                        v = hd[src * Wl + w];
+#pragma unroll 1
+                        for (int i = 0; i < nfork; ++i) {
+                            const int j = pk[i];
+                            if ((j >> 5) == w) v = (v & ~(1u << (j & 31))) | ((uint32_t)((fk >> (nfork - 1 - i)) & 1) << (j & 31));
                         }
-                    } else {
-                        // 32 / size paths per round, one symbol per lane; a path's word is its slice of the ballot
-                        const int ppr = 32 >> l;
-                        #pragma unroll 1
-                        for (int t0 = 0; t0 < nout; t0 += ppr) {
-                            const int t = t0 + (lane >> l), j = lane & (size - 1);
-                            const uint32_t wv = __ballot_sync(FULL, t < nout ? sym(t, j) : 0u);
-                            if (j == 0 && t < nout) R(l, c, t)[0] = (wv >> (lane & ~(size - 1))) & smask;
+                        if (spc) {
+                            const int j = pk[3];
+                            if ((j >> 5) == w) v = (v & ~(1u << (j & 31))) | ((uint32_t)((delta[src] ^ __popc(fk)) & 1) << (j & 31));
                         }
                     }
+                    ro[t * Wl + w] = v;
                 }
             }
             __syncwarp();
@@ -543,11 +588,11 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
 
         // ---- final selection (listDecode :172-213): the genie path is in the list iff a root codeword equals it ----
         const int cnt = nl[n * 2 + 0];
-        #pragma unroll 1
+#pragma unroll 1
         for (int t = 0; t < cnt; ++t) {
             const uint32_t *a = R(n, 0, t), *b = R(n, 0, L);
             bool eq = true;
-            #pragma unroll 1
+#pragma unroll 1
             for (int w = lane; w < NW; w += 32) eq &= a[w] == b[w];
             eq = __all_sync(FULL, eq);
             if (lane == 0) eqf[t] = eq ? 1 : 0;
@@ -555,11 +600,11 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
         __syncwarp();
         if (lane == 0) {
             int found = -1;
-            #pragma unroll 1
+#pragma unroll 1
             for (int t = 0; t < cnt && found < 0; ++t)
                 if (eqf[t]) found = t;
             double maxp = prob[0], minp = prob[0];
-            #pragma unroll 1
+#pragma unroll 1
             for (int t = 1; t < cnt; ++t) {
                 maxp = prob[t] > maxp ? prob[t] : maxp;
                 minp = prob[t] < minp ? prob[t] : minp;
@@ -575,7 +620,7 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
             if (p.list_size) {
                 p.list_size[f] = cnt;
                 p.actual_prob[f] = ap;
-                #pragma unroll 1
+#pragma unroll 1
                 for (int t = 0; t < L; ++t) p.list_prob[f * L + t] = t < cnt ? prob[t] : 0.0;
             }
         }
@@ -583,11 +628,11 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
         // information of a path = gather of T(root codeword): bit-reverse to natural order, butterfly, gather
         const int sel = ivars[1];
         const int npaths = p.list_info ? cnt : 1;
-        #pragma unroll 1
+#pragma unroll 1
         for (int pi = 0; pi < npaths; ++pi) {
             const int t = p.list_info ? pi : sel;
             const uint32_t *root = R(n, 0, t);
-            #pragma unroll 1
+#pragma unroll 1
             for (int w = 0; w < NW; ++w) {
                 const int pos = 32 * w + lane;
                 uint32_t b = 0;
@@ -599,10 +644,10 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
                 if (lane == 0) T0[w] = wv;
             }
             __syncwarp();
-            #pragma unroll 1
+#pragma unroll 1
             for (int st = 0; st < n; ++st) {
                 const int s = 1 << st;
-                #pragma unroll 1
+#pragma unroll 1
                 for (int w = lane; w < NW; w += 32) {
                     if (s < 32) {
                         const uint32_t m = s == 1 ? 0x55555555u : s == 2 ? 0x33333333u : s == 4 ? 0x0f0f0f0fu : s == 8 ? 0x00ff00ffu : 0x0000ffffu;
@@ -613,7 +658,7 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
                 }
                 __syncwarp();
             }
-            #pragma unroll 1
+#pragma unroll 1
             for (int j = lane; j < k; j += 32) {
                 const int pos = p.info_src[j];
                 const uint8_t v = (uint8_t)((T0[pos >> 5] >> (pos & 31)) & 1u);
@@ -702,7 +747,8 @@ int sclw_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_
     p.rgl = c.rgl;
     p.tx_words = c.tx_words;
     p.frames = B;
-    p.ops2 = T->d_ops2;
+    p.ops = T->d_ops3;
+    p.n_ops = (int)T->ops3.size();
     p.a_src = T->d_a_src;
     p.f_src = T->d_f_src;
     p.info_src = T->d_info_src;
