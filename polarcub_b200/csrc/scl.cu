@@ -183,14 +183,18 @@ SclTables *scl_tables(const pc_plan *p) {
         for (const SclOp &o : T->ops)
             T->ops2.push_back(make_uint2((uint32_t)o.kind | (uint32_t)o.l << 3 | (uint32_t)o.c << 7 | (uint32_t)o.i << 8,
                                          (uint32_t)(o.fv_idx & 0xffff) | (uint32_t)(o.kind == OP_REP ? o.coefw_off : 0) << 16));
+        auto is_minus = [&](size_t a, int l) {
+            return a < T->ops2.size() && (T->ops2[a].x & 7) == OP_MINUS && (int)((T->ops2[a].x >> 3) & 15) == l;
+        };
+        const char *mdv = getenv("PC_SCLW_MAXDEPTH");
+        const int maxdepth = mdv && *mdv ? atoi(mdv) : 2;
         for (size_t a = 0; a < T->ops2.size(); ++a) {
             uint2 o = T->ops2[a];
             const int kind = o.x & 7, l = (o.x >> 3) & 15;
-            if ((kind == OP_MINUS || kind == OP_PLUS) && l >= 7 && a + 1 < T->ops2.size()) {
-                const uint2 nx = T->ops2[a + 1];
-                if ((nx.x & 7) == OP_MINUS && (int)((nx.x >> 3) & 15) == l - 1) {
+            if ((kind == OP_MINUS || kind == OP_PLUS) && maxdepth > 1) {
+                if (l >= 7 && is_minus(a + 1, l - 1)) {
                     o.x |= 1u << 30;
-                    ++a;
+                    a += 1;
                 }
             }
             T->ops3.push_back(o);

@@ -25,6 +25,7 @@ namespace pc {
 struct SclwParams {
     int n, k, L, n_ops, nfrozen, lsm;
     int rgl;               // path codewords of levels >= rgl live in the global scratch `rg`, smaller levels in shared memory
+    int xy_al32;           // the channel input is 32-byte aligned
     int tx_words;          // extra shared words behind the path vectors so that the prologue's two N-bit temporaries fit
     int64_t frames;
     const uint2 *ops;      // packed ops (SclTables::ops3): x = kind | l << 3 | c << 7 | i << 8 | fused << 30, y = fv_idx | coefw_off << 16
@@ -49,7 +50,7 @@ static size_t sclw_smem_bytes(int n, int L, int lsm, int rgl, int *tx_words) {
     const int S = L + 1, N = 1 << n, NW = N >= 32 ? N >> 5 : 1;
     size_t v = (size_t)((2 << lsm) - 1) * S * 16;
     int tx = 0;
-    if (v < (size_t)2 * NW * 4) tx = (int)(((size_t)2 * NW * 4 - v + 15) / 16 * 4);
+    if (v < (size_t)3 * NW * 4) tx = (int)(((size_t)3 * NW * 4 - v + 15) / 16 * 4);
     if (tx_words) *tx_words = tx;
     size_t b = v + (size_t)tx * 4;
     b += (size_t)(11 * L + 4) * 8;                                  // prob, newprob, basep, cand, misc
@@ -59,6 +60,19 @@ static size_t sclw_smem_bytes(int n, int L, int lsm, int rgl, int *tx_words) {
     b += (size_t)(4 * L + 3 * (n + 1) + 4) * 4;                     // keep, selsrc, selfk, hds, nl, nin, ivars
     b += (size_t)4 * L * 2 + L + (size_t)(n + 1) * 2 * L + L;       // pick, delta, omap, eqf
     return (b + 15) & ~(size_t)15;
+}
+
+// 32-byte global accesses (two adjacent float64 pairs): one LDG.256 / STG.256 when the address is 32-byte aligned
+__device__ __forceinline__ void ld32(const double2 *p, bool aligned32, double2 &a, double2 &b) {
+    if (aligned32) {
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+    } else {
+        a = p[0];
+        b = p[1];
+    }
+}
+__device__ __forceinline__ void st32(double2 *p, const double2 a, const double2 b) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
 }
 
 __device__ __forceinline__ double warp_max_f64(double v) {
@@ -100,7 +114,7 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
     uint8_t *delta = (uint8_t *)(pick + 4 * L);
     uint8_t *omap = delta + L;               // [(n+1)][2][L]
     uint8_t *eqf = omap + (n + 1) * 2 * L;   // [L]
-    uint32_t *T0 = (uint32_t *)smem_raw, *T1 = T0 + NW;  // prologue / epilogue temporaries over the (then dead) path vectors
+    uint32_t *T0 = (uint32_t *)smem_raw, *T1 = T0 + NW, *T2 = T1 + NW;  // prologue / epilogue temporaries over the (then dead) path vectors
 
     {
         double2 *vg = p.vg + (int64_t)blockIdx.x * p.vg_stride - VS;
@@ -110,6 +124,7 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
             rptr[l] = (l < rgl ? Rw : rgc) + 2 * S * scl2_wsum(l);
         }
     }
+    double *mxs = (double *)(p.vg + (int64_t)(blockIdx.x + 1) * p.vg_stride) - (N / 2 + 2);  // per-leaf list maxima (<= N/2 leaves)
     auto R = [&](int l, int c, int slot) -> uint32_t * { return rptr[l] + (c * S + slot) * scl2_W(l); };
     auto OM = [&](int l, int c) -> uint8_t * { return omap + (l * 2 + c) * L; };
 
@@ -138,6 +153,38 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
             }
         }
         __syncwarp();
+        // root codeword of the actual word (reference order = bit reversal of the natural-order transform): R(n, 0, L)
+#pragma unroll 1
+        for (int w = lane; w < NW; w += 32) T2[w] = T0[w];
+        __syncwarp();
+#pragma unroll 1
+        for (int st = 0; st < n; ++st) {
+            const int s = 1 << st;
+#pragma unroll 1
+            for (int w = lane; w < NW; w += 32) {
+                if (s < 32) {
+                    const uint32_t m = s == 1 ? 0x55555555u : s == 2 ? 0x33333333u : s == 4 ? 0x0f0f0f0fu : s == 8 ? 0x00ff00ffu : 0x0000ffffu;
+                    T2[w] ^= (T2[w] >> s) & m;
+                } else if (!(w & (s >> 5))) {
+                    T2[w] ^= T2[w + (s >> 5)];
+                }
+            }
+            __syncwarp();
+        }
+        {
+            uint32_t *groot = R(n, 0, L);
+#pragma unroll 1
+            for (int w = 0; w < NW; ++w) {
+                const int pos = 32 * w + lane;
+                uint32_t b = 0;
+                if (pos < N) {
+                    const uint32_t r = bitrev_n((uint32_t)pos, n);
+                    b = (T2[r >> 5] >> (r & 31)) & 1u;
+                }
+                const uint32_t wv = __ballot_sync(FULL, b);
+                if (lane == 0) groot[w] = wv;
+            }
+        }
 #pragma unroll 1
         for (int t = 0; t < n; ++t) {
             const int s = 1 << t;
@@ -180,6 +227,30 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
         }
         __syncwarp();
 
+        // pass 0 decodes the list; pass 1 (genie) replays the ops for the actual path alone (slot L) to get listDecode's
+        // actual_prob.  ProbResult needs it only when the actual word is not in the final list, so pass 1 is skipped for
+        // frames that decoded correctly unless the caller asked for the final-list outputs.
+        int found = -1;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+        const bool genie = pass == 1;
+        if (genie) {
+            // the actual word is in the list iff a root codeword equals its codeword: T(u) with the same frozen values, so
+            // compare the information bits instead -- bits of A at information positions vs the path's u
+            const int cntf = nl[n * 2 + 0];
+#pragma unroll 1
+            for (int t = 0; t < cntf; ++t) {
+                const uint32_t *a = R(n, 0, t), *b = R(n, 0, L);
+                bool eq = true;
+#pragma unroll 1
+                for (int w = lane; w < NW; w += 32) eq &= a[w] == b[w];
+                if (__all_sync(FULL, eq) && found < 0) found = t;
+            }
+            if (found >= 0 && !p.list_size) break;
+            if (lane == 0) misc[1] = 1.0;
+            __syncwarp();
+        }
+        int leaf_idx = 0;
         uint2 opn = p.ops[0];
 #pragma unroll 1
         for (int oi = 0; oi < p.n_ops; ++oi) {
@@ -189,7 +260,8 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
             const int size = 1 << l;
             if (kind == OP_MINUS || kind == OP_PLUS) {
                 const bool plus = kind == OP_PLUS;
-                const int cnt = plus ? nl[(l - 1) * 2 + 0] : nin[l];
+                const int cnt = genie ? 0 : (plus ? nl[(l - 1) * 2 + 0] : nin[l]);
+                const int nt = genie ? 1 : cnt;  // paths handled by this pass: the list (slots 0 .. cnt-1) or the genie path (slot L)
                 const uint8_t *om = OM(l - 1, 0);
                 const double2 *sbase = vptr[l];
                 const int sstride = l == n ? 0 : size;  // the channel level is shared by all paths
@@ -201,26 +273,31 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
                     // large level: iteration `it` covers 128 consecutive source elements of one path; the loads of iteration
                     // it+1 are issued before the arithmetic of iteration it.  Plain: lane h and h+32 of the 64 outputs.
                     // Fused: the lane's 4 consecutive elements give 2 outputs of level l-1 and 1 of level l-2.
+                    // (levels >= 6 are always in the global scratch: 32-byte vector loads and stores)
                     const int bsh = l - 7, bmask = (1 << bsh) - 1;
-                    const int niter = (cnt + 1) << bsh;
+                    const int niter = nt << bsh;
                     double2 *d2base = vptr[l - 2];
                     const int o2 = fused ? 2 : 64;
+                    const bool al = l < n || p.xy_al32;
                     auto src_ptr = [&](int it) -> const double2 * {
                         const int t = it >> bsh, blk = it & bmask;
-                        const int src = t == cnt ? L : (plus ? (int)om[t] : t);
+                        const int src = genie ? L : (plus ? (int)om[t] : t);
                         return sbase + src * sstride + blk * 128 + (fused ? 4 * lane : 2 * lane);
                     };
                     const double2 *q = src_ptr(0);
-                    double2 e0 = q[0], e1 = q[1], e2 = q[o2], e3 = q[o2 + 1];
+                    double2 e0, e1, e2, e3;
+                    ld32(q, al, e0, e1);
+                    ld32(q + o2, al, e2, e3);
 #pragma unroll 1
                     for (int it = 0; it < niter; ++it) {
                         double2 f0 = e0, f1 = e1, f2 = e2, f3 = e3;
                         if (it + 1 < niter) {
                             q = src_ptr(it + 1);
-                            f0 = q[0], f1 = q[1], f2 = q[o2], f3 = q[o2 + 1];
+                            ld32(q, al, f0, f1);
+                            ld32(q + o2, al, f2, f3);
                         }
                         const int t = it >> bsh, blk = it & bmask;
-                        const int slot = t == cnt ? L : t;
+                        const int slot = genie ? L : t;
                         uint32_t u0 = 0, u1 = 0;
                         if (plus) {
                             const uint32_t *rp = rb + slot * rw + 2 * blk;
@@ -236,8 +313,7 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
                         const double2 y0 = node_update(e0, e1, plus, u0), y1 = node_update(e2, e3, plus, u1);
                         double2 *D = dbase + (slot << (l - 1)) + blk * 64;
                         if (fused) {
-                            D[2 * lane] = y0;
-                            D[2 * lane + 1] = y1;
+                            st32(D + 2 * lane, y0, y1);
                             d2base[(slot << (l - 2)) + blk * 32 + lane] = node_update(y0, y1, false, 0u);
                         } else {
                             D[lane] = y0;
@@ -245,49 +321,74 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
                         }
                         e0 = f0, e1 = f1, e2 = f2, e3 = f3;
                     }
-                    if (lane == 0 && fused) nin[l - 2] = cnt;
+                    if (lane == 0 && fused && !genie) nin[l - 2] = cnt;
                 } else {
                     const int half = size >> 1;
-                    const int total = (cnt + 1) << (l - 1);
+                    const int total = nt << (l - 1);
 #pragma unroll 1
                     for (int idx = lane; idx < total; idx += 32) {
                         const int t = idx >> (l - 1), h = idx & (half - 1);
-                        const int slot = t == cnt ? L : t;
-                        const int src = t == cnt ? L : (plus ? (int)om[t] : t);
+                        const int slot = genie ? L : t;
+                        const int src = genie ? L : (plus ? (int)om[t] : t);
                         const double2 *P = sbase + src * sstride;
                         const double2 a = P[2 * h], b = P[2 * h + 1];
                         const uint32_t u1 = plus ? (rb[slot * rw + (h >> 5)] >> (h & 31)) & 1u : 0u;
                         dbase[(slot << (l - 1)) + h] = node_update(a, b, plus, u1);
                     }
                 }
-                if (lane == 0) nin[l - 1] = cnt;
+                if (lane == 0 && !genie) nin[l - 1] = cnt;
                 __syncwarp();
                 continue;
             }
             if (kind == OP_COMBINE) {  // :726-754 in reference order: out[2h] = m[h] + p[h], out[2h+1] = -p[h]
-                const int cnt = nl[(l - 1) * 2 + 1];
+                const int cnt = genie ? 0 : nl[(l - 1) * 2 + 1];
+                const int nt = genie ? 1 : cnt;
                 const int Wo = scl2_W(l), wsh = l <= 5 ? 0 : l - 5;
                 const uint8_t *om1 = OM(l - 1, 1), *om0 = OM(l - 1, 0);
                 const uint32_t *rm = R(l - 1, 0, 0), *rp = R(l - 1, 1, 0);
                 uint32_t *ro = R(l, c, 0);
                 const int Wc = scl2_W(l - 1);
 #pragma unroll 1
-                for (int idx = lane; idx < (cnt + 1) << wsh; idx += 32) {
+                for (int idx = lane; idx < nt << wsh; idx += 32) {
                     const int t = idx >> wsh, w = idx & (Wo - 1);
-                    const int slot = t == cnt ? L : t;
-                    const int mi = t == cnt ? L : (int)om1[t];
+                    const int slot = genie ? L : t;
+                    const int mi = genie ? L : (int)om1[t];
                     const int sh = (w & 1) * 16;
                     const uint32_t m16 = (rm[mi * Wc + (w >> 1)] >> sh) & 0xffffu;
                     const uint32_t p16 = (rp[slot * Wc + (w >> 1)] >> sh) & 0xffffu;
                     ro[slot * Wo + w] = spread16(m16 ^ p16) | (spread16(p16) << 1);
                 }
+                if (!genie) {
 #pragma unroll 1
-                for (int t = lane; t < cnt; t += 32) OM(l, c)[t] = om0[om1[t]];
-                if (lane == 0) nl[l * 2 + c] = cnt;
+                    for (int t = lane; t < cnt; t += 32) OM(l, c)[t] = om0[om1[t]];
+                    if (lane == 0) nl[l * 2 + c] = cnt;
+                }
                 __syncwarp();
                 continue;
             }
             // ------------------------------- fast nodes ------------------------------------------------------
+            const int li = leaf_idx++;
+            if (genie) {
+                // genie pass: only the actual path's product over the node (:503-509 etc.), normalised like the list was
+                const double2 *P = vptr[l] + (l == n ? 0 : L * size);
+                const uint32_t *aw = Abits + (i0 >> 5);
+                const int bsh = size >= 32 ? 0 : (i0 & 31);
+                const int Wl = scl2_W(l);
+                const uint32_t smask = size >= 32 ? 0xffffffffu : ((1u << size) - 1u);
+                if (lane == 0) {
+                    double pr = 1.0;
+#pragma unroll 1
+                    for (int j = 0; j < size; ++j) {
+                        const double2 v2 = P[j];
+                        pr = __dmul_rn(pr, (aw[j >> 5] >> (bsh + (j & 31))) & 1u ? v2.y : v2.x);
+                    }
+                    misc[1] = __dmul_rn(misc[1], pr / mxs[li]);
+                }
+#pragma unroll 1
+                for (int w = lane; w < Wl; w += 32) R(l, c, L)[w] = (aw[w] >> bsh) & smask;
+                __syncwarp();
+                continue;
+            }
             const int cnt = nin[l];
             const bool spc = kind == OP_SPC;
             const int nfork = spc ? 3 : 2;
@@ -303,14 +404,13 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
             int nout = cnt;
             if (kind == OP_RATE0 || kind == OP_REP) {
                 // one job per lane: left-to-right product of P[j].{x|y} selected by the candidate codeword's bits
-                // (np.product order; Rate-0 :495-518, Rep :521-578); job njobs-1 is the genie path
-                const int njobs = (kind == OP_REP ? 2 * cnt : cnt) + 1;
+                // (np.product order; Rate-0 :495-518, Rep :521-578)
+                const int njobs = kind == OP_REP ? 2 * cnt : cnt;
 #pragma unroll 1
                 for (int job = lane; job < njobs; job += 32) {
-                    const bool act = job == njobs - 1;
-                    const int s = (act || job < cnt) ? 0 : 1, t = act ? L : job - s * cnt;
+                    const int s = job < cnt ? 0 : 1, t = job - s * cnt;
                     const double2 *P = Vl + t * vstride;
-                    const uint32_t *bw = act ? aw : fw;
+                    const uint32_t *bw = fw;
                     double pr = 1.0;
 #pragma unroll 1
                     for (int w0 = 0; w0 < size; w0 += 32) {
@@ -322,9 +422,7 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
                             pr = __dmul_rn(pr, (bits >> b) & 1u ? v2.y : v2.x);
                         }
                     }
-                    if (act)
-                        misc[0] = pr;
-                    else if (kind == OP_RATE0)
+                    if (kind == OP_RATE0)
                         newprob[t] = __dmul_rn(prob[t], pr);
                     else
                         cand[s * cnt + t] = __dmul_rn(prob[t], pr);
@@ -399,32 +497,21 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
                     if (!spc && qq == 0 && t < cnt) pick[t * 4 + 2] = pick[t * 4 + 3] = -1;
                 }
                 __syncwarp();
-                // per path, in element order: product of the non-forked maxima; the genie path's product runs in lane cnt
+                // per path, in element order: product of the non-forked maxima
                 const int fval = spc ? fvf[opk.y & 0xffffu] : 0;
 #pragma unroll 1
-                for (int job = lane; job <= cnt; job += 32) {
-                    const bool act = job == cnt;
-                    const double2 *P = Vl + (act ? L : job) * vstride;
-                    int p0 = -1, p1 = -1, p2 = -1, p3 = -1;
-                    if (!act) p0 = pick[job * 4], p1 = pick[job * 4 + 1], p2 = pick[job * 4 + 2], p3 = pick[job * 4 + 3];
+                for (int job = lane; job < cnt; job += 32) {
+                    const double2 *P = Vl + job * vstride;
+                    const int p0 = pick[job * 4], p1 = pick[job * 4 + 1], p2 = pick[job * 4 + 2], p3 = pick[job * 4 + 3];
                     double pr = 1.0;
 #pragma unroll 1
-                    for (int w0 = 0; w0 < size; w0 += 32) {
-                        const uint32_t abits = aw[w0 >> 5] >> bsh;
-                        const int m = size - w0 < 32 ? size - w0 : 32;
-#pragma unroll 1
-                        for (int b = 0; b < m; ++b) {
-                            const int j = w0 + b;
-                            const double2 v2 = P[j];
-                            const bool sely = act ? ((abits >> b) & 1u) != 0u : v2.y > v2.x;
-                            const double v = sely ? v2.y : v2.x;
-                            const bool forked = j == p0 || j == p1 || j == p2 || j == p3;
-                            pr = forked ? pr : __dmul_rn(pr, v);
-                        }
+                    for (int j = 0; j < size; ++j) {
+                        const double2 v2 = P[j];
+                        const double v = v2.y > v2.x ? v2.y : v2.x;
+                        const bool forked = j == p0 || j == p1 || j == p2 || j == p3;
+                        pr = forked ? pr : __dmul_rn(pr, v);
                     }
-                    if (act) {
-                        misc[0] = pr;
-                    } else {
+                    {
                         basep[job] = __dmul_rn(prob[job], pr);
                         // parity of the non-forked hard decisions
                         uint32_t par = 0;
@@ -544,7 +631,7 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
 #pragma unroll 1
                 for (int t = lane; t < nout; t += 32) prob[t] = newprob[t] / mx;
                 if (lane == 0) {
-                    misc[1] = __dmul_rn(misc[1], misc[0] / mx);
+                    mxs[li] = mx;
                     nl[l * 2 + c] = nout;
                 }
             }
@@ -554,13 +641,9 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
                 uint32_t *ro = R(l, c, 0);
                 const int wsh = l <= 5 ? 0 : l - 5;
 #pragma unroll 1
-                for (int idx = lane; idx < (nout + 1) << wsh; idx += 32) {
+                for (int idx = lane; idx < nout << wsh; idx += 32) {
                     const int t = idx >> wsh, w = idx & (Wl - 1);
                     uint32_t v;
-                    if (t == nout) {
-                        ro[L * Wl + w] = (aw[w] >> bsh) & smask;
-                        continue;
-                    }
                     if (kind == OP_RATE0 || kind == OP_REP) {
                         v = (fw[w] >> bsh) & smask;
                         if (kind == OP_REP && selfk[t]) v ^= coefw[w];
@@ -586,36 +669,22 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
             __syncwarp();
         }
 
-        // ---- final selection (listDecode :172-213): the genie path is in the list iff a root codeword equals it ----
+        }  // passes
+        // ---- final selection (listDecode :172-213): the actual word is in the list iff a root codeword equals its codeword ----
         const int cnt = nl[n * 2 + 0];
-#pragma unroll 1
-        for (int t = 0; t < cnt; ++t) {
-            const uint32_t *a = R(n, 0, t), *b = R(n, 0, L);
-            bool eq = true;
-#pragma unroll 1
-            for (int w = lane; w < NW; w += 32) eq &= a[w] == b[w];
-            eq = __all_sync(FULL, eq);
-            if (lane == 0) eqf[t] = eq ? 1 : 0;
-        }
-        __syncwarp();
         if (lane == 0) {
-            int found = -1;
-#pragma unroll 1
-            for (int t = 0; t < cnt && found < 0; ++t)
-                if (eqf[t]) found = t;
             double maxp = prob[0], minp = prob[0];
 #pragma unroll 1
             for (int t = 1; t < cnt; ++t) {
                 maxp = prob[t] > maxp ? prob[t] : maxp;
                 minp = prob[t] < minp ? prob[t] : minp;
             }
-            const double ap = misc[1];
+            const double ap = misc[1];  // meaningful (and needed) only when the genie pass ran
             int res;
             if (found >= 0)
                 res = prob[found] == maxp ? 0 : 1;
             else
                 res = ap > maxp ? 2 : (ap == maxp ? 3 : (ap >= minp ? 4 : 5));
-            ivars[1] = found >= 0 ? found : 0;
             p.result[f] = res;
             if (p.list_size) {
                 p.list_size[f] = cnt;
@@ -626,7 +695,7 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
         }
         __syncwarp();
         // information of a path = gather of T(root codeword): bit-reverse to natural order, butterfly, gather
-        const int sel = ivars[1];
+        const int sel = found >= 0 ? found : 0;
         const int npaths = p.list_info ? cnt : 1;
 #pragma unroll 1
         for (int pi = 0; pi < npaths; ++pi) {
@@ -694,10 +763,10 @@ static SclwConfig sclw_config(const pc_plan *plan, int L, int64_t B) {
     // shared-memory budget per warp: aim at `target` resident warps per SM
     const int target = envw_int("PC_SCLW_WARPS_PER_SM", 24);
     const size_t budget = (size_t)(227 * 1024) / (size_t)(target > 0 ? target : 1) - 1024;
-    int lsm = n - 1;
+    int lsm = n - 1 < 5 ? n - 1 : 5;  // levels >= 6 stay in the global scratch (the large-level loops use 32-byte global accesses)
     while (lsm > 0 && sclw_smem_bytes(n, L, lsm, rgl, nullptr) > budget) --lsm;
     const int forced = envw_int("PC_SCLW_LSM", -1);
-    if (forced >= 0 && forced <= n - 1) lsm = forced;
+    if (forced >= 0 && forced <= n - 1 && forced <= 5) lsm = forced;
     c.lsm = lsm;
     c.smem = sclw_smem_bytes(n, L, lsm, rgl, &c.tx_words);
     if (c.smem > 220 * 1024) return c;
@@ -708,8 +777,9 @@ static SclwConfig sclw_config(const pc_plan *plan, int L, int64_t B) {
     if (grid > B) grid = B;
     c.grid = (int)(grid > 0 ? grid : 1);
     const int64_t vtot = (int64_t)((1 << n) - 1) * S, vs = (int64_t)((2 << lsm) - 1) * S;
-    c.vg_stride = (size_t)(vtot > vs ? vtot - vs : 0) + 2;
+    c.vg_stride = (size_t)(vtot > vs ? vtot - vs : 0) + 2 + ((size_t)(1 << n) / 2 + 2 + 1) / 2 + 1;  // + per-leaf maxima (<= N/2 leaves)
     c.rg_stride = (size_t)2 * S * (scl2_wsum(n + 1) - scl2_wsum(rgl)) + 4;
+    c.vg_stride = (c.vg_stride + 1) & ~(size_t)1;  // 32-byte aligned per-warp regions
     c.ok = true;
     return c;
 }
@@ -746,6 +816,7 @@ int sclw_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_
     p.lsm = c.lsm;
     p.rgl = c.rgl;
     p.tx_words = c.tx_words;
+    p.xy_al32 = ((uintptr_t)d_xy & 31) == 0 ? 1 : 0;
     p.frames = B;
     p.ops = T->d_ops3;
     p.n_ops = (int)T->ops3.size();
