@@ -184,7 +184,6 @@ class ScBinary1024:
         self.y_host.copy_(self.y[:Be])
         self.cw_host = torch.empty((Be, plan.Nw), dtype=torch.int32).pin_memory()
         self.info_host = torch.empty((Be, plan.Kw), dtype=torch.int32).pin_memory()
-        self.y_e = torch.empty((Be, N), dtype=torch.uint8, device=dev)
         self.h2d = int(Be * N)
         self.d2h = int(Be * (plan.Nw + plan.Kw) * 4)
         self.input_note = "uint8 channel symbols [B,N] (%.2f GiB per step per GPU, larger than L2: no flush needed)" % (B * N / 2 ** 30)
@@ -193,11 +192,8 @@ class ScBinary1024:
         self.engine.sc_decode_symbols(self.plan, self.y, self.tab, out=(self.cw_out, self.info_out))
 
     def e2e_step(self):
-        Be = self.Be
-        self.y_e.copy_(self.y_host, non_blocking=True)
-        c, i = self.engine.sc_decode_symbols(self.plan, self.y_e, self.tab, out=(self.cw_out[:Be], self.info_out[:Be]))
-        self.cw_host.copy_(c, non_blocking=True)
-        self.info_host.copy_(i, non_blocking=True)
+        # the public host-batch call: chunked, H2D / decode / D2H overlapped on two streams (engine.host_pipeline)
+        self.engine.sc_decode_symbols_host(self.plan, self.y_host, self.tab, self.cw_host, self.info_host)
 
     def counters(self):
         return self.engine.count_errors(self.info_out, self.info_tx, self.K)
@@ -237,7 +233,7 @@ class ScBinaryLarge:
     name = "sc_n2p%s_r0.8_bec0.1" % os.environ.get("PC_BENCH_LARGE_N", "20")
     kernel = "sc_stream_kernel<symbols>"
     dtype = "f64"
-    default_frames, default_e2e, default_cpu = 296, 64, 32
+    default_frames, default_e2e, default_cpu = 1184, 256, 32
     n = int(os.environ.get("PC_BENCH_LARGE_N", "20"))  # 20 is the BASELINE configuration; smaller values are for profiling runs
     N, K = 1 << n, int(0.8 * (1 << n))
     # stages above 2^13 stream 12 N bytes each + channel ingest 4 N + (N + K)/8 out (fp32 soft-input contract)
@@ -288,7 +284,6 @@ class ScBinaryLarge:
         self.y_host.copy_(self.y[:Be])
         self.cw_host = torch.empty((Be, plan.Nw), dtype=torch.int32).pin_memory()
         self.info_host = torch.empty((Be, plan.Kw), dtype=torch.int32).pin_memory()
-        self.y_e = torch.empty((Be, N), dtype=torch.uint8, device=dev)
         self.h2d = int(Be * N)
         self.d2h = int(Be * (plan.Nw + plan.Kw) * 4)
         self.input_note = "uint8 channel symbols [B,N] (%.2f GiB per step per GPU, larger than L2)" % (B * N / 2 ** 30)
@@ -325,9 +320,9 @@ def awgn_frozen_set(n, K, allow_ga):
 class SclBinary4096:
     """C2: binary SCL L=8, N=4096, K=2048 over BI-AWGN at Eb/N0 = 2 dB, linear-domain float64 (listDecode with q=2)."""
     name = "scl_l8_n4096_k2048_biawgn2dB"
-    kernel = "scl2_kernel (frame-per-CTA binary SCL)"
+    kernel = "sclw_kernel (frame-per-warp binary SCL)"
     dtype = "f64"
-    default_frames, default_e2e, default_cpu = 1 << 15, 1 << 13, 1 << 14
+    default_frames, default_e2e, default_cpu = 1 << 15, 1 << 15, 1 << 14
     N, K, n, L = 4096, 2048, 12, 8
     alg_bytes_frame = 16640  # SURVEY.md 8(d): 4 N bytes of soft input + K/8 bytes out
     info_bits = 2048
@@ -373,9 +368,8 @@ class SclBinary4096:
         self.ai_host.copy_(self.info_tx[:Be])
         self.info_host = torch.empty((Be, K), dtype=torch.uint8).pin_memory()
         self.res_host = torch.empty((Be,), dtype=torch.int32).pin_memory()
-        self.xy_e = torch.empty((Be, N, 2), dtype=torch.float64, device=dev)
-        self.ai_e = torch.empty((Be, K), dtype=torch.uint8, device=dev)
-        self.h2d = int(Be * (N * 16 + K))
+        self.fv_host = torch.zeros((Be, N - K), dtype=torch.uint8).pin_memory()
+        self.h2d = int(Be * (N * 16 + K + (N - K)))
         self.d2h = int(Be * (K + 4))
         self.input_note = ("float64 probability pairs [B,N,2] = xyVectorDistribution.probs (%.2f GiB per step per GPU, larger "
                            "than L2: no flush needed)" % (B * N * 16 / 2 ** 30))
@@ -384,12 +378,9 @@ class SclBinary4096:
         self.out = self.engine.scl_decode_probs(self.plan, self.L, self.xy, self.fvals, self.info_tx)
 
     def e2e_step(self):
-        Be = self.Be
-        self.xy_e.copy_(self.xy_host, non_blocking=True)
-        self.ai_e.copy_(self.ai_host, non_blocking=True)
-        o = self.engine.scl_decode_probs(self.plan, self.L, self.xy_e, self.fvals[:Be], self.ai_e)
-        self.info_host.copy_(o["info"], non_blocking=True)
-        self.res_host.copy_(o["prob_result"], non_blocking=True)
+        # the public host-batch call: chunked, H2D / decode / D2H overlapped on two streams (engine.host_pipeline)
+        self.engine.scl_decode_probs_host(self.plan, self.L, self.xy_host, self.fv_host, self.ai_host, self.info_host,
+                                          self.res_host)
 
     def counters(self):
         torch = self.torch
@@ -487,7 +478,6 @@ class ScQary2048:
         self.xy_host = torch.empty((Be, N, q), dtype=torch.float64).pin_memory()
         self.xy_host.copy_(self.xy[:Be])
         self.info_host = torch.empty((Be, K), dtype=torch.uint8).pin_memory()
-        self.xy_e = torch.empty((Be, N, q), dtype=torch.float64, device=dev)
         self.h2d = int(Be * N * q * 8)
         self.d2h = int(Be * K)
         self.input_note = "float64 probability triples [B,N,3] (%.2f GiB per step per GPU, larger than L2)" % (B * N * q * 8 / 2 ** 30)
@@ -496,9 +486,7 @@ class ScQary2048:
         self.out = self.engine.qsc_decode_probs(self.plan, self.xy)
 
     def e2e_step(self):
-        self.xy_e.copy_(self.xy_host, non_blocking=True)
-        _, i = self.engine.qsc_decode_probs(self.plan, self.xy_e)
-        self.info_host.copy_(i, non_blocking=True)
+        self.engine.qsc_decode_probs_host(self.plan, self.xy_host, self.info_host)
 
     def counters(self):
         torch = self.torch

@@ -82,6 +82,9 @@ int pc_polar_transform_bits(int n, const uint32_t *d_cw_packed, uint32_t *d_u_pa
 /* bytes of device scratch the decoders want for a batch of B frames (they accept less and then work in
  * smaller chunks, down to 32 frames; PC_ERR_NOMEM below that) */
 size_t pc_sc_workspace_bytes(const pc_plan *plan, int64_t B, int input_kind);
+/* frames one launch of the binary SC decoder keeps resident on the device (all SMs busy); batches and host-pipeline chunks
+ * are best sized in whole multiples of it.  No reference counterpart (the reference decodes one frame per call). */
+int64_t pc_sc_wave_frames(const pc_plan *plan);
 
 /* d_xy [B][N][2] float64: entry i holds P(X=0,Y=y_i), P(X=1,Y=y_i) exactly as the reference's
  * xyVectorDistribution.probs.  Outputs: d_cw_packed [B][ceil(N/32)] (re-encoded codeword) and
@@ -113,6 +116,8 @@ int pc_qsc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint
  * d_list_size [B] int32, d_list_prob [B][L] float64 (normalised metrics, list order), d_actual_prob [B] float64,
  * d_list_info [B][L][k] uint8 (may be null on its own).  1 <= L <= 32 (q <= 3) or L <= 8 (q = 4, 5); N >= 2. */
 size_t pc_scl_workspace_bytes(const pc_plan *plan, int L, int64_t B, int want_list);
+/* frames one launch of the list decoder keeps resident on the device (see pc_sc_wave_frames) */
+int64_t pc_scl_wave_frames(const pc_plan *plan, int L);
 int pc_scl_decode_probs(const pc_plan *plan, int L, const double *d_xy, const uint8_t *d_frozen_values,
                         const uint8_t *d_actual_info, int64_t B, uint8_t *d_info, int32_t *d_prob_result,
                         int32_t *d_list_size, double *d_list_prob, double *d_actual_prob, uint8_t *d_list_info,

@@ -26,6 +26,7 @@ namespace pc {
 // sc_stream.cu: one frame per CTA, upper stages streamed through HBM (large blocks)
 bool sc_stream_supported(const pc_plan *plan);
 size_t sc_stream_workspace_bytes(const pc_plan *plan, int64_t B);
+int64_t sc_stream_wave_frames(const pc_plan *plan);
 int sc_stream_decode(const pc_plan *plan, int kind, const void *d_in, int64_t B, const double *h_table, int Y, uint32_t *d_cw,
                      uint32_t *d_info, void *ws, size_t ws_bytes, cudaStream_t st);
 
@@ -52,9 +53,23 @@ template <int KIND>
 __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel(const ScParams p) {
     extern __shared__ double sm_vals[];  // [SMEM_VALS][SC_THREADS]
     __shared__ double s_table[32];
+    __shared__ double s_lut[KIND == PC_INPUT_SYMBOLS ? 768 : 1];
     if (threadIdx.x < 32) s_table[threadIdx.x] = p.table[threadIdx.x];
     __syncthreads();
     const int n = p.n, N = 1 << n;
+    // Discrete channel outputs: an element of level n-1 is a function of two channel symbols and at most one decision bit,
+    // so it is looked up (table built here with the same f_raw / g_raw arithmetic: identical bits) instead of being computed,
+    // stored and re-read -- the largest level never touches the global scratch.  [mode][y_a][y_b], mode 0: f, 1 + u: g.
+    const bool lut = KIND == PC_INPUT_SYMBOLS && n >= 7;
+    const int Y = p.Y;
+    if (lut) {
+        for (int idx = threadIdx.x; idx < 3 * Y * Y; idx += SC_THREADS) {
+            const int m = idx / (Y * Y), ya = (idx / Y) % Y, yb = idx % Y;
+            const double a0 = s_table[2 * ya], a1 = s_table[2 * ya + 1], b0 = s_table[2 * yb], b1 = s_table[2 * yb + 1];
+            s_lut[idx] = m == 0 ? f_raw(a0, a1, b0, b1) : g_raw(a0, a1, b0, b1, (uint32_t)(m - 1));
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * (SC_THREADS / 32) + (threadIdx.x >> 5);
     const int warps_total = gridDim.x * (SC_THREADS / 32);
@@ -129,6 +144,32 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
         uint32_t *iw = p.info_t + col;
         uint32_t cwreg = 0, infoacc = 0;
         int icount = 0;
+        int top_mode = 0;  // lut: 0 while level n-1 is f of the channel pairs (first half), 1 when it is g with x[0, N/2)
+        // elements [h0, h0+cnt) of level n-2 straight from the channel symbols (cnt a multiple of 4)
+        auto level_from_lut = [&](bool isg, int h0, int cnt, uint32_t ub) {
+            const uint8_t *sym = (const uint8_t *)p.in_t + col;
+            const int q = N >> 2, hN = N >> 1;
+            for (int hh = 0; hh < cnt; hh += 4) {
+                const int h = h0 + hh;
+                uint32_t wa = 0, wb = 0;
+                if (top_mode) {
+                    wa = xw[(int64_t)(h >> 5) * p.Bpad] >> (h & 31);
+                    wb = xw[(int64_t)((h + q) >> 5) * p.Bpad] >> ((h + q) & 31);
+                }
+                double a[4], b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t y0 = sym[(int64_t)(h + u) * p.Bpad], y1 = sym[(int64_t)(h + u + hN) * p.Bpad];
+                    const uint32_t y2 = sym[(int64_t)(h + u + q) * p.Bpad], y3 = sym[(int64_t)(h + u + q + hN) * p.Bpad];
+                    const uint32_t ma = top_mode ? 1u + ((wa >> u) & 1u) : 0u, mb = top_mode ? 1u + ((wb >> u) & 1u) : 0u;
+                    a[u] = s_lut[(ma * Y + y0) * Y + y1];
+                    b[u] = s_lut[(mb * Y + y2) * Y + y3];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    st(n - 2, h + u, isg ? g_packed(a[u], b[u], (ub >> (hh + u)) & 1u) : f_packed(a[u], b[u]));
+            }
+        };
 
         if (n == 0) {  // no transform: leaf rule on the raw pair (BinaryPolarEncoderDecoder.py:250-252)
             const SchedEntry e = p.sched[0];
@@ -152,6 +193,10 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
             int lev;
             if (i == 0) {
                 lev = n - 1;
+                if (lut) top_mode = 0, lev = n - 2;
+            } else if (lut && top == n - 1) {
+                top_mode = 1;  // level n-1 is now g(channel pairs, x[0, N/2)): looked up on demand
+                lev = n - 2;
             } else if (top >= stop) {
                 // ---- g at level `top` with the sibling's partial sums x[i - 2^top, i) ----------------
                 const int size = 1 << top;
@@ -179,6 +224,8 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                                 root(h + size, b0, b1);
                                 st(top, h, g_raw(a0, a1, b0, b1, (ub >> b) & 1u));
                             }
+                        } else if (lut && top == n - 2) {
+                            level_from_lut(true, 32 * w, 32, ub);
                         } else {
                             g_level(top, 32 * w, 32, ub);
                         }
@@ -198,6 +245,8 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                         root(h + size, b0, b1);
                         st(lev, h, f_raw(a0, a1, b0, b1));
                     }
+                } else if (lut && lev == n - 2) {
+                    level_from_lut(false, 0, size, 0u);
                 } else {
                     f_level(lev);
                 }
@@ -425,6 +474,12 @@ static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int
 }  // namespace pc
 
 extern "C" {
+
+int64_t pc_sc_wave_frames(const pc_plan *plan) {
+    if (!plan) return 0;
+    if (plan->n > pc::SC_MAX_N) return pc::sc_stream_wave_frames(plan);
+    return (int64_t)pc::sc_grid_max() * pc::SC_THREADS;
+}
 
 size_t pc_sc_workspace_bytes(const pc_plan *plan, int64_t B, int input_kind) {
     if (!plan || B <= 0) return 256;

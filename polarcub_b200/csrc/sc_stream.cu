@@ -367,6 +367,8 @@ static StreamConfig stream_config(const pc_plan *plan, int64_t B) {
 
 bool sc_stream_supported(const pc_plan *plan) { return plan && plan->q == 2 && plan->n > STREAM_BLOCK_L && plan->n <= 24; }
 
+int64_t sc_stream_wave_frames(const pc_plan *plan) { return stream_config(plan, (int64_t)1 << 40).grid; }
+
 size_t sc_stream_workspace_bytes(const pc_plan *plan, int64_t B) {
     const StreamConfig c = stream_config(plan, B);
     return align256((size_t)c.grid * c.vg_stride * 8 + 256) + align256((size_t)c.grid * c.xg_stride * 4 + 256);

@@ -43,6 +43,9 @@ int sclw_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_
                 int64_t B, uint8_t *d_info, int32_t *d_res, int32_t *d_lsize, double *d_lprob, double *d_aprob,
                 uint8_t *d_linfo, void *ws, size_t ws_bytes, cudaStream_t st);
 
+int64_t sclw_wave_frames(const pc_plan *plan, int L);
+int64_t scl2_wave_frames(const pc_plan *plan, int L);
+
 static std::mutex g_scl_mu;
 static std::map<const pc_plan *, SclTables *> g_scl_tables;
 
@@ -733,6 +736,13 @@ size_t pc_scl_workspace_bytes(const pc_plan *plan, int L, int64_t B, int want_li
     const int64_t cap = (int64_t)pc::num_sms() * 2 * pc::SCL_THREADS * 4;
     if (chunk > cap) chunk = cap;
     return pc::scl_layout(plan, L, chunk, want_list != 0).total;
+}
+
+int64_t pc_scl_wave_frames(const pc_plan *plan, int L) {
+    if (!plan || L < 1 || L > pc::SCL_LMAX) return 0;
+    if (pc::sclw_supported(plan, L)) return pc::sclw_wave_frames(plan, L);
+    if (pc::scl2_supported(plan, L)) return pc::scl2_wave_frames(plan, L);
+    return (int64_t)pc::num_sms() * 2 * pc::SCL_THREADS;
 }
 
 /* see include/polarcub_b200.h */

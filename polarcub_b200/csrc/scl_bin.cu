@@ -647,6 +647,8 @@ bool scl2_supported(const pc_plan *plan, int L) {
     return scl2_config(plan, L, 1).ok;
 }
 
+int64_t scl2_wave_frames(const pc_plan *plan, int L) { return scl2_config(plan, L, (int64_t)1 << 40).grid; }
+
 size_t scl2_workspace_bytes(const pc_plan *plan, int L, int64_t B) {
     const Scl2Config c = scl2_config(plan, L, B);
     return align256(align256((size_t)c.grid * c.vg_stride * sizeof(double2) + 256) + (size_t)c.grid * c.rg_stride * 4 + 256);

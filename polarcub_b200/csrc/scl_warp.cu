@@ -789,6 +789,8 @@ bool sclw_supported(const pc_plan *plan, int L) {
     return sclw_config(plan, L, 1).ok;
 }
 
+int64_t sclw_wave_frames(const pc_plan *plan, int L) { return sclw_config(plan, L, (int64_t)1 << 40).grid; }
+
 size_t sclw_workspace_bytes(const pc_plan *plan, int L, int64_t B) {
     const SclwConfig c = sclw_config(plan, L, B);
     return align256(align256((size_t)c.grid * c.vg_stride * sizeof(double2) + 256) + (size_t)c.grid * c.rg_stride * 4 + 256);

@@ -80,10 +80,16 @@ class Plan:
         return _lib.lib().pc_plan_schedule_len(self._h)
 
     def workspace(self, nbytes):
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = None
-            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self._ws
+        """Device scratch for one call, private to the CUDA stream the call is launched on (calls on different streams may
+        overlap, see `host_pipeline`)."""
+        if self._ws is None:
+            self._ws = {}
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            self._ws[key] = None
+            ws = self._ws[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return ws
 
 
 def encode_bits(plan, info_packed):
@@ -212,6 +218,157 @@ def trellis_decode(plan, n0, deletion_prob, ones, sub_bits, sub_len, want_collap
                                             int(maxlen), B, _ptr(cw), _ptr(info), _ptr(col), _ptr(ws), ws.numel(), _stream()),
                "pc_trellis_decode")
     return (cw, info[:, :plan.Kw], col) if want_collapse else (cw, info[:, :plan.Kw])
+
+
+# ---- host-resident batches: chunked, copies overlapped with decoding ---------------------------------------------------
+_PIPE_STREAMS = {}
+
+
+def _pipe_streams(device):
+    key = torch.device(device).index
+    if key not in _PIPE_STREAMS:
+        _PIPE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(2)]
+    return _PIPE_STREAMS[key]
+
+
+def host_pipeline(plan, B, chunk, body):
+    """Runs body(lo, hi, slot) for consecutive chunks [lo, hi) of a batch of B frames, alternating between two CUDA
+    streams (slot 0 / 1): the H2D copies of one chunk overlap the decode kernel of the previous one and the D2H copies
+    of the one before.  body must enqueue everything (copies from / to PINNED host tensors with non_blocking=True and the
+    decode call) on the current stream and use per-slot device buffers.  Returns after enqueueing; the caller's
+    stream waits for both."""
+    cur = torch.cuda.current_stream(plan.device)
+    streams = _pipe_streams(plan.device)
+    for s in streams:
+        s.wait_stream(cur)
+    for j, lo in enumerate(range(0, B, chunk)):
+        with torch.cuda.stream(streams[j & 1]):
+            body(lo, min(B, lo + chunk), j & 1)
+    for s in streams:
+        cur.wait_stream(s)
+
+
+class _Slots:
+    """Per-slot device staging buffers, cached on the plan."""
+
+    def __init__(self, plan, tag):
+        self.plan, self.tag = plan, tag
+        if not hasattr(plan, "_slots"):
+            plan._slots = {}
+
+    def get(self, slot, name, shape, dtype):
+        key = (self.tag, slot, name)
+        t = self.plan._slots.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = self.plan._slots[key] = torch.empty(shape, dtype=dtype, device=self.plan.device)
+        return t
+
+
+def _pinned(t, what):
+    assert (not t.is_cuda) and t.is_pinned() and t.is_contiguous(), what + " must be a contiguous pinned host tensor"
+
+
+def default_host_chunk(B, bytes_per_frame, wave=0, target_bytes=128 << 20):
+    """Chunk size for host_pipeline: one resident wave of the decode kernel when known (every SM busy, nothing queued
+    behind it), else ~128 MiB of input; at least 4 chunks when the batch allows it."""
+    if wave > 0:
+        return max(1, min(B, wave))
+    c = max(1024, int(target_bytes // max(1, bytes_per_frame)))
+    c = min(c, max(1024, (B + 3) // 4))
+    return max(1, min(B, (c + 31) // 32 * 32))
+
+
+def sc_wave_frames(plan):
+    return int(_lib.lib().pc_sc_wave_frames(plan._h))
+
+
+def scl_wave_frames(plan, L):
+    return int(_lib.lib().pc_scl_wave_frames(plan._h, int(L)))
+
+
+def sc_decode_symbols_host(plan, y_host, table, cw_host, info_host, chunk=None):
+    """pc_sc_decode_symbols over a batch in pinned host memory: y_host uint8 [B, N] -> cw_host int32 [B, Nw],
+    info_host int32 [B, Kw] (pinned), copies overlapped with decoding."""
+    _pinned(y_host, "y_host"), _pinned(cw_host, "cw_host"), _pinned(info_host, "info_host")
+    B = y_host.shape[0]
+    chunk = chunk or default_host_chunk(B, plan.N, sc_wave_frames(plan))
+    sl = _Slots(plan, "scsym")
+
+    def body(lo, hi, slot):
+        m = hi - lo
+        y = sl.get(slot, "y", (chunk, plan.N), torch.uint8)[:m]
+        cw = sl.get(slot, "cw", (chunk, plan.Nw), torch.int32)[:m]
+        info = sl.get(slot, "info", (chunk, max(plan.Kw, 1)), torch.int32)[:m]
+        y.copy_(y_host[lo:hi], non_blocking=True)
+        sc_decode_symbols(plan, y, table, out=(cw, info))
+        cw_host[lo:hi].copy_(cw, non_blocking=True)
+        info_host[lo:hi].copy_(info[:, :plan.Kw], non_blocking=True)
+
+    host_pipeline(plan, B, chunk, body)
+
+
+def sc_decode_probs_host(plan, xy_host, cw_host, info_host, chunk=None):
+    """pc_sc_decode_probs over a batch in pinned host memory: xy_host float64 [B, N, 2]."""
+    _pinned(xy_host, "xy_host"), _pinned(cw_host, "cw_host"), _pinned(info_host, "info_host")
+    B = xy_host.shape[0]
+    chunk = chunk or default_host_chunk(B, plan.N * 16, sc_wave_frames(plan))
+    sl = _Slots(plan, "scprob")
+
+    def body(lo, hi, slot):
+        m = hi - lo
+        xy = sl.get(slot, "xy", (chunk, plan.N, 2), torch.float64)[:m]
+        cw = sl.get(slot, "cw", (chunk, plan.Nw), torch.int32)[:m]
+        info = sl.get(slot, "info", (chunk, max(plan.Kw, 1)), torch.int32)[:m]
+        xy.copy_(xy_host[lo:hi], non_blocking=True)
+        sc_decode_probs(plan, xy, out=(cw, info))
+        cw_host[lo:hi].copy_(cw, non_blocking=True)
+        info_host[lo:hi].copy_(info[:, :plan.Kw], non_blocking=True)
+
+    host_pipeline(plan, B, chunk, body)
+
+
+def qsc_decode_probs_host(plan, xy_host, info_host, cw_host=None, chunk=None):
+    """pc_qsc_decode_probs over a batch in pinned host memory: xy_host float64 [B, N, q] -> info_host uint8 [B, k]."""
+    _pinned(xy_host, "xy_host"), _pinned(info_host, "info_host")
+    B = xy_host.shape[0]
+    chunk = chunk or default_host_chunk(B, plan.N * plan.q * 8)
+    sl = _Slots(plan, "qsc")
+
+    def body(lo, hi, slot):
+        m = hi - lo
+        xy = sl.get(slot, "xy", (chunk, plan.N, plan.q), torch.float64)[:m]
+        xy.copy_(xy_host[lo:hi], non_blocking=True)
+        cw, info = qsc_decode_probs(plan, xy)
+        info_host[lo:hi].copy_(info, non_blocking=True)
+        if cw_host is not None:
+            cw_host[lo:hi].copy_(cw, non_blocking=True)
+
+    host_pipeline(plan, B, chunk, body)
+
+
+def scl_decode_probs_host(plan, L, xy_host, fv_host, ai_host, info_host, res_host, chunk=None):
+    """pc_scl_decode_probs over a batch in pinned host memory: xy_host float64 [B, N, q], fv_host uint8 [B, N-k],
+    ai_host uint8 [B, k] -> info_host uint8 [B, k], res_host int32 [B]."""
+    for t, nm in ((xy_host, "xy_host"), (fv_host, "fv_host"), (ai_host, "ai_host"), (info_host, "info_host"), (res_host, "res_host")):
+        _pinned(t, nm)
+    B = xy_host.shape[0]
+    nf = plan.N - plan.k
+    chunk = chunk or default_host_chunk(B, plan.N * plan.q * 8, scl_wave_frames(plan, L))
+    sl = _Slots(plan, "scl")
+
+    def body(lo, hi, slot):
+        m = hi - lo
+        xy = sl.get(slot, "xy", (chunk, plan.N, plan.q), torch.float64)[:m]
+        fv = sl.get(slot, "fv", (chunk, nf), torch.uint8)[:m]
+        ai = sl.get(slot, "ai", (chunk, plan.k), torch.uint8)[:m]
+        xy.copy_(xy_host[lo:hi], non_blocking=True)
+        fv.copy_(fv_host[lo:hi], non_blocking=True)
+        ai.copy_(ai_host[lo:hi], non_blocking=True)
+        o = scl_decode_probs(plan, L, xy, fv, ai)
+        info_host[lo:hi].copy_(o["info"], non_blocking=True)
+        res_host[lo:hi].copy_(o["prob_result"], non_blocking=True)
+
+    host_pipeline(plan, B, chunk, body)
 
 
 def kernel_launch_count():
