@@ -49,6 +49,65 @@ struct ScParams {
     double table[32];   // symbols: [Y][2] joint probabilities
 };
 
+// One f / g node update on packed values with a single division site: the g node's same-side case (1 * 1, ra * rb) is
+// already normalised and divides by exactly 1.0 (exact), so both node kinds end in one `mn / mx`.  Same products, sums,
+// comparisons and quotient as f_packed / g_packed (sc_arith.cuh): identical bits.
+__device__ __forceinline__ double node_packed(double a, double b, bool isg, uint32_t u) {
+    const double ra = d_abs(a), rb = d_abs(b);
+    const double prod = __dmul_rn(ra, rb);
+    double mx, mn;
+    bool side;
+    if (!isg) {
+        const uint32_t s = d_sign(a) ^ d_sign(b);
+        const double A = __dadd_rn(1.0, prod), Bv = __dadd_rn(ra, rb);
+        const bool c = Bv > A, d = A > Bv;
+        mx = c ? Bv : A;
+        mn = c ? A : Bv;
+        side = s ? d : c;
+    } else {
+        const uint32_t sa = d_sign(a) ^ u, sb = d_sign(b);
+        const bool same = sa == sb, c = ra > rb, e = rb > ra, lt1 = prod < 1.0;
+        mx = same ? 1.0 : (c ? ra : rb);
+        mn = same ? prod : (c ? rb : ra);
+        const uint32_t s1 = sb & (lt1 ? 1u : 0u), s2 = sb ? (c ? 1u : 0u) : (e ? 1u : 0u);
+        side = (same ? s1 : s2) != 0u;
+    }
+    return d_pack(mn / mx, side ? 1u : 0u);
+}
+
+// Elements [0, size) of a level from the level above (size >= 4), batches of 4: every load of a batch is issued before the
+// first division.  SSTR / DSTR: element strides (doubles) of the source and destination levels -- SC_THREADS for the
+// shared-memory levels, 32 for the warp's global scratch -- compile-time so that the batch's addresses are immediates.
+// g: the decision bits come from `uw` (one word per 32 elements, pitch Bpad) or, for levels below 32, from `ureg`.
+template <int SSTR, int DSTR>
+__device__ __forceinline__ void level_batches(const double *sp, double *dp, int size, bool isg, const uint32_t *uw, int64_t Bpad,
+                                              uint32_t ureg) {
+    const double *sp2 = sp + (int64_t)size * SSTR;
+    const int per_word = size < 32 ? size : 32;
+#pragma unroll 1
+    for (int w0 = 0; w0 < size; w0 += 32) {
+        uint32_t ubw = ureg;
+        if (isg && size >= 32) {
+            ubw = *uw;
+            uw += Bpad;
+        }
+#pragma unroll 1
+        for (int hh = 0; hh < per_word; hh += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a[u] = sp[u * SSTR];
+                b[u] = sp2[u * SSTR];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dp[u * DSTR] = node_packed(a[u], b[u], isg, (ubw >> (hh + u)) & 1u);
+            sp += 4 * SSTR;
+            sp2 += 4 * SSTR;
+            dp += 4 * DSTR;
+        }
+    }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel(const ScParams p) {
     extern __shared__ double sm_vals[];  // [SMEM_VALS][SC_THREADS]
@@ -75,58 +134,14 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
     const int warps_total = gridDim.x * (SC_THREADS / 32);
     const int64_t groups = (p.frames + 31) / 32;
     const int64_t gvals = N > (1 << (LS + 1)) ? (int64_t)N - (1 << (LS + 1)) : 0;
-    double *gv = p.vals + (int64_t)warp_global * gvals * 32 + lane;
-    double *sv = sm_vals + threadIdx.x;
+    // element h of level lev: shared memory (lev <= LS) at sv[((1 << lev) - 1 + h) * SC_THREADS], else the warp's global
+    // scratch at gv[((1 << lev) - 2^(LS+1) + h) * 32]; both reached through generic pointers (one code path)
+    double *gv = p.vals + (int64_t)warp_global * gvals * 32 + lane - (int64_t)(1 << (LS + 1)) * 32;
+    double *sv = sm_vals + threadIdx.x - SC_THREADS;
+    auto lvl_ptr = [&](int lev) -> double * { return lev <= LS ? sv + (int64_t)(SC_THREADS << lev) : gv + ((int64_t)32 << lev); };
+    auto lvl_stride = [&](int lev) -> int { return lev <= LS ? SC_THREADS : 32; };
 
-    auto ld = [&](int lev, int h) -> double {
-        return lev <= LS ? sv[(((1 << lev) - 1) + h) * SC_THREADS] : gv[(int64_t)(((1 << lev) - (1 << (LS + 1))) + h) * 32];
-    };
-    auto st = [&](int lev, int h, double v) {
-        if (lev <= LS)
-            sv[(((1 << lev) - 1) + h) * SC_THREADS] = v;
-        else
-            gv[(int64_t)(((1 << lev) - (1 << (LS + 1))) + h) * 32] = v;
-    };
-
-    // one tree level, UNR elements per batch: every load of the batch is issued before the first division
-    constexpr int UNR = 4;
-    auto f_level = [&](int lev) {
-        const int size = 1 << lev;
-        if (size >= UNR) {
-            for (int h0 = 0; h0 < size; h0 += UNR) {
-                double a[UNR], b[UNR];
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    a[u] = ld(lev + 1, h0 + u);
-                    b[u] = ld(lev + 1, h0 + u + size);
-                }
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) st(lev, h0 + u, f_packed(a[u], b[u]));
-            }
-        } else {
-            for (int h = 0; h < size; ++h) st(lev, h, f_packed(ld(lev + 1, h), ld(lev + 1, h + size)));
-        }
-    };
-    // elements [h0, h0+cnt) of level lev, decision bits in `ub` starting at bit 0 for element h0
-    auto g_level = [&](int lev, int h0, int cnt, uint32_t ub) {
-        const int size = 1 << lev;
-        if (cnt >= UNR) {
-            for (int hh = 0; hh < cnt; hh += UNR) {
-                double a[UNR], b[UNR];
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    a[u] = ld(lev + 1, h0 + hh + u);
-                    b[u] = ld(lev + 1, h0 + hh + u + size);
-                }
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) st(lev, h0 + hh + u, g_packed(a[u], b[u], (ub >> (hh + u)) & 1u));
-            }
-        } else {
-            for (int hh = 0; hh < cnt; ++hh)
-                st(lev, h0 + hh, g_packed(ld(lev + 1, h0 + hh), ld(lev + 1, h0 + hh + size), (ub >> hh) & 1u));
-        }
-    };
-
+#pragma unroll 1
     for (int64_t grp = warp_global; grp < groups; grp += warps_total) {
         const int64_t col = grp * 32 + lane;  // always < Bpad; columns >= frames hold padding
         auto root = [&](int h, double &v0, double &v1) {
@@ -145,31 +160,6 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
         uint32_t cwreg = 0, infoacc = 0;
         int icount = 0;
         int top_mode = 0;  // lut: 0 while level n-1 is f of the channel pairs (first half), 1 when it is g with x[0, N/2)
-        // elements [h0, h0+cnt) of level n-2 straight from the channel symbols (cnt a multiple of 4)
-        auto level_from_lut = [&](bool isg, int h0, int cnt, uint32_t ub) {
-            const uint8_t *sym = (const uint8_t *)p.in_t + col;
-            const int q = N >> 2, hN = N >> 1;
-            for (int hh = 0; hh < cnt; hh += 4) {
-                const int h = h0 + hh;
-                uint32_t wa = 0, wb = 0;
-                if (top_mode) {
-                    wa = xw[(int64_t)(h >> 5) * p.Bpad] >> (h & 31);
-                    wb = xw[(int64_t)((h + q) >> 5) * p.Bpad] >> ((h + q) & 31);
-                }
-                double a[4], b[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t y0 = sym[(int64_t)(h + u) * p.Bpad], y1 = sym[(int64_t)(h + u + hN) * p.Bpad];
-                    const uint32_t y2 = sym[(int64_t)(h + u + q) * p.Bpad], y3 = sym[(int64_t)(h + u + q + hN) * p.Bpad];
-                    const uint32_t ma = top_mode ? 1u + ((wa >> u) & 1u) : 0u, mb = top_mode ? 1u + ((wb >> u) & 1u) : 0u;
-                    a[u] = s_lut[(ma * Y + y0) * Y + y1];
-                    b[u] = s_lut[(mb * Y + y2) * Y + y3];
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    st(n - 2, h + u, isg ? g_packed(a[u], b[u], (ub >> (hh + u)) & 1u) : f_packed(a[u], b[u]));
-            }
-        };
 
         if (n == 0) {  // no transform: leaf rule on the raw pair (BinaryPolarEncoderDecoder.py:250-252)
             const SchedEntry e = p.sched[0];
@@ -186,74 +176,86 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
             continue;
         }
 
+#pragma unroll 1
         for (int ei = 0; ei < p.n_sched; ++ei) {
             const SchedEntry e = p.sched[ei];
             const int i = e.i, l = e.l, top = e.top;
             const int stop = e.kind == NODE_RATE0 ? l + 1 : l;
-            int lev;
-            if (i == 0) {
-                lev = n - 1;
-                if (lut) top_mode = 0, lev = n - 2;
-            } else if (lut && top == n - 1) {
-                top_mode = 1;  // level n-1 is now g(channel pairs, x[0, N/2)): looked up on demand
-                lev = n - 2;
-            } else if (top >= stop) {
-                // ---- g at level `top` with the sibling's partial sums x[i - 2^top, i) ----------------
-                const int size = 1 << top;
-                if (top < 5) {
-                    const uint32_t ub = cwreg >> ((i - size) & 31);
-                    if (top + 1 == n) {
-                        for (int h = 0; h < size; ++h) {
-                            double a0, a1, b0, b1;
-                            root(h, a0, a1);
-                            root(h + size, b0, b1);
-                            st(top, h, g_raw(a0, a1, b0, b1, (ub >> h) & 1u));
-                        }
-                    } else {
-                        g_level(top, 0, size, ub);
-                    }
-                } else {
-                    const uint32_t *uw = xw + (int64_t)((i - size) >> 5) * p.Bpad;
-                    for (int w = 0; w < (size >> 5); ++w) {
-                        const uint32_t ub = uw[(int64_t)w * p.Bpad];
-                        if (top + 1 == n) {
-                            for (int b = 0; b < 32; ++b) {
-                                const int h = 32 * w + b;
-                                double a0, a1, b0, b1;
-                                root(h, a0, a1);
-                                root(h + size, b0, b1);
-                                st(top, h, g_raw(a0, a1, b0, b1, (ub >> b) & 1u));
-                            }
-                        } else if (lut && top == n - 2) {
-                            level_from_lut(true, 32 * w, 32, ub);
-                        } else {
-                            g_level(top, 32 * w, 32, ub);
-                        }
-                    }
-                }
-                lev = top - 1;
-            } else {
-                lev = -1;  // a rate-0 node that is the whole plus child: nothing to compute
-            }
-            // ---- f down to the node ------------------------------------------------------------------
-            for (; lev >= stop; --lev) {
+            // levels to (re)compute for this node: g at level `top` with the sibling's partial sums x[i - 2^top, i), then f
+            // down to the node; i == 0 starts with f at level n-1; a rate-0 node that is a whole plus child needs nothing
+            int lev = i == 0 ? n - 1 : (top >= stop ? top : -1);
+            bool isg = i != 0;
+#pragma unroll 1
+            for (; lev >= stop; --lev, isg = false) {
                 const int size = 1 << lev;
+                if (lut && lev == n - 1) {  // looked up on demand by the level below
+                    top_mode = isg ? 1 : 0;
+                    continue;
+                }
+                const uint32_t *uw = xw + (int64_t)((i - size) >> 5) * p.Bpad;  // g: decision words of whole-word levels
+                const uint32_t ureg = cwreg >> ((i - size) & 31);               // g: decision bits of levels below 32
+                double *dp = lvl_ptr(lev);
+                const int dstr = lvl_stride(lev);
                 if (lev + 1 == n) {
+                    // from the channel pairs (continuous inputs, or block lengths below the lookup-table threshold)
+#pragma unroll 1
                     for (int h = 0; h < size; ++h) {
                         double a0, a1, b0, b1;
                         root(h, a0, a1);
                         root(h + size, b0, b1);
-                        st(lev, h, f_raw(a0, a1, b0, b1));
+                        uint32_t u = 0;
+                        if (isg) u = ((size >= 32 ? uw[(int64_t)(h >> 5) * p.Bpad] : ureg) >> (h & 31)) & 1u;
+                        dp[(int64_t)h * dstr] = isg ? g_raw(a0, a1, b0, b1, u) : f_raw(a0, a1, b0, b1);
                     }
-                } else if (lut && lev == n - 2) {
-                    level_from_lut(false, 0, size, 0u);
-                } else {
-                    f_level(lev);
+                    continue;
                 }
+                if (size < 4) {  // levels 0, 1: shared memory on both sides
+                    const double *sp = sv + (SC_THREADS << (lev + 1));
+#pragma unroll 1
+                    for (int h = 0; h < size; ++h)
+                        dp[h * SC_THREADS] = node_packed(sp[h * SC_THREADS], sp[(h + size) * SC_THREADS], isg, (ureg >> h) & 1u);
+                    continue;
+                }
+                if (lut && lev == n - 2) {
+                    // straight from the channel symbols through the level n-1 table (destination: global scratch)
+                    const uint8_t *y0p = (const uint8_t *)p.in_t + col, *y1p = y0p + (int64_t)(N >> 1) * p.Bpad;
+                    const uint8_t *y2p = y0p + (int64_t)(N >> 2) * p.Bpad, *y3p = y2p + (int64_t)(N >> 1) * p.Bpad;
+                    const uint32_t *xa = xw, *xb = xw + (int64_t)(N >> 7) * p.Bpad;  // x words of elements h and h + N/4
+                    const uint32_t *uwp = uw;
+#pragma unroll 1
+                    for (int w0 = 0; w0 < size; w0 += 32) {
+                        uint32_t ubw = 0, wa = 0, wb = 0;
+                        if (isg) ubw = *uwp, uwp += p.Bpad;
+                        if (top_mode) wa = *xa, wb = *xb, xa += p.Bpad, xb += p.Bpad;
+#pragma unroll 1
+                        for (int hh = 0; hh < 32; hh += 4) {
+                            double a[4], b[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const uint32_t y0 = y0p[u * p.Bpad], y1 = y1p[u * p.Bpad], y2 = y2p[u * p.Bpad], y3 = y3p[u * p.Bpad];
+                                const uint32_t ma = top_mode ? 1u + ((wa >> (hh + u)) & 1u) : 0u;
+                                const uint32_t mb = top_mode ? 1u + ((wb >> (hh + u)) & 1u) : 0u;
+                                a[u] = s_lut[(ma * Y + y0) * Y + y1];
+                                b[u] = s_lut[(mb * Y + y2) * Y + y3];
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) dp[u * 32] = node_packed(a[u], b[u], isg, (ubw >> (hh + u)) & 1u);
+                            y0p += 4 * p.Bpad, y1p += 4 * p.Bpad, y2p += 4 * p.Bpad, y3p += 4 * p.Bpad;
+                            dp += 4 * 32;
+                        }
+                    }
+                    continue;
+                }
+                if (lev > LS)
+                    level_batches<32, 32>(gv + ((int64_t)32 << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
+                else if (lev == LS)
+                    level_batches<32, SC_THREADS>(gv + ((int64_t)32 << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
+                else
+                    level_batches<SC_THREADS, SC_THREADS>(sv + (SC_THREADS << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
             }
             // ---- the node itself -----------------------------------------------------------------------
             if (e.kind == NODE_INFO) {
-                const uint32_t bit = d_sign(ld(0, 0));  // p0 >= p1 -> 0 (ties and (0,0) -> 0), :252
+                const uint32_t bit = d_sign(sv[SC_THREADS]);  // level 0: p0 >= p1 -> 0 (ties and (0,0) -> 0), :252
                 infoacc |= bit << (icount & 31);
                 if ((++icount & 31) == 0) {
                     iw[(int64_t)((icount >> 5) - 1) * p.Bpad] = infoacc;
@@ -263,6 +265,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
             } else if (l < 5) {
                 cwreg |= e.bits << (i & 31);
             } else {
+#pragma unroll 1
                 for (int w = 0; w < (1 << (l - 5)); ++w) xw[(int64_t)((i >> 5) + w) * p.Bpad] = p.r0_words[e.bits + w];
             }
             // ---- partial sums: x[lo, lo+s) ^= x[lo+s, lo+2s) whenever a plus child completes -----------
@@ -282,6 +285,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
             while (lv < n && ((ii >> lv) & 1)) {  // whole words (lv >= 5 here)
                 const int s = 1 << lv;
                 uint32_t *lo = xw + (int64_t)((ii - s) >> 5) * p.Bpad;
+#pragma unroll 1
                 for (int w = 0; w < (s >> 5); ++w) lo[(int64_t)w * p.Bpad] ^= lo[(int64_t)(w + (s >> 5)) * p.Bpad];
                 ii -= s;
                 ++lv;
