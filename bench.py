@@ -141,7 +141,7 @@ class ScBinary1024:
     name = "sc_n1024_k512_bsc0.11"
     kernel = "sc_decode_kernel<symbols>"
     dtype = "f64"
-    default_frames, default_e2e, default_cpu = 1 << 20, 1 << 18, 1 << 16
+    default_frames, default_e2e, default_cpu = 1 << 20, 1 << 20, 1 << 16
     N, K, n = 1024, 512, 10
     alg_bytes_frame = 4288  # 4 N bytes of soft input + (N + K)/8 bytes out
     info_bits = 512

@@ -320,6 +320,77 @@ __global__ void __launch_bounds__(256) ingest_kernel(int n, int64_t frames, int6
     }
 }
 
+// uint8 symbols, N >= 128, 4-byte aligned input: 128 frames x 128 positions per tile, 4-byte global accesses on both
+// sides (a frame row is read as words, an output row is written as 4 frames per lane).
+__global__ void __launch_bounds__(256) ingest_u8_kernel(int n, int64_t frames, int64_t Bpad, const uint8_t *__restrict__ in,
+                                                        uint8_t *__restrict__ out) {
+    __shared__ uint32_t tile[128][33];  // row (f & 3) * 32 + (f >> 2): the four frames of a lane sit 32 rows apart
+    const int N = 1 << n;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int64_t f0 = (int64_t)blockIdx.x * 128;
+    const uint32_t *in32 = (const uint32_t *)in;
+    for (int pt = blockIdx.y; pt < (N >> 7); pt += gridDim.y) {
+        const int i0 = pt * 128;
+#pragma unroll 4
+        for (int r = wrp; r < 128; r += 8) {
+            const int64_t f = f0 + r;
+            tile[(r & 3) * 32 + (r >> 2)][lane] = f < frames ? in32[(f * N + i0) / 4 + lane] : 0u;
+        }
+        __syncthreads();
+        if (f0 + 4 * lane < Bpad) {
+#pragma unroll 4
+            for (int q = wrp; q < 128; q += 8) {
+                const int w = q >> 2, sh = 8 * (q & 3);
+                const uint32_t v = ((tile[lane][w] >> sh) & 0xffu) | (((tile[32 + lane][w] >> sh) & 0xffu) << 8) |
+                                   (((tile[64 + lane][w] >> sh) & 0xffu) << 16) | (((tile[96 + lane][w] >> sh) & 0xffu) << 24);
+                *(uint32_t *)(out + (int64_t)bitrev_n((uint32_t)(i0 + q), n) * Bpad + f0 + 4 * lane) = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- egress of the codeword with the bit-reversal permutation, n >= 10: out[i] = nat[rev_n(i)] splits into 2^(n-10)
+// independent 32 x 32 bit-matrix transposes (word index and bit index swap roles, each 5-bit field reversed), done in
+// registers: 5 x 16 masked swaps instead of 1024 single-bit gathers per group of 32 words.
+__global__ void __launch_bounds__(256) egress_bitrev_kernel(int n, int64_t frames, int64_t Bpad, const uint32_t *__restrict__ in_t,
+                                                            uint32_t *__restrict__ out) {
+    __shared__ uint32_t tile[8][32][33];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int64_t f0 = (int64_t)blockIdx.x * 32;
+    const int G = 1 << (n - 10), W = 1 << (n - 5);
+    const int64_t col = f0 + lane;
+    for (int g = blockIdx.y * 8 + wrp; g < G; g += gridDim.y * 8) {
+        uint32_t A[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) A[k] = in_t[(int64_t)((31 - (int)(__brev((uint32_t)k) >> 27)) * G + g) * Bpad + col];
+        // Hacker's Delight transpose32 (anti-transpose in LSB-first numbering: T[c] bit r = A[31-r] bit 31-c)
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+            const int j = 16 >> jj;
+            const uint32_t m = jj == 0 ? 0x0000ffffu : jj == 1 ? 0x00ff00ffu : jj == 2 ? 0x0f0f0f0fu : jj == 3 ? 0x33333333u : 0x55555555u;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if (!(k & j)) {
+                    const uint32_t t = (A[k] ^ (A[k + j] >> j)) & m;
+                    A[k] ^= t;
+                    A[k + j] ^= t << j;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tile[wrp][lane][c] = A[c];
+        __syncwarp();
+        const int gw = n > 10 ? (int)(__brev((uint32_t)g) >> (32 - (n - 10))) : 0;
+        const int ow = (31 - (int)(__brev((uint32_t)lane) >> 27)) * G + gw;  // output word written by this lane
+        for (int r = 0; r < 32; ++r) {
+            const int64_t f = f0 + r;
+            if (f < frames) out[f * W + ow] = tile[wrp][r][lane];
+        }
+        __syncwarp();
+    }
+}
+
 // ---- egress: [W][Bpad] words -> [frames][W], optionally applying the bit-reversal permutation ---------
 template <bool BITREV>
 __global__ void __launch_bounds__(256) egress_kernel(int n, int W, int64_t frames, int64_t Bpad,
@@ -444,7 +515,10 @@ static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int
         p.frames = frames;
         const int ptiles = (N + 31) / 32;
         dim3 ig((unsigned)tiles, (unsigned)(ptiles < 64 ? ptiles : 64));
-        if (kind == PC_INPUT_SYMBOLS) {
+        if (kind == PC_INPUT_SYMBOLS && N >= 128 && (((uintptr_t)d_in + (size_t)f0 * N) & 3) == 0) {
+            dim3 ig8((unsigned)((frames + 127) / 128), (unsigned)((N >> 7) < 16 ? (N >> 7) : 16));
+            ingest_u8_kernel<<<ig8, 256, 0, st>>>(plan->n, frames, L.Bpad, (const uint8_t *)d_in + f0 * N, (uint8_t *)p.in_t);
+        } else if (kind == PC_INPUT_SYMBOLS) {
             ingest_kernel<uint8_t><<<ig, 256, 0, st>>>(plan->n, frames, L.Bpad, (const uint8_t *)d_in + f0 * N,
                                                        (uint8_t *)p.in_t, (uint8_t)0);
         } else {
@@ -462,8 +536,14 @@ static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int
         prof_mark(st);
         PC_LAUNCH_CHECK();
         const int jt_cw = (Nw + 255) / 256;
-        egress_kernel<true><<<dim3((unsigned)tiles, (unsigned)jt_cw), 256, 0, st>>>(plan->n, Nw, frames, L.Bpad, p.cw_t,
-                                                                                     d_cw + f0 * Nw);
+        if (plan->n >= 10) {
+            const int G = 1 << (plan->n - 10);
+            egress_bitrev_kernel<<<dim3((unsigned)tiles, (unsigned)((G + 7) / 8 < 8 ? (G + 7) / 8 : 8)), 256, 0, st>>>(
+                plan->n, frames, L.Bpad, p.cw_t, d_cw + f0 * Nw);
+        } else {
+            egress_kernel<true><<<dim3((unsigned)tiles, (unsigned)jt_cw), 256, 0, st>>>(plan->n, Nw, frames, L.Bpad, p.cw_t,
+                                                                                         d_cw + f0 * Nw);
+        }
         PC_LAUNCH_CHECK();
         if (Kw > 0) {
             const int jt_i = (Kw + 255) / 256;
