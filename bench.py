@@ -145,6 +145,8 @@ class ScBinary1024:
     N, K, n = 1024, 512, 10
     alg_bytes_frame = 4288  # 4 N bytes of soft input + (N + K)/8 bytes out
     info_bits = 512
+    ncu = {"dram_bytes_per_frame": 70.4e3, "warp_inst_per_frame": 15.17e3, "issue_active_pct": 60.3,
+           "capture": "profiles/r1_b_sc1024_ncu_summary.md (prof_sc_e)"}
 
     def code(self):
         from polarcub_b200.construction import frozen_set_from_pe, load_pe
@@ -326,6 +328,8 @@ class SclBinary4096:
     N, K, n, L = 4096, 2048, 12, 8
     alg_bytes_frame = 16640  # 4 N bytes of soft input + K/8 bytes out
     info_bits = 2048
+    ncu = {"dram_bytes_per_frame": 4.85e6, "warp_inst_per_frame": 0.924e6, "issue_active_pct": 49.9,
+           "capture": "profiles/r1_c_scl_ncu_summary.md (prof_sclw_d)"}
     allow_ga = False
 
     def code(self):
@@ -661,8 +665,22 @@ def run_ours(args, rank, world, local_rank):
                      "kernel": w.kernel, "kernel_ms_per_launch": k_ms / max(1, k_launches),
                      "kernel_launches": int(k_launches), "kernel_share_of_step": k_ms / ms,
                      "algorithmic_bytes_per_frame": w.alg_bytes_frame, "peak_source": peak_kind,
-                     "note": "SC/SCL decoding is FP64-issue bound, not HBM bound (SURVEY.md 8d); pipe utilisation in profiles/"},
+                     "note": "float64 SC/SCL decoding is bound by instruction issue and the latency of the per-frame scratch, "
+                             "not by the algorithmic HBM bytes (SURVEY.md 8d); see `issue` / `traffic` and profiles/"},
     }
+    ncu = getattr(w, "ncu", None)
+    if ncu and k_ms > 0:
+        # figures of the committed `ncu --set full` capture of this kernel (profiles/), scaled to this run's launches:
+        # traffic = measured DRAM bytes per launch; issue = warp instructions issued per second vs 4 schedulers x SMs x clock
+        fpl = B * args.steps / max(1, k_launches)
+        r = line["roofline"]
+        r["traffic"] = ncu["dram_bytes_per_frame"] * fpl
+        r["traffic_frac_of_peak"] = ncu["dram_bytes_per_frame"] * B * args.steps / (k_ms * 1e-3) / 1e9 / peak
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        ipeak = 4 * 148 * sm_mhz * 1e6
+        iach = ncu["warp_inst_per_frame"] * B * args.steps / (k_ms * 1e-3)
+        r["issue"] = {"achieved": iach, "peak": ipeak, "unit": "warp inst/s", "frac": iach / ipeak,
+                      "ncu_issue_active_pct": ncu["issue_active_pct"], "capture": ncu["capture"]}
     if world == 1:
         import oracle
         cores = os.cpu_count() or 1
@@ -684,7 +702,7 @@ def run_ours(args, rank, world, local_rank):
         s.setup(dev, rank, Bs, 1 << 10)
         for _ in range(2):
             s.step()
-        ms_s = time_steps(torch, s.step, 3, barrier)
+        ms_s = time_steps(torch, s.step, 3, torch.cuda.synchronize)  # rank 0 only: no collective barrier here
         line["secondary"] = {"workload": s.name, "value": 3 * Bs * world * s.info_bits / (ms_s * 1e-3) / 1e9, "unit": "Gbit/s",
                              "frames_per_s": 3 * Bs * world / (ms_s * 1e-3), "frames_per_step_per_gpu": Bs, "steps": 3,
                              "note": "device-resident, this rank's clock only; full line: --workload sc1024"}
@@ -716,7 +734,8 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=300))
     try:
         run_ours(args, rank, world, local_rank)
     finally:
