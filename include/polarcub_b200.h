@@ -93,6 +93,15 @@ int64_t pc_sc_wave_frames(const pc_plan *plan);
 int pc_sc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint32_t *d_cw_packed,
                        uint32_t *d_info_packed, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* Genie pass (BinaryPolarEncoderDecoder.genieSingleDecodeSimulatioan, BinaryPolarEncoderDecoder.py:114-178): every index is
+ * frozen to a known bit -- d_u_packed [B][ceil(N/32)], the u vector of each frame, bit i = u_i -- and the decoder captures
+ * marginalizedUProbs (:268-273): d_marg [B][N][2] float64 = P(U_i = x | u_0^{i-1}, y), normalised as
+ * calcMarginalizedProbabilities does.  d_cw_packed receives the codeword of u.  The plan's frozen set is ignored (only its
+ * length is used).  2 <= N <= 65536. */
+size_t pc_sc_genie_workspace_bytes(const pc_plan *plan, int64_t B);
+int pc_sc_genie_probs(const pc_plan *plan, const double *d_xy, const uint32_t *d_u_packed, int64_t B, uint32_t *d_cw_packed,
+                      double *d_marg, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* d_y [B][N] uint8 channel output symbols; h_table [Y][2] float64 = the channel's joint probabilities
  * (BinaryMemorylessDistribution.probs), 1 <= Y <= 16. */
 int pc_sc_decode_symbols(const pc_plan *plan, const uint8_t *d_y, int64_t B, const double *h_table, int Y,
@@ -135,6 +144,11 @@ size_t pc_trellis_workspace_bytes(const pc_plan *plan, int n0, int maxlen, int64
 int pc_trellis_decode(const pc_plan *plan, int n0, double deletion_prob, int ones, const uint8_t *d_sub_bits,
                       const int32_t *d_sub_len, int maxlen, int64_t B, uint32_t *d_cw_packed, uint32_t *d_info_packed,
                       double *d_first_collapse, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* genie pass over trellis collections (see pc_sc_genie_probs); workspace: pc_trellis_workspace_bytes; n - n0 >= 1 */
+int pc_trellis_genie(const pc_plan *plan, int n0, double deletion_prob, int ones, const uint8_t *d_sub_bits,
+                     const int32_t *d_sub_len, int maxlen, const uint32_t *d_u_packed, int64_t B, uint32_t *d_cw_packed,
+                     double *d_marg, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* ---- Monte-Carlo counters and measurement hooks ---------------------------------------------------- */
 /* d_out3[0..2] += {B, frames whose first nbits differ, differing bits} over packed rows of ceil(nbits/32) words.

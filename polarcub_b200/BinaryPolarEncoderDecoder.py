@@ -119,6 +119,80 @@ class BinaryPolarEncoderDecoder:
                engine.unpack_bits(out[1].cpu().numpy(), self.k).astype(np.int64))
         return res + (out[2].cpu().numpy(),) if want_collapse else res
 
+    # ---- genie runs (BinaryPolarEncoderDecoder.py:101-221): all indices frozen, per-leaf probabilities captured -----------
+    def _genie_u(self, seeds):
+        """u vectors of genie runs: every index frozen, u_i = 0 iff 0.5 >= r_i with r from random.Random(seed) (:24-44,
+        :258-262; uniform prior)."""
+        u = np.empty((len(seeds), self.length), dtype=np.uint8)
+        for t, seed in enumerate(seeds):
+            if seed == -1:
+                u[t] = 1
+            else:
+                rng = random.Random()
+                rng.seed(seed)
+                u[t] = [0 if 0.5 >= rng.random() else 1 for _ in range(self.length)]
+        return u
+
+    def genie_encode_batch(self, xVectorDistribution, seeds):
+        """genieSingleEncodeSimulatioan for a list of seeds -> (encodedVectors int64 [B, N], TV [B, N], H [B, N]).
+        With the uniform prior every captured marginal is exactly [0.5, 0.5]: TV = 0, H = eta(0.5) + eta(0.5) = 1."""
+        self._require_uniform(xVectorDistribution)
+        u = self._genie_u(seeds)
+        packed = torch.from_numpy(engine.pack_bits(u).view(np.int32)).to(self.plan.device)
+        cw = engine.polar_transform_bits(self.n, packed.contiguous())  # x = u B_N F^(x)n; the map is an involution
+        enc = engine.unpack_bits(cw.cpu().numpy(), self.length).astype(np.int64)
+        B = len(seeds)
+        return enc, np.zeros((B, self.length)), np.ones((B, self.length))
+
+    def genie_decode_batch(self, xVectorDistribution, xy, seeds, trustXYProbs=True, return_marginals=False):
+        """genieSingleDecodeSimulatioan for a batch: `xy` float64 [B, N, 2] or a trellis-collection descriptor, one genie
+        seed per frame -> (decodedVectors int64 [B, N], Pe [B, N], H [B, N] or None)."""
+        from .simulation import eta
+        self._require_uniform(xVectorDistribution)
+        u = self._genie_u(seeds)
+        dev = self.plan.device
+        up = torch.from_numpy(engine.pack_bits(u).view(np.int32)).to(dev).contiguous()
+        if isinstance(xy, CollectionOfBinaryTrellises):
+            assert xy.frames == len(seeds) and len(xy) == self.length
+            if xy.n0 == 0:
+                raise PolarcubError("n0 = 0 is not supported by the CUDA trellis path")
+            if xy.n == xy.n0:
+                raise PolarcubError("genie runs over a single trellis (n == n0) are not supported by the CUDA path")
+            cw, marg = engine.trellis_genie(self.plan, xy.n0, xy.deletionProb, xy.ones, torch.from_numpy(xy.sub_bits).to(dev),
+                                            torch.from_numpy(xy.sub_len).to(dev), up)
+        else:
+            x = xy if torch.is_tensor(xy) else torch.from_numpy(np.ascontiguousarray(xy, dtype=np.float64))
+            assert x.shape == (len(seeds), self.length, 2)
+            cw, marg = engine.sc_genie_probs(self.plan, x.to(dev).contiguous(), up)
+        dec = engine.unpack_bits(cw.cpu().numpy(), self.length).astype(np.int64)
+        marg = marg.cpu().numpy()
+        if trustXYProbs:  # :153-157
+            Pe = np.minimum(marg[..., 0], marg[..., 1])
+            flat = marg.reshape(-1, 2)
+            H = np.array([eta(a) + eta(b) for a, b in flat.tolist()]).reshape(marg.shape[:2])  # math.log2, as the reference
+        else:  # :158-171: compare the probability of the actual u_i (polarTransformOfBits of the decoded vector) with the other
+            d = u.astype(np.int64)  # the decoded vector is the codeword of u
+            pd = np.take_along_axis(marg, d[..., None], axis=2)[..., 0]
+            po = np.take_along_axis(marg, 1 - d[..., None], axis=2)[..., 0]
+            Pe = np.where(pd > po, 0.0, np.where(pd == po, 0.5, 1.0))
+            H = None
+        return (dec, Pe, H, marg) if return_marginals else (dec, Pe, H)
+
+    def genieSingleDecodeSimulatioan(self, xVectorDistribution, xyVectorDistribution, genieSingleRunSeed, trustXYProbs):
+        """BinaryPolarEncoderDecoder.py:114-178 -> (decodedVector, Pevec, Hvec)."""
+        assert len(xVectorDistribution) == self.length
+        xy = xyVectorDistribution
+        if not isinstance(xy, CollectionOfBinaryTrellises):
+            xy = _probs_of(xy, self.length, 2).reshape(1, self.length, 2)
+        dec, Pe, H = self.genie_decode_batch(xVectorDistribution, xy, [genieSingleRunSeed], trustXYProbs)
+        return dec[0], list(Pe[0]), (list(H[0]) if trustXYProbs else [])
+
+    def genieSingleEncodeSimulatioan(self, xVectorDistribution, genieSingleRunSeed):
+        """BinaryPolarEncoderDecoder.py:180-221 -> (encodedVector, TVvec, Hvec)."""
+        assert len(xVectorDistribution) == self.length
+        enc, TV, H = self.genie_encode_batch(xVectorDistribution, [genieSingleRunSeed])
+        return enc[0], list(TV[0]), list(H[0])
+
     # ---- the reference's entry points -----------------------------------------------------------------
     def encode(self, xVectorDistribution, information):
         """BinaryPolarEncoderDecoder.py:46-69 -> encodedVector int64 [N]."""

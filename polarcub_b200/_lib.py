@@ -36,6 +36,10 @@ SIGNATURES = {
     "pc_scl_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int64, c_int]),
     "pc_scl_decode_probs": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pc_sc_genie_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
+    "pc_sc_genie_probs": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pc_trellis_genie": (c_int, [c_void_p, c_int, ctypes.c_double, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p,
+                                 c_void_p, c_void_p, c_size_t, c_void_p]),
     "pc_trellis_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int64]),
     "pc_trellis_decode": (c_int, [c_void_p, c_int, ctypes.c_double, c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -55,7 +55,7 @@ void prof_mark(cudaStream_t st);  // bench.py timing hook: call before and after
 // BinaryPolarEncoderDecoder.recursiveEncodeDecode (BinaryPolarEncoderDecoder.py:223-325) into a list of
 // nodes visited left to right.  A node is either a single information leaf or a maximal all-frozen
 // (rate-0) sub-tree whose codeword is known in advance, so its probabilities are never computed.
-enum : int { NODE_INFO = 0, NODE_RATE0 = 1 };
+enum : int { NODE_INFO = 0, NODE_RATE0 = 1, NODE_GENIE = 2 };  // GENIE: known leaf bit, leaf probabilities captured
 struct SchedEntry {
     int32_t i;      // first u index covered by the node
     int8_t l;       // log2 of the node size
@@ -68,6 +68,7 @@ struct SchedEntry {
 void scl_tables_release(const pc_plan *p);
 void stream_tables_release(const pc_plan *p);
 void trellis_tables_release(const pc_plan *p);
+void genie_tables_release(const pc_plan *p);
 
 }  // namespace pc
 

@@ -162,6 +162,7 @@ void pc_plan_destroy(pc_plan *p) {
     pc::scl_tables_release(p);
     pc::stream_tables_release(p);
     pc::trellis_tables_release(p);
+    pc::genie_tables_release(p);
     cudaFree(p->d_sched);
     cudaFree(p->d_r0_words);
     cudaFree(p->d_src);

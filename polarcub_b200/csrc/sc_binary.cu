@@ -19,6 +19,9 @@
 //    a register;
 //  * the channel level is read through a transposed, bit-reversed copy made by the ingest kernel, and the
 //    decoded words are transposed back (codeword bit-reversed to the reference order) by the egress kernel.
+#include <map>
+#include <mutex>
+
 #include "sc_arith.cuh"
 
 namespace pc {
@@ -46,6 +49,8 @@ struct ScParams {
     double *vals;       // [warps][N - 2^(LS+1)][32] scratch for levels > LS
     uint32_t *cw_t;     // [Nw][Bpad] natural-order codeword words (also the partial-sum store)
     uint32_t *info_t;   // [Kw][Bpad]
+    const uint32_t *u_t;  // genie: [Nw][Bpad] the known u bits (natural u order)
+    double *marg_t;       // genie: [N][Bpad] packed level-0 value of every leaf
     double table[32];   // symbols: [Y][2] joint probabilities
 };
 
@@ -108,7 +113,7 @@ __device__ __forceinline__ void level_batches(const double *sp, double *dp, int 
     }
 }
 
-template <int KIND>
+template <int KIND, bool GENIE = false>
 __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel(const ScParams p) {
     extern __shared__ double sm_vals[];  // [SMEM_VALS][SC_THREADS]
     __shared__ double s_table[32];
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
         };
         uint32_t *xw = p.cw_t + col;  // word w at xw[w * Bpad]
         uint32_t *iw = p.info_t + col;
-        uint32_t cwreg = 0, infoacc = 0;
+        uint32_t cwreg = 0, infoacc = 0, gword = 0;
         int icount = 0;
         int top_mode = 0;  // lut: 0 while level n-1 is f of the channel pairs (first half), 1 when it is g with x[0, N/2)
 
@@ -254,7 +259,13 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                     level_batches<SC_THREADS, SC_THREADS>(sv + (SC_THREADS << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
             }
             // ---- the node itself -----------------------------------------------------------------------
-            if (e.kind == NODE_INFO) {
+            if (GENIE) {
+                // genie pass (BinaryPolarEncoderDecoder.py:114-178): every index is frozen to a known bit; the leaf's
+                // probabilities P(u_i | u_0^{i-1}, y) are captured (:268-273) as the packed level-0 value
+                if ((i & 31) == 0) gword = p.u_t[(int64_t)(i >> 5) * p.Bpad + col];
+                p.marg_t[(int64_t)i * p.Bpad + col] = sv[SC_THREADS];
+                cwreg |= ((gword >> (i & 31)) & 1u) << (i & 31);
+            } else if (e.kind == NODE_INFO) {
                 const uint32_t bit = d_sign(sv[SC_THREADS]);  // level 0: p0 >= p1 -> 0 (ties and (0,0) -> 0), :252
                 infoacc |= bit << (icount & 31);
                 if ((++icount & 31) == 0) {
@@ -291,7 +302,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                 ++lv;
             }
         }
-        if (icount & 31) iw[(int64_t)(icount >> 5) * p.Bpad] = infoacc;
+        if (!GENIE && (icount & 31)) iw[(int64_t)(icount >> 5) * p.Bpad] = infoacc;
     }
 }
 
@@ -555,6 +566,192 @@ static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int
     return PC_OK;
 }
 
+// ---- genie pass: all indices frozen to per-frame known bits, leaf probabilities captured -------------------------------
+// (BinaryPolarEncoderDecoder.genieSingleDecodeSimulatioan, BinaryPolarEncoderDecoder.py:114-178, capture :268-273)
+struct GenieTables {
+    SchedEntry *d_sched = nullptr;
+    int n_sched = 0;
+};
+static std::mutex g_genie_mu;
+static std::map<const pc_plan *, GenieTables *> g_genie_tables;
+
+static GenieTables *genie_tables(const pc_plan *plan) {
+    std::lock_guard<std::mutex> lk(g_genie_mu);
+    auto it = g_genie_tables.find(plan);
+    if (it != g_genie_tables.end()) return it->second;
+    std::vector<SchedEntry> sched((size_t)plan->N);
+    for (int i = 0; i < plan->N; ++i) {
+        SchedEntry e{};
+        e.i = i;
+        e.l = 0;
+        e.kind = NODE_GENIE;
+        e.top = (int8_t)(i == 0 ? plan->n : __builtin_ctz((unsigned)i));
+        sched[i] = e;
+    }
+    GenieTables *T = new GenieTables();
+    T->n_sched = plan->N;
+    if (cudaMalloc((void **)&T->d_sched, sizeof(SchedEntry) * sched.size()) != cudaSuccess ||
+        cudaMemcpy(T->d_sched, sched.data(), sizeof(SchedEntry) * sched.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("genie schedule: device upload failed");
+        delete T;
+        return nullptr;
+    }
+    g_genie_tables[plan] = T;
+    return T;
+}
+
+void genie_tables_release(const pc_plan *p) {
+    std::lock_guard<std::mutex> lk(g_genie_mu);
+    auto it = g_genie_tables.find(p);
+    if (it == g_genie_tables.end()) return;
+    cudaFree(it->second->d_sched);
+    delete it->second;
+    g_genie_tables.erase(it);
+}
+
+// u_t[w][f] = bits [bit_off + 32 w, bit_off + 32 w + 32) of row f of `u` (row pitch in words), masked to N bits
+__global__ void __launch_bounds__(256) genie_u_ingest_kernel(int N, int64_t frames, int64_t Bpad, const uint32_t *__restrict__ u,
+                                                             int64_t pitch_words, int bit_off, uint32_t *__restrict__ u_t) {
+    const int Nw = N >= 32 ? N >> 5 : 1;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= Bpad * Nw) return;
+    const int w = (int)(gid / Bpad);
+    const int64_t f = gid - (int64_t)w * Bpad;
+    uint32_t v = 0;
+    if (f < frames) {
+        const int64_t b0 = (int64_t)bit_off + 32 * (int64_t)w;
+        const uint32_t *row = u + f * pitch_words;
+        const int sh = (int)(b0 & 31);
+        v = row[b0 >> 5] >> sh;
+        if (sh && N - 32 * w > 32 - sh) v |= row[(b0 >> 5) + 1] << (32 - sh);
+        if (N < 32) v &= (1u << N) - 1u;
+    }
+    u_t[gid] = v;
+}
+
+// marg[f][off + 2 i .. + 1] = calcMarginalizedProbabilities of leaf i (BinaryMemorylessVectorDistribution.py:52-69) from the
+// packed level-0 value: pair (1, r) or (r, 1) by the sign bit, NaN = (0, 0) -> [0.5, 0.5]
+__global__ void __launch_bounds__(256) genie_marg_egress_kernel(int N, int64_t frames, int64_t Bpad, const double *__restrict__ marg_t,
+                                                                double *__restrict__ out, int64_t pitch, int64_t off) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t f0 = (int64_t)blockIdx.x * 32;
+    for (int it = blockIdx.y; it < (N + 31) / 32; it += gridDim.y) {
+        const int i0 = it * 32;
+        for (int r = ty; r < 32; r += 8) tile[r][tx] = (i0 + r < N) ? marg_t[(int64_t)(i0 + r) * Bpad + f0 + tx] : 0.0;
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int64_t f = f0 + r;
+            const int i = i0 + tx;
+            if (f < frames && i < N) {
+                const double v = tile[tx][r];
+                double m0 = 0.5, m1 = 0.5;
+                if (v == v) {
+                    const double rr = d_abs(v);
+                    const double p0 = d_sign(v) ? rr : 1.0, p1 = d_sign(v) ? 1.0 : rr;
+                    const double s = __dadd_rn(__dadd_rn(0.0, p0), p1);
+                    m0 = p0 / s;
+                    m1 = p1 / s;
+                }
+                double2 *o = (double2 *)(out + f * pitch + off) + i;
+                *o = make_double2(m0, m1);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+struct GenieLayout {
+    ScLayout L;
+    size_t off_u, off_marg, total;
+};
+static GenieLayout genie_layout(const pc_plan *plan, int64_t chunk) {
+    GenieLayout G;
+    G.L = sc_layout(plan, chunk, PC_INPUT_PROBS);
+    const int64_t N = plan->N, Nw = N >= 32 ? N >> 5 : 1;
+    size_t o = G.L.total;
+    G.off_u = o;
+    o += align256((size_t)Nw * G.L.Bpad * 4);
+    G.off_marg = o;
+    o += align256((size_t)N * G.L.Bpad * 8);
+    G.total = o;
+    return G;
+}
+
+size_t sc_genie_workspace_bytes(const pc_plan *plan, int64_t B) {
+    return genie_layout(plan, sc_pick_chunk(B, PC_INPUT_PROBS)).total;
+}
+
+// d_u: known u bits, row f at d_u + f * u_pitch_words, first bit u_bit_off; d_marg: row f at d_marg + f * marg_pitch + marg_off
+int sc_genie_common(const pc_plan *plan, const double *d_xy, const uint32_t *d_u, int64_t u_pitch_words, int u_bit_off, int64_t B,
+                    uint32_t *d_cw, double *d_marg, int64_t marg_pitch, int64_t marg_off, void *ws, size_t ws_bytes,
+                    cudaStream_t st) {
+    PC_REQUIRE(plan && plan->q == 2, "binary plan required");
+    PC_REQUIRE(plan->n >= 1 && plan->n <= SC_MAX_N, "genie pass needs 2 <= N <= 65536");
+    PC_REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return PC_OK;
+    PC_REQUIRE(d_xy && d_u && d_cw && d_marg && ws, "null buffer");
+    PC_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+    PC_REQUIRE(((uintptr_t)d_marg & 15) == 0 && (marg_pitch & 1) == 0 && (marg_off & 1) == 0, "marginal output must be 16-byte aligned");
+    GenieTables *T = genie_tables(plan);
+    if (!T) return PC_ERR_CUDA;
+    int64_t chunk = sc_pick_chunk(B, PC_INPUT_PROBS);
+    while (chunk > 32 && genie_layout(plan, chunk).total > ws_bytes) chunk = round_up(chunk / 2, 32);
+    GenieLayout G = genie_layout(plan, chunk);
+    if (G.total > ws_bytes) {
+        set_error("workspace too small: %zu bytes given, %zu needed for a 32-frame chunk", ws_bytes, G.total);
+        return PC_ERR_NOMEM;
+    }
+    const ScLayout &L = G.L;
+    const int N = plan->N, Nw = (N + 31) / 32;
+    char *base = (char *)ws;
+    ScParams p{};
+    p.n = plan->n;
+    p.k = 0;
+    p.n_sched = T->n_sched;
+    p.Bpad = L.Bpad;
+    p.sched = T->d_sched;
+    p.r0_words = plan->d_r0_words;
+    p.in_t = base + L.off_in;
+    p.vals = (double *)(base + L.off_vals);
+    p.cw_t = (uint32_t *)(base + L.off_cw);
+    p.info_t = (uint32_t *)(base + L.off_info);
+    p.u_t = (const uint32_t *)(base + G.off_u);
+    p.marg_t = (double *)(base + G.off_marg);
+    const size_t smem = (size_t)SMEM_VALS * SC_THREADS * sizeof(double);
+    PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<PC_INPUT_PROBS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t f0 = 0; f0 < B; f0 += chunk) {
+        const int64_t frames = (B - f0) < chunk ? (B - f0) : chunk;
+        const int64_t tiles = (frames + 31) / 32;
+        p.frames = frames;
+        const int ptiles = (N + 31) / 32;
+        dim3 ig((unsigned)tiles, (unsigned)(ptiles < 64 ? ptiles : 64));
+        ingest_kernel<double2><<<ig, 256, 0, st>>>(plan->n, frames, L.Bpad, (const double2 *)d_xy + f0 * N, (double2 *)p.in_t,
+                                                   make_double2(0.5, 0.5));
+        PC_LAUNCH_CHECK();
+        const int64_t uitems = L.Bpad * Nw;
+        genie_u_ingest_kernel<<<(unsigned)((uitems + 255) / 256), 256, 0, st>>>(N, frames, L.Bpad, d_u + f0 * u_pitch_words,
+                                                                                 u_pitch_words, u_bit_off, (uint32_t *)p.u_t);
+        PC_LAUNCH_CHECK();
+        const int64_t blocks = (tiles * 32 + SC_THREADS - 1) / SC_THREADS;
+        const int grid = (int)(blocks < L.grid ? blocks : L.grid);
+        sc_decode_kernel<PC_INPUT_PROBS, true><<<grid, SC_THREADS, smem, st>>>(p);
+        PC_LAUNCH_CHECK();
+        if (plan->n >= 10) {
+            const int Gq = 1 << (plan->n - 10);
+            egress_bitrev_kernel<<<dim3((unsigned)tiles, (unsigned)((Gq + 7) / 8 < 8 ? (Gq + 7) / 8 : 8)), 256, 0, st>>>(
+                plan->n, frames, L.Bpad, p.cw_t, d_cw + f0 * Nw);
+        } else {
+            egress_kernel<true><<<dim3((unsigned)tiles, 1u), 256, 0, st>>>(plan->n, Nw, frames, L.Bpad, p.cw_t, d_cw + f0 * Nw);
+        }
+        PC_LAUNCH_CHECK();
+        genie_marg_egress_kernel<<<dim3((unsigned)tiles, (unsigned)(ptiles < 64 ? ptiles : 64)), 256, 0, st>>>(
+            N, frames, L.Bpad, p.marg_t, d_marg + f0 * marg_pitch, marg_pitch, marg_off);
+        PC_LAUNCH_CHECK();
+    }
+    return PC_OK;
+}
+
 }  // namespace pc
 
 extern "C" {
@@ -569,6 +766,22 @@ size_t pc_sc_workspace_bytes(const pc_plan *plan, int64_t B, int input_kind) {
     if (!plan || B <= 0) return 256;
     if (pc::sc_use_stream(plan, B)) return pc::sc_stream_workspace_bytes(plan, B);
     return pc::sc_layout(plan, pc::sc_pick_chunk(B, input_kind), input_kind).total;
+}
+
+size_t pc_sc_genie_workspace_bytes(const pc_plan *plan, int64_t B) {
+    if (!plan || B <= 0) return 256;
+    return pc::sc_genie_workspace_bytes(plan, B);
+}
+
+int pc_sc_genie_probs(const pc_plan *plan, const double *d_xy, const uint32_t *d_u_packed, int64_t B, uint32_t *d_cw_packed,
+                      double *d_marg, void *d_workspace, size_t workspace_bytes, void *stream) {
+    if (!plan) {
+        pc::set_error("plan is null");
+        return PC_ERR_INVALID;
+    }
+    const int Nw = (plan->N + 31) / 32;
+    return pc::sc_genie_common(plan, d_xy, d_u_packed, Nw, 0, B, d_cw_packed, d_marg, (int64_t)2 * plan->N, 0, d_workspace,
+                               workspace_bytes, (cudaStream_t)stream);
 }
 
 int pc_sc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint32_t *d_cw_packed, uint32_t *d_info_packed,

@@ -423,7 +423,15 @@ extern "C" size_t pc_sc_workspace_bytes(const pc_plan *plan, int64_t B, int inpu
 extern "C" int pc_sc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint32_t *d_cw_packed, uint32_t *d_info_packed,
                                   void *d_workspace, size_t workspace_bytes, void *stream);
 
+// sc_binary.cu: genie pass over a (sub-)block
+size_t sc_genie_workspace_bytes(const pc_plan *plan, int64_t B);
+int sc_genie_common(const pc_plan *plan, const double *d_xy, const uint32_t *d_u, int64_t u_pitch_words, int u_bit_off, int64_t B,
+                    uint32_t *d_cw, double *d_marg, int64_t marg_pitch, int64_t marg_off, void *ws, size_t ws_bytes,
+                    cudaStream_t st);
+
 struct TrellisRun {
+    const uint32_t *genie_u = nullptr;  // genie pass: known u bits [frames][Nw] and captured leaf probabilities [frames][N][2]
+    double *genie_marg = nullptr;
     const pc_plan *plan;
     TrellisTables *tabs;
     TrellisWs W;
@@ -475,7 +483,12 @@ static int trellis_descend(TrellisRun &R, int k, int node, uint32_t *cw_out) {
         if (collapse) {
             const pc_plan *sp = R.tabs->sub[child];
             uint32_t *sinfo = (uint32_t *)(R.ws + R.W.off_subinfo[child]);
-            const int rc = pc_sc_decode_probs(sp, p.probs_out, F, dst, sinfo, R.ws + R.W.off_sc, R.sc_bytes, R.st);
+            int rc;
+            if (R.genie_u)
+                rc = sc_genie_common(sp, p.probs_out, R.genie_u, words_of(plan->N), child * Tn, F, dst, R.genie_marg,
+                                     (int64_t)2 * plan->N, (int64_t)2 * child * Tn, R.ws + R.W.off_sc, R.sc_bytes, R.st);
+            else
+                rc = pc_sc_decode_probs(sp, p.probs_out, F, dst, sinfo, R.ws + R.W.off_sc, R.sc_bytes, R.st);
             if (rc) return rc;
         } else {
             const int rc = trellis_descend(R, k + 1, child, dst);
@@ -492,24 +505,34 @@ static int trellis_descend(TrellisRun &R, int k, int node, uint32_t *cw_out) {
 
 extern "C" {
 
+static size_t trellis_sc_bytes(pc::TrellisTables *T, int64_t chunk) {
+    size_t sc = 256;
+    if (T)
+        for (pc_plan *sp : T->sub) {
+            size_t b = pc_sc_workspace_bytes(sp, chunk, PC_INPUT_PROBS);
+            if (sp->n >= 1) {
+                const size_t g = pc::sc_genie_workspace_bytes(sp, chunk);
+                if (g > b) b = g;
+            }
+            if (b > sc) sc = b;
+        }
+    return sc;
+}
+
 size_t pc_trellis_workspace_bytes(const pc_plan *plan, int n0, int maxlen, int64_t B) {
     if (!plan || plan->q != 2 || n0 < 1 || n0 > plan->n || B <= 0 || maxlen < 1) return 256;
     int64_t chunk = B < 4096 ? B : 4096;
     pc::TrellisWs W = pc::trellis_ws(plan, n0, maxlen, chunk);
     pc::TrellisTables *T = pc::trellis_tables(plan, n0);
-    size_t sc = 256;
-    if (T)
-        for (pc_plan *sp : T->sub) {
-            const size_t b = pc_sc_workspace_bytes(sp, chunk, PC_INPUT_PROBS);
-            if (b > sc) sc = b;
-        }
-    return W.total + pc::align256(sc + 256);
+    return W.total + pc::align256(trellis_sc_bytes(T, chunk) + 256);
 }
 
-int pc_trellis_decode(const pc_plan *plan, int n0, double deletion_prob, int ones, const uint8_t *d_sub_bits,
-                      const int32_t *d_sub_len, int maxlen, int64_t B, uint32_t *d_cw_packed, uint32_t *d_info_packed,
-                      double *d_first_collapse, void *d_workspace, size_t workspace_bytes, void *stream) {
+static int trellis_common(const pc_plan *plan, int n0, double deletion_prob, int ones, const uint8_t *d_sub_bits,
+                          const int32_t *d_sub_len, int maxlen, int64_t B, uint32_t *d_cw_packed, uint32_t *d_info_packed,
+                          double *d_first_collapse, const uint32_t *d_genie_u, double *d_genie_marg, void *d_workspace,
+                          size_t workspace_bytes, void *stream) {
     using namespace pc;
+    const bool genie = d_genie_u != nullptr;
     PC_REQUIRE(plan && plan->q == 2, "binary plan required");
     PC_REQUIRE(n0 >= 1 && n0 <= 4 && n0 <= plan->n, "n0 must be in [1, min(4, n)]");
     PC_REQUIRE(plan->n - n0 <= 16, "sub-blocks longer than 2^16 are not supported");
@@ -517,16 +540,13 @@ int pc_trellis_decode(const pc_plan *plan, int n0, double deletion_prob, int one
     PC_REQUIRE(deletion_prob >= 0.0 && deletion_prob <= 1.0, "deletion probability out of range");
     PC_REQUIRE(B >= 0, "negative batch");
     if (B == 0) return PC_OK;
-    PC_REQUIRE(d_sub_bits && d_sub_len && d_cw_packed && (d_info_packed || plan->k == 0) && d_workspace, "null buffer");
+    PC_REQUIRE(d_sub_bits && d_sub_len && d_cw_packed && (genie || d_info_packed || plan->k == 0) && d_workspace, "null buffer");
+    if (genie) PC_REQUIRE(d_genie_marg && plan->n - n0 >= 1, "genie pass needs the marginal output and sub-blocks of at least 2 symbols");
     PC_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "workspace must be 256-byte aligned");
     TrellisTables *T = trellis_tables(plan, n0);
     if (!T) return PC_ERR_CUDA;
     int64_t chunk = B < 4096 ? B : 4096;
-    size_t sc = 256;
-    for (pc_plan *sp : T->sub) {
-        const size_t b = pc_sc_workspace_bytes(sp, chunk, PC_INPUT_PROBS);
-        if (b > sc) sc = b;
-    }
+    const size_t sc = trellis_sc_bytes(T, chunk);
     TrellisWs W = trellis_ws(plan, n0, maxlen, chunk);
     if (W.total + align256(sc + 256) > workspace_bytes) {
         set_error("workspace too small: %zu bytes given, %zu needed", workspace_bytes, W.total + align256(sc + 256));
@@ -573,17 +593,38 @@ int pc_trellis_decode(const pc_plan *plan, int n0, double deletion_prob, int one
         R.base.sub_len = d_sub_len + f0 * Tn;
         R.raw_first = d_first_collapse ? d_first_collapse + f0 * Tn * 2 : nullptr;
         R.raw_done = false;
+        R.genie_u = genie ? d_genie_u + f0 * Nw : nullptr;
+        R.genie_marg = genie ? d_genie_marg + f0 * 2 * plan->N : nullptr;
         uint32_t *root = (uint32_t *)(R.ws + W.off_cw[0]);
         const int rc = trellis_descend(R, 0, 0, root);
         if (rc) return rc;
         PC_CUDA(cudaMemcpyAsync(d_cw_packed + f0 * Nw, root, (size_t)R.frames * Nw * 4, cudaMemcpyDeviceToDevice, R.st));
-        if (Kw > 0) {
+        if (Kw > 0 && !genie) {
             const int64_t warps = R.frames * Kw;
             merge_info_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, R.st>>>(R.frames, M, d_info_packed + f0 * Kw);
             PC_LAUNCH_CHECK();
         }
     }
     return PC_OK;
+}
+
+
+int pc_trellis_decode(const pc_plan *plan, int n0, double deletion_prob, int ones, const uint8_t *d_sub_bits,
+                      const int32_t *d_sub_len, int maxlen, int64_t B, uint32_t *d_cw_packed, uint32_t *d_info_packed,
+                      double *d_first_collapse, void *d_workspace, size_t workspace_bytes, void *stream) {
+    return trellis_common(plan, n0, deletion_prob, ones, d_sub_bits, d_sub_len, maxlen, B, d_cw_packed, d_info_packed,
+                          d_first_collapse, nullptr, nullptr, d_workspace, workspace_bytes, stream);
+}
+
+int pc_trellis_genie(const pc_plan *plan, int n0, double deletion_prob, int ones, const uint8_t *d_sub_bits,
+                     const int32_t *d_sub_len, int maxlen, const uint32_t *d_u_packed, int64_t B, uint32_t *d_cw_packed,
+                     double *d_marg, void *d_workspace, size_t workspace_bytes, void *stream) {
+    if (!d_u_packed || !d_marg) {
+        pc::set_error("genie pass needs the known u bits and the marginal output");
+        return PC_ERR_INVALID;
+    }
+    return trellis_common(plan, n0, deletion_prob, ones, d_sub_bits, d_sub_len, maxlen, B, d_cw_packed, nullptr, nullptr,
+                          d_u_packed, d_marg, d_workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -220,6 +220,37 @@ def trellis_decode(plan, n0, deletion_prob, ones, sub_bits, sub_len, want_collap
     return (cw, info[:, :plan.Kw], col) if want_collapse else (cw, info[:, :plan.Kw])
 
 
+def sc_genie_probs(plan, xy, u_packed):
+    """Genie pass over memoryless inputs: xy float64 [B, N, 2], u_packed int32 [B, Nw] (the known u bits, device)
+    -> (cw_packed int32 [B, Nw], marg float64 [B, N, 2])."""
+    assert xy.is_cuda and xy.dtype == torch.float64 and xy.is_contiguous() and xy.shape[1:] == (plan.N, 2)
+    B = xy.shape[0]
+    assert u_packed.is_cuda and u_packed.dtype == torch.int32 and u_packed.is_contiguous() and u_packed.shape == (B, plan.Nw)
+    cw = torch.empty((B, plan.Nw), dtype=torch.int32, device=xy.device)
+    marg = torch.empty((B, plan.N, 2), dtype=torch.float64, device=xy.device)
+    ws = plan.workspace(_lib.lib().pc_sc_genie_workspace_bytes(plan._h, B))
+    _lib.check(_lib.lib().pc_sc_genie_probs(plan._h, _ptr(xy), _ptr(u_packed), B, _ptr(cw), _ptr(marg), _ptr(ws), ws.numel(),
+                                            _stream()), "pc_sc_genie_probs")
+    return cw, marg
+
+
+def trellis_genie(plan, n0, deletion_prob, ones, sub_bits, sub_len, u_packed):
+    """Genie pass over trellis collections (see trellis_decode / sc_genie_probs)."""
+    assert sub_bits.is_cuda and sub_bits.dtype == torch.uint8 and sub_bits.is_contiguous() and sub_bits.dim() == 3
+    assert sub_len.is_cuda and sub_len.dtype == torch.int32 and sub_len.is_contiguous()
+    B, T, maxlen = sub_bits.shape
+    assert sub_len.shape == (B, T) and T == plan.N >> n0
+    assert u_packed.is_cuda and u_packed.dtype == torch.int32 and u_packed.is_contiguous() and u_packed.shape == (B, plan.Nw)
+    dev = sub_bits.device
+    cw = torch.empty((B, plan.Nw), dtype=torch.int32, device=dev)
+    marg = torch.empty((B, plan.N, 2), dtype=torch.float64, device=dev)
+    ws = plan.workspace(_lib.lib().pc_trellis_workspace_bytes(plan._h, int(n0), int(maxlen), B))
+    _lib.check(_lib.lib().pc_trellis_genie(plan._h, int(n0), float(deletion_prob), int(ones), _ptr(sub_bits), _ptr(sub_len),
+                                           int(maxlen), _ptr(u_packed), B, _ptr(cw), _ptr(marg), _ptr(ws), ws.numel(), _stream()),
+               "pc_trellis_genie")
+    return cw, marg
+
+
 # ---- host-resident batches: chunked, copies overlapped with decoding ---------------------------------------------------
 _PIPE_STREAMS = {}
 
