@@ -102,6 +102,23 @@ size_t pc_sc_genie_workspace_bytes(const pc_plan *plan, int64_t B);
 int pc_sc_genie_probs(const pc_plan *plan, const double *d_xy, const uint32_t *d_u_packed, int64_t B, uint32_t *d_cw_packed,
                       double *d_marg, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* Non-uniform a-priori distributions (frozen bits depend on the data, BinaryPolarEncoderDecoder.py:258-262).
+ * d_rnd: randomlyGeneratedNumbers (:33-44), float64, row f at d_rnd + f * rnd_row_stride (0: one vector of N shared by all
+ * rows; genie batches use one row per frame).  Workspace: pc_sc_genie_workspace_bytes(plan, rows).
+ * pc_sc_decode_probs_prior -- decode (:71-99 with both trees, :277-317): d_pairs [rows][N][2] with rows = 2 B: row 2f holds
+ *   frame f's xyVectorDistribution.probs, row 2f+1 its xVectorDistribution.probs (the two trees run in adjacent lanes).
+ *   Outputs have `rows` rows too (d_cw_packed [rows][ceil(N/32)], d_info_packed [rows][ceil(k/32)]); rows 2f and 2f+1 are equal.
+ *   d_marg (optional) [rows][N][2]: the captured leaf probabilities of both trees.
+ * pc_sc_encode_prior -- encode (:46-69): d_x [B][N][2] the a-priori probabilities, d_u_packed [B][ceil(N/32)] the information
+ *   bits placed at their u positions (frozen positions ignored); frozen u_i = 0 iff P(u_i = 0 | past) >= r_i.  d_marg
+ *   (optional) [B][N][2] captures P(u_i | past) (genieSingleEncodeSimulatioan, :180-221). */
+int pc_sc_decode_probs_prior(const pc_plan *plan, const double *d_pairs, const double *d_rnd, int64_t rnd_row_stride, int64_t rows,
+                             uint32_t *d_cw_packed, uint32_t *d_info_packed, double *d_marg, void *d_workspace,
+                             size_t workspace_bytes, void *stream);
+int pc_sc_encode_prior(const pc_plan *plan, const double *d_x, const uint32_t *d_u_packed, const double *d_rnd,
+                       int64_t rnd_row_stride, int64_t B,
+                       uint32_t *d_cw_packed, double *d_marg, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* d_y [B][N] uint8 channel output symbols; h_table [Y][2] float64 = the channel's joint probabilities
  * (BinaryMemorylessDistribution.probs), 1 <= Y <= 16. */
 int pc_sc_decode_symbols(const pc_plan *plan, const uint8_t *d_y, int64_t B, const double *h_table, int Y,

@@ -71,16 +71,40 @@ class BinaryPolarEncoderDecoder:
     def _require_uniform(self, xVectorDistribution):
         xp = _probs_of(xVectorDistribution, self.length, 2)
         if not is_uniform_prior(xp):
-            raise PolarcubError("non-uniform a-priori distributions (data-dependent frozen bits) are not "
-                                "implemented in the CUDA path yet; there is no CPU fallback")
+            raise PolarcubError("non-uniform a-priori distributions are not supported on this path (trellis inputs); "
+                                "there is no CPU fallback")
+
+    def _prior(self, xVectorDistribution):
+        """None for a uniform prior (frozen bits do not depend on the data: the fast kernels apply), else its probs [N, 2]."""
+        if xVectorDistribution is None:
+            return None
+        xp = _probs_of(xVectorDistribution, self.length, 2)
+        return None if is_uniform_prior(xp) else xp
+
+    @property
+    def genie_plan(self):
+        """All indices frozen (geniePreSteps, BinaryPolarEncoderDecoder.py:101-107)."""
+        if getattr(self, "_gplan", None) is None:
+            self._gplan = engine.Plan(2, self.n, np.ones(self.length, dtype=np.uint8), np.zeros(self.length, dtype=np.uint8))
+        return self._gplan
+
+    def _rnd_dev(self):
+        return torch.from_numpy(np.ascontiguousarray(self.randomlyGeneratedNumbers, dtype=np.float64)).to(self.plan.device)
 
     # ---- batched entry points ---------------------------------------------------------------------
     def encode_batch(self, information, xVectorDistribution=None):
         """information [B, k] of 0/1 (numpy) -> codewords int64 [B, N]."""
-        if xVectorDistribution is not None:
-            self._require_uniform(xVectorDistribution)
         info = np.asarray(information)
         assert info.ndim == 2 and info.shape[1] == self.k
+        xp = self._prior(xVectorDistribution)
+        if xp is not None:  # data-dependent frozen bits: walk the a-priori tree (BinaryPolarEncoderDecoder.py:258-262)
+            dev = self.plan.device
+            u = np.zeros((info.shape[0], self.length), dtype=np.uint8)
+            u[:, self.frozenMask == 0] = info
+            up = torch.from_numpy(engine.pack_bits(u).view(np.int32)).to(dev).contiguous()
+            x = torch.from_numpy(xp).to(dev).expand(info.shape[0], self.length, 2).contiguous()
+            cw = engine.sc_encode_prior(self.plan, x, up, self._rnd_dev())
+            return engine.unpack_bits(cw.cpu().numpy(), self.length).astype(np.int64)
         packed = engine.pack_bits(info) if self.k else np.zeros((info.shape[0], 0), dtype=np.uint32)
         dev = torch.from_numpy(packed.view(np.int32)).to(self.plan.device)
         cw = engine.encode_bits(self.plan, dev.contiguous())
@@ -88,11 +112,14 @@ class BinaryPolarEncoderDecoder:
 
     def decode_batch(self, xyProbs, xVectorDistribution=None):
         """xyProbs float64 [B, N, 2] (numpy or device tensor) -> (codewords int64 [B, N], information int64 [B, k])."""
-        if xVectorDistribution is not None:
-            self._require_uniform(xVectorDistribution)
         xy = xyProbs if torch.is_tensor(xyProbs) else torch.from_numpy(np.ascontiguousarray(xyProbs, dtype=np.float64))
         assert xy.shape[1:] == (self.length, 2)
-        cw, info = engine.sc_decode_probs(self.plan, xy.to(self.plan.device).contiguous())
+        xp = self._prior(xVectorDistribution)
+        if xp is not None:  # a-posteriori and a-priori trees in lock step (BinaryPolarEncoderDecoder.py:277-317)
+            dev = self.plan.device
+            cw, info = engine.sc_decode_probs_prior(self.plan, xy.to(dev).contiguous(), torch.from_numpy(xp).to(dev), self._rnd_dev())
+        else:
+            cw, info = engine.sc_decode_probs(self.plan, xy.to(self.plan.device).contiguous())
         return (engine.unpack_bits(cw.cpu().numpy(), self.length).astype(np.int64),
                 engine.unpack_bits(info.cpu().numpy(), self.k).astype(np.int64))
 
@@ -133,10 +160,34 @@ class BinaryPolarEncoderDecoder:
                 u[t] = [0 if 0.5 >= rng.random() else 1 for _ in range(self.length)]
         return u
 
+    def _genie_rnd(self, seeds):
+        """randomlyGeneratedNumbers of each genie run [B, N] (BinaryPolarEncoderDecoder.py:33-44 with the run's seed)."""
+        r = np.empty((len(seeds), self.length), dtype=np.float64)
+        for t, seed in enumerate(seeds):
+            if seed == -1:
+                r[t] = 1.0
+            else:
+                rng = random.Random()
+                rng.seed(seed)
+                r[t] = [rng.random() for _ in range(self.length)]
+        return r
+
     def genie_encode_batch(self, xVectorDistribution, seeds):
         """genieSingleEncodeSimulatioan for a list of seeds -> (encodedVectors int64 [B, N], TV [B, N], H [B, N]).
         With the uniform prior every captured marginal is exactly [0.5, 0.5]: TV = 0, H = eta(0.5) + eta(0.5) = 1."""
-        self._require_uniform(xVectorDistribution)
+        xp = self._prior(xVectorDistribution)
+        if xp is not None:
+            from .simulation import eta
+            dev = self.plan.device
+            B = len(seeds)
+            rnd = torch.from_numpy(self._genie_rnd(seeds)).to(dev)
+            x = torch.from_numpy(xp).to(dev).expand(B, self.length, 2).contiguous()
+            up = torch.zeros((B, self.plan.Nw), dtype=torch.int32, device=dev)
+            cw, marg = engine.sc_encode_prior(self.genie_plan, x, up, rnd, want_marg=True)
+            marg = marg.cpu().numpy()
+            TV = np.abs(marg[..., 0] - marg[..., 1])
+            H = np.array([eta(a) + eta(b) for a, b in marg.reshape(-1, 2).tolist()]).reshape(marg.shape[:2])
+            return engine.unpack_bits(cw.cpu().numpy(), self.length).astype(np.int64), TV, H
         u = self._genie_u(seeds)
         packed = torch.from_numpy(engine.pack_bits(u).view(np.int32)).to(self.plan.device)
         cw = engine.polar_transform_bits(self.n, packed.contiguous())  # x = u B_N F^(x)n; the map is an involution
@@ -148,11 +199,23 @@ class BinaryPolarEncoderDecoder:
         """genieSingleDecodeSimulatioan for a batch: `xy` float64 [B, N, 2] or a trellis-collection descriptor, one genie
         seed per frame -> (decodedVectors int64 [B, N], Pe [B, N], H [B, N] or None)."""
         from .simulation import eta
-        self._require_uniform(xVectorDistribution)
-        u = self._genie_u(seeds)
         dev = self.plan.device
-        up = torch.from_numpy(engine.pack_bits(u).view(np.int32)).to(dev).contiguous()
-        if isinstance(xy, CollectionOfBinaryTrellises):
+        xp = self._prior(xVectorDistribution)
+        if xp is not None:
+            if isinstance(xy, CollectionOfBinaryTrellises):
+                self._require_uniform(xVectorDistribution)
+            x = xy if torch.is_tensor(xy) else torch.from_numpy(np.ascontiguousarray(xy, dtype=np.float64))
+            assert x.shape == (len(seeds), self.length, 2)
+            rnd = torch.from_numpy(self._genie_rnd(seeds)).to(dev)
+            cw, _, marg, _ = engine.sc_decode_probs_prior(self.genie_plan, x.to(dev).contiguous(), torch.from_numpy(xp).to(dev), rnd,
+                                                           want_marg=True)
+            u = None
+        else:
+            u = self._genie_u(seeds)
+            up = torch.from_numpy(engine.pack_bits(u).view(np.int32)).to(dev).contiguous()
+        if xp is not None:
+            pass
+        elif isinstance(xy, CollectionOfBinaryTrellises):
             assert xy.frames == len(seeds) and len(xy) == self.length
             if xy.n0 == 0:
                 raise PolarcubError("n0 = 0 is not supported by the CUDA trellis path")
@@ -166,6 +229,8 @@ class BinaryPolarEncoderDecoder:
             cw, marg = engine.sc_genie_probs(self.plan, x.to(dev).contiguous(), up)
         dec = engine.unpack_bits(cw.cpu().numpy(), self.length).astype(np.int64)
         marg = marg.cpu().numpy()
+        if u is None:  # the u vector behind the decoded codeword (polarTransformOfBits, :159)
+            u = engine.unpack_bits(engine.polar_transform_bits(self.n, cw.contiguous()).cpu().numpy(), self.length)
         if trustXYProbs:  # :153-157
             Pe = np.minimum(marg[..., 0], marg[..., 1])
             flat = marg.reshape(-1, 2)
@@ -198,20 +263,19 @@ class BinaryPolarEncoderDecoder:
         """BinaryPolarEncoderDecoder.py:46-69 -> encodedVector int64 [N]."""
         assert len(xVectorDistribution) == self.length
         assert len(information) == self.k
-        self._require_uniform(xVectorDistribution)
         info = np.asarray(information, dtype=np.int64).reshape(1, self.k)
-        return self.encode_batch(info)[0]
+        return self.encode_batch(info, xVectorDistribution)[0]
 
     def decode(self, xVectorDistribution, xyVectorDistribution):
         """BinaryPolarEncoderDecoder.py:71-99 -> (encodedVector int64 [N], information int64 [k])."""
         assert len(xVectorDistribution) == len(xyVectorDistribution) == self.length
-        self._require_uniform(xVectorDistribution)
         if isinstance(xyVectorDistribution, CollectionOfBinaryTrellises):  # main_deletion.py:52-59
+            self._require_uniform(xVectorDistribution)
             assert xyVectorDistribution.frames == 1
             cw, info = self.decode_trellis_batch(xyVectorDistribution)
             return cw[0], info[0]
         xy = _probs_of(xyVectorDistribution, self.length, 2).reshape(1, self.length, 2)
-        cw, info = self.decode_batch(xy)
+        cw, info = self.decode_batch(xy, xVectorDistribution)
         return cw[0], info[0]
 
 

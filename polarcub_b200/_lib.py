@@ -38,6 +38,10 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pc_sc_genie_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "pc_sc_genie_probs": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pc_sc_decode_probs_prior": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_size_t, c_void_p]),
+    "pc_sc_encode_prior": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                                   c_void_p]),
     "pc_trellis_genie": (c_int, [c_void_p, c_int, ctypes.c_double, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p,
                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "pc_trellis_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int64]),

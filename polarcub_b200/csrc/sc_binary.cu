@@ -49,8 +49,11 @@ struct ScParams {
     double *vals;       // [warps][N - 2^(LS+1)][32] scratch for levels > LS
     uint32_t *cw_t;     // [Nw][Bpad] natural-order codeword words (also the partial-sum store)
     uint32_t *info_t;   // [Kw][Bpad]
-    const uint32_t *u_t;  // genie: [Nw][Bpad] the known u bits (natural u order)
-    double *marg_t;       // genie: [N][Bpad] packed level-0 value of every leaf
+    const uint32_t *u_t;  // genie / prior-encode: [Nw][Bpad] the known u bits (natural u order)
+    double *marg_t;       // optional capture: [N][Bpad] packed level-0 value of every leaf
+    const uint8_t *fmask; // dual / prior modes: [N] 1 = frozen
+    const double *rnd;    // dual / prior modes: randomlyGeneratedNumbers, row (frame) pitch rnd_stride doubles (0: one shared vector)
+    int64_t rnd_stride;
     double table[32];   // symbols: [Y][2] joint probabilities
 };
 
@@ -113,7 +116,25 @@ __device__ __forceinline__ void level_batches(const double *sp, double *dp, int 
     }
 }
 
-template <int KIND, bool GENIE = false>
+// MODE 0: the decoder.  The other modes walk the UNPRUNED schedule (one NODE_GENIE entry per leaf):
+//   MODE_GENIE  every leaf bit is known (u_t); leaf probabilities are captured (marg_t)
+//   MODE_DUAL   non-uniform a-priori distribution: lanes 2j / 2j+1 hold the a-posteriori (xy) and a-priori (x) trees of ONE
+//               frame in lock step (BinaryPolarEncoderDecoder.py:277-317); an information leaf takes the xy lane's decision
+//               (:248-252), a frozen leaf the x lane's rule `0 iff P(u_i = 0 | past) >= r_i` (:258-262); the pair exchanges
+//               the bit with one shuffle, so both lanes carry the same partial sums
+//   MODE_PRIOR  encoding under a non-uniform prior: the lane holds the x tree; information leaves take the given bit (u_t),
+//               frozen leaves the rule
+enum : int { MODE_DECODE = 0, MODE_GENIE = 1, MODE_DUAL = 2, MODE_PRIOR = 3 };
+
+// P(u = 0 | past) of a packed level-0 value, as calcMarginalizedProbabilities computes it (NaN = (0,0) -> 0.5)
+__device__ __forceinline__ double leaf_m0(double v) {
+    if (v != v) return 0.5;
+    const double rr = d_abs(v);
+    const double p0 = d_sign(v) ? rr : 1.0, p1 = d_sign(v) ? 1.0 : rr;
+    return p0 / __dadd_rn(__dadd_rn(0.0, p0), p1);
+}
+
+template <int KIND, int MODE = MODE_DECODE>
 __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel(const ScParams p) {
     extern __shared__ double sm_vals[];  // [SMEM_VALS][SC_THREADS]
     __shared__ double s_table[32];
@@ -259,12 +280,32 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                     level_batches<SC_THREADS, SC_THREADS>(sv + (SC_THREADS << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
             }
             // ---- the node itself -----------------------------------------------------------------------
-            if (GENIE) {
+            if (MODE != MODE_DECODE) {
                 // genie pass (BinaryPolarEncoderDecoder.py:114-178): every index is frozen to a known bit; the leaf's
                 // probabilities P(u_i | u_0^{i-1}, y) are captured (:268-273) as the packed level-0 value
-                if ((i & 31) == 0) gword = p.u_t[(int64_t)(i >> 5) * p.Bpad + col];
-                p.marg_t[(int64_t)i * p.Bpad + col] = sv[SC_THREADS];
-                cwreg |= ((gword >> (i & 31)) & 1u) << (i & 31);
+                const double v0 = sv[SC_THREADS];
+                if (p.marg_t) p.marg_t[(int64_t)i * p.Bpad + col] = v0;
+                if (MODE != MODE_DUAL && (i & 31) == 0) gword = p.u_t[(int64_t)(i >> 5) * p.Bpad + col];
+                uint32_t bit = (gword >> (i & 31)) & 1u;
+                if (MODE == MODE_DUAL || MODE == MODE_PRIOR) {
+                    const bool frozen = p.fmask[i] != 0;
+                    const int64_t rrow = col < p.frames ? col : p.frames - 1;
+                    const uint32_t rule = leaf_m0(v0) >= p.rnd[rrow * p.rnd_stride + i] ? 0u : 1u;
+                    if (MODE == MODE_PRIOR) {
+                        if (frozen) bit = rule;
+                    } else {
+                        const uint32_t mine = (lane & 1) ? rule : d_sign(v0);
+                        bit = __shfl_sync(0xffffffffu, mine, frozen ? (lane | 1) : (lane & ~1));
+                        if (!frozen) {
+                            infoacc |= bit << (icount & 31);
+                            if ((++icount & 31) == 0) {
+                                iw[(int64_t)((icount >> 5) - 1) * p.Bpad] = infoacc;
+                                infoacc = 0;
+                            }
+                        }
+                    }
+                }
+                cwreg |= bit << (i & 31);
             } else if (e.kind == NODE_INFO) {
                 const uint32_t bit = d_sign(sv[SC_THREADS]);  // level 0: p0 >= p1 -> 0 (ties and (0,0) -> 0), :252
                 infoacc |= bit << (icount & 31);
@@ -302,7 +343,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                 ++lv;
             }
         }
-        if (!GENIE && (icount & 31)) iw[(int64_t)(icount >> 5) * p.Bpad] = infoacc;
+        if ((MODE == MODE_DECODE || MODE == MODE_DUAL) && (icount & 31)) iw[(int64_t)(icount >> 5) * p.Bpad] = infoacc;
     }
 }
 
@@ -682,15 +723,21 @@ size_t sc_genie_workspace_bytes(const pc_plan *plan, int64_t B) {
     return genie_layout(plan, sc_pick_chunk(B, PC_INPUT_PROBS)).total;
 }
 
-// d_u: known u bits, row f at d_u + f * u_pitch_words, first bit u_bit_off; d_marg: row f at d_marg + f * marg_pitch + marg_off
-int sc_genie_common(const pc_plan *plan, const double *d_xy, const uint32_t *d_u, int64_t u_pitch_words, int u_bit_off, int64_t B,
-                    uint32_t *d_cw, double *d_marg, int64_t marg_pitch, int64_t marg_off, void *ws, size_t ws_bytes,
-                    cudaStream_t st) {
+// Walk of the UNPRUNED tree over B rows of probability pairs (see the MODE_* comment above the kernel).
+// d_u: known u bits (genie, prior-encode), row f at d_u + f * u_pitch_words, first bit u_bit_off; d_marg (optional): row f
+// at d_marg + f * marg_pitch + marg_off; d_rnd: randomlyGeneratedNumbers (dual / prior modes), row pitch rnd_stride doubles.
+static int sc_walk_common(int mode, const pc_plan *plan, const double *d_in, const uint32_t *d_u, int64_t u_pitch_words,
+                          int u_bit_off, const double *d_rnd, int64_t rnd_stride, int64_t B, uint32_t *d_cw, uint32_t *d_info, double *d_marg,
+                          int64_t marg_pitch, int64_t marg_off, void *ws, size_t ws_bytes, cudaStream_t st) {
     PC_REQUIRE(plan && plan->q == 2, "binary plan required");
-    PC_REQUIRE(plan->n >= 1 && plan->n <= SC_MAX_N, "genie pass needs 2 <= N <= 65536");
+    PC_REQUIRE(plan->n >= 1 && plan->n <= SC_MAX_N, "this pass needs 2 <= N <= 65536");
     PC_REQUIRE(B >= 0, "negative batch");
     if (B == 0) return PC_OK;
-    PC_REQUIRE(d_xy && d_u && d_cw && d_marg && ws, "null buffer");
+    PC_REQUIRE(d_in && d_cw && ws, "null buffer");
+    PC_REQUIRE(mode == MODE_DUAL || d_u, "known u bits missing");
+    PC_REQUIRE(mode == MODE_GENIE || (d_rnd && (rnd_stride == 0 || rnd_stride >= plan->N)), "common randomness missing");
+    PC_REQUIRE(mode != MODE_DUAL || (B % 2 == 0 && (d_info || plan->k == 0)), "dual pass: rows come in (xy, x) pairs");
+    PC_REQUIRE(mode != MODE_GENIE || d_marg, "genie pass needs the marginal output");
     PC_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
     PC_REQUIRE(((uintptr_t)d_marg & 15) == 0 && (marg_pitch & 1) == 0 && (marg_off & 1) == 0, "marginal output must be 16-byte aligned");
     GenieTables *T = genie_tables(plan);
@@ -703,11 +750,11 @@ int sc_genie_common(const pc_plan *plan, const double *d_xy, const uint32_t *d_u
         return PC_ERR_NOMEM;
     }
     const ScLayout &L = G.L;
-    const int N = plan->N, Nw = (N + 31) / 32;
+    const int N = plan->N, Nw = (N + 31) / 32, Kw = (plan->k + 31) / 32;
     char *base = (char *)ws;
     ScParams p{};
     p.n = plan->n;
-    p.k = 0;
+    p.k = plan->k;
     p.n_sched = T->n_sched;
     p.Bpad = L.Bpad;
     p.sched = T->d_sched;
@@ -717,25 +764,37 @@ int sc_genie_common(const pc_plan *plan, const double *d_xy, const uint32_t *d_u
     p.cw_t = (uint32_t *)(base + L.off_cw);
     p.info_t = (uint32_t *)(base + L.off_info);
     p.u_t = (const uint32_t *)(base + G.off_u);
-    p.marg_t = (double *)(base + G.off_marg);
+    p.marg_t = d_marg ? (double *)(base + G.off_marg) : nullptr;
+    p.fmask = plan->d_frozen_mask;
+    p.rnd_stride = rnd_stride;
     const size_t smem = (size_t)SMEM_VALS * SC_THREADS * sizeof(double);
-    PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<PC_INPUT_PROBS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<PC_INPUT_PROBS, MODE_GENIE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<PC_INPUT_PROBS, MODE_DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<PC_INPUT_PROBS, MODE_PRIOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t f0 = 0; f0 < B; f0 += chunk) {
         const int64_t frames = (B - f0) < chunk ? (B - f0) : chunk;
         const int64_t tiles = (frames + 31) / 32;
         p.frames = frames;
+        p.rnd = d_rnd ? d_rnd + f0 * rnd_stride : nullptr;
         const int ptiles = (N + 31) / 32;
         dim3 ig((unsigned)tiles, (unsigned)(ptiles < 64 ? ptiles : 64));
-        ingest_kernel<double2><<<ig, 256, 0, st>>>(plan->n, frames, L.Bpad, (const double2 *)d_xy + f0 * N, (double2 *)p.in_t,
+        ingest_kernel<double2><<<ig, 256, 0, st>>>(plan->n, frames, L.Bpad, (const double2 *)d_in + f0 * N, (double2 *)p.in_t,
                                                    make_double2(0.5, 0.5));
         PC_LAUNCH_CHECK();
-        const int64_t uitems = L.Bpad * Nw;
-        genie_u_ingest_kernel<<<(unsigned)((uitems + 255) / 256), 256, 0, st>>>(N, frames, L.Bpad, d_u + f0 * u_pitch_words,
-                                                                                 u_pitch_words, u_bit_off, (uint32_t *)p.u_t);
-        PC_LAUNCH_CHECK();
+        if (d_u) {
+            const int64_t uitems = L.Bpad * Nw;
+            genie_u_ingest_kernel<<<(unsigned)((uitems + 255) / 256), 256, 0, st>>>(N, frames, L.Bpad, d_u + f0 * u_pitch_words,
+                                                                                     u_pitch_words, u_bit_off, (uint32_t *)p.u_t);
+            PC_LAUNCH_CHECK();
+        }
         const int64_t blocks = (tiles * 32 + SC_THREADS - 1) / SC_THREADS;
         const int grid = (int)(blocks < L.grid ? blocks : L.grid);
-        sc_decode_kernel<PC_INPUT_PROBS, true><<<grid, SC_THREADS, smem, st>>>(p);
+        if (mode == MODE_GENIE)
+            sc_decode_kernel<PC_INPUT_PROBS, MODE_GENIE><<<grid, SC_THREADS, smem, st>>>(p);
+        else if (mode == MODE_DUAL)
+            sc_decode_kernel<PC_INPUT_PROBS, MODE_DUAL><<<grid, SC_THREADS, smem, st>>>(p);
+        else
+            sc_decode_kernel<PC_INPUT_PROBS, MODE_PRIOR><<<grid, SC_THREADS, smem, st>>>(p);
         PC_LAUNCH_CHECK();
         if (plan->n >= 10) {
             const int Gq = 1 << (plan->n - 10);
@@ -745,11 +804,37 @@ int sc_genie_common(const pc_plan *plan, const double *d_xy, const uint32_t *d_u
             egress_kernel<true><<<dim3((unsigned)tiles, 1u), 256, 0, st>>>(plan->n, Nw, frames, L.Bpad, p.cw_t, d_cw + f0 * Nw);
         }
         PC_LAUNCH_CHECK();
-        genie_marg_egress_kernel<<<dim3((unsigned)tiles, (unsigned)(ptiles < 64 ? ptiles : 64)), 256, 0, st>>>(
-            N, frames, L.Bpad, p.marg_t, d_marg + f0 * marg_pitch, marg_pitch, marg_off);
-        PC_LAUNCH_CHECK();
+        if (mode == MODE_DUAL && Kw > 0) {
+            egress_kernel<false><<<dim3((unsigned)tiles, (unsigned)((Kw + 255) / 256)), 256, 0, st>>>(plan->n, Kw, frames, L.Bpad,
+                                                                                                      p.info_t, d_info + f0 * Kw);
+            PC_LAUNCH_CHECK();
+        }
+        if (d_marg) {
+            genie_marg_egress_kernel<<<dim3((unsigned)tiles, (unsigned)(ptiles < 64 ? ptiles : 64)), 256, 0, st>>>(
+                N, frames, L.Bpad, p.marg_t, d_marg + f0 * marg_pitch, marg_pitch, marg_off);
+            PC_LAUNCH_CHECK();
+        }
     }
     return PC_OK;
+}
+
+int sc_genie_common(const pc_plan *plan, const double *d_xy, const uint32_t *d_u, int64_t u_pitch_words, int u_bit_off, int64_t B,
+                    uint32_t *d_cw, double *d_marg, int64_t marg_pitch, int64_t marg_off, void *ws, size_t ws_bytes,
+                    cudaStream_t st) {
+    return sc_walk_common(MODE_GENIE, plan, d_xy, d_u, u_pitch_words, u_bit_off, nullptr, 0, B, d_cw, nullptr, d_marg, marg_pitch,
+                          marg_off, ws, ws_bytes, st);
+}
+
+int sc_dual_common(const pc_plan *plan, const double *d_pairs, const double *d_rnd, int64_t rnd_stride, int64_t rows, uint32_t *d_cw,
+                   uint32_t *d_info, double *d_marg, void *ws, size_t ws_bytes, cudaStream_t st) {
+    return sc_walk_common(MODE_DUAL, plan, d_pairs, nullptr, 0, 0, d_rnd, rnd_stride, rows, d_cw, d_info, d_marg, (int64_t)2 * plan->N, 0, ws,
+                          ws_bytes, st);
+}
+
+int sc_prior_common(const pc_plan *plan, const double *d_x, const uint32_t *d_u, const double *d_rnd, int64_t rnd_stride, int64_t B,
+                    uint32_t *d_cw, double *d_marg, void *ws, size_t ws_bytes, cudaStream_t st) {
+    return sc_walk_common(MODE_PRIOR, plan, d_x, d_u, (plan->N + 31) / 32, 0, d_rnd, rnd_stride, B, d_cw, nullptr, d_marg, (int64_t)2 * plan->N, 0,
+                          ws, ws_bytes, st);
 }
 
 }  // namespace pc
@@ -782,6 +867,28 @@ int pc_sc_genie_probs(const pc_plan *plan, const double *d_xy, const uint32_t *d
     const int Nw = (plan->N + 31) / 32;
     return pc::sc_genie_common(plan, d_xy, d_u_packed, Nw, 0, B, d_cw_packed, d_marg, (int64_t)2 * plan->N, 0, d_workspace,
                                workspace_bytes, (cudaStream_t)stream);
+}
+
+int pc_sc_decode_probs_prior(const pc_plan *plan, const double *d_pairs, const double *d_rnd, int64_t rnd_row_stride, int64_t rows,
+                             uint32_t *d_cw_packed, uint32_t *d_info_packed, double *d_marg, void *d_workspace,
+                             size_t workspace_bytes, void *stream) {
+    if (!plan) {
+        pc::set_error("plan is null");
+        return PC_ERR_INVALID;
+    }
+    return pc::sc_dual_common(plan, d_pairs, d_rnd, rnd_row_stride, rows, d_cw_packed, d_info_packed, d_marg, d_workspace, workspace_bytes,
+                              (cudaStream_t)stream);
+}
+
+int pc_sc_encode_prior(const pc_plan *plan, const double *d_x, const uint32_t *d_u_packed, const double *d_rnd,
+                       int64_t rnd_row_stride, int64_t B,
+                       uint32_t *d_cw_packed, double *d_marg, void *d_workspace, size_t workspace_bytes, void *stream) {
+    if (!plan) {
+        pc::set_error("plan is null");
+        return PC_ERR_INVALID;
+    }
+    return pc::sc_prior_common(plan, d_x, d_u_packed, d_rnd, rnd_row_stride, B, d_cw_packed, d_marg, d_workspace, workspace_bytes,
+                               (cudaStream_t)stream);
 }
 
 int pc_sc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint32_t *d_cw_packed, uint32_t *d_info_packed,

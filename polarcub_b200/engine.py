@@ -234,6 +234,52 @@ def sc_genie_probs(plan, xy, u_packed):
     return cw, marg
 
 
+def _rnd_arg(rnd, rows_per_frame, B, N):
+    """randomlyGeneratedNumbers as a device float64 tensor + row stride: [N] shared (stride 0) or one row per frame."""
+    assert rnd.is_cuda and rnd.dtype == torch.float64
+    if rnd.dim() == 1:
+        assert rnd.shape == (N,)
+        return rnd.contiguous(), 0
+    assert rnd.shape == (B, N)
+    r = rnd.repeat_interleave(rows_per_frame, dim=0) if rows_per_frame > 1 else rnd
+    return r.contiguous(), N
+
+
+def sc_decode_probs_prior(plan, xy, x, rnd, want_marg=False):
+    """SC decoding under a non-uniform a-priori distribution (two trees in lock step, pc_sc_decode_probs_prior).
+    xy float64 [B, N, 2]; x float64 [B, N, 2] or [N, 2]; rnd float64 [N] or [B, N] (all device).
+    Returns (cw_packed int32 [B, Nw], info_packed int32 [B, Kw]) (+ marg_xy, marg_x float64 [B, N, 2] with want_marg)."""
+    assert xy.is_cuda and xy.dtype == torch.float64 and xy.shape[1:] == (plan.N, 2)
+    B = xy.shape[0]
+    xx = x.expand(B, plan.N, 2) if x.dim() == 2 else x
+    assert xx.shape == xy.shape and xx.dtype == torch.float64
+    pairs = torch.stack([xy, xx], dim=1).reshape(2 * B, plan.N, 2).contiguous()
+    r, stride = _rnd_arg(rnd, 2, B, plan.N)
+    cw = torch.empty((2 * B, plan.Nw), dtype=torch.int32, device=xy.device)
+    info = torch.zeros((2 * B, max(plan.Kw, 1)), dtype=torch.int32, device=xy.device)
+    marg = torch.empty((2 * B, plan.N, 2), dtype=torch.float64, device=xy.device) if want_marg else None
+    ws = plan.workspace(_lib.lib().pc_sc_genie_workspace_bytes(plan._h, 2 * B))
+    _lib.check(_lib.lib().pc_sc_decode_probs_prior(plan._h, _ptr(pairs), _ptr(r), stride, 2 * B, _ptr(cw), _ptr(info), _ptr(marg),
+                                                   _ptr(ws), ws.numel(), _stream()), "pc_sc_decode_probs_prior")
+    out = (cw[0::2].contiguous(), info[0::2, :plan.Kw].contiguous())
+    return out + (marg[0::2], marg[1::2]) if want_marg else out
+
+
+def sc_encode_prior(plan, x, u_packed, rnd, want_marg=False):
+    """Encoding under a non-uniform a-priori distribution (pc_sc_encode_prior).  x float64 [B, N, 2]; u_packed int32
+    [B, Nw] the information bits at their u positions; rnd float64 [N] or [B, N].  Returns cw_packed (+ marg [B, N, 2])."""
+    assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.shape[1:] == (plan.N, 2)
+    B = x.shape[0]
+    assert u_packed.is_cuda and u_packed.dtype == torch.int32 and u_packed.is_contiguous() and u_packed.shape == (B, plan.Nw)
+    r, stride = _rnd_arg(rnd, 1, B, plan.N)
+    cw = torch.empty((B, plan.Nw), dtype=torch.int32, device=x.device)
+    marg = torch.empty((B, plan.N, 2), dtype=torch.float64, device=x.device) if want_marg else None
+    ws = plan.workspace(_lib.lib().pc_sc_genie_workspace_bytes(plan._h, B))
+    _lib.check(_lib.lib().pc_sc_encode_prior(plan._h, _ptr(x), _ptr(u_packed), _ptr(r), stride, B, _ptr(cw), _ptr(marg), _ptr(ws),
+                                             ws.numel(), _stream()), "pc_sc_encode_prior")
+    return (cw, marg) if want_marg else cw
+
+
 def trellis_genie(plan, n0, deletion_prob, ones, sub_bits, sub_len, u_packed):
     """Genie pass over trellis collections (see trellis_decode / sc_genie_probs)."""
     assert sub_bits.is_cuda and sub_bits.dtype == torch.uint8 and sub_bits.is_contiguous() and sub_bits.dim() == 3

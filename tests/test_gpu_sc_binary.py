@@ -26,25 +26,24 @@ def _bec_order(n, eps=0.5):
     return np.argsort(-np.array(z), kind="stable")
 
 
-def test_golden_binary_uniform_prior(golden_dir):
+def test_golden_binary(golden_dir):
     pcb = _setup()
     g = np.load(os.path.join(golden_dir, "sc_binary.npz"))
     checked = 0
     for nm in [str(s) for s in g["names"]]:
-        if "prior" in nm:
-            continue  # non-uniform priors: not in the CUDA path yet (raises loudly, see test below)
         n = int(g[nm + "/n"])
         N = 1 << n
         fs = set(np.nonzero(g[nm + "/frozen"])[0].tolist())
         ed = pcb.BinaryPolarEncoderDecoder(N, fs, int(g[nm + "/seed"]))
         np.testing.assert_array_equal(ed.randomlyGeneratedNumbers, g[nm + "/r"])
         info, cw, xy = g[nm + "/info"], g[nm + "/cw"], g[nm + "/xy"]
-        np.testing.assert_array_equal(ed.encode_batch(info), cw, err_msg=nm)
-        dcw, dinfo = ed.decode_batch(xy)
+        xp = g[nm + "/xprobs"]  # two cases carry a non-uniform a-priori distribution (data-dependent frozen bits)
+        np.testing.assert_array_equal(ed.encode_batch(info, xp), cw, err_msg=nm)
+        dcw, dinfo = ed.decode_batch(xy, xp)
         np.testing.assert_array_equal(dcw, g[nm + "/dec_cw"], err_msg=nm)
         np.testing.assert_array_equal(dinfo, g[nm + "/dec_info"], err_msg=nm)
         checked += 1
-    assert checked >= 75
+    assert checked >= 79
 
 
 def test_reference_style_single_frame_api(golden_dir):
@@ -66,11 +65,64 @@ def test_reference_style_single_frame_api(golden_dir):
     assert dcw.dtype == np.int64 and dinfo.dtype == np.int64
     np.testing.assert_array_equal(dcw, g[nm + "/dec_cw"][0])
     np.testing.assert_array_equal(dinfo, g[nm + "/dec_info"][0])
-    # non-uniform prior must fail loudly, never fall back to the CPU
+    # a non-uniform prior takes the lock-step a-priori tree (data-dependent frozen bits), still on the GPU
+    import oracle
     x.probs[:, 0] = 0.7
     x.probs[:, 1] = 0.3
-    with pytest.raises(Exception):
-        ed.decode(x, xy)
+    dcw, dinfo = ed.decode(x, xy)
+    ocw, oinfo = oracle.bin_decode(8, ed.frozenMask, ed.randomlyGeneratedNumbers, x.probs, xy.probs)
+    np.testing.assert_array_equal(dcw, ocw)
+    np.testing.assert_array_equal(dinfo, oinfo)
+
+
+@pytest.mark.parametrize("n,seed", [(4, 1), (7, 3), (8, -1), (10, 1), (11, 5)])
+def test_nonuniform_prior_vs_oracle(n, seed):
+    """Honda-Yamamoto style shaping: frozen bits follow `0 iff P(u_i = 0 | past) >= r_i` on the a-priori tree
+    (BinaryPolarEncoderDecoder.py:258-262); encode, decode and both genie captures against the oracle (pinned on the
+    reference's own non-uniform goldens in tests/test_oracle_golden.py)."""
+    import oracle
+    pcb = _setup()
+    N = 1 << n
+    rng = np.random.default_rng(4000 + n)
+    k = N // 2
+    fs = set(int(i) for i in _bec_order(n)[:N - k])
+    ed = pcb.BinaryPolarEncoderDecoder(N, fs, seed)
+    p1 = 0.3
+    xp = np.tile(np.array([1 - p1, p1]), (N, 1))
+    if n == 7:
+        xp = np.stack([1 - 0.5 * rng.random(N), 0.5 * rng.random(N)], axis=1)  # position-dependent prior
+    B = 48
+    info = rng.integers(0, 2, size=(B, k))
+    cw = ed.encode_batch(info, xp)
+    ocw = oracle.bin_encode_batch(N, ed.frozenMask, ed.randomlyGeneratedNumbers, xp, info)
+    np.testing.assert_array_equal(cw, ocw)
+    pch = 0.06
+    y = cw ^ (rng.random((B, N)) < pch)
+    # joint probabilities P(x, y) under the prior
+    xy = np.where((y[..., None] == np.arange(2)), 1 - pch, pch) * xp[None]
+    dcw, dinfo = ed.decode_batch(xy, xp)
+    for b in range(B):
+        o1, o2 = oracle.bin_decode(N, ed.frozenMask, ed.randomlyGeneratedNumbers, xp, xy[b])
+        np.testing.assert_array_equal(dcw[b], o1, err_msg="frame %d" % b)
+        np.testing.assert_array_equal(dinfo[b], o2, err_msg="frame %d" % b)
+    # genie runs with the prior: captured marginals of the a-priori (encode) and a-posteriori (decode) trees
+    seeds = [11, 12, 13]
+    enc, TV, H = ed.genie_encode_batch(xp, seeds)
+    ones = np.ones(N, dtype=np.uint8)
+    for t, sd in enumerate(seeds):
+        r = oracle.common_randomness(N, sd)
+        ecw, emarg = oracle.bin_encode(N, ones, r, xp, np.zeros(0, dtype=np.int64), want_marg=True)
+        np.testing.assert_array_equal(enc[t], ecw)
+        assert np.array_equal(TV[t], np.abs(emarg[:, 0] - emarg[:, 1]))
+    ych = enc ^ (rng.random(enc.shape) < pch)
+    xyg = np.where((ych[..., None] == np.arange(2)), 1 - pch, pch) * xp[None]
+    dec, Pe, Hd, marg = ed.genie_decode_batch(xp, xyg, seeds, True, return_marginals=True)
+    for t, sd in enumerate(seeds):
+        r = oracle.common_randomness(N, sd)
+        gcw, _, gm = oracle.bin_decode(N, ones, r, xp, xyg[t], want_marg=True)
+        np.testing.assert_array_equal(dec[t], gcw)
+        assert np.array_equal(marg[t], gm)
+        assert np.array_equal(Pe[t], np.minimum(gm[:, 0], gm[:, 1]))
 
 
 @pytest.mark.parametrize("n,kind", [(5, "bsc"), (6, "bec"), (9, "bsc"), (10, "bsc"), (10, "awgn"), (10, "bec_lossy"),
