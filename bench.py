@@ -434,7 +434,7 @@ class ScQary2048:
     name = "qsc_q3_n2048_k1024_qsc0.02"
     kernel = "qsc_decode_kernel<3>"
     dtype = "f64"
-    default_frames, default_e2e, default_cpu = 1 << 16, 1 << 14, 1 << 11
+    default_frames, default_e2e, default_cpu = 151552, 151552, 1 << 11
     N, K, n, q = 2048, 1024, 11, 3
     alg_bytes_frame = 25344
     info_bits = 1024 * math.log2(3)

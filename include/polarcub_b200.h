@@ -129,6 +129,7 @@ int pc_sc_decode_symbols(const pc_plan *plan, const uint8_t *d_y, int64_t B, con
 /* symbols are uint8 in [0, q).  d_info [B][k] -> d_cw [B][N] */
 int pc_qsc_encode(const pc_plan *plan, const uint8_t *d_info, uint8_t *d_cw, int64_t B, void *stream);
 size_t pc_qsc_workspace_bytes(const pc_plan *plan, int64_t B);
+int64_t pc_qsc_wave_frames(const pc_plan *plan); /* see pc_sc_wave_frames */
 /* d_xy [B][N][q] float64 (linear domain).  Outputs d_cw [B][N], d_info [B][k] uint8. */
 int pc_qsc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint8_t *d_cw, uint8_t *d_info,
                         void *d_workspace, size_t workspace_bytes, void *stream);

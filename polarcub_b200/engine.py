@@ -408,7 +408,7 @@ def qsc_decode_probs_host(plan, xy_host, info_host, cw_host=None, chunk=None):
     """pc_qsc_decode_probs over a batch in pinned host memory: xy_host float64 [B, N, q] -> info_host uint8 [B, k]."""
     _pinned(xy_host, "xy_host"), _pinned(info_host, "info_host")
     B = xy_host.shape[0]
-    chunk = chunk or default_host_chunk(B, plan.N * plan.q * 8)
+    chunk = chunk or default_host_chunk(B, plan.N * plan.q * 8, int(_lib.lib().pc_qsc_wave_frames(plan._h)))
     sl = _Slots(plan, "qsc")
 
     def body(lo, hi, slot):
