@@ -200,6 +200,9 @@ class ScBinary1024:
     def counters(self):
         return self.engine.count_errors(self.info_out, self.info_tx, self.K)
 
+    def gpu_info(self, sample):
+        return self.engine.unpack_bits(self.info_out[:sample].cpu().numpy(), self.K).astype(np.int64)
+
     # ---- CPU leg (oracle port) ----
     def cpu_inputs_from_gpu(self, sample):
         return self.y[:sample].cpu().numpy()
@@ -213,7 +216,7 @@ class ScBinary1024:
         cw = np.tile(cw, ((frames + cw.shape[0] - 1) // cw.shape[0], 1))[:frames]
         return (cw ^ (rng.random((frames, self.N)) < P_BSC)).astype(np.uint8)
 
-    def cpu_decode(self, ys, threads):
+    def cpu_decode(self, ys, threads, out=None):
         import oracle
         oracle.lib()
         xp = np.full((self.N, 2), 0.5)
@@ -222,7 +225,9 @@ class ScBinary1024:
             if len(idx) == 0:
                 return 0
             xy = self.tab[ys[idx]]  # makeBinaryMemorylessVectorDistribution, BinaryMemorylessDistribution.py:245-258
-            oracle.bin_decode_batch(self.N, self.fm, self.r, xp, xy)
+            _, info = oracle.bin_decode_batch(self.N, self.fm, self.r, xp, xy)
+            if out is not None:
+                out[idx] = info
             return len(idx)
 
         return run_threads(work, np.array_split(np.arange(ys.shape[0]), threads), threads)
@@ -293,6 +298,7 @@ class ScBinaryLarge:
     step = ScBinary1024.step
     e2e_step = ScBinary1024.e2e_step
     counters = ScBinary1024.counters
+    gpu_info = ScBinary1024.gpu_info
     cpu_inputs_from_gpu = ScBinary1024.cpu_inputs_from_gpu
     cpu_decode = ScBinary1024.cpu_decode
     cpu_what = ScBinary1024.cpu_what
@@ -398,6 +404,9 @@ class SclBinary4096:
     def cpu_inputs_from_gpu(self, sample):
         return (self.xy[:sample].cpu().numpy(), self.info_tx[:sample].cpu().numpy().astype(np.int64))
 
+    def gpu_info(self, sample):
+        return self.out["info"][:sample].cpu().numpy().astype(np.int64)
+
     def cpu_inputs_synth(self, frames):
         import oracle
         self.code()
@@ -412,7 +421,7 @@ class SclBinary4096:
         m = np.maximum(l0, l1)
         return (np.stack([np.exp(l0 - m), np.exp(l1 - m)], axis=-1), info)
 
-    def cpu_decode(self, inputs, threads):
+    def cpu_decode(self, inputs, threads, out=None):
         import oracle
         oracle.lib()
         xy, info = inputs
@@ -421,7 +430,9 @@ class SclBinary4096:
         def work(idx):
             if len(idx) == 0:
                 return 0
-            oracle.list_decode_batch(2, self.N, self.L, self.fm, xy[idx], fv[idx], info[idx])
+            dinfo, _ = oracle.list_decode_batch(2, self.N, self.L, self.fm, xy[idx], fv[idx], info[idx])
+            if out is not None:
+                out[idx] = dinfo
             return len(idx)
 
         return run_threads(work, np.array_split(np.arange(xy.shape[0]), threads), threads)
@@ -504,6 +515,9 @@ class ScQary2048:
     def cpu_inputs_from_gpu(self, sample):
         return self.xy[:sample].cpu().numpy()
 
+    def gpu_info(self, sample):
+        return self.out[1][:sample].cpu().numpy().astype(np.int64)
+
     def cpu_inputs_synth(self, frames):
         import oracle
         self.code()
@@ -519,7 +533,7 @@ class ScQary2048:
         np.fill_diagonal(tab, 1 - P_QSC)
         return tab[y]
 
-    def cpu_decode(self, xy, threads):
+    def cpu_decode(self, xy, threads, out=None):
         import oracle
         oracle.lib()
         xp = np.full((self.N, self.q), 1.0 / self.q)
@@ -527,7 +541,9 @@ class ScQary2048:
         def work(idx):
             if len(idx) == 0:
                 return 0
-            oracle.q_decode_batch(self.q, self.N, self.fm, xp, xy[idx])
+            _, dinfo = oracle.q_decode_batch(self.q, self.N, self.fm, xp, xy[idx])
+            if out is not None:
+                out[idx] = dinfo
             return len(idx)
 
         return run_threads(work, np.array_split(np.arange(xy.shape[0]), threads), threads)
@@ -688,7 +704,12 @@ def run_ours(args, rank, world, local_rank):
         oracle.build()
         inputs = w.cpu_inputs_from_gpu(sample)
         w.cpu_decode(head(inputs, max(cores, sample // 8)), cores)
-        done, dt = w.cpu_decode(inputs, cores)
+        cpu_info = np.full((sample, w.K), -1, dtype=np.int64)
+        done, dt = w.cpu_decode(inputs, cores, out=cpu_info)
+        # FER parity on identical channel outputs: the CPU port's decisions against the GPU's, frame by frame
+        same = (w.gpu_info(sample) == cpu_info).all(axis=1)
+        line["parity_check"] = {"frames_compared": int(sample), "identical": int(same.sum()), "unexplained": int((~same).sum()),
+                                "against": "oracle port on the same channel outputs (bit-exact bar, no tie tolerance needed)"}
         line["cpu_baseline"] = {"value": done * bits / dt / 1e9, "unit": "Gbit/s", "cores": cores, "kind": "port",
                                 "frames_per_s": done / dt,
                                 "sample": "first %d frames of the GPU batch, %s on %d threads (%.1f s wall)" % (
