@@ -4,6 +4,7 @@ All functions launch on torch's current CUDA stream and return device tensors; p
 int32 views of the uint32 words described in include/polarcub_b200.h (bit i -> word i//32, bit i%32).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -301,16 +302,19 @@ def trellis_genie(plan, n0, deletion_prob, ones, sub_bits, sub_len, u_packed):
 _PIPE_STREAMS = {}
 
 
+PIPE_SLOTS = int(os.environ.get("PC_PIPE_SLOTS", "3"))
+
+
 def _pipe_streams(device):
     key = torch.device(device).index
     if key not in _PIPE_STREAMS:
-        _PIPE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(2)]
+        _PIPE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(PIPE_SLOTS)]
     return _PIPE_STREAMS[key]
 
 
 def host_pipeline(plan, B, chunk, body):
-    """Runs body(lo, hi, slot) for consecutive chunks [lo, hi) of a batch of B frames, alternating between two CUDA
-    streams (slot 0 / 1): the H2D copies of one chunk overlap the decode kernel of the previous one and the D2H copies
+    """Runs body(lo, hi, slot) for consecutive chunks [lo, hi) of a batch of B frames, rotating over PIPE_SLOTS (3) CUDA
+    streams / staging slots: the H2D copies of one chunk overlap the decode kernel of the previous one and the D2H copies
     of the one before.  body must enqueue everything (copies from / to PINNED host tensors with non_blocking=True and the
     decode call) on the current stream and use per-slot device buffers.  Returns after enqueueing; the caller's
     stream waits for both."""
@@ -319,8 +323,8 @@ def host_pipeline(plan, B, chunk, body):
     for s in streams:
         s.wait_stream(cur)
     for j, lo in enumerate(range(0, B, chunk)):
-        with torch.cuda.stream(streams[j & 1]):
-            body(lo, min(B, lo + chunk), j & 1)
+        with torch.cuda.stream(streams[j % len(streams)]):
+            body(lo, min(B, lo + chunk), j % len(streams))
     for s in streams:
         cur.wait_stream(s)
 
