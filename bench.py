@@ -334,8 +334,8 @@ class SclBinary4096:
     N, K, n, L = 4096, 2048, 12, 8
     alg_bytes_frame = 16640  # 4 N bytes of soft input + K/8 bytes out
     info_bits = 2048
-    ncu = {"dram_bytes_per_frame": 4.85e6, "warp_inst_per_frame": 0.924e6, "issue_active_pct": 49.9,
-           "capture": "profiles/r1_c_scl_ncu_summary.md (prof_sclw_d)"}
+    ncu = {"dram_bytes_per_frame": 4.85e6, "warp_inst_per_frame": 0.900e6, "issue_active_pct": 48.6,
+           "capture": "profiles/r1_c_scl_ncu_summary.md (prof_sclw_e)"}
     allow_ga = False
 
     def code(self):
@@ -448,6 +448,8 @@ class ScQary2048:
     default_frames, default_e2e, default_cpu = 151552, 151552, 1 << 11
     N, K, n, q = 2048, 1024, 11, 3
     alg_bytes_frame = 25344
+    ncu = {"dram_bytes_per_frame": 0.903e6, "warp_inst_per_frame": 91.5e3, "issue_active_pct": 24.3,
+           "capture": "profiles/r1_f_qsc_ncu_summary.md (prof_qsc_b)"}
     info_bits = 1024 * math.log2(3)
     allow_ga = False
 
