@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- decoded info Gbit/s of the batched polar decoders on B200 (contract: see DESIGN.md "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload scl4096|sc1024|qsc2048|sc2p20] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload scl4096|sc1024|qsc2048|sc2p20|del256] [--impl ours|reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one pass of the decode hot path over one batch of synthetic channel outputs (frames are
@@ -553,7 +553,138 @@ class ScQary2048:
     cpu_what = "oracle/polar_oracle.c (C restatement of the reference's float64 q-ary SC recursion)"
 
 
-WORKLOADS = {"scl4096": SclBinary4096, "sc1024": ScBinary1024, "qsc2048": ScQary2048, "sc2p20": ScBinaryLarge}
+class DeletionTrellis256:
+    """C5: deletion-channel SC decoding over trellis collections with guard bands, N = 256, n0 = 2 (main_deletion.py
+    defaults: deletion probability 0.1, xi = 0.1, all-zero guard bands).  The frozen set comes from the GENIE pass
+    (genieEncodeDecodeSimulation, 2000 trials, error bound 0.1) run on this stack, whose output is identical to the
+    reference's (tests/test_gpu_genie.py)."""
+    name = "deletion_trellis_n256_n02_d0.1"
+    kernel = "trellis_step_kernel + sc_decode_kernel<probs> (batch-wide top-tree walk)"
+    dtype = "f64"
+    default_frames, default_e2e, default_cpu = 1 << 15, 1 << 15, 1 << 10
+    n, n0, N = 8, 2, 256
+    delta, xi, ones = 0.1, 0.1, 0
+    GENIE_TRIALS = 2000
+
+    def code(self):
+        import contextlib
+        import io
+        import random
+        import polarcub_b200 as pcb
+        from polarcub_b200 import Guardbands, BinaryTrellis
+        from polarcub_b200.CollectionOfBinaryTrellises import buildCollectionOfBinaryTrellises_uniformInput_deletion as build
+        n, n0, N = self.n, self.n0, self.N
+        chan = random.Random()
+        chan.seed(100)
+        with contextlib.redirect_stdout(io.StringIO()):
+            fs = pcb.genieEncodeDecodeSimulation(
+                N, lambda: np.full((N, 2), 0.5), lambda enc: Guardbands.addDeletionGuardBands([int(b) for b in enc], n, n0, self.xi, self.ones),
+                lambda cw: BinaryTrellis.deletionChannelSimulation(cw, self.delta, seed=None, randomNumberGenerator=chan),
+                lambda rw: build(rw, self.delta, self.xi, n, n0, self.ones), self.GENIE_TRIALS, 0.1, 300, trustXYProbs=False)
+        self.fs = fs
+        self.fm = mask_of(N, fs)
+        self.K = int(N - self.fm.sum())
+        self.info_bits = self.K
+        self.r = common_randomness(N, 200)
+        self.construction = "genie pass, %d trials, error bound 0.1, seeds 100/300 (main_deletion.py defaults; identical to the reference's genie)" % self.GENIE_TRIALS
+
+    def setup(self, dev, rank, B, Be):
+        import torch
+        import polarcub_b200 as pcb
+        from polarcub_b200 import engine, Guardbands
+        self.engine, self.torch = engine, torch
+        self.code()
+        N, K, n, n0 = self.N, self.K, self.n, self.n0
+        self.ed = pcb.BinaryPolarEncoderDecoder(N, self.fs, 200)
+        self.plan = self.ed.plan
+        rng = np.random.default_rng(5150 + rank)
+        info = rng.integers(0, 2, size=(B, K))
+        enc = self.ed.encode_batch(info)
+        starts, total = Guardbands.guard_band_layout(n, n0, self.xi, self.ones)
+        sub = (1 << n0)
+        tx = np.zeros((B, total), dtype=np.uint8)
+        for t, s0 in enumerate(starts):
+            tx[:, s0:s0 + sub] = enc[:, t * sub:(t + 1) * sub]
+        keep = rng.random((B, total)) >= self.delta
+        rxs = [tx[b][keep[b]] for b in range(B)]
+        bits, lens = Guardbands.split_batch(rxs, n, n0)
+        self.alg_bytes_frame = int(bits.shape[1] * bits.shape[2] + 4 * lens.shape[1] + (N + K) // 8)
+        self.info_np = info
+        self.bits_np, self.lens_np = bits, lens
+        self.bits = torch.from_numpy(bits).to(dev)
+        self.lens = torch.from_numpy(lens).to(dev)
+        self.info_tx = torch.from_numpy(engine.pack_bits(info).view(np.int32)).to(dev)
+        self.Be = Be
+        self.bits_host = torch.from_numpy(bits[:Be]).pin_memory()
+        self.lens_host = torch.from_numpy(lens[:Be]).pin_memory()
+        self.cw_host = torch.empty((Be, self.plan.Nw), dtype=torch.int32).pin_memory()
+        self.info_host = torch.empty((Be, self.plan.Kw), dtype=torch.int32).pin_memory()
+        self.h2d = int(Be * (bits.shape[1] * bits.shape[2] + 4 * lens.shape[1]))
+        self.d2h = int(Be * (self.plan.Nw + self.plan.Kw) * 4)
+        self.input_note = ("trimmed sub-words uint8 [B,%d,%d] + lengths (received words split at the guard bands on the host; "
+                           "%.3f GiB per step per GPU)" % (bits.shape[1], bits.shape[2], B * self.alg_bytes_frame / 2 ** 30))
+
+    def step(self):
+        self.cw_out, self.info_out = self.engine.trellis_decode(self.plan, self.n0, self.delta, self.ones, self.bits, self.lens)
+
+    def e2e_step(self):
+        eng, plan = self.engine, self.plan
+        sl = eng._Slots(plan, "del")
+        chunk = 8192
+
+        def body(lo, hi, slot):
+            m = hi - lo
+            b = sl.get(slot, "bits", (chunk,) + tuple(self.bits_host.shape[1:]), self.torch.uint8)[:m]
+            ln = sl.get(slot, "lens", (chunk, self.lens_host.shape[1]), self.torch.int32)[:m]
+            b.copy_(self.bits_host[lo:hi], non_blocking=True)
+            ln.copy_(self.lens_host[lo:hi], non_blocking=True)
+            cw, info = eng.trellis_decode(plan, self.n0, self.delta, self.ones, b, ln)
+            self.cw_host[lo:hi].copy_(cw, non_blocking=True)
+            self.info_host[lo:hi].copy_(info, non_blocking=True)
+
+        eng.host_pipeline(plan, self.Be, chunk, body)
+
+    def counters(self):
+        return self.engine.count_errors(self.info_out.contiguous(), self.info_tx, self.K)
+
+    def gpu_info(self, sample):
+        return self.engine.unpack_bits(self.info_out[:sample].cpu().numpy(), self.K).astype(np.int64)
+
+    def cpu_inputs_from_gpu(self, sample):
+        return (self.bits_np[:sample], self.lens_np[:sample])
+
+    def cpu_inputs_synth(self, frames):
+        from polarcub_b200 import Guardbands
+        self.code()
+        rng = np.random.default_rng(5150)
+        enc = rng.integers(0, 2, size=(frames, self.N)).astype(np.uint8)  # decoding work does not depend on the codeword
+        starts, total = Guardbands.guard_band_layout(self.n, self.n0, self.xi, self.ones)
+        sub = 1 << self.n0
+        tx = np.zeros((frames, total), dtype=np.uint8)
+        for t, s0 in enumerate(starts):
+            tx[:, s0:s0 + sub] = enc[:, t * sub:(t + 1) * sub]
+        keep = rng.random((frames, total)) >= self.delta
+        return Guardbands.split_batch([tx[b][keep[b]] for b in range(frames)], self.n, self.n0)
+
+    def cpu_decode(self, inputs, threads, out=None):
+        import oracle
+        oracle.lib()
+        bits, lens = inputs
+
+        def work(idx):
+            for f in idx:
+                _, info = oracle.trellis_decode(self.n, self.n0, self.fm, self.r, bits[f], lens[f], self.delta, self.ones)
+                if out is not None:
+                    out[f] = info
+            return len(idx)
+
+        return run_threads(work, np.array_split(np.arange(bits.shape[0]), threads), threads)
+
+    cpu_what = "oracle/polar_oracle_trellis.c (C restatement of BinaryTrellis / CollectionOfBinaryTrellises under decode)"
+
+
+WORKLOADS = {"scl4096": SclBinary4096, "sc1024": ScBinary1024, "qsc2048": ScQary2048, "sc2p20": ScBinaryLarge,
+             "del256": DeletionTrellis256}
 
 
 def nframes(x):

@@ -49,6 +49,18 @@ static inline size_t align256(size_t a) { return (a + 255) & ~(size_t)255; }
 
 int num_sms();  // SM count of the current device (cached)
 void prof_mark(cudaStream_t st);  // bench.py timing hook: call before and after the dominant kernel launch
+void prof_suspend(int delta);     // +1 / -1: a composite operation that brackets itself silences the marks of its parts
+struct ProfScope {                // brackets a multi-launch operation as ONE measured unit
+    cudaStream_t st;
+    explicit ProfScope(cudaStream_t s) : st(s) {
+        prof_mark(st);
+        prof_suspend(1);
+    }
+    ~ProfScope() {
+        prof_suspend(-1);
+        prof_mark(st);
+    }
+};
 
 // ---- schedule of the SC tree walk -------------------------------------------------------------------
 // The decoder never recurses: the host flattens the tree walk of

@@ -545,6 +545,7 @@ static int trellis_common(const pc_plan *plan, int n0, double deletion_prob, int
     PC_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "workspace must be 256-byte aligned");
     TrellisTables *T = trellis_tables(plan, n0);
     if (!T) return PC_ERR_CUDA;
+    ProfScope prof_scope((cudaStream_t)stream);  // the whole top-tree walk is the measured unit
     int64_t chunk = B < 4096 ? B : 4096;
     const size_t sc = trellis_sc_bytes(T, chunk);
     TrellisWs W = trellis_ws(plan, n0, maxlen, chunk);

@@ -39,8 +39,11 @@ static bool g_prof_on = false;
 static std::vector<cudaEvent_t> g_prof_ev;  // begin/end pairs
 static size_t g_prof_used = 0;
 
+static std::atomic<int> g_prof_suspend{0};
+void prof_suspend(int delta) { g_prof_suspend.fetch_add(delta); }
+
 void prof_mark(cudaStream_t st) {
-    if (!g_prof_on) return;
+    if (!g_prof_on || g_prof_suspend.load() > 0) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (g_prof_used == g_prof_ev.size()) {
         cudaEvent_t e;
