@@ -58,21 +58,29 @@ static TLayout t_layout(int LEN, int VC, int D) {
     return L;
 }
 
+// Records are stored field-major across the launch's records (structure of arrays): element `idx` of a field of record
+// `tid` lives at base + field_offset * nt + (idx * nt + tid) * sizeof(T), so the threads of a warp -- which walk trellises
+// of the same shape in near lock step -- touch consecutive addresses.
 struct TRef {
-    char *b;
+    char *base;
+    int64_t nt, tid;  // records in this launch, this thread's record
     TLayout L;
-    __device__ int &nv(int l) const { return ((int *)(b + L.off_nv))[l]; }
-    __device__ int &ne(int l) const { return ((int *)(b + L.off_ne))[l]; }
-    __device__ uint8_t &vpos(int l, int k) const { return ((uint8_t *)(b + L.off_vpos))[l * L.VC + k]; }
-    __device__ double &vprob(int l, int k) const { return ((double *)(b + L.off_vprob))[l * L.VC + k]; }
-    __device__ uint8_t &nout(int l, int k) const { return ((uint8_t *)(b + L.off_nout))[l * L.VC + k]; }
-    __device__ uint8_t &nin(int l, int k) const { return ((uint8_t *)(b + L.off_nin))[l * L.VC + k]; }
-    __device__ uint16_t &out(int l, int k, int a) const { return ((uint16_t *)(b + L.off_out))[(l * L.VC + k) * L.LC + a]; }
-    __device__ uint16_t &in(int l, int k, int a) const { return ((uint16_t *)(b + L.off_in))[(l * L.VC + k) * L.LC + a]; }
-    __device__ uint8_t &efrom(int l, int e) const { return ((uint8_t *)(b + L.off_efrom))[l * L.EC + e]; }
-    __device__ uint8_t &eto(int l, int e) const { return ((uint8_t *)(b + L.off_eto))[l * L.EC + e]; }
-    __device__ uint8_t &elab(int l, int e) const { return ((uint8_t *)(b + L.off_elab))[l * L.EC + e]; }
-    __device__ double &ep(int l, int e) const { return ((double *)(b + L.off_ep))[l * L.EC + e]; }
+    template <class T>
+    __device__ __forceinline__ T &at(int off, int idx) const {
+        return *(T *)(base + (int64_t)off * nt + ((int64_t)idx * nt + tid) * (int64_t)sizeof(T));
+    }
+    __device__ int &nv(int l) const { return at<int>(L.off_nv, l); }
+    __device__ int &ne(int l) const { return at<int>(L.off_ne, l); }
+    __device__ uint8_t &vpos(int l, int k) const { return at<uint8_t>(L.off_vpos, l * L.VC + k); }
+    __device__ double &vprob(int l, int k) const { return at<double>(L.off_vprob, l * L.VC + k); }
+    __device__ uint8_t &nout(int l, int k) const { return at<uint8_t>(L.off_nout, l * L.VC + k); }
+    __device__ uint8_t &nin(int l, int k) const { return at<uint8_t>(L.off_nin, l * L.VC + k); }
+    __device__ uint16_t &out(int l, int k, int a) const { return at<uint16_t>(L.off_out, (l * L.VC + k) * L.LC + a); }
+    __device__ uint16_t &in(int l, int k, int a) const { return at<uint16_t>(L.off_in, (l * L.VC + k) * L.LC + a); }
+    __device__ uint8_t &efrom(int l, int e) const { return at<uint8_t>(L.off_efrom, l * L.EC + e); }
+    __device__ uint8_t &eto(int l, int e) const { return at<uint8_t>(L.off_eto, l * L.EC + e); }
+    __device__ uint8_t &elab(int l, int e) const { return at<uint8_t>(L.off_elab, l * L.EC + e); }
+    __device__ double &ep(int l, int e) const { return at<double>(L.off_ep, l * L.EC + e); }
 };
 
 __device__ void t_clear(const TRef &t) {
@@ -244,7 +252,8 @@ __global__ void __launch_bounds__(128) trellis_step_kernel(const TrellisParams p
     if (gid >= p.frames * p.T) return;
     const int64_t f = gid / p.T;
     const int i = (int)(gid - f * p.T);
-    TRef in{p.blob_in + gid * p.Lin.bytes, p.Lin};
+    const int64_t nt = p.frames * p.T;
+    TRef in{p.blob_in, nt, gid, p.Lin};
     if (BUILD) {
         const int rlen = p.sub_len[gid];
         t_build(in, p.sub_bits + gid * p.maxlen, rlen < p.maxlen ? rlen : p.maxlen, p);
@@ -257,14 +266,14 @@ __global__ void __launch_bounds__(128) trellis_step_kernel(const TrellisParams p
         dec = (p.decision[f * p.dec_words + (bit0 >> 5)] >> (bit0 & 31)) & ((1u << p.sub) - 1u);
     }
     if (p.Lin.LEN > 2) {
-        TRef out{p.blob_out + gid * p.Lout.bytes, p.Lout};
+        TRef out{p.blob_out, nt, gid, p.Lout};
         t_transform(in, out, plus, dec);
         t_normalize(out);
         return;
     }
     // LEN == 2: the child has length 1 -> calcMarginalizedProbabilities(normalize=False) (BinaryTrellis.py:260-278), then
     // BinaryMemorylessVectorDistribution.normalize (:79-87).  The child is built in the output record, then reduced.
-    TRef out{p.blob_out + gid * p.Lout.bytes, p.Lout};
+    TRef out{p.blob_out, nt, gid, p.Lout};
     t_transform(in, out, plus, dec);
     double m0 = 0.0, m1 = 0.0;
     const int n = out.nv(0);
@@ -521,7 +530,7 @@ static size_t trellis_sc_bytes(pc::TrellisTables *T, int64_t chunk) {
 
 size_t pc_trellis_workspace_bytes(const pc_plan *plan, int n0, int maxlen, int64_t B) {
     if (!plan || plan->q != 2 || n0 < 1 || n0 > plan->n || B <= 0 || maxlen < 1) return 256;
-    int64_t chunk = B < 4096 ? B : 4096;
+    int64_t chunk = B < 8192 ? B : 8192;
     pc::TrellisWs W = pc::trellis_ws(plan, n0, maxlen, chunk);
     pc::TrellisTables *T = pc::trellis_tables(plan, n0);
     return W.total + pc::align256(trellis_sc_bytes(T, chunk) + 256);
@@ -546,7 +555,7 @@ static int trellis_common(const pc_plan *plan, int n0, double deletion_prob, int
     TrellisTables *T = trellis_tables(plan, n0);
     if (!T) return PC_ERR_CUDA;
     ProfScope prof_scope((cudaStream_t)stream);  // the whole top-tree walk is the measured unit
-    int64_t chunk = B < 4096 ? B : 4096;
+    int64_t chunk = B < 8192 ? B : 8192;
     const size_t sc = trellis_sc_bytes(T, chunk);
     TrellisWs W = trellis_ws(plan, n0, maxlen, chunk);
     if (W.total + align256(sc + 256) > workspace_bytes) {
