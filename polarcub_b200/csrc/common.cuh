@@ -81,6 +81,7 @@ void scl_tables_release(const pc_plan *p);
 void stream_tables_release(const pc_plan *p);
 void trellis_tables_release(const pc_plan *p);
 void genie_tables_release(const pc_plan *p);
+void hybrid_tables_release(const pc_plan *p);
 
 }  // namespace pc
 

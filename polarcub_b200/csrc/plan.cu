@@ -163,6 +163,7 @@ void pc_plan_destroy(pc_plan *p) {
     pc::stream_tables_release(p);
     pc::trellis_tables_release(p);
     pc::genie_tables_release(p);
+    pc::hybrid_tables_release(p);
     cudaFree(p->d_sched);
     cudaFree(p->d_r0_words);
     cudaFree(p->d_src);

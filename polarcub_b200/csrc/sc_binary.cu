@@ -37,7 +37,8 @@ constexpr int LS = 4;            // levels 0..LS in shared memory: 2^(LS+1)-1 do
 constexpr int SC_THREADS = 256;  // 8 warps = 256 frames per block
 constexpr int SMEM_VALS = (1 << (LS + 1)) - 1;
 constexpr int SC_BLOCKS_PER_SM = 3;
-constexpr int SC_MAX_N = 16;     // frame-per-lane kernel; larger blocks use the streamed decoder
+constexpr int SC_MAX_N = 16;     // frame-per-lane kernel; larger blocks use the hybrid / streamed decoders
+constexpr int SC_INPUT_PACKED = 2;  // internal input kind: the top level is a packed vector [2^n][Bpad] (hybrid decoder)
 
 struct ScParams {
     int n, k, n_sched, Y;
@@ -175,6 +176,8 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                 const uint32_t y = ((const uint8_t *)p.in_t)[(int64_t)h * p.Bpad + col];
                 v0 = s_table[2 * y];
                 v1 = s_table[2 * y + 1];
+            } else if (KIND == SC_INPUT_PACKED) {
+                v0 = v1 = 1.0;  // n == 0 only: not used by the hybrid decoder
             } else {
                 const double2 t = ((const double2 *)p.in_t)[(int64_t)h * p.Bpad + col];
                 v0 = t.x;
@@ -222,6 +225,27 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                 const uint32_t ureg = cwreg >> ((i - size) & 31);               // g: decision bits of levels below 32
                 double *dp = lvl_ptr(lev);
                 const int dstr = lvl_stride(lev);
+                if (KIND == SC_INPUT_PACKED && lev + 1 == n) {
+                    // the top level is a packed vector [2^n][Bpad] produced by the element-parallel upper stages (sc hybrid)
+                    const double *sp = (const double *)p.in_t + col, *sp2 = sp + (int64_t)size * p.Bpad;
+#pragma unroll 1
+                    for (int h0 = 0; h0 < size; h0 += 4) {
+                        uint32_t ub = 0;
+                        if (isg) ub = (size >= 32 ? uw[(int64_t)(h0 >> 5) * p.Bpad] : ureg) >> (h0 & 31);
+                        double a[4], b[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            a[u] = (h0 + u < size) ? sp[(int64_t)u * p.Bpad] : 1.0;
+                            b[u] = (h0 + u < size) ? sp2[(int64_t)u * p.Bpad] : 1.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (h0 + u < size) dp[(int64_t)(h0 + u) * dstr] = node_packed(a[u], b[u], isg, (ub >> u) & 1u);
+                        sp += 4 * p.Bpad;
+                        sp2 += 4 * p.Bpad;
+                    }
+                    continue;
+                }
                 if (lev + 1 == n) {
                     // from the channel pairs (continuous inputs, or block lengths below the lookup-table threshold)
 #pragma unroll 1
@@ -515,6 +539,11 @@ static int64_t sc_pick_chunk(int64_t B, int kind) {
 
 // Large blocks (and, on request, any block of at least 64 symbols) take the frame-per-CTA streamed decoder:
 // PC_SC_STREAM=1 forces it, PC_SC_STREAM=0 forbids it below the frame-per-lane limit.
+static bool sc_use_hybrid(const pc_plan *plan, int64_t B, int kind);
+static size_t sc_hybrid_workspace_bytes(const pc_plan *plan, int64_t B);
+static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, const double *h_table, int Y, uint32_t *d_cw,
+                            uint32_t *d_info, void *ws, size_t ws_bytes, cudaStream_t st);
+
 static bool sc_use_stream(const pc_plan *plan, int64_t B) {
     if (!sc_stream_supported(plan)) return false;
     if (plan->n > SC_MAX_N) return true;
@@ -531,6 +560,8 @@ static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int
     PC_REQUIRE(d_in && d_cw && (d_info || plan->k == 0) && ws, "null buffer");
     PC_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
     if (kind == PC_INPUT_SYMBOLS) PC_REQUIRE(h_table && Y >= 1 && Y <= 16, "symbol table must have 1..16 rows");
+    if (sc_use_hybrid(plan, B, kind))
+        return sc_hybrid_decode(plan, (const uint8_t *)d_in, B, h_table, Y, d_cw, d_info, ws, ws_bytes, st);
     if (sc_use_stream(plan, B)) return sc_stream_decode(plan, kind, d_in, B, h_table, Y, d_cw, d_info, ws, ws_bytes, st);
     PC_REQUIRE(plan->n <= SC_MAX_N, "block length too large for the frame-per-lane SC decoder");
     // largest chunk (multiple of 32 frames) that fits the workspace
@@ -604,6 +635,293 @@ static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int
             PC_LAUNCH_CHECK();
         }
     }
+    return PC_OK;
+}
+
+// ======================================================================================================================
+// Hybrid decoder for large blocks (N = 2^17 .. 2^24) over discrete channels: the SAME natural-order algorithm as
+// sc_decode_kernel, but the levels >= HY_L0 -- where a level has thousands of elements per frame -- run as batch-wide,
+// element-parallel kernels over [element][frame] vectors streamed through HBM (coalesced over the frames, every lane busy),
+// and the 2^(n - HY_L0) sub-blocks of 2^HY_L0 leaves are decoded by sc_decode_kernel<SC_INPUT_PACKED> (frame per lane),
+// which reads its top level straight from the level-HY_L0 vector.  The host walks the top of the tree exactly like the
+// kernel's schedule loop does (g at level ctz, f down, leaf block, partial sums) -- every frame of the batch executes the
+// same sequence.  Versus the frame-per-CTA streamed decoder (sc_stream.cu) the leaf walk is no longer one warp per frame
+// with 1-16 active lanes: throughput is set by how many frames fit in memory (~9.5 MB of float64 state per 2^20 frame).
+constexpr int HY_L0 = 10;
+
+struct HybridTables {
+    std::vector<pc_plan *> sub;       // one plan per sub-block of 2^HY_L0 leaves
+    std::vector<uint8_t> all_frozen;  // the sub-block is a rate-0 node
+    int32_t *d_info_pos = nullptr;    // [k] u index of information bit j
+};
+static std::mutex g_hy_mu;
+static std::map<const pc_plan *, HybridTables *> g_hy_tables;
+
+static HybridTables *hybrid_tables(const pc_plan *p) {
+    std::lock_guard<std::mutex> lk(g_hy_mu);
+    auto it = g_hy_tables.find(p);
+    if (it != g_hy_tables.end()) return it->second;
+    HybridTables *T = new HybridTables();
+    const int Ns = 1 << HY_L0, NS = p->N >> HY_L0;
+    for (int j = 0; j < NS; ++j) {
+        pc_plan *sp = nullptr;
+        if (pc_plan_create(2, HY_L0, p->frozen_mask.data() + (size_t)j * Ns, p->frozen_vals.data() + (size_t)j * Ns, &sp) != PC_OK) {
+            for (pc_plan *q : T->sub) pc_plan_destroy(q);
+            delete T;
+            return nullptr;
+        }
+        T->sub.push_back(sp);
+        T->all_frozen.push_back(sp->k == 0 ? 1 : 0);
+    }
+    std::vector<int32_t> pos;
+    for (int i = 0; i < p->N; ++i)
+        if (!p->frozen_mask[i]) pos.push_back(i);
+    if (pos.empty()) pos.push_back(0);
+    if (cudaMalloc((void **)&T->d_info_pos, pos.size() * 4) != cudaSuccess ||
+        cudaMemcpy(T->d_info_pos, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("hybrid tables: device upload failed");
+        return nullptr;
+    }
+    g_hy_tables[p] = T;
+    return T;
+}
+
+void hybrid_tables_release(const pc_plan *p) {
+    HybridTables *T = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_hy_mu);
+        auto it = g_hy_tables.find(p);
+        if (it == g_hy_tables.end()) return;
+        T = it->second;
+        g_hy_tables.erase(it);
+    }
+    for (pc_plan *q : T->sub) pc_plan_destroy(q);
+    cudaFree(T->d_info_pos);
+    delete T;
+}
+
+// level n-1 from the channel symbols: out[h][f] = f / g of the pairs of symbols h and h + N/2 (table in constant params)
+struct HyRootParams {
+    double table[32];
+};
+__global__ void __launch_bounds__(256) hy_root_kernel(int64_t half, int64_t Bpad, const uint8_t *__restrict__ sym,
+                                                      const uint32_t *__restrict__ xw, int isg, double *__restrict__ out,
+                                                      const HyRootParams tp) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= half * Bpad) return;
+    const int64_t h = gid / Bpad, f = gid - h * Bpad;
+    const uint32_t ya = sym[h * Bpad + f], yb = sym[(h + half) * Bpad + f];
+    const double a0 = tp.table[2 * ya], a1 = tp.table[2 * ya + 1], b0 = tp.table[2 * yb], b1 = tp.table[2 * yb + 1];
+    uint32_t u = 0;
+    if (isg) u = (xw[(h >> 5) * Bpad + f] >> (h & 31)) & 1u;
+    out[gid] = isg ? g_raw(a0, a1, b0, b1, u) : f_raw(a0, a1, b0, b1);
+}
+
+// out[h][f] = node(in[h][f], in[h + size][f]) for h < size; g: decision bit h of the words at xw (element h -> word h / 32)
+__global__ void __launch_bounds__(256) hy_level_kernel(int64_t size, int64_t Bpad, const double *__restrict__ in,
+                                                       const uint32_t *__restrict__ xw, int isg, double *__restrict__ out) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= size * Bpad) return;
+    const int64_t h = gid / Bpad, f = gid - h * Bpad;
+    uint32_t u = 0;
+    if (isg) u = (xw[(h >> 5) * Bpad + f] >> (h & 31)) & 1u;
+    out[gid] = node_packed(in[gid], in[gid + size * Bpad], isg != 0, u);
+}
+
+// partial sums of a completed plus child: lo[w][f] ^= lo[w + words][f]
+__global__ void __launch_bounds__(256) hy_xor_kernel(int64_t words, int64_t Bpad, uint32_t *__restrict__ lo) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= words * Bpad) return;
+    lo[gid] ^= lo[gid + words * Bpad];
+}
+
+// information bits: word w of frame f gathers the bits of u (packed, [frames][Nw]) at the information positions
+__global__ void __launch_bounds__(256) hy_info_kernel(int64_t frames, int k, int Nw, const int32_t *__restrict__ info_pos,
+                                                      const uint32_t *__restrict__ u, uint32_t *__restrict__ info) {
+    const int Kw = (k + 31) >> 5;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= frames * Kw) return;
+    const int64_t f = wid / Kw;
+    const int w = (int)(wid - f * Kw);
+    const int j = 32 * w + lane;
+    uint32_t b = 0;
+    if (j < k) {
+        const int pos = info_pos[j];
+        b = (u[f * Nw + (pos >> 5)] >> (pos & 31)) & 1u;
+    }
+    const uint32_t wv = __ballot_sync(0xffffffffu, b);
+    if (lane == 0) info[wid] = wv;
+}
+
+struct HyLayout {
+    int64_t chunk, Bpad;
+    size_t off_sym, off_cw, off_u, off_lev[32], off_sub, sub_bytes, total;
+};
+
+static int64_t hy_frames_cap() {
+    const char *s = getenv("PC_SC_HYBRID_FRAMES");
+    const int64_t v = s && *s ? atoll(s) : 8192;
+    return v >= 32 ? round_up(v, 32) : 32;
+}
+
+static HyLayout hy_layout(const pc_plan *plan, HybridTables *T, int64_t chunk) {
+    HyLayout L{};
+    const int64_t N = plan->N, Nw = N >> 5;
+    L.chunk = chunk;
+    L.Bpad = round_up(chunk, 32);
+    size_t o = 0;
+    L.off_sym = o;
+    o += align256((size_t)N * L.Bpad);
+    L.off_cw = o;
+    o += align256((size_t)Nw * L.Bpad * 4);
+    L.off_u = o;  // [chunk][Nw] reference-order codeword, then its transform, for the information gather
+    o += align256((size_t)2 * Nw * L.Bpad * 4);
+    for (int l = HY_L0; l < plan->n; ++l) {
+        L.off_lev[l] = o;
+        o += align256(((size_t)1 << l) * L.Bpad * 8);
+    }
+    L.off_sub = o;
+    size_t sb = 256;
+    if (T)
+        for (size_t j = 0; j < T->sub.size(); j += T->sub.size() > 64 ? T->sub.size() / 64 : 1) {  // all sub-plans share (n, kind): same layout
+            const size_t b = sc_layout(T->sub[j], chunk, PC_INPUT_SYMBOLS).total;
+            if (b > sb) sb = b;
+        }
+    L.sub_bytes = align256(sb);
+    o += L.sub_bytes;
+    L.total = o;
+    return L;
+}
+
+static bool sc_use_hybrid(const pc_plan *plan, int64_t B, int kind) {
+    if (plan->q != 2 || plan->n <= HY_L0 || plan->n > 20 || kind != PC_INPUT_SYMBOLS) return false;
+    const char *s = getenv("PC_SC_HYBRID");  // 1 forces it (any block above 2^10, for tests), 0 forbids it
+    if (s && *s) return atoi(s) != 0;
+    if (plan->n <= SC_MAX_N) return false;
+    return B >= 512;  // the frame-per-lane leaf blocks want thousands of frames; small batches keep the frame-per-CTA decoder
+}
+
+extern "C" int pc_polar_transform_bits(int n, const uint32_t *d_cw_packed, uint32_t *d_u_packed, int64_t B, void *stream);
+
+static size_t sc_hybrid_workspace_bytes(const pc_plan *plan, int64_t B) {
+    HybridTables *T = hybrid_tables(plan);
+    int64_t chunk = round_up(B, 32);
+    if (chunk > hy_frames_cap()) chunk = hy_frames_cap();
+    return hy_layout(plan, T, chunk).total;
+}
+
+static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, const double *h_table, int Y, uint32_t *d_cw,
+                            uint32_t *d_info, void *ws, size_t ws_bytes, cudaStream_t st) {
+    HybridTables *T = hybrid_tables(plan);
+    if (!T) return PC_ERR_CUDA;
+    int64_t chunk = round_up(B, 32);
+    if (chunk > hy_frames_cap()) chunk = hy_frames_cap();
+    while (chunk > 32 && hy_layout(plan, T, chunk).total > ws_bytes) chunk = round_up(chunk / 2, 32);
+    const HyLayout L = hy_layout(plan, T, chunk);
+    if (L.total > ws_bytes) {
+        set_error("workspace too small: %zu bytes given, %zu needed for a 32-frame chunk", ws_bytes, L.total);
+        return PC_ERR_NOMEM;
+    }
+    const int n = plan->n, N = plan->N, Nw = N >> 5, Kw = (plan->k + 31) / 32, Ns = 1 << HY_L0, NS = N >> HY_L0;
+    char *base = (char *)ws;
+    uint8_t *sym = (uint8_t *)(base + L.off_sym);
+    uint32_t *cw_t = (uint32_t *)(base + L.off_cw);
+    uint32_t *cw_ref = (uint32_t *)(base + L.off_u), *u_ref = cw_ref + (size_t)Nw * L.Bpad;
+    auto V = [&](int l) -> double * { return (double *)(base + L.off_lev[l]); };
+    HyRootParams tp{};
+    for (int i = 0; i < 32; ++i) tp.table[i] = i < 2 * Y ? h_table[i] : 0.0;
+    const size_t smem = (size_t)SMEM_VALS * SC_THREADS * sizeof(double);
+    PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<SC_INPUT_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof_scope(st);  // the whole walk is the measured unit
+    const int64_t Bp = L.Bpad;
+    auto blocks_of = [](int64_t items) { return (unsigned)((items + 255) / 256); };
+    for (int64_t f0 = 0; f0 < B; f0 += chunk) {
+        const int64_t frames = (B - f0) < chunk ? (B - f0) : chunk;
+        const int64_t tiles = (frames + 31) / 32;
+        if ((((uintptr_t)d_y + (size_t)f0 * N) & 3) == 0) {
+            dim3 ig8((unsigned)((frames + 127) / 128), (unsigned)((N >> 7) < 64 ? (N >> 7) : 64));
+            ingest_u8_kernel<<<ig8, 256, 0, st>>>(n, frames, Bp, d_y + f0 * N, sym);
+        } else {
+            dim3 ig((unsigned)tiles, 64u);
+            ingest_kernel<uint8_t><<<ig, 256, 0, st>>>(n, frames, Bp, d_y + f0 * N, sym, (uint8_t)0);
+        }
+        PC_LAUNCH_CHECK();
+        // level `lev` (>= HY_L0) of the current path: f, or g with the decision words of x[i - 2^lev, i)
+        auto level_op = [&](int lev, bool isg, int64_t i) -> int {
+            const int64_t size = (int64_t)1 << lev;
+            const uint32_t *xw = isg ? cw_t + ((i - size) >> 5) * Bp : cw_t;
+            if (lev == n - 1)
+                hy_root_kernel<<<blocks_of(size * Bp), 256, 0, st>>>(size, Bp, sym, xw, isg ? 1 : 0, V(lev), tp);
+            else
+                hy_level_kernel<<<blocks_of(size * Bp), 256, 0, st>>>(size, Bp, V(lev + 1), xw, isg ? 1 : 0, V(lev));
+            PC_LAUNCH_CHECK();
+            return PC_OK;
+        };
+        for (int j = 0; j < NS; ++j) {
+            const int64_t i = (int64_t)j * Ns;
+            const int stop = T->all_frozen[j] ? HY_L0 + 1 : HY_L0;  // a rate-0 sub-block never needs its own level
+            int lev;
+            if (j == 0) {
+                lev = n - 1;
+            } else {
+                const int top = HY_L0 + __builtin_ctz((unsigned)j);
+                if (top >= stop) {
+                    const int rc = level_op(top, true, i);
+                    if (rc) return rc;
+                }
+                lev = top - 1;
+            }
+            for (; lev >= stop; --lev) {
+                const int rc = level_op(lev, false, i);
+                if (rc) return rc;
+            }
+            // the sub-block: frame per lane, top level read from V(HY_L0), partial sums written into the frame's words
+            const pc_plan *sp = T->sub[j];
+            const ScLayout SL = sc_layout(sp, chunk, PC_INPUT_SYMBOLS);
+            ScParams p{};
+            p.n = HY_L0;
+            p.k = sp->k;
+            p.n_sched = (int)sp->sched.size();
+            p.Y = Y;
+            p.frames = frames;
+            p.Bpad = Bp;
+            p.sched = sp->d_sched;
+            p.r0_words = sp->d_r0_words;
+            p.in_t = V(HY_L0);
+            p.vals = (double *)(base + L.off_sub + SL.off_vals);
+            p.cw_t = cw_t + (i >> 5) * Bp;
+            p.info_t = (uint32_t *)(base + L.off_sub + SL.off_info);
+            const int64_t blocks = (tiles * 32 + SC_THREADS - 1) / SC_THREADS;
+            const int grid = (int)(blocks < SL.grid ? blocks : SL.grid);
+            sc_decode_kernel<SC_INPUT_PACKED><<<grid, SC_THREADS, smem, st>>>(p);
+            PC_LAUNCH_CHECK();
+            // partial sums above the sub-block: x[ii - s, ii) ^= x[ii, ii + s) whenever a plus child completes
+            int lv = HY_L0;
+            int64_t ii = i;
+            while (lv < n && ((ii >> lv) & 1)) {
+                const int64_t s = (int64_t)1 << lv;
+                hy_xor_kernel<<<blocks_of((s >> 5) * Bp), 256, 0, st>>>(s >> 5, Bp, cw_t + ((ii - s) >> 5) * Bp);
+                PC_LAUNCH_CHECK();
+                ii -= s;
+                ++lv;
+            }
+        }
+        // outputs: codeword to the reference order; information = gather of its transform at the information positions
+        {
+            const int G = 1 << (n - 10);
+            egress_bitrev_kernel<<<dim3((unsigned)tiles, (unsigned)((G + 7) / 8 < 64 ? (G + 7) / 8 : 64)), 256, 0, st>>>(
+                n, frames, Bp, cw_t, d_cw + f0 * Nw);
+            PC_LAUNCH_CHECK();
+            if (Kw > 0) {
+                const int rc = pc_polar_transform_bits(n, d_cw + f0 * Nw, u_ref, frames, st);
+                if (rc) return rc;
+                hy_info_kernel<<<blocks_of(frames * Kw * 32), 256, 0, st>>>(frames, plan->k, Nw, T->d_info_pos, u_ref, d_info + f0 * Kw);
+                PC_LAUNCH_CHECK();
+            }
+        }
+    }
+    (void)cw_ref;
     return PC_OK;
 }
 
@@ -849,6 +1167,7 @@ int64_t pc_sc_wave_frames(const pc_plan *plan) {
 
 size_t pc_sc_workspace_bytes(const pc_plan *plan, int64_t B, int input_kind) {
     if (!plan || B <= 0) return 256;
+    if (pc::sc_use_hybrid(plan, B, input_kind)) return pc::sc_hybrid_workspace_bytes(plan, B);
     if (pc::sc_use_stream(plan, B)) return pc::sc_stream_workspace_bytes(plan, B);
     return pc::sc_layout(plan, pc::sc_pick_chunk(B, input_kind), input_kind).total;
 }

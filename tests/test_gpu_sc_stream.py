@@ -123,3 +123,64 @@ def test_large_block_bec(n, frames):
         ocw, oinfo = oracle.bin_decode(N, ed.frozenMask, ed.randomlyGeneratedNumbers, xp, tab[y[f]])
         np.testing.assert_array_equal(dcw[f], ocw)
         np.testing.assert_array_equal(dinfo[f], oinfo)
+
+
+@pytest.mark.parametrize("n,how,kind,seed,B", [(11, "bec", "bsc", 1, 70), (12, "blocks", "bec_lossy", 5, 45), (13, "random", "bsc", -1, 33),
+                                               (15, "blocks", "bec", 2, 40), (17, "bec", "bsc", 1, 6)])
+def test_hybrid_decoder_vs_oracle(n, how, kind, seed, B, monkeypatch):
+    """The hybrid large-block decoder (element-parallel upper stages through HBM + frame-per-lane 1024-leaf sub-blocks),
+    forced for block lengths the other decoders cover too: bit-exact against the oracle and against the other decoders."""
+    monkeypatch.setenv("PC_SC_HYBRID", "1")
+    import polarcub_b200 as pcb
+    N = 1 << n
+    rng = np.random.default_rng(9000 + 31 * n)
+    fs = _frozen(n, N // 2, how, rng)
+    ed = pcb.BinaryPolarEncoderDecoder(N, fs, seed)
+    info = rng.integers(0, 2, size=(B, ed.k))
+    cw = ed.encode_batch(info)
+    tab, y = _channel(kind, cw, rng)
+    dcw, dinfo = ed.decode_symbols_batch(y, tab)
+    xp = np.full((N, 2), 0.5)
+    nchk = B if n <= 13 else 4
+    ocw, oinfo = oracle.bin_decode_batch(N, ed.frozenMask, ed.randomlyGeneratedNumbers, xp, tab[y[:nchk]])
+    np.testing.assert_array_equal(dcw[:nchk], ocw)
+    np.testing.assert_array_equal(dinfo[:nchk], oinfo)
+    monkeypatch.setenv("PC_SC_HYBRID", "0")
+    dcw2, dinfo2 = ed.decode_symbols_batch(y, tab)
+    np.testing.assert_array_equal(dcw2, dcw)
+    np.testing.assert_array_equal(dinfo2, dinfo)
+
+
+def test_hybrid_large_block_bec_batch():
+    """N = 2^20, BEC(0.1), R = 0.8 (BASELINE config 4) through the hybrid decoder (default for batches >= 512 frames):
+    size-independent properties on the whole batch, the oracle on two frames, and agreement with the streamed decoder."""
+    import os
+    import polarcub_b200 as pcb
+    n, frames = 20, 512
+    N = 1 << n
+    K = int(0.8 * N)
+    order = np.argsort(_z(n, 0.1), kind="stable")
+    fs = set(int(i) for i in order[K:])
+    ed = pcb.BinaryPolarEncoderDecoder(N, fs, 1)
+    rng = np.random.default_rng(4242)
+    info = rng.integers(0, 2, size=(frames, K), dtype=np.int8)
+    cw = ed.encode_batch(info)
+    p = 0.1
+    tab = np.array([[0.5 * (1 - p), 0.0], [0.0, 0.5 * (1 - p)], [0.5 * p, 0.5 * p]])
+    y = np.where(rng.random((frames, N)) < p, 2, cw).astype(np.uint8)
+    dcw, dinfo = ed.decode_symbols_batch(y, tab)
+    np.testing.assert_array_equal(ed.encode_batch(dinfo), dcw)
+    known = y != 2
+    assert np.array_equal(dcw[known], cw[known])
+    xp = np.full((N, 2), 0.5)
+    for f in (0, frames - 1):
+        ocw, oinfo = oracle.bin_decode(N, ed.frozenMask, ed.randomlyGeneratedNumbers, xp, tab[y[f]])
+        np.testing.assert_array_equal(dcw[f], ocw)
+        np.testing.assert_array_equal(dinfo[f], oinfo)
+    os.environ["PC_SC_HYBRID"] = "0"
+    try:
+        scw, sinfo = ed.decode_symbols_batch(y[:8], tab)
+    finally:
+        del os.environ["PC_SC_HYBRID"]
+    np.testing.assert_array_equal(scw, dcw[:8])
+    np.testing.assert_array_equal(sinfo, dinfo[:8])
