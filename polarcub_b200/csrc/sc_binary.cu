@@ -717,6 +717,41 @@ __global__ void __launch_bounds__(256) hy_root_kernel(int64_t half, int64_t Bpad
     out[gid] = isg ? g_raw(a0, a1, b0, b1, u) : f_raw(a0, a1, b0, b1);
 }
 
+// Level n-1 is never stored: an element of it is a function of two channel symbols and (in the second half of the frame) one
+// decision bit, looked up in lut[mode][y_a][y_b] (mode 0: f, 1 + u: g) -- built on the device with f_raw / g_raw, so the
+// bits are those of hy_root_kernel.  Level n-2 is then computed straight from four symbols per element.
+__global__ void hy_lut_kernel(int Y, const HyRootParams tp, double *__restrict__ lut) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 3 * Y * Y) return;
+    const int m = idx / (Y * Y), ya = (idx / Y) % Y, yb = idx % Y;
+    const double a0 = tp.table[2 * ya], a1 = tp.table[2 * ya + 1], b0 = tp.table[2 * yb], b1 = tp.table[2 * yb + 1];
+    lut[idx] = m == 0 ? f_raw(a0, a1, b0, b1) : g_raw(a0, a1, b0, b1, (uint32_t)(m - 1));
+}
+
+// out[h][f], h < quarter = N/4: node(L[h], L[h + quarter]) with L[e] = lut[mode(e)][sym[e]][sym[e + N/2]];
+// top_g: level n-1 is in its g phase, its decision bits are x[0, N/2) = the words at x0; xw: this level's decision words
+__global__ void __launch_bounds__(256) hy_level_sym_kernel(int64_t quarter, int64_t Bpad, const uint8_t *__restrict__ sym, int Y,
+                                                           const double *__restrict__ lut, const uint32_t *__restrict__ x0,
+                                                           int top_g, const uint32_t *__restrict__ xw, int isg,
+                                                           double *__restrict__ out) {
+    __shared__ double s_lut[768];
+    for (int i = threadIdx.x; i < 3 * Y * Y; i += blockDim.x) s_lut[i] = lut[i];
+    __syncthreads();
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= quarter * Bpad) return;
+    const int64_t h = gid / Bpad, f = gid - h * Bpad, hb = h + quarter, half = 2 * quarter;
+    const uint32_t y0 = sym[h * Bpad + f], y1 = sym[(h + half) * Bpad + f];
+    const uint32_t y2 = sym[hb * Bpad + f], y3 = sym[(hb + half) * Bpad + f];
+    uint32_t ma = 0, mb = 0;
+    if (top_g) {
+        ma = 1u + ((x0[(h >> 5) * Bpad + f] >> (h & 31)) & 1u);
+        mb = 1u + ((x0[(hb >> 5) * Bpad + f] >> (hb & 31)) & 1u);
+    }
+    uint32_t u = 0;
+    if (isg) u = (xw[(h >> 5) * Bpad + f] >> (h & 31)) & 1u;
+    out[gid] = node_packed(s_lut[(ma * Y + y0) * Y + y1], s_lut[(mb * Y + y2) * Y + y3], isg != 0, u);
+}
+
 // out[h][f] = node(in[h][f], in[h + size][f]) for h < size; g: decision bit h of the words at xw (element h -> word h / 32)
 __global__ void __launch_bounds__(256) hy_level_kernel(int64_t size, int64_t Bpad, const double *__restrict__ in,
                                                        const uint32_t *__restrict__ xw, int isg, double *__restrict__ out) {
@@ -756,12 +791,12 @@ __global__ void __launch_bounds__(256) hy_info_kernel(int64_t frames, int k, int
 
 struct HyLayout {
     int64_t chunk, Bpad;
-    size_t off_sym, off_cw, off_u, off_lev[32], off_sub, sub_bytes, total;
+    size_t off_sym, off_cw, off_u, off_lut, off_lev[32], off_sub, sub_bytes, total;
 };
 
 static int64_t hy_frames_cap() {
     const char *s = getenv("PC_SC_HYBRID_FRAMES");
-    const int64_t v = s && *s ? atoll(s) : 8192;
+    const int64_t v = s && *s ? atoll(s) : 16384;  // ~5.4 MB of workspace per 2^20-symbol frame
     return v >= 32 ? round_up(v, 32) : 32;
 }
 
@@ -777,7 +812,9 @@ static HyLayout hy_layout(const pc_plan *plan, HybridTables *T, int64_t chunk) {
     o += align256((size_t)Nw * L.Bpad * 4);
     L.off_u = o;  // [chunk][Nw] reference-order codeword, then its transform, for the information gather
     o += align256((size_t)2 * Nw * L.Bpad * 4);
-    for (int l = HY_L0; l < plan->n; ++l) {
+    L.off_lut = o;
+    o += align256(768 * 8);
+    for (int l = HY_L0; l < plan->n - 1; ++l) {  // level n-1 is looked up from the symbols, never stored
         L.off_lev[l] = o;
         o += align256(((size_t)1 << l) * L.Bpad * 8);
     }
@@ -795,11 +832,12 @@ static HyLayout hy_layout(const pc_plan *plan, HybridTables *T, int64_t chunk) {
 }
 
 static bool sc_use_hybrid(const pc_plan *plan, int64_t B, int kind) {
-    if (plan->q != 2 || plan->n <= HY_L0 || plan->n > 20 || kind != PC_INPUT_SYMBOLS) return false;
+    if (plan->q != 2 || plan->n < HY_L0 + 2 || plan->n > 20 || kind != PC_INPUT_SYMBOLS) return false;
     const char *s = getenv("PC_SC_HYBRID");  // 1 forces it (any block above 2^10, for tests), 0 forbids it
     if (s && *s) return atoi(s) != 0;
     if (plan->n <= SC_MAX_N) return false;
-    return B >= 512;  // the frame-per-lane leaf blocks want thousands of frames; small batches keep the frame-per-CTA decoder
+    return B >= 6144;  // a batch takes ~N x 3.4 us whatever its size (the leaf blocks are frame per lane): below ~6 k
+                       // frames the frame-per-CTA streamed decoder is faster
 }
 
 extern "C" int pc_polar_transform_bits(int n, const uint32_t *d_cw_packed, uint32_t *d_u_packed, int64_t B, void *stream);
@@ -834,6 +872,9 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
     const size_t smem = (size_t)SMEM_VALS * SC_THREADS * sizeof(double);
     PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<SC_INPUT_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope prof_scope(st);  // the whole walk is the measured unit
+    double *lut = (double *)(base + L.off_lut);
+    hy_lut_kernel<<<3, 256, 0, st>>>(Y, tp, lut);
+    PC_LAUNCH_CHECK();
     const int64_t Bp = L.Bpad;
     auto blocks_of = [](int64_t items) { return (unsigned)((items + 255) / 256); };
     for (int64_t f0 = 0; f0 < B; f0 += chunk) {
@@ -851,8 +892,10 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
         auto level_op = [&](int lev, bool isg, int64_t i) -> int {
             const int64_t size = (int64_t)1 << lev;
             const uint32_t *xw = isg ? cw_t + ((i - size) >> 5) * Bp : cw_t;
-            if (lev == n - 1)
-                hy_root_kernel<<<blocks_of(size * Bp), 256, 0, st>>>(size, Bp, sym, xw, isg ? 1 : 0, V(lev), tp);
+            if (lev == n - 1) return PC_OK;  // looked up on demand by the level below
+            if (lev == n - 2)
+                hy_level_sym_kernel<<<blocks_of(size * Bp), 256, 0, st>>>(size, Bp, sym, Y, lut, cw_t, i >= N / 2 ? 1 : 0, xw,
+                                                                         isg ? 1 : 0, V(lev));
             else
                 hy_level_kernel<<<blocks_of(size * Bp), 256, 0, st>>>(size, Bp, V(lev + 1), xw, isg ? 1 : 0, V(lev));
             PC_LAUNCH_CHECK();

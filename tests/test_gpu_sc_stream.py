@@ -151,11 +151,13 @@ def test_hybrid_decoder_vs_oracle(n, how, kind, seed, B, monkeypatch):
     np.testing.assert_array_equal(dinfo2, dinfo)
 
 
-def test_hybrid_large_block_bec_batch():
-    """N = 2^20, BEC(0.1), R = 0.8 (BASELINE config 4) through the hybrid decoder (default for batches >= 512 frames):
-    size-independent properties on the whole batch, the oracle on two frames, and agreement with the streamed decoder."""
+def test_hybrid_large_block_bec_batch(monkeypatch):
+    """N = 2^20, BEC(0.1), R = 0.8 (BASELINE config 4) through the hybrid decoder (the default for batches of thousands of
+    frames; forced here): size-independent properties on the whole batch, the oracle on two frames, and agreement with
+    the streamed decoder."""
     import os
     import polarcub_b200 as pcb
+    monkeypatch.setenv("PC_SC_HYBRID", "1")
     n, frames = 20, 512
     N = 1 << n
     K = int(0.8 * N)
@@ -177,10 +179,7 @@ def test_hybrid_large_block_bec_batch():
         ocw, oinfo = oracle.bin_decode(N, ed.frozenMask, ed.randomlyGeneratedNumbers, xp, tab[y[f]])
         np.testing.assert_array_equal(dcw[f], ocw)
         np.testing.assert_array_equal(dinfo[f], oinfo)
-    os.environ["PC_SC_HYBRID"] = "0"
-    try:
-        scw, sinfo = ed.decode_symbols_batch(y[:8], tab)
-    finally:
-        del os.environ["PC_SC_HYBRID"]
+    monkeypatch.setenv("PC_SC_HYBRID", "0")
+    scw, sinfo = ed.decode_symbols_batch(y[:8], tab)
     np.testing.assert_array_equal(scw, dcw[:8])
     np.testing.assert_array_equal(sinfo, dinfo[:8])
