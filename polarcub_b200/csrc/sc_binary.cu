@@ -700,22 +700,10 @@ void hybrid_tables_release(const pc_plan *p) {
     delete T;
 }
 
-// level n-1 from the channel symbols: out[h][f] = f / g of the pairs of symbols h and h + N/2 (table in constant params)
+// the channel's joint-probability table, passed by value to the lookup-table kernel
 struct HyRootParams {
     double table[32];
 };
-__global__ void __launch_bounds__(256) hy_root_kernel(int64_t half, int64_t Bpad, const uint8_t *__restrict__ sym,
-                                                      const uint32_t *__restrict__ xw, int isg, double *__restrict__ out,
-                                                      const HyRootParams tp) {
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= half * Bpad) return;
-    const int64_t h = gid / Bpad, f = gid - h * Bpad;
-    const uint32_t ya = sym[h * Bpad + f], yb = sym[(h + half) * Bpad + f];
-    const double a0 = tp.table[2 * ya], a1 = tp.table[2 * ya + 1], b0 = tp.table[2 * yb], b1 = tp.table[2 * yb + 1];
-    uint32_t u = 0;
-    if (isg) u = (xw[(h >> 5) * Bpad + f] >> (h & 31)) & 1u;
-    out[gid] = isg ? g_raw(a0, a1, b0, b1, u) : f_raw(a0, a1, b0, b1);
-}
 
 // Level n-1 is never stored: an element of it is a function of two channel symbols and (in the second half of the frame) one
 // decision bit, looked up in lut[mode][y_a][y_b] (mode 0: f, 1 + u: g) -- built on the device with f_raw / g_raw, so the

@@ -113,7 +113,6 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
     int16_t *pick = (int16_t *)(ivars + 4);  // [L][4]
     uint8_t *delta = (uint8_t *)(pick + 4 * L);
     uint8_t *omap = delta + L;               // [(n+1)][2][L]
-    uint8_t *eqf = omap + (n + 1) * 2 * L;   // [L]
     uint32_t *T0 = (uint32_t *)smem_raw, *T1 = T0 + NW, *T2 = T1 + NW;  // prologue / epilogue temporaries over the (then dead) path vectors
 
     {
