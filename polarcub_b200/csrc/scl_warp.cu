@@ -273,52 +273,55 @@ __global__ void __launch_bounds__(32, 24) sclw_kernel(const SclwParams p) {
                     // it+1 are issued before the arithmetic of iteration it.  Plain: lane h and h+32 of the 64 outputs.
                     // Fused: the lane's 4 consecutive elements give 2 outputs of level l-1 and 1 of level l-2.
                     // (levels >= 6 are always in the global scratch: 32-byte vector loads and stores)
-                    const int bsh = l - 7, bmask = (1 << bsh) - 1;
-                    const int niter = nt << bsh;
+                    const int nblk = 1 << (l - 7);
                     double2 *d2base = vptr[l - 2];
                     const int o2 = fused ? 2 : 64;
                     const bool al = l < n || p.xy_al32;
-                    auto src_ptr = [&](int it) -> const double2 * {
-                        const int t = it >> bsh, blk = it & bmask;
+                    const int loff = fused ? 4 * lane : 2 * lane;
+                    auto path_src = [&](int t) -> const double2 * {
                         const int src = genie ? L : (plus ? (int)om[t] : t);
-                        return sbase + src * sstride + blk * 128 + (fused ? 4 * lane : 2 * lane);
+                        return sbase + src * sstride + loff;
                     };
-                    const double2 *q = src_ptr(0);
+                    const double2 *q = path_src(0);
                     double2 e0, e1, e2, e3;
                     ld32(q, al, e0, e1);
                     ld32(q + o2, al, e2, e3);
 #pragma unroll 1
-                    for (int it = 0; it < niter; ++it) {
-                        double2 f0 = e0, f1 = e1, f2 = e2, f3 = e3;
-                        if (it + 1 < niter) {
-                            q = src_ptr(it + 1);
-                            ld32(q, al, f0, f1);
-                            ld32(q + o2, al, f2, f3);
-                        }
-                        const int t = it >> bsh, blk = it & bmask;
+                    for (int t = 0; t < nt; ++t) {
                         const int slot = genie ? L : t;
-                        uint32_t u0 = 0, u1 = 0;
-                        if (plus) {
-                            const uint32_t *rp = rb + slot * rw + 2 * blk;
-                            if (fused) {
-                                const uint32_t w = rp[lane >> 4];
-                                u0 = (w >> ((2 * lane) & 31)) & 1u;
-                                u1 = (w >> ((2 * lane + 1) & 31)) & 1u;
-                            } else {
-                                u0 = (rp[0] >> lane) & 1u;
-                                u1 = (rp[1] >> lane) & 1u;
+                        const double2 *qnp = t + 1 < nt ? path_src(t + 1) : nullptr;  // first block of the next path
+                        double2 *D = dbase + (slot << (l - 1)) + (fused ? 2 * lane : lane);
+                        double2 *D2 = d2base + (slot << (l - 2)) + lane;
+                        const uint32_t *rp = rb + slot * rw + (fused ? lane >> 4 : 0);
+                        const int sh0 = fused ? (2 * lane) & 31 : lane;
+#pragma unroll 1
+                        for (int blk = 0; blk < nblk; ++blk) {
+                            const double2 *qn = blk + 1 < nblk ? q + 128 : qnp;
+                            double2 f0 = e0, f1 = e1, f2 = e2, f3 = e3;
+                            if (qn) {
+                                ld32(qn, al, f0, f1);
+                                ld32(qn + o2, al, f2, f3);
                             }
+                            uint32_t u0 = 0, u1 = 0;
+                            if (plus) {
+                                const uint32_t w0 = rp[0], w1 = fused ? w0 >> 1 : rp[1];
+                                u0 = (w0 >> sh0) & 1u;
+                                u1 = (w1 >> sh0) & 1u;
+                            }
+                            const double2 y0 = node_update(e0, e1, plus, u0), y1 = node_update(e2, e3, plus, u1);
+                            if (fused) {
+                                st32(D, y0, y1);
+                                *D2 = node_update(y0, y1, false, 0u);
+                            } else {
+                                D[0] = y0;
+                                D[32] = y1;
+                            }
+                            D += 64;
+                            D2 += 32;
+                            rp += 2;
+                            e0 = f0, e1 = f1, e2 = f2, e3 = f3;
+                            q = qn;
                         }
-                        const double2 y0 = node_update(e0, e1, plus, u0), y1 = node_update(e2, e3, plus, u1);
-                        double2 *D = dbase + (slot << (l - 1)) + blk * 64;
-                        if (fused) {
-                            st32(D + 2 * lane, y0, y1);
-                            d2base[(slot << (l - 2)) + blk * 32 + lane] = node_update(y0, y1, false, 0u);
-                        } else {
-                            D[lane] = y0;
-                            D[lane + 32] = y1;
-                        }
-                        e0 = f0, e1 = f1, e2 = f2, e3 = f3;
                     }
                     if (lane == 0 && fused && !genie) nin[l - 2] = cnt;
                 } else {
