@@ -134,6 +134,12 @@ int64_t pc_qsc_wave_frames(const pc_plan *plan); /* see pc_sc_wave_frames */
 int pc_qsc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint8_t *d_cw, uint8_t *d_info,
                         void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* d_y [B][N] uint8 channel output symbols, h_table [Y][q] float64 = QaryMemorylessDistribution.probs (rows: output symbols),
+ * 1 <= Y <= 16: pc_qsc_decode_probs fused with makeQaryMemorylessVectorDistribution(length, yvec)
+ * (ScalarDistributions/QaryMemorylessDistribution.py:757-766) -- q x 8 times less input traffic. */
+int pc_qsc_decode_symbols(const pc_plan *plan, const uint8_t *d_y, int64_t B, const double *h_table, int Y, uint8_t *d_cw,
+                          uint8_t *d_info, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* ---- SC-list decoding (any q in {2,3,4,5}; binary SCL is q = 2) --------------------------------------- */
 /* QaryPolarEncoderDecoder.listDecode with actualInformation (genie selection, the form ir() uses,
  * QaryPolarEncoderDecoder.py:856).  d_xy [B][N][q] float64 (linear domain); d_frozen_values [B][N-k] uint8 (the

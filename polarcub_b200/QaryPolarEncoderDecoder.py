@@ -84,6 +84,17 @@ class QaryPolarEncoderDecoder:
             return cw.cpu().numpy().astype(np.int64), info
         return info
 
+    def decode_symbols_batch(self, y, table, return_codeword=False):
+        """y uint8 [B, N] channel output symbols, table [Y, q] = QaryMemorylessDistribution.probs: decode fused with
+        makeQaryMemorylessVectorDistribution(length, yvec) (QaryMemorylessDistribution.py:757-766)."""
+        self._require_linear()
+        yt = y if torch.is_tensor(y) else torch.from_numpy(np.ascontiguousarray(y, dtype=np.uint8))
+        cw, info = engine.qsc_decode_symbols(self.plan, yt.to(self.plan.device).contiguous(), table)
+        info = info.cpu().numpy().astype(np.int64)
+        if return_codeword:
+            return cw.cpu().numpy().astype(np.int64), info
+        return info
+
     # ---- the reference's entry points -----------------------------------------------------------------
     def encode(self, xVectorDistribution, information):
         assert len(xVectorDistribution) == self.length

@@ -33,6 +33,7 @@ SIGNATURES = {
     "pc_qsc_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "pc_qsc_wave_frames": (c_int64, [c_void_p]),
     "pc_qsc_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
+    "pc_qsc_decode_symbols": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pc_qsc_decode_probs": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pc_scl_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int64, c_int]),
     "pc_scl_decode_probs": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,

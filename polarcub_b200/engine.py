@@ -164,6 +164,21 @@ def qsc_decode_probs(plan, xy):
     return cw, info[:, :plan.k]
 
 
+def qsc_decode_symbols(plan, y, table, out=None):
+    """y uint8 [B, N] channel output symbols (device), table float64 [Y, q] = QaryMemorylessDistribution.probs (host)
+    -> (cw uint8 [B, N], info uint8 [B, k])."""
+    assert y.is_cuda and y.dtype == torch.uint8 and y.is_contiguous() and y.shape[1] == plan.N
+    table = np.ascontiguousarray(table, dtype=np.float64)
+    assert table.ndim == 2 and table.shape[1] == plan.q and 1 <= table.shape[0] <= 16
+    B = y.shape[0]
+    cw, info = out if out is not None else (torch.empty((B, plan.N), dtype=torch.uint8, device=y.device),
+                                            torch.empty((B, max(plan.k, 1)), dtype=torch.uint8, device=y.device))
+    ws = plan.workspace(_lib.lib().pc_qsc_workspace_bytes(plan._h, B))
+    _lib.check(_lib.lib().pc_qsc_decode_symbols(plan._h, _ptr(y), B, table.ctypes.data_as(ctypes.c_void_p), table.shape[0],
+                                                _ptr(cw), _ptr(info), _ptr(ws), ws.numel(), _stream()), "pc_qsc_decode_symbols")
+    return cw, info[:, :plan.k]
+
+
 def scl_decode_probs(plan, L, xy, frozen_values, actual_info, want_list=False, want_list_info=False):
     """SC-list decoding (QaryPolarEncoderDecoder.listDecode with genie selection) of a batch.
 
@@ -421,6 +436,27 @@ def qsc_decode_probs_host(plan, xy_host, info_host, cw_host=None, chunk=None):
         xy.copy_(xy_host[lo:hi], non_blocking=True)
         cw, info = qsc_decode_probs(plan, xy)
         info_host[lo:hi].copy_(info, non_blocking=True)
+        if cw_host is not None:
+            cw_host[lo:hi].copy_(cw, non_blocking=True)
+
+    host_pipeline(plan, B, chunk, body)
+
+
+def qsc_decode_symbols_host(plan, y_host, table, info_host, cw_host=None, chunk=None):
+    """pc_qsc_decode_symbols over a batch in pinned host memory: y_host uint8 [B, N] -> info_host uint8 [B, k]."""
+    _pinned(y_host, "y_host"), _pinned(info_host, "info_host")
+    B = y_host.shape[0]
+    chunk = chunk or default_host_chunk(B, plan.N, int(_lib.lib().pc_qsc_wave_frames(plan._h)))
+    sl = _Slots(plan, "qscsym")
+
+    def body(lo, hi, slot):
+        m = hi - lo
+        y = sl.get(slot, "y", (chunk, plan.N), torch.uint8)[:m]
+        cw = sl.get(slot, "cw", (chunk, plan.N), torch.uint8)[:m]
+        info = sl.get(slot, "info", (chunk, max(plan.k, 1)), torch.uint8)[:m]
+        y.copy_(y_host[lo:hi], non_blocking=True)
+        qsc_decode_symbols(plan, y, table, out=(cw, info))
+        info_host[lo:hi].copy_(info[:, :plan.k], non_blocking=True)
         if cw_host is not None:
             cw_host[lo:hi].copy_(cw, non_blocking=True)
 

@@ -66,3 +66,31 @@ def test_random_frames_vs_oracle(q, n):
     assert one.dtype == np.int64 and one.shape == (k,)
     np.testing.assert_array_equal(one, oinfo[0])
     np.testing.assert_array_equal(ed.encode(xv, info[0]), cw[0])
+
+
+def test_qary_symbols_entry_point_matches_probs():
+    """pc_qsc_decode_symbols (channel table lookup fused into the ingest) == pc_qsc_decode_probs on tab[y]."""
+    import polarcub_b200 as pcb
+    q, n = 3, 9
+    N = 1 << n
+    rng = np.random.default_rng(31)
+    z = [0.5]
+    for _ in range(n):
+        z = [v for zz in z for v in (2 * zz - zz * zz, zz * zz)]
+    fs = set(int(i) for i in np.argsort(-np.array(z), kind="stable")[:N // 2])
+    ed = pcb.QaryPolarEncoderDecoder(q, N, fs, 1)
+    p = 0.05
+    tab = np.full((q, q), p / (q - 1))
+    np.fill_diagonal(tab, 1.0 - p)
+    info = rng.integers(0, q, size=(300, ed.k))
+    cw = ed.encode_batch(info)
+    err = rng.random(cw.shape) < p
+    y = np.where(err, (cw + rng.integers(1, q, size=cw.shape)) % q, cw).astype(np.uint8)
+    c1, i1 = ed.decode_symbols_batch(y, tab, return_codeword=True)
+    c2, i2 = ed.decode_batch(tab[y], return_codeword=True)
+    np.testing.assert_array_equal(i1, i2)
+    np.testing.assert_array_equal(c1, c2)
+    # erasure-like extra output symbol (Y = q + 1 rows)
+    tab2 = np.vstack([tab, np.full((1, q), 1.0 / q)])
+    y2 = np.where(rng.random(cw.shape) < 0.1, q, y).astype(np.uint8)
+    np.testing.assert_array_equal(ed.decode_symbols_batch(y2, tab2), ed.decode_batch(tab2[y2]))
