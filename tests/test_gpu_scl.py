@@ -101,3 +101,61 @@ def test_random_frames_vs_oracle(q, n, L, B):
     ginfo2, gres2 = ed.listDecode_batch(xy, fv, L, info)
     np.testing.assert_array_equal(ginfo2, ginfo)
     np.testing.assert_array_equal(gres2, gres)
+
+
+def _pattern(n, how, rate, rng):
+    N = 1 << n
+    if how == "bec":
+        return set(int(i) for i in _bec_order(n)[:N - int(rate * N)])
+    if how == "random":
+        return set(int(i) for i in rng.permutation(N)[:N - int(rate * N)])
+    m = np.zeros(N, dtype=bool)  # long frozen / free runs: fast nodes of every kind and size, also very large ones
+    pos = 0
+    while pos < N:
+        run = int(rng.choice([1, 2, 3, 4, 8, 16, 31, 32, 64, 128, 256, 512, 1024]))
+        if rng.random() > rate:
+            m[pos:pos + run] = True
+        pos += run
+    if m.all():
+        m[-1] = False
+    return set(np.nonzero(m)[0].tolist())
+
+
+@pytest.mark.parametrize("n,L,how,rate,B", [(6, 3, "blocks", 0.5, 24), (7, 2, "random", 0.75, 24), (8, 16, "blocks", 0.8, 20),
+                                            (9, 8, "bec", 0.9, 16), (10, 32, "blocks", 0.5, 8), (11, 4, "blocks", 0.25, 12),
+                                            (11, 8, "random", 0.5, 8), (12, 16, "bec", 0.75, 6), (13, 8, "blocks", 0.6, 5),
+                                            (13, 2, "bec", 0.95, 5), (5, 8, "blocks", 1.0, 16), (4, 32, "random", 0.5, 16)])
+def test_binary_scl_shapes_vs_oracle(n, L, how, rate, B):
+    """The frame-per-warp list decoder on irregular frozen patterns (fast nodes of every kind up to 1024 symbols, all-information
+    codes, tiny blocks), list sizes 2 .. 32 and block lengths up to 2^13: everything the oracle reports must match."""
+    import polarcub_b200 as pcb
+    N = 1 << n
+    rng = np.random.default_rng(12000 + 101 * n + L)
+    fs = _pattern(n, how, rate, rng)
+    ed = pcb.QaryPolarEncoderDecoder(2, N, fs, 1)
+    fm, k = ed.frozenMask, ed.k
+    info = rng.integers(0, 2, size=(B, k))
+    fv = np.zeros((B, N - k), dtype=np.int64)
+    if n <= 8:
+        fv = rng.integers(0, 2, size=(B, N - k))  # non-zero frozen values too
+    u = np.zeros((B, N), dtype=np.int64)
+    u[:, fm == 0] = info
+    u[:, fm == 1] = fv
+    cw = np.stack([oracle.polar_transform_qudits(2, u[b]) for b in range(B)])
+    sigma = 0.9
+    y = (1.0 - 2.0 * cw) + sigma * rng.standard_normal((B, N))
+    l0, l1 = -(y - 1) ** 2 / (2 * sigma ** 2), -(y + 1) ** 2 / (2 * sigma ** 2)
+    m = np.maximum(l0, l1)
+    xy = np.stack([np.exp(l0 - m), np.exp(l1 - m)], axis=-1)
+    ginfo, gres, lst = ed.listDecode_batch(xy, fv, L, info, return_list=True)
+    for b in range(B):
+        oi, opr, ols, olinfo, olprob, oap = oracle.list_decode(2, N, L, fm, xy[b], fv[b], info[b], want_list=True)
+        np.testing.assert_array_equal(ginfo[b], oi, err_msg="frame %d" % b)
+        assert int(gres[b]) == opr, b
+        assert int(lst["list_size"][b]) == ols, b
+        np.testing.assert_array_equal(lst["list_info"][b][:ols], olinfo[:ols], err_msg="frame %d" % b)
+        assert np.array_equal(lst["list_prob"][b][:ols], olprob[:ols]), b
+        assert float(lst["actual_prob"][b]) == oap, b
+    ginfo2, gres2 = ed.listDecode_batch(xy, fv, L, info)
+    np.testing.assert_array_equal(ginfo2, ginfo)
+    np.testing.assert_array_equal(gres2, gres)
