@@ -463,7 +463,8 @@ class ScQary2048:
             if not self.allow_ga:
                 raise
             fs = frozen_set_from_pe(bec_pe(self.n, 0.15), self.K)
-            self.construction = "BEC(0.15) Bhattacharyya heuristic, --construction ga"
+            self.construction = ("BEC(0.15) Bhattacharyya heuristic (the reference-derived Pe vector %s is not under "
+                                 "tests/golden/constructions/: its degrade/upgrade pass takes hours; --construction reference insists on it)" % name)
         self.fm = mask_of(self.N, fs)
 
     def setup(self, dev, rank, B, Be):
@@ -705,7 +706,7 @@ def run_reference(args, rank):
     import oracle
     oracle.build()
     w = WORKLOADS[args.workload]()
-    w.allow_ga = args.construction == "ga"
+    w.allow_ga = args.construction != "reference"
     cores = os.cpu_count() or 1
     frames = args.ref_frames or w.default_cpu
     inputs = w.cpu_inputs_synth(frames)
@@ -749,7 +750,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     w = WORKLOADS[args.workload]()
-    w.allow_ga = args.construction == "ga"
+    w.allow_ga = args.construction != "reference"
     B = args.frames or w.default_frames
     Be = min(args.e2e_frames or w.default_e2e, B)
     w.setup(dev, rank, B, Be)
@@ -871,7 +872,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="scl4096", choices=sorted(WORKLOADS))
-    ap.add_argument("--construction", default="reference", choices=["reference", "ga"],
+    ap.add_argument("--construction", default="auto", choices=["auto", "reference", "ga"],
                     help="ga: allow a heuristic frozen set when the reference-derived Pe vector is not in tests/golden/constructions")
     ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (0 = workload default)")
     ap.add_argument("--e2e-frames", type=int, default=0)
