@@ -96,6 +96,9 @@ struct pc_plan {
     uint32_t *d_frozen_words = nullptr;  // [ceil(N/32)] frozen values as bits (binary)
     uint8_t *d_frozen_mask = nullptr;    // [N]
     uint8_t *d_frozen_vals = nullptr;    // [N]
+    // warp-per-frame encoder (encode.cu): per u word w, 8 words {information-position mask, number of information bits
+    // before the word, the five bit-deposit (expand) masks of that mask, frozen-value bits}
+    uint32_t *d_enc_tab = nullptr;       // [ceil(N/32)][8]
 };
 
 // ---- device helpers ---------------------------------------------------------------------------------

@@ -77,6 +77,134 @@ __global__ void __launch_bounds__(256) encode_bits_kernel(int n, int k, int64_t 
     }
 }
 
+// ---- warp per frame, 2^10 <= N <= 2^15: the whole frame lives in registers (G = N / 1024 words per lane, word lane * G + j
+// in register j), 128-bit loads / stores for G >= 4 --------------------------------------------------------------------
+//  1. u words: the information bits are deposited at the information positions of each word with a 5-step bit-deposit
+//     (Hacker's Delight "expand", masks precomputed per plan) from a funnel-shifted window of the packed information;
+//  2. butterfly T([a;b]) = [T(a)^T(b), T(b)]: strides below 32 by shifts and masks, word strides below G between registers,
+//     above by __shfl_xor;
+//  3. x_ref[i] = x_nat[rev_n(i)]: N / 1024 independent 32 x 32 bit-matrix transposes ACROSS THE LANES of the warp
+//     (5 shuffle steps), preceded by one lane permutation; lane c ends up owning G consecutive output words.
+template <int SRC, int LOGG>
+__global__ void __launch_bounds__(256) encode_warp_kernel(int k, int64_t B, const uint32_t *__restrict__ in,
+                                                          const uint32_t *__restrict__ tab, uint32_t *__restrict__ out) {
+    constexpr int G = 1 << LOGG, Nw = 32 * G;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int Kw = (k + 31) >> 5;
+    const int src_lane = 31 - (int)(__brev((uint32_t)lane) >> 27);
+    for (int64_t f = warp; f < B; f += nwarps) {
+        uint32_t x[G];
+        if (SRC == SRC_INFO) {
+            const uint32_t *info = in + f * Kw;
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const uint4 t0 = __ldg((const uint4 *)(tab + (size_t)(lane * G + j) * 8));
+                const uint4 t1 = __ldg((const uint4 *)(tab + (size_t)(lane * G + j) * 8) + 1);
+                const uint32_t m = t0.x, before = t0.y;
+                uint32_t v = 0;
+                if (m) {
+                    const int wi = (int)(before >> 5), sh = (int)(before & 31);
+                    const uint32_t lo = __ldg(info + wi), hi = (sh && wi + 1 < Kw) ? __ldg(info + wi + 1) : 0u;
+                    v = __funnelshift_r(lo, hi, sh);  // the next 32 information bits
+                    // expand: deposit the low popc(m) bits of v at the set bits of m
+                    uint32_t tt;
+                    tt = v << 16, v = (v & ~t1.z) | (tt & t1.z);
+                    tt = v << 8, v = (v & ~t1.y) | (tt & t1.y);
+                    tt = v << 4, v = (v & ~t1.x) | (tt & t1.x);
+                    tt = v << 2, v = (v & ~t0.w) | (tt & t0.w);
+                    tt = v << 1, v = (v & ~t0.z) | (tt & t0.z);
+                    v &= m;
+                }
+                x[j] = v | t1.w;
+            }
+        } else {
+            const uint32_t *xin = in + f * Nw + lane * G;
+            if (G >= 4) {
+#pragma unroll
+                for (int j = 0; j < G; j += 4) {
+                    const uint4 q = __ldg((const uint4 *)(xin + j));
+                    x[j] = q.x, x[j + 1 < G ? j + 1 : j] = q.y, x[j + 2 < G ? j + 2 : j] = q.z, x[j + 3 < G ? j + 3 : j] = q.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < G; ++j) x[j] = __ldg(xin + j);
+            }
+        }
+        // butterfly inside the words, between registers, between lanes
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            uint32_t v = x[j];
+            v ^= (v >> 1) & 0x55555555u;
+            v ^= (v >> 2) & 0x33333333u;
+            v ^= (v >> 4) & 0x0f0f0f0fu;
+            v ^= (v >> 8) & 0x00ff00ffu;
+            v ^= (v >> 16) & 0x0000ffffu;
+            x[j] = v;
+        }
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1)
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                if (!(j & d)) x[j] ^= x[j + d < G ? j + d : j];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const uint32_t pv = __shfl_xor_sync(0xffffffffu, x[j], d);
+                x[j] ^= (lane & d) ? 0u : pv;
+            }
+        // bit reversal: lane permutation, then a 32 x 32 bit transpose across the lanes per register
+        uint32_t y[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            uint32_t v = __shfl_sync(0xffffffffu, x[j], src_lane);
+#pragma unroll
+            for (int jj = 0; jj < 5; ++jj) {
+                const int s = 16 >> jj;
+                const uint32_t msk = jj == 0 ? 0x0000ffffu : jj == 1 ? 0x00ff00ffu : jj == 2 ? 0x0f0f0f0fu : jj == 3 ? 0x33333333u : 0x55555555u;
+                const uint32_t pv = __shfl_xor_sync(0xffffffffu, v, s);
+                if (lane & s) {
+                    const uint32_t t = (pv ^ (v >> s)) & msk;  // this lane is row k + s, the partner row k
+                    v ^= t << s;
+                } else {
+                    const uint32_t t = (v ^ (pv >> s)) & msk;
+                    v ^= t;
+                }
+            }
+            // lane c now holds T_j[c]: output word (31 - rev5(c)) * G + rev_LOGG(j)
+            constexpr int dummy = 0;
+            (void)dummy;
+            y[LOGG ? (int)(__brev((uint32_t)j) >> (32 - (LOGG ? LOGG : 1))) : 0] = v;
+        }
+        uint32_t *o = out + f * Nw + src_lane * G;
+        if (G >= 4) {
+#pragma unroll
+            for (int j = 0; j < G; j += 4)
+                *(uint4 *)(o + j) = make_uint4(y[j], y[j + 1 < G ? j + 1 : j], y[j + 2 < G ? j + 2 : j], y[j + 3 < G ? j + 3 : j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; ++j) o[j] = y[j];
+        }
+    }
+}
+
+template <int SRC>
+static int launch_warp_encoder(int n, int k, int64_t B, const uint32_t *in, const uint32_t *tab, uint32_t *out, cudaStream_t st) {
+    const int64_t want = (B + 7) / 8;
+    const int grid = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+    switch (n) {
+        case 10: encode_warp_kernel<SRC, 0><<<grid, 256, 0, st>>>(k, B, in, tab, out); break;
+        case 11: encode_warp_kernel<SRC, 1><<<grid, 256, 0, st>>>(k, B, in, tab, out); break;
+        case 12: encode_warp_kernel<SRC, 2><<<grid, 256, 0, st>>>(k, B, in, tab, out); break;
+        case 13: encode_warp_kernel<SRC, 3><<<grid, 256, 0, st>>>(k, B, in, tab, out); break;
+        case 14: encode_warp_kernel<SRC, 4><<<grid, 256, 0, st>>>(k, B, in, tab, out); break;
+        default: encode_warp_kernel<SRC, 5><<<grid, 256, 0, st>>>(k, B, in, tab, out); break;
+    }
+    PC_LAUNCH_CHECK();
+    return PC_OK;
+}
+
 // q-ary: one frame per block, one byte per symbol in shared memory.
 __global__ void __launch_bounds__(256) encode_qary_kernel(int q, int n, int k, int64_t B, const uint8_t *__restrict__ info,
                                                           const int32_t *__restrict__ src,
@@ -107,8 +235,13 @@ __global__ void __launch_bounds__(256) encode_qary_kernel(int q, int n, int k, i
 }
 
 static int launch_bits(int src_kind, int n, int k, int64_t B, const uint32_t *in, const int32_t *src,
-                       const uint32_t *frozen_words, uint32_t *out, cudaStream_t st) {
+                       const uint32_t *frozen_words, uint32_t *out, cudaStream_t st, const uint32_t *enc_tab = nullptr) {
     if (B == 0) return PC_OK;
+    const char *ev = getenv("PC_ENCODE_CTA");  // 1: keep the frame-per-CTA kernel (tests compare the two)
+    if (n >= 10 && n <= 15 && !(ev && *ev == '1') && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0) {
+        if (src_kind == SRC_WORDS) return launch_warp_encoder<SRC_WORDS>(n, k, B, in, nullptr, out, st);
+        if (enc_tab) return launch_warp_encoder<SRC_INFO>(n, k, B, in, enc_tab, out, st);
+    }
     const int Nw = ((1 << n) + 31) >> 5;
     const int threads = 256;
     int tpf = 32;
@@ -139,7 +272,7 @@ int pc_encode_bits(const pc_plan *plan, const uint32_t *d_info_packed, uint32_t 
     PC_REQUIRE(plan && plan->q == 2, "binary plan required");
     PC_REQUIRE(B >= 0 && (d_cw_packed || B == 0) && (d_info_packed || plan->k == 0 || B == 0), "null buffer");
     return pc::launch_bits(pc::SRC_INFO, plan->n, plan->k, B, d_info_packed, plan->d_src, plan->d_frozen_words,
-                           d_cw_packed, (cudaStream_t)stream);
+                           d_cw_packed, (cudaStream_t)stream, plan->d_enc_tab);
 }
 
 int pc_polar_transform_bits(int n, const uint32_t *d_cw_packed, uint32_t *d_u_packed, int64_t B, void *stream) {

@@ -129,6 +129,34 @@ int pc_plan_create(int q, int n, const uint8_t *h_frozen_mask, const uint8_t *h_
     for (int i = 0; i < N; ++i)
         if (p->frozen_mask[i] && (p->frozen_vals[i] & 1)) fw[i >> 5] |= 1u << (i & 31);
 
+    // bit-deposit tables of the warp-per-frame encoder: Hacker's Delight 7-5 "expand" masks of each word's information mask
+    std::vector<uint32_t> enc_tab((size_t)Nw * 8, 0u);
+    {
+        uint32_t before = 0;
+        for (int w = 0; w < Nw; ++w) {
+            uint32_t m = 0;
+            for (int b = 0; b < 32 && 32 * w + b < N; ++b)
+                if (!p->frozen_mask[32 * w + b]) m |= 1u << b;
+            uint32_t *t = &enc_tab[(size_t)w * 8];
+            t[0] = m;
+            t[1] = before;
+            uint32_t mm = m, mk = ~m << 1;
+            for (int i = 0; i < 5; ++i) {
+                uint32_t mp = mk ^ (mk << 1);
+                mp ^= mp << 2;
+                mp ^= mp << 4;
+                mp ^= mp << 8;
+                mp ^= mp << 16;
+                const uint32_t mv = mp & mm;
+                t[2 + i] = mv;
+                mm = (mm ^ mv) | (mv >> (1 << i));
+                mk &= ~mp;
+            }
+            t[7] = fw[w];
+            before += (uint32_t)__builtin_popcount(m);
+        }
+    }
+
     cudaError_t e = cudaGetDevice(&p->device);
     auto fail = [&](const char *what) {
         pc::set_error("pc_plan_create: %s -> %s", what, cudaGetErrorString(e));
@@ -152,6 +180,7 @@ int pc_plan_create(int q, int n, const uint8_t *h_frozen_mask, const uint8_t *h_
     UP(p->d_frozen_words, fw, uint32_t);
     UP(p->d_frozen_mask, p->frozen_mask, uint8_t);
     UP(p->d_frozen_vals, p->frozen_vals, uint8_t);
+    UP(p->d_enc_tab, enc_tab, uint32_t);
 #undef UP
     *out = p;
     return PC_OK;
@@ -168,6 +197,7 @@ void pc_plan_destroy(pc_plan *p) {
     cudaFree(p->d_r0_words);
     cudaFree(p->d_src);
     cudaFree(p->d_frozen_words);
+    cudaFree(p->d_enc_tab);
     cudaFree(p->d_frozen_mask);
     cudaFree(p->d_frozen_vals);
     delete p;
