@@ -774,6 +774,8 @@ static SclwConfig sclw_config(const pc_plan *plan, int L, int64_t B) {
     if (c.smem > 220 * 1024) return c;
     int per_sm = (int)((227 * 1024) / (c.smem + 1024));
     if (per_sm > 32) per_sm = 32;
+    const int cap = envw_int("PC_SCLW_MAX_PER_SM", 0);  // tuning: fewer resident warps than the shared memory allows
+    if (cap > 0 && per_sm > cap) per_sm = cap;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)num_sms() * per_sm;
     if (grid > B) grid = B;
