@@ -67,7 +67,8 @@ struct ProfScope {                // brackets a multi-launch operation as ONE me
 // BinaryPolarEncoderDecoder.recursiveEncodeDecode (BinaryPolarEncoderDecoder.py:223-325) into a list of
 // nodes visited left to right.  A node is either a single information leaf or a maximal all-frozen
 // (rate-0) sub-tree whose codeword is known in advance, so its probabilities are never computed.
-enum : int { NODE_INFO = 0, NODE_RATE0 = 1, NODE_GENIE = 2 };  // GENIE: known leaf bit, leaf probabilities captured
+enum : int { NODE_INFO = 0, NODE_RATE0 = 1, NODE_GENIE = 2, NODE_RATE1 = 3 };  // GENIE: known leaf bit, leaf probabilities captured
+// RATE1 (hybrid decoder's sub-block schedules only): all-information sub-tree, `bits` = number of entries it spans after this one
 struct SchedEntry {
     int32_t i;      // first u index covered by the node
     int8_t l;       // log2 of the node size

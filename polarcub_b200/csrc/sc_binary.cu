@@ -135,7 +135,13 @@ __device__ __forceinline__ double leaf_m0(double v) {
     return p0 / __dadd_rn(__dadd_rn(0.0, p0), p1);
 }
 
-template <int KIND, int MODE = MODE_DECODE>
+// R1 (hybrid decoder, channels with hard output symbols): the schedule carries a NODE_RATE1 entry in front of every all-information
+// sub-tree.  When the node's vector is hard knowledge in all 32 frames of the warp (r = 0: every value of a BEC frame that is
+// not an erasure), SC decoding of the sub-tree returns the hard decisions themselves -- the reference's products and sums
+// on (1,0) / (0,1) pairs are exact and no leaf is a tie -- so the node's codeword is read off the sign bits and the
+// sub-tree's entries are skipped; otherwise the walk continues into the sub-tree.  The information words are NOT produced
+// by this variant (the hybrid decoder takes them from the transform of the codeword).
+template <int KIND, int MODE = MODE_DECODE, bool R1 = false>
 __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel(const ScParams p) {
     extern __shared__ double sm_vals[];  // [SMEM_VALS][SC_THREADS]
     __shared__ double s_table[32];
@@ -190,6 +196,8 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
         int icount = 0;
         int top_mode = 0;  // lut: 0 while level n-1 is f of the channel pairs (first half), 1 when it is g with x[0, N/2)
 
+        int resume = -1;  // R1: a rate-1 node was not hard; the next entry (its first child) continues with f at this level
+
         if (n == 0) {  // no transform: leaf rule on the raw pair (BinaryPolarEncoderDecoder.py:250-252)
             const SchedEntry e = p.sched[0];
             uint32_t bit = e.bits & 1u;
@@ -214,6 +222,11 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
             // down to the node; i == 0 starts with f at level n-1; a rate-0 node that is a whole plus child needs nothing
             int lev = i == 0 ? n - 1 : (top >= stop ? top : -1);
             bool isg = i != 0;
+            if (R1 && resume >= 0) {
+                lev = resume;
+                isg = false;
+                resume = -1;
+            }
 #pragma unroll 1
             for (; lev >= stop; --lev, isg = false) {
                 const int size = 1 << lev;
@@ -304,7 +317,50 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                     level_batches<SC_THREADS, SC_THREADS>(sv + (SC_THREADS << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
             }
             // ---- the node itself -----------------------------------------------------------------------
-            if (MODE != MODE_DECODE) {
+            if (R1 && e.kind == NODE_RATE1) {
+                // element h of the node's vector: level l of the tree, or the kernel's input when the node is the whole block
+                const double *np_;
+                int64_t nstr;
+                if (l == n) {
+                    np_ = (const double *)p.in_t + col;
+                    nstr = p.Bpad;
+                } else {
+                    np_ = lvl_ptr(l);
+                    nstr = lvl_stride(l);
+                }
+                unsigned long long soft = 0ULL;  // OR of the magnitudes: 0 iff every element is +-0
+                if (l < 5) {
+                    uint32_t w = 0;
+#pragma unroll 1
+                    for (int h = 0; h < (1 << l); ++h) {
+                        const double v = np_[h * nstr];
+                        soft |= (unsigned long long)__double_as_longlong(v) << 1;
+                        w |= d_sign(v) << h;
+                    }
+                    if (!__all_sync(0xffffffffu, soft == 0ULL)) {
+                        resume = l - 1;
+                        continue;
+                    }
+                    cwreg |= w << (i & 31);
+                } else {
+#pragma unroll 1
+                    for (int w0 = 0; w0 < (1 << (l - 5)); ++w0) {
+                        uint32_t w = 0;
+#pragma unroll 8
+                        for (int h = 0; h < 32; ++h) {
+                            const double v = np_[(int64_t)(32 * w0 + h) * nstr];
+                            soft |= (unsigned long long)__double_as_longlong(v) << 1;
+                            w |= d_sign(v) << h;
+                        }
+                        xw[(int64_t)((i >> 5) + w0) * p.Bpad] = w;  // overwritten by the leaf walk if the node is not hard
+                    }
+                    if (!__all_sync(0xffffffffu, soft == 0ULL)) {
+                        resume = l - 1;
+                        continue;
+                    }
+                }
+                ei += (int)e.bits;  // skip the sub-tree's entries
+            } else if (MODE != MODE_DECODE) {
                 // genie pass (BinaryPolarEncoderDecoder.py:114-178): every index is frozen to a known bit; the leaf's
                 // probabilities P(u_i | u_0^{i-1}, y) are captured (:268-273) as the packed level-0 value
                 const double v0 = sv[SC_THREADS];
@@ -653,7 +709,34 @@ struct HybridTables {
     std::vector<pc_plan *> sub;       // one plan per sub-block of 2^HY_L0 leaves
     std::vector<uint8_t> all_frozen;  // the sub-block is a rate-0 node
     int32_t *d_info_pos = nullptr;    // [k] u index of information bit j
+    // schedules with a NODE_RATE1 entry in front of every all-information sub-tree of 4+ leaves (sc_decode_kernel<.., R1>)
+    SchedEntry *d_sched_r1 = nullptr;
+    std::vector<int32_t> r1_off, r1_len;  // per sub-block: first entry / number of entries in d_sched_r1
 };
+
+// sub-plan schedule -> the same walk with NODE_RATE1 markers; `at` walks sp->sched in step with the recursion
+static void build_r1_schedule(const pc_plan *sp, int i, int l, size_t &at, std::vector<SchedEntry> &out) {
+    const SchedEntry &e = sp->sched[at];
+    if (e.i == i && e.l == l) {  // a leaf or a maximal rate-0 node
+        out.push_back(e);
+        ++at;
+        return;
+    }
+    bool all_info = true;
+    for (int j = i; j < i + (1 << l) && all_info; ++j) all_info = !sp->frozen_mask[j];
+    const size_t mark = out.size();
+    if (all_info && l >= 2) {
+        SchedEntry m{};
+        m.i = i;
+        m.l = (int8_t)l;
+        m.kind = NODE_RATE1;
+        m.top = (int8_t)(i == 0 ? sp->n : __builtin_ctz((unsigned)i));
+        out.push_back(m);
+    }
+    build_r1_schedule(sp, i, l - 1, at, out);
+    build_r1_schedule(sp, i + (1 << (l - 1)), l - 1, at, out);
+    if (all_info && l >= 2) out[mark].bits = (uint32_t)(out.size() - mark - 1);
+}
 static std::mutex g_hy_mu;
 static std::map<const pc_plan *, HybridTables *> g_hy_tables;
 
@@ -672,6 +755,18 @@ static HybridTables *hybrid_tables(const pc_plan *p) {
         }
         T->sub.push_back(sp);
         T->all_frozen.push_back(sp->k == 0 ? 1 : 0);
+    }
+    std::vector<SchedEntry> r1;
+    for (int j = 0; j < NS; ++j) {
+        size_t at = 0;
+        T->r1_off.push_back((int32_t)r1.size());
+        build_r1_schedule(T->sub[j], 0, HY_L0, at, r1);
+        T->r1_len.push_back((int32_t)r1.size() - T->r1_off.back());
+    }
+    if (cudaMalloc((void **)&T->d_sched_r1, r1.size() * sizeof(SchedEntry)) != cudaSuccess ||
+        cudaMemcpy(T->d_sched_r1, r1.data(), r1.size() * sizeof(SchedEntry), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("hybrid tables: device upload failed");
+        return nullptr;
     }
     std::vector<int32_t> pos;
     for (int i = 0; i < p->N; ++i)
@@ -697,6 +792,7 @@ void hybrid_tables_release(const pc_plan *p) {
     }
     for (pc_plan *q : T->sub) pc_plan_destroy(q);
     cudaFree(T->d_info_pos);
+    cudaFree(T->d_sched_r1);
     delete T;
 }
 
@@ -859,6 +955,11 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
     for (int i = 0; i < 32; ++i) tp.table[i] = i < 2 * Y ? h_table[i] : 0.0;
     const size_t smem = (size_t)SMEM_VALS * SC_THREADS * sizeof(double);
     PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<SC_INPUT_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<SC_INPUT_PACKED, MODE_DECODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // rate-1 shortcut: only channels with a hard output symbol (a table row with exactly one zero) can produce r = 0
+    bool r1 = false;
+    for (int y = 0; y < Y; ++y) r1 = r1 || ((h_table[2 * y] == 0.0) != (h_table[2 * y + 1] == 0.0));
+    if (const char *s = getenv("PC_SC_R1")) r1 = r1 && atoi(s) != 0;
     ProfScope prof_scope(st);  // the whole walk is the measured unit
     double *lut = (double *)(base + L.off_lut);
     hy_lut_kernel<<<3, 256, 0, st>>>(Y, tp, lut);
@@ -925,7 +1026,13 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
             p.info_t = (uint32_t *)(base + L.off_sub + SL.off_info);
             const int64_t blocks = (tiles * 32 + SC_THREADS - 1) / SC_THREADS;
             const int grid = (int)(blocks < SL.grid ? blocks : SL.grid);
-            sc_decode_kernel<SC_INPUT_PACKED><<<grid, SC_THREADS, smem, st>>>(p);
+            if (r1) {
+                p.sched = T->d_sched_r1 + T->r1_off[j];
+                p.n_sched = T->r1_len[j];
+                sc_decode_kernel<SC_INPUT_PACKED, MODE_DECODE, true><<<grid, SC_THREADS, smem, st>>>(p);
+            } else {
+                sc_decode_kernel<SC_INPUT_PACKED><<<grid, SC_THREADS, smem, st>>>(p);
+            }
             PC_LAUNCH_CHECK();
             // partial sums above the sub-block: x[ii - s, ii) ^= x[ii, ii + s) whenever a plus child completes
             int lv = HY_L0;

@@ -48,6 +48,10 @@ def _channel(kind, cw, rng):
         p = 0.35
         tab = np.array([[0.5 * (1 - p), 0.0], [0.0, 0.5 * (1 - p)], [0.5 * p, 0.5 * p]])
         return tab, np.where(rng.random((B, N)) < p, 2, cw).astype(np.uint8)
+    if kind == "bec_clean":  # few erasures: most all-information sub-trees see hard knowledge only
+        p = 0.04
+        tab = np.array([[0.5 * (1 - p), 0.0], [0.0, 0.5 * (1 - p)], [0.5 * p, 0.5 * p]])
+        return tab, np.where(rng.random((B, N)) < p, 2, cw).astype(np.uint8)
     if kind == "bec_lossy":  # contradictions: (0,0) states appear
         p = 0.3
         tab = np.array([[0.5 * (1 - p), 0.0], [0.0, 0.5 * (1 - p)], [0.5 * p, 0.5 * p]])
@@ -126,7 +130,10 @@ def test_large_block_bec(n, frames):
 
 
 @pytest.mark.parametrize("n,how,kind,seed,B", [(11, "bec", "bsc", 1, 70), (12, "blocks", "bec_lossy", 5, 45), (13, "random", "bsc", -1, 33),
-                                               (15, "blocks", "bec", 2, 40), (17, "bec", "bsc", 1, 6)])
+                                               (15, "blocks", "bec", 2, 40), (17, "bec", "bsc", 1, 6),
+                                               # erasure channels take the rate-1 shortcut of the sub-block kernel
+                                               (12, "bec", "bec", 1, 64), (13, "bec", "bec_lossy", -1, 40), (14, "random", "bec", 3, 33),
+                                               (12, "bec", "bec_clean", 1, 96), (13, "blocks", "bec_clean", 2, 64)])
 def test_hybrid_decoder_vs_oracle(n, how, kind, seed, B, monkeypatch):
     """The hybrid large-block decoder (element-parallel upper stages through HBM + frame-per-lane 1024-leaf sub-blocks),
     forced for block lengths the other decoders cover too: bit-exact against the oracle and against the other decoders."""
@@ -145,6 +152,11 @@ def test_hybrid_decoder_vs_oracle(n, how, kind, seed, B, monkeypatch):
     ocw, oinfo = oracle.bin_decode_batch(N, ed.frozenMask, ed.randomlyGeneratedNumbers, xp, tab[y[:nchk]])
     np.testing.assert_array_equal(dcw[:nchk], ocw)
     np.testing.assert_array_equal(dinfo[:nchk], oinfo)
+    monkeypatch.setenv("PC_SC_R1", "0")  # the same walk without the rate-1 shortcut
+    dcw3, dinfo3 = ed.decode_symbols_batch(y, tab)
+    np.testing.assert_array_equal(dcw3, dcw)
+    np.testing.assert_array_equal(dinfo3, dinfo)
+    monkeypatch.delenv("PC_SC_R1")
     monkeypatch.setenv("PC_SC_HYBRID", "0")
     dcw2, dinfo2 = ed.decode_symbols_batch(y, tab)
     np.testing.assert_array_equal(dcw2, dcw)
