@@ -88,7 +88,15 @@ __device__ __forceinline__ double node_packed(double a, double b, bool isg, uint
 // first division.  SSTR / DSTR: element strides (doubles) of the source and destination levels -- SC_THREADS for the
 // shared-memory levels, 32 for the warp's global scratch -- compile-time so that the batch's addresses are immediates.
 // g: the decision bits come from `uw` (one word per 32 elements, pitch Bpad) or, for levels below 32, from `ureg`.
-template <int SSTR, int DSTR>
+// F01 (channels with hard output symbols): operands that are hard knowledge or erasures (r = 0 / r = 1 -- every value of a
+// BEC frame) are combined by selection, without the division (sc_arith.cuh: same bits as the general routine).
+template <bool F01>
+__device__ __forceinline__ double node_sel(double a, double b, bool isg, uint32_t u) {
+    if (F01) return isg ? g_packed01(a, b, u) : f_packed01(a, b);
+    return node_packed(a, b, isg, u);
+}
+
+template <int SSTR, int DSTR, bool F01 = false, int BW = 4>
 __device__ __forceinline__ void level_batches(const double *sp, double *dp, int size, bool isg, const uint32_t *uw, int64_t Bpad,
                                               uint32_t ureg) {
     const double *sp2 = sp + (int64_t)size * SSTR;
@@ -101,18 +109,18 @@ __device__ __forceinline__ void level_batches(const double *sp, double *dp, int 
             uw += Bpad;
         }
 #pragma unroll 1
-        for (int hh = 0; hh < per_word; hh += 4) {
-            double a[4], b[4];
+        for (int hh = 0; hh < per_word; hh += BW) {
+            double a[BW], b[BW];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < BW; ++u) {
                 a[u] = sp[u * SSTR];
                 b[u] = sp2[u * SSTR];
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) dp[u * DSTR] = node_packed(a[u], b[u], isg, (ubw >> (hh + u)) & 1u);
-            sp += 4 * SSTR;
-            sp2 += 4 * SSTR;
-            dp += 4 * DSTR;
+            for (int u = 0; u < BW; ++u) dp[u * DSTR] = node_sel<F01>(a[u], b[u], isg, (ubw >> (hh + u)) & 1u);
+            sp += BW * SSTR;
+            sp2 += BW * SSTR;
+            dp += BW * DSTR;
         }
     }
 }
@@ -142,7 +150,7 @@ __device__ __forceinline__ double leaf_m0(double v) {
 // sub-tree's entries are skipped; otherwise the walk continues into the sub-tree.  The information words are NOT produced
 // by this variant (the hybrid decoder takes them from the transform of the codeword).
 template <int KIND, int MODE = MODE_DECODE, bool R1 = false>
-__global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel(const ScParams p) {
+__global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_decode_kernel(const ScParams p) {
     extern __shared__ double sm_vals[];  // [SMEM_VALS][SC_THREADS]
     __shared__ double s_table[32];
     __shared__ double s_lut[KIND == PC_INPUT_SYMBOLS ? 768 : 1];
@@ -241,21 +249,22 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                 if (KIND == SC_INPUT_PACKED && lev + 1 == n) {
                     // the top level is a packed vector [2^n][Bpad] produced by the element-parallel upper stages (sc hybrid)
                     const double *sp = (const double *)p.in_t + col, *sp2 = sp + (int64_t)size * p.Bpad;
+                    constexpr int BW = R1 ? 16 : 4;  // R1: few resident warps, more loads in flight per warp
 #pragma unroll 1
-                    for (int h0 = 0; h0 < size; h0 += 4) {
+                    for (int h0 = 0; h0 < size; h0 += BW) {
                         uint32_t ub = 0;
                         if (isg) ub = (size >= 32 ? uw[(int64_t)(h0 >> 5) * p.Bpad] : ureg) >> (h0 & 31);
-                        double a[4], b[4];
+                        double a[BW], b[BW];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < BW; ++u) {
                             a[u] = (h0 + u < size) ? sp[(int64_t)u * p.Bpad] : 1.0;
                             b[u] = (h0 + u < size) ? sp2[(int64_t)u * p.Bpad] : 1.0;
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (h0 + u < size) dp[(int64_t)(h0 + u) * dstr] = node_packed(a[u], b[u], isg, (ub >> u) & 1u);
-                        sp += 4 * p.Bpad;
-                        sp2 += 4 * p.Bpad;
+                        for (int u = 0; u < BW; ++u)
+                            if (h0 + u < size) dp[(int64_t)(h0 + u) * dstr] = node_sel<R1>(a[u], b[u], isg, (ub >> u) & 1u);
+                        sp += BW * p.Bpad;
+                        sp2 += BW * p.Bpad;
                     }
                     continue;
                 }
@@ -276,7 +285,7 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                     const double *sp = sv + (SC_THREADS << (lev + 1));
 #pragma unroll 1
                     for (int h = 0; h < size; ++h)
-                        dp[h * SC_THREADS] = node_packed(sp[h * SC_THREADS], sp[(h + size) * SC_THREADS], isg, (ureg >> h) & 1u);
+                        dp[h * SC_THREADS] = node_sel<R1>(sp[h * SC_THREADS], sp[(h + size) * SC_THREADS], isg, (ureg >> h) & 1u);
                     continue;
                 }
                 if (lut && lev == n - 2) {
@@ -310,11 +319,11 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM) sc_decode_kernel
                     continue;
                 }
                 if (lev > LS)
-                    level_batches<32, 32>(gv + ((int64_t)32 << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
+                    level_batches<32, 32, R1, R1 ? 16 : 4>(gv + ((int64_t)32 << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
                 else if (lev == LS)
-                    level_batches<32, SC_THREADS>(gv + ((int64_t)32 << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
+                    level_batches<32, SC_THREADS, R1, R1 ? 16 : 4>(gv + ((int64_t)32 << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
                 else
-                    level_batches<SC_THREADS, SC_THREADS>(sv + (SC_THREADS << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
+                    level_batches<SC_THREADS, SC_THREADS, R1>(sv + (SC_THREADS << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
             }
             // ---- the node itself -----------------------------------------------------------------------
             if (R1 && e.kind == NODE_RATE1) {
