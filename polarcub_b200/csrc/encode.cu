@@ -205,6 +205,138 @@ static int launch_warp_encoder(int n, int k, int64_t B, const uint32_t *in, cons
     return PC_OK;
 }
 
+// ---- 2^16 <= N <= 2^20: 2^(n-10) threads per frame, 1024 / 2^(n-10) frames per 1024-thread block, the block's 2^20 bits in
+// 128 KB of shared memory.  Word index bits: [T (top 5) | M (n-10)] = [thread t (n-10) | j (5)].
+//  A. thread t owns the 32 consecutive words t * 32 + j in registers: u words by the same bit-deposit as the warp kernel (or
+//     the packed input words), butterfly strides inside the words, between registers (word bits 0-4) and between lanes
+//     (word bits 5 .. n-11, shuffles); the words go to shared memory;
+//  B. thread M re-reads the 32 words (T, M), T = 0..31: butterfly over the top five word bits between registers, then the
+//     bit reversal x_ref[i] = x_nat[rev_n(i)] -- for every M a 32 x 32 bit-matrix transpose (in registers) whose rows land
+//     in the words (31 - rev5(c), rev(M)); the rows are staged in shared memory and copied out coalesced.
+// Shared-memory word w lives at w ^ ((w >> 5) & 31): phase A's stride-32 stores, phase B's loads and the bit-reversed row
+// stores are all bank-conflict free.
+template <int SRC>
+__global__ void __launch_bounds__(1024, 1) encode_block_kernel(int n, int k, int64_t B, bool vec, const uint32_t *__restrict__ in,
+                                                               const uint32_t *__restrict__ tab, uint32_t *__restrict__ out) {
+    extern __shared__ uint32_t sm_words[];
+    const int lg = n - 10, tpf = 1 << lg, Nw = 32 << lg, fpb = 1024 >> lg;
+    const int slot = threadIdx.x >> lg, t = threadIdx.x & (tpf - 1), lane = threadIdx.x & 31;
+    const int Kw = (k + 31) >> 5;
+    uint32_t *w = sm_words + (size_t)slot * Nw;
+    const uint32_t rev_m = __brev((uint32_t)t) >> (32 - lg);
+    for (int64_t f0 = (int64_t)blockIdx.x * fpb; f0 < B; f0 += (int64_t)gridDim.x * fpb) {
+        const int64_t f = f0 + slot;
+        const bool live = f < B;
+        uint32_t x[32];
+        // ---- A ---------------------------------------------------------------------------------------
+        if (!live) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = 0u;
+        } else if (SRC == SRC_INFO) {
+            const uint32_t *info = in + f * Kw;
+            const uint4 *tp = (const uint4 *)(tab + (size_t)t * 256);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint4 t0 = __ldg(tp + 2 * j), t1 = __ldg(tp + 2 * j + 1);
+                const uint32_t m = t0.x, before = t0.y;
+                uint32_t v = 0;
+                if (m) {
+                    const int wi = (int)(before >> 5), sh = (int)(before & 31);
+                    const uint32_t lo = __ldg(info + wi), hi = (sh && wi + 1 < Kw) ? __ldg(info + wi + 1) : 0u;
+                    v = __funnelshift_r(lo, hi, sh);
+                    uint32_t tt;
+                    tt = v << 16, v = (v & ~t1.z) | (tt & t1.z);
+                    tt = v << 8, v = (v & ~t1.y) | (tt & t1.y);
+                    tt = v << 4, v = (v & ~t1.x) | (tt & t1.x);
+                    tt = v << 2, v = (v & ~t0.w) | (tt & t0.w);
+                    tt = v << 1, v = (v & ~t0.z) | (tt & t0.z);
+                    v &= m;
+                }
+                x[j] = v | t1.w;
+            }
+        } else {
+            const uint32_t *xin = in + f * Nw + t * 32;
+            if (vec) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const uint4 q = __ldg((const uint4 *)(xin + j));
+                    x[j] = q.x, x[j + 1] = q.y, x[j + 2] = q.z, x[j + 3] = q.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = __ldg(xin + j);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            uint32_t v = x[j];
+            v ^= (v >> 1) & 0x55555555u;
+            v ^= (v >> 2) & 0x33333333u;
+            v ^= (v >> 4) & 0x0f0f0f0fu;
+            v ^= (v >> 8) & 0x00ff00ffu;
+            v ^= (v >> 16) & 0x0000ffffu;
+            x[j] = v;
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (!(j & d)) x[j] ^= x[j | d];
+#pragma unroll 1
+        for (int d = 1; d < (1 << (n - 15)); d <<= 1) {  // word bits 5 .. n-11 (the lanes); the higher bits belong to phase B
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t pv = __shfl_xor_sync(0xffffffffu, x[j], d);
+                x[j] ^= (lane & d) ? 0u : pv;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w[(t * 32 + j) ^ lane] = x[j];
+        __syncthreads();
+        // ---- B ---------------------------------------------------------------------------------------
+#pragma unroll
+        for (int T = 0; T < 32; ++T) {
+            const int idx = T * tpf + t;
+            x[T] = w[idx ^ ((idx >> 5) & 31)];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+            for (int T = 0; T < 32; ++T)
+                if (!(T & d)) x[T] ^= x[T | d];
+        uint32_t A[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) A[c] = x[31 - (int)(__brev((uint32_t)c) >> 27)];
+        // Hacker's Delight transpose32 (anti-transpose in LSB-first numbering: T[c] bit r = A[31-r] bit 31-c)
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+            const int j = 16 >> jj;
+            const uint32_t m = jj == 0 ? 0x0000ffffu : jj == 1 ? 0x00ff00ffu : jj == 2 ? 0x0f0f0f0fu : jj == 3 ? 0x33333333u : 0x55555555u;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                if (!(c & j)) {
+                    const uint32_t tt = (A[c] ^ (A[c + j] >> j)) & m;
+                    A[c] ^= tt;
+                    A[c + j] ^= tt << j;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int ow = (31 - (int)(__brev((uint32_t)c) >> 27)) * tpf + (int)rev_m;
+            w[ow ^ ((ow >> 5) & 31)] = A[c];
+        }
+        __syncthreads();
+        if (live) {
+            uint32_t *o = out + f * Nw;
+#pragma unroll 8
+            for (int i = t; i < Nw; i += tpf) o[i] = w[i ^ ((i >> 5) & 31)];
+        }
+        __syncthreads();
+    }
+}
+
 // q-ary: one frame per block, one byte per symbol in shared memory.
 __global__ void __launch_bounds__(256) encode_qary_kernel(int q, int n, int k, int64_t B, const uint8_t *__restrict__ info,
                                                           const int32_t *__restrict__ src,
@@ -241,6 +373,22 @@ static int launch_bits(int src_kind, int n, int k, int64_t B, const uint32_t *in
     if (n >= 10 && n <= 15 && !(ev && *ev == '1') && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0) {
         if (src_kind == SRC_WORDS) return launch_warp_encoder<SRC_WORDS>(n, k, B, in, nullptr, out, st);
         if (enc_tab) return launch_warp_encoder<SRC_INFO>(n, k, B, in, enc_tab, out, st);
+    }
+    if (n >= 16 && n <= 20 && !(ev && *ev == '1') && (src_kind == SRC_WORDS || enc_tab)) {
+        const int fpb = 1024 >> (n - 10);
+        const int64_t want = (B + fpb - 1) / fpb;
+        const int grid = (int)(want < (int64_t)num_sms() ? want : (int64_t)num_sms());
+        const int smem = 128 * 1024;
+        const bool vec = ((uintptr_t)in & 15) == 0;
+        if (src_kind == SRC_WORDS) {
+            PC_CUDA(cudaFuncSetAttribute(encode_block_kernel<SRC_WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            encode_block_kernel<SRC_WORDS><<<grid, 1024, smem, st>>>(n, k, B, vec, in, nullptr, out);
+        } else {
+            PC_CUDA(cudaFuncSetAttribute(encode_block_kernel<SRC_INFO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            encode_block_kernel<SRC_INFO><<<grid, 1024, smem, st>>>(n, k, B, vec, in, enc_tab, out);
+        }
+        PC_LAUNCH_CHECK();
+        return PC_OK;
     }
     const int Nw = ((1 << n) + 31) >> 5;
     const int threads = 256;

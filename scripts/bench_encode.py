@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from polarcub_b200 import engine
-for n, B in ((10, 1 << 22), (12, 1 << 20), (16, 1 << 16), (20, 1 << 12)):
+for n, B in ((10, 1 << 22), (12, 1 << 20), (16, 1 << 16), (18, 1 << 14), (20, 1 << 12)):
     N = 1 << n
     rng = np.random.default_rng(n)
     fm = np.zeros(N, dtype=np.uint8); fm[rng.permutation(N)[:N // 2]] = 1
