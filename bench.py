@@ -240,7 +240,7 @@ class ScBinaryLarge:
     name = "sc_n2p%s_r0.8_bec0.1" % os.environ.get("PC_BENCH_LARGE_N", "20")
     kernel = "hybrid walk: hy_level_kernel (HBM-streamed upper stages) + sc_decode_kernel<packed> (1024-leaf sub-blocks); batches below 6144 frames: sc_stream_kernel"
     dtype = "f64"
-    default_frames, default_e2e, default_cpu = 16384, 2368, 32
+    default_frames, default_e2e, default_cpu = 16384, 16384, 32
     n = int(os.environ.get("PC_BENCH_LARGE_N", "20"))  # 20 is the BASELINE configuration; smaller values are for profiling runs
     N, K = 1 << n, int(0.8 * (1 << n))
     # stages above 2^13 stream 12 N bytes each + channel ingest 4 N + (N + K)/8 out (fp32 soft-input contract)
@@ -271,7 +271,7 @@ class ScBinaryLarge:
         self.y = torch.empty((B, N), dtype=torch.uint8, device=dev)
         self.info_tx = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
         shifts = torch.arange(32, device=dev, dtype=torch.int32)
-        CH = 8
+        CH = 64
         for c0 in range(0, B, CH):
             c1 = min(B, c0 + CH)
             gen.manual_seed(2020 + 7919 * ((rank * B + c0) // CH))

@@ -100,6 +100,9 @@ struct pc_plan {
     // warp-per-frame encoder (encode.cu): per u word w, 8 words {information-position mask, number of information bits
     // before the word, the five bit-deposit (expand) masks of that mask, frozen-value bits}
     uint32_t *d_enc_tab = nullptr;       // [ceil(N/32)][8]
+    // block encoder (2^16 <= N <= 2^20): the same table as [2][32][N/1024] uint4 -- half h of the entry of word t * 32 + j
+    // at ((h * 32 + j) * N/1024 + t), so that the threads t of a warp read consecutive 16-byte chunks
+    uint32_t *d_enc_tab_t = nullptr;
 };
 
 // ---- device helpers ---------------------------------------------------------------------------------

@@ -208,7 +208,9 @@ static int launch_warp_encoder(int n, int k, int64_t B, const uint32_t *in, cons
 // ---- 2^16 <= N <= 2^20: 2^(n-10) threads per frame, 1024 / 2^(n-10) frames per 1024-thread block, the block's 2^20 bits in
 // 128 KB of shared memory.  Word index bits: [T (top 5) | M (n-10)] = [thread t (n-10) | j (5)].
 //  A. thread t owns the 32 consecutive words t * 32 + j in registers: u words by the same bit-deposit as the warp kernel (or
-//     the packed input words), butterfly strides inside the words, between registers (word bits 0-4) and between lanes
+//     the packed input words); the frame's packed input is first staged in shared memory with coalesced loads and the
+//     deposit table is read in a transposed layout (plan->d_enc_tab_t), because per-thread 128-byte windows cost one LSU
+//     wavefront per lane; butterfly strides inside the words, between registers (word bits 0-4) and between lanes
 //     (word bits 5 .. n-11, shuffles); the words go to shared memory;
 //  B. thread M re-reads the 32 words (T, M), T = 0..31: butterfly over the top five word bits between registers, then the
 //     bit reversal x_ref[i] = x_nat[rev_n(i)] -- for every M a 32 x 32 bit-matrix transpose (in registers) whose rows land
@@ -216,7 +218,7 @@ static int launch_warp_encoder(int n, int k, int64_t B, const uint32_t *in, cons
 // Shared-memory word w lives at w ^ ((w >> 5) & 31): phase A's stride-32 stores, phase B's loads and the bit-reversed row
 // stores are all bank-conflict free.
 template <int SRC>
-__global__ void __launch_bounds__(1024, 1) encode_block_kernel(int n, int k, int64_t B, bool vec, const uint32_t *__restrict__ in,
+__global__ void __launch_bounds__(1024, 1) encode_block_kernel(int n, int k, int64_t B, const uint32_t *__restrict__ in,
                                                                const uint32_t *__restrict__ tab, uint32_t *__restrict__ out) {
     extern __shared__ uint32_t sm_words[];
     const int lg = n - 10, tpf = 1 << lg, Nw = 32 << lg, fpb = 1024 >> lg;
@@ -229,20 +231,21 @@ __global__ void __launch_bounds__(1024, 1) encode_block_kernel(int n, int k, int
         const bool live = f < B;
         uint32_t x[32];
         // ---- A ---------------------------------------------------------------------------------------
-        if (!live) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = 0u;
-        } else if (SRC == SRC_INFO) {
-            const uint32_t *info = in + f * Kw;
-            const uint4 *tp = (const uint4 *)(tab + (size_t)t * 256);
+        // the frame's packed input goes through shared memory first, so that the global reads are coalesced (a thread's own
+        // 32 words / information window are 128 bytes apart from its neighbour's)
+        if (SRC == SRC_INFO) {
+            const uint32_t *info = in + (live ? f : 0) * Kw;
+            for (int i = t; i < Kw; i += tpf) w[i] = __ldg(info + i);
+            __syncthreads();
+            const uint4 *tp = (const uint4 *)tab + t;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const uint4 t0 = __ldg(tp + 2 * j), t1 = __ldg(tp + 2 * j + 1);
+                const uint4 t0 = __ldg(tp + (size_t)j * tpf), t1 = __ldg(tp + (size_t)(32 + j) * tpf);
                 const uint32_t m = t0.x, before = t0.y;
                 uint32_t v = 0;
                 if (m) {
                     const int wi = (int)(before >> 5), sh = (int)(before & 31);
-                    const uint32_t lo = __ldg(info + wi), hi = (sh && wi + 1 < Kw) ? __ldg(info + wi + 1) : 0u;
+                    const uint32_t lo = w[wi], hi = (sh && wi + 1 < Kw) ? w[wi + 1] : 0u;
                     v = __funnelshift_r(lo, hi, sh);
                     uint32_t tt;
                     tt = v << 16, v = (v & ~t1.z) | (tt & t1.z);
@@ -254,18 +257,13 @@ __global__ void __launch_bounds__(1024, 1) encode_block_kernel(int n, int k, int
                 }
                 x[j] = v | t1.w;
             }
+            __syncthreads();  // every information window has been read: the buffer now takes the u words
         } else {
-            const uint32_t *xin = in + f * Nw + t * 32;
-            if (vec) {
+            const uint32_t *xin = in + (live ? f : 0) * Nw;
+            for (int i = t; i < Nw; i += tpf) w[i ^ ((i >> 5) & 31)] = __ldg(xin + i);
+            __syncthreads();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const uint4 q = __ldg((const uint4 *)(xin + j));
-                    x[j] = q.x, x[j + 1] = q.y, x[j + 2] = q.z, x[j + 3] = q.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = __ldg(xin + j);
-            }
+            for (int j = 0; j < 32; ++j) x[j] = w[(t * 32 + j) ^ lane];
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -367,25 +365,25 @@ __global__ void __launch_bounds__(256) encode_qary_kernel(int q, int n, int k, i
 }
 
 static int launch_bits(int src_kind, int n, int k, int64_t B, const uint32_t *in, const int32_t *src,
-                       const uint32_t *frozen_words, uint32_t *out, cudaStream_t st, const uint32_t *enc_tab = nullptr) {
+                       const uint32_t *frozen_words, uint32_t *out, cudaStream_t st, const uint32_t *enc_tab = nullptr,
+                       const uint32_t *enc_tab_t = nullptr) {
     if (B == 0) return PC_OK;
     const char *ev = getenv("PC_ENCODE_CTA");  // 1: keep the frame-per-CTA kernel (tests compare the two)
     if (n >= 10 && n <= 15 && !(ev && *ev == '1') && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0) {
         if (src_kind == SRC_WORDS) return launch_warp_encoder<SRC_WORDS>(n, k, B, in, nullptr, out, st);
         if (enc_tab) return launch_warp_encoder<SRC_INFO>(n, k, B, in, enc_tab, out, st);
     }
-    if (n >= 16 && n <= 20 && !(ev && *ev == '1') && (src_kind == SRC_WORDS || enc_tab)) {
+    if (n >= 16 && n <= 20 && !(ev && *ev == '1') && (src_kind == SRC_WORDS || enc_tab_t)) {
         const int fpb = 1024 >> (n - 10);
         const int64_t want = (B + fpb - 1) / fpb;
         const int grid = (int)(want < (int64_t)num_sms() ? want : (int64_t)num_sms());
         const int smem = 128 * 1024;
-        const bool vec = ((uintptr_t)in & 15) == 0;
         if (src_kind == SRC_WORDS) {
             PC_CUDA(cudaFuncSetAttribute(encode_block_kernel<SRC_WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            encode_block_kernel<SRC_WORDS><<<grid, 1024, smem, st>>>(n, k, B, vec, in, nullptr, out);
+            encode_block_kernel<SRC_WORDS><<<grid, 1024, smem, st>>>(n, k, B, in, nullptr, out);
         } else {
             PC_CUDA(cudaFuncSetAttribute(encode_block_kernel<SRC_INFO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            encode_block_kernel<SRC_INFO><<<grid, 1024, smem, st>>>(n, k, B, vec, in, enc_tab, out);
+            encode_block_kernel<SRC_INFO><<<grid, 1024, smem, st>>>(n, k, B, in, enc_tab_t, out);
         }
         PC_LAUNCH_CHECK();
         return PC_OK;
@@ -420,7 +418,7 @@ int pc_encode_bits(const pc_plan *plan, const uint32_t *d_info_packed, uint32_t 
     PC_REQUIRE(plan && plan->q == 2, "binary plan required");
     PC_REQUIRE(B >= 0 && (d_cw_packed || B == 0) && (d_info_packed || plan->k == 0 || B == 0), "null buffer");
     return pc::launch_bits(pc::SRC_INFO, plan->n, plan->k, B, d_info_packed, plan->d_src, plan->d_frozen_words,
-                           d_cw_packed, (cudaStream_t)stream, plan->d_enc_tab);
+                           d_cw_packed, (cudaStream_t)stream, plan->d_enc_tab, plan->d_enc_tab_t);
 }
 
 int pc_polar_transform_bits(int n, const uint32_t *d_cw_packed, uint32_t *d_u_packed, int64_t B, void *stream) {

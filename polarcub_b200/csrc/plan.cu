@@ -181,6 +181,16 @@ int pc_plan_create(int q, int n, const uint8_t *h_frozen_mask, const uint8_t *h_
     UP(p->d_frozen_mask, p->frozen_mask, uint8_t);
     UP(p->d_frozen_vals, p->frozen_vals, uint8_t);
     UP(p->d_enc_tab, enc_tab, uint32_t);
+    if (q == 2 && n >= 16 && n <= 20) {
+        const int G = N >> 10;
+        std::vector<uint32_t> tt(enc_tab.size());
+        for (int t = 0; t < G; ++t)
+            for (int j = 0; j < 32; ++j)
+                for (int h = 0; h < 2; ++h)
+                    for (int c = 0; c < 4; ++c)
+                        tt[((size_t)(h * 32 + j) * G + t) * 4 + c] = enc_tab[(size_t)(t * 32 + j) * 8 + 4 * h + c];
+        UP(p->d_enc_tab_t, tt, uint32_t);
+    }
 #undef UP
     *out = p;
     return PC_OK;
@@ -198,6 +208,7 @@ void pc_plan_destroy(pc_plan *p) {
     cudaFree(p->d_src);
     cudaFree(p->d_frozen_words);
     cudaFree(p->d_enc_tab);
+    cudaFree(p->d_enc_tab_t);
     cudaFree(p->d_frozen_mask);
     cudaFree(p->d_frozen_vals);
     delete p;

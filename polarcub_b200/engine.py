@@ -387,6 +387,17 @@ def sc_decode_symbols_host(plan, y_host, table, cw_host, info_host, chunk=None):
     info_host int32 [B, Kw] (pinned), copies overlapped with decoding."""
     _pinned(y_host, "y_host"), _pinned(cw_host, "cw_host"), _pinned(info_host, "info_host")
     B = y_host.shape[0]
+    if chunk is None and plan.n > 16 and B >= 6144:
+        # large blocks (hybrid decoder): the workspace -- 5.4 MB per 2^20 frame -- is the binding resource, not the copies:
+        # batches of up to 16384 frames go one at a time on the caller's stream and share its workspace
+        y = _Slots(plan, "scsym_big").get(0, "y", (min(B, 16384), plan.N), torch.uint8)
+        for lo in range(0, B, y.shape[0]):
+            hi = min(B, lo + y.shape[0])
+            y[:hi - lo].copy_(y_host[lo:hi], non_blocking=True)
+            cw, info = sc_decode_symbols(plan, y[:hi - lo], table)
+            cw_host[lo:hi].copy_(cw, non_blocking=True)
+            info_host[lo:hi].copy_(info, non_blocking=True)
+        return
     chunk = chunk or default_host_chunk(B, plan.N, sc_wave_frames(plan))
     sl = _Slots(plan, "scsym")
 
