@@ -235,7 +235,19 @@ __global__ void __launch_bounds__(1024, 1) encode_block_kernel(int n, int k, int
         // 32 words / information window are 128 bytes apart from its neighbour's)
         if (SRC == SRC_INFO) {
             const uint32_t *info = in + (live ? f : 0) * Kw;
-            for (int i = t; i < Kw; i += tpf) w[i] = __ldg(info + i);
+            {   // the next frame of this slot: pull its information words into L2 while this one is encoded
+                const int64_t fn = f + (int64_t)gridDim.x * fpb;
+                if (fn < B && t * 32 < Kw) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + fn * Kw + t * 32));
+            }
+#pragma unroll 1
+            for (int i0 = t; i0 < Kw; i0 += 8 * tpf) {  // eight independent loads in flight per thread
+                uint32_t v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = i0 + u * tpf < Kw ? __ldg(info + i0 + u * tpf) : 0u;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (i0 + u * tpf < Kw) w[i0 + u * tpf] = v[u];
+            }
             __syncthreads();
             const uint4 *tp = (const uint4 *)tab + t;
 #pragma unroll
@@ -260,6 +272,11 @@ __global__ void __launch_bounds__(1024, 1) encode_block_kernel(int n, int k, int
             __syncthreads();  // every information window has been read: the buffer now takes the u words
         } else {
             const uint32_t *xin = in + (live ? f : 0) * Nw;
+            {
+                const int64_t fn = f + (int64_t)gridDim.x * fpb;
+                if (fn < B) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + fn * Nw + t * 32));
+            }
+#pragma unroll 8
             for (int i = t; i < Nw; i += tpf) w[i ^ ((i >> 5) & 31)] = __ldg(xin + i);
             __syncthreads();
 #pragma unroll
