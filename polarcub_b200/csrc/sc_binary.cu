@@ -845,15 +845,24 @@ __global__ void __launch_bounds__(256) hy_level_sym_kernel(int64_t quarter, int6
     out[gid] = node_packed(s_lut[(ma * Y + y0) * Y + y1], s_lut[(mb * Y + y2) * Y + y3], isg != 0, u);
 }
 
-// out[h][f] = node(in[h][f], in[h + size][f]) for h < size; g: decision bit h of the words at xw (element h -> word h / 32)
+// out[h][f] = node(in[h][f], in[h + size][f]) for h < size; g: decision bit h of the words at xw (element h -> word h / 32).
+// Two adjacent frames per thread (Bpad is a multiple of 32): 16-byte loads and stores, twice the bytes in flight per SM.
 __global__ void __launch_bounds__(256) hy_level_kernel(int64_t size, int64_t Bpad, const double *__restrict__ in,
                                                        const uint32_t *__restrict__ xw, int isg, double *__restrict__ out) {
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gid = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
     if (gid >= size * Bpad) return;
     const int64_t h = gid / Bpad, f = gid - h * Bpad;
-    uint32_t u = 0;
-    if (isg) u = (xw[(h >> 5) * Bpad + f] >> (h & 31)) & 1u;
-    out[gid] = node_packed(in[gid], in[gid + size * Bpad], isg != 0, u);
+    uint32_t u0 = 0, u1 = 0;
+    if (isg) {
+        const uint2 uw = *(const uint2 *)(xw + (h >> 5) * Bpad + f);
+        u0 = (uw.x >> (h & 31)) & 1u;
+        u1 = (uw.y >> (h & 31)) & 1u;
+    }
+    const double2 a = *(const double2 *)(in + gid), b = *(const double2 *)(in + gid + size * Bpad);
+    double2 r;
+    r.x = node_packed(a.x, b.x, isg != 0, u0);
+    r.y = node_packed(a.y, b.y, isg != 0, u1);
+    *(double2 *)(out + gid) = r;
 }
 
 // partial sums of a completed plus child: lo[w][f] ^= lo[w + words][f]
@@ -995,7 +1004,7 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
                 hy_level_sym_kernel<<<blocks_of(size * Bp), 256, 0, st>>>(size, Bp, sym, Y, lut, cw_t, i >= N / 2 ? 1 : 0, xw,
                                                                          isg ? 1 : 0, V(lev));
             else
-                hy_level_kernel<<<blocks_of(size * Bp), 256, 0, st>>>(size, Bp, V(lev + 1), xw, isg ? 1 : 0, V(lev));
+                hy_level_kernel<<<blocks_of(size * Bp / 2), 256, 0, st>>>(size, Bp, V(lev + 1), xw, isg ? 1 : 0, V(lev));
             PC_LAUNCH_CHECK();
             return PC_OK;
         };
