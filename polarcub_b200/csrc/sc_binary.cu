@@ -88,17 +88,37 @@ __device__ __forceinline__ double node_packed(double a, double b, bool isg, uint
 // first division.  SSTR / DSTR: element strides (doubles) of the source and destination levels -- SC_THREADS for the
 // shared-memory levels, 32 for the warp's global scratch -- compile-time so that the batch's addresses are immediates.
 // g: the decision bits come from `uw` (one word per 32 elements, pitch Bpad) or, for levels below 32, from `ureg`.
-// F01 (channels with hard output symbols): operands that are hard knowledge or erasures (r = 0 / r = 1 -- every value of a
-// BEC frame) are combined by selection, without the division (sc_arith.cuh: same bits as the general routine).
-template <bool F01>
-__device__ __forceinline__ double node_sel(double a, double b, bool isg, uint32_t u) {
-    if (F01) return isg ? g_packed01(a, b, u) : f_packed01(a, b);
-    return node_packed(a, b, isg, u);
+// Erasure-type frames (every value of the sub-block's input vector is hard knowledge r = 0, an erasure r = 1 or the (0,0)
+// contradiction state -- all a BEC frame can hold): the reference's products, sums and quotients on such pairs are exact
+// and stay in the same four states, so a node update is a selection on the high words -- no division, no branch:
+//   f: (0,0) if either is; erasure if either is; else hard with side sa ^ sb
+//   g: (0,0) if either is; both hard: side sb if sa ^ u == sb, else the (0,0) contradiction; one erased: the other one's
+//      (bit-adjusted) knowledge; both erased: erasure
+// Same decisions as node_packed on these operands (f_packed01 / g_packed01 in sc_arith.cuh spell out the cases).
+__device__ __forceinline__ double node01(double a, double b, bool isg, uint32_t u) {
+    const uint32_t ha = (uint32_t)__double2hiint(a), hb = (uint32_t)__double2hiint(b);
+    const bool ca = (ha & 0x7ff00000u) == 0x7ff00000u, cb = (hb & 0x7ff00000u) == 0x7ff00000u;
+    const bool ea = ha == 0x3ff00000u, eb = hb == 0x3ff00000u;
+    uint32_t r;
+    if (!isg) {
+        r = (ea || eb) ? 0x3ff00000u : ((ha ^ hb) & 0x80000000u);
+    } else {
+        const uint32_t sa = (ha ^ (u << 31)) & 0x80000000u, sb = hb & 0x80000000u;
+        const uint32_t hard = sa != sb ? 0x7ff80000u : sb;
+        r = ea ? (eb ? 0x3ff00000u : sb) : (eb ? sa : hard);
+    }
+    if (ca || cb) r = 0x7ff80000u;
+    return __hiloint2double((int)r, 0);
+}
+__device__ __forceinline__ bool d_is01c(double x) {  // +-0, 1.0 or NaN
+    const uint32_t h = (uint32_t)__double2hiint(x) & 0x7fffffffu;
+    return (h == 0u && __double2loint(x) == 0) || (h == 0x3ff00000u && __double2loint(x) == 0) || x != x;
 }
 
+// F01: `w01` (warp-uniform) selects node01 for the whole batch
 template <int SSTR, int DSTR, bool F01 = false, int BW = 4>
 __device__ __forceinline__ void level_batches(const double *sp, double *dp, int size, bool isg, const uint32_t *uw, int64_t Bpad,
-                                              uint32_t ureg) {
+                                              uint32_t ureg, bool w01 = false) {
     const double *sp2 = sp + (int64_t)size * SSTR;
     const int per_word = size < 32 ? size : 32;
 #pragma unroll 1
@@ -116,8 +136,13 @@ __device__ __forceinline__ void level_batches(const double *sp, double *dp, int 
                 a[u] = sp[u * SSTR];
                 b[u] = sp2[u * SSTR];
             }
+            if (F01 && w01) {
 #pragma unroll
-            for (int u = 0; u < BW; ++u) dp[u * DSTR] = node_sel<F01>(a[u], b[u], isg, (ubw >> (hh + u)) & 1u);
+                for (int u = 0; u < BW; ++u) dp[u * DSTR] = node01(a[u], b[u], isg, (ubw >> (hh + u)) & 1u);
+            } else {
+#pragma unroll
+                for (int u = 0; u < BW; ++u) dp[u * DSTR] = node_packed(a[u], b[u], isg, (ubw >> (hh + u)) & 1u);
+            }
             sp += BW * SSTR;
             sp2 += BW * SSTR;
             dp += BW * DSTR;
@@ -205,6 +230,7 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
         int top_mode = 0;  // lut: 0 while level n-1 is f of the channel pairs (first half), 1 when it is g with x[0, N/2)
 
         int resume = -1;  // R1: a rate-1 node was not hard; the next entry (its first child) continues with f at this level
+        bool w01 = false;  // R1: every value of this group's input vector is +-0, 1 or NaN (set by the first f pass): node01
 
         if (n == 0) {  // no transform: leaf rule on the raw pair (BinaryPolarEncoderDecoder.py:250-252)
             const SchedEntry e = p.sched[0];
@@ -260,9 +286,24 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
                             a[u] = (h0 + u < size) ? sp[(int64_t)u * p.Bpad] : 1.0;
                             b[u] = (h0 + u < size) ? sp2[(int64_t)u * p.Bpad] : 1.0;
                         }
+                        bool fast = false;
+                        if (R1) {
+                            // erasure-type test of the sub-block's input vector: its first f pass sees every element once
+                            bool ok = true;
 #pragma unroll
-                        for (int u = 0; u < BW; ++u)
-                            if (h0 + u < size) dp[(int64_t)(h0 + u) * dstr] = node_sel<R1>(a[u], b[u], isg, (ub >> u) & 1u);
+                            for (int u = 0; u < BW; ++u) ok = ok && d_is01c(a[u]) && d_is01c(b[u]);
+                            fast = __all_sync(0xffffffffu, ok);
+                            if (!isg && i == 0) w01 = (h0 == 0 || w01) && fast;
+                        }
+                        if (fast) {
+#pragma unroll
+                            for (int u = 0; u < BW; ++u)
+                                if (h0 + u < size) dp[(int64_t)(h0 + u) * dstr] = node01(a[u], b[u], isg, (ub >> u) & 1u);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < BW; ++u)
+                                if (h0 + u < size) dp[(int64_t)(h0 + u) * dstr] = node_packed(a[u], b[u], isg, (ub >> u) & 1u);
+                        }
                         sp += BW * p.Bpad;
                         sp2 += BW * p.Bpad;
                     }
@@ -285,7 +326,8 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
                     const double *sp = sv + (SC_THREADS << (lev + 1));
 #pragma unroll 1
                     for (int h = 0; h < size; ++h)
-                        dp[h * SC_THREADS] = node_sel<R1>(sp[h * SC_THREADS], sp[(h + size) * SC_THREADS], isg, (ureg >> h) & 1u);
+                        dp[h * SC_THREADS] = (R1 && w01) ? node01(sp[h * SC_THREADS], sp[(h + size) * SC_THREADS], isg, (ureg >> h) & 1u)
+                                                         : node_packed(sp[h * SC_THREADS], sp[(h + size) * SC_THREADS], isg, (ureg >> h) & 1u);
                     continue;
                 }
                 if (lut && lev == n - 2) {
@@ -319,11 +361,11 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
                     continue;
                 }
                 if (lev > LS)
-                    level_batches<32, 32, R1, R1 ? 16 : 4>(gv + ((int64_t)32 << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
+                    level_batches<32, 32, R1, R1 ? 16 : 4>(gv + ((int64_t)32 << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg, w01);
                 else if (lev == LS)
-                    level_batches<32, SC_THREADS, R1, R1 ? 16 : 4>(gv + ((int64_t)32 << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
+                    level_batches<32, SC_THREADS, R1, R1 ? 16 : 4>(gv + ((int64_t)32 << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg, w01);
                 else
-                    level_batches<SC_THREADS, SC_THREADS, R1>(sv + (SC_THREADS << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg);
+                    level_batches<SC_THREADS, SC_THREADS, R1>(sv + (SC_THREADS << (lev + 1)), dp, size, isg, uw, p.Bpad, ureg, w01);
             }
             // ---- the node itself -----------------------------------------------------------------------
             if (R1 && e.kind == NODE_RATE1) {
