@@ -240,7 +240,7 @@ class ScBinaryLarge:
     name = "sc_n2p%s_r0.8_bec0.1" % os.environ.get("PC_BENCH_LARGE_N", "20")
     kernel = "hybrid walk: hy_level_kernel (HBM-streamed upper stages) + sc_decode_kernel<packed> (1024-leaf sub-blocks); batches below 6144 frames: sc_stream_kernel"
     dtype = "f64"
-    default_frames, default_e2e, default_cpu = 16384, 16384, 32
+    default_frames, default_e2e, default_cpu = 32768, 32768, 32
     n = int(os.environ.get("PC_BENCH_LARGE_N", "20"))  # 20 is the BASELINE configuration; smaller values are for profiling runs
     N, K = 1 << n, int(0.8 * (1 << n))
     # stages above 2^13 stream 12 N bytes each + channel ingest 4 N + (N + K)/8 out (fp32 soft-input contract)

@@ -82,6 +82,10 @@ int pc_polar_transform_bits(int n, const uint32_t *d_cw_packed, uint32_t *d_u_pa
 /* bytes of device scratch the decoders want for a batch of B frames (they accept less and then work in
  * smaller chunks, down to 32 frames; PC_ERR_NOMEM below that) */
 size_t pc_sc_workspace_bytes(const pc_plan *plan, int64_t B, int input_kind);
+/* the same for pc_sc_decode_symbols when the channel table is known: erasure-type tables (every row hard knowledge or an
+ * exact erasure, e.g. makeBEC, BinaryMemorylessDistribution.py:493-499) let the large-block decoder keep one byte per
+ * tree element instead of a float64, so it wants less scratch per frame and takes larger batches */
+size_t pc_sc_workspace_bytes_symbols(const pc_plan *plan, int64_t B, const double *h_table, int Y);
 /* frames one launch of the binary SC decoder keeps resident on the device (all SMs busy); batches and host-pipeline chunks
  * are best sized in whole multiples of it.  No reference counterpart (the reference decodes one frame per call). */
 int64_t pc_sc_wave_frames(const pc_plan *plan);

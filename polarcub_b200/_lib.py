@@ -25,6 +25,7 @@ SIGNATURES = {
     "pc_encode_bits": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "pc_polar_transform_bits": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "pc_sc_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int]),
+    "pc_sc_workspace_bytes_symbols": (c_size_t, [c_void_p, c_int64, c_void_p, c_int]),
     "pc_sc_wave_frames": (c_int64, [c_void_p]),
     "pc_scl_wave_frames": (c_int64, [c_void_p, c_int]),
     "pc_sc_decode_probs": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

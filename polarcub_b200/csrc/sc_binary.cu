@@ -47,6 +47,7 @@ struct ScParams {
     const SchedEntry *sched;
     const uint32_t *r0_words;
     const void *in_t;   // [N][Bpad] uint8 symbols or double2 probability pairs, natural (bit-reversed) order
+    int in8;            // packed input (hybrid, erasure-type channels): in_t holds one state code per element (state_double)
     double *vals;       // [warps][N - 2^(LS+1)][32] scratch for levels > LS
     uint32_t *cw_t;     // [Nw][Bpad] natural-order codeword words (also the partial-sum store)
     uint32_t *info_t;   // [Kw][Bpad]
@@ -95,6 +96,32 @@ __device__ __forceinline__ double node_packed(double a, double b, bool isg, uint
 //   g: (0,0) if either is; both hard: side sb if sa ^ u == sb, else the (0,0) contradiction; one erased: the other one's
 //      (bit-adjusted) knowledge; both erased: erasure
 // Same decisions as node_packed on these operands (f_packed01 / g_packed01 in sc_arith.cuh spell out the cases).
+// One-byte state codes of the hybrid decoder's upper stages: bit 0 side, bit 1 erasure, bit 2 contradiction.
+__device__ __forceinline__ double state_double(uint32_t c) {
+    return __hiloint2double((int)(((c & 1u) << 31) | ((c & 2u) ? 0x3ff00000u : 0u) | ((c & 4u) ? 0x7ff80000u : 0u)), 0);
+}
+__device__ __forceinline__ uint32_t state_code(double v) {
+    if (v != v) return 4u;
+    return d_abs(v) == 1.0 ? 2u : d_sign(v);
+}
+// f / g on four frames at once (one code per byte), the same case table as node01
+__device__ __forceinline__ uint32_t f8(uint32_t a, uint32_t b) {
+    const uint32_t o = a | b;
+    const uint32_t c = o & 0x04040404u;
+    const uint32_t e = (o & 0x02020202u) & ~(c >> 1);
+    const uint32_t s = ((a ^ b) & 0x01010101u) & ~(e >> 1) & ~(c >> 2);
+    return c | e | s;
+}
+__device__ __forceinline__ uint32_t g8(uint32_t a, uint32_t b, uint32_t u) {  // u: the decision bit in bit 0 of each byte
+    const uint32_t m = 0x01010101u;
+    const uint32_t ea = (a >> 1) & m, eb = (b >> 1) & m;
+    const uint32_t sa = (a ^ u) & m, sb = b & m;
+    const uint32_t c = ((((a | b) >> 2) & m) | (~(ea | eb) & (sa ^ sb))) & m;
+    const uint32_t e = ea & eb & ~c;
+    const uint32_t s = ((eb & sa) | (~eb & sb)) & m & ~c & ~e;
+    return (c << 2) | (e << 1) | s;
+}
+
 __device__ __forceinline__ double node01(double a, double b, bool isg, uint32_t u) {
     const uint32_t ha = (uint32_t)__double2hiint(a), hb = (uint32_t)__double2hiint(b);
     const bool ca = (ha & 0x7ff00000u) == 0x7ff00000u, cb = (hb & 0x7ff00000u) == 0x7ff00000u;
@@ -283,8 +310,14 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
                         double a[BW], b[BW];
 #pragma unroll
                         for (int u = 0; u < BW; ++u) {
-                            a[u] = (h0 + u < size) ? sp[(int64_t)u * p.Bpad] : 1.0;
-                            b[u] = (h0 + u < size) ? sp2[(int64_t)u * p.Bpad] : 1.0;
+                            if (R1 && p.in8) {
+                                const uint8_t *s8 = (const uint8_t *)p.in_t + col + (int64_t)(h0 + u) * p.Bpad;
+                                a[u] = (h0 + u < size) ? state_double(s8[0]) : 1.0;
+                                b[u] = (h0 + u < size) ? state_double(s8[(int64_t)size * p.Bpad]) : 1.0;
+                            } else {
+                                a[u] = (h0 + u < size) ? sp[(int64_t)u * p.Bpad] : 1.0;
+                                b[u] = (h0 + u < size) ? sp2[(int64_t)u * p.Bpad] : 1.0;
+                            }
                         }
                         bool fast = false;
                         if (R1) {
@@ -380,7 +413,24 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
                     nstr = lvl_stride(l);
                 }
                 unsigned long long soft = 0ULL;  // OR of the magnitudes: 0 iff every element is +-0
-                if (l < 5) {
+                if (l == n && p.in8) {  // the whole block, one state code per element
+                    const uint8_t *s8 = (const uint8_t *)p.in_t + col;
+#pragma unroll 1
+                    for (int w0 = 0; w0 < (1 << (l - 5)); ++w0) {
+                        uint32_t w = 0;
+#pragma unroll 8
+                        for (int h = 0; h < 32; ++h) {
+                            const uint32_t c = s8[(int64_t)(32 * w0 + h) * p.Bpad];
+                            soft |= c >> 1;
+                            w |= (c & 1u) << h;
+                        }
+                        xw[(int64_t)((i >> 5) + w0) * p.Bpad] = w;
+                    }
+                    if (!__all_sync(0xffffffffu, soft == 0ULL)) {
+                        resume = l - 1;
+                        continue;
+                    }
+                } else if (l < 5) {
                     uint32_t w = 0;
 #pragma unroll 1
                     for (int h = 0; h < (1 << l); ++h) {
@@ -647,7 +697,7 @@ static int64_t sc_pick_chunk(int64_t B, int kind) {
 // Large blocks (and, on request, any block of at least 64 symbols) take the frame-per-CTA streamed decoder:
 // PC_SC_STREAM=1 forces it, PC_SC_STREAM=0 forbids it below the frame-per-lane limit.
 static bool sc_use_hybrid(const pc_plan *plan, int64_t B, int kind);
-static size_t sc_hybrid_workspace_bytes(const pc_plan *plan, int64_t B);
+static size_t sc_hybrid_workspace_bytes(const pc_plan *plan, int64_t B, int et = -1);
 static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, const double *h_table, int Y, uint32_t *d_cw,
                             uint32_t *d_info, void *ws, size_t ws_bytes, cudaStream_t st);
 
@@ -860,7 +910,65 @@ __global__ void hy_lut_kernel(int Y, const HyRootParams tp, double *__restrict__
     if (idx >= 3 * Y * Y) return;
     const int m = idx / (Y * Y), ya = (idx / Y) % Y, yb = idx % Y;
     const double a0 = tp.table[2 * ya], a1 = tp.table[2 * ya + 1], b0 = tp.table[2 * yb], b1 = tp.table[2 * yb + 1];
-    lut[idx] = m == 0 ? f_raw(a0, a1, b0, b1) : g_raw(a0, a1, b0, b1, (uint32_t)(m - 1));
+    const double v = m == 0 ? f_raw(a0, a1, b0, b1) : g_raw(a0, a1, b0, b1, (uint32_t)(m - 1));
+    lut[idx] = v;
+    ((uint8_t *)(lut + 768))[idx] = (uint8_t)state_code(v);  // erasure-type channels: the same table as state codes
+}
+
+// ---- erasure-type channels (every table row is hard knowledge, an exact erasure or (0,0)): every value of the tree is one of
+// four states, so the upper stages keep ONE BYTE per element instead of a float64 and update four frames per 32-bit
+// operation (f8 / g8); 8 x less HBM traffic and workspace than the float64 stages, identical decisions. ----
+
+// level n-2 from the channel symbols, four adjacent frames per thread
+__global__ void __launch_bounds__(256) hy_level_sym8_kernel(int64_t quarter, int64_t Bpad, const uint8_t *__restrict__ sym, int Y,
+                                                            const uint8_t *__restrict__ lut8, const uint32_t *__restrict__ x0,
+                                                            int top_g, const uint32_t *__restrict__ xw, int isg,
+                                                            uint8_t *__restrict__ out) {
+    __shared__ uint8_t s_lut[768];
+    for (int i = threadIdx.x; i < 3 * Y * Y; i += blockDim.x) s_lut[i] = lut8[i];
+    __syncthreads();
+    const int64_t Bq = Bpad >> 2;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= quarter * Bq) return;
+    const int64_t h = gid / Bq, fq = gid - h * Bq, hb = h + quarter, half = 2 * quarter;
+    const uint32_t *s32 = (const uint32_t *)sym;
+    const uint32_t y0 = s32[h * Bq + fq], y1 = s32[(h + half) * Bq + fq], y2 = s32[hb * Bq + fq], y3 = s32[(hb + half) * Bq + fq];
+    uint4 wa = make_uint4(0, 0, 0, 0), wb = wa, wu = wa;
+    if (top_g) {
+        wa = *(const uint4 *)(x0 + (h >> 5) * Bpad + 4 * fq);
+        wb = *(const uint4 *)(x0 + (hb >> 5) * Bpad + 4 * fq);
+    }
+    if (isg) wu = *(const uint4 *)(xw + (h >> 5) * Bpad + 4 * fq);
+    const uint32_t wav[4] = {wa.x, wa.y, wa.z, wa.w}, wbv[4] = {wb.x, wb.y, wb.z, wb.w}, wuv[4] = {wu.x, wu.y, wu.z, wu.w};
+    uint32_t A = 0, Bv = 0, U = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t ma = top_g ? 1u + ((wav[j] >> (h & 31)) & 1u) : 0u, mb = top_g ? 1u + ((wbv[j] >> (hb & 31)) & 1u) : 0u;
+        A |= (uint32_t)s_lut[(ma * Y + ((y0 >> (8 * j)) & 255u)) * Y + ((y1 >> (8 * j)) & 255u)] << (8 * j);
+        Bv |= (uint32_t)s_lut[(mb * Y + ((y2 >> (8 * j)) & 255u)) * Y + ((y3 >> (8 * j)) & 255u)] << (8 * j);
+        U |= ((wuv[j] >> (h & 31)) & 1u) << (8 * j);
+    }
+    ((uint32_t *)out)[gid] = isg ? g8(A, Bv, U) : f8(A, Bv);
+}
+
+// out[h][f] = node(in[h][f], in[h + size][f]): a thread owns 32 consecutive elements (one word of decision bits) of four
+// adjacent frames
+__global__ void __launch_bounds__(256) hy_level8_kernel(int64_t size, int64_t Bpad, const uint8_t *__restrict__ in,
+                                                        const uint32_t *__restrict__ xw, int isg, uint8_t *__restrict__ out) {
+    const int64_t Bq = Bpad >> 2;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size >> 5) * Bq) return;
+    const int64_t hb = gid / Bq, fq = gid - hb * Bq;
+    const uint32_t *a = (const uint32_t *)in + hb * 32 * Bq + fq, *b = a + size * Bq;
+    uint32_t *o = (uint32_t *)out + hb * 32 * Bq + fq;
+    uint4 wu = make_uint4(0, 0, 0, 0);
+    if (isg) wu = *(const uint4 *)(xw + hb * Bpad + 4 * fq);
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        const uint32_t av = a[k * Bq], bv = b[k * Bq];
+        const uint32_t u = ((wu.x >> k) & 1u) | (((wu.y >> k) & 1u) << 8) | (((wu.z >> k) & 1u) << 16) | (((wu.w >> k) & 1u) << 24);
+        o[k * Bq] = isg ? g8(av, bv, u) : f8(av, bv);
+    }
 }
 
 // out[h][f], h < quarter = N/4: node(L[h], L[h + quarter]) with L[e] = lut[mode(e)][sym[e]][sym[e + N/2]];
@@ -938,13 +1046,29 @@ struct HyLayout {
     size_t off_sym, off_cw, off_u, off_lut, off_lev[32], off_sub, sub_bytes, total;
 };
 
-static int64_t hy_frames_cap() {
+static int64_t hy_frames_cap(bool et = false) {
     const char *s = getenv("PC_SC_HYBRID_FRAMES");
-    const int64_t v = s && *s ? atoll(s) : 16384;  // ~5.4 MB of workspace per 2^20-symbol frame
+    // ~5.4 MB of workspace per 2^20-symbol frame; erasure-type channels (one byte per element): ~1.9 MB, and one
+    // resident wave of the sub-block kernel (256 frames per SM) is the natural batch
+    const int64_t v = s && *s ? atoll(s) : (et ? (int64_t)num_sms() * SC_THREADS : 16384);
     return v >= 32 ? round_up(v, 32) : 32;
 }
 
-static HyLayout hy_layout(const pc_plan *plan, HybridTables *T, int64_t chunk) {
+// erasure-type channel table: every row is hard knowledge, an exact erasure, or (0,0)
+static bool hy_erasure_type(const double *h_table, int Y) {
+    if (const char *s = getenv("PC_SC_HY8"))
+        if (atoi(s) == 0) return false;
+    bool any_hard = false;
+    for (int y = 0; y < Y; ++y) {
+        const double p0 = h_table[2 * y], p1 = h_table[2 * y + 1];
+        const bool hard = (p0 == 0.0) != (p1 == 0.0);
+        any_hard = any_hard || hard;
+        if (!(hard || p0 == p1)) return false;
+    }
+    return any_hard;
+}
+
+static HyLayout hy_layout(const pc_plan *plan, HybridTables *T, int64_t chunk, bool et = false) {
     HyLayout L{};
     const int64_t N = plan->N, Nw = N >> 5;
     L.chunk = chunk;
@@ -957,10 +1081,10 @@ static HyLayout hy_layout(const pc_plan *plan, HybridTables *T, int64_t chunk) {
     L.off_u = o;  // [chunk][Nw] reference-order codeword, then its transform, for the information gather
     o += align256((size_t)2 * Nw * L.Bpad * 4);
     L.off_lut = o;
-    o += align256(768 * 8);
+    o += align256(768 * 8 + 768);  // float64 table, then the same table as state codes
     for (int l = HY_L0; l < plan->n - 1; ++l) {  // level n-1 is looked up from the symbols, never stored
         L.off_lev[l] = o;
-        o += align256(((size_t)1 << l) * L.Bpad * 8);
+        o += align256(((size_t)1 << l) * L.Bpad * (et ? 1 : 8));
     }
     L.off_sub = o;
     size_t sb = 256;
@@ -986,21 +1110,33 @@ static bool sc_use_hybrid(const pc_plan *plan, int64_t B, int kind) {
 
 extern "C" int pc_polar_transform_bits(int n, const uint32_t *d_cw_packed, uint32_t *d_u_packed, int64_t B, void *stream);
 
-static size_t sc_hybrid_workspace_bytes(const pc_plan *plan, int64_t B) {
+// et: 1 erasure-type table (byte states), 0 float64 states, -1 table unknown (the larger of the two)
+static size_t sc_hybrid_workspace_bytes(const pc_plan *plan, int64_t B, int et) {
     HybridTables *T = hybrid_tables(plan);
-    int64_t chunk = round_up(B, 32);
-    if (chunk > hy_frames_cap()) chunk = hy_frames_cap();
-    return hy_layout(plan, T, chunk).total;
+    size_t need = 0;
+    for (int e = 0; e < 2; ++e) {
+        if (et >= 0 && et != e) continue;
+        int64_t chunk = round_up(B, 32);
+        if (chunk > hy_frames_cap(e != 0)) chunk = hy_frames_cap(e != 0);
+        const size_t b = hy_layout(plan, T, chunk, e != 0).total;
+        if (b > need) need = b;
+    }
+    return need;
 }
 
 static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, const double *h_table, int Y, uint32_t *d_cw,
                             uint32_t *d_info, void *ws, size_t ws_bytes, cudaStream_t st) {
     HybridTables *T = hybrid_tables(plan);
     if (!T) return PC_ERR_CUDA;
+    // rate-1 shortcut: only channels with a hard output symbol (a table row with exactly one zero) can produce r = 0
+    bool r1 = false;
+    for (int y = 0; y < Y; ++y) r1 = r1 || ((h_table[2 * y] == 0.0) != (h_table[2 * y + 1] == 0.0));
+    if (const char *s = getenv("PC_SC_R1")) r1 = r1 && atoi(s) != 0;
+    const bool et = r1 && hy_erasure_type(h_table, Y);  // byte states are read by the R1 variant of the sub-block kernel
     int64_t chunk = round_up(B, 32);
-    if (chunk > hy_frames_cap()) chunk = hy_frames_cap();
-    while (chunk > 32 && hy_layout(plan, T, chunk).total > ws_bytes) chunk = round_up(chunk / 2, 32);
-    const HyLayout L = hy_layout(plan, T, chunk);
+    if (chunk > hy_frames_cap(et)) chunk = hy_frames_cap(et);
+    while (chunk > 32 && hy_layout(plan, T, chunk, et).total > ws_bytes) chunk = round_up(chunk / 2, 32);
+    const HyLayout L = hy_layout(plan, T, chunk, et);
     if (L.total > ws_bytes) {
         set_error("workspace too small: %zu bytes given, %zu needed for a 32-frame chunk", ws_bytes, L.total);
         return PC_ERR_NOMEM;
@@ -1011,15 +1147,12 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
     uint32_t *cw_t = (uint32_t *)(base + L.off_cw);
     uint32_t *cw_ref = (uint32_t *)(base + L.off_u), *u_ref = cw_ref + (size_t)Nw * L.Bpad;
     auto V = [&](int l) -> double * { return (double *)(base + L.off_lev[l]); };
+    auto V8 = [&](int l) -> uint8_t * { return (uint8_t *)(base + L.off_lev[l]); };
     HyRootParams tp{};
     for (int i = 0; i < 32; ++i) tp.table[i] = i < 2 * Y ? h_table[i] : 0.0;
     const size_t smem = (size_t)SMEM_VALS * SC_THREADS * sizeof(double);
     PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<SC_INPUT_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<SC_INPUT_PACKED, MODE_DECODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // rate-1 shortcut: only channels with a hard output symbol (a table row with exactly one zero) can produce r = 0
-    bool r1 = false;
-    for (int y = 0; y < Y; ++y) r1 = r1 || ((h_table[2 * y] == 0.0) != (h_table[2 * y + 1] == 0.0));
-    if (const char *s = getenv("PC_SC_R1")) r1 = r1 && atoi(s) != 0;
     ProfScope prof_scope(st);  // the whole walk is the measured unit
     double *lut = (double *)(base + L.off_lut);
     hy_lut_kernel<<<3, 256, 0, st>>>(Y, tp, lut);
@@ -1042,7 +1175,12 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
             const int64_t size = (int64_t)1 << lev;
             const uint32_t *xw = isg ? cw_t + ((i - size) >> 5) * Bp : cw_t;
             if (lev == n - 1) return PC_OK;  // looked up on demand by the level below
-            if (lev == n - 2)
+            if (et && lev == n - 2)
+                hy_level_sym8_kernel<<<blocks_of(size * Bp / 4), 256, 0, st>>>(size, Bp, sym, Y, (const uint8_t *)(lut + 768), cw_t,
+                                                                              i >= N / 2 ? 1 : 0, xw, isg ? 1 : 0, V8(lev));
+            else if (et)
+                hy_level8_kernel<<<blocks_of((size >> 5) * (Bp / 4)), 256, 0, st>>>(size, Bp, V8(lev + 1), xw, isg ? 1 : 0, V8(lev));
+            else if (lev == n - 2)
                 hy_level_sym_kernel<<<blocks_of(size * Bp), 256, 0, st>>>(size, Bp, sym, Y, lut, cw_t, i >= N / 2 ? 1 : 0, xw,
                                                                          isg ? 1 : 0, V(lev));
             else
@@ -1081,6 +1219,7 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
             p.sched = sp->d_sched;
             p.r0_words = sp->d_r0_words;
             p.in_t = V(HY_L0);
+            p.in8 = et ? 1 : 0;
             p.vals = (double *)(base + L.off_sub + SL.off_vals);
             p.cw_t = cw_t + (i >> 5) * Bp;
             p.info_t = (uint32_t *)(base + L.off_sub + SL.off_info);
@@ -1361,6 +1500,17 @@ int64_t pc_sc_wave_frames(const pc_plan *plan) {
     if (!plan) return 0;
     if (plan->n > pc::SC_MAX_N) return pc::sc_stream_wave_frames(plan);
     return (int64_t)pc::sc_grid_max() * pc::SC_THREADS;
+}
+
+size_t pc_sc_workspace_bytes_symbols(const pc_plan *plan, int64_t B, const double *h_table, int Y) {
+    if (!plan || B <= 0) return 256;
+    if (h_table && Y >= 1 && Y <= 16 && pc::sc_use_hybrid(plan, B, PC_INPUT_SYMBOLS))
+    {
+        const char *s = getenv("PC_SC_R1");
+        const bool et = !(s && atoi(s) == 0) && pc::hy_erasure_type(h_table, Y);
+        return pc::sc_hybrid_workspace_bytes(plan, B, et ? 1 : 0);
+    }
+    return pc_sc_workspace_bytes(plan, B, PC_INPUT_SYMBOLS);
 }
 
 size_t pc_sc_workspace_bytes(const pc_plan *plan, int64_t B, int input_kind) {

@@ -134,7 +134,7 @@ def sc_decode_symbols(plan, y, table, out=None):
     B = y.shape[0]
     cw, info = out if out is not None else (torch.empty((B, plan.Nw), dtype=torch.int32, device=y.device),
                                             torch.empty((B, max(plan.Kw, 1)), dtype=torch.int32, device=y.device))
-    need = _lib.lib().pc_sc_workspace_bytes(plan._h, B, INPUT_SYMBOLS)
+    need = _lib.lib().pc_sc_workspace_bytes_symbols(plan._h, B, table.ctypes.data_as(ctypes.c_void_p), table.shape[0])
     ws = plan.workspace(need)
     _lib.check(_lib.lib().pc_sc_decode_symbols(plan._h, _ptr(y), B, table.ctypes.data_as(ctypes.c_void_p),
                                                table.shape[0], _ptr(cw), _ptr(info), _ptr(ws), ws.numel(), _stream()),
@@ -388,9 +388,10 @@ def sc_decode_symbols_host(plan, y_host, table, cw_host, info_host, chunk=None):
     _pinned(y_host, "y_host"), _pinned(cw_host, "cw_host"), _pinned(info_host, "info_host")
     B = y_host.shape[0]
     if chunk is None and plan.n > 16 and B >= 6144:
-        # large blocks (hybrid decoder): the workspace -- 5.4 MB per 2^20 frame -- is the binding resource, not the copies:
-        # batches of up to 16384 frames go one at a time on the caller's stream and share its workspace
-        y = _Slots(plan, "scsym_big").get(0, "y", (min(B, 16384), plan.N), torch.uint8)
+        # large blocks (hybrid decoder): the workspace -- 5.4 MB per 2^20 frame, 1.9 MB over erasure channels -- is the
+        # binding resource, not the copies: batches of up to 32768 frames go one at a time on the caller's stream and
+        # share its workspace
+        y = _Slots(plan, "scsym_big").get(0, "y", (min(B, 32768), plan.N), torch.uint8)
         for lo in range(0, B, y.shape[0]):
             hi = min(B, lo + y.shape[0])
             y[:hi - lo].copy_(y_host[lo:hi], non_blocking=True)

@@ -52,6 +52,11 @@ def _channel(kind, cw, rng):
         p = 0.04
         tab = np.array([[0.5 * (1 - p), 0.0], [0.0, 0.5 * (1 - p)], [0.5 * p, 0.5 * p]])
         return tab, np.where(rng.random((B, N)) < p, 2, cw).astype(np.uint8)
+    if kind == "bec_soft":  # hard, erased AND soft outputs: rate-1 shortcut without the byte-state upper stages
+        tab = np.array([[0.30, 0.0], [0.0, 0.30], [0.05, 0.05], [0.12, 0.03], [0.03, 0.12]])
+        r = rng.random((B, N))
+        y = np.where(r < 0.6, cw, np.where(r < 0.7, 2, np.where(r < 0.97, 3 + cw, 4 - cw)))
+        return tab, y.astype(np.uint8)
     if kind == "bec_lossy":  # contradictions: (0,0) states appear
         p = 0.3
         tab = np.array([[0.5 * (1 - p), 0.0], [0.0, 0.5 * (1 - p)], [0.5 * p, 0.5 * p]])
@@ -133,7 +138,9 @@ def test_large_block_bec(n, frames):
                                                (15, "blocks", "bec", 2, 40), (17, "bec", "bsc", 1, 6),
                                                # erasure channels take the rate-1 shortcut of the sub-block kernel
                                                (12, "bec", "bec", 1, 64), (13, "bec", "bec_lossy", -1, 40), (14, "random", "bec", 3, 33),
-                                               (12, "bec", "bec_clean", 1, 96), (13, "blocks", "bec_clean", 2, 64)])
+                                               (12, "bec", "bec_clean", 1, 96), (13, "blocks", "bec_clean", 2, 64),
+                                               (12, "bec", "bec_soft", 1, 64), (13, "random", "bec_soft", 4, 40),
+                                               (16, "bec", "bec_lossy", 2, 36)])
 def test_hybrid_decoder_vs_oracle(n, how, kind, seed, B, monkeypatch):
     """The hybrid large-block decoder (element-parallel upper stages through HBM + frame-per-lane 1024-leaf sub-blocks),
     forced for block lengths the other decoders cover too: bit-exact against the oracle and against the other decoders."""
