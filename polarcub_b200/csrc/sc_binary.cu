@@ -47,7 +47,6 @@ struct ScParams {
     const SchedEntry *sched;
     const uint32_t *r0_words;
     const void *in_t;   // [N][Bpad] uint8 symbols or double2 probability pairs, natural (bit-reversed) order
-    int in8;            // packed input (hybrid, erasure-type channels): in_t holds one state code per element (state_double)
     double *vals;       // [warps][N - 2^(LS+1)][32] scratch for levels > LS
     uint32_t *cw_t;     // [Nw][Bpad] natural-order codeword words (also the partial-sum store)
     uint32_t *info_t;   // [Kw][Bpad]
@@ -97,9 +96,6 @@ __device__ __forceinline__ double node_packed(double a, double b, bool isg, uint
 //      (bit-adjusted) knowledge; both erased: erasure
 // Same decisions as node_packed on these operands (f_packed01 / g_packed01 in sc_arith.cuh spell out the cases).
 // One-byte state codes of the hybrid decoder's upper stages: bit 0 side, bit 1 erasure, bit 2 contradiction.
-__device__ __forceinline__ double state_double(uint32_t c) {
-    return __hiloint2double((int)(((c & 1u) << 31) | ((c & 2u) ? 0x3ff00000u : 0u) | ((c & 4u) ? 0x7ff80000u : 0u)), 0);
-}
 __device__ __forceinline__ uint32_t state_code(double v) {
     if (v != v) return 4u;
     return d_abs(v) == 1.0 ? 2u : d_sign(v);
@@ -310,14 +306,8 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
                         double a[BW], b[BW];
 #pragma unroll
                         for (int u = 0; u < BW; ++u) {
-                            if (R1 && p.in8) {
-                                const uint8_t *s8 = (const uint8_t *)p.in_t + col + (int64_t)(h0 + u) * p.Bpad;
-                                a[u] = (h0 + u < size) ? state_double(s8[0]) : 1.0;
-                                b[u] = (h0 + u < size) ? state_double(s8[(int64_t)size * p.Bpad]) : 1.0;
-                            } else {
-                                a[u] = (h0 + u < size) ? sp[(int64_t)u * p.Bpad] : 1.0;
-                                b[u] = (h0 + u < size) ? sp2[(int64_t)u * p.Bpad] : 1.0;
-                            }
+                            a[u] = (h0 + u < size) ? sp[(int64_t)u * p.Bpad] : 1.0;
+                            b[u] = (h0 + u < size) ? sp2[(int64_t)u * p.Bpad] : 1.0;
                         }
                         bool fast = false;
                         if (R1) {
@@ -413,24 +403,7 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
                     nstr = lvl_stride(l);
                 }
                 unsigned long long soft = 0ULL;  // OR of the magnitudes: 0 iff every element is +-0
-                if (l == n && p.in8) {  // the whole block, one state code per element
-                    const uint8_t *s8 = (const uint8_t *)p.in_t + col;
-#pragma unroll 1
-                    for (int w0 = 0; w0 < (1 << (l - 5)); ++w0) {
-                        uint32_t w = 0;
-#pragma unroll 8
-                        for (int h = 0; h < 32; ++h) {
-                            const uint32_t c = s8[(int64_t)(32 * w0 + h) * p.Bpad];
-                            soft |= c >> 1;
-                            w |= (c & 1u) << h;
-                        }
-                        xw[(int64_t)((i >> 5) + w0) * p.Bpad] = w;
-                    }
-                    if (!__all_sync(0xffffffffu, soft == 0ULL)) {
-                        resume = l - 1;
-                        continue;
-                    }
-                } else if (l < 5) {
+                if (l < 5) {
                     uint32_t w = 0;
 #pragma unroll 1
                     for (int h = 0; h < (1 << l); ++h) {
@@ -525,6 +498,179 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
             }
         }
         if ((MODE == MODE_DECODE || MODE == MODE_DUAL) && (icount & 31)) iw[(int64_t)(icount >> 5) * p.Bpad] = infoacc;
+    }
+}
+
+// ---- sub-block decoder on state codes (hybrid decoder, erasure-type channels) ----------------------------------------
+// The same schedule walk as sc_decode_kernel<.., R1> (frame per lane, rate-0 pruning, exact rate-1 shortcut), but a node
+// vector is one BYTE per element, four consecutive elements per 32-bit word, updated four at a time by f8 / g8.  The whole
+// tree below level 9 is 516 bytes per frame and lives in shared memory ([word][thread]); level 9 (128 words per frame) in a
+// per-warp global scratch that stays in L2.  Input: the level-n vector as [2^n / 4][Bpad] words (hy_level8_kernel<PACK4>).
+// Output: the codeword words (partial sums) only -- the hybrid decoder takes the information bits from their transform.
+constexpr int S8_LS = 8;                                  // levels <= S8_LS in shared memory
+constexpr int S8_WORDS = 2 + ((1 << (S8_LS - 1)) - 1);    // level 0, level 1, then 2^(l-2) words for l = 2..S8_LS
+__device__ __forceinline__ uint32_t expand4(uint32_t b) { return (b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21); }
+__device__ __forceinline__ uint32_t signs4(uint32_t w) {  // bit 0 of each byte -> 4 bits
+    const uint32_t x = w & 0x01010101u;
+    return (x | (x >> 7) | (x >> 14) | (x >> 21)) & 15u;
+}
+
+__global__ void __launch_bounds__(SC_THREADS, 1) sc_decode8_kernel(const ScParams p) {
+    extern __shared__ uint32_t sm_w8[];  // [S8_WORDS][SC_THREADS]
+    const int n = p.n, N = 1 << n;
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * (SC_THREADS / 32) + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * (SC_THREADS / 32);
+    const int64_t groups = (p.frames + 31) / 32;
+    uint32_t *sv = sm_w8 + threadIdx.x;
+    uint32_t *gv = (uint32_t *)p.vals + (int64_t)warp_global * (N >> 3) * 32 + lane;  // level n-1: 2^(n-3) words per lane
+    // words of level lev (2 <= lev < n): base pointer and word stride
+    auto lvl_ptr = [&](int lev) -> uint32_t * {
+        return lev > S8_LS ? gv : sv + (lev >= 2 ? (1 + (1 << (lev - 2))) : lev) * SC_THREADS;
+    };
+    auto lvl_stride = [&](int lev) -> int64_t { return lev > S8_LS ? 32 : SC_THREADS; };
+
+#pragma unroll 1
+    for (int64_t grp = warp_global; grp < groups; grp += warps_total) {
+        const int64_t col = grp * 32 + lane;
+        const uint32_t *in_w = (const uint32_t *)p.in_t + col;  // word g of the input at in_w[g * Bpad]
+        uint32_t *xw = p.cw_t + col;
+        uint32_t cwreg = 0;
+        int resume = -1;
+#pragma unroll 1
+        for (int ei = 0; ei < p.n_sched; ++ei) {
+            const SchedEntry e = p.sched[ei];
+            const int i = e.i, l = e.l, top = e.top;
+            const int stop = e.kind == NODE_RATE0 ? l + 1 : l;
+            int lev = i == 0 ? n - 1 : (top >= stop ? top : -1);
+            bool isg = i != 0;
+            if (resume >= 0) {
+                lev = resume;
+                isg = false;
+                resume = -1;
+            }
+#pragma unroll 1
+            for (; lev >= stop; --lev, isg = false) {
+                const int size = 1 << lev;
+                const uint32_t *uw = xw + (int64_t)((i - size) >> 5) * p.Bpad;  // g: decision words of whole-word levels
+                const uint32_t ureg = cwreg >> ((i - size) & 31);               // g: decision bits of levels below 32
+                const uint32_t *sp;
+                int64_t ss;
+                if (lev + 1 == n) {
+                    sp = in_w;
+                    ss = p.Bpad;
+                } else {
+                    sp = lvl_ptr(lev + 1);
+                    ss = lvl_stride(lev + 1);
+                }
+                uint32_t *dp = lvl_ptr(lev);
+                const int64_t ds = lvl_stride(lev);
+                if (lev < 2) {  // the source level is a single word: elements (0,2),(1,3) of level 2 / (0,1) of level 1
+                    const uint32_t a = sp[0];
+                    const uint32_t b = a >> (lev == 1 ? 16 : 8), u = expand4(ureg & 15u);
+                    dp[0] = isg ? g8(a, b, u) : f8(a, b);
+                    continue;
+                }
+                const int nw = size >> 2;
+                const uint32_t *sp2 = sp + (int64_t)nw * ss;
+                if (nw < 8) {
+#pragma unroll 1
+                    for (int w = 0; w < nw; ++w) {
+                        const uint32_t a = sp[w * ss], b = sp2[w * ss], u = expand4((ureg >> (4 * w)) & 15u);
+                        dp[w * ds] = isg ? g8(a, b, u) : f8(a, b);
+                    }
+                    continue;
+                }
+#pragma unroll 1
+                for (int w0 = 0; w0 < nw; w0 += 8) {  // eight words = 32 elements = one word of decision bits
+                    uint32_t ub = 0;
+                    if (isg) ub = size >= 32 ? uw[(int64_t)(w0 >> 3) * p.Bpad] : ureg;
+                    uint32_t a[8], b[8];
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        a[w] = sp[(w0 + w) * ss];
+                        b[w] = sp2[(w0 + w) * ss];
+                    }
+#pragma unroll
+                    for (int w = 0; w < 8; ++w)
+                        dp[(w0 + w) * ds] = isg ? g8(a[w], b[w], expand4((ub >> (4 * w)) & 15u)) : f8(a[w], b[w]);
+                }
+            }
+            // ---- the node itself -----------------------------------------------------------------------
+            if (e.kind == NODE_RATE1) {
+                const uint32_t *np_;
+                int64_t nstr;
+                if (l == n) {
+                    np_ = in_w;
+                    nstr = p.Bpad;
+                } else {
+                    np_ = lvl_ptr(l);
+                    nstr = lvl_stride(l);
+                }
+                uint32_t soft = 0;  // erasure / contradiction bits of any element
+                if (l < 5) {
+                    uint32_t w = 0;
+#pragma unroll 1
+                    for (int q = 0; q < (1 << (l - 2)); ++q) {
+                        const uint32_t v = np_[q * nstr];
+                        soft |= v & 0x06060606u;
+                        w |= signs4(v) << (4 * q);
+                    }
+                    if (!__all_sync(0xffffffffu, soft == 0u)) {
+                        resume = l - 1;
+                        continue;
+                    }
+                    cwreg |= w << (i & 31);
+                } else {
+#pragma unroll 1
+                    for (int w0 = 0; w0 < (1 << (l - 5)); ++w0) {
+                        uint32_t v[8], w = 0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = np_[(int64_t)(8 * w0 + q) * nstr];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            soft |= v[q] & 0x06060606u;
+                            w |= signs4(v[q]) << (4 * q);
+                        }
+                        xw[(int64_t)((i >> 5) + w0) * p.Bpad] = w;  // overwritten by the leaf walk if the node is not hard
+                    }
+                    if (!__all_sync(0xffffffffu, soft == 0u)) {
+                        resume = l - 1;
+                        continue;
+                    }
+                }
+                ei += (int)e.bits;  // skip the sub-tree's entries
+            } else if (e.kind == NODE_INFO) {
+                cwreg |= (sv[0] & 1u) << (i & 31);  // level 0: side bit; erasure (tie) and (0,0) -> 0
+            } else if (l < 5) {
+                cwreg |= e.bits << (i & 31);
+            } else {
+#pragma unroll 1
+                for (int w = 0; w < (1 << (l - 5)); ++w) xw[(int64_t)((i >> 5) + w) * p.Bpad] = p.r0_words[e.bits + w];
+            }
+            // ---- partial sums: x[lo, lo+s) ^= x[lo+s, lo+2s) whenever a plus child completes -----------
+            int lv = l, ii = i;
+            while (lv < 5 && lv < n && ((ii >> lv) & 1)) {
+                const int s = 1 << lv;
+                const int sh = (ii - s) & 31;
+                cwreg ^= ((cwreg >> (sh + s)) & ((1u << s) - 1u)) << sh;
+                ii -= s;
+                ++lv;
+            }
+            const int end = i + (1 << l);
+            if (l < 5 && ((end & 31) == 0 || end == N)) {
+                xw[(int64_t)((end - 1) >> 5) * p.Bpad] = cwreg;
+                cwreg = 0;
+            }
+            while (lv < n && ((ii >> lv) & 1)) {
+                const int s = 1 << lv;
+                uint32_t *lo = xw + (int64_t)((ii - s) >> 5) * p.Bpad;
+#pragma unroll 1
+                for (int w = 0; w < (s >> 5); ++w) lo[(int64_t)w * p.Bpad] ^= lo[(int64_t)(w + (s >> 5)) * p.Bpad];
+                ii -= s;
+                ++lv;
+            }
+        }
     }
 }
 
@@ -952,7 +1098,9 @@ __global__ void __launch_bounds__(256) hy_level_sym8_kernel(int64_t quarter, int
 }
 
 // out[h][f] = node(in[h][f], in[h + size][f]): a thread owns 32 consecutive elements (one word of decision bits) of four
-// adjacent frames
+// adjacent frames.  PACK4 (the level the sub-block kernel reads): the output is [h / 4][f] WORDS of four consecutive elements
+// (a 4 x 4 byte transpose in registers), the sub-block kernel's own packing.
+template <bool PACK4>
 __global__ void __launch_bounds__(256) hy_level8_kernel(int64_t size, int64_t Bpad, const uint8_t *__restrict__ in,
                                                         const uint32_t *__restrict__ xw, int isg, uint8_t *__restrict__ out) {
     const int64_t Bq = Bpad >> 2;
@@ -963,11 +1111,30 @@ __global__ void __launch_bounds__(256) hy_level8_kernel(int64_t size, int64_t Bp
     uint32_t *o = (uint32_t *)out + hb * 32 * Bq + fq;
     uint4 wu = make_uint4(0, 0, 0, 0);
     if (isg) wu = *(const uint4 *)(xw + hb * Bpad + 4 * fq);
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-        const uint32_t av = a[k * Bq], bv = b[k * Bq];
-        const uint32_t u = ((wu.x >> k) & 1u) | (((wu.y >> k) & 1u) << 8) | (((wu.z >> k) & 1u) << 16) | (((wu.w >> k) & 1u) << 24);
-        o[k * Bq] = isg ? g8(av, bv, u) : f8(av, bv);
+#pragma unroll 2
+    for (int k0 = 0; k0 < 32; k0 += 4) {
+        uint32_t r[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = k0 + kk;
+            const uint32_t av = a[k * Bq], bv = b[k * Bq];
+            const uint32_t u = ((wu.x >> k) & 1u) | (((wu.y >> k) & 1u) << 8) | (((wu.z >> k) & 1u) << 16) | (((wu.w >> k) & 1u) << 24);
+            r[kk] = isg ? g8(av, bv, u) : f8(av, bv);
+        }
+        if (PACK4) {
+            // r[e] holds element k0 + e of frames 0..3 (byte j = frame j) -> t[j] holds frame j's elements k0..k0+3
+            const uint32_t lo01 = __byte_perm(r[0], r[1], 0x5140), hi01 = __byte_perm(r[0], r[1], 0x7362);
+            const uint32_t lo23 = __byte_perm(r[2], r[3], 0x5140), hi23 = __byte_perm(r[2], r[3], 0x7362);
+            uint4 t;
+            t.x = __byte_perm(lo01, lo23, 0x5410);
+            t.y = __byte_perm(lo01, lo23, 0x7632);
+            t.z = __byte_perm(hi01, hi23, 0x5410);
+            t.w = __byte_perm(hi01, hi23, 0x7632);
+            *(uint4 *)((uint32_t *)out + (hb * 8 + (k0 >> 2)) * Bpad + 4 * fq) = t;
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) o[(k0 + kk) * Bq] = r[kk];
+        }
     }
 }
 
@@ -1132,7 +1299,7 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
     bool r1 = false;
     for (int y = 0; y < Y; ++y) r1 = r1 || ((h_table[2 * y] == 0.0) != (h_table[2 * y + 1] == 0.0));
     if (const char *s = getenv("PC_SC_R1")) r1 = r1 && atoi(s) != 0;
-    const bool et = r1 && hy_erasure_type(h_table, Y);  // byte states are read by the R1 variant of the sub-block kernel
+    const bool et = r1 && plan->n >= HY_L0 + 3 && hy_erasure_type(h_table, Y);
     int64_t chunk = round_up(B, 32);
     if (chunk > hy_frames_cap(et)) chunk = hy_frames_cap(et);
     while (chunk > 32 && hy_layout(plan, T, chunk, et).total > ws_bytes) chunk = round_up(chunk / 2, 32);
@@ -1153,6 +1320,7 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
     const size_t smem = (size_t)SMEM_VALS * SC_THREADS * sizeof(double);
     PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<SC_INPUT_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PC_CUDA(cudaFuncSetAttribute(sc_decode_kernel<SC_INPUT_PACKED, MODE_DECODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PC_CUDA(cudaFuncSetAttribute(sc_decode8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S8_WORDS * SC_THREADS * 4));
     ProfScope prof_scope(st);  // the whole walk is the measured unit
     double *lut = (double *)(base + L.off_lut);
     hy_lut_kernel<<<3, 256, 0, st>>>(Y, tp, lut);
@@ -1178,8 +1346,10 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
             if (et && lev == n - 2)
                 hy_level_sym8_kernel<<<blocks_of(size * Bp / 4), 256, 0, st>>>(size, Bp, sym, Y, (const uint8_t *)(lut + 768), cw_t,
                                                                               i >= N / 2 ? 1 : 0, xw, isg ? 1 : 0, V8(lev));
+            else if (et && lev == HY_L0)
+                hy_level8_kernel<true><<<blocks_of((size >> 5) * (Bp / 4)), 256, 0, st>>>(size, Bp, V8(lev + 1), xw, isg ? 1 : 0, V8(lev));
             else if (et)
-                hy_level8_kernel<<<blocks_of((size >> 5) * (Bp / 4)), 256, 0, st>>>(size, Bp, V8(lev + 1), xw, isg ? 1 : 0, V8(lev));
+                hy_level8_kernel<false><<<blocks_of((size >> 5) * (Bp / 4)), 256, 0, st>>>(size, Bp, V8(lev + 1), xw, isg ? 1 : 0, V8(lev));
             else if (lev == n - 2)
                 hy_level_sym_kernel<<<blocks_of(size * Bp), 256, 0, st>>>(size, Bp, sym, Y, lut, cw_t, i >= N / 2 ? 1 : 0, xw,
                                                                          isg ? 1 : 0, V(lev));
@@ -1219,13 +1389,18 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
             p.sched = sp->d_sched;
             p.r0_words = sp->d_r0_words;
             p.in_t = V(HY_L0);
-            p.in8 = et ? 1 : 0;
             p.vals = (double *)(base + L.off_sub + SL.off_vals);
             p.cw_t = cw_t + (i >> 5) * Bp;
             p.info_t = (uint32_t *)(base + L.off_sub + SL.off_info);
             const int64_t blocks = (tiles * 32 + SC_THREADS - 1) / SC_THREADS;
             const int grid = (int)(blocks < SL.grid ? blocks : SL.grid);
-            if (r1) {
+            if (et) {
+                p.sched = T->d_sched_r1 + T->r1_off[j];
+                p.n_sched = T->r1_len[j];
+                p.in_t = V8(HY_L0);
+                const int g8 = (int)(blocks < num_sms() ? blocks : num_sms());
+                sc_decode8_kernel<<<g8, SC_THREADS, (size_t)S8_WORDS * SC_THREADS * 4, st>>>(p);
+            } else if (r1) {
                 p.sched = T->d_sched_r1 + T->r1_off[j];
                 p.n_sched = T->r1_len[j];
                 sc_decode_kernel<SC_INPUT_PACKED, MODE_DECODE, true><<<grid, SC_THREADS, smem, st>>>(p);
@@ -1507,7 +1682,7 @@ size_t pc_sc_workspace_bytes_symbols(const pc_plan *plan, int64_t B, const doubl
     if (h_table && Y >= 1 && Y <= 16 && pc::sc_use_hybrid(plan, B, PC_INPUT_SYMBOLS))
     {
         const char *s = getenv("PC_SC_R1");
-        const bool et = !(s && atoi(s) == 0) && pc::hy_erasure_type(h_table, Y);
+        const bool et = !(s && atoi(s) == 0) && plan->n >= pc::HY_L0 + 3 && pc::hy_erasure_type(h_table, Y);
         return pc::sc_hybrid_workspace_bytes(plan, B, et ? 1 : 0);
     }
     return pc_sc_workspace_bytes(plan, B, PC_INPUT_SYMBOLS);
