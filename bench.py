@@ -238,7 +238,9 @@ class ScBinary1024:
 class ScBinaryLarge:
     """C4: large-block binary SC, N=2^20, R=0.8 over BEC(0.1); upper stages streamed through HBM (sc_stream.cu)."""
     name = "sc_n2p%s_r0.8_bec0.1" % os.environ.get("PC_BENCH_LARGE_N", "20")
-    kernel = "hybrid walk: hy_level_kernel (HBM-streamed upper stages) + sc_decode_kernel<packed> (1024-leaf sub-blocks); batches below 6144 frames: sc_stream_kernel"
+    kernel = ("hybrid walk (whole batch = one profiled unit): HBM-streamed upper stages hy_level8_kernel / hy_level_sym8_kernel on one-byte "
+              "state codes (erasure-type channel) + sc_decode8_kernel (1024-leaf sub-blocks, frame per lane, exact rate-1 shortcut); "
+              "other discrete channels: hy_level_kernel + sc_decode_kernel<packed> on float64; batches below 6144 frames: sc_stream_kernel")
     dtype = "f64"
     default_frames, default_e2e, default_cpu = 32768, 32768, 32
     n = int(os.environ.get("PC_BENCH_LARGE_N", "20"))  # 20 is the BASELINE configuration; smaller values are for profiling runs
@@ -753,6 +755,8 @@ def run_ours(args, rank, world, local_rank):
     w.allow_ga = args.construction != "reference"
     B = args.frames or w.default_frames
     Be = min(args.e2e_frames or w.default_e2e, B)
+    if world > 1 and args.workload == "sc2p20" and not args.e2e_frames:
+        Be = min(Be, 8192)  # pinned host staging is per rank: 8 GiB each instead of 32
     w.setup(dev, rank, B, Be)
     torch.cuda.synchronize()
 
