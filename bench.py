@@ -249,6 +249,10 @@ class ScBinaryLarge:
     alg_bytes_frame = 4 * N * (1 + 3 * max(0, n - 13)) + (N + K) // 8
     info_bits = K
     P_BEC = 0.1
+    roofline_note = ("achieved = SURVEY.md 8d's algorithmic bytes (fp32 soft-input contract, stages above 2^13 streamed: 92.5 MB per "
+                     "2^20 frame) / time of the whole hybrid walk (~4,000 launches, one profiled unit).  Over this erasure-type "
+                     "channel the walk keeps ONE BYTE per tree element, so the bytes actually moved are ~45 MB per frame "
+                     "(profiles/r1_h_c4_hybrid_rate1.md); the float64 walk of the same code (PC_SC_HY8=0) reaches 9.8 Gbit/s")
 
     def code(self):
         from polarcub_b200.construction import bec_pe
@@ -820,7 +824,8 @@ def run_ours(args, rank, world, local_rank):
                      "kernel": w.kernel, "kernel_ms_per_launch": k_ms / max(1, k_launches),
                      "kernel_launches": int(k_launches), "kernel_share_of_step": k_ms / ms,
                      "algorithmic_bytes_per_frame": w.alg_bytes_frame, "peak_source": peak_kind,
-                     "note": "float64 SC/SCL decoding is bound by instruction issue and the latency of the per-frame scratch, "
+                     "note": getattr(w, "roofline_note", None) or
+                             "float64 SC/SCL decoding is bound by instruction issue and the latency of the per-frame scratch, "
                              "not by the algorithmic HBM bytes (SURVEY.md 8d); see `issue` / `traffic` and profiles/"},
     }
     ncu = getattr(w, "ncu", None)

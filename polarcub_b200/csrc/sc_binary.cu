@@ -1208,6 +1208,53 @@ __global__ void __launch_bounds__(256) hy_info_kernel(int64_t frames, int k, int
     if (lane == 0) info[wid] = wv;
 }
 
+// The same gather, one thread per u WORD: the word's information bits are compressed to the low end (Hacker's Delight
+// "compress" with the plan's bit-deposit masks, the inverse of the encoder's deposit) and OR-ed into the frame's information
+// words at bit offset `before`.  A block covers 256 consecutive u words = one contiguous bit range of the output, assembled
+// in shared memory; fully covered output words are stored, the two partial ones OR-ed (the output is zeroed first).
+__global__ void __launch_bounds__(256) hy_info_words_kernel(int Nw, int Kw, const uint32_t *__restrict__ tab,
+                                                            const uint32_t *__restrict__ u, uint32_t *__restrict__ info) {
+    __shared__ uint32_t win[264];
+    __shared__ uint32_t s_first, s_end;
+    const int64_t f = blockIdx.x;
+    const int wb = blockIdx.y * 256, w = wb + threadIdx.x;
+    for (int i = threadIdx.x; i < 264; i += 256) win[i] = 0u;
+    uint32_t m = 0, before = 0, x = 0;
+    if (w < Nw) {
+        const uint4 t0 = __ldg((const uint4 *)(tab + (size_t)w * 8)), t1 = __ldg((const uint4 *)(tab + (size_t)w * 8) + 1);
+        m = t0.x, before = t0.y;
+        x = u[f * Nw + w] & m;
+        uint32_t t;
+        t = x & t0.z, x = (x ^ t) | (t >> 1);
+        t = x & t0.w, x = (x ^ t) | (t >> 2);
+        t = x & t1.x, x = (x ^ t) | (t >> 4);
+        t = x & t1.y, x = (x ^ t) | (t >> 8);
+        t = x & t1.z, x = (x ^ t) | (t >> 16);
+    }
+    if (threadIdx.x == 0) s_first = before;
+    const int last = (Nw - wb < 256 ? Nw - wb : 256) - 1;
+    if (threadIdx.x == last) s_end = before + (uint32_t)__popc(m);
+    __syncthreads();
+    const uint32_t base = s_first >> 5;  // first output word this block touches
+    if (m) {
+        const uint32_t rel = before - 32u * base, sh = rel & 31u;
+        atomicOr(&win[rel >> 5], x << sh);
+        if (sh && (x >> (32u - sh))) atomicOr(&win[(rel >> 5) + 1], x >> (32u - sh));
+    }
+    __syncthreads();
+    const uint32_t first = s_first, end = s_end;
+    if (end == first) return;
+    const uint32_t nwords = ((end + 31u) >> 5) - base;
+    uint32_t *o = info + f * Kw + base;
+    for (uint32_t i = threadIdx.x; i < nwords; i += 256) {
+        const bool full = 32u * (base + i) >= first && 32u * (base + i + 1) <= end;
+        if (full)
+            o[i] = win[i];
+        else if (win[i])
+            atomicOr(o + i, win[i]);
+    }
+}
+
 struct HyLayout {
     int64_t chunk, Bpad;
     size_t off_sym, off_cw, off_u, off_lut, off_lev[32], off_sub, sub_bytes, total;
@@ -1428,7 +1475,13 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
             if (Kw > 0) {
                 const int rc = pc_polar_transform_bits(n, d_cw + f0 * Nw, u_ref, frames, st);
                 if (rc) return rc;
-                hy_info_kernel<<<blocks_of(frames * Kw * 32), 256, 0, st>>>(frames, plan->k, Nw, T->d_info_pos, u_ref, d_info + f0 * Kw);
+                if (getenv("PC_HY_INFO_GATHER")) {  // the per-bit gather (kept for comparison)
+                    hy_info_kernel<<<blocks_of(frames * Kw * 32), 256, 0, st>>>(frames, plan->k, Nw, T->d_info_pos, u_ref, d_info + f0 * Kw);
+                } else {
+                    PC_CUDA(cudaMemsetAsync(d_info + f0 * Kw, 0, (size_t)frames * Kw * 4, st));
+                    hy_info_words_kernel<<<dim3((unsigned)frames, (unsigned)((Nw + 255) / 256)), 256, 0, st>>>(Nw, Kw, plan->d_enc_tab, u_ref,
+                                                                                                        d_info + f0 * Kw);
+                }
                 PC_LAUNCH_CHECK();
             }
         }
