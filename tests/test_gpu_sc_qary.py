@@ -94,3 +94,46 @@ def test_qary_symbols_entry_point_matches_probs():
     tab2 = np.vstack([tab, np.full((1, q), 1.0 / q)])
     y2 = np.where(rng.random(cw.shape) < 0.1, q, y).astype(np.uint8)
     np.testing.assert_array_equal(ed.decode_symbols_batch(y2, tab2), ed.decode_batch(tab2[y2]))
+
+
+@pytest.mark.parametrize("q,n,how", [(2, 3, "random"), (3, 3, "random"), (3, 4, "half"), (4, 6, "random"), (3, 11, "bec"),
+                                     (2, 10, "bec"), (3, 7, "tail")])
+def test_qary_symbol_lookup_variant(q, n, how, monkeypatch):
+    """The lookup-table variant of the symbol entry point (level n-1 never stored) against the expanding ingest
+    (PC_QSC_LUT=0), the probability entry point and the oracle; out-of-range symbols behave like the all-ones row."""
+    import polarcub_b200 as pcb
+    N = 1 << n
+    rng = np.random.default_rng(77 + 13 * n + q)
+    if how == "random":
+        fs = set(int(i) for i in rng.permutation(N)[:N // 2])
+    elif how == "half":  # the whole second half frozen: level n-1 is never in its g phase
+        fs = set(range(N // 2, N)) | {0}
+    elif how == "tail":  # only the last quarter carries information
+        fs = set(range(3 * N // 4))
+    else:
+        z = [0.5]
+        for _ in range(n):
+            z = [v for zz in z for v in (2 * zz - zz * zz, zz * zz)]
+        fs = set(int(i) for i in np.argsort(-np.array(z), kind="stable")[:N // 2])
+    ed = pcb.QaryPolarEncoderDecoder(q, N, fs, 1)
+    p = 0.08
+    tab = np.full((q, q), p / (q - 1))
+    np.fill_diagonal(tab, 1.0 - p)
+    B = 70
+    info = rng.integers(0, q, size=(B, ed.k))
+    cw = ed.encode_batch(info)
+    err = rng.random(cw.shape) < p
+    y = np.where(err, (cw + rng.integers(1, q, size=cw.shape)) % q, cw).astype(np.uint8)
+    y[0, : min(N, 5)] = 200  # out of range
+    c1, i1 = ed.decode_symbols_batch(y, tab, return_codeword=True)
+    monkeypatch.setenv("PC_QSC_LUT", "0")
+    c0, i0 = ed.decode_symbols_batch(y, tab, return_codeword=True)
+    monkeypatch.delenv("PC_QSC_LUT")
+    np.testing.assert_array_equal(i1, i0)
+    np.testing.assert_array_equal(c1, c0)
+    xy = tab[np.minimum(y[1:], q - 1)]
+    c2, i2 = ed.decode_batch(xy, return_codeword=True)
+    np.testing.assert_array_equal(i1[1:], i2)
+    np.testing.assert_array_equal(c1[1:], c2)
+    _, oinfo = oracle.q_decode_batch(q, N, ed.frozenMask, np.full((N, q), 1.0 / q), xy[:16])
+    np.testing.assert_array_equal(i1[1:17], oinfo)
