@@ -554,47 +554,47 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sc_decode8_kernel(const ScParam
                 const int size = 1 << lev;
                 const uint32_t *uw = xw + (int64_t)((i - size) >> 5) * p.Bpad;  // g: decision words of whole-word levels
                 const uint32_t ureg = cwreg >> ((i - size) & 31);               // g: decision bits of levels below 32
-                const uint32_t *sp;
-                int64_t ss;
-                if (lev + 1 == n) {
-                    sp = in_w;
-                    ss = p.Bpad;
-                } else {
-                    sp = lvl_ptr(lev + 1);
-                    ss = lvl_stride(lev + 1);
-                }
-                uint32_t *dp = lvl_ptr(lev);
-                const int64_t ds = lvl_stride(lev);
-                if (lev < 2) {  // the source level is a single word: elements (0,2),(1,3) of level 2 / (0,1) of level 1
-                    const uint32_t a = sp[0];
-                    const uint32_t b = a >> (lev == 1 ? 16 : 8), u = expand4(ureg & 15u);
-                    dp[0] = isg ? g8(a, b, u) : f8(a, b);
-                    continue;
-                }
-                const int nw = size >> 2;
-                const uint32_t *sp2 = sp + (int64_t)nw * ss;
-                if (nw < 8) {
-#pragma unroll 1
-                    for (int w = 0; w < nw; ++w) {
-                        const uint32_t a = sp[w * ss], b = sp2[w * ss], u = expand4((ureg >> (4 * w)) & 15u);
-                        dp[w * ds] = isg ? g8(a, b, u) : f8(a, b);
+                // one code path per (source, destination) memory pair, so that shared-memory levels use shared-memory
+                // instructions with compile-time strides: words of level lev from level lev + 1
+                auto run = [&](const uint32_t *sp, const int64_t ss, uint32_t *dp, const int64_t ds) {
+                    if (lev < 2) {  // the source level is a single word: elements (0,2),(1,3) of level 2 / (0,1) of level 1
+                        const uint32_t a = sp[0];
+                        const uint32_t b = a >> (lev == 1 ? 16 : 8), u = expand4(ureg & 15u);
+                        dp[0] = isg ? g8(a, b, u) : f8(a, b);
+                        return;
                     }
-                    continue;
-                }
+                    const int nw = size >> 2;
+                    const uint32_t *sp2 = sp + (int64_t)nw * ss;
+                    if (nw < 8) {
 #pragma unroll 1
-                for (int w0 = 0; w0 < nw; w0 += 8) {  // eight words = 32 elements = one word of decision bits
-                    uint32_t ub = 0;
-                    if (isg) ub = size >= 32 ? uw[(int64_t)(w0 >> 3) * p.Bpad] : ureg;
-                    uint32_t a[8], b[8];
-#pragma unroll
-                    for (int w = 0; w < 8; ++w) {
-                        a[w] = sp[(w0 + w) * ss];
-                        b[w] = sp2[(w0 + w) * ss];
+                        for (int w = 0; w < nw; ++w) {
+                            const uint32_t a = sp[w * ss], b = sp2[w * ss], u = expand4((ureg >> (4 * w)) & 15u);
+                            dp[w * ds] = isg ? g8(a, b, u) : f8(a, b);
+                        }
+                        return;
                     }
+#pragma unroll 1
+                    for (int w0 = 0; w0 < nw; w0 += 8) {  // eight words = 32 elements = one word of decision bits
+                        uint32_t ub = 0;
+                        if (isg) ub = size >= 32 ? uw[(int64_t)(w0 >> 3) * p.Bpad] : ureg;
+                        uint32_t a[8], b[8];
 #pragma unroll
-                    for (int w = 0; w < 8; ++w)
-                        dp[(w0 + w) * ds] = isg ? g8(a[w], b[w], expand4((ub >> (4 * w)) & 15u)) : f8(a[w], b[w]);
-                }
+                        for (int w = 0; w < 8; ++w) {
+                            a[w] = sp[(w0 + w) * ss];
+                            b[w] = sp2[(w0 + w) * ss];
+                        }
+#pragma unroll
+                        for (int w = 0; w < 8; ++w)
+                            dp[(w0 + w) * ds] = isg ? g8(a[w], b[w], expand4((ub >> (4 * w)) & 15u)) : f8(a[w], b[w]);
+                    }
+                };
+                auto soff = [](int l) { return (l >= 2 ? (1 + (1 << (l - 2))) : l) * SC_THREADS; };  // shared-memory word offset of level l
+                if (lev + 1 == n)
+                    run(in_w, p.Bpad, lev > S8_LS ? gv : sv + soff(lev), lev > S8_LS ? 32 : SC_THREADS);
+                else if (lev + 1 > S8_LS)
+                    run(gv, 32, sv + soff(lev), SC_THREADS);
+                else
+                    run(sv + soff(lev + 1), SC_THREADS, sv + soff(lev), SC_THREADS);
             }
             // ---- the node itself -----------------------------------------------------------------------
             if (e.kind == NODE_RATE1) {

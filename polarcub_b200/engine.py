@@ -389,13 +389,28 @@ def sc_decode_symbols_host(plan, y_host, table, cw_host, info_host, chunk=None):
     B = y_host.shape[0]
     if chunk is None and plan.n > 16 and B >= 6144:
         # large blocks (hybrid decoder): the workspace -- 5.4 MB per 2^20 frame, 1.9 MB over erasure channels -- is the
-        # binding resource, not the copies: batches of up to 32768 frames go one at a time on the caller's stream and
-        # share its workspace
-        y = _Slots(plan, "scsym_big").get(0, "y", (min(B, 32768), plan.N), torch.uint8)
-        for lo in range(0, B, y.shape[0]):
-            hi = min(B, lo + y.shape[0])
-            y[:hi - lo].copy_(y_host[lo:hi], non_blocking=True)
-            cw, info = sc_decode_symbols(plan, y[:hi - lo], table)
+        # binding resource, so every batch is decoded on the caller's stream with its workspace; the H2D copy of the next
+        # batch (1 MiB of symbols per 2^20 frame: PCIe time comparable to the decode) runs on a side stream into the other of
+        # two staging slots
+        cb = B if B <= 16384 else 16384
+        sl = _Slots(plan, "scsym_big")
+        cur = torch.cuda.current_stream(plan.device)
+        side = _pipe_streams(plan.device)[0]
+        side.wait_stream(cur)
+        free = [None, None]
+        for j, lo in enumerate(range(0, B, cb)):
+            hi = min(B, lo + cb)
+            y = sl.get(j % 2, "y", (cb, plan.N), torch.uint8)[:hi - lo]
+            with torch.cuda.stream(side):
+                if free[j % 2] is not None:
+                    side.wait_event(free[j % 2])  # the decode that read this slot two batches ago
+                y.copy_(y_host[lo:hi], non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(side)
+            cur.wait_event(copied)
+            cw, info = sc_decode_symbols(plan, y, table)
+            free[j % 2] = torch.cuda.Event()
+            free[j % 2].record(cur)
             cw_host[lo:hi].copy_(cw, non_blocking=True)
             info_host[lo:hi].copy_(info, non_blocking=True)
         return
