@@ -202,3 +202,29 @@ def test_hybrid_large_block_bec_batch(monkeypatch):
     scw, sinfo = ed.decode_symbols_batch(y[:8], tab)
     np.testing.assert_array_equal(scw, dcw[:8])
     np.testing.assert_array_equal(sinfo, dinfo[:8])
+
+
+@pytest.mark.parametrize("kind", ["bec", "bsc", "bec_soft"])
+def test_hybrid_decoder_multi_chunk(kind, monkeypatch):
+    """Batches larger than the hybrid decoder's frame cap are walked chunk by chunk (PC_SC_HYBRID_FRAMES=64 here): the result
+    does not depend on the chunking, for the byte-state, the float64 + rate-1 and the plain float64 walks."""
+    import polarcub_b200 as pcb
+    n, B = 13, 150
+    N = 1 << n
+    rng = np.random.default_rng(515)
+    fs = _frozen(n, N // 2, "bec", rng)
+    ed = pcb.BinaryPolarEncoderDecoder(N, fs, 1)
+    info = rng.integers(0, 2, size=(B, ed.k))
+    cw = ed.encode_batch(info)
+    tab, y = _channel(kind, cw, rng)
+    monkeypatch.setenv("PC_SC_HYBRID", "1")
+    ref_cw, ref_info = ed.decode_symbols_batch(y, tab)
+    monkeypatch.setenv("PC_SC_HYBRID_FRAMES", "64")
+    dcw, dinfo = ed.decode_symbols_batch(y, tab)
+    np.testing.assert_array_equal(dcw, ref_cw)
+    np.testing.assert_array_equal(dinfo, ref_info)
+    monkeypatch.delenv("PC_SC_HYBRID_FRAMES")
+    monkeypatch.setenv("PC_SC_HYBRID", "0")
+    scw, sinfo = ed.decode_symbols_batch(y, tab)
+    np.testing.assert_array_equal(scw, ref_cw)
+    np.testing.assert_array_equal(sinfo, ref_info)
