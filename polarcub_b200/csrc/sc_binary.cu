@@ -949,7 +949,14 @@ static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int
 // which reads its top level straight from the level-HY_L0 vector.  The host walks the top of the tree exactly like the
 // kernel's schedule loop does (g at level ctz, f down, leaf block, partial sums) -- every frame of the batch executes the
 // same sequence.  Versus the frame-per-CTA streamed decoder (sc_stream.cu) the leaf walk is no longer one warp per frame
-// with 1-16 active lanes: throughput is set by how many frames fit in memory (~9.5 MB of float64 state per 2^20 frame).
+// with 1-16 active lanes: throughput is set by how many frames fit in memory (5.4 MB of float64 state per 2^20 frame).
+// Three walks share this host loop:
+//   * float64 states, any discrete channel: hy_level_sym_kernel / hy_level_kernel + sc_decode_kernel<packed>;
+//   * channels with a hard output symbol: the sub-block schedules carry NODE_RATE1 markers (exact rate-1 shortcut,
+//     sc_decode_kernel<packed, decode, R1>), warps whose sub-block input is hard / erased / (0,0) only use node01;
+//   * erasure-type channels (every table row hard knowledge or an exact erasure; n >= 13): one-byte state codes all the
+//     way -- hy_level_sym8_kernel / hy_level8_kernel + sc_decode8_kernel -- 1.9 MB per 2^20 frame, batches of one sub-block
+//     wave.  PC_SC_R1=0 / PC_SC_HY8=0 select the plainer walks (the tests compare all three).
 constexpr int HY_L0 = 10;
 
 struct HybridTables {
