@@ -251,8 +251,12 @@ class ScBinaryLarge:
     P_BEC = 0.1
     roofline_note = ("achieved = SURVEY.md 8d's algorithmic bytes (fp32 soft-input contract, stages above 2^13 streamed: 92.5 MB per "
                      "2^20 frame) / time of the whole hybrid walk (~4,000 launches, one profiled unit).  Over this erasure-type "
-                     "channel the walk keeps ONE BYTE per tree element, so the bytes actually moved are ~45 MB per frame "
-                     "(profiles/r1_h_c4_hybrid_rate1.md); the float64 walk of the same code (PC_SC_HY8=0) reaches 9.8 Gbit/s")
+                     "channel the walk keeps ONE BYTE per tree element where the contract assumes a 4-byte value, so frac can "
+                     "exceed 1; `design` is the traffic of the byte-state layout itself (~37 N bytes per frame: ingest 2 N, "
+                     "level n-2 from the symbols 5 N, eight streamed levels 3 N each, sub-block input 2 N, decision bits / "
+                     "partial sums / codeword and information egress ~4 N).  The float64 walk of the same code (PC_SC_HY8=0) "
+                     "reaches 9.8 Gbit/s (profiles/r1_h_c4_hybrid_rate1.md)")
+    design_bytes_frame = 37 * N
 
     def code(self):
         from polarcub_b200.construction import bec_pe
@@ -828,6 +832,9 @@ def run_ours(args, rank, world, local_rank):
                              "float64 SC/SCL decoding is bound by instruction issue and the latency of the per-frame scratch, "
                              "not by the algorithmic HBM bytes (SURVEY.md 8d); see `issue` / `traffic` and profiles/"},
     }
+    if getattr(w, "design_bytes_frame", None) and k_ms > 0:
+        d_ach = (B * args.steps * w.design_bytes_frame) / (k_ms * 1e-3) / 1e9
+        line["roofline"]["design"] = {"bytes_per_frame": w.design_bytes_frame, "achieved": d_ach, "unit": "GB/s", "frac": d_ach / peak}
     ncu = getattr(w, "ncu", None)
     if ncu and k_ms > 0:
         # figures of the committed `ncu --set full` capture of this kernel (profiles/), scaled to this run's launches:

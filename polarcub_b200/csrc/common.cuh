@@ -78,6 +78,7 @@ struct SchedEntry {
     uint32_t bits;  // rate-0, l < 5: the node codeword (natural order) in the low 2^l bits; l >= 5: word offset into r0_words
 };
 
+int bitrev_words_launch(int n, int64_t B, const uint32_t *in, uint32_t *out, cudaStream_t st);  // encode.cu
 void scl_tables_release(const pc_plan *p);
 void stream_tables_release(const pc_plan *p);
 void trellis_tables_release(const pc_plan *p);

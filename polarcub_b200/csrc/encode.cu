@@ -217,7 +217,8 @@ static int launch_warp_encoder(int n, int k, int64_t B, const uint32_t *in, cons
 //     in the words (31 - rev5(c), rev(M)); the rows are staged in shared memory and copied out coalesced.
 // Shared-memory word w lives at w ^ ((w >> 5) & 31): phase A's stride-32 stores, phase B's loads and the bit-reversed row
 // stores are all bank-conflict free.
-template <int SRC>
+// BFLY = false: the bit-reversal permutation alone (x_ref = B_N x_nat), used by the hybrid decoder's egress.
+template <int SRC, bool BFLY = true>
 __global__ void __launch_bounds__(1024, 1) encode_block_kernel(int n, int k, int64_t B, const uint32_t *__restrict__ in,
                                                                const uint32_t *__restrict__ tab, uint32_t *__restrict__ out) {
     extern __shared__ uint32_t sm_words[];
@@ -282,27 +283,29 @@ __global__ void __launch_bounds__(1024, 1) encode_block_kernel(int n, int k, int
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = w[(t * 32 + j) ^ lane];
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            uint32_t v = x[j];
-            v ^= (v >> 1) & 0x55555555u;
-            v ^= (v >> 2) & 0x33333333u;
-            v ^= (v >> 4) & 0x0f0f0f0fu;
-            v ^= (v >> 8) & 0x00ff00ffu;
-            v ^= (v >> 16) & 0x0000ffffu;
-            x[j] = v;
-        }
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (!(j & d)) x[j] ^= x[j | d];
-#pragma unroll 1
-        for (int d = 1; d < (1 << (n - 15)); d <<= 1) {  // word bits 5 .. n-11 (the lanes); the higher bits belong to phase B
+        if (BFLY) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const uint32_t pv = __shfl_xor_sync(0xffffffffu, x[j], d);
-                x[j] ^= (lane & d) ? 0u : pv;
+                uint32_t v = x[j];
+                v ^= (v >> 1) & 0x55555555u;
+                v ^= (v >> 2) & 0x33333333u;
+                v ^= (v >> 4) & 0x0f0f0f0fu;
+                v ^= (v >> 8) & 0x00ff00ffu;
+                v ^= (v >> 16) & 0x0000ffffu;
+                x[j] = v;
+            }
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (!(j & d)) x[j] ^= x[j | d];
+#pragma unroll 1
+            for (int d = 1; d < (1 << (n - 15)); d <<= 1) {  // word bits 5 .. n-11 (the lanes); the higher bits belong to phase B
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t pv = __shfl_xor_sync(0xffffffffu, x[j], d);
+                    x[j] ^= (lane & d) ? 0u : pv;
+                }
             }
         }
 #pragma unroll
@@ -315,11 +318,13 @@ __global__ void __launch_bounds__(1024, 1) encode_block_kernel(int n, int k, int
             x[T] = w[idx ^ ((idx >> 5) & 31)];
         }
         __syncthreads();
+        if (BFLY) {
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
+            for (int d = 1; d < 32; d <<= 1)
 #pragma unroll
-            for (int T = 0; T < 32; ++T)
-                if (!(T & d)) x[T] ^= x[T | d];
+                for (int T = 0; T < 32; ++T)
+                    if (!(T & d)) x[T] ^= x[T | d];
+        }
         uint32_t A[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) A[c] = x[31 - (int)(__brev((uint32_t)c) >> 27)];
@@ -423,6 +428,20 @@ static int launch_bits(int src_kind, int n, int k, int64_t B, const uint32_t *in
             PC_CUDA(cudaFuncSetAttribute(encode_bits_kernel<SRC_WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         encode_bits_kernel<SRC_WORDS><<<grid, threads, smem, st>>>(n, k, B, tpf, in, src, frozen_words, out);
     }
+    PC_LAUNCH_CHECK();
+    return PC_OK;
+}
+
+// x_ref = B_N x_nat on packed words, [B][N/32] -> [B][N/32], 16 <= n <= 20 (the hybrid decoder's codeword egress)
+int bitrev_words_launch(int n, int64_t B, const uint32_t *in, uint32_t *out, cudaStream_t st) {
+    if (B == 0) return PC_OK;
+    PC_REQUIRE(n >= 16 && n <= 20, "bitrev_words_launch: 16 <= n <= 20");
+    const int fpb = 1024 >> (n - 10);
+    const int64_t want = (B + fpb - 1) / fpb;
+    const int grid = (int)(want < (int64_t)num_sms() ? want : (int64_t)num_sms());
+    const int smem = 128 * 1024;
+    PC_CUDA(cudaFuncSetAttribute(encode_block_kernel<SRC_WORDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    encode_block_kernel<SRC_WORDS, false><<<grid, 1024, smem, st>>>(n, 0, B, in, nullptr, out);
     PC_LAUNCH_CHECK();
     return PC_OK;
 }

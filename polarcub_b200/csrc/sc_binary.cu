@@ -1476,9 +1476,19 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
         // outputs: codeword to the reference order; information = gather of its transform at the information positions
         {
             const int G = 1 << (n - 10);
-            egress_bitrev_kernel<<<dim3((unsigned)tiles, (unsigned)((G + 7) / 8 < 64 ? (G + 7) / 8 : 64)), 256, 0, st>>>(
-                n, frames, Bp, cw_t, d_cw + f0 * Nw);
-            PC_LAUNCH_CHECK();
+            if (n >= 16 && !getenv("PC_HY_EGRESS_GATHER")) {
+                // word transpose to frame rows (coalesced on both sides), then the bit reversal with the block encoder's
+                // shared-memory 32 x 32 bit transposes: the one-pass egress below scatters 4-byte stores G words apart
+                const int jt = (Nw + 255) / 256;
+                egress_kernel<false><<<dim3((unsigned)tiles, (unsigned)(jt < 64 ? jt : 64)), 256, 0, st>>>(n, Nw, frames, Bp, cw_t, cw_ref);
+                PC_LAUNCH_CHECK();
+                const int rc = bitrev_words_launch(n, frames, cw_ref, d_cw + f0 * Nw, st);
+                if (rc) return rc;
+            } else {
+                egress_bitrev_kernel<<<dim3((unsigned)tiles, (unsigned)((G + 7) / 8 < 64 ? (G + 7) / 8 : 64)), 256, 0, st>>>(
+                    n, frames, Bp, cw_t, d_cw + f0 * Nw);
+                PC_LAUNCH_CHECK();
+            }
             if (Kw > 0) {
                 const int rc = pc_polar_transform_bits(n, d_cw + f0 * Nw, u_ref, frames, st);
                 if (rc) return rc;
@@ -1493,7 +1503,6 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
             }
         }
     }
-    (void)cw_ref;
     return PC_OK;
 }
 
