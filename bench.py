@@ -458,8 +458,8 @@ class ScQary2048:
     default_frames, default_e2e, default_cpu = 151552, 151552, 1 << 11
     N, K, n, q = 2048, 1024, 11, 3
     alg_bytes_frame = 25344
-    ncu = {"dram_bytes_per_frame": 0.903e6, "warp_inst_per_frame": 91.5e3, "issue_active_pct": 24.3,
-           "capture": "profiles/r1_f_qsc_ncu_summary.md (prof_qsc_b)"}
+    ncu = {"dram_bytes_per_frame": 0.740e6, "warp_inst_per_frame": 80.8e3, "issue_active_pct": 24.6,
+           "capture": "profiles/r1_f_qsc_ncu_summary.md (prof_qsc_c)"}
     info_bits = 1024 * math.log2(3)
     allow_ga = False
 
