@@ -131,3 +131,55 @@ def test_compute_calls_fail_loudly_without_cuda():
     qd = pcb.QaryPolarEncoderDecoder(3, 8, {0, 1, 2, 4}, 1)
     with pytest.raises(PolarcubError):
         qd.decode_batch(np.full((2, 8, 3), 1.0 / 3))
+
+
+def test_four_state_algebra_matches_the_reference_arithmetic():
+    """The erasure-type fast path (csrc/sc_binary.cu: node01, f8 / g8) rests on one claim: on probability pairs that are hard
+    knowledge, an erasure or the (0,0) contradiction, BinaryMemorylessVectorDistribution's minus / plus transforms followed by
+    the max-normalisation (BinaryMemorylessVectorDistribution.py:15-47, :71-87) are exact in float64 and stay within those four
+    states.  Checked here by running the reference's arithmetic on every operand combination -- normalised states and raw
+    BEC table rows -- next to a Python copy of the kernels' bit logic (bit 0 side, bit 1 erasure, bit 2 contradiction)."""
+    def normalise(p0, p1):
+        m = max(p0, p1)
+        return (p0 / m, p1 / m) if m > 0 else (p0, p1)
+
+    def minus(a, b):
+        return normalise(a[0] * b[0] + a[1] * b[1], a[0] * b[1] + a[1] * b[0])
+
+    def plus(a, b, u):
+        return normalise(a[0] * b[0], a[1] * b[1]) if u == 0 else normalise(a[1] * b[0], a[0] * b[1])
+
+    def f8(a, b):
+        o = a | b
+        c = o & 4
+        e = (o & 2) & ~(c >> 1)
+        s = ((a ^ b) & 1) & ~(e >> 1) & ~(c >> 2)
+        return c | e | s
+
+    def g8(a, b, u):
+        ea, eb = (a >> 1) & 1, (b >> 1) & 1
+        sa, sb = (a ^ u) & 1, b & 1
+        c = ((((a | b) >> 2) & 1) | (~(ea | eb) & (sa ^ sb))) & 1
+        e = ea & eb & ~c & 1
+        s = ((eb & sa) | (~eb & sb)) & 1 & ~c & ~e
+        return (c << 2) | (e << 1) | s
+
+    states = {0: (1.0, 0.0), 1: (0.0, 1.0), 2: (1.0, 1.0), 4: (0.0, 0.0)}
+    code_of = {v: k for k, v in states.items()}
+    for ca, pa in states.items():
+        for cb, pb in states.items():
+            assert code_of[minus(pa, pb)] == f8(ca, cb), (ca, cb)
+            for u in (0, 1):
+                assert code_of[plus(pa, pb, u)] == g8(ca, cb, u), (ca, cb, u)
+    # raw channel rows of makeBEC (BinaryMemorylessDistribution.py:493-499) land in the same states after one transform,
+    # for any erasure probability: the products and sums involve one non-zero term at most, or two equal ones
+    for p in (0.1, 0.35, 0.5, 1e-3):
+        rows = {0: (0.5 * (1 - p), 0.0), 1: (0.0, 0.5 * (1 - p)), 2: (0.5 * p, 0.5 * p)}
+        for ca, ra in rows.items():
+            for cb, rb in rows.items():
+                assert code_of[minus(ra, rb)] == f8(ca, cb)
+                for u in (0, 1):
+                    assert code_of[plus(ra, rb, u)] == g8(ca, cb, u)
+    # leaf rule (BinaryPolarEncoderDecoder.py:250-252): p0 >= p1 -> 0, so only "hard 1" decides 1 -- the side bit
+    for c, (p0, p1) in states.items():
+        assert (0 if p0 >= p1 else 1) == (c & 1)
