@@ -178,6 +178,14 @@ int pc_trellis_genie(const pc_plan *plan, int n0, double deletion_prob, int ones
                      const int32_t *d_sub_len, int maxlen, const uint32_t *d_u_packed, int64_t B, uint32_t *d_cw_packed,
                      double *d_marg, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---- code construction (HOST only: no device buffers, no stream) -------------------------------------- */
+/* Tal-Vardy degrading construction for a binary-input memoryless channel with a uniform input: h_pe[i], i < 2^n, is the
+ * error probability of the degraded synthetic channel i (MSB-first minus / plus order) -- the Pevec of
+ * calcFrozenSet_degradingUpgrading(n, L, eps, None, xyDistribution) (ScalarDistributions/BinaryMemorylessDistribution.py:
+ * 620-680: minusTransform().degrade(L) / plusTransform().degrade(L) per level, errorProb() per leaf), float64-identical to
+ * the reference.  h_table [Y][2] = xyDistribution.probs; `threads` host threads share the nodes of a level. */
+int pc_tv_degrade_pe(int n, int L, const double *h_table, int Y, double *h_pe, int threads);
+
 /* ---- Monte-Carlo counters and measurement hooks ---------------------------------------------------- */
 /* d_out3[0..2] += {B, frames whose first nbits differ, differing bits} over packed rows of ceil(nbits/32) words.
  * Replaces the serial comparison loop BinaryPolarEncoderDecoder.py:374-385 / QaryPolarEncoderDecoder.py:907-909;

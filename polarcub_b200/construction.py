@@ -83,3 +83,42 @@ def ga_awgn_pe(n, sigma):
             nxt.append(2.0 * v)
         m = nxt
     return np.array([0.5 * math.erfc(math.sqrt(v / 2.0) / math.sqrt(2.0)) for v in m])
+
+
+def tal_vardy_pe(n, L, xy_probs, threads=None):
+    """Pe vector of the reference's degrading construction for a binary-input memoryless channel with a uniform input:
+    `dist.minusTransform().degrade(L)` / `dist.plusTransform().degrade(L)` per level and `errorProb()` per leaf
+    (ScalarDistributions/BinaryMemorylessDistribution.py:657-677), computed by the native host routine
+    `pc_tv_degrade_pe` (csrc/tv_construct.cu) -- float64-identical to the reference, seconds instead of the reference's
+    ~11 minutes at N = 1024, L = 100.  xy_probs: [Y, 2] joint probabilities p(y, x) (`BinaryMemorylessDistribution.probs`)."""
+    import ctypes
+    from . import _lib
+    t = np.ascontiguousarray(getattr(xy_probs, "probs", xy_probs), dtype=np.float64)
+    assert t.ndim == 2 and t.shape[1] == 2 and t.shape[0] >= 1
+    pe = np.empty(1 << n, dtype=np.float64)
+    _lib.check(_lib.lib().pc_tv_degrade_pe(int(n), int(L), t.ctypes.data_as(ctypes.c_void_p), int(t.shape[0]),
+                                           pe.ctypes.data_as(ctypes.c_void_p), int(threads or os.cpu_count() or 1)),
+               "pc_tv_degrade_pe")
+    return pe
+
+
+def calcFrozenSet_degradingUpgrading(n, L, upperBoundOnErrorProbability, xDistribution, xyDistribution, threads=None):
+    """calcFrozenSet_degradingUpgrading (ScalarDistributions/BinaryMemorylessDistribution.py:620-680) for the uniform-input
+    form (xDistribution=None) -- the only form that runs in the reference (the other branch calls a
+    method that does not exist)."""
+    assert n >= 0 and L > 0 and upperBoundOnErrorProbability > 0 and xyDistribution is not None
+    if xDistribution is not None:
+        from ._lib import PolarcubError
+        raise PolarcubError("calcFrozenSet_degradingUpgrading: only the uniform-input form (xDistribution=None) is offered")
+    pe = tal_vardy_pe(n, L, xyDistribution, threads)
+    return frozen_set_from_tv_and_pe([0.0] * len(pe), list(pe), upperBoundOnErrorProbability)
+
+
+def make_bsc(p):
+    """makeBSC (BinaryMemorylessDistribution.py:478-483) as a [2, 2] table."""
+    return np.array([[0.5 * (1.0 - p), 0.5 * p], [0.5 * p, 0.5 * (1.0 - p)]])
+
+
+def make_bec(p):
+    """makeBEC (BinaryMemorylessDistribution.py:486-492) as a [3, 2] table."""
+    return np.array([[0.5 * (1.0 - p), 0.0], [0.0, 0.5 * (1.0 - p)], [0.5 * p, 0.5 * p]])

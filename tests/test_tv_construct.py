@@ -1,0 +1,65 @@
+"""The native Tal-Vardy degrading construction (pc_tv_degrade_pe, csrc/tv_construct.cu -- host code, no GPU needed) against
+the live reference: the small cases of tests/golden/tv_construct.npz (oracle/gen_golden_tv.py: BSC / BEC / random / duplicate-LLR
+and zero-probability outputs, L from 1 to 33) and the BASELINE-size Pe vectors under tests/golden/constructions/
+(oracle/gen_constructions.py: 11 minutes of the reference's Python at N = 1024).  Bar: float64-identical Pe vectors."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_small_cases_match_the_live_reference():
+    from polarcub_b200 import construction as c
+    d = np.load(os.path.join(GOLD, "tv_construct.npz"), allow_pickle=True)
+    for nm in d["names"]:
+        n, L = (int(v) for v in d[nm + "/params"])
+        tab = d[nm + "/table"]
+        pe = c.tal_vardy_pe(n, L, tab, threads=3)
+        np.testing.assert_array_equal(pe, d[nm + "/pe"], err_msg=str(nm))
+        np.testing.assert_array_equal(c.tal_vardy_pe(n, L, tab, threads=1), pe)  # the thread split changes nothing
+        fs = c.calcFrozenSet_degradingUpgrading(n, L, float(d[nm + "/eps"]), None, tab)
+        assert sorted(fs) == [int(i) for i in d[nm + "/frozen"]], nm
+        if n >= 1:  # the first degraded minus channel is the n = 1 construction's first leaf: its Pe pins the symbol table
+            acc = 0.0
+            for r in d[nm + "/first_minus"].tolist():
+                acc += min(r)  # errorProb's plain running sum (builtin sum() would compensate)
+            assert c.tal_vardy_pe(1, L, tab)[0] == acc
+
+
+@pytest.mark.parametrize("name,n,kind", [("bsc_p0.11_n7_L100_pe.npy", 7, "bsc"), ("bsc_p0.11_n10_L100_pe.npy", 10, "bsc"),
+                                         ("bec_p0.1_n8_L100_pe.npy", 8, "bec"), ("biawgn_ebn02.0_n8_L100_pe.npy", 8, "biawgn")])
+def test_baseline_constructions_match_the_live_reference(name, n, kind):
+    from polarcub_b200 import construction as c
+    if kind == "bsc":
+        tab = c.make_bsc(0.11)
+    elif kind == "bec":
+        tab = c.make_bec(0.1)
+    else:  # the 400-bin quantised BI-AWGN of oracle/gen_constructions.py (Eb/N0 = 2 dB, R = 1/2)
+        from scipy.stats import norm
+        sigma = math.sqrt(1.0 / (2.0 * 0.5 * 10.0 ** (2.0 / 10.0)))
+        edges = np.linspace(-6.0 * sigma - 1.0, 6.0 * sigma + 1.0, 401)
+        edges[0], edges[-1] = -np.inf, np.inf
+        tab = np.array([[float(0.5 * (norm.cdf((edges[b + 1] - 1.0) / sigma) - norm.cdf((edges[b] - 1.0) / sigma))),
+                         float(0.5 * (norm.cdf((edges[b + 1] + 1.0) / sigma) - norm.cdf((edges[b] + 1.0) / sigma)))]
+                        for b in range(400)])
+    pe = c.tal_vardy_pe(n, 100, tab)
+    np.testing.assert_array_equal(pe, c.load_pe(name))
+
+
+def test_survey_known_answer_k361():
+    """BSC(0.11), L = 100, epsilon = 0.1, N = 1024 -> K = 361 information indices."""
+    from polarcub_b200 import construction as c
+    fs = c.calcFrozenSet_degradingUpgrading(10, 100, 0.1, None, c.make_bsc(0.11))
+    assert 1024 - len(fs) == 361
+
+
+def test_argument_validation():
+    from polarcub_b200 import construction as c
+    from polarcub_b200._lib import PolarcubError
+    with pytest.raises(PolarcubError):
+        c.tal_vardy_pe(3, 0, c.make_bsc(0.1))  # L must be positive
+    with pytest.raises(PolarcubError):
+        c.calcFrozenSet_degradingUpgrading(3, 8, 0.1, c.make_bsc(0.1), c.make_bsc(0.1))  # non-uniform input: not offered
