@@ -185,6 +185,10 @@ int pc_trellis_genie(const pc_plan *plan, int n0, double deletion_prob, int ones
  * 620-680: minusTransform().degrade(L) / plusTransform().degrade(L) per level, errorProb() per leaf), float64-identical to
  * the reference.  h_table [Y][2] = xyDistribution.probs; `threads` host threads share the nodes of a level. */
 int pc_tv_degrade_pe(int n, int L, const double *h_table, int Y, double *h_pe, int threads);
+/* The same for a q-ary input alphabet: the Pevec of QaryMemorylessDistribution's calcTVAndPe_degradingUpgrading(n, L, None,
+ * xyDistribution) (ScalarDistributions/QaryMemorylessDistribution.py:934-990; degrade = degrade_dynamic :215-260 over the
+ * q-1 one-hot binary channels :98-153).  h_table [Y][q] = xyDistribution.probs. */
+int pc_tv_degrade_pe_qary(int q, int n, int L, const double *h_table, int Y, double *h_pe, int threads);
 
 /* ---- Monte-Carlo counters and measurement hooks ---------------------------------------------------- */
 /* d_out3[0..2] += {B, frames whose first nbits differ, differing bits} over packed rows of ceil(nbits/32) words.

@@ -71,6 +71,49 @@ def main():
         out[nm + "/frozen"] = np.array(sorted(fs), dtype=np.int64)
         out[nm + "/first_minus"] = first if first is not None else np.zeros((0, 2))
         print(nm, "N", 1 << n, "L", L, "frozen", len(fs), "sum Pe", pe.sum())
+    # ---- q-ary: QaryMemorylessDistribution.minusTransform().degrade(L) / plusTransform().degrade(L), errorProb() ----------
+    QMD = ref.QMD
+
+    def qdist_of(q, rows):
+        d = QMD.QaryMemorylessDistribution(q)
+        for r in rows:
+            d.append([float(v) for v in r])
+        return d
+
+    def qsc(q, p):
+        return np.array(QMD.makeQSC(q, p).probs, dtype=np.float64)
+
+    def qec(q, p):
+        return np.array(QMD.makeQEC(q, p).probs, dtype=np.float64)
+
+    def rand_q(Y, q):
+        t = rng.random((Y, q)) ** 2
+        return t / t.sum()
+
+    qcases = [  # name, q, table, n, L
+        ("q3_qsc0.1_n4_L16", 3, qsc(3, 0.1), 4, 16),
+        ("q3_qsc0.02_n5_L100", 3, qsc(3, 0.02), 5, 100),
+        ("q3_qec0.3_n4_L9", 3, qec(3, 0.3), 4, 9),
+        ("q2_qsc0.11_n5_L8", 2, qsc(2, 0.11), 5, 8),
+        ("q4_qsc0.1_n3_L27", 4, qsc(4, 0.1), 3, 27),
+        ("q5_qsc0.05_n2_L16", 5, qsc(5, 0.05), 2, 16),
+        ("q3_rand4_n3_L25", 3, rand_q(4, 3), 3, 25),
+        ("q3_qsc0.1_n3_L1", 3, qsc(3, 0.1), 3, 1),
+    ]
+    out["qnames"] = np.array([c[0] for c in qcases])
+    for nm, q, tab, n, L in qcases:
+        dists = [qdist_of(q, tab)]
+        for m in range(1, n + 1):
+            nxt = []
+            for d in dists:
+                nxt.append(d.minusTransform().degrade(L))
+                nxt.append(d.plusTransform().degrade(L))
+            dists = nxt
+        pe = np.array([d.errorProb() for d in dists], dtype=np.float64)
+        out[nm + "/table"] = np.asarray(tab, dtype=np.float64)
+        out[nm + "/params"] = np.array([q, n, L], dtype=np.int64)
+        out[nm + "/pe"] = pe
+        print(nm, "q", q, "N", 1 << n, "L", L, "sum Pe", pe.sum())
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

@@ -51,6 +51,7 @@ SIGNATURES = {
     "pc_trellis_decode": (c_int, [c_void_p, c_int, ctypes.c_double, c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "pc_tv_degrade_pe": (c_int, [c_int, c_int, c_void_p, c_int, c_void_p, c_int]),
+    "pc_tv_degrade_pe_qary": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int]),
     "pc_count_errors": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "pc_profile_enable": (c_int, [c_int]),
     "pc_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong)]),

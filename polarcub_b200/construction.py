@@ -122,3 +122,25 @@ def make_bsc(p):
 def make_bec(p):
     """makeBEC (BinaryMemorylessDistribution.py:486-492) as a [3, 2] table."""
     return np.array([[0.5 * (1.0 - p), 0.0], [0.0, 0.5 * (1.0 - p)], [0.5 * p, 0.5 * p]])
+
+
+def tal_vardy_pe_qary(q, n, L, xy_probs, threads=None):
+    """Pe vector of the q-ary degrading construction: `calcTVAndPe_degradingUpgrading(n, L, None, xyDistribution)`
+    (ScalarDistributions/QaryMemorylessDistribution.py:934-990, `degrade_dynamic` :218-260) by the native host routine
+    `pc_tv_degrade_pe_qary`; float64-identical to the reference.  xy_probs: [Y, q] (`QaryMemorylessDistribution.probs`)."""
+    import ctypes
+    from . import _lib
+    t = np.ascontiguousarray(getattr(xy_probs, "probs", xy_probs), dtype=np.float64)
+    assert t.ndim == 2 and t.shape[1] == q and t.shape[0] >= 1
+    pe = np.empty(1 << n, dtype=np.float64)
+    _lib.check(_lib.lib().pc_tv_degrade_pe_qary(int(q), int(n), int(L), t.ctypes.data_as(ctypes.c_void_p), int(t.shape[0]),
+                                                pe.ctypes.data_as(ctypes.c_void_p), int(threads or os.cpu_count() or 1)),
+               "pc_tv_degrade_pe_qary")
+    return pe
+
+
+def make_qsc(q, p):
+    """makeQSC (QaryMemorylessDistribution.py:780-784): probs[y][x] = 1 - p if x == y else p / (q - 1)."""
+    t = np.full((q, q), p / (q - 1))
+    np.fill_diagonal(t, 1.0 - p)
+    return t

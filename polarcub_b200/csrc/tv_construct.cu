@@ -24,9 +24,24 @@
 
 namespace {
 
+// one output symbol of a binary channel; head / tail: the chain (through a shared `next` array) of the original output
+// letters merged into it -- the reference's `auxiliary` sets, used only by the q-ary construction (-1: not tracked)
 struct Pair {
     double p0, p1;
+    int head = -1, tail = -1;
+    Pair() : p0(0.0), p1(0.0) {}
+    Pair(double a, double b) : p0(a), p1(b) {}
 };
+// aux union: a |= b
+inline void aux_join(Pair &a, const Pair &b, std::vector<int> *next) {
+    if (!next || b.head < 0) return;
+    if (a.head < 0) {
+        a.head = b.head;
+    } else {
+        (*next)[a.tail] = b.head;
+    }
+    a.tail = b.tail;
+}
 
 // builtin sum() of a list of exact Python floats with the default integer start (Python/bltinmodule.c, 3.12+): 0 + v[0],
 // then Neumaier's compensated additions, the compensation added once at the end
@@ -65,7 +80,7 @@ double key_degrade(const Pair &l, const Pair &c) {  // :499-511
     return hxgiveny(l.p0 + c.p0, l.p1 + c.p1) - hxgiveny(l.p0, l.p1) - hxgiveny(c.p0, c.p1);
 }
 
-void merge_equivalent_symbols(std::vector<Pair> &probs) {
+void merge_equivalent_symbols(std::vector<Pair> &probs, std::vector<int> *next) {
     // removeZeroProbOutput
     std::vector<Pair> kept;
     kept.reserve(probs.size());
@@ -104,6 +119,7 @@ void merge_equivalent_symbols(std::vector<Pair> &probs) {
         } else {
             prev.p0 += p.p0;
             prev.p1 += p.p1;
+            aux_join(prev, p, next);
         }
     }
     // normalize
@@ -191,8 +207,8 @@ struct Heap {
     }
 };
 
-void degrade(std::vector<Pair> &probs, int L) {  // :287-345
-    merge_equivalent_symbols(probs);
+void degrade(std::vector<Pair> &probs, int L, std::vector<int> *next = nullptr) {  // :287-345
+    merge_equivalent_symbols(probs, next);
     const double inf = std::numeric_limits<double>::infinity();
     Heap h;
     h.el.reserve(probs.size());
@@ -205,6 +221,7 @@ void degrade(std::vector<Pair> &probs, int L) {  // :287-345
         const int l = h.el[top].left, r = h.el[top].right;
         h.el[l].d.p0 += h.el[top].d.p0;
         h.el[l].d.p1 += h.el[top].d.p1;
+        aux_join(h.el[l].d, h.el[top].d, next);
         const int ll = h.el[l].left;
         if (ll >= 0) h.update_key(l, key_degrade(h.el[ll].d, h.el[l].d));
         if (r >= 0) h.update_key(r, key_degrade(h.el[l].d, h.el[r].d));
@@ -218,7 +235,7 @@ std::vector<Pair> minus_transform(const std::vector<Pair> &p) {  // :259-270
     std::vector<Pair> o;
     o.reserve(p.size() * p.size());
     for (const Pair &a : p)
-        for (const Pair &b : p) o.push_back({a.p0 * b.p0 + a.p1 * b.p1, a.p0 * b.p1 + a.p1 * b.p0});
+        for (const Pair &b : p) o.push_back(Pair(a.p0 * b.p0 + a.p1 * b.p1, a.p0 * b.p1 + a.p1 * b.p0));
     return o;
 }
 std::vector<Pair> plus_transform(const std::vector<Pair> &p) {  // :272-285
@@ -226,8 +243,8 @@ std::vector<Pair> plus_transform(const std::vector<Pair> &p) {  // :272-285
     o.reserve(2 * p.size() * p.size());
     for (const Pair &a : p)
         for (const Pair &b : p) {
-            o.push_back({a.p0 * b.p0, a.p1 * b.p1});
-            o.push_back({a.p1 * b.p0, a.p0 * b.p1});
+            o.push_back(Pair(a.p0 * b.p0, a.p1 * b.p1));
+            o.push_back(Pair(a.p1 * b.p0, a.p0 * b.p1));
         }
     return o;
 }
@@ -239,7 +256,7 @@ extern "C" int pc_tv_degrade_pe(int n, int L, const double *h_table, int Y, doub
     PC_REQUIRE(L >= 1, "L must be positive");
     PC_REQUIRE(h_table && Y >= 1 && h_pe, "null table / output");
     std::vector<std::vector<Pair>> cur(1);
-    for (int y = 0; y < Y; ++y) cur[0].push_back({h_table[2 * y], h_table[2 * y + 1]});
+    for (int y = 0; y < Y; ++y) cur[0].push_back(Pair(h_table[2 * y], h_table[2 * y + 1]));
     for (int m = 1; m <= n; ++m) {
         std::vector<std::vector<Pair>> nxt(2 * cur.size());
         // the children of different parents are independent: a static split over host threads changes no result
@@ -266,5 +283,140 @@ extern "C" int pc_tv_degrade_pe(int n, int L, const double *h_table, int Y, doub
         for (const Pair &p : cur[i]) s += std::min(p.p0, p.p1);
         h_pe[i] = s;
     }
+    return PC_OK;
+}
+
+// ---- q-ary channels: QaryMemorylessDistribution.degrade = degrade_dynamic (ScalarDistributions/QaryMemorylessDistribution.py
+// :215-260): q-1 one-hot binary channels (:98-153), each degraded to M = floor(L^(1/(q-1)) + eps) letters with the binary
+// routine above while tracking which original letters every new letter absorbed, the product alphabet of the q-1 degraded
+// channels, zero-probability letters dropped, and a normalisation whose sum runs over the SORTED probabilities (:736-751).
+namespace {
+
+typedef std::vector<double> QSym;  // q probabilities of one output letter
+
+std::vector<QSym> q_minus(const std::vector<QSym> &p, int q) {  // :182-196
+    std::vector<QSym> o;
+    o.reserve(p.size() * p.size());
+    for (const QSym &a : p)
+        for (const QSym &b : p) {
+            QSym t(q, 0.0);
+            for (int x1 = 0; x1 < q; ++x1)
+                for (int x2 = 0; x2 < q; ++x2) t[(x1 + x2) % q] += a[x1] * b[x2];
+            o.push_back(std::move(t));
+        }
+    return o;
+}
+std::vector<QSym> q_plus(const std::vector<QSym> &p, int q) {  // :198-212
+    std::vector<QSym> o;
+    o.reserve(p.size() * p.size() * q);
+    for (const QSym &a : p)
+        for (const QSym &b : p)
+            for (int u1 = 0; u1 < q; ++u1) {
+                QSym t(q, 0.0);
+                for (int u2 = 0; u2 < q; ++u2) t[u2] += a[(u1 - u2 + q) % q] * b[u2];
+                o.push_back(std::move(t));
+            }
+    return o;
+}
+
+void q_degrade(std::vector<QSym> &probs, int q, int L) {
+    const int Yold = (int)probs.size();
+    // one-hot binary channels, :98-153
+    std::vector<double> marg(q, 0.0), pgt(q, 0.0);
+    for (int x = 0; x < q; ++x) {
+        double t = 0.0;
+        for (const QSym &y : probs) t += y[x];
+        marg[x] = t;
+    }
+    for (int x = q - 2; x >= 0; --x) pgt[x] = pgt[x + 1] + marg[x + 1];
+    std::vector<std::vector<Pair>> onehot(q - 1);
+    for (int j = 0; j < q - 1; ++j) onehot[j].reserve(Yold);
+    for (int y = 0; y < Yold; ++y) {
+        double prev0 = 0.0, prev1 = 0.0;
+        for (int j = q - 2; j >= 0; --j) {
+            const double pb1 = probs[y][j];
+            const double pb0 = j == q - 2 ? probs[y][j + 1] : prev1 + prev0;
+            prev0 = pb0, prev1 = pb1;
+            Pair pr = j == 0 ? Pair(pb0, pb1) : Pair(pb0 / pgt[j - 1], pb1 / pgt[j - 1]);
+            pr.head = pr.tail = y;
+            onehot[j].push_back(pr);
+        }
+    }
+    const int M = (int)std::floor(std::pow((double)L, 1.0 / (q - 1)) + std::numeric_limits<double>::epsilon());  // :753-755
+    // degrade each one-hot channel; letters of zero probability in a channel keep the default mapping 0
+    std::vector<std::vector<int>> mapped(q - 1, std::vector<int>(Yold, 0));
+    std::vector<int> mult(q - 1, 1);
+    long newsize = 1;
+    for (int x = 0; x < q - 1; ++x) {
+        std::vector<int> next(Yold, -1);
+        degrade(onehot[x], M, &next);
+        for (int yi = 0; yi < (int)onehot[x].size(); ++yi)
+            for (int y = onehot[x][yi].head; y >= 0; y = next[y]) mapped[x][y] = yi;
+        if (x > 0) mult[x] = mult[x - 1] * (int)onehot[x - 1].size();
+        newsize *= (long)onehot[x].size();
+    }
+    std::vector<QSym> out((size_t)newsize, QSym(q, 0.0));
+    for (int y = 0; y < Yold; ++y) {
+        int ynew = 0;
+        for (int x = 0; x < q - 1; ++x) ynew += mapped[x][y] * mult[x];
+        for (int x = 0; x < q; ++x) out[ynew][x] += probs[y][x];
+    }
+    // removeZeroProbOutput :708-715 (builtin sum of non-negative floats: positive iff any entry is)
+    std::vector<QSym> kept;
+    for (QSym &t : out)
+        if (py_sum(t) > 0.0) kept.push_back(std::move(t));
+    // normalize :736-751: plain running sum over the ascending probabilities
+    std::vector<double> flat;
+    for (const QSym &t : kept)
+        for (double v : t) flat.push_back(v);
+    std::sort(flat.begin(), flat.end());
+    double total = 0.0;
+    for (double v : flat) total += v;
+    for (QSym &t : kept)
+        for (double &v : t) v /= total;
+    probs.swap(kept);
+}
+
+double q_error_prob(const std::vector<QSym> &probs) {  // :53-61
+    double total = 0.0;
+    for (const QSym &t : probs) {
+        QSym s(t);
+        std::sort(s.begin(), s.end());
+        s.pop_back();
+        total += py_sum(s);
+    }
+    return total;
+}
+
+}  // namespace
+
+extern "C" int pc_tv_degrade_pe_qary(int q, int n, int L, const double *h_table, int Y, double *h_pe, int threads) {
+    PC_REQUIRE(q >= 2 && q <= 16, "alphabet size must be in [2,16]");
+    PC_REQUIRE(n >= 0 && n <= 20, "n must be in [0,20]");
+    PC_REQUIRE(L >= 1, "L must be positive");
+    PC_REQUIRE(h_table && Y >= 1 && h_pe, "null table / output");
+    std::vector<std::vector<QSym>> cur(1);
+    for (int y = 0; y < Y; ++y) cur[0].push_back(QSym(h_table + (size_t)y * q, h_table + (size_t)(y + 1) * q));
+    for (int m = 1; m <= n; ++m) {
+        std::vector<std::vector<QSym>> nxt(2 * cur.size());
+        const int T = std::max(1, std::min<int>(threads, (int)cur.size()));
+        auto work = [&](int t) {
+            for (size_t i = t; i < cur.size(); i += T) {
+                nxt[2 * i] = q_minus(cur[i], q);
+                q_degrade(nxt[2 * i], q, L);
+                nxt[2 * i + 1] = q_plus(cur[i], q);
+                q_degrade(nxt[2 * i + 1], q, L);
+            }
+        };
+        if (T == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < T; ++t) th.emplace_back(work, t);
+            for (auto &x : th) x.join();
+        }
+        cur.swap(nxt);
+    }
+    for (size_t i = 0; i < cur.size(); ++i) h_pe[i] = q_error_prob(cur[i]);
     return PC_OK;
 }

@@ -63,3 +63,23 @@ def test_argument_validation():
         c.tal_vardy_pe(3, 0, c.make_bsc(0.1))  # L must be positive
     with pytest.raises(PolarcubError):
         c.calcFrozenSet_degradingUpgrading(3, 8, 0.1, c.make_bsc(0.1), c.make_bsc(0.1))  # non-uniform input: not offered
+
+
+def test_qary_small_cases_match_the_live_reference():
+    """pc_tv_degrade_pe_qary against QaryMemorylessDistribution.minusTransform().degrade(L) / plusTransform().degrade(L) +
+    errorProb() of the live reference (q = 2..5, QSC / QEC / random channels, L down to 1)."""
+    from polarcub_b200 import construction as c
+    d = np.load(os.path.join(GOLD, "tv_construct.npz"), allow_pickle=True)
+    for nm in d["qnames"]:
+        q, n, L = (int(v) for v in d[nm + "/params"])
+        pe = c.tal_vardy_pe_qary(q, n, L, d[nm + "/table"], threads=2)
+        np.testing.assert_array_equal(pe, d[nm + "/pe"], err_msg=str(nm))
+        np.testing.assert_array_equal(c.tal_vardy_pe_qary(q, n, L, d[nm + "/table"], threads=1), pe)
+
+
+def test_qary_baseline_construction_matches_the_live_reference():
+    """C3's code: q = 3, QSC(0.02), N = 2048, L = 100 -- hours of the reference's Python, committed as
+    tests/golden/constructions/qsc_q3_p0.02_n11_L100_pe.npy; the native routine reproduces all 2048 values bit for bit."""
+    from polarcub_b200 import construction as c
+    pe = c.tal_vardy_pe_qary(3, 11, 100, c.make_qsc(3, 0.02))
+    np.testing.assert_array_equal(pe, c.load_pe("qsc_q3_p0.02_n11_L100_pe.npy"))
