@@ -113,6 +113,10 @@ def main():
         out[nm + "/table"] = np.asarray(tab, dtype=np.float64)
         out[nm + "/params"] = np.array([q, n, L], dtype=np.int64)
         out[nm + "/pe"] = pe
+        # QaryPolarEncoderDecoder.frozenSetFromTVAndPe (:1156-1190), both selection rules, uniform input (TV = 0)
+        out[nm + "/frozen_eps"] = np.array(sorted(ref.QPED.frozenSetFromTVAndPe([0.0] * len(pe), list(pe), 0.2, None)), dtype=np.int64)
+        kk = max(0, (1 << n) // 2 - 1)
+        out[nm + "/frozen_k"] = np.array(sorted(ref.QPED.frozenSetFromTVAndPe([0.0] * len(pe), list(pe), None, kk)), dtype=np.int64)
         print(nm, "q", q, "N", 1 << n, "L", L, "sum Pe", pe.sum())
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

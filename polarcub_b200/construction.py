@@ -144,3 +144,38 @@ def make_qsc(q, p):
     t = np.full((q, q), p / (q - 1))
     np.fill_diagonal(t, 1.0 - p)
     return t
+
+
+def frozenSetFromTVAndPe_qary(TVvec, Pevec, errorUpperBoundForFrozenSet=None, numInfoIndices=None):
+    """QaryPolarEncoderDecoder.frozenSetFromTVAndPe (QaryPolarEncoderDecoder.py:1156-1190): the epsilon rule, or a fixed
+    number of information indices -- which, exactly as in the reference, leaves numInfoIndices + 1 of them (the slice starts
+    at `numInfoIndices + 1`, :1173-1176); the single-parity fix-up loop that follows never fires there (`numpy.bool_ is
+    False` is never true, :1180) and is therefore not reproduced."""
+    s = np.add(TVvec, Pevec)
+    N = len(s)
+    order = sorted(range(N), key=lambda k: s[k])
+    if numInfoIndices is None:
+        err, idx = 0.0, -1
+        while err < errorUpperBoundForFrozenSet and idx + 1 < N:
+            i = order[idx + 1]
+            if s[i] + err <= errorUpperBoundForFrozenSet:
+                err += s[i]
+                idx += 1
+            else:
+                break
+    else:
+        idx = numInfoIndices
+    return set(int(i) for i in order[idx + 1:])
+
+
+def calcFrozenSet_degradingUpgrading_qary(q, n, L, xDistribution, xyDistribution, upperBoundOnErrorProbability=None,
+                                          numInfoIndices=None, threads=None):
+    """QaryMemorylessDistribution.calcFrozenSet_degradingUpgrading (ScalarDistributions/QaryMemorylessDistribution.py:910-932)
+    for a uniform input (xDistribution=None); no directory cache -- the native pass takes seconds."""
+    assert n >= 0 and L > 0 and xyDistribution is not None
+    assert upperBoundOnErrorProbability is None or upperBoundOnErrorProbability > 0
+    if xDistribution is not None:
+        from ._lib import PolarcubError
+        raise PolarcubError("calcFrozenSet_degradingUpgrading: only the uniform-input form (xDistribution=None) is offered")
+    pe = tal_vardy_pe_qary(q, n, L, xyDistribution, threads)
+    return frozenSetFromTVAndPe_qary(np.zeros(len(pe)), pe, upperBoundOnErrorProbability, numInfoIndices)

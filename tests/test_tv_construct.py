@@ -75,6 +75,13 @@ def test_qary_small_cases_match_the_live_reference():
         pe = c.tal_vardy_pe_qary(q, n, L, d[nm + "/table"], threads=2)
         np.testing.assert_array_equal(pe, d[nm + "/pe"], err_msg=str(nm))
         np.testing.assert_array_equal(c.tal_vardy_pe_qary(q, n, L, d[nm + "/table"], threads=1), pe)
+        # QaryPolarEncoderDecoder.frozenSetFromTVAndPe: epsilon rule, and a fixed count (which keeps one index more: reference quirk)
+        fs = c.calcFrozenSet_degradingUpgrading_qary(q, n, L, None, d[nm + "/table"], upperBoundOnErrorProbability=0.2)
+        assert sorted(fs) == [int(i) for i in d[nm + "/frozen_eps"]], nm
+        kk = max(0, (1 << n) // 2 - 1)
+        fk = c.calcFrozenSet_degradingUpgrading_qary(q, n, L, None, d[nm + "/table"], numInfoIndices=kk)
+        assert sorted(fk) == [int(i) for i in d[nm + "/frozen_k"]], nm
+        assert (1 << n) - len(fk) == kk + 1
 
 
 def test_qary_baseline_construction_matches_the_live_reference():
