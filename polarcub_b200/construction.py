@@ -179,3 +179,33 @@ def calcFrozenSet_degradingUpgrading_qary(q, n, L, xDistribution, xyDistribution
         raise PolarcubError("calcFrozenSet_degradingUpgrading: only the uniform-input form (xDistribution=None) is offered")
     pe = tal_vardy_pe_qary(q, n, L, xyDistribution, threads)
     return frozenSetFromTVAndPe_qary(np.zeros(len(pe)), pe, upperBoundOnErrorProbability, numInfoIndices)
+
+
+def calcTVAndPe_degradingUpgrading(n, L, xDistribution, xyDistribution, directory_name=None, verbosity=False, q=None,
+                                   threads=None):
+    """QaryMemorylessDistribution.calcTVAndPe_degradingUpgrading (ScalarDistributions/QaryMemorylessDistribution.py:934-990)
+    for a uniform input, with the reference's directory cache: `<directory_name>DegradingUpgrading_L=<L>_tv.npy` / `_pe.npy`
+    are loaded when both exist and written otherwise, so caches produced by either side serve the other.  Unlike the
+    reference (which returns None without a directory, :935) the vectors are also returned when directory_name is None."""
+    if xDistribution is not None:
+        from ._lib import PolarcubError
+        raise PolarcubError("calcTVAndPe_degradingUpgrading: only the uniform-input form (xDistribution=None) is offered")
+    t = np.ascontiguousarray(getattr(xyDistribution, "probs", xyDistribution), dtype=np.float64)
+    q = int(q or getattr(xyDistribution, "q", t.shape[1]))
+    tv_name = pe_name = None
+    if directory_name is not None:
+        tv_name = directory_name + "{}.npy".format("DegradingUpgrading_L=" + str(L) + "_tv")
+        pe_name = directory_name + "{}.npy".format("DegradingUpgrading_L=" + str(L) + "_pe")
+        if verbosity:
+            print(tv_name)
+            print(pe_name)
+        if os.path.isfile(tv_name) and os.path.isfile(pe_name):
+            return np.load(tv_name), np.load(pe_name)
+    pe = tal_vardy_pe_qary(q, n, L, t, threads)
+    tv = np.zeros(len(pe))
+    if directory_name is not None:
+        if not os.path.exists(directory_name):
+            os.makedirs(directory_name)
+        np.save(tv_name, tv)
+        np.save(pe_name, pe)
+    return tv, pe

@@ -90,3 +90,20 @@ def test_qary_baseline_construction_matches_the_live_reference():
     from polarcub_b200 import construction as c
     pe = c.tal_vardy_pe_qary(3, 11, 100, c.make_qsc(3, 0.02))
     np.testing.assert_array_equal(pe, c.load_pe("qsc_q3_p0.02_n11_L100_pe.npy"))
+
+
+def test_directory_cache_is_the_reference_layout(tmp_path):
+    """calcTVAndPe_degradingUpgrading writes / reads `DegradingUpgrading_L=<L>_tv.npy` and `_pe.npy` under directory_name
+    (QaryMemorylessDistribution.py:936-947, :987-990), so a cache written here is what the reference would load."""
+    from polarcub_b200 import construction as c
+    d = np.load(os.path.join(GOLD, "tv_construct.npz"), allow_pickle=True)
+    nm = "q3_qsc0.1_n4_L16"
+    q, n, L = (int(v) for v in d[nm + "/params"])
+    root = str(tmp_path) + "/cons/"
+    tv, pe = c.calcTVAndPe_degradingUpgrading(n, L, None, d[nm + "/table"], root)
+    np.testing.assert_array_equal(pe, d[nm + "/pe"])
+    assert np.all(tv == 0.0)
+    assert sorted(os.listdir(root)) == ["DegradingUpgrading_L=16_pe.npy", "DegradingUpgrading_L=16_tv.npy"]
+    np.save(root + "DegradingUpgrading_L=16_pe.npy", np.asarray(pe) + 1.0)  # a second call must LOAD, not recompute
+    _, pe2 = c.calcTVAndPe_degradingUpgrading(n, L, None, d[nm + "/table"], root)
+    np.testing.assert_array_equal(pe2, np.asarray(pe) + 1.0)
