@@ -76,8 +76,10 @@ double hxgiveny(double d0, double d1) {  // :471-473
     const double py = d0 + d1;
     return py * (eta(d0 / py) + eta(d1 / py));
 }
-double key_degrade(const Pair &l, const Pair &c) {  // :499-511
-    return hxgiveny(l.p0 + c.p0, l.p1 + c.p1) - hxgiveny(l.p0, l.p1) - hxgiveny(c.p0, c.p1);
+// :499-511: hxgiveny(merged) - hxgiveny(left) - hxgiveny(center); hl / hc are the two symbols' own (cached) terms -- the same
+// function of the same operands, so caching changes no bit
+double key_degrade(const Pair &l, double hl, const Pair &c, double hc) {
+    return hxgiveny(l.p0 + c.p0, l.p1 + c.p1) - hl - hc;
 }
 
 void merge_equivalent_symbols(std::vector<Pair> &probs, std::vector<int> *next) {
@@ -213,8 +215,9 @@ void degrade(std::vector<Pair> &probs, int L, std::vector<int> *next = nullptr) 
     Heap h;
     h.el.reserve(probs.size());
     h.arr.reserve(probs.size());
-    std::vector<double> keys(probs.size());
-    for (size_t i = 0; i < probs.size(); ++i) keys[i] = i == 0 ? inf : key_degrade(probs[i - 1], probs[i]);
+    std::vector<double> keys(probs.size()), hs(probs.size());
+    for (size_t i = 0; i < probs.size(); ++i) hs[i] = hxgiveny(probs[i].p0, probs[i].p1);
+    for (size_t i = 0; i < probs.size(); ++i) keys[i] = i == 0 ? inf : key_degrade(probs[i - 1], hs[i - 1], probs[i], hs[i]);
     for (size_t i = 0; i < probs.size(); ++i) h.insert_at_tail(keys[i], probs[i]);
     while ((int)h.arr.size() > L) {
         const int top = h.extract_min();
@@ -222,9 +225,10 @@ void degrade(std::vector<Pair> &probs, int L, std::vector<int> *next = nullptr) 
         h.el[l].d.p0 += h.el[top].d.p0;
         h.el[l].d.p1 += h.el[top].d.p1;
         aux_join(h.el[l].d, h.el[top].d, next);
+        hs[l] = hxgiveny(h.el[l].d.p0, h.el[l].d.p1);
         const int ll = h.el[l].left;
-        if (ll >= 0) h.update_key(l, key_degrade(h.el[ll].d, h.el[l].d));
-        if (r >= 0) h.update_key(r, key_degrade(h.el[l].d, h.el[r].d));
+        if (ll >= 0) h.update_key(l, key_degrade(h.el[ll].d, hs[ll], h.el[l].d, hs[l]));
+        if (r >= 0) h.update_key(r, key_degrade(h.el[l].d, hs[l], h.el[r].d, hs[r]));
     }
     std::vector<Pair> out;
     for (int e = probs.empty() ? -1 : 0; e >= 0; e = h.el[e].right) out.push_back(h.el[e].d);  // the head is never extracted (key inf)
