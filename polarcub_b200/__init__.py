@@ -8,8 +8,9 @@ include/polarcub_b200.h (polarcub_b200/csrc).  PyTorch is used only for device m
 from . import engine  # noqa: F401
 from .BinaryPolarEncoderDecoder import BinaryPolarEncoderDecoder, polarTransformOfBits  # noqa: F401
 from .simulation import encodeDecodeSimulation, genieEncodeDecodeSimulation, frozenSetFromTVAndPe, readFrozenSetFromFile  # noqa: F401
-from . import Guardbands, CollectionOfBinaryTrellises  # noqa: F401
+from . import Guardbands, CollectionOfBinaryTrellises, construction  # noqa: F401
+from .construction import calcFrozenSet_degradingUpgrading, calcTVAndPe_degradingUpgrading  # noqa: F401
 from .QaryPolarEncoderDecoder import QaryPolarEncoderDecoder, polarTransformOfQudits, ProbResult  # noqa: F401
 
 __all__ = ["BinaryPolarEncoderDecoder", "QaryPolarEncoderDecoder", "polarTransformOfBits", "polarTransformOfQudits",
-           "ProbResult", "engine"]
+           "ProbResult", "engine", "construction", "calcFrozenSet_degradingUpgrading", "calcTVAndPe_degradingUpgrading"]
