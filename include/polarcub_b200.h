@@ -25,6 +25,9 @@
  *                             recursion :318-401, arithmetic QaryMemorylessVectorDistribution.py:26-118)
  *   pc_scl_decode_probs       QaryPolarEncoderDecoder.listDecode          (QaryPolarEncoderDecoder.py:118-227,
  *                             recursion :403-757, helpers :759-820, :867-872)
+ *   pc_scl_decode_packed      the same entry point for q = 2 on bit-packed buffers, float64 pairs or, fused with
+ *   pc_scl_decode_symbols     makeQaryMemorylessVectorDistribution(q, length, yvec) (ScalarDistributions/
+ *                             QaryMemorylessDistribution.py:757-776), uint8 channel output symbols + the channel table
  *   pc_trellis_decode         BinaryPolarEncoderDecoder.decode over CollectionOfBinaryTrellises (uniform prior), fused with
  *                             buildCollectionOfBinaryTrellises_uniformInput_deletion's per-sub-word trellis construction
  *                             (VectorDistributions/BinaryTrellis.py:206-438, CollectionOfBinaryTrellises.py:55-129)
@@ -159,6 +162,28 @@ int pc_scl_decode_probs(const pc_plan *plan, int L, const double *d_xy, const ui
                         const uint8_t *d_actual_info, int64_t B, uint8_t *d_info, int32_t *d_prob_result,
                         int32_t *d_list_size, double *d_list_prob, double *d_actual_prob, uint8_t *d_list_info,
                         void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Binary (q = 2) listDecode on BIT-PACKED buffers (bit i of a row in word i/32, position i%32), 2 <= N <= 8192.
+ * Channel input, exactly one of:
+ *   d_xy [B][N][2] float64 = xyVectorDistribution.probs (linear domain), or
+ *   d_y  [B][N] uint8 channel output symbols, every y < Y, with h_table [Y][2] float64 = the rows
+ *        makeQaryMemorylessVectorDistribution would copy into probs (QaryMemorylessDistribution.py:757-776), 1 <= Y <= 256:
+ *        16 x less input traffic; results are those of pc_scl_decode_probs on h_table[y].
+ * d_frozen_packed [B][ceil((N-k)/32)]: the explicit frozen values in u order (frozenValuesIterator), or NULL = all zero.
+ * d_actual_info_packed [B][ceil(k/32)].  Outputs: d_info_packed [B][ceil(k/32)], d_prob_result [B] int32 (ProbResult).
+ * Optional final list (all null, or the first three non-null): d_list_size [B], d_list_prob [B][L], d_actual_prob [B],
+ * d_list_info_packed [B][L][ceil(k/32)] (may be null on its own).  Workspace: pc_scl_workspace_bytes_packed. */
+size_t pc_scl_workspace_bytes_packed(const pc_plan *plan, int L, int64_t B, int want_list);
+int pc_scl_decode_packed(const pc_plan *plan, int L, const double *d_xy, const uint8_t *d_y, const double *h_table, int Y,
+                         const uint32_t *d_frozen_packed, const uint32_t *d_actual_info_packed, int64_t B,
+                         uint32_t *d_info_packed, int32_t *d_prob_result, int32_t *d_list_size, double *d_list_prob,
+                         double *d_actual_prob, uint32_t *d_list_info_packed, void *d_workspace, size_t workspace_bytes,
+                         void *stream);
+/* pc_scl_decode_packed on channel symbols without the list outputs */
+int pc_scl_decode_symbols(const pc_plan *plan, int L, const uint8_t *d_y, const double *h_table, int Y,
+                          const uint32_t *d_frozen_packed, const uint32_t *d_actual_info_packed, int64_t B,
+                          uint32_t *d_info_packed, int32_t *d_prob_result, void *d_workspace, size_t workspace_bytes,
+                          void *stream);
 
 /* ---- deletion channel: SC decoding over a collection of trellises ---------------------------------------- */
 /* The received word is split by the caller into T = 2^(n-n0) trimmed sub-words (Guardbands.removeDeletionGuardBands,

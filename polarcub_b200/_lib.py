@@ -39,6 +39,11 @@ SIGNATURES = {
     "pc_scl_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int64, c_int]),
     "pc_scl_decode_probs": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pc_scl_workspace_bytes_packed": (c_size_t, [c_void_p, c_int, c_int64, c_int]),
+    "pc_scl_decode_packed": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pc_scl_decode_symbols": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                      c_void_p, c_size_t, c_void_p]),
     "pc_sc_genie_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "pc_sc_genie_probs": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pc_sc_decode_probs_prior": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,

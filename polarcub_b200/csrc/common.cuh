@@ -1,5 +1,12 @@
 // common.cuh -- shared host/device helpers for the polarcub_b200 CUDA library (sm_100a).
 #pragma once
+#ifdef PC_EMU
+#include "../../tests/emu/cuda_emu.h"  // CPU emulation of the kernel sources: test builds only (tests/emu)
+#else
+// dynamic shared memory and kernel launches, spelled so that tests/emu can run the kernel sources on the CPU
+#define PC_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define PC_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 

@@ -29,14 +29,20 @@ namespace pc {
 int qsc_ingest_launch(int n, int q, int64_t frames, int64_t Bpad, const double *in, double *out, cudaStream_t st);
 int byte_egress_launch(bool bitrev, int n, int R, int64_t frames, int64_t Bpad, const uint8_t *in_t, uint8_t *out,
                        cudaStream_t st);
-// scl_bin.cu: frame-per-CTA binary decoder
-bool scl2_supported(const pc_plan *plan, int L);
-size_t scl2_workspace_bytes(const pc_plan *plan, int L, int64_t B);
-int scl2_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_xy, const uint8_t *d_fv, const uint8_t *d_ainfo,
-                int64_t B, uint8_t *d_info, int32_t *d_res, int32_t *d_lsize, double *d_lprob, double *d_aprob,
-                uint8_t *d_linfo, void *ws, size_t ws_bytes, cudaStream_t st);
+// scl_path.cu: path-per-lane binary decoder (the default for q = 2)
+bool sclp_supported(const pc_plan *plan, int L);
+size_t sclp_workspace_bytes(const pc_plan *plan, int L, int64_t B, bool want_list);
+size_t sclp_workspace_bytes_packed(const pc_plan *plan, int L, int64_t B, bool want_list);
+int64_t sclp_wave_frames(const pc_plan *plan, int L);
+int sclp_decode_bytes(const pc_plan *plan, const SclTables *T, int L, const double *d_xy, const uint8_t *d_fv, const uint8_t *d_ainfo,
+                      int64_t B, uint8_t *d_info, int32_t *d_res, int32_t *d_lsize, double *d_lprob, double *d_aprob,
+                      uint8_t *d_linfo, void *ws, size_t ws_bytes, cudaStream_t st);
+int sclp_decode_packed(const pc_plan *plan, const SclTables *T, int L, const double *d_xy, const uint8_t *d_y, const double *h_table,
+                       int Y, const uint32_t *d_fvp, const uint32_t *d_ainfo, int64_t B, uint32_t *d_info, int32_t *d_res,
+                       int32_t *d_lsize, double *d_lprob, double *d_aprob, uint32_t *d_linfo, void *ws, size_t ws_bytes,
+                       cudaStream_t st);
 
-// scl_warp.cu: frame-per-warp binary decoder (the default for q = 2)
+// scl_warp.cu: frame-per-warp binary decoder (round 1's kernel, kept for comparison: PC_SCL_WARP=1)
 bool sclw_supported(const pc_plan *plan, int L);
 size_t sclw_workspace_bytes(const pc_plan *plan, int L, int64_t B);
 int sclw_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_xy, const uint8_t *d_fv, const uint8_t *d_ainfo,
@@ -44,193 +50,6 @@ int sclw_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_
                 uint8_t *d_linfo, void *ws, size_t ws_bytes, cudaStream_t st);
 
 int64_t sclw_wave_frames(const pc_plan *plan, int L);
-int64_t scl2_wave_frames(const pc_plan *plan, int L);
-
-static std::mutex g_scl_mu;
-static std::map<const pc_plan *, SclTables *> g_scl_tables;
-
-static void scl_build(const pc_plan *p, SclTables &T, int i, int l, int c, int &info_idx, int &fv_idx) {
-    const int size = 1 << l, q = p->q;
-    int ninfo = 0;
-    for (int j = i; j < i + size; ++j) ninfo += !p->frozen_mask[j];
-    SclOp op{};
-    op.l = (int8_t)l;
-    op.c = (int8_t)c;
-    op.i = i;
-    op.info_idx = info_idx;
-    op.fv_idx = fv_idx;
-    auto mark = [&]() {
-        for (int j = i; j < i + size; ++j) T.node_level[j] = (int8_t)l;
-    };
-    if (ninfo == 0) {
-        op.kind = OP_RATE0;
-        for (int j = 0; j < size; ++j) {
-            T.a_src[i + j] = ~(fv_idx + j);
-            T.f_src[i + j] = fv_idx + j;
-        }
-        fv_idx += size;
-        mark();
-        T.ops.push_back(op);
-    } else if (ninfo == 1) {
-        op.kind = OP_REP;
-        int kpos = 0;
-        while (p->frozen_mask[i + kpos]) ++kpos;
-        op.kpos = kpos;
-        int f = fv_idx;
-        for (int j = 0; j < size; ++j) {
-            if (j == kpos) {
-                T.a_src[i + j] = info_idx;
-                T.f_src[i + j] = -1;
-                T.info_src[info_idx] = i + j;
-            } else {
-                T.a_src[i + j] = ~f;
-                T.f_src[i + j] = f;
-                ++f;
-            }
-        }
-        // natural-order T(e_kpos) mod q: T([a;b]) = [T(a)+T(b), -T(b)]
-        std::vector<int> cf(size, 0);
-        cf[kpos] = 1;
-        for (int s = 1; s < size; s <<= 1)
-            for (int b = 0; b < size; b += 2 * s)
-                for (int j = b; j < b + s; ++j) {
-                    const int x = cf[j], y = cf[j + s];
-                    cf[j] = (x + y) % q;
-                    cf[j + s] = (q - y) % q;
-                }
-        op.coef_off = (int32_t)T.rep_coef.size();
-        for (int j = 0; j < size; ++j) T.rep_coef.push_back((uint8_t)cf[j]);
-        if (q == 2) {  // reference order: position j of the node is natural position bitrev(j, l)
-            op.coefw_off = (int32_t)T.rep_coef_words.size();
-            const int words = size >= 32 ? size / 32 : 1;
-            for (int w = 0; w < words; ++w) {
-                uint32_t v = 0;
-                for (int b = 0; b < 32 && 32 * w + b < size; ++b) {
-                    const int j = 32 * w + b;
-                    int r = 0;
-                    for (int t = 0; t < l; ++t) r |= ((j >> t) & 1) << (l - 1 - t);
-                    v |= (uint32_t)(cf[r] & 1) << b;
-                }
-                T.rep_coef_words.push_back(v);
-            }
-        }
-        fv_idx += size - 1;
-        info_idx += 1;
-        mark();
-        T.ops.push_back(op);
-    } else if (ninfo == size) {
-        op.kind = OP_RATE1;
-        for (int j = 0; j < size; ++j) {
-            T.a_src[i + j] = info_idx + j;
-            T.f_src[i + j] = -1;
-            T.info_src[info_idx + j] = i + j;
-        }
-        info_idx += size;
-        mark();
-        T.ops.push_back(op);
-    } else if (ninfo == size - 1) {
-        // SPC.  The reference treats the frozen value as u[first of the segment] wherever the frozen index
-        // really is (QaryPolarEncoderDecoder.py:637, :662, :673): u' = [frozenValue, info...]; reproduced here.
-        op.kind = OP_SPC;
-        T.a_src[i] = ~fv_idx;
-        T.f_src[i] = -1;
-        for (int j = 1; j < size; ++j) {
-            T.a_src[i + j] = info_idx + j - 1;
-            T.f_src[i + j] = -1;
-            T.info_src[info_idx + j - 1] = i + j;
-        }
-        fv_idx += 1;
-        info_idx += size - 1;
-        mark();
-        T.ops.push_back(op);
-    } else {
-        op.kind = OP_MINUS;
-        T.ops.push_back(op);
-        scl_build(p, T, i, l - 1, 0, info_idx, fv_idx);
-        op.kind = OP_PLUS;
-        T.ops.push_back(op);
-        scl_build(p, T, i + size / 2, l - 1, 1, info_idx, fv_idx);
-        op.kind = OP_COMBINE;
-        T.ops.push_back(op);
-    }
-}
-
-template <class T>
-static cudaError_t upload(T *&dst, const std::vector<T> &v) {
-    cudaError_t e = cudaMalloc((void **)&dst, sizeof(T) * (v.size() ? v.size() : 1));
-    if (e != cudaSuccess) return e;
-    if (v.size()) e = cudaMemcpy(dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
-    return e;
-}
-
-SclTables *scl_tables(const pc_plan *p) {
-    std::lock_guard<std::mutex> lk(g_scl_mu);
-    auto it = g_scl_tables.find(p);
-    if (it != g_scl_tables.end()) return it->second;
-    SclTables *T = new SclTables();
-    T->a_src.assign(p->N, 0);
-    T->f_src.assign(p->N, -1);
-    T->node_level.assign(p->N, 0);
-    T->info_src.assign(p->k > 0 ? p->k : 1, 0);
-    int ii = 0, fi = 0;
-    scl_build(p, *T, 0, p->n, 0, ii, fi);
-    if (p->q == 2) {
-        const int N = p->N, NW = N >= 32 ? N / 32 : 1;
-        T->perm.assign(N, 0);
-        for (int i = 0; i < N; ++i) {
-            const int l = T->node_level[i], size = 1 << l, i0 = i & ~(size - 1), j = i - i0;
-            int r = 0;
-            for (int t = 0; t < l; ++t) r |= ((j >> t) & 1) << (l - 1 - t);
-            T->perm[i] = i0 + r;
-        }
-        for (const SclOp &o : T->ops)
-            T->ops2.push_back(make_uint2((uint32_t)o.kind | (uint32_t)o.l << 3 | (uint32_t)o.c << 7 | (uint32_t)o.i << 8,
-                                         (uint32_t)(o.fv_idx & 0xffff) | (uint32_t)(o.kind == OP_REP ? o.coefw_off : 0) << 16));
-        auto is_minus = [&](size_t a, int l) {
-            return a < T->ops2.size() && (T->ops2[a].x & 7) == OP_MINUS && (int)((T->ops2[a].x >> 3) & 15) == l;
-        };
-        const char *mdv = getenv("PC_SCLW_MAXDEPTH");
-        const int maxdepth = mdv && *mdv ? atoi(mdv) : 2;
-        for (size_t a = 0; a < T->ops2.size(); ++a) {
-            uint2 o = T->ops2[a];
-            const int kind = o.x & 7, l = (o.x >> 3) & 15;
-            if ((kind == OP_MINUS || kind == OP_PLUS) && maxdepth > 1) {
-                if (l >= 7 && is_minus(a + 1, l - 1)) {
-                    o.x |= 1u << 30;
-                    a += 1;
-                }
-            }
-            T->ops3.push_back(o);
-        }
-        T->stage_mask.assign((size_t)(p->n > 0 ? p->n : 1) * NW, 0u);
-        for (int t = 0; t < p->n; ++t)
-            for (int pos = 0; pos < N; ++pos)
-                if (!(pos & (1 << t)) && T->node_level[pos] > t) T->stage_mask[(size_t)t * NW + (pos >> 5)] |= 1u << (pos & 31);
-    }
-    if (upload(T->d_ops, T->ops) != cudaSuccess || upload(T->d_a_src, T->a_src) != cudaSuccess ||
-        upload(T->d_f_src, T->f_src) != cudaSuccess || upload(T->d_info_src, T->info_src) != cudaSuccess ||
-        upload(T->d_node_level, T->node_level) != cudaSuccess || upload(T->d_rep_coef, T->rep_coef) != cudaSuccess ||
-        upload(T->d_rep_coef_words, T->rep_coef_words) != cudaSuccess || upload(T->d_stage_mask, T->stage_mask) != cudaSuccess ||
-        upload(T->d_perm, T->perm) != cudaSuccess || upload(T->d_ops2, T->ops2) != cudaSuccess ||
-        upload(T->d_ops3, T->ops3) != cudaSuccess) {
-        set_error("scl tables: device upload failed");
-        return nullptr;
-    }
-    g_scl_tables[p] = T;
-    return T;
-}
-
-void scl_tables_release(const pc_plan *p) {
-    std::lock_guard<std::mutex> lk(g_scl_mu);
-    auto it = g_scl_tables.find(p);
-    if (it == g_scl_tables.end()) return;
-    SclTables *T = it->second;
-    cudaFree(T->d_ops), cudaFree(T->d_a_src), cudaFree(T->d_f_src), cudaFree(T->d_info_src);
-    cudaFree(T->d_node_level), cudaFree(T->d_rep_coef);
-    cudaFree(T->d_rep_coef_words), cudaFree(T->d_stage_mask), cudaFree(T->d_perm), cudaFree(T->d_ops2), cudaFree(T->d_ops3);
-    delete T;
-    g_scl_tables.erase(it);
-}
 
 struct SclParams {
     int n, k, L, n_ops, nfrozen;
@@ -730,8 +549,8 @@ extern "C" {
 
 size_t pc_scl_workspace_bytes(const pc_plan *plan, int L, int64_t B, int want_list) {
     if (!plan || B <= 0 || L < 1 || L > pc::SCL_LMAX) return 256;
+    if (pc::sclp_supported(plan, L)) return pc::sclp_workspace_bytes(plan, L, B, want_list != 0);
     if (pc::sclw_supported(plan, L)) return pc::sclw_workspace_bytes(plan, L, B);
-    if (pc::scl2_supported(plan, L)) return pc::scl2_workspace_bytes(plan, L, B);
     int64_t chunk = pc::round_up(B, 32);
     const int64_t cap = (int64_t)pc::num_sms() * 2 * pc::SCL_THREADS * 4;
     if (chunk > cap) chunk = cap;
@@ -740,8 +559,8 @@ size_t pc_scl_workspace_bytes(const pc_plan *plan, int L, int64_t B, int want_li
 
 int64_t pc_scl_wave_frames(const pc_plan *plan, int L) {
     if (!plan || L < 1 || L > pc::SCL_LMAX) return 0;
+    if (pc::sclp_supported(plan, L)) return pc::sclp_wave_frames(plan, L);
     if (pc::sclw_supported(plan, L)) return pc::sclw_wave_frames(plan, L);
-    if (pc::scl2_supported(plan, L)) return pc::scl2_wave_frames(plan, L);
     return (int64_t)pc::num_sms() * 2 * pc::SCL_THREADS;
 }
 
@@ -766,11 +585,11 @@ int pc_scl_decode_probs(const pc_plan *plan, int L, const double *d_xy, const ui
     SclTables *T = scl_tables(plan);
     if (!T) return PC_ERR_CUDA;
     cudaStream_t st = (cudaStream_t)stream;
-    if (sclw_supported(plan, L))  // q = 2: one frame per warp, small state in shared memory (scl_warp.cu)
+    if (sclp_supported(plan, L))  // q = 2: one path per lane, 32 / L frames per warp (scl_path.cu)
+        return sclp_decode_bytes(plan, T, L, d_xy, d_frozen_values, d_actual_info, B, d_info, d_prob_result, d_list_size,
+                                 d_list_prob, d_actual_prob, d_list_info, d_workspace, workspace_bytes, st);
+    if (sclw_supported(plan, L))  // q = 2: one frame per warp (scl_warp.cu), PC_SCL_WARP=1
         return sclw_decode(plan, T, L, d_xy, d_frozen_values, d_actual_info, B, d_info, d_prob_result, d_list_size,
-                           d_list_prob, d_actual_prob, d_list_info, d_workspace, workspace_bytes, st);
-    if (scl2_supported(plan, L))  // q = 2: one frame per CTA, state in shared memory (scl_bin.cu)
-        return scl2_decode(plan, T, L, d_xy, d_frozen_values, d_actual_info, B, d_info, d_prob_result, d_list_size,
                            d_list_prob, d_actual_prob, d_list_info, d_workspace, workspace_bytes, st);
     int64_t chunk = round_up(B, 32);
     const int64_t cap = (int64_t)num_sms() * 2 * SCL_THREADS * 4;
@@ -841,6 +660,44 @@ int pc_scl_decode_probs(const pc_plan *plan, int L, const double *d_xy, const ui
         }
     }
     return PC_OK;
+}
+
+/* see include/polarcub_b200.h */
+size_t pc_scl_workspace_bytes_packed(const pc_plan *plan, int L, int64_t B, int want_list) {
+    if (!plan || B <= 0 || L < 1 || L > pc::SCL_LMAX || !pc::sclp_supported(plan, L)) return 256;
+    return pc::sclp_workspace_bytes_packed(plan, L, B, want_list != 0);
+}
+
+int pc_scl_decode_packed(const pc_plan *plan, int L, const double *d_xy, const uint8_t *d_y, const double *h_table, int Y,
+                         const uint32_t *d_frozen_packed, const uint32_t *d_actual_info_packed, int64_t B,
+                         uint32_t *d_info_packed, int32_t *d_prob_result, int32_t *d_list_size, double *d_list_prob,
+                         double *d_actual_prob, uint32_t *d_list_info_packed, void *d_workspace, size_t workspace_bytes,
+                         void *stream) {
+    using namespace pc;
+    PC_REQUIRE(plan != nullptr, "plan is null");
+    PC_REQUIRE(plan->q == 2, "the packed list decoder is binary (q = 2)");
+    PC_REQUIRE(L >= 1 && L <= SCL_LMAX, "list size must be in [1,32]");
+    PC_REQUIRE(sclp_supported(plan, L), "block length not supported by the packed list decoder (2 <= N <= 8192)");
+    PC_REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return PC_OK;
+    PC_REQUIRE((d_xy != nullptr) != (d_y != nullptr), "exactly one of d_xy / d_y must be given");
+    if (d_y) PC_REQUIRE(h_table != nullptr && Y >= 1 && Y <= 256, "channel table missing or larger than 256 rows");
+    PC_REQUIRE(d_actual_info_packed && d_prob_result && d_workspace && (d_info_packed || plan->k == 0), "null buffer");
+    PC_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "workspace must be 256-byte aligned");
+    if (d_list_size) PC_REQUIRE(d_list_prob && d_actual_prob, "list outputs incomplete");
+    SclTables *T = scl_tables(plan);
+    if (!T) return PC_ERR_CUDA;
+    return sclp_decode_packed(plan, T, L, d_xy, d_y, h_table, Y, d_frozen_packed, d_actual_info_packed, B, d_info_packed,
+                              d_prob_result, d_list_size, d_list_prob, d_actual_prob, d_list_info_packed, d_workspace,
+                              workspace_bytes, (cudaStream_t)stream);
+}
+
+int pc_scl_decode_symbols(const pc_plan *plan, int L, const uint8_t *d_y, const double *h_table, int Y,
+                          const uint32_t *d_frozen_packed, const uint32_t *d_actual_info_packed, int64_t B,
+                          uint32_t *d_info_packed, int32_t *d_prob_result, void *d_workspace, size_t workspace_bytes,
+                          void *stream) {
+    return pc_scl_decode_packed(plan, L, nullptr, d_y, h_table, Y, d_frozen_packed, d_actual_info_packed, B, d_info_packed,
+                                d_prob_result, nullptr, nullptr, nullptr, nullptr, d_workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -10,6 +10,13 @@ namespace pc {
 enum : int { OP_MINUS = 0, OP_PLUS = 1, OP_COMBINE = 2, OP_RATE0 = 3, OP_REP = 4, OP_RATE1 = 5, OP_SPC = 6 };
 constexpr int SCL_LMAX = 32;
 constexpr int SCL_THREADS = 64;
+// scl_path.cu op flags
+enum : uint32_t {
+    SCLP_SSRC = 1u << 8,   // the source vector is in the shared ("single path") layout: written before the first fork
+    SCLP_SDST = 1u << 9,   // the op runs before the first fork: one path, the lanes of a frame share its elements
+    SCLP_FUSED = 1u << 10, // MINUS / PLUS (l) with the following MINUS (l-1) folded in
+    SCLP_CHAN = 1u << 11   // the source is the channel level (l == n)
+};
 
 struct alignas(16) SclOp {
     int8_t kind, l, c, pad;
@@ -34,6 +41,9 @@ struct SclTables {
     std::vector<uint2> ops2;               // packed ops: x = kind | l << 3 | c << 7 | i << 8, y = fv_idx | coefw_off << 16
     std::vector<uint2> ops3;               // scl_warp.cu: ops2 with PLUS/MINUS (l >= 7) + MINUS (l-1) pairs fused (x bit 30)
     std::vector<int32_t> perm;             // [N] reference position -> natural position inside its fast node
+    // scl_path.cu: x = kind | l << 3 | c << 7 | flags (SCLP_*), y = first u index, z = fv_idx, w = coefw_off (Rep)
+    std::vector<uint4> opsP;
+    int n_leaf = 0;                        // number of fast nodes
     SclOp *d_ops = nullptr;
     int32_t *d_a_src = nullptr, *d_f_src = nullptr, *d_info_src = nullptr;
     int8_t *d_node_level = nullptr;
@@ -41,6 +51,7 @@ struct SclTables {
     uint32_t *d_rep_coef_words = nullptr, *d_stage_mask = nullptr;
     int32_t *d_perm = nullptr;
     uint2 *d_ops2 = nullptr, *d_ops3 = nullptr;
+    uint4 *d_opsP = nullptr;
 };
 
 

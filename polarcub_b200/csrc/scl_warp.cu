@@ -789,7 +789,8 @@ static SclwConfig sclw_config(const pc_plan *plan, int L, int64_t B) {
 }
 
 bool sclw_supported(const pc_plan *plan, int L) {
-    if (envw_int("PC_SCL_GENERIC", 0) || envw_int("PC_SCL_CTA", 0)) return false;
+    static const bool on = envw_int("PC_SCL_WARP", 0) != 0;  // round 1's kernel: comparison runs only (read once)
+    if (!on) return false;
     return sclw_config(plan, L, 1).ok;
 }
 

@@ -214,6 +214,114 @@ def scl_decode_probs(plan, L, xy, frozen_values, actual_info, want_list=False, w
     return out
 
 
+def scl_decode_packed(plan, L, actual_info_packed, xy=None, y=None, table=None, frozen_packed=None, want_list=False,
+                      want_list_info=False, out=None):
+    """Binary SC-list decoding on bit-packed buffers (pc_scl_decode_packed).  Channel input: xy float64 [B, N, 2], or y uint8
+    [B, N] output symbols + table float64 [Y, 2] (host).  actual_info_packed int32 [B, Kw]; frozen_packed int32 [B, ceil((N-k)/32)]
+    or None (all-zero frozen values).  Returns dict(info_packed int32 [B, Kw], prob_result int32 [B]) plus the list outputs."""
+    assert plan.q == 2
+    B = actual_info_packed.shape[0]
+    dev = actual_info_packed.device
+    assert actual_info_packed.is_cuda and actual_info_packed.dtype == torch.int32 and actual_info_packed.is_contiguous()
+    assert actual_info_packed.shape == (B, max(plan.Kw, 1)) or actual_info_packed.shape == (B, plan.Kw)
+    tptr, Y = ctypes.c_void_p(0), 0
+    if xy is not None:
+        assert y is None and xy.is_cuda and xy.dtype == torch.float64 and xy.is_contiguous() and xy.shape == (B, plan.N, 2)
+    else:
+        assert y.is_cuda and y.dtype == torch.uint8 and y.is_contiguous() and y.shape == (B, plan.N)
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        assert table.ndim == 2 and table.shape[1] == 2 and 1 <= table.shape[0] <= 256
+        tptr, Y = table.ctypes.data_as(ctypes.c_void_p), table.shape[0]
+    nfw = (plan.N - plan.k + 31) // 32
+    if frozen_packed is not None:
+        assert frozen_packed.is_cuda and frozen_packed.dtype == torch.int32 and frozen_packed.is_contiguous()
+        assert frozen_packed.shape == (B, nfw)
+    if out is not None:
+        info, res = out
+    else:
+        info = torch.empty((B, max(plan.Kw, 1)), dtype=torch.int32, device=dev)
+        res = torch.empty((B,), dtype=torch.int32, device=dev)
+    ls = lp = ap = li = None
+    if want_list or want_list_info:
+        want_list = True
+        ls = torch.empty((B,), dtype=torch.int32, device=dev)
+        lp = torch.empty((B, L), dtype=torch.float64, device=dev)
+        ap = torch.empty((B,), dtype=torch.float64, device=dev)
+        if want_list_info:
+            li = torch.empty((B, L, max(plan.Kw, 1)), dtype=torch.int32, device=dev)
+    need = _lib.lib().pc_scl_workspace_bytes_packed(plan._h, int(L), B, 1 if want_list else 0)
+    ws = plan.workspace(need)
+    _lib.check(_lib.lib().pc_scl_decode_packed(plan._h, int(L), _ptr(xy), _ptr(y), tptr, Y, _ptr(frozen_packed),
+                                               _ptr(actual_info_packed), B, _ptr(info), _ptr(res), _ptr(ls), _ptr(lp), _ptr(ap),
+                                               _ptr(li), _ptr(ws), ws.numel(), _stream()), "pc_scl_decode_packed")
+    o = {"info_packed": info[:, :plan.Kw], "prob_result": res}
+    if want_list:
+        o.update(list_size=ls, list_prob=lp, actual_prob=ap)
+        if want_list_info:
+            o["list_info_packed"] = li[:, :, :plan.Kw]
+    return o
+
+
+def scl_decode_symbols_host(plan, L, y_host, table, ai_host, info_host, res_host, fv_host=None, chunk=None):
+    """pc_scl_decode_symbols over a batch in pinned host memory: y_host uint8 [B, N] channel symbols, ai_host int32 [B, Kw]
+    packed actual information, fv_host int32 [B, ceil((N-k)/32)] or None -> info_host int32 [B, Kw], res_host int32 [B]."""
+    for t, nm in ((y_host, "y_host"), (ai_host, "ai_host"), (info_host, "info_host"), (res_host, "res_host")):
+        _pinned(t, nm)
+    if fv_host is not None:
+        _pinned(fv_host, "fv_host")
+    B = y_host.shape[0]
+    nfw = (plan.N - plan.k + 31) // 32
+    chunk = chunk or default_host_chunk(B, plan.N, scl_wave_frames(plan, L))
+    sl = _Slots(plan, "sclsym")
+
+    def body(lo, hi, slot):
+        m = hi - lo
+        y = sl.get(slot, "y", (chunk, plan.N), torch.uint8)[:m]
+        ai = sl.get(slot, "ai", (chunk, max(plan.Kw, 1)), torch.int32)[:m]
+        info = sl.get(slot, "info", (chunk, max(plan.Kw, 1)), torch.int32)[:m]
+        res = sl.get(slot, "res", (chunk,), torch.int32)[:m]
+        y.copy_(y_host[lo:hi], non_blocking=True)
+        ai.copy_(ai_host[lo:hi], non_blocking=True)
+        fv = None
+        if fv_host is not None:
+            fv = sl.get(slot, "fv", (chunk, nfw), torch.int32)[:m]
+            fv.copy_(fv_host[lo:hi], non_blocking=True)
+        scl_decode_packed(plan, L, ai, y=y, table=table, frozen_packed=fv, out=(info, res))
+        info_host[lo:hi].copy_(info[:, :plan.Kw], non_blocking=True)
+        res_host[lo:hi].copy_(res, non_blocking=True)
+
+    host_pipeline(plan, B, chunk, body)
+
+
+def scl_decode_packed_host(plan, L, xy_host, ai_host, info_host, res_host, fv_host=None, chunk=None):
+    """pc_scl_decode_packed over float64 probability pairs in pinned host memory (xy_host [B, N, 2]); packed side buffers as
+    scl_decode_symbols_host."""
+    for t, nm in ((xy_host, "xy_host"), (ai_host, "ai_host"), (info_host, "info_host"), (res_host, "res_host")):
+        _pinned(t, nm)
+    B = xy_host.shape[0]
+    nfw = (plan.N - plan.k + 31) // 32
+    chunk = chunk or default_host_chunk(B, plan.N * 16, scl_wave_frames(plan, L))
+    sl = _Slots(plan, "sclpk")
+
+    def body(lo, hi, slot):
+        m = hi - lo
+        xy = sl.get(slot, "xy", (chunk, plan.N, 2), torch.float64)[:m]
+        ai = sl.get(slot, "ai", (chunk, max(plan.Kw, 1)), torch.int32)[:m]
+        info = sl.get(slot, "info", (chunk, max(plan.Kw, 1)), torch.int32)[:m]
+        res = sl.get(slot, "res", (chunk,), torch.int32)[:m]
+        xy.copy_(xy_host[lo:hi], non_blocking=True)
+        ai.copy_(ai_host[lo:hi], non_blocking=True)
+        fv = None
+        if fv_host is not None:
+            fv = sl.get(slot, "fv", (chunk, nfw), torch.int32)[:m]
+            fv.copy_(fv_host[lo:hi], non_blocking=True)
+        scl_decode_packed(plan, L, ai, xy=xy, frozen_packed=fv, out=(info, res))
+        info_host[lo:hi].copy_(info[:, :plan.Kw], non_blocking=True)
+        res_host[lo:hi].copy_(res, non_blocking=True)
+
+    host_pipeline(plan, B, chunk, body)
+
+
 def trellis_decode(plan, n0, deletion_prob, ones, sub_bits, sub_len, want_collapse=False):
     """Deletion-channel SC decoding (BinaryPolarEncoderDecoder.decode over a CollectionOfBinaryTrellises).
 

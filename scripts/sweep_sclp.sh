@@ -1,0 +1,17 @@
+#!/bin/bash
+# knob sweep of the path-per-lane list decoder (scl_path.cu); one process per setting
+mkdir -p gpurun_out
+out=gpurun_out/sweep_sclp.log
+: > $out
+PC_SCL_WARP=1 python scripts/sweep_sclp_old.py >> $out 2>&1
+for w in 6 8 10 12 16 20; do
+  PC_SCLP_WARPS_PER_SM=$w python scripts/sweep_sclp.py --mode probs >> $out 2>&1
+done
+for w in 8 12 16; do
+  PC_SCLP_WARPS_PER_SM=$w python scripts/sweep_sclp.py --mode sym >> $out 2>&1
+done
+PC_SCLP_WARPS_PER_SM=12 PC_SCLP_NOFUSE=1 python scripts/sweep_sclp.py --mode probs >> $out 2>&1
+PC_SCLP_WARPS_PER_SM=6 PC_SCLP_LSM=5 python scripts/sweep_sclp.py --mode probs >> $out 2>&1
+PC_SCLP_WARPS_PER_SM=12 PC_SCLP_RGL=9 python scripts/sweep_sclp.py --mode probs >> $out 2>&1
+PC_SCLP_WARPS_PER_SM=12 python scripts/sweep_sclp.py --mode probs --ebn0 1.0 >> $out 2>&1
+grep SWEEP $out
