@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sc_decode8_kernel(const ScParam
 // ---- ingest: caller layout [frames][N] -> transposed, bit-reversed [N][Bpad] --------------------------
 template <class T>
 __global__ void __launch_bounds__(256) ingest_kernel(int n, int64_t frames, int64_t Bpad, const T *__restrict__ in,
-                                                     T *__restrict__ out, T pad_value) {
+                                                     T *__restrict__ out, T pad_value, int ymax = 255) {
     __shared__ T tile[32][33];
     const int N = 1 << n;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -688,7 +688,9 @@ __global__ void __launch_bounds__(256) ingest_kernel(int n, int64_t frames, int6
         for (int r = ty; r < 32; r += 8) {
             const int64_t f = f0 + r;
             const int pos = i0 + tx;
-            tile[r][tx] = (f < frames && pos < N) ? in[f * N + pos] : pad_value;
+            T v = (f < frames && pos < N) ? in[f * N + pos] : pad_value;
+            if constexpr (sizeof(T) == 1) v = v > (T)ymax ? (T)ymax : v;  // symbols index a Y-row table: out-of-range bytes read row Y-1
+            tile[r][tx] = v;
         }
         __syncthreads();
         for (int r = ty; r < 32; r += 8) {
@@ -702,7 +704,7 @@ __global__ void __launch_bounds__(256) ingest_kernel(int n, int64_t frames, int6
 // uint8 symbols, N >= 128, 4-byte aligned input: 128 frames x 128 positions per tile, 4-byte global accesses on both
 // sides (a frame row is read as words, an output row is written as 4 frames per lane).
 __global__ void __launch_bounds__(256) ingest_u8_kernel(int n, int64_t frames, int64_t Bpad, const uint8_t *__restrict__ in,
-                                                        uint8_t *__restrict__ out) {
+                                                        uint8_t *__restrict__ out, int ymax) {
     __shared__ uint32_t tile[128][33];  // row (f & 3) * 32 + (f >> 2): the four frames of a lane sit 32 rows apart
     const int N = 1 << n;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -713,7 +715,8 @@ __global__ void __launch_bounds__(256) ingest_u8_kernel(int n, int64_t frames, i
 #pragma unroll 4
         for (int r = wrp; r < 128; r += 8) {
             const int64_t f = f0 + r;
-            tile[(r & 3) * 32 + (r >> 2)][lane] = f < frames ? in32[(f * N + i0) / 4 + lane] : 0u;
+            // symbols index a Y-row table: out-of-range bytes read row Y-1 (the ABI requires y < Y; this keeps the lookups in bounds)
+            tile[(r & 3) * 32 + (r >> 2)][lane] = f < frames ? __vminu4(in32[(f * N + i0) / 4 + lane], (uint32_t)ymax * 0x01010101u) : 0u;
         }
         __syncthreads();
         if (f0 + 4 * lane < Bpad) {
@@ -903,10 +906,10 @@ static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int
         dim3 ig((unsigned)tiles, (unsigned)(ptiles < 64 ? ptiles : 64));
         if (kind == PC_INPUT_SYMBOLS && N >= 128 && (((uintptr_t)d_in + (size_t)f0 * N) & 3) == 0) {
             dim3 ig8((unsigned)((frames + 127) / 128), (unsigned)((N >> 7) < 16 ? (N >> 7) : 16));
-            ingest_u8_kernel<<<ig8, 256, 0, st>>>(plan->n, frames, L.Bpad, (const uint8_t *)d_in + f0 * N, (uint8_t *)p.in_t);
+            ingest_u8_kernel<<<ig8, 256, 0, st>>>(plan->n, frames, L.Bpad, (const uint8_t *)d_in + f0 * N, (uint8_t *)p.in_t, Y - 1);
         } else if (kind == PC_INPUT_SYMBOLS) {
             ingest_kernel<uint8_t><<<ig, 256, 0, st>>>(plan->n, frames, L.Bpad, (const uint8_t *)d_in + f0 * N,
-                                                       (uint8_t *)p.in_t, (uint8_t)0);
+                                                       (uint8_t *)p.in_t, (uint8_t)0, Y - 1);
         } else {
             ingest_kernel<double2><<<ig, 256, 0, st>>>(plan->n, frames, L.Bpad, (const double2 *)d_in + f0 * N,
                                                        (double2 *)p.in_t, make_double2(0.5, 0.5));
@@ -1310,7 +1313,7 @@ static HyLayout hy_layout(const pc_plan *plan, HybridTables *T, int64_t chunk, b
     L.off_sub = o;
     size_t sb = 256;
     if (T)
-        for (size_t j = 0; j < T->sub.size(); j += T->sub.size() > 64 ? T->sub.size() / 64 : 1) {  // all sub-plans share (n, kind): same layout
+        for (size_t j = 0; j < T->sub.size(); ++j) {  // EVERY sub-plan: the layout depends on the sub-plan's k (host arithmetic only)
             const size_t b = sc_layout(T->sub[j], chunk, PC_INPUT_SYMBOLS).total;
             if (b > sb) sb = b;
         }
@@ -1386,10 +1389,10 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
         const int64_t tiles = (frames + 31) / 32;
         if ((((uintptr_t)d_y + (size_t)f0 * N) & 3) == 0) {
             dim3 ig8((unsigned)((frames + 127) / 128), (unsigned)((N >> 7) < 64 ? (N >> 7) : 64));
-            ingest_u8_kernel<<<ig8, 256, 0, st>>>(n, frames, Bp, d_y + f0 * N, sym);
+            ingest_u8_kernel<<<ig8, 256, 0, st>>>(n, frames, Bp, d_y + f0 * N, sym, Y - 1);
         } else {
             dim3 ig((unsigned)tiles, 64u);
-            ingest_kernel<uint8_t><<<ig, 256, 0, st>>>(n, frames, Bp, d_y + f0 * N, sym, (uint8_t)0);
+            ingest_kernel<uint8_t><<<ig, 256, 0, st>>>(n, frames, Bp, d_y + f0 * N, sym, (uint8_t)0, Y - 1);
         }
         PC_LAUNCH_CHECK();
         // level `lev` (>= HY_L0) of the current path: f, or g with the decision words of x[i - 2^lev, i)

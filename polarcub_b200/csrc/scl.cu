@@ -682,6 +682,7 @@ int pc_scl_decode_packed(const pc_plan *plan, int L, const double *d_xy, const u
     if (B == 0) return PC_OK;
     PC_REQUIRE((d_xy != nullptr) != (d_y != nullptr), "exactly one of d_xy / d_y must be given");
     if (d_y) PC_REQUIRE(h_table != nullptr && Y >= 1 && Y <= 256, "channel table missing or larger than 256 rows");
+    if (d_y) PC_REQUIRE(((uintptr_t)d_y & 3) == 0, "d_y must be 4-byte aligned");
     PC_REQUIRE(d_actual_info_packed && d_prob_result && d_workspace && (d_info_packed || plan->k == 0), "null buffer");
     PC_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "workspace must be 256-byte aligned");
     if (d_list_size) PC_REQUIRE(d_list_prob && d_actual_prob, "list outputs incomplete");

@@ -25,12 +25,14 @@
 // list outputs -- ProbResult needs actual_prob in no other case).
 #include <mutex>
 
+#include "async_copy.cuh"
 #include "scl_arith.cuh"
 
 namespace pc {
 
 struct SclpParams {
     int n, k, L, G, gsh, n_ops, lsm, rgl, NW, n_leaf, sym, want_list, nfw;
+    int nst;              // stages of the bulk-copy ring (0: plain loads)
     int64_t frames;
     const uint4 *ops;
     const uint32_t *coef_words;
@@ -51,50 +53,115 @@ struct SclpParams {
     double *mxs;          // [frames][n_leaf] list maximum at every fast node (the genie replay divides by them)
 };
 
-static size_t sclp_smem_bytes(int n, int lsm, int rgl) {
+static size_t sclp_smem_bytes(int n, int lsm, int rgl, int nst) {
     size_t b = (size_t)((2 << lsm) - 1) * 32 * 16;  // path vectors
     b += (size_t)2 * scl2_wsum(rgl) * 32 * 4;       // path codewords of levels < rgl
     b += (size_t)(n + 1) * 2 * 32;                  // parent maps
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)nst * (4 * 32 * 16 + 8);           // bulk-copy ring: four rows per stage, one mbarrier per stage
     return (b + 15) & ~(size_t)15;
 }
 
-// one f / g pass over the lane's own path (per-path layout on both sides): element e of the source at sp[e * 32], of the
-// destinations at dp[e * 32] / dp2[e * 32]; u bits of the left child's codeword at rp[word * 32]
-template <bool FUSED>
-__device__ __forceinline__ void fg_own(const double2 *sp, double2 *dp, double2 *dp2, const uint32_t *rp, const bool plus,
+// One f / g pass over the lane's own path.  Element e of the source comes from the loader (four consecutive elements per
+// step), of the destinations at dp[e * 32] / dp2[e * 32]; u bits of the left child's codeword at rp[word * 32].  The loads of
+// step it+1 are issued before the arithmetic of step it; source and destination levels never overlap (__restrict__).
+struct SrcStride {  // a path vector ([element][lane], stride 32) or the channel probability pairs (stride 1)
+    const double2 *__restrict__ p;
+    int ss;
+    __device__ __forceinline__ void load4(int it, double2 &a0, double2 &b0, double2 &a1, double2 &b1) const {
+        const double2 *q = p + (int64_t)(4 * it) * ss;
+        a0 = q[0], b0 = q[ss], a1 = q[2 * ss], b1 = q[3 * ss];
+    }
+};
+struct SrcSym {  // channel output symbols looked up in the channel table
+    const uint8_t *__restrict__ y;
+    const double2 *__restrict__ tab;
+    __device__ __forceinline__ void load4(int it, double2 &a0, double2 &b0, double2 &a1, double2 &b1) const {
+        const uchar4 v = *(const uchar4 *)(y + 4 * it);
+        a0 = tab[v.x], b0 = tab[v.y], a1 = tab[v.z], b1 = tab[v.w];
+    }
+};
+
+struct SrcDual {  // a two-variant vector (shared layout, element (e, v) at index 2 e + v): the path picks v = its bit e
+    const double2 *__restrict__ p;  // level base + the frame's first lane
+    const uint32_t *bits;           // the codeword that selected the variants, this path's column
+    int gsh;
+    __device__ __forceinline__ void load4(int it, double2 &a0, double2 &b0, double2 &a1, double2 &b1) const {
+        const uint32_t w = bits[((4 * it) >> 5) << 5] >> ((4 * it) & 31);
+        const int gm = (1 << gsh) - 1, i0 = 8 * it + (int)(w & 1u), i1 = 8 * it + 2 + (int)((w >> 1) & 1u);
+        const int i2 = 8 * it + 4 + (int)((w >> 2) & 1u), i3 = 8 * it + 6 + (int)((w >> 3) & 1u);
+        a0 = p[((i0 >> gsh) << 5) + (i0 & gm)], b0 = p[((i1 >> gsh) << 5) + (i1 & gm)];
+        a1 = p[((i2 >> gsh) << 5) + (i2 & gm)], b1 = p[((i3 >> gsh) << 5) + (i3 & gm)];
+    }
+};
+
+template <bool PLUS, bool FUSED, class Src>
+__device__ __forceinline__ void fg_own(const Src src, double2 *__restrict__ dp, double2 *__restrict__ dp2, const uint32_t *rp,
                                        const int half) {
-    if (!FUSED) {
+    const int niter = half >> 1;  // two elements of level l-1 per step (and one of level l-2 when fused)
+    double2 a0, b0, a1, b1;
+    src.load4(0, a0, b0, a1, b1);
+    uint32_t w = PLUS ? rp[0] : 0u;
 #pragma unroll 1
-        for (int hb = 0; hb < half; hb += 32) {
-            const uint32_t w = plus ? rp[(hb >> 5) << 5] : 0u;
-            const int m = half - hb < 32 ? half - hb : 32;
-#pragma unroll 2
-            for (int j = 0; j < m; j += 2) {
-                const double2 a0 = sp[0], b0 = sp[32], a1 = sp[64], b1 = sp[96];
-                const double2 y0 = node_update(a0, b0, plus, (w >> j) & 1u), y1 = node_update(a1, b1, plus, (w >> (j + 1)) & 1u);
-                dp[0] = y0;
-                dp[32] = y1;
-                sp += 128;
-                dp += 64;
-            }
+    for (int it = 0; it < niter; ++it) {
+        double2 na0 = a0, nb0 = b0, na1 = a1, nb1 = b1;
+        if (it + 1 < niter) src.load4(it + 1, na0, nb0, na1, nb1);
+        const int j = (2 * it) & 31;
+        const double2 y0 = PLUS ? node_g(a0, b0, (w >> j) & 1u) : node_f(a0, b0);
+        const double2 y1 = PLUS ? node_g(a1, b1, (w >> (j + 1)) & 1u) : node_f(a1, b1);
+        dp[0] = y0;
+        dp[32] = y1;
+        dp += 64;
+        if (FUSED) {
+            dp2[0] = node_f(y0, y1);
+            dp2 += 32;
         }
-    } else {
-        const int quarter = half >> 1;
+        if (PLUS && j == 30 && it + 1 < niter) w = rp[((2 * it + 2) >> 5) << 5];
+        a0 = na0, b0 = nb0, a1 = na1, b1 = nb1;
+    }
+}
+
+// The same pass with the source rows of a GLOBAL level staged through shared memory by bulk asynchronous copies: one step
+// consumes the four 512-byte rows [4 it, 4 it + 4) of the level array -- 2 KB contiguous in HBM -- that lane 0 requested NST
+// steps earlier; every lane then reads its path's column of the staged rows.  All 32 lanes run the loop (the ring is warp-wide);
+// lanes without a path skip the arithmetic.  `ph` keeps the phase parity of each stage across calls.
+template <bool PLUS, bool FUSED>
+__device__ __forceinline__ void fg_staged(const double2 *__restrict__ grows, const int col, const bool valid, double2 *__restrict__ dp,
+                                          double2 *__restrict__ dp2, const uint32_t *rp, const int half, double2 *stg, uint64_t *bars,
+                                          const int nst, uint32_t &ph, const int lane) {
+    const int niter = half >> 1;
+    if (lane == 0) {
+        const int pre = niter < nst ? niter : nst;
+        for (int s = 0; s < pre; ++s) {
+            mbar_expect_tx(bars + s, 2048u);
+            bulk_g2s(stg + s * 128, grows + (int64_t)s * 128, 2048u, bars + s);
+        }
+    }
+    uint32_t w = (PLUS && valid) ? rp[0] : 0u;
 #pragma unroll 1
-        for (int hb = 0; hb < quarter; hb += 16) {
-            const uint32_t w = plus ? rp[(hb >> 4) << 5] : 0u;
-            const int m = quarter - hb < 16 ? quarter - hb : 16;
-#pragma unroll 2
-            for (int j = 0; j < m; ++j) {
-                const double2 a0 = sp[0], b0 = sp[32], a1 = sp[64], b1 = sp[96];
-                const double2 y0 = node_update(a0, b0, plus, (w >> (2 * j)) & 1u), y1 = node_update(a1, b1, plus, (w >> (2 * j + 1)) & 1u);
-                dp[0] = y0;
-                dp[32] = y1;
-                dp2[0] = node_update(y0, y1, false, 0u);
-                sp += 128;
-                dp += 64;
+    for (int it = 0; it < niter; ++it) {
+        const int s = it & (nst - 1);
+        mbar_wait(bars + s, (ph >> s) & 1u);
+        ph ^= 1u << s;
+        const double2 *q = stg + s * 128 + col;
+        const double2 a0 = q[0], b0 = q[32], a1 = q[64], b1 = q[96];
+        __syncwarp();
+        if (lane == 0 && it + nst < niter) {
+            mbar_expect_tx(bars + s, 2048u);
+            bulk_g2s(stg + s * 128, grows + (int64_t)(it + nst) * 128, 2048u, bars + s);
+        }
+        if (valid) {
+            const int j = (2 * it) & 31;
+            const double2 y0 = PLUS ? node_g(a0, b0, (w >> j) & 1u) : node_f(a0, b0);
+            const double2 y1 = PLUS ? node_g(a1, b1, (w >> (j + 1)) & 1u) : node_f(a1, b1);
+            dp[0] = y0;
+            dp[32] = y1;
+            dp += 64;
+            if (FUSED) {
+                dp2[0] = node_f(y0, y1);
                 dp2 += 32;
             }
+            if (PLUS && j == 30 && it + 1 < niter) w = rp[((2 * it + 2) >> 5) << 5];
         }
     }
 }
@@ -162,7 +229,9 @@ __device__ __forceinline__ void select_paths(const double (&cv)[M], const int ib
     nout = ns;
 }
 
-__global__ void __launch_bounds__(32) sclp_kernel(const SclpParams p) {
+// MB = resident warps per SM the build is register-capped for (picked by the host from the shared-memory footprint)
+template <int MB>
+__global__ void __launch_bounds__(32, MB) sclp_kernel(const SclpParams p) {
     PC_DYN_SMEM(smem_raw);
     const int n = p.n, N = 1 << n, L = p.L, G = p.G, gsh = p.gsh, lsm = p.lsm, NW = p.NW, rgl = p.rgl;
     const int lane = threadIdx.x, t = lane & (G - 1), gbase = lane & ~(G - 1);
@@ -172,6 +241,16 @@ __global__ void __launch_bounds__(32) sclp_kernel(const SclpParams p) {
     double2 *Vs = (double2 *)smem_raw;
     uint32_t *Rs = (uint32_t *)(Vs + vrows * 32);
     uint8_t *om = (uint8_t *)(Rs + 2 * scl2_wsum(rgl) * 32);
+    double2 *stg = (double2 *)(smem_raw + (((size_t)((char *)(om + (n + 1) * 2 * 32) - (char *)smem_raw) + 15) & ~(size_t)15));
+    uint64_t *bars = (uint64_t *)(stg + p.nst * 128);
+    uint32_t ph = 0;
+    if (p.nst) {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < p.nst; ++s) mbar_init(bars + s, 1u);
+            mbar_fence_init();
+        }
+        __syncwarp();
+    }
     double2 *Vg = p.vg + (int64_t)blockIdx.x * p.vg_stride - (int64_t)vrows * 32;
     uint32_t *Rg = p.rg + (int64_t)blockIdx.x * p.rg_stride - (int64_t)2 * scl2_wsum(rgl) * 32;
     // level l of the path vectors: rows (2^l - 1) .. ; per-path layout: element e of slot s at [e][gbase + s]; shared layout
@@ -180,6 +259,7 @@ __global__ void __launch_bounds__(32) sclp_kernel(const SclpParams p) {
     auto rbase = [&](int l, int c) -> uint32_t * { return (l < rgl ? Rs : Rg) + (int64_t)(2 * scl2_wsum(l) + c * scl2_W(l)) * 32; };
     auto OM = [&](int l, int c) -> uint8_t * { return om + (l * 2 + c) * 32; };
     const int fpw = 32 >> gsh;
+    const bool dualon = G >= 4;  // two-variant storage of SCLP_DUAL outputs pays with four or more paths
 
 #pragma unroll 1
     for (int64_t wave = blockIdx.x; wave * fpw < p.frames; wave += gridDim.x) {
@@ -197,12 +277,17 @@ __global__ void __launch_bounds__(32) sclp_kernel(const SclpParams p) {
             const uint4 op = p.ops[oi];
             const int kind = op.x & 7, l = (op.x >> 3) & 15, c = (op.x >> 7) & 1, i0 = (int)op.y;
             const bool ssrc = op.x & SCLP_SSRC, sdst = op.x & SCLP_SDST, chan = op.x & SCLP_CHAN;
+            const bool dsrc = dualon && (op.x & SCLP_DSRC), ddst = dualon && (op.x & SCLP_DUAL);
             const int size = 1 << l;
             const bool valid = t < cnt;
             // element j of the source vector of this op, for the slot `slot` of the lane's frame
             auto ldsrc = [&](int e, int slot) -> double2 {
                 if (chan) return p.sym ? p.tab[yf[e]] : xyf[e];
                 const double2 *b = vbase(l);
+                if (dsrc) {
+                    const int i = 2 * e + (int)((rbase(l, 0)[((e >> 5) << 5) + gbase + slot] >> (e & 31)) & 1u);
+                    return b[((i >> gsh) << 5) + gbase + (i & (G - 1))];
+                }
                 return ssrc ? b[((e >> gsh) << 5) + gbase + (e & (G - 1))] : b[(e << 5) + gbase + slot];
             };
             if (kind == OP_MINUS || kind == OP_PLUS) {
@@ -211,55 +296,117 @@ __global__ void __launch_bounds__(32) sclp_kernel(const SclpParams p) {
                 int srcslot = t;
                 if (plus && !sdst && valid) srcslot = OM(l - 1, 0)[lane];
                 const uint32_t *rp = rbase(l - 1, 0) + (sdst ? gbase : lane);  // u bits: the left child's codeword of this path
-                if (!chan && !ssrc && !sdst) {
-                    if (valid) {
-                        // address spaces resolved per call site: all shared, all global, or mixed (generic)
-                        if (l <= lsm) {
-                            const double2 *sp = Vs + ((1 << l) - 1) * 32 + gbase + srcslot;
-                            double2 *dp = Vs + ((1 << (l - 1)) - 1) * 32 + lane, *dp2 = Vs + ((1 << (l - 2)) - 1) * 32 + lane;
-                            if (fused)
-                                fg_own<true>(sp, dp, dp2, rp, plus, half);
+                if (ddst) {
+                    // one shared parent (the channel or a shared-layout vector) and four or more paths: the output has only two
+                    // variants per element, g(a, b, 0) and g(a, b, 1); the lanes of the frame share the 2 x half items, the
+                    // paths pick their variant by their codeword bit when they read the vector (SrcDual / ldsrc)
+                    const double2 *sb = chan ? nullptr : vbase(l);
+                    double2 *db = vbase(l - 1);
+#pragma unroll 1
+                    for (int i = t; i < size; i += G) {
+                        const int e = i >> 1;
+                        double2 a, b;
+                        if (chan) {
+                            if (p.sym)
+                                a = p.tab[yf[2 * e]], b = p.tab[yf[2 * e + 1]];
                             else
-                                fg_own<false>(sp, dp, dp2, rp, plus, half);
-                        } else if (fused ? l - 2 > lsm : l - 1 > lsm) {
-                            const double2 *sp = Vg + (((int64_t)1 << l) - 1) * 32 + gbase + srcslot;
-                            double2 *dp = Vg + (((int64_t)1 << (l - 1)) - 1) * 32 + lane, *dp2 = Vg + (((int64_t)1 << (l - 2)) - 1) * 32 + lane;
-                            if (fused)
-                                fg_own<true>(sp, dp, dp2, rp, plus, half);
-                            else
-                                fg_own<false>(sp, dp, dp2, rp, plus, half);
+                                a = xyf[2 * e], b = xyf[2 * e + 1];
                         } else {
-                            const double2 *sp = vbase(l) + gbase + srcslot;
-                            double2 *dp = vbase(l - 1) + lane, *dp2 = l >= 2 ? vbase(l - 2) + lane : nullptr;
+                            const double2 *q = sb + (((2 * e) >> gsh) << 5) + gbase + ((2 * e) & (G - 1));
+                            a = q[0], b = q[1];
+                        }
+                        db[((i >> gsh) << 5) + gbase + (i & (G - 1))] = node_g(a, b, (uint32_t)(i & 1));
+                    }
+                } else if (!sdst && !ssrc && !(chan && p.sym && !plus)) {
+                    // the lane's own path: per-path destination, source = a per-path vector or the channel
+                    if (!chan && !dsrc && l > lsm && p.nst) {
+                        // source level in HBM: rows staged through the bulk-copy ring (all lanes run the loop)
+                        double2 *dp = vbase(l - 1) + lane, *dp2 = vbase(l - 2) + lane;
+                        const double2 *grows = Vg + (((int64_t)1 << l) - 1) * 32;
+                        const int col = gbase + srcslot;
+                        if (plus) {
                             if (fused)
-                                fg_own<true>(sp, dp, dp2, rp, plus, half);
+                                fg_staged<true, true>(grows, col, valid, dp, dp2, rp, half, stg, bars, p.nst, ph, lane);
                             else
-                                fg_own<false>(sp, dp, dp2, rp, plus, half);
+                                fg_staged<true, false>(grows, col, valid, dp, dp2, rp, half, stg, bars, p.nst, ph, lane);
+                        } else {
+                            if (fused)
+                                fg_staged<false, true>(grows, col, valid, dp, dp2, rp, half, stg, bars, p.nst, ph, lane);
+                            else
+                                fg_staged<false, false>(grows, col, valid, dp, dp2, rp, half, stg, bars, p.nst, ph, lane);
+                        }
+                    } else if (valid) {
+                        double2 *dp = vbase(l - 1) + lane, *dp2 = l >= 2 ? vbase(l - 2) + lane : nullptr;
+                        if (dsrc) {
+                            const SrcDual sr{vbase(l) + gbase, rbase(l, 0) + gbase + srcslot, gsh};
+                            if (plus) {
+                                if (fused)
+                                    fg_own<true, true>(sr, dp, dp2, rp, half);
+                                else
+                                    fg_own<true, false>(sr, dp, dp2, rp, half);
+                            } else {
+                                if (fused)
+                                    fg_own<false, true>(sr, dp, dp2, rp, half);
+                                else
+                                    fg_own<false, false>(sr, dp, dp2, rp, half);
+                            }
+                        } else if (chan && p.sym) {
+                            // the channel level is the source of PLUS (n) only (MINUS (n) runs before the first fork)
+                            const SrcSym sr{yf, p.tab};
+                            if (fused)
+                                fg_own<true, true>(sr, dp, dp2, rp, half);
+                            else
+                                fg_own<true, false>(sr, dp, dp2, rp, half);
+                        } else {
+                            const SrcStride sr{chan ? xyf : vbase(l) + gbase + srcslot, chan ? 1 : 32};
+                            if (plus) {
+                                if (fused)
+                                    fg_own<true, true>(sr, dp, dp2, rp, half);
+                                else
+                                    fg_own<true, false>(sr, dp, dp2, rp, half);
+                            } else {
+                                if (fused)
+                                    fg_own<false, true>(sr, dp, dp2, rp, half);
+                                else
+                                    fg_own<false, false>(sr, dp, dp2, rp, half);
+                            }
                         }
                     }
                 } else {
-                    // channel / shared-layout sources, cooperative (single path) mode
-                    double2 *d1 = vbase(l - 1), *d2 = l >= 2 ? vbase(l - 2) : nullptr;
-                    auto dst = [&](double2 *b, int e) -> double2 * {
-                        return sdst ? b + ((e >> gsh) << 5) + gbase + (e & (G - 1)) : b + (e << 5) + lane;
-                    };
-                    auto ubit = [&](int h) -> uint32_t { return plus ? (rp[(h >> 5) << 5] >> (h & 31)) & 1u : 0u; };
-                    const int h0 = sdst ? t : 0, hs = sdst ? G : 1;
-                    if (sdst || valid) {
-                        if (!fused) {
+                    // shared-layout sources and the cooperative (single path) mode before the first fork: one level per pass
+                    const int npass = fused ? 2 : 1;
 #pragma unroll 1
-                            for (int h = h0; h < half; h += hs)
-                                *dst(d1, h) = node_update(ldsrc(2 * h, srcslot), ldsrc(2 * h + 1, srcslot), plus, ubit(h));
-                        } else {
+                    for (int ps = 0; ps < npass; ++ps) {
+                        const int lv = l - ps;
+                        const bool pl = plus && ps == 0, shs = ps == 0 ? ssrc : sdst, ch = chan && ps == 0;
+                        const double2 *sb = ch ? nullptr : vbase(lv);
+                        double2 *db = vbase(lv - 1);
+                        const int h0 = sdst ? t : 0, hs = sdst ? G : 1;
+                        if (sdst || valid) {
 #pragma unroll 1
-                            for (int h = h0; h < (half >> 1); h += hs) {
-                                const double2 y0 = node_update(ldsrc(4 * h, srcslot), ldsrc(4 * h + 1, srcslot), plus, ubit(2 * h));
-                                const double2 y1 = node_update(ldsrc(4 * h + 2, srcslot), ldsrc(4 * h + 3, srcslot), plus, ubit(2 * h + 1));
-                                *dst(d1, 2 * h) = y0;
-                                *dst(d1, 2 * h + 1) = y1;
-                                *dst(d2, h) = node_update(y0, y1, false, 0u);
+                            for (int h = h0; h < (1 << (lv - 1)); h += hs) {
+                                double2 a, b;
+                                if (ch) {
+                                    if (p.sym)
+                                        a = p.tab[yf[2 * h]], b = p.tab[yf[2 * h + 1]];
+                                    else
+                                        a = xyf[2 * h], b = xyf[2 * h + 1];
+                                } else if (shs) {
+                                    const double2 *q = sb + (((2 * h) >> gsh) << 5) + gbase;
+                                    if (G >= 2)
+                                        a = q[(2 * h) & (G - 1)], b = q[((2 * h) & (G - 1)) + 1];
+                                    else
+                                        a = q[0], b = q[32];
+                                } else {
+                                    const double2 *q = sb + ((2 * h) << 5) + (ps == 0 ? gbase + srcslot : lane);  // pass 2: the vector just written
+                                    a = q[0], b = q[32];
+                                }
+                                const uint32_t u = pl ? (rp[(h >> 5) << 5] >> (h & 31)) & 1u : 0u;
+                                double2 *d = sdst ? db + ((h >> gsh) << 5) + gbase + (h & (G - 1)) : db + (h << 5) + lane;
+                                *d = node_update(a, b, pl, u);
                             }
                         }
+                        if (ps + 1 < npass) __syncwarp();
                     }
                 }
                 __syncwarp();
@@ -809,7 +956,7 @@ __global__ void __launch_bounds__(256) sclp_tab_kernel(const SclpTab t, double2 
 
 // ---- host side ------------------------------------------------------------------------------------------------
 struct SclpConfig {
-    int G, gsh, lsm, rgl, lsmA, grid, grid2;
+    int G, gsh, lsm, rgl, lsmA, grid, grid2, per_sm, nst;
     size_t smem, smem2, vg_stride, rg_stride, va_stride;
     bool ok;
 };
@@ -822,11 +969,12 @@ static int envp_int(const char *name, int dflt) {
 // tuning knobs are read ONCE per process (a changed environment between the workspace query and the decode cannot break
 // the sizing contract)
 struct SclpKnobs {
-    int warps_per_sm, lsm, rgl, off;
+    int warps_per_sm, lsm, rgl, off, nst;
     SclpKnobs() {
         warps_per_sm = envp_int("PC_SCLP_WARPS_PER_SM", 12);
         lsm = envp_int("PC_SCLP_LSM", -1);
         rgl = envp_int("PC_SCLP_RGL", 7);
+        nst = envp_int("PC_SCLP_STAGES", 4);
         off = envp_int("PC_SCL_WARP", 0) || envp_int("PC_SCL_GENERIC", 0) || envp_int("PC_SCL_CTA", 0);
     }
 };
@@ -856,15 +1004,19 @@ static SclpConfig sclp_config(const pc_plan *plan, int L, int64_t B) {
     const size_t budget = (size_t)(227 * 1024) / (size_t)target - 1024;
     int lsm = n - 1 < 6 ? n - 1 : 6;
     if (lsm < 1) lsm = 1;
-    while (lsm > 1 && sclp_smem_bytes(n, lsm, rgl) > budget) --lsm;
+    int nst = kn.nst;
+    nst = nst >= 8 ? 8 : nst >= 4 ? 4 : nst >= 2 ? 2 : 0;  // a power of two, or 0 = plain loads
+    c.nst = nst;
+    while (lsm > 1 && sclp_smem_bytes(n, lsm, rgl, nst) > budget) --lsm;
     if (kn.lsm >= 1 && kn.lsm <= 7) lsm = kn.lsm;
     c.lsm = lsm;
-    c.smem = sclp_smem_bytes(n, lsm, rgl);
+    c.smem = sclp_smem_bytes(n, lsm, rgl, nst);
     if (c.smem > 220 * 1024) return c;
     int per_sm = (int)((227 * 1024) / (c.smem + 1024));
     if (per_sm > target) per_sm = target;
     if (per_sm > 32) per_sm = 32;
     if (per_sm < 1) per_sm = 1;
+    c.per_sm = per_sm;
     const int fpw = 32 / G;
     int64_t waves = (B + fpw - 1) / fpw;
     int64_t grid = (int64_t)num_sms() * per_sm;
@@ -940,6 +1092,14 @@ size_t sclp_workspace_bytes(const pc_plan *plan, int L, int64_t B, bool want_lis
     return sclp_layout(plan, T, L, B, want_list, true).total;
 }
 
+template <int MB>
+static int sclp_launch(const SclpParams &p, int grid, size_t smem, cudaStream_t st) {
+    PC_CUDA(cudaFuncSetAttribute(sclp_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PC_LAUNCH(sclp_kernel<MB>, grid, 32, smem, st, p);
+    PC_LAUNCH_CHECK();
+    return PC_OK;
+}
+
 // The decoder proper on packed inputs.  d_xy (float64 pairs) or d_y + d_tab (symbols); d_fvp may be null (all-zero frozen
 // values); outputs packed information [B][kw], ProbResult [B] and the optional final-list outputs.
 struct SclpIo {
@@ -969,7 +1129,6 @@ static int sclp_run(const pc_plan *plan, const SclTables *T, int L, const SclpIo
         PC_LAUNCH(sclp_tab_kernel, 1, 256, 0, st, tb, d_tab);
         PC_LAUNCH_CHECK();
     }
-    PC_CUDA(cudaFuncSetAttribute(sclp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     for (int64_t f0 = 0; f0 < B; f0 += SCLP_CHUNK) {
         const int64_t F = B - f0 < SCLP_CHUNK ? B - f0 : SCLP_CHUNK;
         SclpPrepParams q{};
@@ -988,6 +1147,7 @@ static int sclp_run(const pc_plan *plan, const SclTables *T, int L, const SclpIo
 
         SclpParams p{};
         p.n = plan->n, p.k = k, p.L = L, p.G = c.G, p.gsh = c.gsh, p.lsm = c.lsm, p.rgl = c.rgl, p.NW = NW;
+        p.nst = c.nst;
         p.n_ops = (int)T->opsP.size(), p.n_leaf = T->n_leaf, p.sym = io.d_y ? 1 : 0, p.want_list = want_list ? 1 : 0, p.nfw = nfw;
         p.frames = F;
         p.ops = T->d_opsP;
@@ -1011,9 +1171,21 @@ static int sclp_run(const pc_plan *plan, const SclTables *T, int L, const SclpIo
         int64_t grid = (F + fpw - 1) / fpw;
         if (grid > c.grid) grid = c.grid;
         prof_mark(st);
-        PC_LAUNCH(sclp_kernel, (int)grid, 32, c.smem, st, p);
+        {
+            int rc;
+            if (c.per_sm <= 12)
+                rc = sclp_launch<12>(p, (int)grid, c.smem, st);
+            else if (c.per_sm <= 16)
+                rc = sclp_launch<16>(p, (int)grid, c.smem, st);
+            else if (c.per_sm <= 20)
+                rc = sclp_launch<20>(p, (int)grid, c.smem, st);
+            else if (c.per_sm <= 24)
+                rc = sclp_launch<24>(p, (int)grid, c.smem, st);
+            else
+                rc = sclp_launch<32>(p, (int)grid, c.smem, st);
+            if (rc) return rc;
+        }
         prof_mark(st);
-        PC_LAUNCH_CHECK();
 
         SclpFinalParams r{};
         r.n = plan->n, r.k = k, r.L = L, r.NW = NW, r.kw = kw, r.n_ops = p.n_ops, r.n_leaf = T->n_leaf, r.sym = p.sym;

@@ -169,18 +169,22 @@ SclTables *scl_tables(const pc_plan *p) {
         }
         {   // scl_path.cu: layout flags from a static walk (the list holds one path until the first forking node)
             bool single = true;
-            std::vector<char> lay(p->n + 1, 0);
+            std::vector<char> lay(p->n + 1, 0);  // 0 per-path, 1 shared (single path), 2 dual (two variants of a shared parent)
             std::vector<uint4> tmp;
             for (const SclOp &o : T->ops) {
                 uint32_t x = (uint32_t)o.kind | (uint32_t)o.l << 3 | (uint32_t)o.c << 7;
                 const bool chan = o.l == p->n;
                 if (chan) x |= SCLP_CHAN;
                 if (o.kind == OP_MINUS || o.kind == OP_PLUS) {
-                    if (!chan && lay[o.l]) x |= SCLP_SSRC;
+                    if (!chan && lay[o.l] == 1) x |= SCLP_SSRC;
+                    if (!chan && lay[o.l] == 2) x |= SCLP_DSRC;
                     if (single) x |= SCLP_SDST;
-                    lay[o.l - 1] = single;
+                    const bool dual = o.kind == OP_PLUS && !single && (chan || lay[o.l] == 1);
+                    if (dual) x |= SCLP_DUAL;
+                    lay[o.l - 1] = single ? 1 : (dual ? 2 : 0);
                 } else if (o.kind != OP_COMBINE) {
-                    if (!chan && lay[o.l]) x |= SCLP_SSRC;
+                    if (!chan && lay[o.l] == 1) x |= SCLP_SSRC;
+                    if (!chan && lay[o.l] == 2) x |= SCLP_DSRC;
                     if (single) x |= SCLP_SDST;
                     if (o.kind != OP_RATE0) single = false;
                     ++T->n_leaf;
@@ -194,8 +198,8 @@ SclTables *scl_tables(const pc_plan *p) {
             for (size_t a = 0; a < tmp.size(); ++a) {
                 uint4 o = tmp[a];
                 const int kind = o.x & 7, l = (o.x >> 3) & 15;
-                if (fuse && (kind == OP_MINUS || kind == OP_PLUS) && l >= 3 && a + 1 < tmp.size() && (tmp[a + 1].x & 7) == OP_MINUS &&
-                    (int)((tmp[a + 1].x >> 3) & 15) == l - 1) {
+                if (fuse && (kind == OP_MINUS || kind == OP_PLUS) && !(o.x & SCLP_DUAL) && l >= 3 && a + 1 < tmp.size() &&
+                    (tmp[a + 1].x & 7) == OP_MINUS && (int)((tmp[a + 1].x >> 3) & 15) == l - 1) {
                     o.x |= SCLP_FUSED;
                     ++a;
                 }

@@ -15,7 +15,10 @@ enum : uint32_t {
     SCLP_SSRC = 1u << 8,   // the source vector is in the shared ("single path") layout: written before the first fork
     SCLP_SDST = 1u << 9,   // the op runs before the first fork: one path, the lanes of a frame share its elements
     SCLP_FUSED = 1u << 10, // MINUS / PLUS (l) with the following MINUS (l-1) folded in
-    SCLP_CHAN = 1u << 11   // the source is the channel level (l == n)
+    SCLP_CHAN = 1u << 11,  // the source is the channel level (l == n)
+    SCLP_DUAL = 1u << 12,  // PLUS after the first fork whose source is one shared vector (or the channel): its output has two
+                           // variants per element only, g(a, b, 0) and g(a, b, 1); lists of 4+ store those instead of L vectors
+    SCLP_DSRC = 1u << 13   // the source level was written by a SCLP_DUAL op
 };
 
 struct alignas(16) SclOp {

@@ -14,7 +14,7 @@ from polarcub_b200 import engine  # noqa: E402
 from polarcub_b200.construction import frozen_set_from_pe, load_pe  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--frames", type=int, default=16384)
+ap.add_argument("--frames", type=int, default=0, help="0 = three resident waves")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--mode", default="probs")
 ap.add_argument("--L", type=int, default=8)
@@ -28,7 +28,7 @@ dev = torch.device("cuda", 0)
 plan = engine.Plan(2, n, fm, None, device=dev)
 gen = torch.Generator(device=dev)
 gen.manual_seed(99)
-B = a.frames
+B = a.frames or 3 * engine.scl_wave_frames(plan, L)
 info = torch.randint(0, 2, (B, K), dtype=torch.uint8, device=dev, generator=gen)
 cw = engine.qsc_encode(plan, info)
 sigma = math.sqrt(1.0 / (2.0 * 0.5 * 10.0 ** (a.ebn0 / 10.0)))

@@ -32,6 +32,8 @@
 #define __shared__ static  // static shared arrays: one block runs at a time
 #undef __launch_bounds__
 #define __launch_bounds__(...)
+#undef __noinline__
+#define __noinline__ __attribute__((noinline))
 
 namespace emu {
 
