@@ -51,6 +51,7 @@ struct SclpParams {
     int32_t *lsize;       // [frames]
     double *lprob;        // [frames][L] normalised metrics in list order
     double *mxs;          // [frames][n_leaf] list maximum at every fast node (the genie replay divides by them)
+    unsigned long long *timing;  // optional [8][16] cycles per (op kind, level), summed over warps (tuning runs: PC_SCLP_TIMING)
 };
 
 static size_t sclp_smem_bytes(int n, int lsm, int rgl, int nst) {
@@ -58,111 +59,139 @@ static size_t sclp_smem_bytes(int n, int lsm, int rgl, int nst) {
     b += (size_t)2 * scl2_wsum(rgl) * 32 * 4;       // path codewords of levels < rgl
     b += (size_t)(n + 1) * 2 * 32;                  // parent maps
     b = (b + 15) & ~(size_t)15;
-    b += (size_t)nst * (4 * 32 * 16 + 8);           // bulk-copy ring: four rows per stage, one mbarrier per stage
+    b += (size_t)nst * (8 * 32 * 16 + 8);           // bulk-copy ring: eight rows per stage, one mbarrier per stage
     return (b + 15) & ~(size_t)15;
 }
 
-// One f / g pass over the lane's own path.  Element e of the source comes from the loader (four consecutive elements per
-// step), of the destinations at dp[e * 32] / dp2[e * 32]; u bits of the left child's codeword at rp[word * 32].  The loads of
-// step it+1 are issued before the arithmetic of step it; source and destination levels never overlap (__restrict__).
-struct SrcStride {  // a path vector ([element][lane], stride 32) or the channel probability pairs (stride 1)
-    const double2 *__restrict__ p;
-    int ss;
-    __device__ __forceinline__ void load4(int it, double2 &a0, double2 &b0, double2 &a1, double2 &b1) const {
-        const double2 *q = p + (int64_t)(4 * it) * ss;
-        a0 = q[0], b0 = q[ss], a1 = q[2 * ss], b1 = q[3 * ss];
-    }
+// ---- the f / g pass over the lane's own path ------------------------------------------------------------------------------------
+// ONE loop serves every source kind through warp-uniform switches, so that the kernel's hot code stays resident in the
+// instruction cache while 12-24 warps per SM sit at different ops of the list.  A step takes EIGHT consecutive source elements:
+// four independent level l-1 updates and (fused) two level l-2 updates -- the float64 division of the normalisation is a chain of
+// ~14 dependent operations, and interleaved chains are what keeps the FP64 pipe fed with 3-4 warps per scheduler.  The raw
+// elements of step k+1 are fetched before step k is computed.
+enum : int { SK_PATH = 0, SK_STAGED = 1, SK_SYM = 2, SK_DUAL = 3, SK_SHARED = 4 };
+struct Src {
+    int kind;
+    // SK_PATH: float64 pairs at element stride ss: a path vector ([element][lane], stride 32) or the channel probabilities (1)
+    // SK_STAGED: an HBM level through the bulk-copy ring: a stage holds the eight 512-byte rows of a step (4 KB contiguous in
+    //   HBM), requested by lane 0 `nst` steps ahead; every lane reads its path's column `col` of the staged rows
+    // SK_DUAL / SK_SHARED: pairs in the shared layout from p = level base + the frame's first lane; SK_DUAL picks variant
+    //   v = bit e of `bits` (the codeword that selected the variants, this path's column): index 2 e + v
+    // SK_SYM: channel symbols through the channel table
+    const double2 *p;
+    int ss, gsh;
+    const uint32_t *bits;
+    const uint8_t *y;
+    const double2 *tab;
+    double2 *stg;
+    uint64_t *bars;
+    uint32_t *ph;
+    int nst, nsteps, col, lane;
 };
-struct SrcSym {  // channel output symbols looked up in the channel table
-    const uint8_t *__restrict__ y;
-    const double2 *__restrict__ tab;
-    __device__ __forceinline__ void load4(int it, double2 &a0, double2 &b0, double2 &a1, double2 &b1) const {
-        const uchar4 v = *(const uchar4 *)(y + 4 * it);
-        a0 = tab[v.x], b0 = tab[v.y], a1 = tab[v.z], b1 = tab[v.w];
-    }
+struct Raw8 {
+    double2 v[8];
 };
-
-struct SrcDual {  // a two-variant vector (shared layout, element (e, v) at index 2 e + v): the path picks v = its bit e
-    const double2 *__restrict__ p;  // level base + the frame's first lane
-    const uint32_t *bits;           // the codeword that selected the variants, this path's column
-    int gsh;
-    __device__ __forceinline__ void load4(int it, double2 &a0, double2 &b0, double2 &a1, double2 &b1) const {
-        const uint32_t w = bits[((4 * it) >> 5) << 5] >> ((4 * it) & 31);
-        const int gm = (1 << gsh) - 1, i0 = 8 * it + (int)(w & 1u), i1 = 8 * it + 2 + (int)((w >> 1) & 1u);
-        const int i2 = 8 * it + 4 + (int)((w >> 2) & 1u), i3 = 8 * it + 6 + (int)((w >> 3) & 1u);
-        a0 = p[((i0 >> gsh) << 5) + (i0 & gm)], b0 = p[((i1 >> gsh) << 5) + (i1 & gm)];
-        a1 = p[((i2 >> gsh) << 5) + (i2 & gm)], b1 = p[((i3 >> gsh) << 5) + (i3 & gm)];
-    }
-};
-
-template <bool PLUS, bool FUSED, class Src>
-__device__ __forceinline__ void fg_own(const Src src, double2 *__restrict__ dp, double2 *__restrict__ dp2, const uint32_t *rp,
-                                       const int half) {
-    const int niter = half >> 1;  // two elements of level l-1 per step (and one of level l-2 when fused)
-    double2 a0, b0, a1, b1;
-    src.load4(0, a0, b0, a1, b1);
-    uint32_t w = PLUS ? rp[0] : 0u;
-#pragma unroll 1
-    for (int it = 0; it < niter; ++it) {
-        double2 na0 = a0, nb0 = b0, na1 = a1, nb1 = b1;
-        if (it + 1 < niter) src.load4(it + 1, na0, nb0, na1, nb1);
-        const int j = (2 * it) & 31;
-        const double2 y0 = PLUS ? node_g(a0, b0, (w >> j) & 1u) : node_f(a0, b0);
-        const double2 y1 = PLUS ? node_g(a1, b1, (w >> (j + 1)) & 1u) : node_f(a1, b1);
-        dp[0] = y0;
-        dp[32] = y1;
-        dp += 64;
-        if (FUSED) {
-            dp2[0] = node_f(y0, y1);
-            dp2 += 32;
+__device__ __forceinline__ void src_issue(const Src &s, int k) {
+    const int st = k & (s.nst - 1);
+    mbar_expect_tx(s.bars + st, 4096u);
+    bulk_g2s(s.stg + st * 256, s.p + (int64_t)k * 256, 4096u, s.bars + st);
+}
+__device__ __forceinline__ double2 src_at(const Src &s, int i) { return s.p[((i >> s.gsh) << 5) + (i & ((1 << s.gsh) - 1))]; }
+// raw elements [8k, 8k + CNT) of the source (CNT = 8, or 4 for the two-element levels)
+template <int CNT>
+__device__ __forceinline__ void src_fetch(const Src &s, int k, Raw8 &r) {
+    switch (s.kind) {
+        case SK_PATH: {
+            const double2 *q = s.p + (int64_t)(8 * k) * s.ss;
+#pragma unroll
+            for (int i = 0; i < CNT; ++i) r.v[i] = q[i * s.ss];
+            break;
         }
-        if (PLUS && j == 30 && it + 1 < niter) w = rp[((2 * it + 2) >> 5) << 5];
-        a0 = na0, b0 = nb0, a1 = na1, b1 = nb1;
+        case SK_STAGED: {
+            const int st = k & (s.nst - 1);
+            mbar_wait(s.bars + st, (*s.ph >> st) & 1u);
+            *s.ph ^= 1u << st;
+            const double2 *q = s.stg + st * 256 + s.col;
+#pragma unroll
+            for (int i = 0; i < CNT; ++i) r.v[i] = q[i << 5];
+            __syncwarp();
+            if (s.lane == 0 && k + s.nst < s.nsteps) src_issue(s, k + s.nst);
+            break;
+        }
+        case SK_SYM: {
+            const uint8_t *q = s.y + 8 * k;
+#pragma unroll
+            for (int i = 0; i < CNT; ++i) r.v[i] = s.tab[q[i]];
+            break;
+        }
+        case SK_DUAL: {
+            const uint32_t w = s.bits[((8 * k) >> 5) << 5] >> ((8 * k) & 31);
+#pragma unroll
+            for (int i = 0; i < CNT; ++i) r.v[i] = src_at(s, 16 * k + 2 * i + (int)((w >> i) & 1u));
+            break;
+        }
+        default:
+#pragma unroll
+            for (int i = 0; i < CNT; ++i) r.v[i] = src_at(s, 8 * k + i);
     }
 }
 
-// The same pass with the source rows of a GLOBAL level staged through shared memory by bulk asynchronous copies: one step
-// consumes the four 512-byte rows [4 it, 4 it + 4) of the level array -- 2 KB contiguous in HBM -- that lane 0 requested NST
-// steps earlier; every lane then reads its path's column of the staged rows.  All 32 lanes run the loop (the ring is warp-wide);
-// lanes without a path skip the arithmetic.  `ph` keeps the phase parity of each stage across calls.
-template <bool PLUS, bool FUSED>
-__device__ __forceinline__ void fg_staged(const double2 *__restrict__ grows, const int col, const bool valid, double2 *__restrict__ dp,
-                                          double2 *__restrict__ dp2, const uint32_t *rp, const int half, double2 *stg, uint64_t *bars,
-                                          const int nst, uint32_t &ph, const int lane) {
-    const int niter = half >> 1;
-    if (lane == 0) {
-        const int pre = niter < nst ? niter : nst;
-        for (int s = 0; s < pre; ++s) {
-            mbar_expect_tx(bars + s, 2048u);
-            bulk_g2s(stg + s * 128, grows + (int64_t)s * 128, 2048u, bars + s);
-        }
-    }
-    uint32_t w = (PLUS && valid) ? rp[0] : 0u;
-#pragma unroll 1
-    for (int it = 0; it < niter; ++it) {
-        const int s = it & (nst - 1);
-        mbar_wait(bars + s, (ph >> s) & 1u);
-        ph ^= 1u << s;
-        const double2 *q = stg + s * 128 + col;
-        const double2 a0 = q[0], b0 = q[32], a1 = q[64], b1 = q[96];
-        __syncwarp();
-        if (lane == 0 && it + nst < niter) {
-            mbar_expect_tx(bars + s, 2048u);
-            bulk_g2s(stg + s * 128, grows + (int64_t)(it + nst) * 128, 2048u, bars + s);
-        }
+// level l (the source, 2 * half elements) -> level l-1 at dp[e * 32], and with `fused` also level l-2 at dp2[e * 32] (f of adjacent
+// pairs of level l-1: the MINUS (l-1) that follows).  u bits of the left child's codeword at rp[word * 32].  All lanes run the
+// loop (the staged source is warp-wide); lanes without a path skip the arithmetic.  The node updates of a step are branch-free
+// (node_fast) so that their dependency chains interleave; the rare operands outside the fast division's range are redone after.
+__device__ __forceinline__ void fg_pass(const Src &src, double2 *__restrict__ dp, double2 *__restrict__ dp2, const bool plus,
+                                        const bool fused, const uint32_t *rp, const int half, const bool valid) {
+    Raw8 cur, nxt;
+    if (half == 2) {  // four source elements: one half step
+        src_fetch<4>(src, 0, cur);
         if (valid) {
-            const int j = (2 * it) & 31;
-            const double2 y0 = PLUS ? node_g(a0, b0, (w >> j) & 1u) : node_f(a0, b0);
-            const double2 y1 = PLUS ? node_g(a1, b1, (w >> (j + 1)) & 1u) : node_f(a1, b1);
-            dp[0] = y0;
-            dp[32] = y1;
-            dp += 64;
-            if (FUSED) {
-                dp2[0] = node_f(y0, y1);
-                dp2 += 32;
-            }
-            if (PLUS && j == 30 && it + 1 < niter) w = rp[((2 * it + 2) >> 5) << 5];
+            const uint32_t w = plus ? rp[0] : 0u;
+            const double2 y0 = node_fg(cur.v[0], cur.v[1], plus, w & 1u), y1 = node_fg(cur.v[2], cur.v[3], plus, (w >> 1) & 1u);
+            dp[0] = y0, dp[32] = y1;
+            if (fused) dp2[0] = node_fg(y0, y1, false, 0u);
         }
+        return;
+    }
+    const int nsteps = half >> 2;  // four elements of level l-1 per step
+    if (src.kind == SK_STAGED && src.lane == 0) {
+        const int pre = nsteps < src.nst ? nsteps : src.nst;
+        for (int k = 0; k < pre; ++k) src_issue(src, k);
+    }
+    // u bits: word w of the codeword covers eight steps; the next word is requested as soon as a word is taken into use
+    const bool pv = plus && valid;
+    uint32_t w = pv ? rp[0] : 0u, wn = (pv && nsteps > 8) ? rp[32] : 0u;
+#pragma unroll 1
+    for (int k = -1; k < nsteps; ++k) {
+        nxt = cur;
+        if (k + 1 < nsteps) src_fetch<8>(src, k + 1, nxt);
+        if (k >= 0 && valid) {
+            const int j = (4 * k) & 31;
+            const uint32_t u = w >> j;
+            bool s0, s1, s2, s3, s4 = false, s5 = false;
+            double2 y0 = node_fast(cur.v[0], cur.v[1], plus, u & 1u, s0), y1 = node_fast(cur.v[2], cur.v[3], plus, (u >> 1) & 1u, s1);
+            double2 y2 = node_fast(cur.v[4], cur.v[5], plus, (u >> 2) & 1u, s2), y3 = node_fast(cur.v[6], cur.v[7], plus, (u >> 3) & 1u, s3);
+            if (s0 || s1 || s2 || s3) {  // rare: an operand below 1e-291 (or an un-normalised channel pair): the IEEE division
+                if (s0) y0 = node_fg(cur.v[0], cur.v[1], plus, u & 1u);
+                if (s1) y1 = node_fg(cur.v[2], cur.v[3], plus, (u >> 1) & 1u);
+                if (s2) y2 = node_fg(cur.v[4], cur.v[5], plus, (u >> 2) & 1u);
+                if (s3) y3 = node_fg(cur.v[6], cur.v[7], plus, (u >> 3) & 1u);
+            }
+            dp[0] = y0, dp[32] = y1, dp[64] = y2, dp[96] = y3;
+            dp += 128;
+            if (fused) {
+                double2 z0 = node_fast(y0, y1, false, 0u, s4), z1 = node_fast(y2, y3, false, 0u, s5);
+                if (s4) z0 = node_fg(y0, y1, false, 0u);
+                if (s5) z1 = node_fg(y2, y3, false, 0u);
+                dp2[0] = z0, dp2[32] = z1;
+                dp2 += 64;
+            }
+            if (plus && j == 28) {
+                w = wn;
+                if (k + 9 < nsteps) wn = rp[((4 * k + 36) >> 5) << 5];
+            }
+        }
+        cur = nxt;
     }
 }
 
@@ -178,22 +207,21 @@ __device__ __forceinline__ int group_sum(int v, const int G) {
     return v;
 }
 
-// The prune of recursiveListDecode (:446-451 etc.) over the M candidates each lane of a frame holds: keep the ns =
-// min(#nonzero, L) largest under the total order (metric, index), listed ascending; lists with at most L candidates keep all
-// of them in index order (the same rounds keyed by the index alone).  Candidate i of the lane has index ibase + i * istep.
-// On return lane t < nout holds its new path: the metric and the candidate index.
-template <int M>
-__device__ __forceinline__ void select_paths(const double (&cv)[M], const int ibase, const int istep, const bool valid,
+// The prune of recursiveListDecode (:446-451 etc.) over the M <= 8 candidates each lane of a frame holds (one instance for all
+// node kinds: code size): keep the ns = min(#nonzero, L) largest under the total order (metric, index), listed ascending;
+// lists with at most L candidates keep all of them in index order (the same rounds keyed by the index alone).  Candidate i of
+// the lane has index ibase + i * istep.  On return lane t < nout holds its new path: the metric and the candidate index.
+__device__ __forceinline__ void select_paths(const double (&cv)[8], const int M, const int ibase, const int istep, const bool valid,
                                              const int cnt, const int L, const int G, const int t, int &nout, double &newprob,
                                              int &ci) {
     const int C = cnt * M;
     int nzl = 0;
 #pragma unroll
-    for (int i = 0; i < M; ++i) nzl += (valid && cv[i] != 0.0) ? 1 : 0;
+    for (int i = 0; i < 8; ++i) nzl += (valid && i < M && cv[i] != 0.0) ? 1 : 0;
     const int nz = group_sum(nzl, G);
     const bool byidx = C <= L;
     const int ns = byidx ? C : (nz < L ? nz : L);
-    uint32_t taken = valid ? 0u : 0xffffffffu;
+    uint32_t taken = valid ? ~((1u << M) - 1u) : 0xffffffffu;
     newprob = 0.0;
     ci = 0;
 #pragma unroll 1
@@ -201,12 +229,10 @@ __device__ __forceinline__ void select_paths(const double (&cv)[M], const int ib
         double bv = -1.0;
         int bi = -1;
 #pragma unroll
-        for (int i = 0; i < M; ++i) {
-            const int idx = ibase + i * istep;
-            const bool free_ = !((taken >> i) & 1u);
-            const bool better = free_ && (bi < 0 || (byidx ? idx > bi : (cv[i] > bv || (cv[i] == bv && idx > bi))));
+        for (int i = 0; i < 8; ++i) {  // candidates in increasing index order: among equals the later index wins
+            const bool better = !((taken >> i) & 1u) && (byidx || cv[i] >= bv);
             bv = better ? cv[i] : bv;
-            bi = better ? idx : bi;
+            bi = better ? ibase + i * istep : bi;
         }
         const int mine = bi;
         for (int o = 1; o < G; o <<= 1) {
@@ -216,11 +242,7 @@ __device__ __forceinline__ void select_paths(const double (&cv)[M], const int ib
             bv = better ? ov : bv;
             bi = better ? oidx : bi;
         }
-        if (mine >= 0 && mine == bi) {
-#pragma unroll
-            for (int i = 0; i < M; ++i)
-                if (ibase + i * istep == bi) taken |= 1u << i;
-        }
+        if (mine >= 0 && mine == bi) taken |= 1u << ((bi - ibase) / istep);
         if (r < ns && t == ns - 1 - r) {
             newprob = bv;
             ci = bi;
@@ -229,7 +251,10 @@ __device__ __forceinline__ void select_paths(const double (&cv)[M], const int ib
     nout = ns;
 }
 
-// MB = resident warps per SM the build is register-capped for (picked by the host from the shared-memory footprint)
+// MB = resident warps per SM the build is register-capped for.  Twelve (168 registers) is where the eight-element steps of
+// fg_pass fit without spilling; sweeps of 8..32 warps per SM with smaller steps all ended within 5 % of each other (the
+// kernel trades latency hiding by warps against DRAM traffic of the resident frames, profiles/r2_a), so there is ONE build.
+constexpr int SCLP_MAX_WARPS_PER_SM = 12;
 template <int MB>
 __global__ void __launch_bounds__(32, MB) sclp_kernel(const SclpParams p) {
     PC_DYN_SMEM(smem_raw);
@@ -242,7 +267,7 @@ __global__ void __launch_bounds__(32, MB) sclp_kernel(const SclpParams p) {
     uint32_t *Rs = (uint32_t *)(Vs + vrows * 32);
     uint8_t *om = (uint8_t *)(Rs + 2 * scl2_wsum(rgl) * 32);
     double2 *stg = (double2 *)(smem_raw + (((size_t)((char *)(om + (n + 1) * 2 * 32) - (char *)smem_raw) + 15) & ~(size_t)15));
-    uint64_t *bars = (uint64_t *)(stg + p.nst * 128);
+    uint64_t *bars = (uint64_t *)(stg + p.nst * 256);
     uint32_t ph = 0;
     if (p.nst) {
         if (threadIdx.x == 0) {
@@ -271,11 +296,21 @@ __global__ void __launch_bounds__(32, MB) sclp_kernel(const SclpParams p) {
         const uint32_t *Ff = p.Fb ? p.Fb + f * NW : nullptr;
         double prob = 1.0;
         int cnt = 1, leaf = 0;
+        long long tprev = 0;
+        int tkey = 0;
         __syncwarp();
 #pragma unroll 1
         for (int oi = 0; oi < p.n_ops; ++oi) {
             const uint4 op = p.ops[oi];
             const int kind = op.x & 7, l = (op.x >> 3) & 15, c = (op.x >> 7) & 1, i0 = (int)op.y;
+#ifndef PC_EMU
+            if (p.timing) {
+                const long long now = clock64();
+                if (oi > 0 && lane == 0) atomicAdd(p.timing + tkey, (unsigned long long)(now - tprev));
+                tprev = now;
+                tkey = kind * 16 + l + (((op.x & SCLP_FUSED) && kind <= OP_PLUS) ? 0 : 0);
+            }
+#endif
             const bool ssrc = op.x & SCLP_SSRC, sdst = op.x & SCLP_SDST, chan = op.x & SCLP_CHAN;
             const bool dsrc = dualon && (op.x & SCLP_DSRC), ddst = dualon && (op.x & SCLP_DUAL);
             const int size = 1 << l;
@@ -296,118 +331,57 @@ __global__ void __launch_bounds__(32, MB) sclp_kernel(const SclpParams p) {
                 int srcslot = t;
                 if (plus && !sdst && valid) srcslot = OM(l - 1, 0)[lane];
                 const uint32_t *rp = rbase(l - 1, 0) + (sdst ? gbase : lane);  // u bits: the left child's codeword of this path
-                if (ddst) {
-                    // one shared parent (the channel or a shared-layout vector) and four or more paths: the output has only two
-                    // variants per element, g(a, b, 0) and g(a, b, 1); the lanes of the frame share the 2 x half items, the
-                    // paths pick their variant by their codeword bit when they read the vector (SrcDual / ldsrc)
-                    const double2 *sb = chan ? nullptr : vbase(l);
-                    double2 *db = vbase(l - 1);
-#pragma unroll 1
-                    for (int i = t; i < size; i += G) {
-                        const int e = i >> 1;
-                        double2 a, b;
-                        if (chan) {
-                            if (p.sym)
-                                a = p.tab[yf[2 * e]], b = p.tab[yf[2 * e + 1]];
-                            else
-                                a = xyf[2 * e], b = xyf[2 * e + 1];
-                        } else {
-                            const double2 *q = sb + (((2 * e) >> gsh) << 5) + gbase + ((2 * e) & (G - 1));
-                            a = q[0], b = q[1];
-                        }
-                        db[((i >> gsh) << 5) + gbase + (i & (G - 1))] = node_g(a, b, (uint32_t)(i & 1));
-                    }
-                } else if (!sdst && !ssrc && !(chan && p.sym && !plus)) {
-                    // the lane's own path: per-path destination, source = a per-path vector or the channel
-                    if (!chan && !dsrc && l > lsm && p.nst) {
-                        // source level in HBM: rows staged through the bulk-copy ring (all lanes run the loop)
-                        double2 *dp = vbase(l - 1) + lane, *dp2 = vbase(l - 2) + lane;
-                        const double2 *grows = Vg + (((int64_t)1 << l) - 1) * 32;
-                        const int col = gbase + srcslot;
-                        if (plus) {
-                            if (fused)
-                                fg_staged<true, true>(grows, col, valid, dp, dp2, rp, half, stg, bars, p.nst, ph, lane);
-                            else
-                                fg_staged<true, false>(grows, col, valid, dp, dp2, rp, half, stg, bars, p.nst, ph, lane);
-                        } else {
-                            if (fused)
-                                fg_staged<false, true>(grows, col, valid, dp, dp2, rp, half, stg, bars, p.nst, ph, lane);
-                            else
-                                fg_staged<false, false>(grows, col, valid, dp, dp2, rp, half, stg, bars, p.nst, ph, lane);
-                        }
-                    } else if (valid) {
-                        double2 *dp = vbase(l - 1) + lane, *dp2 = l >= 2 ? vbase(l - 2) + lane : nullptr;
-                        if (dsrc) {
-                            const SrcDual sr{vbase(l) + gbase, rbase(l, 0) + gbase + srcslot, gsh};
-                            if (plus) {
-                                if (fused)
-                                    fg_own<true, true>(sr, dp, dp2, rp, half);
-                                else
-                                    fg_own<true, false>(sr, dp, dp2, rp, half);
-                            } else {
-                                if (fused)
-                                    fg_own<false, true>(sr, dp, dp2, rp, half);
-                                else
-                                    fg_own<false, false>(sr, dp, dp2, rp, half);
-                            }
-                        } else if (chan && p.sym) {
-                            // the channel level is the source of PLUS (n) only (MINUS (n) runs before the first fork)
-                            const SrcSym sr{yf, p.tab};
-                            if (fused)
-                                fg_own<true, true>(sr, dp, dp2, rp, half);
-                            else
-                                fg_own<true, false>(sr, dp, dp2, rp, half);
-                        } else {
-                            const SrcStride sr{chan ? xyf : vbase(l) + gbase + srcslot, chan ? 1 : 32};
-                            if (plus) {
-                                if (fused)
-                                    fg_own<true, true>(sr, dp, dp2, rp, half);
-                                else
-                                    fg_own<true, false>(sr, dp, dp2, rp, half);
-                            } else {
-                                if (fused)
-                                    fg_own<false, true>(sr, dp, dp2, rp, half);
-                                else
-                                    fg_own<false, false>(sr, dp, dp2, rp, half);
-                            }
-                        }
-                    }
-                } else {
-                    // shared-layout sources and the cooperative (single path) mode before the first fork: one level per pass
-                    const int npass = fused ? 2 : 1;
+                if (ddst || sdst) {
+                    // The lanes of a frame share the items of ONE vector, float64 pairs in the shared layout:
+                    //  * cooperative mode before the first fork (sdst): the single path's f / g pass, one level per round;
+                    //  * two-variant outputs (ddst): one shared parent (the channel or a shared-layout vector) and four or more
+                    //    paths -- item 2 e + v = g(a_e, b_e, v); the paths pick their variant by their codeword bit when they read
+                    //    the vector (SK_DUAL / ldsrc).
+                    const int npass = (sdst && fused) ? 2 : 1;
 #pragma unroll 1
                     for (int ps = 0; ps < npass; ++ps) {
                         const int lv = l - ps;
-                        const bool pl = plus && ps == 0, shs = ps == 0 ? ssrc : sdst, ch = chan && ps == 0;
+                        const bool pl = plus && ps == 0, ch = chan && ps == 0;
                         const double2 *sb = ch ? nullptr : vbase(lv);
                         double2 *db = vbase(lv - 1);
-                        const int h0 = sdst ? t : 0, hs = sdst ? G : 1;
-                        if (sdst || valid) {
+                        const int items = ddst ? (1 << lv) : (1 << (lv - 1));
 #pragma unroll 1
-                            for (int h = h0; h < (1 << (lv - 1)); h += hs) {
-                                double2 a, b;
-                                if (ch) {
-                                    if (p.sym)
-                                        a = p.tab[yf[2 * h]], b = p.tab[yf[2 * h + 1]];
-                                    else
-                                        a = xyf[2 * h], b = xyf[2 * h + 1];
-                                } else if (shs) {
-                                    const double2 *q = sb + (((2 * h) >> gsh) << 5) + gbase;
-                                    if (G >= 2)
-                                        a = q[(2 * h) & (G - 1)], b = q[((2 * h) & (G - 1)) + 1];
-                                    else
-                                        a = q[0], b = q[32];
-                                } else {
-                                    const double2 *q = sb + ((2 * h) << 5) + (ps == 0 ? gbase + srcslot : lane);  // pass 2: the vector just written
-                                    a = q[0], b = q[32];
-                                }
-                                const uint32_t u = pl ? (rp[(h >> 5) << 5] >> (h & 31)) & 1u : 0u;
-                                double2 *d = sdst ? db + ((h >> gsh) << 5) + gbase + (h & (G - 1)) : db + (h << 5) + lane;
-                                *d = node_update(a, b, pl, u);
+                        for (int i = t; i < items; i += G) {
+                            const int e = ddst ? i >> 1 : i;
+                            double2 a, b;
+                            if (ch) {
+                                if (p.sym)
+                                    a = p.tab[yf[2 * e]], b = p.tab[yf[2 * e + 1]];
+                                else
+                                    a = xyf[2 * e], b = xyf[2 * e + 1];
+                            } else {
+                                const double2 *q = sb + (((2 * e) >> gsh) << 5) + gbase + ((2 * e) & (G - 1));
+                                a = q[0], b = G >= 2 ? q[1] : q[32];  // one lane per frame: consecutive elements sit in consecutive rows
                             }
+                            const uint32_t u = ddst ? (uint32_t)(i & 1) : (pl ? (rp[(e >> 5) << 5] >> (e & 31)) & 1u : 0u);
+                            db[((i >> gsh) << 5) + gbase + (i & (G - 1))] = node_fg(a, b, pl, u);
                         }
                         if (ps + 1 < npass) __syncwarp();
                     }
+                } else {
+                    // the lane's own path: per-path destination(s)
+                    Src sr;
+                    sr.gsh = gsh, sr.ss = 32;
+                    if (chan) {
+                        sr.kind = p.sym ? SK_SYM : SK_PATH;
+                        sr.y = yf, sr.tab = p.tab, sr.p = xyf, sr.ss = 1;
+                    } else if (dsrc || ssrc) {
+                        sr.kind = dsrc ? SK_DUAL : SK_SHARED;
+                        sr.p = vbase(l) + gbase, sr.bits = rbase(l, 0) + gbase + srcslot;
+                    } else if (l > lsm && p.nst && half >= 4) {
+                        sr.kind = SK_STAGED;
+                        sr.p = vbase(l), sr.stg = stg, sr.bars = bars, sr.ph = &ph, sr.nst = p.nst, sr.nsteps = half >> 2;
+                        sr.col = gbase + srcslot, sr.lane = lane;
+                    } else {
+                        sr.kind = SK_PATH;
+                        sr.p = vbase(l) + gbase + srcslot;
+                    }
+                    fg_pass(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, plus, fused, rp, half, valid);
                 }
                 __syncwarp();
                 continue;
@@ -430,106 +404,100 @@ __global__ void __launch_bounds__(32, MB) sclp_kernel(const SclpParams p) {
                 continue;
             }
             // ------------------------------- fast nodes ------------------------------------------------------
+            // Rate-0 :495-518, Rep :521-578, Rate-1 :581-628, SPC :631-682.  One element loop serves all four kinds (code size);
+            // the order-dependent float64 products (np.product is a left-to-right product) run one path per lane.
             const int li = leaf++;
             const int Wl = scl2_W(l);
             const uint32_t smask = size >= 32 ? 0xffffffffu : ((1u << size) - 1u);
             const int bsh = size >= 32 ? 0 : (i0 & 31);  // node-local slice of the frame-wide bit arrays: word i0/32 + w, shifted by bsh
             auto fslice = [&](int w) -> uint32_t { return Ff ? (Ff[(i0 >> 5) + w] >> bsh) & smask : 0u; };
-            // in cooperative mode only slot 0 exists; its vector is in the shared layout (or the channel)
-            auto ldv = [&](int j) -> double2 { return ldsrc(j, t); };
+            const bool rep = kind == OP_REP, fork = kind == OP_RATE1 || kind == OP_SPC, spc = kind == OP_SPC;
+            const bool plain = !chan && !dsrc && !ssrc;  // the lane's own vector, per-path layout
+            const uint32_t *coefw = p.coef_words + op.w;
             uint32_t *ro = rbase(l, c) + lane;
+            uint32_t *hdp = (fork && l >= 6) ? rbase(l - 1, 0) + lane : nullptr;  // hard-decision words of large nodes: the dead child areas
+            const int nb = size < 4 ? size : 4;
             int nout = cnt, src = t;
             double newprob = 0.0;
-            if (kind == OP_RATE0 || kind == OP_REP) {
-                // left-to-right products of P[j].{x|y} selected by the candidate codeword's bits (np.product order;
-                // Rate-0 :495-518, Rep :521-578)
-                const bool rep = kind == OP_REP;
-                const uint32_t *coefw = p.coef_words + op.w;
-                double cv[2] = {0.0, 0.0};
-                if (valid) {
-                    double pr0 = 1.0, pr1 = 1.0;
-#pragma unroll 1
-                    for (int w0 = 0; w0 < size; w0 += 32) {
-                        const uint32_t fb = fslice(w0 >> 5), cb = rep ? fb ^ coefw[w0 >> 5] : 0u;
-                        const int m = size - w0 < 32 ? size - w0 : 32;
-#pragma unroll 1
-                        for (int b = 0; b < m; ++b) {
-                            const double2 v2 = ldv(w0 + b);
-                            pr0 = __dmul_rn(pr0, (fb >> b) & 1u ? v2.y : v2.x);
-                            if (rep) pr1 = __dmul_rn(pr1, (cb >> b) & 1u ? v2.y : v2.x);
-                        }
-                    }
-                    cv[0] = __dmul_rn(prob, pr0);
-                    cv[1] = __dmul_rn(prob, pr1);
-                }
-                int sel = 0;
-                if (!rep) {
-                    newprob = cv[0];
-                } else {
-                    int ci;
-                    select_paths<2>(cv, t, cnt, valid, cnt, L, G, t, nout, newprob, ci);
-                    sel = ci >= cnt ? 1 : 0;
-                    src = ci - sel * cnt;
-                }
-                if (t < nout) {
-#pragma unroll 1
-                    for (int w = 0; w < Wl; ++w) ro[w << 5] = fslice(w) ^ (sel ? coefw[w] : 0u);
-                    OM(l, c)[lane] = (uint8_t)src;
-                }
-            } else {  // Rate-1 :581-628 and SPC :631-682
-                const bool spc = kind == OP_SPC;
-                // pass 1 over the path's elements: hard decisions, reliabilities (second-largest / largest, :763-768) and
-                // the 2 (Rate-1) or 4 (SPC) largest (score, j), ties to the later index (pickLeastReliableIndices :759-761),
-                // kept ascending s0 <= .. <= s3 by a branch-free insertion
-                uint32_t *hdp = l >= 6 ? rbase(l - 1, 0) + lane : nullptr;  // hard-decision words of large nodes: the dead child areas
-                uint32_t hdw = 0, par = 0;
-                double s0 = -1.0, s1 = -1.0, s2 = -1.0, s3 = -1.0;
+            double cv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cv[i] = 0.0;
+            uint32_t hdw = 0, par = 0, delta = 0;
+            int pk0 = -1, pk1 = -1, pk2 = -1, pk3 = -1;
+            if (valid) {
+                double pr0 = 1.0, pr1 = 1.0;                         // Rate-0 / Rep products; pass 2: product of the non-forked maxima
+                double s0 = -1.0, s1 = -1.0, s2 = -1.0, s3 = -1.0;    // pass 1 of Rate-1 / SPC: the four largest (score, j), ascending
                 int j0 = 0, j1 = 0, j2 = 0, j3 = 0;
-                if (valid) {
+                uint32_t fb = 0, cb = 0;
+                const int npass = fork ? 2 : 1;
 #pragma unroll 1
-                    for (int j = 0; j < size; ++j) {
-                        const double2 v2 = ldv(j);
-                        const bool one = v2.y > v2.x;
-                        const double m1 = one ? v2.y : v2.x, m2 = one ? v2.x : v2.y;
-                        const double s = m2 / m1;
-                        const bool g0 = s >= s0, g1 = s >= s1, g2 = s >= s2, g3 = s >= s3;
-                        s0 = g1 ? s1 : (g0 ? s : s0), j0 = g1 ? j1 : (g0 ? j : j0);
-                        s1 = g2 ? s2 : (g1 ? s : s1), j1 = g2 ? j2 : (g1 ? j : j1);
-                        s2 = g3 ? s3 : (g2 ? s : s2), j2 = g3 ? j3 : (g2 ? j : j2);
-                        s3 = g3 ? s : s3, j3 = g3 ? j : j3;
-                        hdw |= (one ? 1u : 0u) << (j & 31);
-                        if ((j & 31) == 31 || j == size - 1) {
+                for (int ps = 0; ps < npass; ++ps) {
+#pragma unroll 1
+                    for (int jb = 0; jb < size; jb += 4) {
+                        // four consecutive elements of the lane's own vector: independent loads ahead of the sequential chains
+                        double2 v[4];
+                        if (plain) {
+                            const double2 *q = vbase(l) + (jb << 5) + lane;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) v[i] = i < nb ? q[i << 5] : make_double2(1.0, 1.0);
+                        } else {
+#pragma unroll 1
+                            for (int i = 0; i < nb; ++i) {  // the channel, shared-layout and two-variant vectors: few nodes per frame
+                                const double2 x = ldsrc(jb + i, t);
+                                if (i == 0) v[0] = x;
+                                if (i == 1) v[1] = x;
+                                if (i == 2) v[2] = x;
+                                if (i == 3) v[3] = x;
+                            }
+                        }
+                        if (!fork && (jb & 31) == 0) fb = fslice(jb >> 5), cb = rep ? fb ^ coefw[jb >> 5] : 0u;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (i < nb) {
+                                const int j = jb + i;
+                                const double2 v2 = v[i];
+                                if (!fork) {
+                                    // products of P[j].{x|y} selected by the candidate codeword's bits
+                                    pr0 = __dmul_rn(pr0, (fb >> (j & 31)) & 1u ? v2.y : v2.x);
+                                    if (rep) pr1 = __dmul_rn(pr1, (cb >> (j & 31)) & 1u ? v2.y : v2.x);
+                                } else if (ps == 0) {
+                                    // hard decisions, reliabilities (second-largest / largest, :763-768) and the 2 (Rate-1) or 4 (SPC)
+                                    // largest (score, j), ties to the later index (pickLeastReliableIndices :759-761), kept ascending
+                                    // s0 <= .. <= s3 by a branch-free insertion
+                                    const bool one = v2.y > v2.x;
+                                    const double s = (one ? v2.x : v2.y) / (one ? v2.y : v2.x);
+                                    const bool g0 = s >= s0, g1 = s >= s1, g2 = s >= s2, g3 = s >= s3;
+                                    s0 = g1 ? s1 : (g0 ? s : s0), j0 = g1 ? j1 : (g0 ? j : j0);
+                                    s1 = g2 ? s2 : (g1 ? s : s1), j1 = g2 ? j2 : (g1 ? j : j1);
+                                    s2 = g3 ? s3 : (g2 ? s : s2), j2 = g3 ? j3 : (g2 ? j : j2);
+                                    s3 = g3 ? s : s3, j3 = g3 ? j : j3;
+                                    hdw |= (one ? 1u : 0u) << (j & 31);
+                                } else {
+                                    // in element order: product of the non-forked maxima (:785-788, :814-817)
+                                    const bool forked = j == pk0 || j == pk1 || j == pk2 || j == pk3;
+                                    pr0 = forked ? pr0 : __dmul_rn(pr0, v2.y > v2.x ? v2.y : v2.x);
+                                }
+                            }
+                        if (fork && ps == 0 && (((jb + 3) & 31) == 31 || jb + 4 >= size)) {
                             par ^= hdw;
                             if (hdp) {
-                                hdp[(j >> 5) << 5] = hdw;
+                                hdp[(jb >> 5) << 5] = hdw;
                                 hdw = 0;
                             }
                         }
                     }
-                }
-                // picks in ascending (score, index) order
-                int pk0, pk1, pk2 = -1, pk3 = -1;
-                if (spc)
-                    pk0 = j0, pk1 = j1, pk2 = j2, pk3 = j3;
-                else
-                    pk0 = j2, pk1 = j3;
-                // pass 2, in element order: product of the non-forked maxima (:785-788, :814-817); the forked pairs on the way
-                double cv[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) cv[i] = 0.0;
-                uint32_t delta = 0;
-                if (valid) {
-                    double pr = 1.0;
-                    double2 f0 = make_double2(1.0, 1.0), f1 = f0, f2 = f0, f3 = f0;
-#pragma unroll 1
-                    for (int j = 0; j < size; ++j) {
-                        const double2 v2 = ldv(j);
-                        const double v = v2.y > v2.x ? v2.y : v2.x;
-                        const bool e0 = j == pk0, e1 = j == pk1, e2 = j == pk2, e3 = j == pk3;
-                        f0 = e0 ? v2 : f0, f1 = e1 ? v2 : f1, f2 = e2 ? v2 : f2, f3 = e3 ? v2 : f3;
-                        pr = (e0 || e1 || e2 || e3) ? pr : __dmul_rn(pr, v);
+                    if (fork && ps == 0) {  // picks in ascending (score, index) order
+                        if (spc)
+                            pk0 = j0, pk1 = j1, pk2 = j2, pk3 = j3;
+                        else
+                            pk0 = j2, pk1 = j3;
                     }
-                    const double basep = __dmul_rn(prob, pr);
+                }
+                if (!fork) {
+                    cv[0] = __dmul_rn(prob, pr0);
+                    cv[1] = __dmul_rn(prob, pr1);
+                } else {
+                    const double basep = __dmul_rn(prob, pr0);
                     // parity of the non-forked hard decisions
                     auto hbit = [&](int j) -> uint32_t {
                         const uint32_t w = hdp ? hdp[(j >> 5) << 5] : hdw;
@@ -540,33 +508,50 @@ __global__ void __launch_bounds__(32, MB) sclp_kernel(const SclpParams p) {
                     if (spc) pp ^= hbit(pk2) ^ hbit(pk3);
                     const uint32_t fval = spc && p.fvp ? (p.fvp[f * p.nfw + (op.z >> 5)] >> (op.z & 31)) & 1u : 0u;
                     delta = (fval ^ pp) & 1u;
-                    // candidate metrics (forkIndices / forkIndicesSpc, :770-820): digits of the fork index, first pick outermost
-                    if (!spc) {
+                    // candidate metrics (forkIndices / forkIndicesSpc, :770-820): digits of the fork index, first pick outermost.
+                    // The partial products are built pick by pick: c[fk] = ((f0 * f1) * f2) * f3 in that order.
+                    const int npk = spc ? 4 : 2;
+#pragma unroll 1
+                    for (int w = 0; w < npk; ++w) {
+                        const int pj = w == 0 ? pk0 : (w == 1 ? pk1 : (w == 2 ? pk2 : pk3));
+                        const double2 fw = ldsrc(pj, t);
+                        if (w == 0) {
 #pragma unroll
-                        for (int fk = 0; fk < 4; ++fk) {
-                            const double pf = __dmul_rn((fk >> 1) & 1 ? f0.y : f0.x, fk & 1 ? f1.y : f1.x);
-                            cv[fk] = __dmul_rn(pf, basep);
-                        }
-                    } else {
+                            for (int fk = 0; fk < 8; ++fk) cv[fk] = (spc ? (fk >> 2) : (fk >> 1)) & 1 ? fw.y : fw.x;
+                        } else {
 #pragma unroll
-                        for (int fk = 0; fk < 8; ++fk) {
-                            double pf = __dmul_rn((fk >> 2) & 1 ? f0.y : f0.x, (fk >> 1) & 1 ? f1.y : f1.x);
-                            pf = __dmul_rn(pf, fk & 1 ? f2.y : f2.x);
-                            const uint32_t dep = (delta ^ (uint32_t)__popc((uint32_t)fk)) & 1u;
-                            pf = __dmul_rn(pf, dep ? f3.y : f3.x);
-                            cv[fk] = __dmul_rn(pf, basep);
+                            for (int fk = 0; fk < 8; ++fk) {
+                                // digit of pick w in fork index fk: Rate-1 has two digits (w = 0, 1), SPC three plus the dependent pick
+                                const uint32_t dg = w == 3 ? (delta ^ (uint32_t)__popc((uint32_t)fk)) & 1u
+                                                           : (uint32_t)(fk >> (spc ? 2 - w : 1 - w)) & 1u;
+                                cv[fk] = __dmul_rn(cv[fk], dg ? fw.y : fw.x);
+                            }
                         }
                     }
+#pragma unroll
+                    for (int fk = 0; fk < 8; ++fk) cv[fk] = (spc || fk < 4) ? __dmul_rn(cv[fk], basep) : 0.0;
                 }
-                int ci, fk;
-                if (spc) {
-                    select_paths<8>(cv, t * 8, 1, valid, cnt, L, G, t, nout, newprob, ci);
-                    src = ci >> 3, fk = ci & 7;
-                } else {
-                    const double c4[4] = {cv[0], cv[1], cv[2], cv[3]};
-                    select_paths<4>(c4, t * 4, 1, valid, cnt, L, G, t, nout, newprob, ci);
-                    src = ci >> 2, fk = ci & 3;
+            }
+            // prune / order the candidates (Rate-0 keeps its paths as they are)
+            int sel = 0, fk = 0;
+            if (kind == OP_RATE0) {
+                newprob = cv[0];
+            } else {
+                int ci;
+                const int M = rep ? 2 : (spc ? 8 : 4);
+                select_paths(cv, M, rep ? t : t * M, rep ? cnt : 1, valid, cnt, L, G, t, nout, newprob, ci);
+                if (rep)
+                    sel = ci >= cnt ? 1 : 0, src = ci - sel * cnt;
+                else
+                    src = ci / M, fk = ci - src * M;
+            }
+            if (!fork) {
+                if (t < nout) {
+#pragma unroll 1
+                    for (int w = 0; w < Wl; ++w) ro[w << 5] = fslice(w) ^ (sel ? coefw[w] : 0u);
+                    OM(l, c)[lane] = (uint8_t)src;
                 }
+            } else {
                 if (hdp) __syncwarp();  // the hard-decision words of the source paths
                 // the source path's picks, parity and hard decisions; forked positions overwritten
                 const int sl = gbase + (t < nout ? src : t);
@@ -603,6 +588,9 @@ __global__ void __launch_bounds__(32, MB) sclp_kernel(const SclpParams p) {
             }
             __syncwarp();
         }
+#ifndef PC_EMU
+        if (p.timing && lane == 0) atomicAdd(p.timing + tkey, (unsigned long long)(clock64() - tprev));
+#endif
         // ---- final list: is the actual word in it (listDecode :172-213 compares the information vectors; codewords here) ----
         {
             const bool valid = t < cnt;
@@ -969,12 +957,15 @@ static int envp_int(const char *name, int dflt) {
 // tuning knobs are read ONCE per process (a changed environment between the workspace query and the decode cannot break
 // the sizing contract)
 struct SclpKnobs {
-    int warps_per_sm, lsm, rgl, off, nst;
+    int warps_per_sm, lsm, rgl, off, nst, timing, skew;
     SclpKnobs() {
-        warps_per_sm = envp_int("PC_SCLP_WARPS_PER_SM", 12);
+        warps_per_sm = envp_int("PC_SCLP_WARPS_PER_SM", SCLP_MAX_WARPS_PER_SM);
+        if (warps_per_sm > SCLP_MAX_WARPS_PER_SM) warps_per_sm = SCLP_MAX_WARPS_PER_SM;
         lsm = envp_int("PC_SCLP_LSM", -1);
         rgl = envp_int("PC_SCLP_RGL", 7);
-        nst = envp_int("PC_SCLP_STAGES", 4);
+        nst = envp_int("PC_SCLP_STAGES", 2);
+        timing = envp_int("PC_SCLP_TIMING", 0);
+        skew = envp_int("PC_SCLP_SKEW", 1);
         off = envp_int("PC_SCL_WARP", 0) || envp_int("PC_SCL_GENERIC", 0) || envp_int("PC_SCL_CTA", 0);
     }
 };
@@ -1000,7 +991,7 @@ static SclpConfig sclp_config(const pc_plan *plan, int L, int64_t B) {
     int rgl = kn.rgl < 1 ? 1 : kn.rgl;
     if (rgl > n + 1) rgl = n + 1;
     c.rgl = rgl;
-    const int target = kn.warps_per_sm > 0 ? kn.warps_per_sm : 12;
+    const int target = kn.warps_per_sm > 0 ? kn.warps_per_sm : SCLP_MAX_WARPS_PER_SM;
     const size_t budget = (size_t)(227 * 1024) / (size_t)target - 1024;
     int lsm = n - 1 < 6 ? n - 1 : 6;
     if (lsm < 1) lsm = 1;
@@ -1023,7 +1014,7 @@ static SclpConfig sclp_config(const pc_plan *plan, int L, int64_t B) {
     if (grid > waves) grid = waves;
     c.grid = (int)(grid > 0 ? grid : 1);
     const int64_t vrows_all = ((int64_t)1 << n) - 1, vrows_s = ((int64_t)2 << lsm) - 1;
-    c.vg_stride = (size_t)(vrows_all > vrows_s ? vrows_all - vrows_s : 0) * 32 + 32;
+    c.vg_stride = (size_t)(vrows_all > vrows_s ? vrows_all - vrows_s : 0) * 32 + 32 * (size_t)(kn.skew > 0 ? kn.skew : 1);
     c.rg_stride = (size_t)2 * (scl2_wsum(n + 1) - scl2_wsum(rgl)) * 32 + 32;
     c.lsmA = n - 1 < 7 ? (n - 1 < 0 ? 0 : n - 1) : 7;
     c.smem2 = sclp_final_smem_bytes(n, c.lsmA);
@@ -1170,22 +1161,40 @@ static int sclp_run(const pc_plan *plan, const SclTables *T, int L, const SclpIo
         const int fpw = 32 / c.G;
         int64_t grid = (F + fpw - 1) / fpw;
         if (grid > c.grid) grid = c.grid;
+        static unsigned long long *d_timing = nullptr;
+#ifndef PC_EMU
+        if (sclp_knobs().timing && !d_timing) {
+            cudaMalloc((void **)&d_timing, 128 * 8);
+            cudaMemset(d_timing, 0, 128 * 8);
+        }
+#endif
+        p.timing = d_timing;
         prof_mark(st);
         {
-            int rc;
-            if (c.per_sm <= 12)
-                rc = sclp_launch<12>(p, (int)grid, c.smem, st);
-            else if (c.per_sm <= 16)
-                rc = sclp_launch<16>(p, (int)grid, c.smem, st);
-            else if (c.per_sm <= 20)
-                rc = sclp_launch<20>(p, (int)grid, c.smem, st);
-            else if (c.per_sm <= 24)
-                rc = sclp_launch<24>(p, (int)grid, c.smem, st);
-            else
-                rc = sclp_launch<32>(p, (int)grid, c.smem, st);
+            const int rc = sclp_launch<SCLP_MAX_WARPS_PER_SM>(p, (int)grid, c.smem, st);
             if (rc) return rc;
         }
         prof_mark(st);
+#ifndef PC_EMU
+        if (d_timing) {  // tuning runs only: cycles per (op kind, level) of the launch just made, summed over warps
+            unsigned long long h[128];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, d_timing, sizeof h, cudaMemcpyDeviceToHost);
+            cudaMemset(d_timing, 0, sizeof h);
+            static const char *names[8] = {"MINUS", "PLUS", "COMBINE", "RATE0", "REP", "RATE1", "SPC", "?"};
+            unsigned long long tot = 0;
+            for (int i = 0; i < 128; ++i) tot += h[i];
+            fprintf(stderr, "SCLP_TIMING total warp-cycles %llu over %d warps\n", tot, (int)grid);
+            for (int kk = 0; kk < 7; ++kk) {
+                unsigned long long ks = 0;
+                for (int l2 = 0; l2 < 16; ++l2) ks += h[kk * 16 + l2];
+                fprintf(stderr, "SCLP_TIMING %-8s %5.1f%% :", names[kk], 100.0 * ks / (tot ? tot : 1));
+                for (int l2 = 0; l2 < 16; ++l2)
+                    if (h[kk * 16 + l2]) fprintf(stderr, " l%d=%.1f%%", l2, 100.0 * h[kk * 16 + l2] / (tot ? tot : 1));
+                fprintf(stderr, "\n");
+            }
+        }
+#endif
 
         SclpFinalParams r{};
         r.n = plan->n, r.k = k, r.L = L, r.NW = NW, r.kw = kw, r.n_ops = p.n_ops, r.n_leaf = T->n_leaf, r.sym = p.sym;
