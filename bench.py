@@ -145,8 +145,7 @@ class ScBinary1024:
     N, K, n = 1024, 512, 10
     alg_bytes_frame = 4288  # 4 N bytes of soft input + (N + K)/8 bytes out
     info_bits = 512
-    ncu = {"dram_bytes_per_frame": 70.4e3, "warp_inst_per_frame": 15.17e3, "issue_active_pct": 60.3,
-           "capture": "profiles/r1_b_sc1024_ncu_summary.md (prof_sc_e)"}
+    ncu_key = "sc_decode_kernel_symbols"
 
     def code(self):
         from polarcub_b200.construction import frozen_set_from_pe, load_pe
@@ -335,28 +334,56 @@ def awgn_frozen_set(n, K, allow_ga):
         return frozen_set_from_pe(ga_awgn_pe(n, awgn_sigma()), K), "Gaussian approximation (Chung et al.), --construction ga"
 
 
+def awgn_quantiser(sigma, Y=256):
+    """Uniform Y-level quantiser of the BI-AWGN output over [-1 - 4 sigma, 1 + 4 sigma] (outer bins open) and its channel
+    table [Y, 2]: row s = (P(bin s, x=0), P(bin s, x=1)) for equiprobable inputs -- the rows a
+    QaryMemorylessDistribution.makeQaryMemorylessVectorDistribution would copy into probs."""
+    ymax = 1.0 + 4.0 * sigma
+    step = 2.0 * ymax / Y
+    edges = -ymax + step * np.arange(Y + 1)
+    edges[0], edges[-1] = -np.inf, np.inf
+
+    def cdf(x):
+        return 0.5 * (1.0 + np.vectorize(math.erf)(x / math.sqrt(2.0)))
+
+    tab = np.stack([0.5 * (cdf((edges[1:] - 1.0) / sigma) - cdf((edges[:-1] - 1.0) / sigma)),
+                    0.5 * (cdf((edges[1:] + 1.0) / sigma) - cdf((edges[:-1] + 1.0) / sigma))], axis=-1)
+    return ymax, step, np.ascontiguousarray(tab, dtype=np.float64)
+
+
 class SclBinary4096:
-    """C2: binary SCL L=8, N=4096, K=2048 over BI-AWGN at Eb/N0 = 2 dB, linear-domain float64 (listDecode with q=2)."""
+    """C2: binary SCL L=8, N=4096, K=2048 over BI-AWGN at Eb/N0 = 2 dB, linear-domain float64 (listDecode with q=2).
+    The channel output is quantised to 256 levels (one byte per symbol) and enters the decoder as symbols + channel table
+    (pc_scl_decode_symbols = listDecode on makeQaryMemorylessVectorDistribution(length, y)); `records.float64_pairs` runs the
+    same frames' unquantised outputs through the float64-pair entry point (round 1's headline input)."""
     name = "scl_l8_n4096_k2048_biawgn2dB"
-    kernel = "sclw_kernel (frame-per-warp binary SCL)"
+    kernel = "sclp_kernel (binary SCL, one path per lane, 32/L frames per warp)"
     dtype = "f64"
-    default_frames, default_e2e, default_cpu = 1 << 15, 1 << 15, 1 << 14
+    default_frames, default_e2e, default_cpu = 0, 0, 1 << 14  # frames: five resident waves of the decode kernel
     N, K, n, L = 4096, 2048, 12, 8
     alg_bytes_frame = 16640  # SURVEY.md 8(d): 4 N bytes of soft input + K/8 bytes out
     info_bits = 2048
-    ncu = {"dram_bytes_per_frame": 4.85e6, "warp_inst_per_frame": 0.900e6, "issue_active_pct": 48.6,
-           "capture": "profiles/r1_c_scl_ncu_summary.md (prof_sclw_e)"}
+    ncu_key = "sclp_kernel"
     allow_ga = False
+    ebn0_db = EBN0_DB
+    pairs_frames = 1 << 14
 
     def code(self):
         fs, self.construction = awgn_frozen_set(self.n, self.K, self.allow_ga)
         self.fm = mask_of(self.N, fs)
+        self.sigma = awgn_sigma(ebn0_db=self.ebn0_db)
+        self.ymax, self.qstep, self.tab = awgn_quantiser(self.sigma)
 
-    def make_xy(self, torch, cw, gen):
-        sigma = awgn_sigma()
-        y = (1.0 - 2.0 * cw.to(torch.float64)) + sigma * torch.randn(cw.shape, dtype=torch.float64, device=cw.device, generator=gen)
-        l0 = -(y - 1.0) ** 2 / (2 * sigma * sigma)
-        l1 = -(y + 1.0) ** 2 / (2 * sigma * sigma)
+    def make_y(self, torch, cw, gen):
+        return (1.0 - 2.0 * cw.to(torch.float64)) + self.sigma * torch.randn(cw.shape, dtype=torch.float64, device=cw.device, generator=gen)
+
+    def quantise(self, torch, y):
+        return torch.clamp(torch.floor((y + self.ymax) / self.qstep), 0, self.tab.shape[0] - 1).to(torch.uint8)
+
+    def pairs(self, torch, y):
+        s = self.sigma
+        l0 = -(y - 1.0) ** 2 / (2 * s * s)
+        l1 = -(y + 1.0) ** 2 / (2 * s * s)
         m = torch.maximum(l0, l1)
         return torch.stack([torch.exp(l0 - m), torch.exp(l1 - m)], dim=-1).contiguous()
 
@@ -367,55 +394,87 @@ class SclBinary4096:
         self.code()
         N, K = self.N, self.K
         self.plan = plan = engine.Plan(2, self.n, self.fm, None, device=dev)
+        wave = engine.scl_wave_frames(plan, self.L)
+        if not B:
+            B = 5 * wave
+        if not Be:
+            Be = B
+        Be = min(Be, B)
+        self.B, self.Be = B, Be
         gen = torch.Generator(device=dev)
-        self.xy = torch.empty((B, N, 2), dtype=torch.float64, device=dev)
-        self.info_tx = torch.empty((B, K), dtype=torch.uint8, device=dev)
-        self.fvals = torch.zeros((B, N - K), dtype=torch.uint8, device=dev)
+        self.ys = torch.empty((B, N), dtype=torch.uint8, device=dev)
+        self.info_tx = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
+        npairs = min(self.pairs_frames, B)
+        self.xy = torch.empty((npairs, N, 2), dtype=torch.float64, device=dev)
+        shifts = torch.arange(32, device=dev, dtype=torch.int32)
         CH = 1 << 12
         for c0 in range(0, B, CH):
             c1 = min(B, c0 + CH)
             gen.manual_seed(4321 + 7919 * ((rank * B + c0) // CH))
-            it = torch.randint(0, 2, (c1 - c0, K), dtype=torch.uint8, device=dev, generator=gen)
+            it = torch.randint(-2 ** 31, 2 ** 31 - 1, (c1 - c0, plan.Kw), dtype=torch.int64, device=dev, generator=gen).to(torch.int32)
             self.info_tx[c0:c1] = it
-            cw = engine.qsc_encode(plan, it.contiguous())
-            self.xy[c0:c1] = self.make_xy(torch, cw, gen)
-            del it, cw
-        self.out = None
-        self.Be = Be
-        self.xy_host = torch.empty((Be, N, 2), dtype=torch.float64).pin_memory()
-        self.xy_host.copy_(self.xy[:Be])
-        self.ai_host = torch.empty((Be, K), dtype=torch.uint8).pin_memory()
+            bits = ((it.unsqueeze(-1) >> shifts) & 1).reshape(c1 - c0, K).to(torch.uint8)
+            cw = engine.qsc_encode(plan, bits.contiguous())
+            y = self.make_y(torch, cw, gen)
+            self.ys[c0:c1] = self.quantise(torch, y)
+            if c0 < npairs:
+                m = min(c1, npairs) - c0
+                self.xy[c0:c0 + m] = self.pairs(torch, y[:m])
+            del it, bits, cw, y
+        self.info_out = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
+        self.res_out = torch.empty((B,), dtype=torch.int32, device=dev)
+        self.y_host = torch.empty((Be, N), dtype=torch.uint8).pin_memory()
+        self.y_host.copy_(self.ys[:Be])
+        self.ai_host = torch.empty((Be, plan.Kw), dtype=torch.int32).pin_memory()
         self.ai_host.copy_(self.info_tx[:Be])
-        self.info_host = torch.empty((Be, K), dtype=torch.uint8).pin_memory()
+        self.info_host = torch.empty((Be, plan.Kw), dtype=torch.int32).pin_memory()
         self.res_host = torch.empty((Be,), dtype=torch.int32).pin_memory()
-        self.fv_host = torch.zeros((Be, N - K), dtype=torch.uint8).pin_memory()
-        self.h2d = int(Be * (N * 16 + K + (N - K)))
-        self.d2h = int(Be * (K + 4))
-        self.input_note = ("float64 probability pairs [B,N,2] = xyVectorDistribution.probs (%.2f GiB per step per GPU, larger "
-                           "than L2: no flush needed)" % (B * N * 16 / 2 ** 30))
+        self.h2d = int(Be * (N + plan.Kw * 4))
+        self.d2h = int(Be * (plan.Kw * 4 + 4))
+        self.input_note = ("uint8 channel symbols [B,N] (BI-AWGN output quantised to 256 levels) + the [256,2] channel table; "
+                           "actual information bit-packed; %.2f GiB of symbols per step per GPU (device-resident run: inputs "
+                           "larger than L2, no flush needed)" % (B * N / 2 ** 30))
 
     def step(self):
-        self.out = self.engine.scl_decode_probs(self.plan, self.L, self.xy, self.fvals, self.info_tx)
+        self.engine.scl_decode_packed(self.plan, self.L, self.info_tx, y=self.ys, table=self.tab, out=(self.info_out, self.res_out))
 
     def e2e_step(self):
-        # the public host-batch call: chunked, H2D / decode / D2H overlapped on two streams (engine.host_pipeline)
-        self.engine.scl_decode_probs_host(self.plan, self.L, self.xy_host, self.fv_host, self.ai_host, self.info_host,
-                                          self.res_host)
+        # the public host-batch call: chunks of one resident wave, H2D / decode / D2H overlapped on three streams
+        self.engine.scl_decode_symbols_host(self.plan, self.L, self.y_host, self.tab, self.ai_host, self.info_host, self.res_host)
 
     def counters(self):
-        torch = self.torch
-        diff = (self.out["info"] != self.info_tx)
-        c = torch.zeros(3, dtype=torch.int64, device=diff.device)
-        c[0] = diff.shape[0]
-        c[1] = diff.any(dim=1).sum()
-        c[2] = diff.sum()
-        return c
+        return self.engine.count_errors(self.info_out, self.info_tx, self.K)
+
+    def prob_result_hist(self):
+        return self.torch.bincount(self.res_out.clamp(min=0), minlength=6).cpu().numpy().tolist()
+
+    # ---- second record: the unquantised outputs of the first frames as float64 pairs ----
+    def pairs_setup(self):
+        torch, plan = self.torch, self.plan
+        m = self.xy.shape[0]
+        self.p_info = torch.empty((m, plan.Kw), dtype=torch.int32, device=self.xy.device)
+        self.p_res = torch.empty((m,), dtype=torch.int32, device=self.xy.device)
+        self.xy_host = torch.empty((m, self.N, 2), dtype=torch.float64).pin_memory()
+        self.xy_host.copy_(self.xy)
+        self.p_ai_host = torch.empty((m, plan.Kw), dtype=torch.int32).pin_memory()
+        self.p_ai_host.copy_(self.info_tx[:m])
+        self.p_info_host = torch.empty((m, plan.Kw), dtype=torch.int32).pin_memory()
+        self.p_res_host = torch.empty((m,), dtype=torch.int32).pin_memory()
+
+    def pairs_step(self):
+        m = self.xy.shape[0]
+        self.engine.scl_decode_packed(self.plan, self.L, self.info_tx[:m], xy=self.xy, out=(self.p_info, self.p_res))
+
+    def pairs_e2e_step(self):
+        self.engine.scl_decode_packed_host(self.plan, self.L, self.xy_host, self.p_ai_host, self.p_info_host, self.p_res_host)
 
     def cpu_inputs_from_gpu(self, sample):
-        return (self.xy[:sample].cpu().numpy(), self.info_tx[:sample].cpu().numpy().astype(np.int64))
+        ys = self.ys[:sample].cpu().numpy()
+        info = self.engine.unpack_bits(self.info_tx[:sample].cpu().numpy(), self.K).astype(np.int64)
+        return (self.tab[ys], info)  # makeQaryMemorylessVectorDistribution, QaryMemorylessDistribution.py:757-776
 
     def gpu_info(self, sample):
-        return self.out["info"][:sample].cpu().numpy().astype(np.int64)
+        return self.engine.unpack_bits(self.info_out[:sample].cpu().numpy(), self.K).astype(np.int64)
 
     def cpu_inputs_synth(self, frames):
         import oracle
@@ -425,11 +484,9 @@ class SclBinary4096:
         u = np.zeros((frames, self.N), dtype=np.int64)
         u[:, self.fm == 0] = info
         cw = np.stack([oracle.polar_transform_qudits(2, u[b]) for b in range(frames)])
-        sigma = awgn_sigma()
-        y = (1.0 - 2.0 * cw) + sigma * rng.standard_normal(cw.shape)
-        l0, l1 = -(y - 1) ** 2 / (2 * sigma ** 2), -(y + 1) ** 2 / (2 * sigma ** 2)
-        m = np.maximum(l0, l1)
-        return (np.stack([np.exp(l0 - m), np.exp(l1 - m)], axis=-1), info)
+        y = (1.0 - 2.0 * cw) + self.sigma * rng.standard_normal(cw.shape)
+        ys = np.clip(np.floor((y + self.ymax) / self.qstep), 0, self.tab.shape[0] - 1).astype(np.int64)
+        return (self.tab[ys], info)
 
     def cpu_decode(self, inputs, threads, out=None):
         import oracle
@@ -458,8 +515,7 @@ class ScQary2048:
     default_frames, default_e2e, default_cpu = 151552, 151552, 1 << 11
     N, K, n, q = 2048, 1024, 11, 3
     alg_bytes_frame = 25344
-    ncu = {"dram_bytes_per_frame": 0.740e6, "warp_inst_per_frame": 80.8e3, "issue_active_pct": 24.6,
-           "capture": "profiles/r1_f_qsc_ncu_summary.md (prof_qsc_c)"}
+    ncu_key = "qsc_decode_kernel_q3"
     info_bits = 1024 * math.log2(3)
     allow_ga = False
 
@@ -708,9 +764,55 @@ def head(x, m):
 
 
 # ---------------------------------------------------------------------------------------------------
+def wilson(errors, frames, z=1.959963984540054):
+    """95 % Wilson score interval of an error rate (the reference prints a bare ratio, BinaryPolarEncoderDecoder.py:387)."""
+    if frames <= 0:
+        return [0.0, 1.0]
+    ph = errors / frames
+    d = 1.0 + z * z / frames
+    c = ph + z * z / (2 * frames)
+    h = z * math.sqrt(ph * (1 - ph) / frames + z * z / (4.0 * frames * frames))
+    return [max(0.0, (c - h) / d), min(1.0, (c + h) / d)]
+
+
+def source_sha(files):
+    import hashlib
+    h = hashlib.sha256()
+    for f in files:
+        with open(os.path.join(ROOT, "polarcub_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_figures(key):
+    """Figures of the committed `ncu --set full` capture of a kernel (profiles/r2_ncu.json, written by scripts/ncu_to_json.py
+    from the .ncu-rep of the same bench command).  Each entry records a hash of the kernel's source files; when the sources
+    have changed since the capture the figures are refused (None) instead of being quoted stale."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu.json")) as f:
+            e = json.load(f).get(key)
+    except Exception:
+        return None, "profiles/r2_ncu.json missing"
+    if not e:
+        return None, "no capture of %s in profiles/r2_ncu.json" % key
+    try:
+        now = source_sha(e["source_files"])
+    except Exception:
+        return None, "source files of the capture not found"
+    if now != e["source_sha"]:
+        return None, "capture %s is of other sources (%s, now %s): refused as stale" % (e.get("capture"), e["source_sha"], now)
+    return e, None
+
+
+def config_of(w):
+    """Identical in both arms (ours / reference)."""
+    return {"workload": w.name, "N": w.N, "K": int(w.K), "construction": w.construction,
+            "parity": "bit-identical to the reference (float64 probability arithmetic, same rounding order)"}
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU algorithm (the oracle port; the Python original cannot travel to the GPU box),
-    all host threads, bounded sample per step."""
+    """--impl reference: the reference's CPU algorithm (the oracle PORT of it in C; the Python original cannot travel to the
+    GPU box), all host threads, a bounded sample of the workload per step."""
     if rank != 0:
         return
     import oracle
@@ -732,7 +834,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "decoded info Gbit/s", "value": val, "unit": "Gbit/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
-        "config": {"workload": w.name, "frames_per_step": frames, "construction": w.construction},
+        "config": config_of(w), "frames_per_step": frames,
         "frames_per_s": done / t,
         "cpu_baseline": {"value": val, "unit": "Gbit/s", "cores": cores, "kind": "port",
                          "sample": "%d frames/step x %d steps, %s, %d threads" % (frames, args.steps, w.cpu_what, cores)},
@@ -753,21 +855,9 @@ def time_steps(torch, fn, steps, barrier):
     return e0.elapsed_time(e1)
 
 
-def run_ours(args, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
-    from polarcub_b200 import engine
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    w = WORKLOADS[args.workload]()
-    w.allow_ga = args.construction != "reference"
-    B = args.frames or w.default_frames
-    Be = min(args.e2e_frames or w.default_e2e, B)
-    if world > 1 and args.workload == "sc2p20" and not args.e2e_frames:
-        Be = min(Be, 8192)  # pinned host staging is per rank: 8 GiB each instead of 32
-    w.setup(dev, rank, B, Be)
-    torch.cuda.synchronize()
-
+def measure(w, args, torch, engine, dist, world, rank, local_rank, dev, B, Be, with_cpu):
+    """One full record of a workload: device-resident value, e2e through host buffers, roofline of the dominant kernel, error
+    counters (+ the CPU leg and the frame-by-frame parity check at N = 1).  Every rank runs it; rank 0 returns the record."""
     def barrier():
         if world > 1:
             dist.barrier()
@@ -802,7 +892,7 @@ def run_ours(args, rank, world, local_rank):
     ms, ms_e2e = float(t[0]), float(t[1])
     cnt = counters.cpu().numpy()
     if rank != 0:
-        return
+        return None
 
     frames_total = B * world * args.steps
     bits = w.info_bits
@@ -810,15 +900,15 @@ def run_ours(args, rank, world, local_rank):
     e2e_val = Be * world * args.steps * bits / (ms_e2e * 1e-3) / 1e9
     peak, peak_kind = measured_peak_hbm()
     achieved = (B * args.steps * w.alg_bytes_frame) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
-    line = {
+    frames_counted, ferr = int(cnt[0]), int(cnt[1])
+    rec = {
         "metric": "decoded info Gbit/s", "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
-        "config": {"workload": w.name, "N": w.N, "K": w.K, "frames_per_step_per_gpu": B, "input": w.input_note,
-                   "construction": w.construction,
-                   "parity": "bit-identical to the reference (float64 probability arithmetic, same rounding order)"},
+        "config": config_of(w), "frames_per_step_per_gpu": B, "input": w.input_note,
         "frames_per_s": frames_total / (ms * 1e-3),
-        "fer": float(cnt[1]) / max(1, int(cnt[0])), "ber": float(cnt[2]) / max(1, int(cnt[0]) * w.K),
+        "fer": ferr / max(1, frames_counted), "fer_ci95": wilson(ferr, frames_counted), "frames_counted": frames_counted,
+        "ber": float(cnt[2]) / max(1, frames_counted * w.K),
         "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h,
                 "frames_per_step_per_gpu": Be},
         "gpu_launches": int(launches),
@@ -832,23 +922,30 @@ def run_ours(args, rank, world, local_rank):
                              "float64 SC/SCL decoding is bound by instruction issue and the latency of the per-frame scratch, "
                              "not by the algorithmic HBM bytes (SURVEY.md 8d); see `issue` / `traffic` and profiles/"},
     }
+    if hasattr(w, "prob_result_hist"):
+        rec["prob_result_hist"] = w.prob_result_hist()
     if getattr(w, "design_bytes_frame", None) and k_ms > 0:
         d_ach = (B * args.steps * w.design_bytes_frame) / (k_ms * 1e-3) / 1e9
-        line["roofline"]["design"] = {"bytes_per_frame": w.design_bytes_frame, "achieved": d_ach, "unit": "GB/s", "frac": d_ach / peak}
-    ncu = getattr(w, "ncu", None)
-    if ncu and k_ms > 0:
-        # figures of the committed `ncu --set full` capture of this kernel (profiles/), scaled to this run's launches:
+        rec["roofline"]["design"] = {"bytes_per_frame": w.design_bytes_frame, "achieved": d_ach, "unit": "GB/s", "frac": d_ach / peak}
+    key = getattr(w, "ncu_key", None)
+    if key and k_ms > 0:
+        # figures of the committed `ncu --set full` capture of this kernel, scaled to this run's launches:
         # traffic = measured DRAM bytes per launch; issue = warp instructions issued per second vs 4 schedulers x SMs x clock
-        fpl = B * args.steps / max(1, k_launches)
-        r = line["roofline"]
-        r["traffic"] = ncu["dram_bytes_per_frame"] * fpl
-        r["traffic_frac_of_peak"] = ncu["dram_bytes_per_frame"] * B * args.steps / (k_ms * 1e-3) / 1e9 / peak
-        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        ipeak = 4 * 148 * sm_mhz * 1e6
-        iach = ncu["warp_inst_per_frame"] * B * args.steps / (k_ms * 1e-3)
-        r["issue"] = {"achieved": iach, "peak": ipeak, "unit": "warp inst/s", "frac": iach / ipeak,
-                      "ncu_issue_active_pct": ncu["issue_active_pct"], "capture": ncu["capture"]}
-    if world == 1:
+        ncu, why = ncu_figures(key)
+        r = rec["roofline"]
+        if ncu is None:
+            r["traffic_note"] = why
+        else:
+            fpl = B * args.steps / max(1, k_launches)
+            r["traffic"] = ncu["dram_bytes_per_frame"] * fpl
+            r["traffic_bytes_per_frame"] = ncu["dram_bytes_per_frame"]
+            r["traffic_frac_of_peak"] = ncu["dram_bytes_per_frame"] * B * args.steps / (k_ms * 1e-3) / 1e9 / peak
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            ipeak = 4 * 148 * sm_mhz * 1e6
+            iach = ncu["warp_inst_per_frame"] * B * args.steps / (k_ms * 1e-3)
+            r["issue"] = {"achieved": iach, "peak": ipeak, "unit": "warp inst/s", "frac": iach / ipeak,
+                          "ncu_issue_active_pct": ncu["issue_active_pct"], "capture": ncu["capture"], "source_sha": ncu["source_sha"]}
+    if with_cpu:
         import oracle
         cores = os.cpu_count() or 1
         sample = min(B, args.cpu_frames or w.default_cpu)
@@ -859,26 +956,95 @@ def run_ours(args, rank, world, local_rank):
         done, dt = w.cpu_decode(inputs, cores, out=cpu_info)
         # FER parity on identical channel outputs: the CPU port's decisions against the GPU's, frame by frame
         same = (w.gpu_info(sample) == cpu_info).all(axis=1)
-        line["parity_check"] = {"frames_compared": int(sample), "identical": int(same.sum()), "unexplained": int((~same).sum()),
-                                "against": "oracle port on the same channel outputs (bit-exact bar, no tie tolerance needed)"}
-        line["cpu_baseline"] = {"value": done * bits / dt / 1e9, "unit": "Gbit/s", "cores": cores, "kind": "port",
-                                "frames_per_s": done / dt,
-                                "sample": "first %d frames of the GPU batch, %s on %d threads (%.1f s wall)" % (
-                                    sample, w.cpu_what, cores, dt)}
+        rec["parity_check"] = {"frames_compared": int(sample), "identical": int(same.sum()), "unexplained": int((~same).sum()),
+                               "against": "oracle port on the same channel outputs (bit-exact bar, no tie tolerance needed)"}
+        rec["cpu_baseline"] = {"value": done * bits / dt / 1e9, "unit": "Gbit/s", "cores": cores, "kind": "port",
+                               "frames_per_s": done / dt,
+                               "sample": "first %d frames of the GPU batch, %s on %d threads (%.1f s wall)" % (
+                                   sample, w.cpu_what, cores, dt)}
+    return rec
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from polarcub_b200 import engine
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    w = WORKLOADS[args.workload]()
+    w.allow_ga = args.construction != "reference"
+    B = args.frames or w.default_frames
+    Be = min(args.e2e_frames or w.default_e2e, B) if B else args.e2e_frames
+    if world > 1 and args.workload == "sc2p20" and not args.e2e_frames:
+        Be = min(Be, 8192)  # pinned host staging is per rank: 8 GiB each instead of 32
+    w.setup(dev, rank, B, Be)
+    B, Be = getattr(w, "B", B), getattr(w, "Be", Be)
+    torch.cuda.synchronize()
+    line = measure(w, args, torch, engine, dist, world, rank, local_rank, dev, B, Be, with_cpu=(world == 1))
+
+    records = {}
     if args.workload == "scl4096" and not args.no_secondary:
-        # BASELINE.json's metric also names SC N=1024: a short device-resident measurement of it rides along
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # (1) the same code on float64 probability pairs (xyVectorDistribution.probs, round 1's input): device-resident and
+        #     end to end (64 KiB per frame over PCIe)
+        w.pairs_setup()
+        for _ in range(2):
+            w.pairs_step()
+        st = max(3, args.steps // 4)
+        ms_p = time_steps(torch, w.pairs_step, st, barrier)
+        w.pairs_e2e_step()
+        ms_pe = time_steps(torch, w.pairs_e2e_step, st, barrier)
+        tt = torch.tensor([ms_p, ms_pe], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        m = w.xy.shape[0]
+        if rank == 0:
+            records["float64_pairs"] = {
+                "input": "float64 probability pairs [B,N,2] of the unquantised channel outputs of the first %d frames" % m,
+                "value": st * m * world * w.info_bits / (float(tt[0]) * 1e-3) / 1e9, "unit": "Gbit/s",
+                "frames_per_s": st * m * world / (float(tt[0]) * 1e-3), "steps": st, "frames_per_step_per_gpu": m,
+                "e2e": {"value": st * m * world * w.info_bits / (float(tt[1]) * 1e-3) / 1e9, "unit": "Gbit/s",
+                        "h2d_bytes_per_step": int(m * (w.N * 16 + w.plan.Kw * 4)), "d2h_bytes_per_step": int(m * (w.plan.Kw * 4 + 4))}}
+        del w.xy, w.xy_host
+        # (2) a noisier operating point: more frames end outside the list, so the genie replay of the final kernel runs
+        w2 = SclBinary4096()
+        w2.ebn0_db, w2.pairs_frames, w2.allow_ga = 1.0, 0, w.allow_ga
+        w2.setup(dev, rank, 2 * engine.scl_wave_frames(w.plan, w.L), 1024)
+        for _ in range(2):
+            w2.step()
+        ms_n = time_steps(torch, w2.step, st, barrier)
+        c2 = w2.counters()
+        tt = torch.tensor([ms_n], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c2, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            c2 = c2.cpu().numpy()
+            records["ebn0_1dB"] = {"value": st * w2.B * world * w2.info_bits / (float(tt[0]) * 1e-3) / 1e9, "unit": "Gbit/s",
+                                   "frames_per_s": st * w2.B * world / (float(tt[0]) * 1e-3), "steps": st,
+                                   "frames_per_step_per_gpu": w2.B, "fer": int(c2[1]) / max(1, int(c2[0])),
+                                   "fer_ci95": wilson(int(c2[1]), int(c2[0])), "prob_result_hist": w2.prob_result_hist(),
+                                   "note": "Eb/N0 = 1 dB, same code: frames whose actual word is not in the final list take the "
+                                           "genie replay of sclp_final_kernel (ProbResult >= 2)"}
+        del w2
+        # (3) BASELINE.json's metric also names SC N=1024: a FULL second record (value, e2e, roofline, cpu_baseline, parity)
         del w
         torch.cuda.empty_cache()
         s = ScBinary1024()
-        Bs = 1 << 19
-        s.setup(dev, rank, Bs, 1 << 10)
-        for _ in range(2):
-            s.step()
-        ms_s = time_steps(torch, s.step, 3, torch.cuda.synchronize)  # rank 0 only: no collective barrier here
-        line["secondary"] = {"workload": s.name, "value": 3 * Bs * world * s.info_bits / (ms_s * 1e-3) / 1e9, "unit": "Gbit/s",
-                             "frames_per_s": 3 * Bs * world / (ms_s * 1e-3), "frames_per_step_per_gpu": Bs, "steps": 3,
-                             "note": "device-resident, this rank's clock only; full line: --workload sc1024"}
-    print(json.dumps(line), flush=True)
+        s.allow_ga = args.construction != "reference"
+        Bs = s.default_frames
+        s.setup(dev, rank, Bs, Bs)
+        rec = measure(s, args, torch, engine, dist, world, rank, local_rank, dev, Bs, Bs, with_cpu=(world == 1))
+        if rank == 0:
+            records["sc_n1024"] = rec
+    if rank == 0:
+        if records:
+            line["records"] = records
+        print(json.dumps(line), flush=True)
 
 
 def main():

@@ -19,9 +19,18 @@ from .CollectionOfBinaryTrellises import CollectionOfBinaryTrellises
 def _probs_of(vd, length, cols):
     """Accept any VectorDistribution-like object exposing `.probs` [length, cols] (the reference's own
     BinaryMemorylessVectorDistribution works unchanged), or a plain array."""
+    if not hasattr(vd, "probs") and (hasattr(vd, "trellises") or hasattr(vd, "layers") or type(vd).__name__ in (
+            "CollectionOfBinaryTrellises", "BinaryTrellis")):
+        # the reference's own CollectionOfBinaryTrellises / BinaryTrellis objects (dict-of-objects trellises) cannot be read
+        # by the CUDA path: the collection has to come from this package's builder, which keeps the trimmed sub-words
+        raise PolarcubError(
+            "trellis inputs must be built with polarcub_b200.CollectionOfBinaryTrellises."
+            "buildCollectionOfBinaryTrellises_uniformInput_deletion (the reference-built %s object holds Python trellis "
+            "graphs the CUDA decoder cannot ingest); swap the builder import as INTEGRATION.md shows" % type(vd).__name__)
     p = getattr(vd, "probs", vd)
     p = np.asarray(p, dtype=np.float64)
-    assert p.shape == (length, cols)
+    if p.shape != (length, cols):
+        raise AssertionError("vector distribution of shape %s where (%d, %d) is expected" % (p.shape, length, cols))
     return p
 
 

@@ -116,6 +116,9 @@ class QaryPolarEncoderDecoder:
         dev = self.plan.device
         xy = xyProbs if torch.is_tensor(xyProbs) else torch.from_numpy(np.ascontiguousarray(xyProbs, dtype=np.float64))
         B = xy.shape[0]
+        if self.q == 2 and 1 <= self.n <= 13:
+            return self._list_decode_packed(B, frozenValues, maxListSize, actualInformation, return_list,
+                                            xy=xy.to(dev).contiguous())
         fv = torch.from_numpy(np.ascontiguousarray(frozenValues, dtype=np.uint8).reshape(B, self.length - self.k))
         ai = torch.from_numpy(np.ascontiguousarray(actualInformation, dtype=np.uint8).reshape(B, self.k))
         out = engine.scl_decode_probs(self.plan, int(maxListSize), xy.to(dev).contiguous(), fv.to(dev).contiguous(),
@@ -127,6 +130,45 @@ class QaryPolarEncoderDecoder:
         lst = {"list_size": out["list_size"].cpu().numpy(), "list_prob": out["list_prob"].cpu().numpy(),
                "actual_prob": out["actual_prob"].cpu().numpy(),
                "list_info": out["list_info"].cpu().numpy().astype(np.int64)}
+        return info, res, lst
+
+    def listDecode_symbols_batch(self, y, table, frozenValues, maxListSize, actualInformation, return_list=False):
+        """Binary listDecode of channel OUTPUT SYMBOLS: y uint8 [B,N] with table [Y,2] = the rows
+        makeQaryMemorylessVectorDistribution(length, y) copies into probs (QaryMemorylessDistribution.py:757-776), fused
+        into the decoder (pc_scl_decode_symbols).  Same returns as listDecode_batch."""
+        self._require_linear()
+        if self.q != 2:
+            raise PolarcubError("listDecode_symbols_batch is binary (q = 2)")
+        yt = y if torch.is_tensor(y) else torch.from_numpy(np.ascontiguousarray(y, dtype=np.uint8))
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        if not torch.is_tensor(y) and yt.numel() and int(yt.max()) >= table.shape[0]:
+            raise PolarcubError("channel symbol %d outside the %d-row table" % (int(yt.max()), table.shape[0]))
+        return self._list_decode_packed(yt.shape[0], frozenValues, maxListSize, actualInformation, return_list,
+                                        y=yt.to(self.plan.device).contiguous(), table=table)
+
+    def _list_decode_packed(self, B, frozenValues, maxListSize, actualInformation, return_list, **chan):
+        """pc_scl_decode_packed: bit-packed side buffers; all-zero frozen values travel as NULL."""
+        dev = self.plan.device
+        nf = self.length - self.k
+        fvn = np.ascontiguousarray(frozenValues, dtype=np.uint8).reshape(B, nf)
+        fvp = None
+        if nf and fvn.any():
+            fvp = torch.from_numpy(engine.pack_bits(fvn).view(np.int32)).to(dev)
+        ain = np.ascontiguousarray(actualInformation, dtype=np.uint8).reshape(B, self.k)
+        aip = torch.from_numpy(engine.pack_bits(ain).view(np.int32).reshape(B, -1)).to(dev)
+        if aip.shape[1] == 0:
+            aip = torch.zeros((B, 1), dtype=torch.int32, device=dev)
+        out = engine.scl_decode_packed(self.plan, int(maxListSize), aip, frozen_packed=fvp, want_list=return_list,
+                                       want_list_info=return_list, **chan)
+        info = engine.unpack_bits(out["info_packed"].cpu().numpy(), self.k).astype(np.int64)
+        res = out["prob_result"].cpu().numpy()
+        if (res < 0).any():
+            raise PolarcubError("list decoder: a node value left the range of the compressed level format")
+        if not return_list:
+            return info, res
+        lst = {"list_size": out["list_size"].cpu().numpy(), "list_prob": out["list_prob"].cpu().numpy(),
+               "actual_prob": out["actual_prob"].cpu().numpy(),
+               "list_info": engine.unpack_bits(out["list_info_packed"].cpu().numpy(), self.k).astype(np.int64)}
         return info, res, lst
 
     def listDecode(self, xyVectorDistribution, frozenValues, maxListSize, check_matrix, check_value,

@@ -42,14 +42,6 @@ int sclp_decode_packed(const pc_plan *plan, const SclTables *T, int L, const dou
                        int32_t *d_lsize, double *d_lprob, double *d_aprob, uint32_t *d_linfo, void *ws, size_t ws_bytes,
                        cudaStream_t st);
 
-// scl_warp.cu: frame-per-warp binary decoder (round 1's kernel, kept for comparison: PC_SCL_WARP=1)
-bool sclw_supported(const pc_plan *plan, int L);
-size_t sclw_workspace_bytes(const pc_plan *plan, int L, int64_t B);
-int sclw_decode(const pc_plan *plan, const SclTables *T, int L, const double *d_xy, const uint8_t *d_fv, const uint8_t *d_ainfo,
-                int64_t B, uint8_t *d_info, int32_t *d_res, int32_t *d_lsize, double *d_lprob, double *d_aprob,
-                uint8_t *d_linfo, void *ws, size_t ws_bytes, cudaStream_t st);
-
-int64_t sclw_wave_frames(const pc_plan *plan, int L);
 
 struct SclParams {
     int n, k, L, n_ops, nfrozen;
@@ -550,7 +542,6 @@ extern "C" {
 size_t pc_scl_workspace_bytes(const pc_plan *plan, int L, int64_t B, int want_list) {
     if (!plan || B <= 0 || L < 1 || L > pc::SCL_LMAX) return 256;
     if (pc::sclp_supported(plan, L)) return pc::sclp_workspace_bytes(plan, L, B, want_list != 0);
-    if (pc::sclw_supported(plan, L)) return pc::sclw_workspace_bytes(plan, L, B);
     int64_t chunk = pc::round_up(B, 32);
     const int64_t cap = (int64_t)pc::num_sms() * 2 * pc::SCL_THREADS * 4;
     if (chunk > cap) chunk = cap;
@@ -560,7 +551,6 @@ size_t pc_scl_workspace_bytes(const pc_plan *plan, int L, int64_t B, int want_li
 int64_t pc_scl_wave_frames(const pc_plan *plan, int L) {
     if (!plan || L < 1 || L > pc::SCL_LMAX) return 0;
     if (pc::sclp_supported(plan, L)) return pc::sclp_wave_frames(plan, L);
-    if (pc::sclw_supported(plan, L)) return pc::sclw_wave_frames(plan, L);
     return (int64_t)pc::num_sms() * 2 * pc::SCL_THREADS;
 }
 
@@ -588,9 +578,6 @@ int pc_scl_decode_probs(const pc_plan *plan, int L, const double *d_xy, const ui
     if (sclp_supported(plan, L))  // q = 2: one path per lane, 32 / L frames per warp (scl_path.cu)
         return sclp_decode_bytes(plan, T, L, d_xy, d_frozen_values, d_actual_info, B, d_info, d_prob_result, d_list_size,
                                  d_list_prob, d_actual_prob, d_list_info, d_workspace, workspace_bytes, st);
-    if (sclw_supported(plan, L))  // q = 2: one frame per warp (scl_warp.cu), PC_SCL_WARP=1
-        return sclw_decode(plan, T, L, d_xy, d_frozen_values, d_actual_info, B, d_info, d_prob_result, d_list_size,
-                           d_list_prob, d_actual_prob, d_list_info, d_workspace, workspace_bytes, st);
     int64_t chunk = round_up(B, 32);
     const int64_t cap = (int64_t)num_sms() * 2 * SCL_THREADS * 4;
     if (chunk > cap) chunk = cap;

@@ -966,7 +966,7 @@ struct SclpKnobs {
         nst = envp_int("PC_SCLP_STAGES", 2);
         timing = envp_int("PC_SCLP_TIMING", 0);
         skew = envp_int("PC_SCLP_SKEW", 1);
-        off = envp_int("PC_SCL_WARP", 0) || envp_int("PC_SCL_GENERIC", 0) || envp_int("PC_SCL_CTA", 0);
+        off = envp_int("PC_SCL_GENERIC", 0);  // tests: force the generic (q <= 5, frame per lane) decoder for q = 2
     }
 };
 #ifdef PC_EMU

@@ -3,7 +3,6 @@
 mkdir -p gpurun_out
 out=gpurun_out/sweep_sclp.log
 : > $out
-PC_SCL_WARP=1 python scripts/sweep_sclp_old.py >> $out 2>&1
 for w in 8 12 16 20 24 32; do
   PC_SCLP_WARPS_PER_SM=$w python scripts/sweep_sclp.py --mode probs >> $out 2>&1
 done

@@ -228,3 +228,64 @@ def test_hybrid_decoder_multi_chunk(kind, monkeypatch):
     scw, sinfo = ed.decode_symbols_batch(y, tab)
     np.testing.assert_array_equal(scw, ref_cw)
     np.testing.assert_array_equal(sinfo, ref_info)
+
+
+def test_large_block_bec_64_frames_vs_oracle(monkeypatch):
+    """BASELINE config 4 (N = 2^20, R = 0.8, BEC(0.1)) through the HYBRID decoder on one-byte state codes (the path bench.py
+    times; forced here because it engages on its own only from 6144 frames): 64 frames, every codeword and information word
+    against the oracle."""
+    import polarcub_b200 as pcb
+    from concurrent.futures import ThreadPoolExecutor
+    monkeypatch.setenv("PC_SC_HYBRID", "1")
+    n, frames = 20, 64
+    N = 1 << n
+    K = int(0.8 * N)
+    order = np.argsort(_z(n, 0.1), kind="stable")
+    fs = set(int(i) for i in order[K:])
+    ed = pcb.BinaryPolarEncoderDecoder(N, fs, 1)
+    rng = np.random.default_rng(2020)
+    info = rng.integers(0, 2, size=(frames, K))
+    cw = ed.encode_batch(info)
+    p = 0.1
+    tab = np.array([[0.5 * (1 - p), 0.0], [0.0, 0.5 * (1 - p)], [0.5 * p, 0.5 * p]])
+    y = np.where(rng.random((frames, N)) < p, 2, cw).astype(np.uint8)
+    dcw, dinfo = ed.decode_symbols_batch(y, tab)
+    xp = np.full((N, 2), 0.5)
+    oracle.lib()
+
+    def one(f):
+        return oracle.bin_decode(N, ed.frozenMask, ed.randomlyGeneratedNumbers, xp, tab[y[f]])
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        res = list(ex.map(one, range(frames)))
+    for f, (ocw, oinfo) in enumerate(res):
+        np.testing.assert_array_equal(dcw[f], ocw, err_msg="frame %d" % f)
+        np.testing.assert_array_equal(dinfo[f], oinfo, err_msg="frame %d" % f)
+
+
+@pytest.mark.parametrize("kind", ["bsc", "bec"])
+def test_hybrid_random_frozen_set_exact_workspace(kind, monkeypatch):
+    """Forced hybrid decoder at N = 2^17 with a RANDOM frozen set (sub-blocks of every rate: the sub-block scratch is sized
+    from all of them) in a workspace of exactly pc_sc_workspace_bytes_symbols, against the oracle."""
+    import polarcub_b200 as pcb
+    monkeypatch.setenv("PC_SC_HYBRID", "1")
+    n, B = 17, 24
+    N = 1 << n
+    rng = np.random.default_rng(1717)
+    fm = np.zeros(N, dtype=np.uint8)
+    # rates from ~0 to ~1 across the 128 sub-blocks of 1024 leaves, the last ones almost all information
+    for sb in range(N // 1024):
+        rate = sb / (N // 1024 - 1)
+        fm[sb * 1024:(sb + 1) * 1024] = rng.random(1024) >= rate
+    fm[-1024:] = 0
+    fs = set(np.nonzero(fm)[0].tolist())
+    ed = pcb.BinaryPolarEncoderDecoder(N, fs, 3)
+    info = rng.integers(0, 2, size=(B, ed.k))
+    cw = ed.encode_batch(info)
+    tab, y = _channel(kind, cw, rng)
+    dcw, dinfo = ed.decode_symbols_batch(y, tab)
+    xp = np.full((N, 2), 0.5)
+    for f in range(B):
+        ocw, oinfo = oracle.bin_decode(N, ed.frozenMask, ed.randomlyGeneratedNumbers, xp, tab[y[f]])
+        np.testing.assert_array_equal(dcw[f], ocw, err_msg="frame %d" % f)
+        np.testing.assert_array_equal(dinfo[f], oinfo, err_msg="frame %d" % f)

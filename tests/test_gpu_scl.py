@@ -159,3 +159,138 @@ def test_binary_scl_shapes_vs_oracle(n, L, how, rate, B):
     ginfo2, gres2 = ed.listDecode_batch(xy, fv, L, info)
     np.testing.assert_array_equal(ginfo2, ginfo)
     np.testing.assert_array_equal(gres2, gres)
+
+
+def test_ir_vs_live_reference_golden(golden_dir):
+    """QaryPolarEncoderDecoder.ir end to end (QaryPolarEncoderDecoder.py:841-858: syndrome, frozen values, listDecode with
+    genie selection): keys and ProbResult identical to the live reference (oracle/gen_golden_ir.py), q = 2 and 3, L = 1..8."""
+    import polarcub_b200 as pcb
+    g = np.load(os.path.join(golden_dir, "ir.npz"))
+    for nm in [str(s) for s in g["names"]]:
+        q, n, L, p = int(g[nm + "/q"]), int(g[nm + "/n"]), int(g[nm + "/L"]), float(g[nm + "/p"])
+        N = 1 << n
+        fs = set(np.nonzero(g[nm + "/frozen"])[0].tolist())
+        ed = pcb.QaryPolarEncoderDecoder(q, N, fs, 1)
+        for f in range(g[nm + "/a"].shape[0]):
+            jit = g[nm + "/jit"][f]
+
+            def make_xy(bv, jit=jit):
+                return np.where(np.arange(q)[None, :] == np.asarray(bv)[:, None], 1.0 - p, p / (q - 1)) * jit
+
+            a_key, b_key, pr = ed.ir(np.copy(g[nm + "/a"][f]), np.copy(g[nm + "/b"][f]), make_xy, list_size=L, check_size=0)
+            np.testing.assert_array_equal(a_key, g[nm + "/a_key"][f], err_msg="%s frame %d" % (nm, f))
+            np.testing.assert_array_equal(b_key, g[nm + "/b_key"][f], err_msg="%s frame %d" % (nm, f))
+            assert pr.value == int(g[nm + "/pr"][f]), (nm, f)
+
+
+def _awgn_table(sigma, Y):
+    import math
+    ymax = 1.0 + 4.0 * sigma
+    step = 2 * ymax / Y
+    edges = -ymax + step * np.arange(Y + 1)
+    edges[0], edges[-1] = -np.inf, np.inf
+    cdf = np.vectorize(lambda x: 0.5 * (1.0 + math.erf(x / math.sqrt(2.0))))
+    tab = np.stack([0.5 * (cdf((edges[1:] - 1) / sigma) - cdf((edges[:-1] - 1) / sigma)),
+                    0.5 * (cdf((edges[1:] + 1) / sigma) - cdf((edges[:-1] + 1) / sigma))], axis=-1)
+    return ymax, step, tab
+
+
+@pytest.mark.parametrize("n,L,Y,B", [(10, 8, 256, 24), (8, 4, 16, 40), (6, 32, 64, 12), (12, 8, 256, 9)])
+def test_symbol_input_vs_oracle(n, L, Y, B):
+    """pc_scl_decode_symbols: channel output symbols + the channel table (makeQaryMemorylessVectorDistribution fused into the
+    decoder, QaryMemorylessDistribution.py:757-776) must give what the oracle gives on the table rows; quantised BI-AWGN, where
+    equal rows make equal metrics possible, so only the returned word and ProbResult are compared with the list outputs off,
+    and the whole list where the oracle's list is tie-free."""
+    import polarcub_b200 as pcb
+    N = 1 << n
+    rng = np.random.default_rng(4000 + n + L)
+    k = N // 2
+    fs = set(int(i) for i in _bec_order(n)[:N - k])
+    ed = pcb.QaryPolarEncoderDecoder(2, N, fs, 1)
+    fm = ed.frozenMask
+    info = rng.integers(0, 2, size=(B, k))
+    fv = np.zeros((B, N - k), dtype=np.int64)
+    u = np.zeros((B, N), dtype=np.int64)
+    u[:, fm == 0] = info
+    cw = np.stack([oracle.polar_transform_qudits(2, u[b]) for b in range(B)])
+    sigma = 0.8
+    ymax, step, tab = _awgn_table(sigma, Y)
+    y = (1.0 - 2.0 * cw) + sigma * rng.standard_normal((B, N))
+    ys = np.clip(np.floor((y + ymax) / step), 0, Y - 1).astype(np.uint8)
+    ginfo, gres, lst = ed.listDecode_symbols_batch(ys, tab, fv, L, info, return_list=True)
+    xy = tab[ys]
+    for b in range(B):
+        oi, opr, ols, olinfo, olprob, oap = oracle.list_decode(2, N, L, fm, xy[b], fv[b], info[b], want_list=True)
+        if len(set(olprob[:ols].tolist())) < ols:
+            continue  # exact ties in the oracle's list: the candidate order is numpy-implementation-defined (oracle header)
+        np.testing.assert_array_equal(ginfo[b], oi, err_msg="frame %d" % b)
+        assert int(gres[b]) == opr, b
+        assert int(lst["list_size"][b]) == ols, b
+        np.testing.assert_array_equal(lst["list_info"][b][:ols], olinfo[:ols], err_msg="frame %d" % b)
+        assert np.array_equal(lst["list_prob"][b][:ols], olprob[:ols]), b
+        assert float(lst["actual_prob"][b]) == oap, b
+    with pytest.raises(pcb.PolarcubError):
+        ed.listDecode_symbols_batch(np.full((1, N), Y, dtype=np.uint8), tab, fv[:1], L, info[:1])
+
+
+def test_c2_code_tal_vardy_frozen_set():
+    """BASELINE config 2 itself: N=4096, K=2048 on the committed Tal-Vardy frozen set (the reference's degrade pass over the
+    400-bin BI-AWGN, tests/golden/constructions), L=8, Eb/N0 = 2 dB and 1 dB: word, ProbResult and the whole final list against
+    the oracle, through both channel inputs (float64 pairs and 256-level symbols)."""
+    import math
+    import polarcub_b200 as pcb
+    from polarcub_b200.construction import frozen_set_from_pe, load_pe
+    n, N, K, L, B = 12, 4096, 2048, 8, 10
+    fs = frozen_set_from_pe(load_pe("biawgn_ebn02.0_n12_L100_pe.npy"), K)
+    ed = pcb.QaryPolarEncoderDecoder(2, N, fs, 1)
+    fm = ed.frozenMask
+    rng = np.random.default_rng(20480)
+    for ebn0 in (2.0, 1.0):
+        sigma = math.sqrt(1.0 / (2.0 * 0.5 * 10.0 ** (ebn0 / 10.0)))
+        info = rng.integers(0, 2, size=(B, K))
+        fv = np.zeros((B, N - K), dtype=np.int64)
+        u = np.zeros((B, N), dtype=np.int64)
+        u[:, fm == 0] = info
+        cw = np.stack([oracle.polar_transform_qudits(2, u[b]) for b in range(B)])
+        y = (1.0 - 2.0 * cw) + sigma * rng.standard_normal((B, N))
+        l0, l1 = -(y - 1) ** 2 / (2 * sigma ** 2), -(y + 1) ** 2 / (2 * sigma ** 2)
+        m = np.maximum(l0, l1)
+        xy = np.stack([np.exp(l0 - m), np.exp(l1 - m)], axis=-1)
+        ginfo, gres, lst = ed.listDecode_batch(xy, fv, L, info, return_list=True)
+        for b in range(B):
+            oi, opr, ols, olinfo, olprob, oap = oracle.list_decode(2, N, L, fm, xy[b], fv[b], info[b], want_list=True)
+            np.testing.assert_array_equal(ginfo[b], oi, err_msg="frame %d" % b)
+            assert int(gres[b]) == opr and int(lst["list_size"][b]) == ols, b
+            np.testing.assert_array_equal(lst["list_info"][b][:ols], olinfo[:ols], err_msg="frame %d" % b)
+            assert np.array_equal(lst["list_prob"][b][:ols], olprob[:ols]) and float(lst["actual_prob"][b]) == oap, b
+        ymax, step, tab = _awgn_table(sigma, 256)
+        ys = np.clip(np.floor((y + ymax) / step), 0, 255).astype(np.uint8)
+        sinfo, sres = ed.listDecode_symbols_batch(ys, tab, fv, L, info)
+        for b in range(B):
+            oi, opr, ols, olinfo, olprob, oap = oracle.list_decode(2, N, L, fm, tab[ys[b]], fv[b], info[b], want_list=True)
+            if len(set(olprob[:ols].tolist())) < ols:
+                continue
+            np.testing.assert_array_equal(sinfo[b], oi, err_msg="symbols, frame %d" % b)
+            assert int(sres[b]) == opr, b
+
+
+def test_list_decode_without_actual_information():
+    """listDecode without actualInformation (the reference crashes in that form, QaryPolarEncoderDecoder.py:569): the first
+    list entry that passes the check matrix is returned, None as ProbResult."""
+    import polarcub_b200 as pcb
+    n, N, L = 6, 64, 8
+    rng = np.random.default_rng(6)
+    fs = set(int(i) for i in _bec_order(n)[:N // 2])
+    ed = pcb.QaryPolarEncoderDecoder(2, N, fs, 1)
+    fm, k = ed.frozenMask, ed.k
+    info = rng.integers(0, 2, size=k)
+    u = np.zeros(N, dtype=np.int64)
+    u[fm == 0] = info
+    cw = oracle.polar_transform_qudits(2, u)
+    y = (1.0 - 2.0 * cw) + 0.6 * rng.standard_normal(N)
+    l0, l1 = -(y - 1) ** 2 / 0.72, -(y + 1) ** 2 / 0.72
+    xy = np.stack([np.exp(l0 - np.maximum(l0, l1)), np.exp(l1 - np.maximum(l0, l1))], axis=-1)
+    cm = rng.integers(0, 2, size=(k, 8))
+    out, pr = ed.listDecode(xy, np.zeros(N - k, dtype=np.int64), L, cm, info @ cm % 2)
+    assert pr is None
+    np.testing.assert_array_equal(out, info)

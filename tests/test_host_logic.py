@@ -183,3 +183,38 @@ def test_four_state_algebra_matches_the_reference_arithmetic():
     # leaf rule (BinaryPolarEncoderDecoder.py:250-252): p0 >= p1 -> 0, so only "hard 1" decides 1 -- the side bit
     for c, (p0, p1) in states.items():
         assert (0 if p0 >= p1 else 1) == (c & 1)
+
+
+def test_calculate_syndrome_and_complement_vs_live_reference_golden(golden_dir):
+    """QaryPolarEncoderDecoder.calculate_syndrome_and_complement (QaryPolarEncoderDecoder.py:822-833), the host half of ir():
+    (w, u) identical to the live reference's on the goldens of oracle/gen_golden_ir.py.  No GPU needed (no plan is built)."""
+    from polarcub_b200.QaryPolarEncoderDecoder import QaryPolarEncoderDecoder
+    g = np.load(os.path.join(golden_dir, "ir.npz"))
+    for nm in [str(s) for s in g["names"]]:
+        q, n = int(g[nm + "/q"]), int(g[nm + "/n"])
+        fs = set(np.nonzero(g[nm + "/frozen"])[0].tolist())
+        ed = QaryPolarEncoderDecoder(q, 1 << n, fs, 1)
+        for f in range(g[nm + "/a"].shape[0]):
+            w, u = ed.calculate_syndrome_and_complement(np.copy(g[nm + "/a"][f]))
+            np.testing.assert_array_equal(w, g[nm + "/w"][f])
+            np.testing.assert_array_equal(u, g[nm + "/u"][f])
+            np.testing.assert_array_equal(ed.get_message_info_bits(u), g[nm + "/a_key"][f])
+
+
+def test_reference_built_trellis_objects_are_rejected_with_a_clear_error():
+    """The reference's CollectionOfBinaryTrellises / BinaryTrellis hold Python trellis graphs the CUDA path cannot read: the
+    drop-in needs the builder swapped too, and says so (a bare shape assertion used to fire)."""
+    from polarcub_b200._lib import PolarcubError
+    from polarcub_b200.BinaryPolarEncoderDecoder import _probs_of
+
+    class CollectionOfBinaryTrellises:  # duck-type of the reference's class (VectorDistributions/CollectionOfBinaryTrellises.py:24-32)
+        def __init__(self):
+            self.length, self.numberOfTrellises, self.trellises = 8, 2, [object(), object()]
+
+        def __len__(self):
+            return self.length
+
+    with pytest.raises(PolarcubError, match="buildCollectionOfBinaryTrellises_uniformInput_deletion"):
+        _probs_of(CollectionOfBinaryTrellises(), 8, 2)
+    with pytest.raises(AssertionError):
+        _probs_of(np.zeros((4, 2)), 8, 2)
