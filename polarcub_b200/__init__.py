@@ -6,6 +6,7 @@ array entry points.  Device side: hand-written sm_100a CUDA kernels behind the C
 include/polarcub_b200.h (polarcub_b200/csrc).  PyTorch is used only for device memory and streams.
 """
 from . import engine  # noqa: F401
+from ._lib import PolarcubError  # noqa: F401
 from .BinaryPolarEncoderDecoder import BinaryPolarEncoderDecoder, polarTransformOfBits  # noqa: F401
 from .simulation import encodeDecodeSimulation, genieEncodeDecodeSimulation, frozenSetFromTVAndPe, readFrozenSetFromFile  # noqa: F401
 from . import Guardbands, CollectionOfBinaryTrellises, construction  # noqa: F401
@@ -13,4 +14,4 @@ from .construction import calcFrozenSet_degradingUpgrading, calcTVAndPe_degradin
 from .QaryPolarEncoderDecoder import QaryPolarEncoderDecoder, polarTransformOfQudits, ProbResult  # noqa: F401
 
 __all__ = ["BinaryPolarEncoderDecoder", "QaryPolarEncoderDecoder", "polarTransformOfBits", "polarTransformOfQudits",
-           "ProbResult", "engine", "construction", "calcFrozenSet_degradingUpgrading", "calcTVAndPe_degradingUpgrading"]
+           "ProbResult", "PolarcubError", "engine", "construction", "calcFrozenSet_degradingUpgrading", "calcTVAndPe_degradingUpgrading"]

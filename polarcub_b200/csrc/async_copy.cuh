@@ -7,6 +7,13 @@
 
 namespace pc {
 
+// barrier `id` (1..15) among `threads` threads of the CTA (whole warps)
+#ifndef PC_EMU
+__device__ __forceinline__ void pc_named_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+#else
+__device__ __forceinline__ void pc_named_barrier(int id, int threads) { emu::named_bar(id, threads); }
+#endif
+
 #ifndef PC_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

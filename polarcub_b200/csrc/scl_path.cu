@@ -33,6 +33,7 @@ namespace pc {
 struct SclpParams {
     int n, k, L, G, gsh, n_ops, lsm, rgl, NW, n_leaf, sym, want_list, nfw;
     int nst;              // stages of the bulk-copy ring (0: plain loads)
+    int wpc, sync, smem_per_warp;  // warps per CTA, per-op barrier among the warps of a scheduler, shared-memory bytes per warp
     int64_t frames;
     const uint4 *ops;
     const uint32_t *coef_words;
@@ -230,9 +231,11 @@ __device__ __forceinline__ void select_paths(const double (&cv)[8], const int M,
         int bi = -1;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {  // candidates in increasing index order: among equals the later index wins
-            const bool better = !((taken >> i) & 1u) && (byidx || cv[i] >= bv);
-            bv = better ? cv[i] : bv;
-            bi = better ? ibase + i * istep : bi;
+            if (i < M) {                // M is warp-uniform
+                const bool better = !((taken >> i) & 1u) && (byidx || cv[i] >= bv);
+                bv = better ? cv[i] : bv;
+                bi = better ? ibase + i * istep : bi;
+            }
         }
         const int mine = bi;
         for (int o = 1; o < G; o <<= 1) {
@@ -256,10 +259,16 @@ __device__ __forceinline__ void select_paths(const double (&cv)[8], const int M,
 // kernel trades latency hiding by warps against DRAM traffic of the resident frames, profiles/r2_a), so there is ONE build.
 constexpr int SCLP_MAX_WARPS_PER_SM = 12;
 template <int MB>
-__global__ void __launch_bounds__(32, MB) sclp_kernel(const SclpParams p) {
-    PC_DYN_SMEM(smem_raw);
+__global__ void __launch_bounds__(32 * MB, 1) sclp_kernel(const SclpParams p) {
+    PC_DYN_SMEM(smem_all);
+    // a CTA is p.wpc independent warps (one CTA per SM); each warp owns its slice of the shared memory and its frames.  With
+    // p.sync the warps that share a scheduler (warp index mod 4) meet at a named barrier before every op, so that they fetch
+    // the same instructions at the same time.
+    const int wic = threadIdx.x >> 5;
+    unsigned char *smem_raw = smem_all + (size_t)wic * p.smem_per_warp;
+    const int64_t gw = (int64_t)blockIdx.x * p.wpc + wic, nwarps = (int64_t)gridDim.x * p.wpc;
     const int n = p.n, N = 1 << n, L = p.L, G = p.G, gsh = p.gsh, lsm = p.lsm, NW = p.NW, rgl = p.rgl;
-    const int lane = threadIdx.x, t = lane & (G - 1), gbase = lane & ~(G - 1);
+    const int lane = threadIdx.x & 31, t = lane & (G - 1), gbase = lane & ~(G - 1);
     constexpr uint32_t FULL = 0xffffffffu;
     // ---- shared-memory carve-up (sclp_smem_bytes mirrors this) ----
     const int vrows = (2 << lsm) - 1;
@@ -270,14 +279,14 @@ __global__ void __launch_bounds__(32, MB) sclp_kernel(const SclpParams p) {
     uint64_t *bars = (uint64_t *)(stg + p.nst * 256);
     uint32_t ph = 0;
     if (p.nst) {
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
             for (int s = 0; s < p.nst; ++s) mbar_init(bars + s, 1u);
             mbar_fence_init();
         }
         __syncwarp();
     }
-    double2 *Vg = p.vg + (int64_t)blockIdx.x * p.vg_stride - (int64_t)vrows * 32;
-    uint32_t *Rg = p.rg + (int64_t)blockIdx.x * p.rg_stride - (int64_t)2 * scl2_wsum(rgl) * 32;
+    double2 *Vg = p.vg + gw * p.vg_stride - (int64_t)vrows * 32;
+    uint32_t *Rg = p.rg + gw * p.rg_stride - (int64_t)2 * scl2_wsum(rgl) * 32;
     // level l of the path vectors: rows (2^l - 1) .. ; per-path layout: element e of slot s at [e][gbase + s]; shared layout
     // (one path, written before the first fork): element e at [e / G][gbase + e % G]
     auto vbase = [&](int l) -> double2 * { return (l <= lsm ? Vs : Vg) + (((int64_t)1 << l) - 1) * 32; };
@@ -287,7 +296,12 @@ __global__ void __launch_bounds__(32, MB) sclp_kernel(const SclpParams p) {
     const bool dualon = G >= 4;  // two-variant storage of SCLP_DUAL outputs pays with four or more paths
 
 #pragma unroll 1
-    for (int64_t wave = blockIdx.x; wave * fpw < p.frames; wave += gridDim.x) {
+    // every warp of the grid runs the same number of rounds (the barriers below need that); surplus rounds decode a copy of
+    // the last frame and write nothing
+    const int64_t nwaves = (p.frames + fpw - 1) / fpw, rounds = (nwaves + nwarps - 1) / nwarps;
+#pragma unroll 1
+    for (int64_t rd = 0; rd < rounds; ++rd) {
+        const int64_t wave = rd * nwarps + gw;
         int64_t f = wave * fpw + (lane >> gsh);
         const bool fvalid = f < p.frames;
         if (!fvalid) f = p.frames - 1;  // idle lane groups decode a copy of the last frame and write nothing
@@ -301,6 +315,10 @@ __global__ void __launch_bounds__(32, MB) sclp_kernel(const SclpParams p) {
         __syncwarp();
 #pragma unroll 1
         for (int oi = 0; oi < p.n_ops; ++oi) {
+            if (p.sync == 1)
+                pc_named_barrier(1 + (wic & 3), 32 * ((p.wpc - (wic & 3) + 3) >> 2));
+            else if (p.sync == 2)
+                pc_named_barrier(1, 32 * p.wpc);
             const uint4 op = p.ops[oi];
             const int kind = op.x & 7, l = (op.x >> 3) & 15, c = (op.x >> 7) & 1, i0 = (int)op.y;
 #ifndef PC_EMU
@@ -345,21 +363,44 @@ __global__ void __launch_bounds__(32, MB) sclp_kernel(const SclpParams p) {
                         const double2 *sb = ch ? nullptr : vbase(lv);
                         double2 *db = vbase(lv - 1);
                         const int items = ddst ? (1 << lv) : (1 << (lv - 1));
+                        // four items per lane and step: the eight loads go out together, the four node updates interleave
 #pragma unroll 1
-                        for (int i = t; i < items; i += G) {
-                            const int e = ddst ? i >> 1 : i;
-                            double2 a, b;
-                            if (ch) {
-                                if (p.sym)
-                                    a = p.tab[yf[2 * e]], b = p.tab[yf[2 * e + 1]];
-                                else
-                                    a = xyf[2 * e], b = xyf[2 * e + 1];
-                            } else {
-                                const double2 *q = sb + (((2 * e) >> gsh) << 5) + gbase + ((2 * e) & (G - 1));
-                                a = q[0], b = G >= 2 ? q[1] : q[32];  // one lane per frame: consecutive elements sit in consecutive rows
+                        for (int i0 = t; i0 < items; i0 += 4 * G) {
+                            double2 a[4], b[4];
+                            uint32_t u[4];
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const int i = i0 + r * G;
+                                a[r] = b[r] = make_double2(1.0, 1.0);
+                                u[r] = 0;
+                                if (i < items) {
+                                    const int e = ddst ? i >> 1 : i;
+                                    if (ch) {
+                                        if (p.sym)
+                                            a[r] = p.tab[yf[2 * e]], b[r] = p.tab[yf[2 * e + 1]];
+                                        else
+                                            a[r] = xyf[2 * e], b[r] = xyf[2 * e + 1];
+                                    } else {
+                                        const double2 *q = sb + (((2 * e) >> gsh) << 5) + gbase + ((2 * e) & (G - 1));
+                                        a[r] = q[0], b[r] = G >= 2 ? q[1] : q[32];  // one lane per frame: consecutive elements sit in consecutive rows
+                                    }
+                                    u[r] = ddst ? (uint32_t)(i & 1) : (pl ? (rp[(e >> 5) << 5] >> (e & 31)) & 1u : 0u);
+                                }
                             }
-                            const uint32_t u = ddst ? (uint32_t)(i & 1) : (pl ? (rp[(e >> 5) << 5] >> (e & 31)) & 1u : 0u);
-                            db[((i >> gsh) << 5) + gbase + (i & (G - 1))] = node_fg(a, b, pl, u);
+                            bool sl[4];
+                            double2 y[4];
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) y[r] = node_fast(a[r], b[r], pl, u[r], sl[r]);
+                            if (sl[0] || sl[1] || sl[2] || sl[3]) {
+#pragma unroll
+                                for (int r = 0; r < 4; ++r)
+                                    if (sl[r]) y[r] = node_fg(a[r], b[r], pl, u[r]);
+                            }
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const int i = i0 + r * G;
+                                if (i < items) db[((i >> gsh) << 5) + gbase + (i & (G - 1))] = y[r];
+                            }
                         }
                         if (ps + 1 < npass) __syncwarp();
                     }
@@ -957,7 +998,7 @@ static int envp_int(const char *name, int dflt) {
 // tuning knobs are read ONCE per process (a changed environment between the workspace query and the decode cannot break
 // the sizing contract)
 struct SclpKnobs {
-    int warps_per_sm, lsm, rgl, off, nst, timing, skew;
+    int warps_per_sm, lsm, rgl, off, nst, timing, skew, sync;
     SclpKnobs() {
         warps_per_sm = envp_int("PC_SCLP_WARPS_PER_SM", SCLP_MAX_WARPS_PER_SM);
         if (warps_per_sm > SCLP_MAX_WARPS_PER_SM) warps_per_sm = SCLP_MAX_WARPS_PER_SM;
@@ -966,6 +1007,7 @@ struct SclpKnobs {
         nst = envp_int("PC_SCLP_STAGES", 2);
         timing = envp_int("PC_SCLP_TIMING", 0);
         skew = envp_int("PC_SCLP_SKEW", 1);
+        sync = envp_int("PC_SCLP_SYNC", 1);
         off = envp_int("PC_SCL_GENERIC", 0);  // tests: force the generic (q <= 5, frame per lane) decoder for q = 2
     }
 };
@@ -1011,8 +1053,8 @@ static SclpConfig sclp_config(const pc_plan *plan, int L, int64_t B) {
     const int fpw = 32 / G;
     int64_t waves = (B + fpw - 1) / fpw;
     int64_t grid = (int64_t)num_sms() * per_sm;
-    if (grid > waves) grid = waves;
-    c.grid = (int)(grid > 0 ? grid : 1);
+    if (grid > waves) grid = (waves + per_sm - 1) / per_sm * per_sm;  // whole CTAs of per_sm warps
+    c.grid = (int)(grid > 0 ? grid : per_sm);
     const int64_t vrows_all = ((int64_t)1 << n) - 1, vrows_s = ((int64_t)2 << lsm) - 1;
     c.vg_stride = (size_t)(vrows_all > vrows_s ? vrows_all - vrows_s : 0) * 32 + 32 * (size_t)(kn.skew > 0 ? kn.skew : 1);
     c.rg_stride = (size_t)2 * (scl2_wsum(n + 1) - scl2_wsum(rgl)) * 32 + 32;
@@ -1084,9 +1126,9 @@ size_t sclp_workspace_bytes(const pc_plan *plan, int L, int64_t B, bool want_lis
 }
 
 template <int MB>
-static int sclp_launch(const SclpParams &p, int grid, size_t smem, cudaStream_t st) {
+static int sclp_launch(const SclpParams &p, int ctas, size_t smem, cudaStream_t st) {
     PC_CUDA(cudaFuncSetAttribute(sclp_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PC_LAUNCH(sclp_kernel<MB>, grid, 32, smem, st, p);
+    PC_LAUNCH(sclp_kernel<MB>, ctas, 32 * p.wpc, smem, st, p);
     PC_LAUNCH_CHECK();
     return PC_OK;
 }
@@ -1159,7 +1201,7 @@ static int sclp_run(const pc_plan *plan, const SclTables *T, int L, const SclpIo
         p.lprob = (double *)(base + y.off_lprob);
         p.mxs = (double *)(base + y.off_mxs);
         const int fpw = 32 / c.G;
-        int64_t grid = (F + fpw - 1) / fpw;
+        int64_t grid = ((F + fpw - 1) / fpw + c.per_sm - 1) / c.per_sm * c.per_sm;
         if (grid > c.grid) grid = c.grid;
         static unsigned long long *d_timing = nullptr;
 #ifndef PC_EMU
@@ -1171,7 +1213,10 @@ static int sclp_run(const pc_plan *plan, const SclTables *T, int L, const SclpIo
         p.timing = d_timing;
         prof_mark(st);
         {
-            const int rc = sclp_launch<SCLP_MAX_WARPS_PER_SM>(p, (int)grid, c.smem, st);
+            // grid warps in CTAs of per_sm warps (one CTA per SM)
+            p.wpc = c.per_sm, p.sync = sclp_knobs().sync, p.smem_per_warp = (int)c.smem;
+            const int ctas = (int)((grid + c.per_sm - 1) / c.per_sm);
+            const int rc = sclp_launch<SCLP_MAX_WARPS_PER_SM>(p, ctas, c.smem * (size_t)c.per_sm, st);
             if (rc) return rc;
         }
         prof_mark(st);

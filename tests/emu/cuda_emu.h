@@ -45,6 +45,7 @@ struct Block {
     std::vector<Lane *> lanes;
     std::vector<std::map<uint32_t, Bar>> warp_bars;  // per warp, keyed by member mask
     Bar block_bar;
+    Bar named[16];
     std::vector<unsigned char> smem;
     uint64_t slots[1024][2];  // exchange slots, one per thread
     bool progress = false;
@@ -91,6 +92,7 @@ inline void arrive_wait(Bar &b, unsigned members) {
     while (b.gen == my) yield();
 }
 
+inline void named_bar(int id, int threads) { arrive_wait(S().cur->blk->named[id & 15], (unsigned)threads); }
 inline int lane_id() { return S().cur->linear & 31; }
 inline int warp_id() { return S().cur->linear >> 5; }
 

@@ -229,8 +229,9 @@ def test_symbol_input_vs_oracle(n, L, Y, B):
         np.testing.assert_array_equal(lst["list_info"][b][:ols], olinfo[:ols], err_msg="frame %d" % b)
         assert np.array_equal(lst["list_prob"][b][:ols], olprob[:ols]), b
         assert float(lst["actual_prob"][b]) == oap, b
-    with pytest.raises(pcb.PolarcubError):
-        ed.listDecode_symbols_batch(np.full((1, N), Y, dtype=np.uint8), tab, fv[:1], L, info[:1])
+    if Y < 256:  # a symbol outside the table is refused (host arrays are checked; device tensors are read as row Y-1)
+        with pytest.raises(pcb.PolarcubError):
+            ed.listDecode_symbols_batch(np.full((1, N), Y, dtype=np.uint8), tab, fv[:1], L, info[:1])
 
 
 def test_c2_code_tal_vardy_frozen_set():
