@@ -33,7 +33,7 @@ namespace pc {
 struct SclpParams {
     int n, k, L, G, gsh, n_ops, lsm, rgl, NW, n_leaf, sym, want_list, nfw;
     int nst;              // stages of the bulk-copy ring (0: plain loads)
-    int wpc, sync, smem_per_warp;  // warps per CTA, per-op barrier among the warps of a scheduler, shared-memory bytes per warp
+    int wpc, sync, smem_per_warp, bar_every;  // warps per CTA, per-op barrier among the warps of a scheduler, shared-memory bytes per warp
     int64_t frames;
     const uint4 *ops;
     const uint32_t *coef_words;
@@ -142,7 +142,8 @@ __device__ __forceinline__ void src_fetch(const Src &s, int k, Raw8 &r) {
 // loop (the staged source is warp-wide); lanes without a path skip the arithmetic.  The node updates of a step are branch-free
 // (node_fast) so that their dependency chains interleave; the rare operands outside the fast division's range are redone after.
 __device__ __forceinline__ void fg_pass(const Src &src, double2 *__restrict__ dp, double2 *__restrict__ dp2, const bool plus,
-                                        const bool fused, const uint32_t *rp, const int half, const bool valid) {
+                                        const bool fused, const uint32_t *rp, const int half, const bool valid, const int bar_id,
+                                        const int bar_threads, const int bar_every) {
     Raw8 cur, nxt;
     if (half == 2) {  // four source elements: one half step
         src_fetch<4>(src, 0, cur);
@@ -164,6 +165,7 @@ __device__ __forceinline__ void fg_pass(const Src &src, double2 *__restrict__ dp
     uint32_t w = pv ? rp[0] : 0u, wn = (pv && nsteps > 8) ? rp[32] : 0u;
 #pragma unroll 1
     for (int k = -1; k < nsteps; ++k) {
+        if (bar_every && k > 0 && (k & (bar_every - 1)) == 0) pc_named_barrier(bar_id, bar_threads);  // keep the scheduler-mates in step
         nxt = cur;
         if (k + 1 < nsteps) src_fetch<8>(src, k + 1, nxt);
         if (k >= 0 && valid) {
@@ -422,7 +424,8 @@ __global__ void __launch_bounds__(32 * MB, 1) sclp_kernel(const SclpParams p) {
                         sr.kind = SK_PATH;
                         sr.p = vbase(l) + gbase + srcslot;
                     }
-                    fg_pass(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, plus, fused, rp, half, valid);
+                    fg_pass(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, plus, fused, rp, half, valid, 1 + (wic & 3),
+                            32 * ((p.wpc - (wic & 3) + 3) >> 2), p.sync == 1 ? p.bar_every : 0);
                 }
                 __syncwarp();
                 continue;
@@ -998,7 +1001,7 @@ static int envp_int(const char *name, int dflt) {
 // tuning knobs are read ONCE per process (a changed environment between the workspace query and the decode cannot break
 // the sizing contract)
 struct SclpKnobs {
-    int warps_per_sm, lsm, rgl, off, nst, timing, skew, sync;
+    int warps_per_sm, lsm, rgl, off, nst, timing, skew, sync, bar_every;
     SclpKnobs() {
         warps_per_sm = envp_int("PC_SCLP_WARPS_PER_SM", SCLP_MAX_WARPS_PER_SM);
         if (warps_per_sm > SCLP_MAX_WARPS_PER_SM) warps_per_sm = SCLP_MAX_WARPS_PER_SM;
@@ -1008,6 +1011,7 @@ struct SclpKnobs {
         timing = envp_int("PC_SCLP_TIMING", 0);
         skew = envp_int("PC_SCLP_SKEW", 1);
         sync = envp_int("PC_SCLP_SYNC", 1);
+        bar_every = envp_int("PC_SCLP_BAR_EVERY", 0);  // power of two, 0 = no barrier inside the passes
         off = envp_int("PC_SCL_GENERIC", 0);  // tests: force the generic (q <= 5, frame per lane) decoder for q = 2
     }
 };
@@ -1214,7 +1218,7 @@ static int sclp_run(const pc_plan *plan, const SclTables *T, int L, const SclpIo
         prof_mark(st);
         {
             // grid warps in CTAs of per_sm warps (one CTA per SM)
-            p.wpc = c.per_sm, p.sync = sclp_knobs().sync, p.smem_per_warp = (int)c.smem;
+            p.wpc = c.per_sm, p.sync = sclp_knobs().sync, p.smem_per_warp = (int)c.smem, p.bar_every = sclp_knobs().bar_every;
             const int ctas = (int)((grid + c.per_sm - 1) / c.per_sm);
             const int rc = sclp_launch<SCLP_MAX_WARPS_PER_SM>(p, ctas, c.smem * (size_t)c.per_sm, st);
             if (rc) return rc;
