@@ -33,7 +33,8 @@ namespace pc {
 struct SclpParams {
     int n, k, L, G, gsh, n_ops, lsm, rgl, NW, n_leaf, sym, want_list, nfw;
     int nst;              // stages of the bulk-copy ring (0: plain loads)
-    int wpc, sync, smem_per_warp, bar_every;  // warps per CTA, per-op barrier among the warps of a scheduler, shared-memory bytes per warp
+    int alias;            // diagnostic (PC_SCLP_ALIAS): every CTA uses the scratch of CTA 0 -- wrong results, shows the DRAM-free speed
+    int wpc, sync, smem_per_warp;  // warps per CTA, per-op barrier among the warps of a scheduler, shared-memory bytes per warp
     int64_t frames;
     const uint4 *ops;
     const uint32_t *coef_words;
@@ -139,62 +140,74 @@ __device__ __forceinline__ void src_fetch(const Src &s, int k, Raw8 &r) {
 
 // level l (the source, 2 * half elements) -> level l-1 at dp[e * 32], and with `fused` also level l-2 at dp2[e * 32] (f of adjacent
 // pairs of level l-1: the MINUS (l-1) that follows).  u bits of the left child's codeword at rp[word * 32].  All lanes run the
-// loop (the staged source is warp-wide); lanes without a path skip the arithmetic.  The node updates of a step are branch-free
-// (node_fast) so that their dependency chains interleave; the rare operands outside the fast division's range are redone after.
-__device__ __forceinline__ void fg_pass(const Src &src, double2 *__restrict__ dp, double2 *__restrict__ dp2, const bool plus,
-                                        const bool fused, const uint32_t *rp, const int half, const bool valid, const int bar_id,
-                                        const int bar_threads, const int bar_every) {
-    Raw8 cur, nxt;
+// loop (the staged source is warp-wide); lanes without a path skip the arithmetic.  PLUS is a compile-time parameter and the
+// four (+ two) node updates of a step run in lock step (node_lockstep), so their dependency chains overlap; the rare operands
+// outside the fast division's range are redone after.  The loop is unrolled by two over a pair of element buffers: the raw
+// elements of step k+1 are fetched before step k is computed and no buffer is ever copied.
+template <bool PLUS>
+__device__ __forceinline__ void fg_step(const Raw8 &r, const uint32_t u4, double2 *__restrict__ &dp, double2 *__restrict__ &dp2,
+                                        const bool fused) {
+    double2 y[4];
+    const uint32_t slow = node_lockstep<4, PLUS>(r.v, u4, y);
+    if (slow) {  // rare: an operand below 1e-291 (or an un-normalised channel pair): the IEEE division
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if ((slow >> i) & 1u) y[i] = node_fg(r.v[2 * i], r.v[2 * i + 1], PLUS, (u4 >> i) & 1u);
+    }
+    dp[0] = y[0], dp[32] = y[1], dp[64] = y[2], dp[96] = y[3];
+    dp += 128;
+    if (fused) {
+        double2 z[2];
+        const uint32_t s2 = node_lockstep<2, false>(y, 0u, z);
+        if (s2) {
+            if (s2 & 1u) z[0] = node_fg(y[0], y[1], false, 0u);
+            if (s2 & 2u) z[1] = node_fg(y[2], y[3], false, 0u);
+        }
+        dp2[0] = z[0], dp2[32] = z[1];
+        dp2 += 64;
+    }
+}
+
+template <bool PLUS>
+__device__ __forceinline__ void fg_pass(const Src &src, double2 *__restrict__ dp, double2 *__restrict__ dp2, const bool fused,
+                                        const uint32_t *rp, const int half, const bool valid) {
+    Raw8 A, B;
     if (half == 2) {  // four source elements: one half step
-        src_fetch<4>(src, 0, cur);
+        src_fetch<4>(src, 0, A);
         if (valid) {
-            const uint32_t w = plus ? rp[0] : 0u;
-            const double2 y0 = node_fg(cur.v[0], cur.v[1], plus, w & 1u), y1 = node_fg(cur.v[2], cur.v[3], plus, (w >> 1) & 1u);
+            const uint32_t w = PLUS ? rp[0] : 0u;
+            const double2 y0 = node_fg(A.v[0], A.v[1], PLUS, w & 1u), y1 = node_fg(A.v[2], A.v[3], PLUS, (w >> 1) & 1u);
             dp[0] = y0, dp[32] = y1;
             if (fused) dp2[0] = node_fg(y0, y1, false, 0u);
         }
         return;
     }
-    const int nsteps = half >> 2;  // four elements of level l-1 per step
+    const int nsteps = half >> 2;  // four elements of level l-1 per step: 1, 2, 4, ...
     if (src.kind == SK_STAGED && src.lane == 0) {
         const int pre = nsteps < src.nst ? nsteps : src.nst;
         for (int k = 0; k < pre; ++k) src_issue(src, k);
     }
     // u bits: word w of the codeword covers eight steps; the next word is requested as soon as a word is taken into use
-    const bool pv = plus && valid;
+    const bool pv = PLUS && valid;
     uint32_t w = pv ? rp[0] : 0u, wn = (pv && nsteps > 8) ? rp[32] : 0u;
+    src_fetch<8>(src, 0, A);
+    if (nsteps == 1) {
+        if (valid) fg_step<PLUS>(A, w & 15u, dp, dp2, fused);
+        return;
+    }
 #pragma unroll 1
-    for (int k = -1; k < nsteps; ++k) {
-        if (bar_every && k > 0 && (k & (bar_every - 1)) == 0) pc_named_barrier(bar_id, bar_threads);  // keep the scheduler-mates in step
-        nxt = cur;
-        if (k + 1 < nsteps) src_fetch<8>(src, k + 1, nxt);
-        if (k >= 0 && valid) {
-            const int j = (4 * k) & 31;
-            const uint32_t u = w >> j;
-            bool s0, s1, s2, s3, s4 = false, s5 = false;
-            double2 y0 = node_fast(cur.v[0], cur.v[1], plus, u & 1u, s0), y1 = node_fast(cur.v[2], cur.v[3], plus, (u >> 1) & 1u, s1);
-            double2 y2 = node_fast(cur.v[4], cur.v[5], plus, (u >> 2) & 1u, s2), y3 = node_fast(cur.v[6], cur.v[7], plus, (u >> 3) & 1u, s3);
-            if (s0 || s1 || s2 || s3) {  // rare: an operand below 1e-291 (or an un-normalised channel pair): the IEEE division
-                if (s0) y0 = node_fg(cur.v[0], cur.v[1], plus, u & 1u);
-                if (s1) y1 = node_fg(cur.v[2], cur.v[3], plus, (u >> 1) & 1u);
-                if (s2) y2 = node_fg(cur.v[4], cur.v[5], plus, (u >> 2) & 1u);
-                if (s3) y3 = node_fg(cur.v[6], cur.v[7], plus, (u >> 3) & 1u);
-            }
-            dp[0] = y0, dp[32] = y1, dp[64] = y2, dp[96] = y3;
-            dp += 128;
-            if (fused) {
-                double2 z0 = node_fast(y0, y1, false, 0u, s4), z1 = node_fast(y2, y3, false, 0u, s5);
-                if (s4) z0 = node_fg(y0, y1, false, 0u);
-                if (s5) z1 = node_fg(y2, y3, false, 0u);
-                dp2[0] = z0, dp2[32] = z1;
-                dp2 += 64;
-            }
-            if (plus && j == 28) {
+    for (int k = 0; k < nsteps; k += 2) {
+        src_fetch<8>(src, k + 1, B);
+        if (valid) fg_step<PLUS>(A, (w >> ((4 * k) & 31)) & 15u, dp, dp2, fused);
+        if (k + 2 < nsteps) src_fetch<8>(src, k + 2, A);
+        if (valid) {
+            const int j = (4 * k + 4) & 31;
+            fg_step<PLUS>(B, (w >> j) & 15u, dp, dp2, fused);
+            if (PLUS && j == 28) {
                 w = wn;
-                if (k + 9 < nsteps) wn = rp[((4 * k + 36) >> 5) << 5];
+                if (k + 10 < nsteps) wn = rp[((4 * k + 40) >> 5) << 5];
             }
         }
-        cur = nxt;
     }
 }
 
@@ -210,50 +223,88 @@ __device__ __forceinline__ int group_sum(int v, const int G) {
     return v;
 }
 
-// The prune of recursiveListDecode (:446-451 etc.) over the M <= 8 candidates each lane of a frame holds (one instance for all
-// node kinds: code size): keep the ns = min(#nonzero, L) largest under the total order (metric, index), listed ascending;
-// lists with at most L candidates keep all of them in index order (the same rounds keyed by the index alone).  Candidate i of
-// the lane has index ibase + i * istep.  On return lane t < nout holds its new path: the metric and the candidate index.
-__device__ __forceinline__ void select_paths(const double (&cv)[8], const int M, const int ibase, const int istep, const bool valid,
-                                             const int cnt, const int L, const int G, const int t, int &nout, double &newprob,
-                                             int &ci) {
+// The prune of recursiveListDecode (:446-451 etc.) over the M <= 8 candidates each lane of a frame holds: keep the
+// ns = min(#nonzero, L) largest under the total order (metric, index), listed ascending; lists with at most L candidates keep
+// all of them in index order (the same rounds keyed by the index alone).  Candidate i of the lane has index ibase + i * istep.
+// On return lane t < nout holds its new path: the metric and the candidate index.
+// The metrics are non-negative float64, so their bit patterns order like unsigned integers: a lane first sorts its own
+// candidates (descending (key, index); a sorting network in registers), then every round is one arg-max of the lanes' heads
+// over the frame's lane group -- three redux.sync (high word, low word among the equals, index among the equals) -- and the
+// winning lane pops its head.
+struct Cand {
+    uint32_t hi, lo;
+    int idx;  // -1: no candidate
+};
+__device__ __forceinline__ void cand_cx(Cand &a, Cand &b) {  // a >= b after
+    const bool sw = b.hi > a.hi || (b.hi == a.hi && (b.lo > a.lo || (b.lo == a.lo && b.idx > a.idx)));
+    const Cand x = a;
+    a.hi = sw ? b.hi : a.hi, a.lo = sw ? b.lo : a.lo, a.idx = sw ? b.idx : a.idx;
+    b.hi = sw ? x.hi : b.hi, b.lo = sw ? x.lo : b.lo, b.idx = sw ? x.idx : b.idx;
+}
+template <int M>
+__device__ __forceinline__ void select_paths(const double (&cv)[8], const int ibase, const int istep, const bool valid, const int cnt,
+                                             const int L, const int G, const int t, const uint32_t gmask, int &nout,
+                                             double &newprob, int &ci) {
     const int C = cnt * M;
     int nzl = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) nzl += (valid && i < M && cv[i] != 0.0) ? 1 : 0;
-    const int nz = group_sum(nzl, G);
+    for (int i = 0; i < M; ++i) nzl += (valid && cv[i] != 0.0) ? 1 : 0;
+    const int nz = G == 1 ? nzl : (int)__reduce_add_sync(gmask, (unsigned)nzl);
     const bool byidx = C <= L;
     const int ns = byidx ? C : (nz < L ? nz : L);
-    uint32_t taken = valid ? ~((1u << M) - 1u) : 0xffffffffu;
+    nout = ns;
     newprob = 0.0;
     ci = 0;
-#pragma unroll 1
-    for (int r = 0; r < L; ++r) {
-        double bv = -1.0;
-        int bi = -1;
+    if (byidx) {  // list growth: new path t is candidate t (the candidate indices of a frame are 0 .. C-1)
+        const int own = istep == 1 ? t / M : (cnt ? t % cnt : 0), slot = istep == 1 ? t % M : (cnt ? t / cnt : 0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {  // candidates in increasing index order: among equals the later index wins
-            if (i < M) {                // M is warp-uniform
-                const bool better = !((taken >> i) & 1u) && (byidx || cv[i] >= bv);
-                bv = better ? cv[i] : bv;
-                bi = better ? ibase + i * istep : bi;
-            }
+        for (int i = 0; i < M; ++i) {
+            const double v = __shfl_sync(gmask, cv[i], (own & (G - 1)) + (int)(__ffs((int)gmask) - 1));
+            if (t < C && slot == i) newprob = v;
         }
-        const int mine = bi;
-        for (int o = 1; o < G; o <<= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oidx = __shfl_xor_sync(0xffffffffu, bi, o);
-            const bool better = oidx >= 0 && (bi < 0 || (byidx ? oidx > bi : (ov > bv || (ov == bv && oidx > bi))));
-            bv = better ? ov : bv;
-            bi = better ? oidx : bi;
-        }
-        if (mine >= 0 && mine == bi) taken |= 1u << ((bi - ibase) / istep);
-        if (r < ns && t == ns - 1 - r) {
-            newprob = bv;
+        ci = t < C ? t : 0;
+        return;
+    }
+    Cand c[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        c[i].hi = valid ? (uint32_t)__double2hiint(cv[i]) : 0u;
+        c[i].lo = valid ? (uint32_t)__double2loint(cv[i]) : 0u;
+        c[i].idx = valid ? ibase + i * istep : -1;
+    }
+    if (M == 2) {
+        cand_cx(c[0], c[1]);
+    } else if (M == 4) {
+        cand_cx(c[0], c[1]), cand_cx(c[2], c[3]), cand_cx(c[0], c[2]), cand_cx(c[1], c[3]), cand_cx(c[1], c[2]);
+    } else {  // 19 compare-exchanges
+        cand_cx(c[0], c[1]), cand_cx(c[2], c[3]), cand_cx(c[4], c[5]), cand_cx(c[6], c[7]);
+        cand_cx(c[0], c[2]), cand_cx(c[1], c[3]), cand_cx(c[4], c[6]), cand_cx(c[5], c[7]);
+        cand_cx(c[1], c[2]), cand_cx(c[5], c[6]), cand_cx(c[0], c[4]), cand_cx(c[3], c[7]);
+        cand_cx(c[1], c[5]), cand_cx(c[2], c[6]);
+        cand_cx(c[1], c[4]), cand_cx(c[3], c[6]);
+        cand_cx(c[2], c[4]), cand_cx(c[3], c[5]);
+        cand_cx(c[3], c[4]);
+    }
+#pragma unroll 1
+    for (int r = 0; r < ns; ++r) {
+        const uint32_t mh = __reduce_max_sync(gmask, c[0].hi);
+        const bool e1 = c[0].hi == mh;
+        const uint32_t ml = __reduce_max_sync(gmask, e1 ? c[0].lo : 0u);
+        const bool e2 = e1 && c[0].lo == ml;
+        const int bi = (int)__reduce_max_sync(gmask, e2 ? (uint32_t)(c[0].idx + 1) : 0u) - 1;
+        if (t == ns - 1 - r) {
+            newprob = __hiloint2double((int)mh, (int)ml);
             ci = bi;
         }
+        const bool pop = e2 && c[0].idx == bi;
+#pragma unroll
+        for (int i = 0; i + 1 < M; ++i) {
+            c[i].hi = pop ? c[i + 1].hi : c[i].hi;
+            c[i].lo = pop ? c[i + 1].lo : c[i].lo;
+            c[i].idx = pop ? c[i + 1].idx : c[i].idx;
+        }
+        if (pop) c[M - 1].hi = 0u, c[M - 1].lo = 0u, c[M - 1].idx = -1;
     }
-    nout = ns;
 }
 
 // MB = resident warps per SM the build is register-capped for.  Twelve (168 registers) is where the eight-element steps of
@@ -287,7 +338,8 @@ __global__ void __launch_bounds__(32 * MB, 1) sclp_kernel(const SclpParams p) {
         }
         __syncwarp();
     }
-    double2 *Vg = p.vg + gw * p.vg_stride - (int64_t)vrows * 32;
+    const int64_t gws = p.alias ? wic : gw;
+    double2 *Vg = p.vg + gws * p.vg_stride - (int64_t)vrows * 32;
     uint32_t *Rg = p.rg + gw * p.rg_stride - (int64_t)2 * scl2_wsum(rgl) * 32;
     // level l of the path vectors: rows (2^l - 1) .. ; per-path layout: element e of slot s at [e][gbase + s]; shared layout
     // (one path, written before the first fork): element e at [e / G][gbase + e % G]
@@ -389,14 +441,15 @@ __global__ void __launch_bounds__(32 * MB, 1) sclp_kernel(const SclpParams p) {
                                     u[r] = ddst ? (uint32_t)(i & 1) : (pl ? (rp[(e >> 5) << 5] >> (e & 31)) & 1u : 0u);
                                 }
                             }
-                            bool sl[4];
-                            double2 y[4];
+                            double2 y[4], in[8];
 #pragma unroll
-                            for (int r = 0; r < 4; ++r) y[r] = node_fast(a[r], b[r], pl, u[r], sl[r]);
-                            if (sl[0] || sl[1] || sl[2] || sl[3]) {
+                            for (int r = 0; r < 4; ++r) in[2 * r] = a[r], in[2 * r + 1] = b[r];
+                            const uint32_t ub = u[0] | u[1] << 1 | u[2] << 2 | u[3] << 3;
+                            const uint32_t sl = pl ? node_lockstep<4, true>(in, ub, y) : node_lockstep<4, false>(in, 0u, y);
+                            if (sl) {
 #pragma unroll
                                 for (int r = 0; r < 4; ++r)
-                                    if (sl[r]) y[r] = node_fg(a[r], b[r], pl, u[r]);
+                                    if ((sl >> r) & 1u) y[r] = node_fg(a[r], b[r], pl, u[r]);
                             }
 #pragma unroll
                             for (int r = 0; r < 4; ++r) {
@@ -424,8 +477,10 @@ __global__ void __launch_bounds__(32 * MB, 1) sclp_kernel(const SclpParams p) {
                         sr.kind = SK_PATH;
                         sr.p = vbase(l) + gbase + srcslot;
                     }
-                    fg_pass(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, plus, fused, rp, half, valid, 1 + (wic & 3),
-                            32 * ((p.wpc - (wic & 3) + 3) >> 2), p.sync == 1 ? p.bar_every : 0);
+                    if (plus)
+                        fg_pass<true>(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, fused, rp, half, valid);
+                    else
+                        fg_pass<false>(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, fused, rp, half, valid);
                 }
                 __syncwarp();
                 continue;
@@ -583,7 +638,13 @@ __global__ void __launch_bounds__(32 * MB, 1) sclp_kernel(const SclpParams p) {
             } else {
                 int ci;
                 const int M = rep ? 2 : (spc ? 8 : 4);
-                select_paths(cv, M, rep ? t : t * M, rep ? cnt : 1, valid, cnt, L, G, t, nout, newprob, ci);
+                const uint32_t gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u) << gbase;
+                if (rep)
+                    select_paths<2>(cv, t, cnt, valid, cnt, L, G, t, gmask, nout, newprob, ci);
+                else if (spc)
+                    select_paths<8>(cv, t * 8, 1, valid, cnt, L, G, t, gmask, nout, newprob, ci);
+                else
+                    select_paths<4>(cv, t * 4, 1, valid, cnt, L, G, t, gmask, nout, newprob, ci);
                 if (rep)
                     sel = ci >= cnt ? 1 : 0, src = ci - sel * cnt;
                 else
@@ -1001,7 +1062,7 @@ static int envp_int(const char *name, int dflt) {
 // tuning knobs are read ONCE per process (a changed environment between the workspace query and the decode cannot break
 // the sizing contract)
 struct SclpKnobs {
-    int warps_per_sm, lsm, rgl, off, nst, timing, skew, sync, bar_every;
+    int warps_per_sm, lsm, rgl, off, nst, timing, skew, sync, alias;
     SclpKnobs() {
         warps_per_sm = envp_int("PC_SCLP_WARPS_PER_SM", SCLP_MAX_WARPS_PER_SM);
         if (warps_per_sm > SCLP_MAX_WARPS_PER_SM) warps_per_sm = SCLP_MAX_WARPS_PER_SM;
@@ -1011,7 +1072,7 @@ struct SclpKnobs {
         timing = envp_int("PC_SCLP_TIMING", 0);
         skew = envp_int("PC_SCLP_SKEW", 1);
         sync = envp_int("PC_SCLP_SYNC", 1);
-        bar_every = envp_int("PC_SCLP_BAR_EVERY", 0);  // power of two, 0 = no barrier inside the passes
+        alias = envp_int("PC_SCLP_ALIAS", 0);
         off = envp_int("PC_SCL_GENERIC", 0);  // tests: force the generic (q <= 5, frame per lane) decoder for q = 2
     }
 };
@@ -1038,7 +1099,7 @@ static SclpConfig sclp_config(const pc_plan *plan, int L, int64_t B) {
     if (rgl > n + 1) rgl = n + 1;
     c.rgl = rgl;
     const int target = kn.warps_per_sm > 0 ? kn.warps_per_sm : SCLP_MAX_WARPS_PER_SM;
-    const size_t budget = (size_t)(227 * 1024) / (size_t)target - 1024;
+    const size_t budget = (size_t)(227 * 1024 - 1024) / (size_t)target;  // 1 KB per CTA is the system's
     int lsm = n - 1 < 6 ? n - 1 : 6;
     if (lsm < 1) lsm = 1;
     int nst = kn.nst;
@@ -1049,7 +1110,7 @@ static SclpConfig sclp_config(const pc_plan *plan, int L, int64_t B) {
     c.lsm = lsm;
     c.smem = sclp_smem_bytes(n, lsm, rgl, nst);
     if (c.smem > 220 * 1024) return c;
-    int per_sm = (int)((227 * 1024) / (c.smem + 1024));
+    int per_sm = (int)((227 * 1024 - 1024) / c.smem);
     if (per_sm > target) per_sm = target;
     if (per_sm > 32) per_sm = 32;
     if (per_sm < 1) per_sm = 1;
@@ -1218,7 +1279,8 @@ static int sclp_run(const pc_plan *plan, const SclTables *T, int L, const SclpIo
         prof_mark(st);
         {
             // grid warps in CTAs of per_sm warps (one CTA per SM)
-            p.wpc = c.per_sm, p.sync = sclp_knobs().sync, p.smem_per_warp = (int)c.smem, p.bar_every = sclp_knobs().bar_every;
+            p.alias = sclp_knobs().alias;
+            p.wpc = c.per_sm, p.sync = sclp_knobs().sync, p.smem_per_warp = (int)c.smem;
             const int ctas = (int)((grid + c.per_sm - 1) / c.per_sm);
             const int rc = sclp_launch<SCLP_MAX_WARPS_PER_SM>(p, ctas, c.smem * (size_t)c.per_sm, st);
             if (rc) return rc;
