@@ -140,7 +140,8 @@ def q_encode(q, N, fmask, xprobs, info):
     return cw
 
 
-def q_decode(q, N, fmask, xprobs, xyprobs, want_marg=False, want_lvl1=False):
+def q_decode(q, N, fmask, xprobs, xyprobs, want_marg=False, want_lvl1=False, use_log=False):
+    """use_log=True: xprobs / xyprobs are natural logarithms (QaryPolarEncoderDecoder(..., use_log=True))."""
     fmask, xprobs, xyprobs = _c(fmask, np.uint8), _c(xprobs, np.float64), _c(xyprobs, np.float64)
     k = int(N - fmask.sum())
     cw = np.empty(N, dtype=np.int64)
@@ -148,8 +149,9 @@ def q_decode(q, N, fmask, xprobs, xyprobs, want_marg=False, want_lvl1=False):
     marg = np.empty((N, q), dtype=np.float64) if want_marg else None
     l1m = np.empty((N // 2, q), dtype=np.float64) if want_lvl1 and N > 1 else None
     l1p = np.empty((N // 2, q), dtype=np.float64) if want_lvl1 and N > 1 else None
-    rc = lib().po_q_decode(ctypes.c_int(q), ctypes.c_int(N), _p(fmask, _u8p), _p(xprobs, _f64p), _p(xyprobs, _f64p),
-                           _p(cw, _i64p), _p(info, _i64p), _p(marg, _f64p), _p(l1m, _f64p), _p(l1p, _f64p))
+    fn = lib().po_q_decode_log if use_log else lib().po_q_decode
+    rc = fn(ctypes.c_int(q), ctypes.c_int(N), _p(fmask, _u8p), _p(xprobs, _f64p), _p(xyprobs, _f64p),
+            _p(cw, _i64p), _p(info, _i64p), _p(marg, _f64p), _p(l1m, _f64p), _p(l1p, _f64p))
     assert rc == 0, rc
     out = [cw, info]
     if want_marg:
@@ -180,8 +182,8 @@ def polar_transform_qudits(q, x):
 
 
 # ---------------------------------------------------------------------------------------------------
-def list_decode(q, N, L, fmask, xyprobs, frozen_values, actual_info, want_list=False):
-    """QaryPolarEncoderDecoder.listDecode with actualInformation (genie selection).
+def list_decode(q, N, L, fmask, xyprobs, frozen_values, actual_info, want_list=False, use_log=False):
+    """QaryPolarEncoderDecoder.listDecode with actualInformation (genie selection); use_log=True: log-domain inputs and metrics.
     Returns (information[k], ProbResult value) and, with want_list, (list_size, list_info[L,k], list_prob[L], actual_prob)."""
     fmask, xyprobs = _c(fmask, np.uint8), _c(xyprobs, np.float64)
     fv, ai = _c(frozen_values, np.int64), _c(actual_info, np.int64)
@@ -192,9 +194,10 @@ def list_decode(q, N, L, fmask, xyprobs, frozen_values, actual_info, want_list=F
     linfo = np.full((L, k), -1, dtype=np.int64)
     lprob = np.zeros(L, dtype=np.float64)
     ap = ctypes.c_double(0)
-    rc = lib().po_list_decode(ctypes.c_int(q), ctypes.c_int(N), ctypes.c_int(L), _p(fmask, _u8p), _p(xyprobs, _f64p),
-                              _p(fv, _i64p), _p(ai, _i64p), _p(info, _i64p), ctypes.byref(pr), ctypes.byref(ls),
-                              _p(linfo, _i64p), _p(lprob, _f64p), ctypes.byref(ap))
+    fn = lib().po_list_decode_log if use_log else lib().po_list_decode
+    rc = fn(ctypes.c_int(q), ctypes.c_int(N), ctypes.c_int(L), _p(fmask, _u8p), _p(xyprobs, _f64p),
+            _p(fv, _i64p), _p(ai, _i64p), _p(info, _i64p), ctypes.byref(pr), ctypes.byref(ls),
+            _p(linfo, _i64p), _p(lprob, _f64p), ctypes.byref(ap))
     assert rc == 0, rc
     if want_list:
         return info, pr.value, ls.value, linfo, lprob, ap.value

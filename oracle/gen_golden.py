@@ -6,6 +6,7 @@ reference.
 
   python oracle/gen_golden.py sc        -> tests/golden/sc_binary.npz, tests/golden/sc_qary.npz
   python oracle/gen_golden.py list      -> tests/golden/scl.npz
+  python oracle/gen_golden.py log       -> tests/golden/qlog.npz (use_log=True)
   python oracle/gen_golden.py trellis   -> tests/golden/trellis.npz
   python oracle/gen_golden.py c1        -> tests/golden/c1_n1024.npz   (needs constructions/bsc_p0.11_n10_L100_pe.npy)
 
@@ -270,6 +271,9 @@ def main():
     elif what == "list":
         from oracle import gen_golden_list
         gen_golden_list.main(ref)
+    elif what == "log":
+        from oracle import gen_golden_log
+        gen_golden_log.main(ref)
     elif what == "trellis":
         from oracle import gen_golden_trellis
         gen_golden_trellis.main(ref)

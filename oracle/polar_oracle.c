@@ -19,6 +19,7 @@
  *   q-ary f / g / norm    VectorDistributions/QaryMemorylessVectorDistribution.py:26-118
  *   q-ary inverse         QaryPolarEncoderDecoder.py:1136-1154
  */
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -287,8 +288,85 @@ static void q_marginal(int q, const double *p, double *m) {
         for (int x = 0; x < q; ++x) m[x] = 1.0 / q;
 }
 
+/* ---- log domain (use_log=True): numpy.logaddexp and scipy.special.logsumexp (scipy >= 1.15) restated ---- */
+/* npy_logaddexp (numpy/_core/src/npymath/npy_math_internal.h.src) */
+double po_logaddexp(double x, double y) {
+    if (x == y) return x + 0.693147180559945309417232121458176568; /* NPY_LOGE2: also covers equal infinities */
+    double tmp = x - y;
+    if (tmp > 0) return x + log1p(exp(-tmp));
+    if (tmp <= 0) return y + log1p(exp(tmp));
+    return tmp; /* NaN */
+}
+/* scipy.special._logsumexp._logsumexp for a real vector, b=None: the maximal elements are taken out of the sum (m of them),
+ * out = log1p(sum_{others} exp(a - a_max) / m) + log(m) + a_max; an infinite result falls back to log(sum(exp(a))) */
+double po_logsumexp(const double *a, int n) {
+    double mx = a[0];
+    for (int i = 1; i < n; ++i)
+        if (a[i] > mx) mx = a[i];
+    double m = 0, s = 0;
+    for (int i = 0; i < n; ++i) {
+        if (a[i] == mx)
+            m += 1.0;
+        else
+            s += exp(a[i] - mx);
+    }
+    if (s != 0) s = s / m;
+    double out = log1p(s) + log(m) + mx;
+    if (!isfinite(out)) {
+        double t = 0;
+        for (int i = 0; i < n; ++i) t += exp(a[i]);
+        out = log(t);
+    }
+    return out;
+}
+
+/* QaryMemorylessVectorDistribution.py:26-43, log branch */
+static void q_minus_log(int q, const double *p, int len, double *o) {
+    int half = len / 2;
+    for (int h = 0; h < half; ++h) {
+        const double *a = p + (size_t)2 * h * q, *b = a + q;
+        double *d = o + (size_t)h * q;
+        for (int s = 0; s < q; ++s) d[s] = -INFINITY;
+        for (int x1 = 0; x1 < q; ++x1)
+            for (int x2 = 0; x2 < q; ++x2) {
+                int u1 = (x1 + x2) % q;
+                d[u1] = po_logaddexp(d[u1], a[x1] + b[x2]);
+            }
+    }
+}
+/* :45-64, log branch */
+static void q_plus_log(int q, const double *p, int len, const int64_t *u, double *o) {
+    int half = len / 2;
+    for (int h = 0; h < half; ++h) {
+        const double *a = p + (size_t)2 * h * q, *b = a + q;
+        double *d = o + (size_t)h * q;
+        for (int u2 = 0; u2 < q; ++u2) {
+            int x1 = (int)((u[h] + u2) % q);
+            int x2 = (q - u2) % q;
+            d[u2] = po_logaddexp(-INFINITY, a[x1] + b[x2]);
+        }
+    }
+}
+/* :92-118, log branch */
+static void q_normalize_log(int q, double *p, int len) {
+    for (int i = 0; i < len; ++i) {
+        double *row = p + (size_t)i * q;
+        double t = po_logsumexp(row, q);
+        if (t != -INFINITY)
+            for (int x = 0; x < q; ++x) row[x] -= t;
+    }
+}
+/* :69-90, log branch */
+static void q_marginal_log(int q, const double *p, double *m) {
+    double s = po_logsumexp(p, q);
+    if (s > -INFINITY)
+        for (int x = 0; x < q; ++x) m[x] = p[x] - s;
+    else
+        for (int x = 0; x < q; ++x) m[x] = -log((double)q);
+}
+
 typedef struct {
-    int q;
+    int q, use_log;
     const uint8_t *frozen;
     int64_t *info;
     double *marg; /* optional [N][q] */
@@ -306,7 +384,7 @@ static void q_rec(q_ctx *c, int len, const double *x, const double *xy, int64_t 
         double m[64];
         if (!c->frozen[c->uidx]) {
             if (xy) {
-                q_marginal(q, xy, m);
+                (c->use_log ? q_marginal_log : q_marginal)(q, xy, m);
                 int best = 0; /* np.argmax: first maximum */
                 for (int s = 1; s < q; ++s)
                     if (m[s] > m[best]) best = s;
@@ -318,7 +396,7 @@ static void q_rec(q_ctx *c, int len, const double *x, const double *xy, int64_t 
             enc[0] = 0; /* :351 */
         }
         if (c->marg) {
-            q_marginal(q, xy ? xy : x, m);
+            (c->use_log ? q_marginal_log : q_marginal)(q, xy ? xy : x, m);
             memcpy(c->marg + (size_t)c->uidx * q, m, sizeof(double) * q);
         }
         c->uidx += 1;
@@ -334,19 +412,22 @@ static void q_rec(q_ctx *c, int len, const double *x, const double *xy, int64_t 
         c->oom = 1;
         return;
     }
-    q_minus(q, x, len, xc);
-    q_normalize(q, xc, half);
+    void (*qm)(int, const double *, int, double *) = c->use_log ? q_minus_log : q_minus;
+    void (*qp)(int, const double *, int, const int64_t *, double *) = c->use_log ? q_plus_log : q_plus;
+    void (*qn)(int, double *, int) = c->use_log ? q_normalize_log : q_normalize;
+    qm(q, x, len, xc);
+    qn(q, xc, half);
     if (xy) {
-        q_minus(q, xy, len, xyc);
-        q_normalize(q, xyc, half);
+        qm(q, xy, len, xyc);
+        qn(q, xyc, half);
         if (len == c->top_len && c->lvl1_minus) memcpy(c->lvl1_minus, xyc, sizeof(double) * q * half);
     }
     q_rec(c, half, xc, xyc, em);
-    q_plus(q, x, len, em, xc);
-    q_normalize(q, xc, half);
+    qp(q, x, len, em, xc);
+    qn(q, xc, half);
     if (xy) {
-        q_plus(q, xy, len, em, xyc);
-        q_normalize(q, xyc, half);
+        qp(q, xy, len, em, xyc);
+        qn(q, xyc, half);
         if (len == c->top_len && c->lvl1_plus) memcpy(c->lvl1_plus, xyc, sizeof(double) * q * half);
     }
     q_rec(c, half, xc, xyc, ep);
@@ -357,12 +438,13 @@ static void q_rec(q_ctx *c, int len, const double *x, const double *xy, int64_t 
     c->ar.top = mark;
 }
 
-static int q_run(int q, int N, const uint8_t *frozen, const double *x, const double *xy, int64_t *info, int64_t *cw,
+static int q_run(int q, int use_log, int N, const uint8_t *frozen, const double *x, const double *xy, int64_t *info, int64_t *cw,
                  double *marg, double *l1m, double *l1p) {
     if (q < 2 || q > 64) return -1;
     q_ctx c;
     memset(&c, 0, sizeof c);
     c.q = q;
+    c.use_log = use_log;
     c.frozen = frozen;
     c.info = info;
     c.marg = marg;
@@ -379,13 +461,19 @@ static int q_run(int q, int N, const uint8_t *frozen, const double *x, const dou
 
 /* QaryPolarEncoderDecoder.encode, :65-88 */
 int po_q_encode(int q, int N, const uint8_t *frozen, const double *xprobs, const int64_t *info, int64_t *cw) {
-    return q_run(q, N, frozen, xprobs, NULL, (int64_t *)info, cw, NULL, NULL, NULL);
+    return q_run(q, 0, N, frozen, xprobs, NULL, (int64_t *)info, cw, NULL, NULL, NULL);
 }
 
 /* QaryPolarEncoderDecoder.decode, :90-116 (the reference returns only `information`; cw is extra) */
 int po_q_decode(int q, int N, const uint8_t *frozen, const double *xprobs, const double *xyprobs, int64_t *cw,
                 int64_t *info, double *marg, double *lvl1_minus, double *lvl1_plus) {
-    return q_run(q, N, frozen, xprobs, xyprobs, info, cw, marg, lvl1_minus, lvl1_plus);
+    return q_run(q, 0, N, frozen, xprobs, xyprobs, info, cw, marg, lvl1_minus, lvl1_plus);
+}
+
+/* the same with use_log=True: xprobs / xyprobs hold natural logarithms (-inf for 0) */
+int po_q_decode_log(int q, int N, const uint8_t *frozen, const double *xprobs, const double *xyprobs, int64_t *cw,
+                    int64_t *info, double *marg, double *lvl1_minus, double *lvl1_plus) {
+    return q_run(q, 1, N, frozen, xprobs, xyprobs, info, cw, marg, lvl1_minus, lvl1_plus);
 }
 
 int po_q_decode_batch(int B, int q, int N, int k, const uint8_t *frozen, const double *xprobs, const double *xyprobs,
