@@ -147,6 +147,17 @@ int pc_qsc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint
 int pc_qsc_decode_symbols(const pc_plan *plan, const uint8_t *d_y, int64_t B, const double *h_table, int Y, uint8_t *d_cw,
                           uint8_t *d_info, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* The LOG DOMAIN of the q-ary SC decoder: QaryPolarEncoderDecoder(q, length, frozenSet, seed, use_log=True).decode
+ * (QaryPolarEncoderDecoder.py:27,47; the `if self.use_log` branches of QaryMemorylessVectorDistribution,
+ * VectorDistributions/QaryMemorylessVectorDistribution.py:31-42 logaddexp convolution, :50-62, :74-82, :97-118 logsumexp
+ * normalisation).  d_xy_log [B][N][q] float64 natural logarithms (-inf for probability 0); h_log_table [Y][q] likewise
+ * (makeQaryMemorylessVectorDistribution(..., use_log=True), QaryMemorylessDistribution.py:757-776).  The device's exp / log1p
+ * replace the host libm's: decisions equal the reference's except at ties within ~1e-15 of the log values. */
+int pc_qsc_decode_logprobs(const pc_plan *plan, const double *d_xy_log, int64_t B, uint8_t *d_cw, uint8_t *d_info,
+                           void *d_workspace, size_t workspace_bytes, void *stream);
+int pc_qsc_decode_symbols_log(const pc_plan *plan, const uint8_t *d_y, int64_t B, const double *h_log_table, int Y,
+                              uint8_t *d_cw, uint8_t *d_info, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* ---- SC-list decoding (any q in {2,3,4,5}; binary SCL is q = 2) --------------------------------------- */
 /* QaryPolarEncoderDecoder.listDecode with actualInformation (genie selection, the form ir() uses,
  * QaryPolarEncoderDecoder.py:856).  d_xy [B][N][q] float64 (linear domain); d_frozen_values [B][N-k] uint8 (the
@@ -162,6 +173,16 @@ int pc_scl_decode_probs(const pc_plan *plan, int L, const double *d_xy, const ui
                         const uint8_t *d_actual_info, int64_t B, uint8_t *d_info, int32_t *d_prob_result,
                         int32_t *d_list_size, double *d_list_prob, double *d_actual_prob, uint8_t *d_list_info,
                         void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* listDecode in the LOG DOMAIN (use_log=True: QaryPolarEncoderDecoder.py:140, :176, :232, :436-566, :594-663, :765, :784,
+ * :813, :869): d_xy_log [B][N][q] natural logarithms; d_list_prob / d_actual_prob are log metrics (list maximum 0).  Same
+ * buffers otherwise; q in {2,3,4,5} (q = 2 runs on the generic frame-per-lane kernel here).  Metrics agree with the
+ * reference's to ~1e-14 (device exp / log1p), decisions on tie-free inputs are identical. */
+size_t pc_scl_workspace_bytes_log(const pc_plan *plan, int L, int64_t B, int want_list);
+int pc_scl_decode_logprobs(const pc_plan *plan, int L, const double *d_xy_log, const uint8_t *d_frozen_values,
+                           const uint8_t *d_actual_info, int64_t B, uint8_t *d_info, int32_t *d_prob_result,
+                           int32_t *d_list_size, double *d_list_prob, double *d_actual_prob, uint8_t *d_list_info,
+                           void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Binary (q = 2) listDecode on BIT-PACKED buffers (bit i of a row in word i/32, position i%32), 2 <= N <= 8192.
  * Channel input, exactly one of:

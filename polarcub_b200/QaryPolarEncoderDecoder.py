@@ -62,10 +62,10 @@ class QaryPolarEncoderDecoder:
             self._plan = engine.Plan(self.q, self.n, self.frozenMask, None)
         return self._plan
 
-    def _require_linear(self):
+    def _require_linear(self, what):
         if self.use_log:
-            raise PolarcubError("use_log=True (log-domain arithmetic) is not implemented in the CUDA path yet; "
-                                "there is no CPU fallback")
+            raise PolarcubError(what + " is a linear-domain entry point; with use_log=True pass log-probabilities to "
+                                "decode_batch / listDecode_batch (there is no CPU fallback)")
 
     # ---- batched --------------------------------------------------------------------------------------
     def encode_batch(self, information):
@@ -75,10 +75,11 @@ class QaryPolarEncoderDecoder:
         return cw.cpu().numpy().astype(np.int64)
 
     def decode_batch(self, xyProbs, return_codeword=False):
-        self._require_linear()
+        """xyProbs [B, N, q] float64: probabilities, or with use_log=True their natural logarithms (-inf for 0), the values
+        QaryMemorylessVectorDistribution.probs holds in that mode (QaryMemorylessDistribution.py:764-765)."""
         xy = xyProbs if torch.is_tensor(xyProbs) else torch.from_numpy(np.ascontiguousarray(xyProbs, dtype=np.float64))
         assert xy.shape[1:] == (self.length, self.q)
-        cw, info = engine.qsc_decode_probs(self.plan, xy.to(self.plan.device).contiguous())
+        cw, info = engine.qsc_decode_probs(self.plan, xy.to(self.plan.device).contiguous(), use_log=self.use_log)
         info = info.cpu().numpy().astype(np.int64)
         if return_codeword:
             return cw.cpu().numpy().astype(np.int64), info
@@ -86,10 +87,14 @@ class QaryPolarEncoderDecoder:
 
     def decode_symbols_batch(self, y, table, return_codeword=False):
         """y uint8 [B, N] channel output symbols, table [Y, q] = QaryMemorylessDistribution.probs: decode fused with
-        makeQaryMemorylessVectorDistribution(length, yvec) (QaryMemorylessDistribution.py:757-766)."""
-        self._require_linear()
+        makeQaryMemorylessVectorDistribution(length, yvec, use_log) (QaryMemorylessDistribution.py:757-766).  `table` is
+        always the LINEAR table; with use_log=True its logarithm is taken here with math.log as the reference does."""
         yt = y if torch.is_tensor(y) else torch.from_numpy(np.ascontiguousarray(y, dtype=np.uint8))
-        cw, info = engine.qsc_decode_symbols(self.plan, yt.to(self.plan.device).contiguous(), table)
+        if self.use_log:
+            import math
+            lin = np.asarray(table, dtype=np.float64)
+            table = np.array([[math.log(v) if v != 0 else -math.inf for v in row] for row in lin], dtype=np.float64)
+        cw, info = engine.qsc_decode_symbols(self.plan, yt.to(self.plan.device).contiguous(), table, use_log=self.use_log)
         info = info.cpu().numpy().astype(np.int64)
         if return_codeword:
             return cw.cpu().numpy().astype(np.int64), info
@@ -111,18 +116,19 @@ class QaryPolarEncoderDecoder:
     def listDecode_batch(self, xyProbs, frozenValues, maxListSize, actualInformation, return_list=False):
         """Batched listDecode with genie selection.  xyProbs [B,N,q] float64, frozenValues [B,N-k],
         actualInformation [B,k].  Returns (information int64 [B,k], ProbResult values int32 [B]) and, with
-        return_list, a dict with the final list (sizes, normalised metrics, genie metric, per-path information)."""
-        self._require_linear()
+        return_list, a dict with the final list (sizes, normalised metrics, genie metric, per-path information).
+        With use_log=True xyProbs and the returned metrics are natural logarithms (pc_scl_decode_logprobs)."""
         dev = self.plan.device
         xy = xyProbs if torch.is_tensor(xyProbs) else torch.from_numpy(np.ascontiguousarray(xyProbs, dtype=np.float64))
         B = xy.shape[0]
-        if self.q == 2 and 1 <= self.n <= 13:
+        if self.q == 2 and 1 <= self.n <= 13 and not self.use_log:
             return self._list_decode_packed(B, frozenValues, maxListSize, actualInformation, return_list,
                                             xy=xy.to(dev).contiguous())
         fv = torch.from_numpy(np.ascontiguousarray(frozenValues, dtype=np.uint8).reshape(B, self.length - self.k))
         ai = torch.from_numpy(np.ascontiguousarray(actualInformation, dtype=np.uint8).reshape(B, self.k))
         out = engine.scl_decode_probs(self.plan, int(maxListSize), xy.to(dev).contiguous(), fv.to(dev).contiguous(),
-                                      ai.to(dev).contiguous(), want_list=return_list, want_list_info=return_list)
+                                      ai.to(dev).contiguous(), want_list=return_list, want_list_info=return_list,
+                                      use_log=self.use_log)
         info = out["info"].cpu().numpy().astype(np.int64)
         res = out["prob_result"].cpu().numpy()
         if not return_list:
@@ -136,7 +142,7 @@ class QaryPolarEncoderDecoder:
         """Binary listDecode of channel OUTPUT SYMBOLS: y uint8 [B,N] with table [Y,2] = the rows
         makeQaryMemorylessVectorDistribution(length, y) copies into probs (QaryMemorylessDistribution.py:757-776), fused
         into the decoder (pc_scl_decode_symbols).  Same returns as listDecode_batch."""
-        self._require_linear()
+        self._require_linear("listDecode_symbols_batch")
         if self.q != 2:
             raise PolarcubError("listDecode_symbols_batch is binary (q = 2)")
         yt = y if torch.is_tensor(y) else torch.from_numpy(np.ascontiguousarray(y, dtype=np.uint8))

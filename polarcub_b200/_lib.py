@@ -36,6 +36,12 @@ SIGNATURES = {
     "pc_qsc_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "pc_qsc_decode_symbols": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pc_qsc_decode_probs": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pc_qsc_decode_logprobs": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pc_qsc_decode_symbols_log": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                          c_void_p]),
+    "pc_scl_workspace_bytes_log": (c_size_t, [c_void_p, c_int, c_int64, c_int]),
+    "pc_scl_decode_logprobs": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pc_scl_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int64, c_int]),
     "pc_scl_decode_probs": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

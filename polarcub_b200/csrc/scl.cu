@@ -22,6 +22,7 @@
 #include <map>
 #include <mutex>
 
+#include "qlog_arith.cuh"
 #include "scl_tables.cuh"
 
 namespace pc {
@@ -63,7 +64,9 @@ struct SclParams {
     uint8_t *list_info;
 };
 
-template <int Q>
+// LOG: the log domain (QaryPolarEncoderDecoder(..., use_log=True)): inputs, path vectors and metrics are natural logarithms;
+// products become sums (np.sum: numpy's pairwise order), the transforms go through logaddexp / logsumexp (qlog_arith.cuh)
+template <int Q, bool LOG = false>
 __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams p) {
     constexpr int LQ = Q <= 3 ? SCL_LMAX : 8;  // largest list this instantiation is sized for
     const int n = p.n, N = 1 << n, L = p.L, k = p.k;
@@ -119,11 +122,11 @@ __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams
         }
 
         double prob[SCL_LMAX];
-        double actual_prob = 1.0;
+        double actual_prob = LOG ? 0.0 : 1.0;
         uint8_t omap[25][2][SCL_LMAX];
         int nl[25][2];
         int nin[25];
-        prob[0] = 1.0;
+        prob[0] = LOG ? 0.0 : 1.0;
         nin[n] = 1;
         nl[n][0] = 1;
 
@@ -132,13 +135,13 @@ __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams
             double mx = prob[0];
             for (int t = 1; t < cnt; ++t)
                 if (prob[t] > mx) mx = prob[t];
-            for (int t = 0; t < cnt; ++t) prob[t] = prob[t] / mx;
+            for (int t = 0; t < cnt; ++t) prob[t] = LOG ? prob[t] - mx : prob[t] / mx;
             return mx;
         };
         // keep the min(#nonzero, L) largest candidates, ascending (metric, index)
         auto prune = [&](const double *m, int C, int *keep) -> int {
             int nz = 0;
-            for (int c = 0; c < C; ++c) nz += (m[c] != 0.0);
+            for (int c = 0; c < C; ++c) nz += LOG ? (m[c] != -INFINITY) : (m[c] != 0.0);  // np.isneginf / np.count_nonzero
             const int ns = nz < L ? nz : L;
             int cnt = 0;
             for (int c = 0; c < C; ++c) {
@@ -175,31 +178,35 @@ __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams
                             a[x] = act ? ldVA(l, h, x) : ldV(l, h, x, src);
                             b[x] = act ? ldVA(l, h + half, x) : ldV(l, h + half, x, src);
                         }
-                        if (!plus) {  // QaryMemorylessVectorDistribution.py:36-42
+                        const int u1 = !plus ? 0 : (act ? RAb[ridx(l - 1, 0, h)] : Rb[ridx(l - 1, 0, h) * L + t]);
+                        if (LOG) {
+                            q_node_log<Q>(a, b, plus, u1, d);
+                        } else {
+                            if (!plus) {  // QaryMemorylessVectorDistribution.py:36-42
 #pragma unroll
-                            for (int x = 0; x < Q; ++x) d[x] = 0.0;
+                                for (int x = 0; x < Q; ++x) d[x] = 0.0;
 #pragma unroll
-                            for (int x1 = 0; x1 < Q; ++x1)
+                                for (int x1 = 0; x1 < Q; ++x1)
 #pragma unroll
-                                for (int x2 = 0; x2 < Q; ++x2)
-                                    d[(x1 + x2) % Q] = __dadd_rn(d[(x1 + x2) % Q], __dmul_rn(a[x1], b[x2]));
-                        } else {  // :56-62
-                            const int u1 = act ? RAb[ridx(l - 1, 0, h)] : Rb[ridx(l - 1, 0, h) * L + t];
+                                    for (int x2 = 0; x2 < Q; ++x2)
+                                        d[(x1 + x2) % Q] = __dadd_rn(d[(x1 + x2) % Q], __dmul_rn(a[x1], b[x2]));
+                            } else {  // :56-62
 #pragma unroll
-                            for (int u2 = 0; u2 < Q; ++u2) {
-                                double av = a[0];
+                                for (int u2 = 0; u2 < Q; ++u2) {
+                                    double av = a[0];
 #pragma unroll
-                                for (int x = 1; x < Q; ++x)
-                                    if ((u1 + u2) % Q == x) av = a[x];
-                                d[u2] = __dadd_rn(0.0, __dmul_rn(av, b[(Q - u2) % Q]));
+                                    for (int x = 1; x < Q; ++x)
+                                        if ((u1 + u2) % Q == x) av = a[x];
+                                    d[u2] = __dadd_rn(0.0, __dmul_rn(av, b[(Q - u2) % Q]));
+                                }
                             }
-                        }
-                        double tsum = 0.0;
+                            double tsum = 0.0;
 #pragma unroll
-                        for (int x = 0; x < Q; ++x) tsum = __dadd_rn(tsum, d[x]);
-                        if (tsum != 0.0) {
+                            for (int x = 0; x < Q; ++x) tsum = __dadd_rn(tsum, d[x]);
+                            if (tsum != 0.0) {
 #pragma unroll
-                            for (int x = 0; x < Q; ++x) d[x] = d[x] / tsum;
+                                for (int x = 0; x < Q; ++x) d[x] = d[x] / tsum;
+                            }
                         }
 #pragma unroll
                         for (int x = 0; x < Q; ++x) {
@@ -240,16 +247,24 @@ __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams
             const int cnt = nin[l];
             const int i0 = op.i;
             // the genie path's node codeword (natural order) is A[i0 .. i0+size)
-            double aprod = 1.0;
-            for (int j = 0; j < size; ++j) {  // reference order j, natural position rev(j)
+            auto aval = [&](int j) -> double {  // reference order j, natural position rev(j)
                 const int pos = bitrev_n((uint32_t)j, l);
                 const int sym = A(i0 + pos);
                 double v = ldVA(l, pos, 0);
 #pragma unroll
                 for (int x = 1; x < Q; ++x)
                     if (sym == x) v = ldVA(l, pos, x);
-                aprod = j == 0 ? v : __dmul_rn(aprod, v);
-                RAb[ridx(l, op.c, pos)] = (uint8_t)sym;
+                return v;
+            };
+            double aprod = 1.0;
+            if (LOG) aprod = np_sum_pow2(aval, size);
+            for (int j = 0; j < size; ++j) {
+                const int pos = bitrev_n((uint32_t)j, l);
+                if (!LOG) {
+                    const double v = aval(j);
+                    aprod = j == 0 ? v : __dmul_rn(aprod, v);
+                }
+                RAb[ridx(l, op.c, pos)] = (uint8_t)A(i0 + pos);
             }
             auto ldsym = [&](int pos, int slot, int sym) -> double {
                 double v = ldV(l, pos, 0, slot);
@@ -262,14 +277,17 @@ __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams
             if (op.kind == OP_RATE0) {  // :495-518
                 for (int t = 0; t < cnt; ++t) {
                     double pr = 1.0;
+                    if (LOG) pr = np_sum_pow2([&](int j) { const int pos = bitrev_n((uint32_t)j, l); return ldsym(pos, t, F(i0 + pos)); }, size);
                     for (int j = 0; j < size; ++j) {
                         const int pos = bitrev_n((uint32_t)j, l);
                         const int sym = F(i0 + pos);
-                        const double v = ldsym(pos, t, sym);
-                        pr = j == 0 ? v : __dmul_rn(pr, v);
+                        if (!LOG) {
+                            const double v = ldsym(pos, t, sym);
+                            pr = j == 0 ? v : __dmul_rn(pr, v);
+                        }
                         Rb[ridx(l, op.c, pos) * L + t] = (uint8_t)sym;
                     }
-                    prob[t] = __dmul_rn(prob[t], pr);
+                    prob[t] = LOG ? prob[t] + pr : __dmul_rn(prob[t], pr);
                     omap[l][op.c][t] = (uint8_t)t;
                 }
             } else if (op.kind == OP_REP) {  // :521-578
@@ -278,14 +296,20 @@ __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams
                 const uint8_t *coef = p.rep_coef + op.coef_off;
                 for (int t = 0; t < cnt; ++t)
                     for (int s = 0; s < Q; ++s) {
-                        double pr = 1.0;
-                        for (int j = 0; j < size; ++j) {
+                        auto rval = [&](int j) -> double {
                             const int pos = bitrev_n((uint32_t)j, l);
-                            const int sym = (F(i0 + pos) + s * coef[pos]) % Q;
-                            const double v = ldsym(pos, t, sym);
-                            pr = j == 0 ? v : __dmul_rn(pr, v);
+                            return ldsym(pos, t, (F(i0 + pos) + s * coef[pos]) % Q);
+                        };
+                        double pr = 1.0;
+                        if (LOG) {
+                            pr = np_sum_pow2(rval, size);
+                        } else {
+                            for (int j = 0; j < size; ++j) {
+                                const double v = rval(j);
+                                pr = j == 0 ? v : __dmul_rn(pr, v);
+                            }
                         }
-                        cand[s * cnt + t] = __dmul_rn(prob[t], pr);
+                        cand[s * cnt + t] = LOG ? prob[t] + pr : __dmul_rn(prob[t], pr);
                     }
                 const int C = cnt * Q;
                 if (C > L) {
@@ -312,12 +336,13 @@ __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams
                 uint8_t delta[SCL_LMAX];
                 for (int t = 0; t < cnt; ++t) {
                     // pickLeastReliableIndices: the npick largest (score, j), ascending
-                    double sc[4] = {-1.0, -1.0, -1.0, -1.0};
+                    const double lowest = LOG ? -INFINITY : -1.0;
+                    double sc[4] = {lowest, lowest, lowest, lowest};
                     int sj[4] = {0, 0, 0, 0};
-                    double prodmax = 1.0;
+                    double prodmax = LOG ? 0.0 : 1.0;  // log: builtin sum() starts from 0
                     for (int j = 0; j < size; ++j) {
                         const int pos = bitrev_n((uint32_t)j, l);
-                        double m1 = -1.0, m2 = -1.0;
+                        double m1 = lowest, m2 = lowest;
 #pragma unroll
                         for (int x = 0; x < Q; ++x) {
                             const double v = ldV(l, pos, x, t);
@@ -328,7 +353,7 @@ __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams
                                 m2 = v;
                             }
                         }
-                        const double s = m2 / m1;  // reliability, :763-768
+                        const double s = LOG ? m2 - m1 : m2 / m1;  // reliability, :763-768
                         if (s >= sc[0]) {  // enters the top-npick buffer (sc[npick-1] is the largest)
                             int w = 0;
                             while (w + 1 < npick && s >= sc[w + 1]) {
@@ -343,7 +368,7 @@ __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams
                     // sc[] / sj[] hold the npick largest ascending in slots [0, npick) -- but unfilled slots start at
                     // -1 and are pushed out by the first npick positions (size >= npick always holds)
                     int sumconst = 0;
-                    bool first = true;
+                    bool first = !LOG;
                     for (int j = 0; j < size; ++j) {
                         bool forked = false;
                         for (int w = 0; w < npick; ++w) forked |= (sj[w] == j);
@@ -360,10 +385,10 @@ __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams
                             }
                         }
                         sumconst += am;
-                        prodmax = first ? mv : __dmul_rn(prodmax, mv);
+                        prodmax = first ? mv : (LOG ? prodmax + mv : __dmul_rn(prodmax, mv));
                         first = false;
                     }
-                    const double base_prob = __dmul_rn(prob[t], prodmax);
+                    const double base_prob = LOG ? prob[t] + prodmax : __dmul_rn(prob[t], prodmax);
                     for (int w = 0; w < npick; ++w) pick[t][w] = (int16_t)sj[w];
                     const int dl = ((fval - sumconst) % Q + Q) % Q;
                     delta[t] = (uint8_t)dl;
@@ -376,14 +401,15 @@ __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams
                         double pf = 1.0;
                         for (int w = 0; w < nfork; ++w) {
                             const double v = ldsym(bitrev_n((uint32_t)sj[w], l), t, dg[w]);
-                            pf = w == 0 ? v : __dmul_rn(pf, v);
+                            pf = LOG ? (w == 0 ? 0.0 + v : pf + v) : (w == 0 ? v : __dmul_rn(pf, v));
                             sf += dg[w];
                         }
                         if (spc) {
                             const int dep = ((dl - sf) % Q + Q) % Q;
-                            pf = __dmul_rn(pf, ldsym(bitrev_n((uint32_t)sj[3], l), t, dep));
+                            const double vd = ldsym(bitrev_n((uint32_t)sj[3], l), t, dep);
+                            pf = LOG ? pf + vd : __dmul_rn(pf, vd);
                         }
-                        cand[t * fs + f] = __dmul_rn(pf, base_prob);
+                        cand[t * fs + f] = LOG ? pf + base_prob : __dmul_rn(pf, base_prob);
                     }
                 }
                 const int C = cnt * fs;
@@ -431,7 +457,7 @@ __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams
             }
             nl[l][op.c] = nout;
             const double nw = normalize(nout);
-            actual_prob = __dmul_rn(actual_prob, aprod / nw);
+            actual_prob = LOG ? actual_prob + (aprod - nw) : __dmul_rn(actual_prob, aprod / nw);
         }
 
         // ---- final selection (listDecode :172-213): the genie path is in the list iff a root codeword equals it ----
@@ -457,7 +483,7 @@ __global__ void __launch_bounds__(SCL_THREADS) scl_decode_kernel(const SclParams
         if (p.list_size) {
             p.list_size[col] = cnt;
             p.actual_prob[col] = actual_prob;
-            for (int t = 0; t < L; ++t) p.list_prob[(int64_t)t * p.Bpad + col] = t < cnt ? prob[t] : 0.0;
+            for (int t = 0; t < L; ++t) p.list_prob[(int64_t)t * p.Bpad + col] = t < cnt ? prob[t] : (LOG ? -INFINITY : 0.0);
         }
         // information of a path = gather of T(root codeword) (u = T(x) in natural order)
         const int npaths = p.list_info ? cnt : 1;
@@ -527,9 +553,12 @@ __global__ void scl_list_egress_kernel(int L, int k, int64_t frames, int64_t Bpa
 }
 
 template <int Q>
-static int scl_launch(const SclParams &p, int grid, cudaStream_t st) {
+static int scl_launch(const SclParams &p, int grid, cudaStream_t st, bool use_log) {
     prof_mark(st);
-    scl_decode_kernel<Q><<<grid, SCL_THREADS, 0, st>>>(p);
+    if (use_log)
+        scl_decode_kernel<Q, true><<<grid, SCL_THREADS, 0, st>>>(p);
+    else
+        scl_decode_kernel<Q, false><<<grid, SCL_THREADS, 0, st>>>(p);
     prof_mark(st);
     PC_LAUNCH_CHECK();
     return PC_OK;
@@ -539,13 +568,19 @@ static int scl_launch(const SclParams &p, int grid, cudaStream_t st) {
 
 extern "C" {
 
-size_t pc_scl_workspace_bytes(const pc_plan *plan, int L, int64_t B, int want_list) {
+static size_t scl_workspace_common(const pc_plan *plan, int L, int64_t B, int want_list, int use_log) {
     if (!plan || B <= 0 || L < 1 || L > pc::SCL_LMAX) return 256;
-    if (pc::sclp_supported(plan, L)) return pc::sclp_workspace_bytes(plan, L, B, want_list != 0);
+    if (!use_log && pc::sclp_supported(plan, L)) return pc::sclp_workspace_bytes(plan, L, B, want_list != 0);
     int64_t chunk = pc::round_up(B, 32);
     const int64_t cap = (int64_t)pc::num_sms() * 2 * pc::SCL_THREADS * 4;
     if (chunk > cap) chunk = cap;
     return pc::scl_layout(plan, L, chunk, want_list != 0).total;
+}
+size_t pc_scl_workspace_bytes(const pc_plan *plan, int L, int64_t B, int want_list) {
+    return scl_workspace_common(plan, L, B, want_list, 0);
+}
+size_t pc_scl_workspace_bytes_log(const pc_plan *plan, int L, int64_t B, int want_list) {
+    return scl_workspace_common(plan, L, B, want_list, 1);
 }
 
 int64_t pc_scl_wave_frames(const pc_plan *plan, int L) {
@@ -554,11 +589,31 @@ int64_t pc_scl_wave_frames(const pc_plan *plan, int L) {
     return (int64_t)pc::num_sms() * 2 * pc::SCL_THREADS;
 }
 
+static int scl_decode_common(const pc_plan *plan, int L, const double *d_xy, const uint8_t *d_frozen_values,
+                             const uint8_t *d_actual_info, int64_t B, uint8_t *d_info, int32_t *d_prob_result,
+                             int32_t *d_list_size, double *d_list_prob, double *d_actual_prob, uint8_t *d_list_info,
+                             void *d_workspace, size_t workspace_bytes, void *stream, int use_log);
+
 /* see include/polarcub_b200.h */
 int pc_scl_decode_probs(const pc_plan *plan, int L, const double *d_xy, const uint8_t *d_frozen_values,
                         const uint8_t *d_actual_info, int64_t B, uint8_t *d_info, int32_t *d_prob_result,
                         int32_t *d_list_size, double *d_list_prob, double *d_actual_prob, uint8_t *d_list_info,
                         void *d_workspace, size_t workspace_bytes, void *stream) {
+    return scl_decode_common(plan, L, d_xy, d_frozen_values, d_actual_info, B, d_info, d_prob_result, d_list_size, d_list_prob,
+                             d_actual_prob, d_list_info, d_workspace, workspace_bytes, stream, 0);
+}
+int pc_scl_decode_logprobs(const pc_plan *plan, int L, const double *d_xy_log, const uint8_t *d_frozen_values,
+                           const uint8_t *d_actual_info, int64_t B, uint8_t *d_info, int32_t *d_prob_result,
+                           int32_t *d_list_size, double *d_list_prob, double *d_actual_prob, uint8_t *d_list_info,
+                           void *d_workspace, size_t workspace_bytes, void *stream) {
+    return scl_decode_common(plan, L, d_xy_log, d_frozen_values, d_actual_info, B, d_info, d_prob_result, d_list_size,
+                             d_list_prob, d_actual_prob, d_list_info, d_workspace, workspace_bytes, stream, 1);
+}
+
+static int scl_decode_common(const pc_plan *plan, int L, const double *d_xy, const uint8_t *d_frozen_values,
+                             const uint8_t *d_actual_info, int64_t B, uint8_t *d_info, int32_t *d_prob_result,
+                             int32_t *d_list_size, double *d_list_prob, double *d_actual_prob, uint8_t *d_list_info,
+                             void *d_workspace, size_t workspace_bytes, void *stream, int use_log) {
     using namespace pc;
     PC_REQUIRE(plan != nullptr, "plan is null");
     PC_REQUIRE(plan->q == 2 || plan->q == 3 || plan->q == 4 || plan->q == 5, "SCL is built for q in {2,3,4,5}");
@@ -575,7 +630,7 @@ int pc_scl_decode_probs(const pc_plan *plan, int L, const double *d_xy, const ui
     SclTables *T = scl_tables(plan);
     if (!T) return PC_ERR_CUDA;
     cudaStream_t st = (cudaStream_t)stream;
-    if (sclp_supported(plan, L))  // q = 2: one path per lane, 32 / L frames per warp (scl_path.cu)
+    if (!use_log && sclp_supported(plan, L))  // q = 2: one path per lane, 32 / L frames per warp (scl_path.cu)
         return sclp_decode_bytes(plan, T, L, d_xy, d_frozen_values, d_actual_info, B, d_info, d_prob_result, d_list_size,
                                  d_list_prob, d_actual_prob, d_list_info, d_workspace, workspace_bytes, st);
     int64_t chunk = round_up(B, 32);
@@ -624,10 +679,10 @@ int pc_scl_decode_probs(const pc_plan *plan, int L, const double *d_xy, const ui
         const int64_t blocks = (tiles * 32 + SCL_THREADS - 1) / SCL_THREADS;
         const int grid = (int)(blocks < Y.grid ? blocks : Y.grid);
         switch (q) {
-            case 2: rc = scl_launch<2>(p, grid, st); break;
-            case 3: rc = scl_launch<3>(p, grid, st); break;
-            case 4: rc = scl_launch<4>(p, grid, st); break;
-            default: rc = scl_launch<5>(p, grid, st); break;
+            case 2: rc = scl_launch<2>(p, grid, st, use_log != 0); break;
+            case 3: rc = scl_launch<3>(p, grid, st, use_log != 0); break;
+            case 4: rc = scl_launch<4>(p, grid, st, use_log != 0); break;
+            default: rc = scl_launch<5>(p, grid, st, use_log != 0); break;
         }
         if (rc) return rc;
         if (k > 0) {

@@ -151,22 +151,24 @@ def qsc_encode(plan, info):
     return cw
 
 
-def qsc_decode_probs(plan, xy):
-    """xy float64 [B, N, q] (device) -> (cw uint8 [B, N], info uint8 [B, k])."""
+def qsc_decode_probs(plan, xy, use_log=False):
+    """xy float64 [B, N, q] (device) -> (cw uint8 [B, N], info uint8 [B, k]).  use_log: xy holds natural logarithms
+    (QaryPolarEncoderDecoder(..., use_log=True))."""
     assert xy.is_cuda and xy.dtype == torch.float64 and xy.is_contiguous() and xy.shape[1:] == (plan.N, plan.q)
     B = xy.shape[0]
     cw = torch.empty((B, plan.N), dtype=torch.uint8, device=xy.device)
     info = torch.empty((B, max(plan.k, 1)), dtype=torch.uint8, device=xy.device)
     need = _lib.lib().pc_qsc_workspace_bytes(plan._h, B)
     ws = plan.workspace(need)
-    _lib.check(_lib.lib().pc_qsc_decode_probs(plan._h, _ptr(xy), B, _ptr(cw), _ptr(info), _ptr(ws), ws.numel(),
-                                              _stream()), "pc_qsc_decode_probs")
+    fn = _lib.lib().pc_qsc_decode_logprobs if use_log else _lib.lib().pc_qsc_decode_probs
+    _lib.check(fn(plan._h, _ptr(xy), B, _ptr(cw), _ptr(info), _ptr(ws), ws.numel(), _stream()),
+               "pc_qsc_decode_logprobs" if use_log else "pc_qsc_decode_probs")
     return cw, info[:, :plan.k]
 
 
-def qsc_decode_symbols(plan, y, table, out=None):
+def qsc_decode_symbols(plan, y, table, out=None, use_log=False):
     """y uint8 [B, N] channel output symbols (device), table float64 [Y, q] = QaryMemorylessDistribution.probs (host)
-    -> (cw uint8 [B, N], info uint8 [B, k])."""
+    -> (cw uint8 [B, N], info uint8 [B, k]).  use_log: `table` holds natural logarithms (-inf for 0)."""
     assert y.is_cuda and y.dtype == torch.uint8 and y.is_contiguous() and y.shape[1] == plan.N
     table = np.ascontiguousarray(table, dtype=np.float64)
     assert table.ndim == 2 and table.shape[1] == plan.q and 1 <= table.shape[0] <= 16
@@ -174,17 +176,19 @@ def qsc_decode_symbols(plan, y, table, out=None):
     cw, info = out if out is not None else (torch.empty((B, plan.N), dtype=torch.uint8, device=y.device),
                                             torch.empty((B, max(plan.k, 1)), dtype=torch.uint8, device=y.device))
     ws = plan.workspace(_lib.lib().pc_qsc_workspace_bytes(plan._h, B))
-    _lib.check(_lib.lib().pc_qsc_decode_symbols(plan._h, _ptr(y), B, table.ctypes.data_as(ctypes.c_void_p), table.shape[0],
-                                                _ptr(cw), _ptr(info), _ptr(ws), ws.numel(), _stream()), "pc_qsc_decode_symbols")
+    fn = _lib.lib().pc_qsc_decode_symbols_log if use_log else _lib.lib().pc_qsc_decode_symbols
+    _lib.check(fn(plan._h, _ptr(y), B, table.ctypes.data_as(ctypes.c_void_p), table.shape[0],
+                  _ptr(cw), _ptr(info), _ptr(ws), ws.numel(), _stream()), "pc_qsc_decode_symbols")
     return cw, info[:, :plan.k]
 
 
-def scl_decode_probs(plan, L, xy, frozen_values, actual_info, want_list=False, want_list_info=False):
+def scl_decode_probs(plan, L, xy, frozen_values, actual_info, want_list=False, want_list_info=False, use_log=False):
     """SC-list decoding (QaryPolarEncoderDecoder.listDecode with genie selection) of a batch.
 
     xy float64 [B, N, q]; frozen_values uint8 [B, N-k]; actual_info uint8 [B, k] (all on the device).
     Returns dict(info uint8 [B,k], prob_result int32 [B]) plus, with want_list, list_size int32 [B],
-    list_prob float64 [B,L], actual_prob float64 [B] and (want_list_info) list_info uint8 [B,L,k]."""
+    list_prob float64 [B,L], actual_prob float64 [B] and (want_list_info) list_info uint8 [B,L,k].
+    use_log: xy, list_prob and actual_prob are natural logarithms (QaryPolarEncoderDecoder(..., use_log=True))."""
     assert xy.is_cuda and xy.dtype == torch.float64 and xy.is_contiguous() and xy.shape[1:] == (plan.N, plan.q)
     B = xy.shape[0]
     dev = xy.device
@@ -201,11 +205,13 @@ def scl_decode_probs(plan, L, xy, frozen_values, actual_info, want_list=False, w
         ap = torch.empty((B,), dtype=torch.float64, device=dev)
         if want_list_info:
             li = torch.empty((B, L, max(plan.k, 1)), dtype=torch.uint8, device=dev)
-    need = _lib.lib().pc_scl_workspace_bytes(plan._h, int(L), B, 1 if want_list else 0)
+    wsf = _lib.lib().pc_scl_workspace_bytes_log if use_log else _lib.lib().pc_scl_workspace_bytes
+    need = wsf(plan._h, int(L), B, 1 if want_list else 0)
     ws = plan.workspace(need)
-    _lib.check(_lib.lib().pc_scl_decode_probs(plan._h, int(L), _ptr(xy), _ptr(frozen_values), _ptr(actual_info), B,
-                                              _ptr(info), _ptr(res), _ptr(ls), _ptr(lp), _ptr(ap), _ptr(li), _ptr(ws),
-                                              ws.numel(), _stream()), "pc_scl_decode_probs")
+    fn = _lib.lib().pc_scl_decode_logprobs if use_log else _lib.lib().pc_scl_decode_probs
+    _lib.check(fn(plan._h, int(L), _ptr(xy), _ptr(frozen_values), _ptr(actual_info), B,
+                  _ptr(info), _ptr(res), _ptr(ls), _ptr(lp), _ptr(ap), _ptr(li), _ptr(ws),
+                  ws.numel(), _stream()), "pc_scl_decode_logprobs" if use_log else "pc_scl_decode_probs")
     out = {"info": info[:, :plan.k], "prob_result": res}
     if want_list:
         out.update(list_size=ls, list_prob=lp, actual_prob=ap)

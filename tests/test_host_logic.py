@@ -37,9 +37,11 @@ def test_qary_constructor_conventions():
     assert list(ed.frozenSet) == [0, 1, 2, 4] and list(ed.infoSet) == [3, 5, 6, 7]
     np.testing.assert_array_equal(ed.frozenMask, [1, 1, 1, 0, 1, 0, 0, 0])
     from polarcub_b200._lib import PolarcubError
-    lg = pcb.QaryPolarEncoderDecoder(3, 8, {0}, 1, use_log=True)
-    with pytest.raises(PolarcubError, match="use_log"):  # log-domain arithmetic is not offered: loud, not silent
-        lg.decode_batch(np.full((1, 8, 3), 1.0 / 3))
+    lg = pcb.QaryPolarEncoderDecoder(2, 8, {0}, 1, use_log=True)
+    assert lg.use_log
+    with pytest.raises(PolarcubError, match="use_log"):  # the symbol-input list decoder is linear-domain only: loud, not silent
+        lg.listDecode_symbols_batch(np.zeros((1, 8), dtype=np.uint8), np.full((2, 2), 0.5), np.zeros((1, 1)), 2,
+                                    np.zeros((1, 7)))
 
 
 def test_guard_bands_match_reference_goldens():
