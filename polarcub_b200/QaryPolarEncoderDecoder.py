@@ -237,3 +237,74 @@ def polarTransformOfQudits(q, xvec):
     first = (x[0::2] + x[1::2]) % q
     second = (q - x[1::2]) % q
     return np.concatenate((polarTransformOfQudits(q, first), polarTransformOfQudits(q, second)))
+
+
+def hamming(x, y):  # QaryPolarEncoderDecoder.py:932-933
+    return sum(x != y)
+
+
+def irSimulation(q, length, simulateChannel, make_xyVectorDistribution, numberOfTrials, frozenSet, maxListSize=1, checkSize=0,
+                 commonRandomnessSeed=1, randomInformationSeed=1, use_log=False, verbosity=0, ir_version=1):
+    """QaryPolarEncoderDecoder.irSimulation (QaryPolarEncoderDecoder.py:887-930), same arguments and returns
+    (frame_error_prob, symbol_error_prob, rate, probResultList), with the `numberOfTrials` calls of ir() -> listDecode run as
+    ONE batch on the GPU.  The three random streams are consumed trial by trial in the reference's order (information:
+    random.Random(randomInformationSeed).choices; channel: whatever simulateChannel draws from; check matrix:
+    np.random.choice), and make_xyVectorDistribution is called once per trial in order, so seeded runs reproduce the
+    reference's inputs exactly.  ir_version=2 calls ir2, which passes listDecode's arguments in the wrong order in the
+    reference (:864) and cannot run there either."""
+    import math
+    if ir_version != 1:
+        raise PolarcubError("ir_version=2 (ir2) does not run in the reference either (QaryPolarEncoderDecoder.py:864)")
+    encDec = QaryPolarEncoderDecoder(q, length, frozenSet, commonRandomnessSeed, use_log=use_log)
+    informationRNG = random.Random(randomInformationSeed)
+    k = encDec.k
+    xy = np.empty((numberOfTrials, length, q), dtype=np.float64)
+    fvs = np.empty((numberOfTrials, length - k), dtype=np.int64)
+    a_keys = np.empty((numberOfTrials, k), dtype=np.int64)
+    checks = []
+    for t in range(numberOfTrials):
+        a = informationRNG.choices(range(0, q), k=encDec.length)
+        b = simulateChannel(a)
+        w, u = encDec.calculate_syndrome_and_complement(a)  # ir(), :841-858
+        a_keys[t] = encDec.get_message_info_bits(u)
+        fvs[t] = (encDec.get_message_frozen_bits(w) * (q - 1)) % q
+        check_matrix = np.random.choice(range(q), (k, checkSize))
+        checks.append((check_matrix, np.matmul(a_keys[t], check_matrix) % q))
+        xy[t] = _probs_of(make_xyVectorDistribution(b), length, q)
+    # with actualInformation the selection never looks at the check matrix (:172-213); it is drawn to keep numpy's stream in step
+    b_keys, res = encDec.listDecode_batch(xy, fvs, maxListSize, a_keys) if numberOfTrials else (a_keys, np.zeros(0, dtype=np.int32))
+    probResultList = [ProbResult(int(r)) for r in res]
+    bad = (a_keys != b_keys)
+    badKeys = int(bad.any(axis=1).sum())
+    badSymbols = int(bad[bad.any(axis=1)].sum())
+    assert k == length - len(frozenSet)
+    rate = (math.log2(q) * k - math.log2(maxListSize)) / length
+    frame_error_prob = badKeys / numberOfTrials
+    symbol_error_prob = badSymbols / (numberOfTrials * encDec.length)
+    if verbosity:
+        print("Rate: ", rate)
+        print("Frame error probability = ", badKeys, "/", numberOfTrials, " = ", frame_error_prob)
+        print("Symbol error probability = ", badSymbols, "/ (", numberOfTrials, " * ", encDec.length, ") = ", symbol_error_prob)
+    return frame_error_prob, symbol_error_prob, rate, probResultList
+
+
+def encodeDecodeSimulation(q, length, make_xVectorDistribution, make_codeword, simulateChannel, make_xyVectorDistribution,
+                           numberOfTrials, frozenSet, commonRandomnessSeed=1, randomInformationSeed=1, verbosity=0):
+    """QaryPolarEncoderDecoder.encodeDecodeSimulation (QaryPolarEncoderDecoder.py:935-982; SC, not SCL): all trials encoded
+    in one batch, the channel simulated trial by trial in the reference's order, all received words decoded in one batch.
+    Prints the reference's summary line; additionally returns the number of misdecoded words (the reference returns None)."""
+    xVectorDistribution = make_xVectorDistribution()
+    assert len(xVectorDistribution) == length
+    encDec = QaryPolarEncoderDecoder(q, length, frozenSet, commonRandomnessSeed)
+    informationRNG = random.Random(randomInformationSeed)
+    info = np.array([informationRNG.choices(range(0, q), k=encDec.k) for _ in range(numberOfTrials)],
+                    dtype=np.int64).reshape(numberOfTrials, encDec.k)
+    encoded = encDec.encode_batch(info) if numberOfTrials else np.zeros((0, length), dtype=np.int64)
+    xy = np.empty((numberOfTrials, length, q), dtype=np.float64)
+    for t in range(numberOfTrials):
+        receivedWord = simulateChannel(make_codeword(encoded[t]))
+        xy[t] = _probs_of(make_xyVectorDistribution(receivedWord), length, q)
+    decoded = encDec.decode_batch(xy) if numberOfTrials else info
+    misdecodedWords = int((decoded != info).any(axis=1).sum())
+    print("Error probability = ", misdecodedWords, "/", numberOfTrials, " = ", misdecodedWords / numberOfTrials)
+    return misdecodedWords

@@ -11,7 +11,8 @@ from .BinaryPolarEncoderDecoder import BinaryPolarEncoderDecoder, polarTransform
 from .simulation import encodeDecodeSimulation, genieEncodeDecodeSimulation, frozenSetFromTVAndPe, readFrozenSetFromFile  # noqa: F401
 from . import Guardbands, CollectionOfBinaryTrellises, construction  # noqa: F401
 from .construction import calcFrozenSet_degradingUpgrading, calcTVAndPe_degradingUpgrading  # noqa: F401
-from .QaryPolarEncoderDecoder import QaryPolarEncoderDecoder, polarTransformOfQudits, ProbResult  # noqa: F401
+from .QaryPolarEncoderDecoder import QaryPolarEncoderDecoder, polarTransformOfQudits, ProbResult, irSimulation  # noqa: F401
+from . import results_csv  # noqa: F401
 
 __all__ = ["BinaryPolarEncoderDecoder", "QaryPolarEncoderDecoder", "polarTransformOfBits", "polarTransformOfQudits",
            "ProbResult", "PolarcubError", "engine", "construction", "calcFrozenSet_degradingUpgrading", "calcTVAndPe_degradingUpgrading"]
