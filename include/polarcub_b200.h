@@ -206,6 +206,33 @@ int pc_scl_decode_symbols(const pc_plan *plan, int L, const uint8_t *d_y, const 
                           uint32_t *d_info_packed, int32_t *d_prob_result, void *d_workspace, size_t workspace_bytes,
                           void *stream);
 
+/* ---- channel simulation and guard-band plumbing on the device (the steps either side of the decoders) ------------------- */
+/* Discrete memoryless channel: y[f][i] = the first output symbol whose cumulated P(y | x[f][i]) reaches a uniform draw -- the
+ * inverse-CDF walk of the reference's simulators (test3.py:35-54, test2.py:29-65).  h_cond [X][Y] float64 rows P(. | x).
+ * Input symbols: d_x [B][N] uint8, or (binary) d_x_packed [B][ceil(N/32)] -- exactly one non-null.  The generator is
+ * counter-based, keyed by (seed, frame0 + f, i): the output of a frame does not depend on how the batch is split over calls or
+ * ranks.  Workspace: X * Y * 8 bytes. */
+int pc_channel_simulate_dmc(const uint8_t *d_x, const uint32_t *d_x_packed, int64_t B, int N, int X, int Y, const double *h_cond,
+                            uint64_t seed, int64_t frame0, uint8_t *d_y, void *d_workspace, size_t workspace_bytes, void *stream);
+/* BI-AWGN: y = (1 - 2 x) + sigma * N(0, 1); d_y_real [B][N] float64 and / or d_y_quantised [B][N] uint8 =
+ * clamp(floor((y + ymax) / (2 ymax / Y)), 0, Y - 1), the symbol input of pc_sc_decode_symbols / pc_scl_decode_symbols. */
+int pc_channel_simulate_biawgn(const uint8_t *d_x, const uint32_t *d_x_packed, int64_t B, int N, double sigma, uint64_t seed,
+                               int64_t frame0, int Y, double ymax, uint8_t *d_y_quantised, double *d_y_real, void *stream);
+/* Guardbands.addDeletionGuardBands (Guardbands.py:4-44) on a batch: d_encoded [B][2^n] uint8 -> d_out [B][pc_guard_band_length]
+ * (zeros between the halves of every block above level n0, `ones` ones around each sub-word).  Workspace: 4 * 2^(n-n0) bytes. */
+int pc_guard_band_length(int n, int n0, double xi, int ones);
+int pc_add_guard_bands(const uint8_t *d_encoded, int64_t B, int n, int n0, double xi, int ones, uint8_t *d_out, void *d_workspace,
+                       size_t workspace_bytes, void *stream);
+/* deletionChannelSimulation (VectorDistributions/BinaryTrellis.py:441-461): symbol i of d_in [B][len] survives iff its uniform
+ * draw is >= deletion_prob; survivors in order at d_out [B][len] (zero padded), their number in d_out_len [B]. */
+int pc_deletion_channel(const uint8_t *d_in, int64_t B, int len, double deletion_prob, uint64_t seed, int64_t frame0, uint8_t *d_out,
+                        int32_t *d_out_len, void *stream);
+/* Guardbands.removeDeletionGuardBands (Guardbands.py:47-93): d_received [B][stride] uint8 with lengths d_received_len [B] (null:
+ * every word has `stride` symbols) -> the 2^(n-n0) trimmed sub-words d_sub_bits [B][2^(n-n0)][maxlen], d_sub_len [B][2^(n-n0)]
+ * (the inputs of pc_trellis_decode); *d_overflow is set when a sub-word is longer than maxlen. */
+int pc_remove_guard_bands(const uint8_t *d_received, const int32_t *d_received_len, int64_t B, int stride, int n, int n0, int maxlen,
+                          uint8_t *d_sub_bits, int32_t *d_sub_len, int32_t *d_overflow, void *stream);
+
 /* ---- deletion channel: SC decoding over a collection of trellises ---------------------------------------- */
 /* The received word is split by the caller into T = 2^(n-n0) trimmed sub-words (Guardbands.removeDeletionGuardBands,
  * Guardbands.py:47-63): d_sub_bits [B][T][maxlen] uint8 (0/1), d_sub_len [B][T] int32 (lengths <= maxlen).  Each sub-word

@@ -12,7 +12,7 @@ from .simulation import encodeDecodeSimulation, genieEncodeDecodeSimulation, fro
 from . import Guardbands, CollectionOfBinaryTrellises, construction  # noqa: F401
 from .construction import calcFrozenSet_degradingUpgrading, calcTVAndPe_degradingUpgrading  # noqa: F401
 from .QaryPolarEncoderDecoder import QaryPolarEncoderDecoder, polarTransformOfQudits, ProbResult, irSimulation  # noqa: F401
-from . import results_csv  # noqa: F401
+from . import results_csv, channels  # noqa: F401
 
 __all__ = ["BinaryPolarEncoderDecoder", "QaryPolarEncoderDecoder", "polarTransformOfBits", "polarTransformOfQudits",
            "ProbResult", "PolarcubError", "engine", "construction", "calcFrozenSet_degradingUpgrading", "calcTVAndPe_degradingUpgrading"]

@@ -63,6 +63,14 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "pc_tv_degrade_pe": (c_int, [c_int, c_int, c_void_p, c_int, c_void_p, c_int]),
     "pc_tv_degrade_pe_qary": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int]),
+    "pc_channel_simulate_dmc": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, ctypes.c_uint64, c_int64, c_void_p,
+                                        c_void_p, c_size_t, c_void_p]),
+    "pc_channel_simulate_biawgn": (c_int, [c_void_p, c_void_p, c_int64, c_int, ctypes.c_double, ctypes.c_uint64, c_int64, c_int,
+                                           ctypes.c_double, c_void_p, c_void_p, c_void_p]),
+    "pc_guard_band_length": (c_int, [c_int, c_int, ctypes.c_double, c_int]),
+    "pc_add_guard_bands": (c_int, [c_void_p, c_int64, c_int, c_int, ctypes.c_double, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pc_deletion_channel": (c_int, [c_void_p, c_int64, c_int, ctypes.c_double, ctypes.c_uint64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "pc_remove_guard_bands": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pc_count_errors": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "pc_profile_enable": (c_int, [c_int]),
     "pc_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong)]),
