@@ -158,7 +158,7 @@ class ScBinary1024:
 
     def setup(self, dev, rank, B, Be):
         import torch
-        from polarcub_b200 import engine
+        from polarcub_b200 import channels, engine
         self.engine, self.torch = engine, torch
         self.code()
         N = self.N
@@ -174,10 +174,10 @@ class ScBinary1024:
             it = torch.randint(-2 ** 31, 2 ** 31 - 1, (c1 - c0, plan.Kw), dtype=torch.int64, device=dev, generator=gen).to(torch.int32)
             self.info_tx[c0:c1] = it
             cwp = engine.encode_bits(plan, it.contiguous())
-            bits = ((cwp.unsqueeze(-1) >> shifts) & 1).reshape(c1 - c0, N).to(torch.uint8)
-            flips = (torch.rand((c1 - c0, N), device=dev, generator=gen) < P_BSC).to(torch.uint8)
-            self.y[c0:c1] = bits ^ flips
-            del it, cwp, bits, flips
+            # BSC(p) by the product's device simulator (csrc/channel.cu: counter-based noise keyed by the global frame index)
+            self.y[c0:c1] = channels.simulate_dmc(cwp, [[1 - P_BSC, P_BSC], [P_BSC, 1 - P_BSC]], seed=1234, frame0=rank * B + c0,
+                                                  packed_bits=N)
+            del it, cwp
         self.cw_out = torch.empty((B, plan.Nw), dtype=torch.int32, device=dev)
         self.info_out = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
         self.Be = Be
@@ -271,7 +271,7 @@ class ScBinaryLarge:
 
     def setup(self, dev, rank, B, Be):
         import torch
-        from polarcub_b200 import engine
+        from polarcub_b200 import channels, engine
         self.engine, self.torch = engine, torch
         self.code()
         N = self.N
@@ -289,10 +289,10 @@ class ScBinaryLarge:
                 it[:, -1] &= (1 << (self.K & 31)) - 1
             self.info_tx[c0:c1] = it
             cwp = engine.encode_bits(plan, it.contiguous())
-            bits = ((cwp.unsqueeze(-1) >> shifts) & 1).reshape(c1 - c0, N).to(torch.uint8)
-            erased = torch.rand((c1 - c0, N), device=dev, generator=gen) < self.P_BEC
-            self.y[c0:c1] = torch.where(erased, torch.full_like(bits, 2), bits)
-            del it, cwp, bits, erased
+            e = self.P_BEC  # BEC(e): output 2 is the erasure (makeBEC, BinaryMemorylessDistribution.py:493-499)
+            self.y[c0:c1] = channels.simulate_dmc(cwp, [[1 - e, 0.0, e], [0.0, 1 - e, e]], seed=2020, frame0=rank * B + c0,
+                                                  packed_bits=N)
+            del it, cwp
         self.cw_out = torch.empty((B, plan.Nw), dtype=torch.int32, device=dev)
         self.info_out = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
         self.Be = Be
@@ -374,12 +374,6 @@ class SclBinary4096:
         self.sigma = awgn_sigma(ebn0_db=self.ebn0_db)
         self.ymax, self.qstep, self.tab = awgn_quantiser(self.sigma)
 
-    def make_y(self, torch, cw, gen):
-        return (1.0 - 2.0 * cw.to(torch.float64)) + self.sigma * torch.randn(cw.shape, dtype=torch.float64, device=cw.device, generator=gen)
-
-    def quantise(self, torch, y):
-        return torch.clamp(torch.floor((y + self.ymax) / self.qstep), 0, self.tab.shape[0] - 1).to(torch.uint8)
-
     def pairs(self, torch, y):
         s = self.sigma
         l0 = -(y - 1.0) ** 2 / (2 * s * s)
@@ -389,7 +383,7 @@ class SclBinary4096:
 
     def setup(self, dev, rank, B, Be):
         import torch
-        from polarcub_b200 import engine
+        from polarcub_b200 import channels, engine
         self.engine, self.torch = engine, torch
         self.code()
         N, K = self.N, self.K
@@ -415,12 +409,13 @@ class SclBinary4096:
             self.info_tx[c0:c1] = it
             bits = ((it.unsqueeze(-1) >> shifts) & 1).reshape(c1 - c0, K).to(torch.uint8)
             cw = engine.qsc_encode(plan, bits.contiguous())
-            y = self.make_y(torch, cw, gen)
-            self.ys[c0:c1] = self.quantise(torch, y)
+            yq, y = channels.simulate_biawgn(cw, self.sigma, seed=4321, frame0=rank * B + c0, levels=self.tab.shape[0],
+                                             ymax=self.ymax, want_real=c0 < npairs)
+            self.ys[c0:c1] = yq
             if c0 < npairs:
                 m = min(c1, npairs) - c0
                 self.xy[c0:c0 + m] = self.pairs(torch, y[:m])
-            del it, bits, cw, y
+            del it, bits, cw, y, yq
         self.info_out = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
         self.res_out = torch.empty((B,), dtype=torch.int32, device=dev)
         self.y_host = torch.empty((Be, N), dtype=torch.uint8).pin_memory()
@@ -535,7 +530,7 @@ class ScQary2048:
 
     def setup(self, dev, rank, B, Be):
         import torch
-        from polarcub_b200 import engine
+        from polarcub_b200 import channels, engine
         self.engine, self.torch = engine, torch
         self.code()
         N, K, q = self.N, self.K, self.q
@@ -551,12 +546,9 @@ class ScQary2048:
             gen.manual_seed(777 + 7919 * ((rank * B + c0) // CH))
             it = torch.randint(0, q, (c1 - c0, K), dtype=torch.uint8, device=dev, generator=gen)
             self.info_tx[c0:c1] = it
-            cw = engine.qsc_encode(plan, it.contiguous()).to(torch.int64)
-            err = torch.rand(cw.shape, device=dev, generator=gen) < P_QSC
-            off = torch.randint(1, q, cw.shape, device=dev, generator=gen)
-            y = torch.where(err, (cw + off) % q, cw)
-            self.y[c0:c1] = y.to(torch.uint8)
-            del it, cw, err, off, y
+            cw = engine.qsc_encode(plan, it.contiguous())
+            self.y[c0:c1] = channels.simulate_dmc(cw, channels.conditional_table(self.tab), seed=777, frame0=rank * B + c0)
+            del it, cw
         self.out = None
         self.Be = Be
         self.y_host = torch.empty((Be, N), dtype=torch.uint8).pin_memory()
