@@ -270,7 +270,8 @@ int pc_tv_degrade_pe_qary(int q, int n, int L, const double *h_table, int Y, dou
 int pc_count_errors(const uint32_t *d_a, const uint32_t *d_b, int64_t B, int nbits, unsigned long long *d_out3,
                     void *stream);
 /* When enabled, the library records CUDA events on the launching stream around every launch of the dominant
- * decode kernel; pc_profile_read returns their summed duration (ms) and the number of launches. */
+ * decode kernel; pc_profile_read returns the time (ms) during which at least one of them was running (the union of their
+ * intervals: their summed duration when they follow each other on one stream) and the number of launches. */
 int pc_profile_enable(int on);
 int pc_profile_read(double *total_ms, unsigned long long *launches);
 

@@ -742,13 +742,14 @@ struct SclpPrepParams {
                               // actual word and of the frozen values (Fb null when fvp is null)
 };
 
-__global__ void __launch_bounds__(32) sclp_prep_kernel(const SclpPrepParams p) {
+constexpr int SCLP_AUX_WARPS = 4;  // warps per block of the prep / final kernels: independent frames, own shared-memory slices
+__global__ void __launch_bounds__(32 * SCLP_AUX_WARPS) sclp_prep_kernel(const SclpPrepParams p) {
     PC_DYN_SMEM(smem_raw);
-    const int n = p.n, N = 1 << n, NW = p.NW, lane = threadIdx.x;
+    const int n = p.n, N = 1 << n, NW = p.NW, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     constexpr uint32_t FULL = 0xffffffffu;
-    uint32_t *T0 = (uint32_t *)smem_raw, *T1 = T0 + NW, *T2 = T1 + NW;
+    uint32_t *T0 = (uint32_t *)smem_raw + (size_t)wib * (3 * NW + 4), *T1 = T0 + NW, *T2 = T1 + NW;
 #pragma unroll 1
-    for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
+    for (int64_t f = (int64_t)blockIdx.x * SCLP_AUX_WARPS + wib; f < p.frames; f += (int64_t)gridDim.x * SCLP_AUX_WARPS) {
         const uint32_t *ai = p.ainfo + f * p.kw, *fv = p.fvp ? p.fvp + f * p.nfw : nullptr;
         __syncwarp();
         // u-domain bits in natural order: the actual word (A) and the frozen values alone (F)
@@ -837,7 +838,7 @@ __global__ void __launch_bounds__(32) sclp_prep_kernel(const SclpPrepParams p) {
 
 // ---- final: selection, ProbResult, information bits; genie replay where listDecode's actual_prob is needed ------------------
 struct SclpFinalParams {
-    int n, k, L, NW, kw, n_ops, n_leaf, sym, want_list, lsmA;
+    int n, k, L, NW, kw, n_ops, n_leaf, sym, want_list, lsmA, smem_per_warp;
     int64_t frames;
     const uint4 *ops;
     const int32_t *info_src;
@@ -864,19 +865,21 @@ static size_t sclp_final_smem_bytes(int n, int lsmA) {
     return (b + 15) & ~(size_t)15;
 }
 
-__global__ void __launch_bounds__(32) sclp_final_kernel(const SclpFinalParams p) {
-    PC_DYN_SMEM(smem_raw);
-    const int n = p.n, N = 1 << n, NW = p.NW, L = p.L, k = p.k, lane = threadIdx.x, lsmA = p.lsmA;
+__global__ void __launch_bounds__(32 * SCLP_AUX_WARPS) sclp_final_kernel(const SclpFinalParams p) {
+    PC_DYN_SMEM(smem_all);
+    const int n = p.n, N = 1 << n, NW = p.NW, L = p.L, k = p.k, lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lsmA = p.lsmA;
     constexpr uint32_t FULL = 0xffffffffu;
     const int vrows = (2 << lsmA) - 1;
+    unsigned char *smem_raw = smem_all + (size_t)wib * p.smem_per_warp;
     double2 *VAs = (double2 *)smem_raw;
     uint32_t *RA = (uint32_t *)(VAs + vrows);
     uint32_t *T0 = RA + 2 * scl2_wsum(n + 1) + 2;
-    double2 *VAg = p.va + (int64_t)blockIdx.x * p.va_stride - vrows;
+    const int64_t gwarp = (int64_t)blockIdx.x * SCLP_AUX_WARPS + wib, gwarps = (int64_t)gridDim.x * SCLP_AUX_WARPS;
+    double2 *VAg = p.va + gwarp * p.va_stride - vrows;
     auto vbase = [&](int l) -> double2 * { return (l <= lsmA ? VAs : VAg) + (((int64_t)1 << l) - 1); };
     auto rbase = [&](int l, int c) -> uint32_t * { return RA + 2 * scl2_wsum(l) + c * scl2_W(l); };
 #pragma unroll 1
-    for (int64_t f = blockIdx.x; f < p.frames; f += gridDim.x) {
+    for (int64_t f = gwarp; f < p.frames; f += gwarps) {
         const int found = p.found[f], cnt = p.lsize[f];
         const double *lp = p.lprob + f * L;
         double maxp = lp[0], minp = lp[0];
@@ -1125,9 +1128,9 @@ static SclpConfig sclp_config(const pc_plan *plan, int L, int64_t B) {
     c.rg_stride = (size_t)2 * (scl2_wsum(n + 1) - scl2_wsum(rgl)) * 32 + 32;
     c.lsmA = n - 1 < 7 ? (n - 1 < 0 ? 0 : n - 1) : 7;
     c.smem2 = sclp_final_smem_bytes(n, c.lsmA);
-    int64_t grid2 = (int64_t)num_sms() * 16;
-    if (grid2 > B) grid2 = B;
-    c.grid2 = (int)(grid2 > 0 ? grid2 : 1);
+    int64_t grid2 = (int64_t)num_sms() * 32;  // warps of the final kernel (each with its own replay scratch)
+    if (grid2 > B) grid2 = (B + SCLP_AUX_WARPS - 1) / SCLP_AUX_WARPS * SCLP_AUX_WARPS;
+    c.grid2 = (int)(grid2 > 0 ? grid2 : SCLP_AUX_WARPS);
     const int64_t arows = ((int64_t)1 << n) - 1, arows_s = ((int64_t)2 << c.lsmA) - 1;
     c.va_stride = (size_t)(arows > arows_s ? arows - arows_s : 0) + 2;
     c.ok = true;
@@ -1239,8 +1242,8 @@ static int sclp_run(const pc_plan *plan, const SclTables *T, int L, const SclpIo
         q.Ab = (uint32_t *)(base + y.off_ab);
         q.Fb = io.d_fvp ? (uint32_t *)(base + y.off_fb) : nullptr;
         int64_t g0 = (int64_t)num_sms() * 16;
-        if (g0 > F) g0 = F;
-        PC_LAUNCH(sclp_prep_kernel, (int)g0, 32, (size_t)3 * NW * 4 + 16, st, q);
+        if (g0 > (F + SCLP_AUX_WARPS - 1) / SCLP_AUX_WARPS) g0 = (F + SCLP_AUX_WARPS - 1) / SCLP_AUX_WARPS;
+        PC_LAUNCH(sclp_prep_kernel, (int)g0, 32 * SCLP_AUX_WARPS, (size_t)SCLP_AUX_WARPS * (3 * NW + 4) * 4, st, q);
         PC_LAUNCH_CHECK();
 
         SclpParams p{};
@@ -1325,9 +1328,11 @@ static int sclp_run(const pc_plan *plan, const SclTables *T, int L, const SclpIo
             r.out_aprob = io.d_aprob + f0;
             r.out_linfo = io.d_linfo ? io.d_linfo + f0 * L * kw : nullptr;
         }
-        int64_t g2 = c.grid2 < F ? c.grid2 : F;
-        PC_CUDA(cudaFuncSetAttribute(sclp_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem2));
-        PC_LAUNCH(sclp_final_kernel, (int)g2, 32, c.smem2, st, r);
+        int64_t g2 = (c.grid2 + SCLP_AUX_WARPS - 1) / SCLP_AUX_WARPS;  // c.grid2 warps (the va scratch is sized per warp)
+        if (g2 > (F + SCLP_AUX_WARPS - 1) / SCLP_AUX_WARPS) g2 = (F + SCLP_AUX_WARPS - 1) / SCLP_AUX_WARPS;
+        r.smem_per_warp = (int)c.smem2;
+        PC_CUDA(cudaFuncSetAttribute(sclp_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c.smem2 * SCLP_AUX_WARPS)));
+        PC_LAUNCH(sclp_final_kernel, (int)g2, 32 * SCLP_AUX_WARPS, c.smem2 * SCLP_AUX_WARPS, st, r);
         PC_LAUNCH_CHECK();
     }
     return PC_OK;

@@ -3,7 +3,10 @@
 // The reference counts frame errors serially on the host (BinaryPolarEncoderDecoder.py:374-387,
 // QaryPolarEncoderDecoder.py:907-909); here one kernel reduces {frames, frame errors, bit errors} per rank
 // and the host all-reduces the three int64 over NCCL.
+#include <algorithm>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -77,19 +80,29 @@ int pc_profile_enable(int on) {
     return PC_OK;
 }
 
+// total_ms: the time during which at least one of the marked launches was running -- the union of their [begin, end] intervals.
+// Launches on one stream follow each other and the union is the sum of their durations; launches that a caller spreads over
+// several streams overlap (the CTAs of the next one start on the SMs the previous one has left) and are not counted twice.
 int pc_profile_read(double *total_ms, unsigned long long *launches) {
     std::lock_guard<std::mutex> lk(pc::g_prof_mu);
-    double tot = 0;
-    unsigned long long cnt = 0;
+    std::vector<std::pair<double, double>> iv;
     for (size_t i = 0; i + 1 < pc::g_prof_used; i += 2) {
-        float ms = 0;
+        float b = 0, e = 0;
         PC_CUDA(cudaEventSynchronize(pc::g_prof_ev[i + 1]));
-        PC_CUDA(cudaEventElapsedTime(&ms, pc::g_prof_ev[i], pc::g_prof_ev[i + 1]));
-        tot += ms;
-        ++cnt;
+        PC_CUDA(cudaEventSynchronize(pc::g_prof_ev[i]));
+        PC_CUDA(cudaEventElapsedTime(&b, pc::g_prof_ev[0], pc::g_prof_ev[i]));  // may be negative: another stream started earlier
+        PC_CUDA(cudaEventElapsedTime(&e, pc::g_prof_ev[i], pc::g_prof_ev[i + 1]));
+        iv.emplace_back((double)b, (double)b + (double)e);
+    }
+    std::sort(iv.begin(), iv.end());
+    double tot = 0, hi = -1e300;
+    for (const auto &v : iv) {
+        const double lo = v.first > hi ? v.first : hi;
+        if (v.second > lo) tot += v.second - lo;
+        if (v.second > hi) hi = v.second;
     }
     if (total_ms) *total_ms = tot;
-    if (launches) *launches = cnt;
+    if (launches) *launches = (unsigned long long)iv.size();
     return PC_OK;
 }
 

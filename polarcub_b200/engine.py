@@ -220,12 +220,69 @@ def scl_decode_probs(plan, L, xy, frozen_values, actual_info, want_list=False, w
     return out
 
 
+DEVICE_PIPELINE = True  # batches larger than one resident wave: wave-sized calls rotated over the three pipeline streams
+
+
 def scl_decode_packed(plan, L, actual_info_packed, xy=None, y=None, table=None, frozen_packed=None, want_list=False,
                       want_list_info=False, out=None):
     """Binary SC-list decoding on bit-packed buffers (pc_scl_decode_packed).  Channel input: xy float64 [B, N, 2], or y uint8
     [B, N] output symbols + table float64 [Y, 2] (host).  actual_info_packed int32 [B, Kw]; frozen_packed int32 [B, ceil((N-k)/32)]
-    or None (all-zero frozen values).  Returns dict(info_packed int32 [B, Kw], prob_result int32 [B]) plus the list outputs."""
+    or None (all-zero frozen values).  Returns dict(info_packed int32 [B, Kw], prob_result int32 [B]) plus the list outputs.
+
+    A batch larger than one resident wave of the decode kernel goes out as wave-sized calls on three CUDA streams (the caller's
+    stream waits for all of them): the preparation / selection kernels of one chunk and the tail of its decode kernel overlap
+    the decode kernel of the next chunk, as in the host-buffer pipeline (host_pipeline)."""
     assert plan.q == 2
+    B = actual_info_packed.shape[0]
+    wave = scl_wave_frames(plan, L)
+    if DEVICE_PIPELINE and wave > 0 and B > wave and torch.cuda.current_stream(plan.device) not in _pipe_streams(plan.device):
+        dev = actual_info_packed.device
+        if out is not None:
+            info, res = out
+        else:
+            info = torch.empty((B, max(plan.Kw, 1)), dtype=torch.int32, device=dev)
+            res = torch.empty((B,), dtype=torch.int32, device=dev)
+        ls = lp = ap = li = None
+        if want_list or want_list_info:
+            want_list = True
+            ls = torch.empty((B,), dtype=torch.int32, device=dev)
+            lp = torch.empty((B, L), dtype=torch.float64, device=dev)
+            ap = torch.empty((B,), dtype=torch.float64, device=dev)
+            if want_list_info:
+                li = torch.empty((B, L, max(plan.Kw, 1)), dtype=torch.int32, device=dev)
+
+        def body(lo, hi, slot):
+            _scl_decode_packed_one(plan, L, actual_info_packed[lo:hi], None if xy is None else xy[lo:hi],
+                                   None if y is None else y[lo:hi], table, None if frozen_packed is None else frozen_packed[lo:hi],
+                                   want_list, info[lo:hi], res[lo:hi], None if ls is None else ls[lo:hi],
+                                   None if lp is None else lp[lo:hi], None if ap is None else ap[lo:hi],
+                                   None if li is None else li[lo:hi])
+
+        host_pipeline(plan, B, wave, body)
+        o = {"info_packed": info[:, :plan.Kw], "prob_result": res}
+        if want_list:
+            o.update(list_size=ls, list_prob=lp, actual_prob=ap)
+            if want_list_info:
+                o["list_info_packed"] = li[:, :, :plan.Kw]
+        return o
+    return _scl_decode_packed_single(plan, L, actual_info_packed, xy, y, table, frozen_packed, want_list, want_list_info, out)
+
+
+def _scl_decode_packed_one(plan, L, ai, xy, y, table, fvp, want_list, info, res, ls, lp, ap, li):
+    """One pc_scl_decode_packed call on views of the caller's buffers, on the current stream."""
+    B = ai.shape[0]
+    tptr, Y = ctypes.c_void_p(0), 0
+    if y is not None:
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        tptr, Y = table.ctypes.data_as(ctypes.c_void_p), table.shape[0]
+    need = _lib.lib().pc_scl_workspace_bytes_packed(plan._h, int(L), B, 1 if want_list else 0)
+    ws = plan.workspace(need)
+    _lib.check(_lib.lib().pc_scl_decode_packed(plan._h, int(L), _ptr(xy), _ptr(y), tptr, Y, _ptr(fvp), _ptr(ai), B, _ptr(info),
+                                               _ptr(res), _ptr(ls), _ptr(lp), _ptr(ap), _ptr(li), _ptr(ws), ws.numel(), _stream()),
+               "pc_scl_decode_packed")
+
+
+def _scl_decode_packed_single(plan, L, actual_info_packed, xy, y, table, frozen_packed, want_list, want_list_info, out):
     B = actual_info_packed.shape[0]
     dev = actual_info_packed.device
     assert actual_info_packed.is_cuda and actual_info_packed.dtype == torch.int32 and actual_info_packed.is_contiguous()
