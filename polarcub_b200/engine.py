@@ -223,6 +223,14 @@ def scl_decode_probs(plan, L, xy, frozen_values, actual_info, want_list=False, w
 DEVICE_PIPELINE = True  # batches larger than one resident wave: wave-sized calls rotated over the three pipeline streams
 
 
+def _pipelined(plan, B, wave):
+    """True when a device-resident batch should go out as wave-sized calls over the pipeline streams (not from inside one)."""
+    return bool(DEVICE_PIPELINE and wave > 0 and B > wave and
+                torch.cuda.current_stream(plan.device) not in _pipe_streams(plan.device))
+# (measured on the SC decoders too: binary SC N=1024 loses 5 % -- its ingest / egress transposes compete with the DRAM-bound
+# decode kernel -- and q-ary SC gains 1 %: only the list decoder, whose kernels have long tails, is pipelined.)
+
+
 def scl_decode_packed(plan, L, actual_info_packed, xy=None, y=None, table=None, frozen_packed=None, want_list=False,
                       want_list_info=False, out=None):
     """Binary SC-list decoding on bit-packed buffers (pc_scl_decode_packed).  Channel input: xy float64 [B, N, 2], or y uint8
@@ -235,7 +243,7 @@ def scl_decode_packed(plan, L, actual_info_packed, xy=None, y=None, table=None, 
     assert plan.q == 2
     B = actual_info_packed.shape[0]
     wave = scl_wave_frames(plan, L)
-    if DEVICE_PIPELINE and wave > 0 and B > wave and torch.cuda.current_stream(plan.device) not in _pipe_streams(plan.device):
+    if _pipelined(plan, B, wave):
         dev = actual_info_packed.device
         if out is not None:
             info, res = out
