@@ -170,6 +170,7 @@ struct TrellisParams {
     int dec_words, sub;        // decision bits per trellis
     double *probs_out;         // collapse: [frames][T][2] max-normalised pairs (input of the sub-block SC decoder)
     double *raw_out;           // optional: the unnormalised collapsed pairs (tests)
+    const int32_t *perm;       // [frames * T] record handled by each thread: (frame, trellis) pairs bucketed by sub-word length
 };
 
 // buildTrellis_uniformInput_deletion (BinaryTrellis.py:309-438)
@@ -250,13 +251,17 @@ template <bool BUILD>
 __global__ void __launch_bounds__(128) trellis_step_kernel(const TrellisParams p) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= p.frames * p.T) return;
-    const int64_t f = gid / p.T;
-    const int i = (int)(gid - f * p.T);
+    // Thread gid works on record rec = perm[gid] and keeps that trellis in slot gid of the blobs in every launch of the walk.
+    // The permutation lists the (frame, trellis) pairs by sub-word length (= number of deletions = the shape of the trellis:
+    // vertices per layer, edges per vertex), so the threads of a warp run the same loops instead of waiting for the widest one.
+    const int64_t rec = p.perm ? (int64_t)p.perm[gid] : gid;
+    const int64_t f = rec / p.T;
+    const int i = (int)(rec - f * p.T);
     const int64_t nt = p.frames * p.T;
     TRef in{p.blob_in, nt, gid, p.Lin};
     if (BUILD) {
-        const int rlen = p.sub_len[gid];
-        t_build(in, p.sub_bits + gid * p.maxlen, rlen < p.maxlen ? rlen : p.maxlen, p);
+        const int rlen = p.sub_len[rec];
+        t_build(in, p.sub_bits + rec * p.maxlen, rlen < p.maxlen ? rlen : p.maxlen, p);
         if (!p.blob_out && !p.probs_out) return;
     }
     const bool plus = p.decision != nullptr;
@@ -289,13 +294,45 @@ __global__ void __launch_bounds__(128) trellis_step_kernel(const TrellisParams p
         }
     }
     if (p.raw_out) {
-        p.raw_out[gid * 2] = m0;
-        p.raw_out[gid * 2 + 1] = m1;
+        p.raw_out[rec * 2] = m0;
+        p.raw_out[rec * 2 + 1] = m1;
     }
     double nrm = m0 > m1 ? m0 : m1;
     if (nrm == 0.0) nrm = 1.0;
-    p.probs_out[gid * 2] = m0 / nrm;
-    p.probs_out[gid * 2 + 1] = m1 / nrm;
+    p.probs_out[rec * 2] = m0 / nrm;
+    p.probs_out[rec * 2 + 1] = m1 / nrm;
+}
+
+// ---- bucketing of the records by sub-word length: a counting sort (keys 0 .. 255) -------------------------------------------
+__global__ void __launch_bounds__(256) tr_hist_kernel(const int32_t *__restrict__ len, int64_t nt, int maxlen, int32_t *hist) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += (int64_t)gridDim.x * blockDim.x) {
+        int k = len[i];
+        k = k < 0 ? 0 : (k > maxlen ? maxlen : k);
+        atomicAdd(hist + k, 1);
+    }
+}
+__global__ void __launch_bounds__(256) tr_scan_kernel(int32_t *hist) {  // exclusive prefix sums of 256 bins, in place
+    __shared__ int32_t s[256];
+    s[threadIdx.x] = hist[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t acc = 0;
+        for (int i = 0; i < 256; ++i) {
+            const int32_t v = s[i];
+            s[i] = acc;
+            acc += v;
+        }
+    }
+    __syncthreads();
+    hist[threadIdx.x] = s[threadIdx.x];
+}
+__global__ void __launch_bounds__(256) tr_scatter_kernel(const int32_t *__restrict__ len, int64_t nt, int maxlen, int32_t *cursor,
+                                                         int32_t *perm) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += (int64_t)gridDim.x * blockDim.x) {
+        int k = len[i];
+        k = k < 0 ? 0 : (k > maxlen ? maxlen : k);
+        perm[atomicAdd(cursor + k, 1)] = (int32_t)i;  // the order inside a bucket does not matter: records are independent
+    }
 }
 
 __device__ __forceinline__ uint32_t tr_spread16(uint32_t x) {
@@ -397,7 +434,7 @@ struct TrellisWs {
     std::vector<TLayout> lay;       // level k = 0 .. n0 (level n0: the length-1 children)
     std::vector<size_t> off_blob;   // per level
     std::vector<size_t> off_cw;     // per level k: two buffers (minus, plus child codewords of a level-k node) + result
-    size_t off_probs, off_raw, off_info, off_sc, sc_bytes, total;
+    size_t off_probs, off_raw, off_info, off_sc, off_perm, off_hist, sc_bytes, total;
     std::vector<size_t> off_subinfo;
 };
 
@@ -420,6 +457,8 @@ static TrellisWs trellis_ws(const pc_plan *plan, int n0, int maxlen, int64_t chu
     for (int k = 0; k <= n0; ++k) W.off_cw.push_back(take((size_t)2 * chunk * words_of(plan->N >> k) * 4));
     W.off_probs = take((size_t)chunk * Tn * 16);
     W.off_raw = take((size_t)chunk * Tn * 16);
+    W.off_perm = take((size_t)chunk * Tn * 4);
+    W.off_hist = take(256 * 4);
     W.off_info = 0;
     for (int j = 0; j < (1 << n0); ++j) W.off_subinfo.push_back(take((size_t)chunk * words_of(Tn) * 4));
     W.sc_bytes = 0;
@@ -603,6 +642,23 @@ static int trellis_common(const pc_plan *plan, int n0, double deletion_prob, int
         R.base.sub_len = d_sub_len + f0 * Tn;
         R.raw_first = d_first_collapse ? d_first_collapse + f0 * Tn * 2 : nullptr;
         R.raw_done = false;
+        {
+            // bucket this chunk's (frame, trellis) records by sub-word length (PC_TRELLIS_BUCKET=0 keeps the natural order)
+            static const bool bucket = !(getenv("PC_TRELLIS_BUCKET") && atoi(getenv("PC_TRELLIS_BUCKET")) == 0);
+            R.base.perm = nullptr;
+            if (bucket && maxlen <= 255) {
+                const int64_t nt = R.frames * Tn;
+                int32_t *hist = (int32_t *)(R.ws + W.off_hist), *perm = (int32_t *)(R.ws + W.off_perm);
+                int64_t g = (nt + 255) / 256;
+                if (g > (int64_t)num_sms() * 8) g = (int64_t)num_sms() * 8;
+                PC_CUDA(cudaMemsetAsync(hist, 0, 256 * 4, R.st));
+                tr_hist_kernel<<<(unsigned)g, 256, 0, R.st>>>(R.base.sub_len, nt, maxlen, hist);
+                tr_scan_kernel<<<1, 256, 0, R.st>>>(hist);
+                tr_scatter_kernel<<<(unsigned)g, 256, 0, R.st>>>(R.base.sub_len, nt, maxlen, hist, perm);
+                PC_LAUNCH_CHECK();
+                R.base.perm = perm;
+            }
+        }
         R.genie_u = genie ? d_genie_u + f0 * Nw : nullptr;
         R.genie_marg = genie ? d_genie_marg + f0 * 2 * plan->N : nullptr;
         uint32_t *root = (uint32_t *)(R.ws + W.off_cw[0]);
