@@ -34,6 +34,14 @@ def _probs_of(vd, length, cols):
     return p
 
 
+def _check_n0(n0):
+    """The CUDA trellis path keeps trellises of 2^n0 <= 16 symbols (n0 in [1, 4]); the reference's default n0 = n // 3
+    (main_deletion.py:100) is outside that range for n < 3 and n >= 15."""
+    if not 1 <= n0 <= 4:
+        raise PolarcubError("n0 = %d: the CUDA trellis path supports n0 in [1, 4] (trellises of 2..16 symbols); "
+                            "there is no CPU fallback" % n0)
+
+
 def is_uniform_prior(xprobs):
     """A prior whose rows are (c, c) makes every leaf marginal exactly 0.5 in the reference's arithmetic
     (f: 2c^2 on both sides, max-normalised to (1,1); (0,0) after underflow also yields [0.5,0.5],
@@ -144,8 +152,7 @@ class BinaryPolarEncoderDecoder:
         CollectionOfBinaryTrellises.buildCollection[Batch]_uniformInput_deletion -> (codewords int64 [B, N],
         information int64 [B, k]) (+ the first collapsed vector float64 [B, T, 2] with want_collapse)."""
         assert isinstance(collection, CollectionOfBinaryTrellises) and len(collection) == self.length
-        if collection.n0 == 0:  # trellises of one symbol are not a reference use (main_deletion.py:74 takes n0 >= 1)
-            raise PolarcubError("n0 = 0 is not supported by the CUDA trellis path")
+        _check_n0(collection.n0)
         dev = self.plan.device
         bits = torch.from_numpy(collection.sub_bits).to(dev)
         lens = torch.from_numpy(collection.sub_len).to(dev)
@@ -226,8 +233,7 @@ class BinaryPolarEncoderDecoder:
             pass
         elif isinstance(xy, CollectionOfBinaryTrellises):
             assert xy.frames == len(seeds) and len(xy) == self.length
-            if xy.n0 == 0:
-                raise PolarcubError("n0 = 0 is not supported by the CUDA trellis path")
+            _check_n0(xy.n0)
             if xy.n == xy.n0:
                 raise PolarcubError("genie runs over a single trellis (n == n0) are not supported by the CUDA path")
             cw, marg = engine.trellis_genie(self.plan, xy.n0, xy.deletionProb, xy.ones, torch.from_numpy(xy.sub_bits).to(dev),

@@ -568,7 +568,8 @@ static size_t trellis_sc_bytes(pc::TrellisTables *T, int64_t chunk) {
 }
 
 size_t pc_trellis_workspace_bytes(const pc_plan *plan, int n0, int maxlen, int64_t B) {
-    if (!plan || plan->q != 2 || n0 < 1 || n0 > plan->n || B <= 0 || maxlen < 1) return 256;
+    // the same limits as pc_trellis_decode, BEFORE any table is built (2^n0 sub-plans)
+    if (!plan || plan->q != 2 || n0 < 1 || n0 > 4 || n0 > plan->n || plan->n - n0 > 16 || B <= 0 || maxlen < 1 || maxlen > 250) return 256;
     int64_t chunk = B < 8192 ? B : 8192;
     pc::TrellisWs W = pc::trellis_ws(plan, n0, maxlen, chunk);
     pc::TrellisTables *T = pc::trellis_tables(plan, n0);

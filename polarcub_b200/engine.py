@@ -19,6 +19,18 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_plan_device(fn):
+    """Runs an entry point whose first argument is a Plan with the plan's device current: the plan's tables live there, and
+    `_stream()` / `Plan.workspace()` then agree on that device's current stream whatever device the caller had selected."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(plan, *a, **kw):
+        with torch.cuda.device(plan.device):
+            return fn(plan, *a, **kw)
+    return wrapper
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
 
@@ -93,6 +105,7 @@ class Plan:
         return ws
 
 
+@_on_plan_device
 def encode_bits(plan, info_packed):
     """info_packed int32 [B, Kw] (device) -> codewords int32 [B, Nw] (BinaryPolarEncoderDecoder.encode, uniform prior)."""
     B = info_packed.shape[0]
@@ -113,6 +126,7 @@ def polar_transform_bits(n, cw_packed):
     return u
 
 
+@_on_plan_device
 def sc_decode_probs(plan, xy, out=None):
     """xy float64 [B, N, 2] (device) -> (cw_packed int32 [B, Nw], info_packed int32 [B, Kw])."""
     assert xy.is_cuda and xy.dtype == torch.float64 and xy.is_contiguous() and xy.shape[1:] == (plan.N, 2)
@@ -126,6 +140,7 @@ def sc_decode_probs(plan, xy, out=None):
     return cw, info[:, :plan.Kw]
 
 
+@_on_plan_device
 def sc_decode_symbols(plan, y, table, out=None):
     """y uint8 [B, N] channel output symbols (device), table float64 [Y, 2] joint probabilities (host)."""
     assert y.is_cuda and y.dtype == torch.uint8 and y.is_contiguous() and y.shape[1] == plan.N
@@ -142,6 +157,7 @@ def sc_decode_symbols(plan, y, table, out=None):
     return cw, info[:, :plan.Kw]
 
 
+@_on_plan_device
 def qsc_encode(plan, info):
     """info uint8 [B, k] (device) -> codeword symbols uint8 [B, N] (QaryPolarEncoderDecoder.encode)."""
     assert info.is_cuda and info.dtype == torch.uint8 and info.is_contiguous() and info.shape[1] == plan.k
@@ -151,6 +167,7 @@ def qsc_encode(plan, info):
     return cw
 
 
+@_on_plan_device
 def qsc_decode_probs(plan, xy, use_log=False):
     """xy float64 [B, N, q] (device) -> (cw uint8 [B, N], info uint8 [B, k]).  use_log: xy holds natural logarithms
     (QaryPolarEncoderDecoder(..., use_log=True))."""
@@ -166,6 +183,7 @@ def qsc_decode_probs(plan, xy, use_log=False):
     return cw, info[:, :plan.k]
 
 
+@_on_plan_device
 def qsc_decode_symbols(plan, y, table, out=None, use_log=False):
     """y uint8 [B, N] channel output symbols (device), table float64 [Y, q] = QaryMemorylessDistribution.probs (host)
     -> (cw uint8 [B, N], info uint8 [B, k]).  use_log: `table` holds natural logarithms (-inf for 0)."""
@@ -182,6 +200,7 @@ def qsc_decode_symbols(plan, y, table, out=None, use_log=False):
     return cw, info[:, :plan.k]
 
 
+@_on_plan_device
 def scl_decode_probs(plan, L, xy, frozen_values, actual_info, want_list=False, want_list_info=False, use_log=False):
     """SC-list decoding (QaryPolarEncoderDecoder.listDecode with genie selection) of a batch.
 
@@ -223,6 +242,7 @@ def scl_decode_probs(plan, L, xy, frozen_values, actual_info, want_list=False, w
 DEVICE_PIPELINE = True  # batches larger than one resident wave: wave-sized calls rotated over the three pipeline streams
 
 
+@_on_plan_device
 def _pipelined(plan, B, wave):
     """True when a device-resident batch should go out as wave-sized calls over the pipeline streams (not from inside one)."""
     return bool(DEVICE_PIPELINE and wave > 0 and B > wave and
@@ -231,6 +251,7 @@ def _pipelined(plan, B, wave):
 # decode kernel -- and q-ary SC gains 1 %: only the list decoder, whose kernels have long tails, is pipelined.)
 
 
+@_on_plan_device
 def scl_decode_packed(plan, L, actual_info_packed, xy=None, y=None, table=None, frozen_packed=None, want_list=False,
                       want_list_info=False, out=None):
     """Binary SC-list decoding on bit-packed buffers (pc_scl_decode_packed).  Channel input: xy float64 [B, N, 2], or y uint8
@@ -276,6 +297,7 @@ def scl_decode_packed(plan, L, actual_info_packed, xy=None, y=None, table=None, 
     return _scl_decode_packed_single(plan, L, actual_info_packed, xy, y, table, frozen_packed, want_list, want_list_info, out)
 
 
+@_on_plan_device
 def _scl_decode_packed_one(plan, L, ai, xy, y, table, fvp, want_list, info, res, ls, lp, ap, li):
     """One pc_scl_decode_packed call on views of the caller's buffers, on the current stream."""
     B = ai.shape[0]
@@ -290,6 +312,7 @@ def _scl_decode_packed_one(plan, L, ai, xy, y, table, fvp, want_list, info, res,
                "pc_scl_decode_packed")
 
 
+@_on_plan_device
 def _scl_decode_packed_single(plan, L, actual_info_packed, xy, y, table, frozen_packed, want_list, want_list_info, out):
     B = actual_info_packed.shape[0]
     dev = actual_info_packed.device
@@ -333,6 +356,7 @@ def _scl_decode_packed_single(plan, L, actual_info_packed, xy, y, table, frozen_
     return o
 
 
+@_on_plan_device
 def scl_decode_symbols_host(plan, L, y_host, table, ai_host, info_host, res_host, fv_host=None, chunk=None):
     """pc_scl_decode_symbols over a batch in pinned host memory: y_host uint8 [B, N] channel symbols, ai_host int32 [B, Kw]
     packed actual information, fv_host int32 [B, ceil((N-k)/32)] or None -> info_host int32 [B, Kw], res_host int32 [B]."""
@@ -364,6 +388,7 @@ def scl_decode_symbols_host(plan, L, y_host, table, ai_host, info_host, res_host
     host_pipeline(plan, B, chunk, body)
 
 
+@_on_plan_device
 def scl_decode_packed_host(plan, L, xy_host, ai_host, info_host, res_host, fv_host=None, chunk=None):
     """pc_scl_decode_packed over float64 probability pairs in pinned host memory (xy_host [B, N, 2]); packed side buffers as
     scl_decode_symbols_host."""
@@ -393,6 +418,7 @@ def scl_decode_packed_host(plan, L, xy_host, ai_host, info_host, res_host, fv_ho
     host_pipeline(plan, B, chunk, body)
 
 
+@_on_plan_device
 def trellis_decode(plan, n0, deletion_prob, ones, sub_bits, sub_len, want_collapse=False):
     """Deletion-channel SC decoding (BinaryPolarEncoderDecoder.decode over a CollectionOfBinaryTrellises).
 
@@ -415,6 +441,7 @@ def trellis_decode(plan, n0, deletion_prob, ones, sub_bits, sub_len, want_collap
     return (cw, info[:, :plan.Kw], col) if want_collapse else (cw, info[:, :plan.Kw])
 
 
+@_on_plan_device
 def sc_genie_probs(plan, xy, u_packed):
     """Genie pass over memoryless inputs: xy float64 [B, N, 2], u_packed int32 [B, Nw] (the known u bits, device)
     -> (cw_packed int32 [B, Nw], marg float64 [B, N, 2])."""
@@ -440,6 +467,7 @@ def _rnd_arg(rnd, rows_per_frame, B, N):
     return r.contiguous(), N
 
 
+@_on_plan_device
 def sc_decode_probs_prior(plan, xy, x, rnd, want_marg=False):
     """SC decoding under a non-uniform a-priori distribution (two trees in lock step, pc_sc_decode_probs_prior).
     xy float64 [B, N, 2]; x float64 [B, N, 2] or [N, 2]; rnd float64 [N] or [B, N] (all device).
@@ -460,6 +488,7 @@ def sc_decode_probs_prior(plan, xy, x, rnd, want_marg=False):
     return out + (marg[0::2], marg[1::2]) if want_marg else out
 
 
+@_on_plan_device
 def sc_encode_prior(plan, x, u_packed, rnd, want_marg=False):
     """Encoding under a non-uniform a-priori distribution (pc_sc_encode_prior).  x float64 [B, N, 2]; u_packed int32
     [B, Nw] the information bits at their u positions; rnd float64 [N] or [B, N].  Returns cw_packed (+ marg [B, N, 2])."""
@@ -475,6 +504,7 @@ def sc_encode_prior(plan, x, u_packed, rnd, want_marg=False):
     return (cw, marg) if want_marg else cw
 
 
+@_on_plan_device
 def trellis_genie(plan, n0, deletion_prob, ones, sub_bits, sub_len, u_packed):
     """Genie pass over trellis collections (see trellis_decode / sc_genie_probs)."""
     assert sub_bits.is_cuda and sub_bits.dtype == torch.uint8 and sub_bits.is_contiguous() and sub_bits.dim() == 3
@@ -506,6 +536,7 @@ def _pipe_streams(device):
     return _PIPE_STREAMS[key]
 
 
+@_on_plan_device
 def host_pipeline(plan, B, chunk, body):
     """Runs body(lo, hi, slot) for consecutive chunks [lo, hi) of a batch of B frames, rotating over PIPE_SLOTS (3) CUDA
     streams / staging slots: the H2D copies of one chunk overlap the decode kernel of the previous one and the D2H copies
@@ -553,14 +584,17 @@ def default_host_chunk(B, bytes_per_frame, wave=0, target_bytes=128 << 20):
     return max(1, min(B, (c + 31) // 32 * 32))
 
 
+@_on_plan_device
 def sc_wave_frames(plan):
     return int(_lib.lib().pc_sc_wave_frames(plan._h))
 
 
+@_on_plan_device
 def scl_wave_frames(plan, L):
     return int(_lib.lib().pc_scl_wave_frames(plan._h, int(L)))
 
 
+@_on_plan_device
 def sc_decode_symbols_host(plan, y_host, table, cw_host, info_host, chunk=None):
     """pc_sc_decode_symbols over a batch in pinned host memory: y_host uint8 [B, N] -> cw_host int32 [B, Nw],
     info_host int32 [B, Kw] (pinned), copies overlapped with decoding."""
@@ -609,6 +643,7 @@ def sc_decode_symbols_host(plan, y_host, table, cw_host, info_host, chunk=None):
     host_pipeline(plan, B, chunk, body)
 
 
+@_on_plan_device
 def sc_decode_probs_host(plan, xy_host, cw_host, info_host, chunk=None):
     """pc_sc_decode_probs over a batch in pinned host memory: xy_host float64 [B, N, 2]."""
     _pinned(xy_host, "xy_host"), _pinned(cw_host, "cw_host"), _pinned(info_host, "info_host")
@@ -629,6 +664,7 @@ def sc_decode_probs_host(plan, xy_host, cw_host, info_host, chunk=None):
     host_pipeline(plan, B, chunk, body)
 
 
+@_on_plan_device
 def qsc_decode_probs_host(plan, xy_host, info_host, cw_host=None, chunk=None):
     """pc_qsc_decode_probs over a batch in pinned host memory: xy_host float64 [B, N, q] -> info_host uint8 [B, k]."""
     _pinned(xy_host, "xy_host"), _pinned(info_host, "info_host")
@@ -648,6 +684,7 @@ def qsc_decode_probs_host(plan, xy_host, info_host, cw_host=None, chunk=None):
     host_pipeline(plan, B, chunk, body)
 
 
+@_on_plan_device
 def qsc_decode_symbols_host(plan, y_host, table, info_host, cw_host=None, chunk=None):
     """pc_qsc_decode_symbols over a batch in pinned host memory: y_host uint8 [B, N] -> info_host uint8 [B, k]."""
     _pinned(y_host, "y_host"), _pinned(info_host, "info_host")
@@ -669,6 +706,7 @@ def qsc_decode_symbols_host(plan, y_host, table, info_host, cw_host=None, chunk=
     host_pipeline(plan, B, chunk, body)
 
 
+@_on_plan_device
 def scl_decode_probs_host(plan, L, xy_host, fv_host, ai_host, info_host, res_host, chunk=None):
     """pc_scl_decode_probs over a batch in pinned host memory: xy_host float64 [B, N, q], fv_host uint8 [B, N-k],
     ai_host uint8 [B, k] -> info_host uint8 [B, k], res_host int32 [B]."""
