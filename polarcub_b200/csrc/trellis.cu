@@ -467,6 +467,16 @@ static TrellisWs trellis_ws(const pc_plan *plan, int n0, int maxlen, int64_t chu
     return W;
 }
 
+// frames per batch-wide launch of the top-tree walk (read once: the workspace query and the decode must agree)
+static int64_t trellis_chunk() {
+    static const int64_t c = [] {
+        const char *s = getenv("PC_TRELLIS_CHUNK");
+        const int64_t v = s && *s ? atoll(s) : 32768;  // 8192 -> 32768: +15 % (fewer, longer launches; tails amortised)
+        return v < 32 ? (int64_t)32 : v;
+    }();
+    return c;
+}
+
 extern "C" size_t pc_sc_workspace_bytes(const pc_plan *plan, int64_t B, int input_kind);
 extern "C" int pc_sc_decode_probs(const pc_plan *plan, const double *d_xy, int64_t B, uint32_t *d_cw_packed, uint32_t *d_info_packed,
                                   void *d_workspace, size_t workspace_bytes, void *stream);
@@ -570,7 +580,7 @@ static size_t trellis_sc_bytes(pc::TrellisTables *T, int64_t chunk) {
 size_t pc_trellis_workspace_bytes(const pc_plan *plan, int n0, int maxlen, int64_t B) {
     // the same limits as pc_trellis_decode, BEFORE any table is built (2^n0 sub-plans)
     if (!plan || plan->q != 2 || n0 < 1 || n0 > 4 || n0 > plan->n || plan->n - n0 > 16 || B <= 0 || maxlen < 1 || maxlen > 250) return 256;
-    int64_t chunk = B < 8192 ? B : 8192;
+    int64_t chunk = B < pc::trellis_chunk() ? B : pc::trellis_chunk();
     pc::TrellisWs W = pc::trellis_ws(plan, n0, maxlen, chunk);
     pc::TrellisTables *T = pc::trellis_tables(plan, n0);
     return W.total + pc::align256(trellis_sc_bytes(T, chunk) + 256);
@@ -595,7 +605,7 @@ static int trellis_common(const pc_plan *plan, int n0, double deletion_prob, int
     TrellisTables *T = trellis_tables(plan, n0);
     if (!T) return PC_ERR_CUDA;
     ProfScope prof_scope((cudaStream_t)stream);  // the whole top-tree walk is the measured unit
-    int64_t chunk = B < 8192 ? B : 8192;
+    int64_t chunk = B < pc::trellis_chunk() ? B : pc::trellis_chunk();
     const size_t sc = trellis_sc_bytes(T, chunk);
     TrellisWs W = trellis_ws(plan, n0, maxlen, chunk);
     if (W.total + align256(sc + 256) > workspace_bytes) {
