@@ -181,20 +181,27 @@ class ScBinary1024:
         self.cw_out = torch.empty((B, plan.Nw), dtype=torch.int32, device=dev)
         self.info_out = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
         self.Be = Be
-        self.y_host = torch.empty((Be, N), dtype=torch.uint8).pin_memory()
-        self.y_host.copy_(self.y[:Be])
+        # host side of the e2e leg: a BSC output symbol is one bit -- the host buffer holds the symbols bit-packed
+        # (channels.pack_symbols layout), the device unpacks them in front of the decoder (pc_unpack_symbols)
+        self.host_bits = channels.symbol_bits(self.tab.shape[0])
+        self.y_host = torch.empty((Be, N * self.host_bits // 8), dtype=torch.uint8).pin_memory()
+        for c0 in range(0, Be, 1 << 16):
+            c1 = min(Be, c0 + (1 << 16))
+            self.y_host[c0:c1].copy_(channels.pack_symbols(self.y[c0:c1].contiguous(), self.host_bits))
         self.cw_host = torch.empty((Be, plan.Nw), dtype=torch.int32).pin_memory()
         self.info_host = torch.empty((Be, plan.Kw), dtype=torch.int32).pin_memory()
-        self.h2d = int(Be * N)
+        self.h2d = int(Be * N * self.host_bits // 8)
         self.d2h = int(Be * (plan.Nw + plan.Kw) * 4)
-        self.input_note = "uint8 channel symbols [B,N] (%.2f GiB per step per GPU, larger than L2: no flush needed)" % (B * N / 2 ** 30)
+        self.input_note = ("uint8 channel symbols [B,N] (%.2f GiB per step per GPU, larger than L2: no flush needed); e2e: %d-bit packed "
+                           "symbols in pinned host memory" % (B * N / 2 ** 30, self.host_bits))
 
     def step(self):
         self.engine.sc_decode_symbols(self.plan, self.y, self.tab, out=(self.cw_out, self.info_out))
 
     def e2e_step(self):
         # the public host-batch call: chunked, H2D / decode / D2H overlapped on two streams (engine.host_pipeline)
-        self.engine.sc_decode_symbols_host(self.plan, self.y_host, self.tab, self.cw_host, self.info_host)
+        self.engine.sc_decode_symbols_host(self.plan, self.y_host, self.tab, self.cw_host, self.info_host,
+                                           packed_bits=self.host_bits)
 
     def counters(self):
         return self.engine.count_errors(self.info_out, self.info_tx, self.K)
@@ -296,13 +303,18 @@ class ScBinaryLarge:
         self.cw_out = torch.empty((B, plan.Nw), dtype=torch.int32, device=dev)
         self.info_out = torch.empty((B, plan.Kw), dtype=torch.int32, device=dev)
         self.Be = Be
-        self.y_host = torch.empty((Be, N), dtype=torch.uint8).pin_memory()
-        self.y_host.copy_(self.y[:Be])
+        # e2e: a BEC output symbol (0, 1, erasure) travels as 2 bits (channels.pack_symbols layout), unpacked on the device
+        self.host_bits = channels.symbol_bits(self.tab.shape[0])
+        self.y_host = torch.empty((Be, N * self.host_bits // 8), dtype=torch.uint8).pin_memory()
+        for c0 in range(0, Be, 256):
+            c1 = min(Be, c0 + 256)
+            self.y_host[c0:c1].copy_(channels.pack_symbols(self.y[c0:c1].contiguous(), self.host_bits))
         self.cw_host = torch.empty((Be, plan.Nw), dtype=torch.int32).pin_memory()
         self.info_host = torch.empty((Be, plan.Kw), dtype=torch.int32).pin_memory()
-        self.h2d = int(Be * N)
+        self.h2d = int(Be * N * self.host_bits // 8)
         self.d2h = int(Be * (plan.Nw + plan.Kw) * 4)
-        self.input_note = "uint8 channel symbols [B,N] (%.2f GiB per step per GPU, larger than L2)" % (B * N / 2 ** 30)
+        self.input_note = ("uint8 channel symbols [B,N] (%.2f GiB per step per GPU, larger than L2); e2e: %d-bit packed symbols in "
+                           "pinned host memory" % (B * N / 2 ** 30, self.host_bits))
 
     step = ScBinary1024.step
     e2e_step = ScBinary1024.e2e_step

@@ -218,6 +218,11 @@ int pc_channel_simulate_dmc(const uint8_t *d_x, const uint32_t *d_x_packed, int6
  * clamp(floor((y + ymax) / (2 ymax / Y)), 0, Y - 1), the symbol input of pc_sc_decode_symbols / pc_scl_decode_symbols. */
 int pc_channel_simulate_biawgn(const uint8_t *d_x, const uint32_t *d_x_packed, int64_t B, int N, double sigma, uint64_t seed,
                                int64_t frame0, int Y, double ymax, uint8_t *d_y_quantised, double *d_y_real, void *stream);
+/* Channel symbols of small alphabets travel packed between host and device (a BSC output is one bit, a BEC output two):
+ * `bits` in {1, 2, 4} bits per symbol, symbol i of the stream in bits [i * bits, (i + 1) * bits) of the little-endian word stream;
+ * `count` symbols, count * bits a multiple of 32.  The decoders take the unpacked uint8 symbols (pc_sc_decode_symbols, ...). */
+int pc_unpack_symbols(const void *d_packed, int bits, int64_t count, uint8_t *d_symbols, void *stream);
+int pc_pack_symbols(const uint8_t *d_symbols, int bits, int64_t count, void *d_packed, void *stream);
 /* Guardbands.addDeletionGuardBands (Guardbands.py:4-44) on a batch: d_encoded [B][2^n] uint8 -> d_out [B][pc_guard_band_length]
  * (zeros between the halves of every block above level n0, `ones` ones around each sub-word).  Workspace: 4 * 2^(n-n0) bytes. */
 int pc_guard_band_length(int n, int n0, double xi, int ones);

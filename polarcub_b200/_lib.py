@@ -67,6 +67,8 @@ SIGNATURES = {
                                         c_void_p, c_size_t, c_void_p]),
     "pc_channel_simulate_biawgn": (c_int, [c_void_p, c_void_p, c_int64, c_int, ctypes.c_double, ctypes.c_uint64, c_int64, c_int,
                                            ctypes.c_double, c_void_p, c_void_p, c_void_p]),
+    "pc_unpack_symbols": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "pc_pack_symbols": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "pc_guard_band_length": (c_int, [c_int, c_int, ctypes.c_double, c_int]),
     "pc_add_guard_bands": (c_int, [c_void_p, c_int64, c_int, c_int, ctypes.c_double, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pc_deletion_channel": (c_int, [c_void_p, c_int64, c_int, ctypes.c_double, ctypes.c_uint64, c_int64, c_void_p, c_void_p, c_void_p]),

@@ -124,3 +124,31 @@ def remove_guard_bands(received, lengths, n, n0, maxlen):
         _lib.check(_lib.lib().pc_remove_guard_bands(_ptr(received), _ptr(lengths), B, stride, int(n), int(n0), int(maxlen), _ptr(sb),
                                                     _ptr(sl), _ptr(ov), _stream(received.device)), "pc_remove_guard_bands")
     return sb, sl, bool(int(ov.item()))
+
+
+def symbol_bits(Y):
+    """Bits per channel symbol of the packed host format for an alphabet of Y output symbols (1, 2 or 4; None above 16)."""
+    return 1 if Y <= 2 else 2 if Y <= 4 else 4 if Y <= 16 else None
+
+
+def pack_symbols(y, bits):
+    """uint8 symbols [B, N] (device) -> packed uint8 [B, N * bits / 8] (device), `bits` in {1, 2, 4} per symbol."""
+    _need_cuda(y)
+    assert y.dtype == torch.uint8 and y.is_contiguous() and (y.shape[-1] * bits) % 32 == 0
+    out = torch.empty(y.shape[:-1] + (y.shape[-1] * bits // 8,), dtype=torch.uint8, device=y.device)
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.lib().pc_pack_symbols(_ptr(y), int(bits), y.numel(), _ptr(out), _stream(y.device)), "pc_pack_symbols")
+    return out
+
+
+def unpack_symbols(packed, bits, out=None):
+    """packed uint8 [B, N * bits / 8] (device) -> uint8 symbols [B, N]."""
+    _need_cuda(packed)
+    assert packed.dtype == torch.uint8 and packed.is_contiguous()
+    n = packed.shape[-1] * 8 // bits
+    if out is None:
+        out = torch.empty(packed.shape[:-1] + (n,), dtype=torch.uint8, device=packed.device)
+    with torch.cuda.device(packed.device):
+        _lib.check(_lib.lib().pc_unpack_symbols(_ptr(packed), int(bits), packed.numel() * 8 // bits, _ptr(out), _stream(packed.device)),
+                   "pc_unpack_symbols")
+    return out

@@ -196,6 +196,46 @@ __global__ void __launch_bounds__(128) remove_guard_bands_kernel(const uint8_t *
     }
 }
 
+// ---- packed channel symbols (host <-> device traffic): `bits` in {1, 2, 4} bits per symbol, little-endian inside a byte ---------
+// one thread per packed 32-bit word: 32 / bits symbols, written as 16-byte stores
+__global__ void __launch_bounds__(256) unpack_symbols_kernel(const uint32_t *__restrict__ in, int bits, int64_t words, uint8_t *__restrict__ out) {
+    const int per = 32 / bits;
+    const uint32_t mask = (1u << bits) - 1u;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = in[w];
+        uint4 *o = (uint4 *)(out + w * per);
+        for (int g = 0; g < per / 16; ++g) {
+            uint32_t q[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t b = 0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) b |= ((v >> ((g * 16 + j * 4 + t) * bits)) & mask) << (8 * t);
+                q[j] = b;
+            }
+            o[g] = make_uint4(q[0], q[1], q[2], q[3]);
+        }
+        if (per == 8) {  // 4 bits per symbol: eight symbols = two 32-bit stores
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                lo |= ((v >> (t * 4)) & 15u) << (8 * t);
+                hi |= ((v >> ((t + 4) * 4)) & 15u) << (8 * t);
+            }
+            ((uint2 *)(out + w * 8))[0] = make_uint2(lo, hi);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) pack_symbols_kernel(const uint8_t *__restrict__ in, int bits, int64_t words, uint32_t *__restrict__ out) {
+    const int per = 32 / bits;
+    const uint32_t mask = (1u << bits) - 1u;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+        for (int t = 0; t < per; ++t) v |= ((uint32_t)in[w * per + t] & mask) << (t * bits);
+        out[w] = v;
+    }
+}
+
 static int grid_for(int64_t items, int block) {
     int64_t g = (items + block - 1) / block;
     const int64_t cap = (int64_t)num_sms() * 16;
@@ -262,6 +302,30 @@ int pc_channel_simulate_biawgn(const uint8_t *d_x, const uint32_t *d_x_packed, i
         awgn_kernel<true><<<grid, 256, 0, st>>>(nullptr, d_x_packed, N, B, frame0, seed, sigma, Y, ymax, d_y_quantised, d_y_real);
     else
         awgn_kernel<false><<<grid, 256, 0, st>>>(d_x, nullptr, N, B, frame0, seed, sigma, Y, ymax, d_y_quantised, d_y_real);
+    PC_LAUNCH_CHECK();
+    return PC_OK;
+}
+
+int pc_unpack_symbols(const void *d_packed, int bits, int64_t count, uint8_t *d_symbols, void *stream) {
+    using namespace pc;
+    PC_REQUIRE(bits == 1 || bits == 2 || bits == 4, "1, 2 or 4 bits per symbol");
+    PC_REQUIRE(count >= 0 && (count * bits) % 32 == 0, "the symbol count must fill whole 32-bit words");
+    if (count == 0) return PC_OK;
+    PC_REQUIRE(d_packed && d_symbols && ((uintptr_t)d_packed & 3) == 0 && ((uintptr_t)d_symbols & 15) == 0, "null or misaligned buffer");
+    const int64_t words = count * bits / 32;
+    unpack_symbols_kernel<<<grid_for(words, 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t *)d_packed, bits, words, d_symbols);
+    PC_LAUNCH_CHECK();
+    return PC_OK;
+}
+
+int pc_pack_symbols(const uint8_t *d_symbols, int bits, int64_t count, void *d_packed, void *stream) {
+    using namespace pc;
+    PC_REQUIRE(bits == 1 || bits == 2 || bits == 4, "1, 2 or 4 bits per symbol");
+    PC_REQUIRE(count >= 0 && (count * bits) % 32 == 0, "the symbol count must fill whole 32-bit words");
+    if (count == 0) return PC_OK;
+    PC_REQUIRE(d_packed && d_symbols && ((uintptr_t)d_packed & 3) == 0, "null or misaligned buffer");
+    const int64_t words = count * bits / 32;
+    pack_symbols_kernel<<<grid_for(words, 256), 256, 0, (cudaStream_t)stream>>>(d_symbols, bits, words, (uint32_t *)d_packed);
     PC_LAUNCH_CHECK();
     return PC_OK;
 }

@@ -595,47 +595,76 @@ def scl_wave_frames(plan, L):
 
 
 @_on_plan_device
-def sc_decode_symbols_host(plan, y_host, table, cw_host, info_host, chunk=None):
+def sc_decode_symbols_host(plan, y_host, table, cw_host, info_host, chunk=None, packed_bits=0):
     """pc_sc_decode_symbols over a batch in pinned host memory: y_host uint8 [B, N] -> cw_host int32 [B, Nw],
-    info_host int32 [B, Kw] (pinned), copies overlapped with decoding."""
+    info_host int32 [B, Kw] (pinned), copies overlapped with decoding.  packed_bits in {1, 2, 4}: y_host holds the symbols
+    packed (uint8 [B, N * packed_bits / 8], channels.pack_symbols layout) -- 8 / 4 / 2 times less PCIe traffic for the small
+    alphabets of BSC / BEC-type channels; they are unpacked on the device (pc_unpack_symbols) in front of the decoder."""
     _pinned(y_host, "y_host"), _pinned(cw_host, "cw_host"), _pinned(info_host, "info_host")
     B = y_host.shape[0]
+    ycols = y_host.shape[1]
+    assert ycols == (plan.N * packed_bits // 8 if packed_bits else plan.N)
+
+    def stage(slots, slot, rows, lo, hi):
+        """H2D copy of frames [lo, hi) into the slot's buffers; returns the uint8 [m, N] symbols on the device."""
+        m = hi - lo
+        if not packed_bits:
+            y = slots.get(slot, "y", (rows, plan.N), torch.uint8)[:m]
+            y.copy_(y_host[lo:hi], non_blocking=True)
+            return y
+        yp = slots.get(slot, "yp", (rows, ycols), torch.uint8)[:m]
+        yp.copy_(y_host[lo:hi], non_blocking=True)
+        y = slots.get(slot, "y", (rows, plan.N), torch.uint8)[:m]
+        _lib.check(_lib.lib().pc_unpack_symbols(_ptr(yp), int(packed_bits), m * plan.N, _ptr(y), _stream()), "pc_unpack_symbols")
+        return y
+
     if chunk is None and plan.n > 16 and B >= 6144:
         # large blocks (hybrid decoder): the workspace -- 5.4 MB per 2^20 frame, 1.9 MB over erasure channels -- is the
         # binding resource, so every batch is decoded on the caller's stream with its workspace; the H2D copy of the next
-        # batch (1 MiB of symbols per 2^20 frame: PCIe time comparable to the decode) runs on a side stream into the other of
-        # two staging slots
+        # batch (256 KiB - 1 MiB of symbols per 2^20 frame: PCIe time comparable to the decode) runs on a side stream into the
+        # other of two staging slots, and the D2H copies of the previous batch's results (228 KB per frame) on a third stream
         cb = B if B <= 16384 else 16384
         sl = _Slots(plan, "scsym_big")
         cur = torch.cuda.current_stream(plan.device)
-        side = _pipe_streams(plan.device)[0]
+        side, back = _pipe_streams(plan.device)[0], _pipe_streams(plan.device)[1]
         side.wait_stream(cur)
-        free = [None, None]
+        back.wait_stream(cur)
+        free = [None, None]     # the decode that read staging slot s has finished
+        drained = [None, None]  # the D2H copies out of output slot s have finished
         for j, lo in enumerate(range(0, B, cb)):
             hi = min(B, lo + cb)
-            y = sl.get(j % 2, "y", (cb, plan.N), torch.uint8)[:hi - lo]
+            s2 = j % 2
             with torch.cuda.stream(side):
-                if free[j % 2] is not None:
-                    side.wait_event(free[j % 2])  # the decode that read this slot two batches ago
-                y.copy_(y_host[lo:hi], non_blocking=True)
+                if free[s2] is not None:
+                    side.wait_event(free[s2])  # the decode that read this slot two batches ago
+                y = stage(sl, s2, cb, lo, hi)
                 copied = torch.cuda.Event()
                 copied.record(side)
             cur.wait_event(copied)
-            cw, info = sc_decode_symbols(plan, y, table)
-            free[j % 2] = torch.cuda.Event()
-            free[j % 2].record(cur)
-            cw_host[lo:hi].copy_(cw, non_blocking=True)
-            info_host[lo:hi].copy_(info, non_blocking=True)
+            if drained[s2] is not None:
+                cur.wait_event(drained[s2])
+            cw = sl.get(s2, "cw", (cb, plan.Nw), torch.int32)[:hi - lo]
+            info = sl.get(s2, "info", (cb, max(plan.Kw, 1)), torch.int32)[:hi - lo]
+            sc_decode_symbols(plan, y, table, out=(cw, info))
+            free[s2] = torch.cuda.Event()
+            free[s2].record(cur)
+            with torch.cuda.stream(back):  # results go home while the next batch decodes
+                back.wait_event(free[s2])
+                cw_host[lo:hi].copy_(cw, non_blocking=True)
+                info_host[lo:hi].copy_(info[:, :plan.Kw], non_blocking=True)
+                drained[s2] = torch.cuda.Event()
+                drained[s2].record(back)
+        cur.wait_stream(back)
+        cur.wait_stream(side)
         return
     chunk = chunk or default_host_chunk(B, plan.N, sc_wave_frames(plan))
     sl = _Slots(plan, "scsym")
 
     def body(lo, hi, slot):
         m = hi - lo
-        y = sl.get(slot, "y", (chunk, plan.N), torch.uint8)[:m]
         cw = sl.get(slot, "cw", (chunk, plan.Nw), torch.int32)[:m]
         info = sl.get(slot, "info", (chunk, max(plan.Kw, 1)), torch.int32)[:m]
-        y.copy_(y_host[lo:hi], non_blocking=True)
+        y = stage(sl, slot, chunk, lo, hi)
         sc_decode_symbols(plan, y, table, out=(cw, info))
         cw_host[lo:hi].copy_(cw, non_blocking=True)
         info_host[lo:hi].copy_(info[:, :plan.Kw], non_blocking=True)

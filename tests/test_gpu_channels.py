@@ -132,3 +132,39 @@ def test_biawgn_statistics_and_quantiser():
     assert tab.shape == (Y, 2) and abs(tab.sum() - 1.0) < 1e-12
     emp = np.bincount(yq.cpu().numpy()[xs == 0], minlength=Y) / (xs == 0).sum()
     assert np.abs(emp - 2 * tab[:, 0]).max() < 6 * math.sqrt(0.02 / (xs == 0).sum())
+
+
+@pytest.mark.parametrize("bits,Y", [(1, 2), (2, 3), (2, 4), (4, 11)])
+def test_pack_unpack_symbols_and_packed_host_decode(bits, Y):
+    """pc_pack_symbols / pc_unpack_symbols round trip and layout (symbol i in bits [i*bits, (i+1)*bits) of the little-endian
+    stream), and the packed host-buffer SC pipeline against the unpacked one."""
+    rng = np.random.default_rng(bits * 10 + Y)
+    B, N = 300, 1024
+    ys = rng.integers(0, Y, (B, N)).astype(np.uint8)
+    y = torch.from_numpy(ys).to(DEV)
+    p = channels.pack_symbols(y, bits)
+    assert p.shape == (B, N * bits // 8)
+    want = np.zeros((B, N * bits // 8), dtype=np.uint8)
+    per = 8 // bits
+    for j in range(per):
+        want |= (ys[:, j::per] << (j * bits)).astype(np.uint8)
+    assert np.array_equal(p.cpu().numpy(), want)
+    assert torch.equal(channels.unpack_symbols(p, bits), y)
+    if Y <= 3:  # SC decode through pinned host buffers: packed == unpacked
+        import polarcub_b200 as pcb
+        from polarcub_b200 import engine
+        n = 10
+        fm = np.zeros(N, dtype=np.uint8)
+        fm[rng.permutation(N)[: N // 2]] = 1
+        plan = engine.Plan(2, n, fm, np.zeros(N, dtype=np.uint8), device=DEV)
+        tab = np.array([[0.445, 0.055], [0.055, 0.445], [0.05, 0.05]])[:Y]
+        outs = []
+        for pb, src in ((0, y), (bits, p)):
+            yh = src.cpu().pin_memory()
+            cw = torch.empty((B, plan.Nw), dtype=torch.int32).pin_memory()
+            info = torch.empty((B, plan.Kw), dtype=torch.int32).pin_memory()
+            engine.sc_decode_symbols_host(plan, yh, tab, cw, info, chunk=64, packed_bits=pb)
+            torch.cuda.synchronize()
+            outs.append((cw.clone(), info.clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        assert pcb is not None
