@@ -168,7 +168,7 @@ __device__ __forceinline__ void fg_step(const Raw8 &r, const uint32_t u4, double
     }
 }
 
-template <bool PLUS>
+template <bool PLUS, bool PREFETCH>
 __device__ __forceinline__ void fg_pass(const Src &src, double2 *__restrict__ dp, double2 *__restrict__ dp2, const bool fused,
                                         const uint32_t *rp, const int half, const bool valid) {
     Raw8 A, B;
@@ -190,6 +190,23 @@ __device__ __forceinline__ void fg_pass(const Src &src, double2 *__restrict__ dp
     // u bits: word w of the codeword covers eight steps; the next word is requested as soon as a word is taken into use
     const bool pv = PLUS && valid;
     uint32_t w = pv ? rp[0] : 0u, wn = (pv && nsteps > 8) ? rp[32] : 0u;
+    if (!PREFETCH) {
+        // register-lean variant (16 warps per SM): one element buffer, the operands of a step are fetched right before it; the
+        // HBM levels are still prefetched by the bulk-copy ring
+#pragma unroll 1
+        for (int k = 0; k < nsteps; ++k) {
+            src_fetch<8>(src, k, A);
+            if (valid) {
+                const int j = (4 * k) & 31;
+                fg_step<PLUS>(A, (w >> j) & 15u, dp, dp2, fused);
+                if (PLUS && j == 28) {
+                    w = wn;
+                    if (k + 9 < nsteps) wn = rp[((4 * k + 36) >> 5) << 5];
+                }
+            }
+        }
+        return;
+    }
     src_fetch<8>(src, 0, A);
     if (nsteps == 1) {
         if (valid) fg_step<PLUS>(A, w & 15u, dp, dp2, fused);
@@ -307,10 +324,12 @@ __device__ __forceinline__ void select_paths(const double (&cv)[8], const int ib
     }
 }
 
-// MB = resident warps per SM the build is register-capped for.  Twelve (168 registers) is where the eight-element steps of
-// fg_pass fit without spilling; sweeps of 8..32 warps per SM with smaller steps all ended within 5 % of each other (the
-// kernel trades latency hiding by warps against DRAM traffic of the resident frames, profiles/r2_a), so there is ONE build.
-constexpr int SCLP_MAX_WARPS_PER_SM = 12;
+// MB = resident warps per SM the build is register-capped for.  The decoder is bound by per-warp latency (profiles/r2_a): its
+// throughput is linear in the resident warps as long as nothing spills.  Two builds: 12 warps (168 registers: eight-element steps
+// with the next step's operands prefetched into registers) and 16 warps (128 registers: the same steps, operands fetched right
+// before use -- the HBM levels still arrive through the bulk-copy ring): 16 warps decode 18 % more frames per second.
+constexpr int SCLP_MAX_WARPS_PER_SM = 16;
+constexpr int SCLP_DEFAULT_WARPS_PER_SM = 16;
 template <int MB>
 __global__ void __launch_bounds__(32 * MB, 1) sclp_kernel(const SclpParams p) {
     PC_DYN_SMEM(smem_all);
@@ -478,9 +497,9 @@ __global__ void __launch_bounds__(32 * MB, 1) sclp_kernel(const SclpParams p) {
                         sr.p = vbase(l) + gbase + srcslot;
                     }
                     if (plus)
-                        fg_pass<true>(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, fused, rp, half, valid);
+                        fg_pass<true, (MB <= 12)>(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, fused, rp, half, valid);
                     else
-                        fg_pass<false>(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, fused, rp, half, valid);
+                        fg_pass<false, (MB <= 12)>(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, fused, rp, half, valid);
                 }
                 __syncwarp();
                 continue;
@@ -1067,7 +1086,7 @@ static int envp_int(const char *name, int dflt) {
 struct SclpKnobs {
     int warps_per_sm, lsm, rgl, off, nst, timing, skew, sync, alias;
     SclpKnobs() {
-        warps_per_sm = envp_int("PC_SCLP_WARPS_PER_SM", SCLP_MAX_WARPS_PER_SM);
+        warps_per_sm = envp_int("PC_SCLP_WARPS_PER_SM", SCLP_DEFAULT_WARPS_PER_SM);
         if (warps_per_sm > SCLP_MAX_WARPS_PER_SM) warps_per_sm = SCLP_MAX_WARPS_PER_SM;
         lsm = envp_int("PC_SCLP_LSM", -1);
         rgl = envp_int("PC_SCLP_RGL", 7);
@@ -1101,7 +1120,7 @@ static SclpConfig sclp_config(const pc_plan *plan, int L, int64_t B) {
     int rgl = kn.rgl < 1 ? 1 : kn.rgl;
     if (rgl > n + 1) rgl = n + 1;
     c.rgl = rgl;
-    const int target = kn.warps_per_sm > 0 ? kn.warps_per_sm : SCLP_MAX_WARPS_PER_SM;
+    const int target = kn.warps_per_sm > 0 ? kn.warps_per_sm : SCLP_DEFAULT_WARPS_PER_SM;
     const size_t budget = (size_t)(227 * 1024 - 1024) / (size_t)target;  // 1 KB per CTA is the system's
     int lsm = n - 1 < 6 ? n - 1 : 6;
     if (lsm < 1) lsm = 1;
@@ -1285,7 +1304,8 @@ static int sclp_run(const pc_plan *plan, const SclTables *T, int L, const SclpIo
             p.alias = sclp_knobs().alias;
             p.wpc = c.per_sm, p.sync = sclp_knobs().sync, p.smem_per_warp = (int)c.smem;
             const int ctas = (int)((grid + c.per_sm - 1) / c.per_sm);
-            const int rc = sclp_launch<SCLP_MAX_WARPS_PER_SM>(p, ctas, c.smem * (size_t)c.per_sm, st);
+            const int rc = c.per_sm <= 12 ? sclp_launch<12>(p, ctas, c.smem * (size_t)c.per_sm, st)
+                                          : sclp_launch<16>(p, ctas, c.smem * (size_t)c.per_sm, st);
             if (rc) return rc;
         }
         prof_mark(st);
