@@ -76,6 +76,8 @@ def _check(n, L, fm, xy, fv, info, out):
     (5, 8, "blocks", 1.0, 9, {}), (4, 32, "random", 0.5, 5, {}), (8, 8, "bec", 0.5, 9, {"PC_SCLP_NOFUSE": "1"}),
     (9, 8, "blocks", 0.6, 6, {"PC_SCLP_LSM": "6", "PC_SCLP_RGL": "9"}), (10, 8, "bec", 0.5, 5, {"PC_SCLP_LSM": "1", "PC_SCLP_RGL": "1"}),
     (3, 8, "bec", 0.5, 9, {}), (1, 8, "bec", 0.5, 9, {}), (2, 4, "bec", 0.5, 17, {}), (7, 1, "bec", 0.5, 40, {}),
+    # the 12-warp build (operands of the next step prefetched into registers); the default is the 16-warp build
+    (10, 8, "bec", 0.5, 5, {"PC_SCLP_WARPS_PER_SM": "12"}), (9, 8, "blocks", 0.6, 6, {"PC_SCLP_WARPS_PER_SM": "12", "PC_SCLP_STAGES": "0"}),
 ])
 def test_emulated_kernels_vs_oracle(n, L, how, rate, B, env, monkeypatch):
     for kk, v in env.items():
