@@ -45,6 +45,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// ---- L2 eviction priorities (createpolicy + .L2::cache_hint): the list decoder streams its large levels (written once, read back a
+// sub-tree later: they only pass through L2) and keeps re-using its small global levels; an evict_first policy on the former and
+// evict_last on the latter keeps the small levels of all resident frames in L2.  A policy value 0 means "no hint".
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// 16-byte global store / load with a policy (GLOBAL addresses only)
+__device__ __forceinline__ void st_global_hint(double2 *p, const double2 v, const uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ double2 ld_global_hint(const double2 *p, const uint64_t pol) {
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, const uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
 #else
 // CPU emulation (tests/emu): the copy happens at issue; the barrier word holds the parity of the phase in progress
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t) { *bar = 0; }
@@ -60,6 +88,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while ((*bar & 1) == parity) emu::yield();
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { return 1; }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { return 2; }
+__device__ __forceinline__ void st_global_hint(double2 *p, const double2 v, const uint64_t) { *p = v; }
+__device__ __forceinline__ double2 ld_global_hint(const double2 *p, const uint64_t) { return *p; }
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, const uint64_t) {
+    bulk_g2s(dst_smem, src_gmem, bytes, bar);
 }
 #endif
 

@@ -33,6 +33,7 @@ namespace pc {
 struct SclpParams {
     int n, k, L, G, gsh, n_ops, lsm, rgl, NW, n_leaf, sym, want_list, nfw;
     int nst;              // stages of the bulk-copy ring (0: plain loads)
+    int l2lvl;            // L2 policies: global levels <= l2lvl are kept (evict_last), larger ones stream (evict_first); 0 = no hints
     int alias;            // diagnostic (PC_SCLP_ALIAS): every CTA uses the scratch of CTA 0 -- wrong results, shows the DRAM-free speed
     int wpc, sync, smem_per_warp;  // warps per CTA, per-op barrier among the warps of a scheduler, shared-memory bytes per warp
     int64_t frames;
@@ -89,6 +90,7 @@ struct Src {
     uint64_t *bars;
     uint32_t *ph;
     int nst, nsteps, col, lane;
+    uint64_t pol;  // L2 policy of the bulk copies of an SK_STAGED source (0: none)
 };
 struct Raw8 {
     double2 v[8];
@@ -96,7 +98,10 @@ struct Raw8 {
 __device__ __forceinline__ void src_issue(const Src &s, int k) {
     const int st = k & (s.nst - 1);
     mbar_expect_tx(s.bars + st, 4096u);
-    bulk_g2s(s.stg + st * 256, s.p + (int64_t)k * 256, 4096u, s.bars + st);
+    if (s.pol)
+        bulk_g2s_hint(s.stg + st * 256, s.p + (int64_t)k * 256, 4096u, s.bars + st, s.pol);
+    else
+        bulk_g2s(s.stg + st * 256, s.p + (int64_t)k * 256, 4096u, s.bars + st);
 }
 __device__ __forceinline__ double2 src_at(const Src &s, int i) { return s.p[((i >> s.gsh) << 5) + (i & ((1 << s.gsh) - 1))]; }
 // raw elements [8k, 8k + CNT) of the source (CNT = 8, or 4 for the two-element levels)
@@ -144,9 +149,19 @@ __device__ __forceinline__ void src_fetch(const Src &s, int k, Raw8 &r) {
 // four (+ two) node updates of a step run in lock step (node_lockstep), so their dependency chains overlap; the rare operands
 // outside the fast division's range are redone after.  The loop is unrolled by two over a pair of element buffers: the raw
 // elements of step k+1 are fetched before step k is computed and no buffer is ever copied.
+// destination policies: pd / pd2 != 0 -> the level is in GLOBAL memory and stored with that L2 policy, 0 -> generic store (shared memory)
+struct DstPol {
+    uint64_t pd, pd2;
+};
+__device__ __forceinline__ void vstore(double2 *p, const double2 v, const uint64_t pol) {
+    if (pol)
+        st_global_hint(p, v, pol);
+    else
+        *p = v;
+}
 template <bool PLUS>
 __device__ __forceinline__ void fg_step(const Raw8 &r, const uint32_t u4, double2 *__restrict__ &dp, double2 *__restrict__ &dp2,
-                                        const bool fused) {
+                                        const bool fused, const DstPol dpol) {
     double2 y[4];
     const uint32_t slow = node_lockstep<4, PLUS>(r.v, u4, y);
     if (slow) {  // rare: an operand below 1e-291 (or an un-normalised channel pair): the IEEE division
@@ -154,7 +169,7 @@ __device__ __forceinline__ void fg_step(const Raw8 &r, const uint32_t u4, double
         for (int i = 0; i < 4; ++i)
             if ((slow >> i) & 1u) y[i] = node_fg(r.v[2 * i], r.v[2 * i + 1], PLUS, (u4 >> i) & 1u);
     }
-    dp[0] = y[0], dp[32] = y[1], dp[64] = y[2], dp[96] = y[3];
+    vstore(dp, y[0], dpol.pd), vstore(dp + 32, y[1], dpol.pd), vstore(dp + 64, y[2], dpol.pd), vstore(dp + 96, y[3], dpol.pd);
     dp += 128;
     if (fused) {
         double2 z[2];
@@ -163,14 +178,14 @@ __device__ __forceinline__ void fg_step(const Raw8 &r, const uint32_t u4, double
             if (s2 & 1u) z[0] = node_fg(y[0], y[1], false, 0u);
             if (s2 & 2u) z[1] = node_fg(y[2], y[3], false, 0u);
         }
-        dp2[0] = z[0], dp2[32] = z[1];
+        vstore(dp2, z[0], dpol.pd2), vstore(dp2 + 32, z[1], dpol.pd2);
         dp2 += 64;
     }
 }
 
 template <bool PLUS, bool PREFETCH>
 __device__ __forceinline__ void fg_pass(const Src &src, double2 *__restrict__ dp, double2 *__restrict__ dp2, const bool fused,
-                                        const uint32_t *rp, const int half, const bool valid) {
+                                        const uint32_t *rp, const int half, const bool valid, const DstPol dpol) {
     Raw8 A, B;
     if (half == 2) {  // four source elements: one half step
         src_fetch<4>(src, 0, A);
@@ -198,7 +213,7 @@ __device__ __forceinline__ void fg_pass(const Src &src, double2 *__restrict__ dp
             src_fetch<8>(src, k, A);
             if (valid) {
                 const int j = (4 * k) & 31;
-                fg_step<PLUS>(A, (w >> j) & 15u, dp, dp2, fused);
+                fg_step<PLUS>(A, (w >> j) & 15u, dp, dp2, fused, dpol);
                 if (PLUS && j == 28) {
                     w = wn;
                     if (k + 9 < nsteps) wn = rp[((4 * k + 36) >> 5) << 5];
@@ -209,17 +224,17 @@ __device__ __forceinline__ void fg_pass(const Src &src, double2 *__restrict__ dp
     }
     src_fetch<8>(src, 0, A);
     if (nsteps == 1) {
-        if (valid) fg_step<PLUS>(A, w & 15u, dp, dp2, fused);
+        if (valid) fg_step<PLUS>(A, w & 15u, dp, dp2, fused, dpol);
         return;
     }
 #pragma unroll 1
     for (int k = 0; k < nsteps; k += 2) {
         src_fetch<8>(src, k + 1, B);
-        if (valid) fg_step<PLUS>(A, (w >> ((4 * k) & 31)) & 15u, dp, dp2, fused);
+        if (valid) fg_step<PLUS>(A, (w >> ((4 * k) & 31)) & 15u, dp, dp2, fused, dpol);
         if (k + 2 < nsteps) src_fetch<8>(src, k + 2, A);
         if (valid) {
             const int j = (4 * k + 4) & 31;
-            fg_step<PLUS>(B, (w >> j) & 15u, dp, dp2, fused);
+            fg_step<PLUS>(B, (w >> j) & 15u, dp, dp2, fused, dpol);
             if (PLUS && j == 28) {
                 w = wn;
                 if (k + 10 < nsteps) wn = rp[((4 * k + 40) >> 5) << 5];
@@ -365,6 +380,9 @@ __global__ void __launch_bounds__(32 * MB, 1) sclp_kernel(const SclpParams p) {
     auto vbase = [&](int l) -> double2 * { return (l <= lsm ? Vs : Vg) + (((int64_t)1 << l) - 1) * 32; };
     auto rbase = [&](int l, int c) -> uint32_t * { return (l < rgl ? Rs : Rg) + (int64_t)(2 * scl2_wsum(l) + c * scl2_W(l)) * 32; };
     auto OM = [&](int l, int c) -> uint8_t * { return om + (l * 2 + c) * 32; };
+    // L2 policy of level l's vectors: 0 for the shared-memory levels (generic accesses) and when the hints are off
+    const uint64_t pol_first = p.l2lvl ? l2_policy_evict_first() : 0, pol_last = p.l2lvl ? l2_policy_evict_last() : 0;
+    auto lvl_pol = [&](int l) -> uint64_t { return (l <= lsm || !p.l2lvl) ? (uint64_t)0 : (l <= p.l2lvl ? pol_last : pol_first); };
     const int fpw = 32 >> gsh;
     const bool dualon = G >= 4;  // two-variant storage of SCLP_DUAL outputs pays with four or more paths
 
@@ -481,7 +499,7 @@ __global__ void __launch_bounds__(32 * MB, 1) sclp_kernel(const SclpParams p) {
                 } else {
                     // the lane's own path: per-path destination(s)
                     Src sr;
-                    sr.gsh = gsh, sr.ss = 32;
+                    sr.gsh = gsh, sr.ss = 32, sr.pol = 0;
                     if (chan) {
                         sr.kind = p.sym ? SK_SYM : SK_PATH;
                         sr.y = yf, sr.tab = p.tab, sr.p = xyf, sr.ss = 1;
@@ -492,14 +510,16 @@ __global__ void __launch_bounds__(32 * MB, 1) sclp_kernel(const SclpParams p) {
                         sr.kind = SK_STAGED;
                         sr.p = vbase(l), sr.stg = stg, sr.bars = bars, sr.ph = &ph, sr.nst = p.nst, sr.nsteps = half >> 2;
                         sr.col = gbase + srcslot, sr.lane = lane;
+                        sr.pol = lvl_pol(l);
                     } else {
                         sr.kind = SK_PATH;
                         sr.p = vbase(l) + gbase + srcslot;
                     }
+                    const DstPol dpol{lvl_pol(l - 1), lvl_pol(l >= 2 ? l - 2 : 0)};
                     if (plus)
-                        fg_pass<true, (MB <= 12)>(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, fused, rp, half, valid);
+                        fg_pass<true, (MB <= 12)>(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, fused, rp, half, valid, dpol);
                     else
-                        fg_pass<false, (MB <= 12)>(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, fused, rp, half, valid);
+                        fg_pass<false, (MB <= 12)>(sr, vbase(l - 1) + lane, vbase(l >= 2 ? l - 2 : 0) + lane, fused, rp, half, valid, dpol);
                 }
                 __syncwarp();
                 continue;
@@ -556,8 +576,10 @@ __global__ void __launch_bounds__(32 * MB, 1) sclp_kernel(const SclpParams p) {
                         double2 v[4];
                         if (plain) {
                             const double2 *q = vbase(l) + (jb << 5) + lane;
+                            const uint64_t pl = lvl_pol(l);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) v[i] = i < nb ? q[i << 5] : make_double2(1.0, 1.0);
+                            for (int i = 0; i < 4; ++i)
+                                v[i] = i < nb ? (pl ? ld_global_hint(q + (i << 5), pl) : q[i << 5]) : make_double2(1.0, 1.0);
                         } else {
 #pragma unroll 1
                             for (int i = 0; i < nb; ++i) {  // the channel, shared-layout and two-variant vectors: few nodes per frame
@@ -1084,7 +1106,7 @@ static int envp_int(const char *name, int dflt) {
 // tuning knobs are read ONCE per process (a changed environment between the workspace query and the decode cannot break
 // the sizing contract)
 struct SclpKnobs {
-    int warps_per_sm, lsm, rgl, off, nst, timing, skew, sync, alias;
+    int warps_per_sm, lsm, rgl, off, nst, timing, skew, sync, alias, l2lvl;
     SclpKnobs() {
         warps_per_sm = envp_int("PC_SCLP_WARPS_PER_SM", SCLP_DEFAULT_WARPS_PER_SM);
         if (warps_per_sm > SCLP_MAX_WARPS_PER_SM) warps_per_sm = SCLP_MAX_WARPS_PER_SM;
@@ -1095,6 +1117,7 @@ struct SclpKnobs {
         skew = envp_int("PC_SCLP_SKEW", 1);
         sync = envp_int("PC_SCLP_SYNC", 1);
         alias = envp_int("PC_SCLP_ALIAS", 0);
+        l2lvl = envp_int("PC_SCLP_L2LVL", 5);  // +3 % (sweep: 0 / 4 / 5 / 6 / 7 / 12 -> 1.698 / 1.737 / 1.753 / 1.751 / 1.727 / 1.698 Gbit/s)
         off = envp_int("PC_SCL_GENERIC", 0);  // tests: force the generic (q <= 5, frame per lane) decoder for q = 2
     }
 };
@@ -1302,6 +1325,7 @@ static int sclp_run(const pc_plan *plan, const SclTables *T, int L, const SclpIo
         {
             // grid warps in CTAs of per_sm warps (one CTA per SM)
             p.alias = sclp_knobs().alias;
+            p.l2lvl = sclp_knobs().l2lvl;
             p.wpc = c.per_sm, p.sync = sclp_knobs().sync, p.smem_per_warp = (int)c.smem;
             const int ctas = (int)((grid + c.per_sm - 1) / c.per_sm);
             const int rc = c.per_sm <= 12 ? sclp_launch<12>(p, ctas, c.smem * (size_t)c.per_sm, st)
