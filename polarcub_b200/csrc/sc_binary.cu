@@ -1002,14 +1002,20 @@ static HybridTables *hybrid_tables(const pc_plan *p) {
     auto it = g_hy_tables.find(p);
     if (it != g_hy_tables.end()) return it->second;
     HybridTables *T = new HybridTables();
+    // every failure path below releases what was built so far (sub-plans, device buffers): nothing is cached half-built
+    auto fail = [&](const char *why) -> HybridTables * {
+        if (why) set_error("%s", why);
+        for (pc_plan *q : T->sub) pc_plan_destroy(q);
+        if (T->d_info_pos) cudaFree(T->d_info_pos);
+        if (T->d_sched_r1) cudaFree(T->d_sched_r1);
+        delete T;
+        return nullptr;
+    };
     const int Ns = 1 << HY_L0, NS = p->N >> HY_L0;
     for (int j = 0; j < NS; ++j) {
         pc_plan *sp = nullptr;
-        if (pc_plan_create(2, HY_L0, p->frozen_mask.data() + (size_t)j * Ns, p->frozen_vals.data() + (size_t)j * Ns, &sp) != PC_OK) {
-            for (pc_plan *q : T->sub) pc_plan_destroy(q);
-            delete T;
-            return nullptr;
-        }
+        if (pc_plan_create(2, HY_L0, p->frozen_mask.data() + (size_t)j * Ns, p->frozen_vals.data() + (size_t)j * Ns, &sp) != PC_OK)
+            return fail(nullptr);
         T->sub.push_back(sp);
         T->all_frozen.push_back(sp->k == 0 ? 1 : 0);
     }
@@ -1021,19 +1027,15 @@ static HybridTables *hybrid_tables(const pc_plan *p) {
         T->r1_len.push_back((int32_t)r1.size() - T->r1_off.back());
     }
     if (cudaMalloc((void **)&T->d_sched_r1, r1.size() * sizeof(SchedEntry)) != cudaSuccess ||
-        cudaMemcpy(T->d_sched_r1, r1.data(), r1.size() * sizeof(SchedEntry), cudaMemcpyHostToDevice) != cudaSuccess) {
-        set_error("hybrid tables: device upload failed");
-        return nullptr;
-    }
+        cudaMemcpy(T->d_sched_r1, r1.data(), r1.size() * sizeof(SchedEntry), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail("hybrid tables: device upload failed");
     std::vector<int32_t> pos;
     for (int i = 0; i < p->N; ++i)
         if (!p->frozen_mask[i]) pos.push_back(i);
     if (pos.empty()) pos.push_back(0);
     if (cudaMalloc((void **)&T->d_info_pos, pos.size() * 4) != cudaSuccess ||
-        cudaMemcpy(T->d_info_pos, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
-        set_error("hybrid tables: device upload failed");
-        return nullptr;
-    }
+        cudaMemcpy(T->d_info_pos, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail("hybrid tables: device upload failed");
     g_hy_tables[p] = T;
     return T;
 }
