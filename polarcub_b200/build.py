@@ -15,7 +15,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--shared", "-Xptxas", "-v",
-]
+] + os.environ.get("PC_NVCC_EXTRA", "").split()  # experiment builds only (e.g. -DSCLP_SELECT_SHFL=0)
 
 
 def sources():

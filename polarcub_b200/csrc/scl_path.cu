@@ -263,6 +263,9 @@ __device__ __forceinline__ int group_sum(int v, const int G) {
 // candidates (descending (key, index); a sorting network in registers), then every round is one arg-max of the lanes' heads
 // over the frame's lane group -- three redux.sync (high word, low word among the equals, index among the equals) -- and the
 // winning lane pops its head.
+#ifndef SCLP_SELECT_SHFL
+#define SCLP_SELECT_SHFL 1
+#endif
 struct Cand {
     uint32_t hi, lo;
     int idx;  // -1: no candidate
@@ -319,16 +322,28 @@ __device__ __forceinline__ void select_paths(const double (&cv)[8], const int ib
     }
 #pragma unroll 1
     for (int r = 0; r < ns; ++r) {
-        const uint32_t mh = __reduce_max_sync(gmask, c[0].hi);
-        const bool e1 = c[0].hi == mh;
-        const uint32_t ml = __reduce_max_sync(gmask, e1 ? c[0].lo : 0u);
-        const bool e2 = e1 && c[0].lo == ml;
-        const int bi = (int)__reduce_max_sync(gmask, e2 ? (uint32_t)(c[0].idx + 1) : 0u) - 1;
+        uint32_t mh, ml;
+        int bi;
+        if (SCLP_SELECT_SHFL) {  // butterfly arg-max inside the lane group: 3 shuffles per stage
+            mh = c[0].hi, ml = c[0].lo, bi = c[0].idx;
+            for (int o = 1; o < G; o <<= 1) {
+                const uint32_t oh = __shfl_xor_sync(gmask, mh, o), ol = __shfl_xor_sync(gmask, ml, o);
+                const int oi = __shfl_xor_sync(gmask, bi, o);
+                const bool better = oh > mh || (oh == mh && (ol > ml || (ol == ml && oi > bi)));
+                mh = better ? oh : mh, ml = better ? ol : ml, bi = better ? oi : bi;
+            }
+        } else {
+            mh = __reduce_max_sync(gmask, c[0].hi);
+            const bool e1 = c[0].hi == mh;
+            ml = __reduce_max_sync(gmask, e1 ? c[0].lo : 0u);
+            const bool e2 = e1 && c[0].lo == ml;
+            bi = (int)__reduce_max_sync(gmask, e2 ? (uint32_t)(c[0].idx + 1) : 0u) - 1;
+        }
         if (t == ns - 1 - r) {
             newprob = __hiloint2double((int)mh, (int)ml);
             ci = bi;
         }
-        const bool pop = e2 && c[0].idx == bi;
+        const bool pop = c[0].idx == bi && bi >= 0;  // candidate indices are unique inside a frame
 #pragma unroll
         for (int i = 0; i + 1 < M; ++i) {
             c[i].hi = pop ? c[i + 1].hi : c[i].hi;
