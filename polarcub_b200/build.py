@@ -37,9 +37,12 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    only = [t for t in os.environ.get("PC_BUILD_ONLY", "").split(",") if t]  # experiment builds: recompile these, reuse the other objects
     for s in sources():
         o = os.path.join(HERE, "build", os.path.basename(s)[:-3] + ".o")
         objs.append(o)
+        if only and os.path.basename(s)[:-3] not in only and os.path.isfile(o):
+            continue
         cmd = [NVCC] + [f for f in FLAGS if f != "--shared"] + ["-c", s, "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
