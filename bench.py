@@ -248,7 +248,8 @@ class ScBinaryLarge:
               "state codes (erasure-type channel) + sc_decode8_kernel (1024-leaf sub-blocks, frame per lane, exact rate-1 shortcut); "
               "other discrete channels: hy_level_kernel + sc_decode_kernel<packed> on float64; batches below 6144 frames: sc_stream_kernel")
     dtype = "f64"
-    default_frames, default_e2e, default_cpu = 32768, 32768, 32
+    # one full wave of the sub-block kernel (148 SMs x 256 frames): its time does not depend on the batch size below that
+    default_frames, default_e2e, default_cpu = 148 * 256, 32768, 32
     n = int(os.environ.get("PC_BENCH_LARGE_N", "20"))  # 20 is the BASELINE configuration; smaller values are for profiling runs
     N, K = 1 << n, int(0.8 * (1 << n))
     # stages above 2^13 stream 12 N bytes each + channel ingest 4 N + (N + K)/8 out (fp32 soft-input contract)

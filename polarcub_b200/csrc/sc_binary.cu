@@ -1077,7 +1077,8 @@ __global__ void hy_lut_kernel(int Y, const HyRootParams tp, double *__restrict__
 // four states, so the upper stages keep ONE BYTE per element instead of a float64 and update four frames per 32-bit
 // operation (f8 / g8); 8 x less HBM traffic and workspace than the float64 stages, identical decisions. ----
 
-// level n-2 from the channel symbols, four adjacent frames per thread
+// level n-2 from the channel symbols: a thread owns 32 consecutive elements (one word of decision bits per operand) of four
+// adjacent frames, so the decision words of levels n-1 / n-2 are loaded once per 32 elements and the symbol rows stream through
 __global__ void __launch_bounds__(256) hy_level_sym8_kernel(int64_t quarter, int64_t Bpad, const uint8_t *__restrict__ sym, int Y,
                                                             const uint8_t *__restrict__ lut8, const uint32_t *__restrict__ x0,
                                                             int top_g, const uint32_t *__restrict__ xw, int isg,
@@ -1087,26 +1088,32 @@ __global__ void __launch_bounds__(256) hy_level_sym8_kernel(int64_t quarter, int
     __syncthreads();
     const int64_t Bq = Bpad >> 2;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= quarter * Bq) return;
-    const int64_t h = gid / Bq, fq = gid - h * Bq, hb = h + quarter, half = 2 * quarter;
-    const uint32_t *s32 = (const uint32_t *)sym;
-    const uint32_t y0 = s32[h * Bq + fq], y1 = s32[(h + half) * Bq + fq], y2 = s32[hb * Bq + fq], y3 = s32[(hb + half) * Bq + fq];
+    if (gid >= (quarter >> 5) * Bq) return;
+    const int64_t hb = gid / Bq, fq = gid - hb * Bq, half = 2 * quarter;
+    const uint32_t *p0 = (const uint32_t *)sym + hb * 32 * Bq + fq;  // symbols of element h = 32 hb + k, frames 4 fq .. 4 fq + 3
+    const uint32_t *p1 = p0 + half * Bq, *p2 = p0 + quarter * Bq, *p3 = p2 + half * Bq;
+    uint32_t *o = (uint32_t *)out + hb * 32 * Bq + fq;
     uint4 wa = make_uint4(0, 0, 0, 0), wb = wa, wu = wa;
     if (top_g) {
-        wa = *(const uint4 *)(x0 + (h >> 5) * Bpad + 4 * fq);
-        wb = *(const uint4 *)(x0 + (hb >> 5) * Bpad + 4 * fq);
+        wa = *(const uint4 *)(x0 + hb * Bpad + 4 * fq);
+        wb = *(const uint4 *)(x0 + (hb + (quarter >> 5)) * Bpad + 4 * fq);
     }
-    if (isg) wu = *(const uint4 *)(xw + (h >> 5) * Bpad + 4 * fq);
+    if (isg) wu = *(const uint4 *)(xw + hb * Bpad + 4 * fq);
     const uint32_t wav[4] = {wa.x, wa.y, wa.z, wa.w}, wbv[4] = {wb.x, wb.y, wb.z, wb.w}, wuv[4] = {wu.x, wu.y, wu.z, wu.w};
-    uint32_t A = 0, Bv = 0, U = 0;
+    const uint32_t YY = (uint32_t)(Y * Y);
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) {
+        const uint32_t y0 = p0[k * Bq], y1 = p1[k * Bq], y2 = p2[k * Bq], y3 = p3[k * Bq];
+        uint32_t A = 0, Bv = 0, U = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t ma = top_g ? 1u + ((wav[j] >> (h & 31)) & 1u) : 0u, mb = top_g ? 1u + ((wbv[j] >> (hb & 31)) & 1u) : 0u;
-        A |= (uint32_t)s_lut[(ma * Y + ((y0 >> (8 * j)) & 255u)) * Y + ((y1 >> (8 * j)) & 255u)] << (8 * j);
-        Bv |= (uint32_t)s_lut[(mb * Y + ((y2 >> (8 * j)) & 255u)) * Y + ((y3 >> (8 * j)) & 255u)] << (8 * j);
-        U |= ((wuv[j] >> (h & 31)) & 1u) << (8 * j);
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t ma = top_g ? YY + YY * ((wav[j] >> k) & 1u) : 0u, mb = top_g ? YY + YY * ((wbv[j] >> k) & 1u) : 0u;
+            A |= (uint32_t)s_lut[ma + ((y0 >> (8 * j)) & 255u) * Y + ((y1 >> (8 * j)) & 255u)] << (8 * j);
+            Bv |= (uint32_t)s_lut[mb + ((y2 >> (8 * j)) & 255u) * Y + ((y3 >> (8 * j)) & 255u)] << (8 * j);
+            U |= ((wuv[j] >> k) & 1u) << (8 * j);
+        }
+        o[k * Bq] = isg ? g8(A, Bv, U) : f8(A, Bv);
     }
-    ((uint32_t *)out)[gid] = isg ? g8(A, Bv, U) : f8(A, Bv);
 }
 
 // out[h][f] = node(in[h][f], in[h + size][f]): a thread owns 32 consecutive elements (one word of decision bits) of four
@@ -1403,7 +1410,7 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
             const uint32_t *xw = isg ? cw_t + ((i - size) >> 5) * Bp : cw_t;
             if (lev == n - 1) return PC_OK;  // looked up on demand by the level below
             if (et && lev == n - 2)
-                hy_level_sym8_kernel<<<blocks_of(size * Bp / 4), 256, 0, st>>>(size, Bp, sym, Y, (const uint8_t *)(lut + 768), cw_t,
+                hy_level_sym8_kernel<<<blocks_of((size >> 5) * (Bp / 4)), 256, 0, st>>>(size, Bp, sym, Y, (const uint8_t *)(lut + 768), cw_t,
                                                                               i >= N / 2 ? 1 : 0, xw, isg ? 1 : 0, V8(lev));
             else if (et && lev == HY_L0)
                 hy_level8_kernel<true><<<blocks_of((size >> 5) * (Bp / 4)), 256, 0, st>>>(size, Bp, V8(lev + 1), xw, isg ? 1 : 0, V8(lev));
@@ -1421,18 +1428,15 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
             const int64_t i = (int64_t)j * Ns;
             const int stop = T->all_frozen[j] ? HY_L0 + 1 : HY_L0;  // a rate-0 sub-block never needs its own level
             int lev;
+            bool isg = false;
             if (j == 0) {
                 lev = n - 1;
             } else {
-                const int top = HY_L0 + __builtin_ctz((unsigned)j);
-                if (top >= stop) {
-                    const int rc = level_op(top, true, i);
-                    if (rc) return rc;
-                }
-                lev = top - 1;
+                lev = HY_L0 + __builtin_ctz((unsigned)j);  // g at this level, then f down to the sub-block
+                isg = true;
             }
-            for (; lev >= stop; --lev) {
-                const int rc = level_op(lev, false, i);
+            for (; lev >= stop; --lev, isg = false) {
+                const int rc = level_op(lev, isg, i);
                 if (rc) return rc;
             }
             // the sub-block: frame per lane, top level read from V(HY_L0), partial sums written into the frame's words
