@@ -137,3 +137,34 @@ def test_qary_symbol_lookup_variant(q, n, how, monkeypatch):
     np.testing.assert_array_equal(c1[1:], c2)
     _, oinfo = oracle.q_decode_batch(q, N, ed.frozenMask, np.full((N, q), 1.0 / q), xy[:16])
     np.testing.assert_array_equal(i1[1:17], oinfo)
+
+
+@pytest.mark.parametrize("q", [2, 3, 5, 8])
+def test_fused_sweeps_every_depth_vs_oracle(q):
+    """The fused two-level sweeps of qsc_decode_kernel (sc_qary.cu: fused_q) against the oracle on every block length 2 .. 512 with
+    random frozen sets of several rates: descents of every length start at every level (g or f first), end at every stop level
+    (rate-0 sub-trees) and cross the shared-memory / global-scratch boundary of each q; probability and symbol entry points."""
+    import polarcub_b200 as pcb
+    rng = np.random.default_rng(4242 + q)
+    p = 0.07
+    tab = np.full((q, q), p / (q - 1))
+    np.fill_diagonal(tab, 1.0 - p)
+    for n in range(1, 10):
+        N = 1 << n
+        for rate in (0.25, 0.5, 0.8):
+            k = max(1, int(rate * N))
+            fs = set(int(i) for i in rng.permutation(N)[:N - k])
+            ed = pcb.QaryPolarEncoderDecoder(q, N, fs, 1)
+            B = 40
+            info = rng.integers(0, q, size=(B, ed.k))
+            cw = ed.encode_batch(info)
+            err = rng.random(cw.shape) < p
+            y = np.where(err, (cw + rng.integers(1, q, size=cw.shape)) % q, cw).astype(np.uint8)
+            xp = np.full((N, q), 1.0 / q)
+            ocw, oinfo = oracle.q_decode_batch(q, N, ed.frozenMask, xp, tab[y])
+            c1, i1 = ed.decode_batch(tab[y], return_codeword=True)
+            np.testing.assert_array_equal(i1, oinfo, err_msg="probs n=%d rate=%s" % (n, rate))
+            np.testing.assert_array_equal(c1, ocw, err_msg="probs n=%d rate=%s" % (n, rate))
+            c2, i2 = ed.decode_symbols_batch(y, tab, return_codeword=True)
+            np.testing.assert_array_equal(i2, oinfo, err_msg="symbols n=%d rate=%s" % (n, rate))
+            np.testing.assert_array_equal(c2, ocw, err_msg="symbols n=%d rate=%s" % (n, rate))
