@@ -74,7 +74,11 @@ struct ProfScope {                // brackets a multi-launch operation as ONE me
 // BinaryPolarEncoderDecoder.recursiveEncodeDecode (BinaryPolarEncoderDecoder.py:223-325) into a list of
 // nodes visited left to right.  A node is either a single information leaf or a maximal all-frozen
 // (rate-0) sub-tree whose codeword is known in advance, so its probabilities are never computed.
-enum : int { NODE_INFO = 0, NODE_RATE0 = 1, NODE_GENIE = 2, NODE_RATE1 = 3 };  // GENIE: known leaf bit, leaf probabilities captured
+enum : int { NODE_INFO = 0, NODE_RATE0 = 1, NODE_GENIE = 2, NODE_RATE1 = 3, NODE_BLOCK = 4 };  // GENIE: known leaf bit, leaf probabilities captured
+// BLOCK (binary decoder's block schedule, pc_plan::sched_b): a sub-tree of 2^SC_LB leaves that is not all-frozen, decoded by one unrolled
+// routine on registers -- the same node updates in the same order as the leaf-by-leaf walk; `bits` = frozen mask (low 8 bits, bit j =
+// leaf i + j is frozen) | frozen values << 8
+constexpr int SC_LB = 3;
 // RATE1 (hybrid decoder's sub-block schedules only): all-information sub-tree, `bits` = number of entries it spans after this one
 struct SchedEntry {
     int32_t i;      // first u index covered by the node
@@ -98,6 +102,8 @@ struct pc_plan {
     int q, n, N, k, device;
     std::vector<uint8_t> frozen_mask, frozen_vals;
     std::vector<pc::SchedEntry> sched;
+    std::vector<pc::SchedEntry> sched_b;  // binary, n > SC_LB: the same walk with NODE_BLOCK entries for the leaf blocks (sc_binary.cu)
+    pc::SchedEntry *d_sched_b = nullptr;
     // device copies
     pc::SchedEntry *d_sched = nullptr;
     uint32_t *d_r0_words = nullptr;   // natural-order codewords of rate-0 nodes with l >= 5

@@ -34,7 +34,10 @@ int num_sms() {
     return cached[dev];
 }
 
-static void build_schedule(pc_plan *p, int i, int l, std::vector<uint32_t> &r0_words) {
+// out: p->sched (lb < 0: leaf by leaf) or p->sched_b (lb = SC_LB: NODE_BLOCK entries for the mixed / information sub-trees of 2^lb leaves);
+// both reference the same r0_words (the block pass re-uses the offsets the first pass assigned, in the same order)
+static void build_schedule(pc_plan *p, int i, int l, std::vector<uint32_t> &r0_words, int lb = -1) {
+    std::vector<SchedEntry> &out = lb < 0 ? p->sched : p->sched_b;
     const int size = 1 << l;
     bool all_frozen = true;
     for (int j = i; j < i + size; ++j)
@@ -67,16 +70,27 @@ static void build_schedule(pc_plan *p, int i, int l, std::vector<uint32_t> &r0_w
                 }
             }
         }
-        p->sched.push_back(e);
+        out.push_back(e);
+        return;
+    }
+    if (l == lb) {
+        e.kind = NODE_BLOCK;
+        uint32_t m = 0, v = 0;
+        for (int j = 0; j < size; ++j) {
+            if (p->frozen_mask[i + j]) m |= 1u << j;
+            if (p->frozen_mask[i + j] && (p->frozen_vals[i + j] & 1)) v |= 1u << j;
+        }
+        e.bits = m | (v << 8);
+        out.push_back(e);
         return;
     }
     if (l == 0) {
         e.kind = NODE_INFO;
-        p->sched.push_back(e);
+        out.push_back(e);
         return;
     }
-    build_schedule(p, i, l - 1, r0_words);
-    build_schedule(p, i + size / 2, l - 1, r0_words);
+    build_schedule(p, i, l - 1, r0_words, lb);
+    build_schedule(p, i + size / 2, l - 1, r0_words, lb);
 }
 
 }  // namespace pc
@@ -124,6 +138,10 @@ int pc_plan_create(int q, int n, const uint8_t *h_frozen_mask, const uint8_t *h_
     }
     std::vector<uint32_t> r0_words;
     pc::build_schedule(p, 0, n, r0_words);
+    if (q == 2 && n > pc::SC_LB) {  // the block schedule visits the same rate-0 nodes in the same order: identical r0_words offsets
+        std::vector<uint32_t> r0_again;
+        pc::build_schedule(p, 0, n, r0_again, pc::SC_LB);
+    }
     const int Nw = (N + 31) / 32;
     std::vector<uint32_t> fw(Nw, 0u);
     for (int i = 0; i < N; ++i)
@@ -175,6 +193,7 @@ int pc_plan_create(int q, int n, const uint8_t *h_frozen_mask, const uint8_t *h_
         }                                                                                     \
     } while (0)
     UP(p->d_sched, p->sched, pc::SchedEntry);
+    if (p->sched_b.size()) UP(p->d_sched_b, p->sched_b, pc::SchedEntry);
     UP(p->d_r0_words, r0_words, uint32_t);
     UP(p->d_src, src, int32_t);
     UP(p->d_frozen_words, fw, uint32_t);
@@ -204,6 +223,7 @@ void pc_plan_destroy(pc_plan *p) {
     pc::genie_tables_release(p);
     pc::hybrid_tables_release(p);
     cudaFree(p->d_sched);
+    cudaFree(p->d_sched_b);
     cudaFree(p->d_r0_words);
     cudaFree(p->d_src);
     cudaFree(p->d_frozen_words);

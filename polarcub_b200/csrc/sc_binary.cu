@@ -33,6 +33,9 @@ int64_t sc_stream_wave_frames(const pc_plan *plan);
 int sc_stream_decode(const pc_plan *plan, int kind, const void *d_in, int64_t B, const double *h_table, int Y, uint32_t *d_cw,
                      uint32_t *d_info, void *ws, size_t ws_bytes, cudaStream_t st);
 
+#ifndef SC_SYNC
+#define SC_SYNC 2                // barriers among the warps of a block (see the kernel's group loop)
+#endif
 constexpr int LS = 4;            // levels 0..LS in shared memory: 2^(LS+1)-1 doubles per thread
 constexpr int SC_THREADS = 256;  // 8 warps = 256 frames per block
 constexpr int SMEM_VALS = (1 << (LS + 1)) - 1;
@@ -82,6 +85,81 @@ __device__ __forceinline__ double node_packed(double a, double b, bool isg, uint
         side = (same ? s1 : s2) != 0u;
     }
     return d_pack(mn / mx, side ? 1u : 0u);
+}
+
+// ---- leaf blocks (NODE_BLOCK, common.cuh): the 8 leaves of a sub-tree that is not all-frozen, decoded on registers from the level-3
+// vector.  The leaf-by-leaf walk pays ~200 instructions of schedule handling per entry (entry decode, level-loop set-up for levels
+// of 1 / 2 / 4 elements, partial sums, information word bookkeeping) on top of its node updates; here the SAME node updates run in
+// the same order on the same operands (frozen leaves take their values, all-frozen halves are skipped exactly as the walk skips its
+// rate-0 nodes), so decisions and codewords are identical, and the bookkeeping is paid once per block.  Loops over the two halves of a
+// (sub-)block are not unrolled: one copy of the node routine per tree level keeps the code small.
+__device__ __forceinline__ uint32_t xf2(uint32_t u) { return ((u ^ (u >> 1)) & 1u) | (u & 2u); }  // natural-order transform (u0 ^ u1, u1)
+__device__ __forceinline__ uint32_t xf4(uint32_t u) {
+    const uint32_t a = xf2(u & 3u), b = xf2((u >> 2) & 3u);
+    return (a ^ b) | (b << 2);
+}
+// two leaves from their level-1 vector (v0, v1); fm / fv: frozen mask / values of the two leaves; u: decisions, x: their codeword
+__device__ __forceinline__ void decode2(double v0, double v1, uint32_t fm, uint32_t fv, uint32_t &u, uint32_t &x) {
+    uint32_t u0 = fv & 1u, u1 = (fv >> 1) & 1u;
+    if (!(fm & 1u)) u0 = d_sign(node_packed(v0, v1, false, 0u));  // level 0: p0 >= p1 -> 0 (ties and (0,0) -> 0)
+    if (!(fm & 2u)) u1 = d_sign(node_packed(v0, v1, true, u0));
+    u = u0 | (u1 << 1);
+    x = (u0 ^ u1) | (u1 << 1);
+}
+// v2: the thread's level-2 vector, element h at v2[h * STR] (re-read per half: nothing stays in registers across the halves)
+template <int STR>
+__device__ __forceinline__ void decode4(const double *v2, uint32_t fm, uint32_t fv, uint32_t &u, uint32_t &x) {
+    uint32_t uu = 0, xl = 0, xr = 0;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t m2 = (fm >> (2 * half)) & 3u, f2 = (fv >> (2 * half)) & 3u;
+        uint32_t u2 = f2, x2 = xf2(f2);
+        if (m2 != 3u) {  // f (first half) or g with the first half's codeword
+            double t0, t1;  // one warp-uniform branch around specialised f / g code (a run-time node kind computes both)
+            if (half == 0) {
+                t0 = node_packed(v2[0], v2[2 * STR], false, 0u);
+                t1 = node_packed(v2[STR], v2[3 * STR], false, 0u);
+            } else {
+                t0 = node_packed(v2[0], v2[2 * STR], true, xl & 1u);
+                t1 = node_packed(v2[STR], v2[3 * STR], true, (xl >> 1) & 1u);
+            }
+            decode2(t0, t1, m2, f2, u2, x2);
+        }
+        uu |= u2 << (2 * half);
+        if (half == 0)
+            xl = x2;
+        else
+            xr = x2;
+    }
+    u = uu;
+    x = (xl ^ xr) | (xr << 2);
+}
+// v3: the thread's level-3 vector, element h at v3[h * STR]; v2: its level-2 slots (written here, as the walk does)
+template <int STR>
+__device__ __forceinline__ void decode_block8(const double *v3, double *v2, uint32_t fm, uint32_t fv, uint32_t &u, uint32_t &x) {
+    uint32_t uu = 0, xl = 0, xr = 0;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t m4 = (fm >> (4 * half)) & 15u, f4 = (fv >> (4 * half)) & 15u;
+        uint32_t u4 = f4, x4 = xf4(f4);
+        if (m4 != 15u) {
+            if (half == 0) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) v2[h * STR] = node_packed(v3[h * STR], v3[(h + 4) * STR], false, 0u);
+            } else {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) v2[h * STR] = node_packed(v3[h * STR], v3[(h + 4) * STR], true, (xl >> h) & 1u);
+            }
+            decode4<STR>(v2, m4, f4, u4, x4);
+        }
+        uu |= u4 << (4 * half);
+        if (half == 0)
+            xl = x4;
+        else
+            xr = x4;
+    }
+    u = uu;
+    x = (xl ^ xr) | (xr << 4);
 }
 
 // Elements [0, size) of a level from the level above (size >= 4), batches of 4: every load of a batch is issued before the
@@ -230,8 +308,21 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
     auto lvl_ptr = [&](int lev) -> double * { return lev <= LS ? sv + (int64_t)(SC_THREADS << lev) : gv + ((int64_t)32 << lev); };
     auto lvl_stride = [&](int lev) -> int { return lev <= LS ? SC_THREADS : 32; };
 
+    // SYNC: the warps of a block walk the same schedule on different frames; meeting at a barrier keeps them fetching the same
+    // instructions at the same time (the kernel is ~100 KB of code: warps that drift apart over a long grid-stride loop thrash the
+    // instruction cache).  1: at the start of every frame group, 2: and before every schedule entry.  A warp that has no group left
+    // still attends the block's barriers.
+    constexpr int SYNC = (R1 || MODE != MODE_DECODE) ? 0 : SC_SYNC;
+    const int64_t iters = (groups + warps_total - 1) / warps_total;
 #pragma unroll 1
-    for (int64_t grp = warp_global; grp < groups; grp += warps_total) {
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t grp = warp_global + it * warps_total;
+        if (SYNC) __syncthreads();
+        if (grp >= groups) {
+            if (SYNC >= 2 && n > 0)
+                for (int ei = 0; ei < p.n_sched; ++ei) __syncthreads();
+            continue;
+        }
         const int64_t col = grp * 32 + lane;  // always < Bpad; columns >= frames hold padding
         auto root = [&](int h, double &v0, double &v1) {
             if (KIND == PC_INPUT_SYMBOLS) {
@@ -272,6 +363,7 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
 
 #pragma unroll 1
         for (int ei = 0; ei < p.n_sched; ++ei) {
+            if (SYNC >= 2) __syncthreads();
             const SchedEntry e = p.sched[ei];
             const int i = e.i, l = e.l, top = e.top;
             const int stop = e.kind == NODE_RATE0 ? l + 1 : l;
@@ -460,6 +552,24 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
                     }
                 }
                 cwreg |= bit << (i & 31);
+            } else if (!R1 && e.kind == NODE_BLOCK) {
+                uint32_t u8, x8;
+                decode_block8<SC_THREADS>(sv + (SC_THREADS << SC_LB), sv + (SC_THREADS << (SC_LB - 1)), e.bits & 255u, (e.bits >> 8) & 255u, u8, x8);
+                uint32_t m = ~e.bits & 255u, packed = 0;  // the block's information bits, in u order
+                int cnt = 0;
+                while (m) {
+                    packed |= ((u8 >> (__ffs(m) - 1)) & 1u) << cnt;
+                    ++cnt;
+                    m &= m - 1;
+                }
+                const int sh = icount & 31;
+                infoacc |= packed << sh;
+                if (sh + cnt >= 32) {
+                    iw[(int64_t)(icount >> 5) * p.Bpad] = infoacc;
+                    infoacc = sh + cnt > 32 ? packed >> (32 - sh) : 0u;
+                }
+                icount += cnt;
+                cwreg |= x8 << (i & 31);
             } else if (e.kind == NODE_INFO) {
                 const uint32_t bit = d_sign(sv[SC_THREADS]);  // level 0: p0 >= p1 -> 0 (ties and (0,0) -> 0), :252
                 infoacc |= bit << (icount & 31);
@@ -887,6 +997,11 @@ static int sc_decode_common(const pc_plan *plan, int kind, const void *d_in, int
     p.Y = Y;
     p.Bpad = L.Bpad;
     p.sched = plan->d_sched;
+    const char *bl = getenv("PC_SC_BLOCK");  // 0: the leaf-by-leaf schedule (tests compare the two)
+    if (plan->d_sched_b && !(bl && atoi(bl) == 0)) {
+        p.sched = plan->d_sched_b;
+        p.n_sched = (int)plan->sched_b.size();
+    }
     p.r0_words = plan->d_r0_words;
     p.in_t = base + L.off_in;
     p.vals = (double *)(base + L.off_vals);
