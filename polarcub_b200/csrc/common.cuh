@@ -76,9 +76,12 @@ struct ProfScope {                // brackets a multi-launch operation as ONE me
 // (rate-0) sub-tree whose codeword is known in advance, so its probabilities are never computed.
 enum : int { NODE_INFO = 0, NODE_RATE0 = 1, NODE_GENIE = 2, NODE_RATE1 = 3, NODE_BLOCK = 4 };  // GENIE: known leaf bit, leaf probabilities captured
 // BLOCK (binary decoder's block schedule, pc_plan::sched_b): a sub-tree of 2^SC_LB leaves that is not all-frozen, decoded by one unrolled
-// routine on registers -- the same node updates in the same order as the leaf-by-leaf walk; `bits` = frozen mask (low 8 bits, bit j =
-// leaf i + j is frozen) | frozen values << 8
-constexpr int SC_LB = 3;
+// routine -- the same node updates in the same order as the leaf-by-leaf walk; `bits` = frozen mask (low 2^SC_LB bits, bit j = leaf
+// i + j is frozen) | frozen values << 2^SC_LB
+#ifndef SC_LEAF_BLOCK_LOG
+#define SC_LEAF_BLOCK_LOG 4
+#endif
+constexpr int SC_LB = SC_LEAF_BLOCK_LOG;  // <= 4: the block's vector lives in the walk's shared-memory levels and its masks in 32 bits
 // RATE1 (hybrid decoder's sub-block schedules only): all-information sub-tree, `bits` = number of entries it spans after this one
 struct SchedEntry {
     int32_t i;      // first u index covered by the node

@@ -80,7 +80,7 @@ static void build_schedule(pc_plan *p, int i, int l, std::vector<uint32_t> &r0_w
             if (p->frozen_mask[i + j]) m |= 1u << j;
             if (p->frozen_mask[i + j] && (p->frozen_vals[i + j] & 1)) v |= 1u << j;
         }
-        e.bits = m | (v << 8);
+        e.bits = m | (v << size);
         out.push_back(e);
         return;
     }

@@ -87,80 +87,68 @@ __device__ __forceinline__ double node_packed(double a, double b, bool isg, uint
     return d_pack(mn / mx, side ? 1u : 0u);
 }
 
-// ---- leaf blocks (NODE_BLOCK, common.cuh): the 8 leaves of a sub-tree that is not all-frozen, decoded on registers from the level-3
-// vector.  The leaf-by-leaf walk pays ~200 instructions of schedule handling per entry (entry decode, level-loop set-up for levels
+// ---- leaf blocks (NODE_BLOCK, common.cuh): the 2^SC_LB leaves of a sub-tree that is not all-frozen, decoded by one routine from the
+// level-SC_LB vector.  The leaf-by-leaf walk pays ~200 instructions of schedule handling per entry (entry decode, level-loop set-up for levels
 // of 1 / 2 / 4 elements, partial sums, information word bookkeeping) on top of its node updates; here the SAME node updates run in
 // the same order on the same operands (frozen leaves take their values, all-frozen halves are skipped exactly as the walk skips its
 // rate-0 nodes), so decisions and codewords are identical, and the bookkeeping is paid once per block.  Loops over the two halves of a
 // (sub-)block are not unrolled: one copy of the node routine per tree level keeps the code small.
-__device__ __forceinline__ uint32_t xf2(uint32_t u) { return ((u ^ (u >> 1)) & 1u) | (u & 2u); }  // natural-order transform (u0 ^ u1, u1)
-__device__ __forceinline__ uint32_t xf4(uint32_t u) {
-    const uint32_t a = xf2(u & 3u), b = xf2((u >> 2) & 3u);
-    return (a ^ b) | (b << 2);
+// natural-order polar transform of the low 2^L bits: T([a; b]) = [T(a) ^ T(b); T(b)]
+template <int L>
+__device__ __forceinline__ uint32_t xf_bits(uint32_t w) {
+    if (L >= 1) w ^= (w >> 1) & 0x55555555u;
+    if (L >= 2) w ^= (w >> 2) & 0x33333333u;
+    if (L >= 3) w ^= (w >> 4) & 0x0f0f0f0fu;
+    if (L >= 4) w ^= (w >> 8) & 0x00ff00ffu;
+    return w & ((1u << (1 << L)) - 1u);
 }
-// two leaves from their level-1 vector (v0, v1); fm / fv: frozen mask / values of the two leaves; u: decisions, x: their codeword
-__device__ __forceinline__ void decode2(double v0, double v1, uint32_t fm, uint32_t fv, uint32_t &u, uint32_t &x) {
-    uint32_t u0 = fv & 1u, u1 = (fv >> 1) & 1u;
-    if (!(fm & 1u)) u0 = d_sign(node_packed(v0, v1, false, 0u));  // level 0: p0 >= p1 -> 0 (ties and (0,0) -> 0)
-    if (!(fm & 2u)) u1 = d_sign(node_packed(v0, v1, true, u0));
-    u = u0 | (u1 << 1);
-    x = (u0 ^ u1) | (u1 << 1);
-}
-// v2: the thread's level-2 vector, element h at v2[h * STR] (re-read per half: nothing stays in registers across the halves)
-template <int STR>
-__device__ __forceinline__ void decode4(const double *v2, uint32_t fm, uint32_t fv, uint32_t &u, uint32_t &x) {
-    uint32_t uu = 0, xl = 0, xr = 0;
+// The sub-tree of 2^L leaves whose level-L vector is in the thread's shared-memory slots (element h of level l at sv[((1 << l) + h) * STR],
+// the walk's own layout; the levels below L are written there as the walk does).  fm / fv: frozen mask / values of the leaves;
+// u: decisions, x: their codeword.  The two halves run through ONE copy of the code per level (the half loop is not unrolled) with a
+// warp-uniform branch around the specialised f / g updates.
+template <int L, int STR>
+struct LeafBlock {
+    static __device__ __forceinline__ void run(double *sv, uint32_t fm, uint32_t fv, uint32_t &u, uint32_t &x) {
+        constexpr int H = 1 << (L - 1);
+        constexpr uint32_t HM = (1u << H) - 1u;
+        const double *vL = sv + (STR << L);
+        double *vl = sv + (STR << (L - 1));
+        uint32_t uu = 0, xl = 0, xr = 0;
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        const uint32_t m2 = (fm >> (2 * half)) & 3u, f2 = (fv >> (2 * half)) & 3u;
-        uint32_t u2 = f2, x2 = xf2(f2);
-        if (m2 != 3u) {  // f (first half) or g with the first half's codeword
-            double t0, t1;  // one warp-uniform branch around specialised f / g code (a run-time node kind computes both)
-            if (half == 0) {
-                t0 = node_packed(v2[0], v2[2 * STR], false, 0u);
-                t1 = node_packed(v2[STR], v2[3 * STR], false, 0u);
-            } else {
-                t0 = node_packed(v2[0], v2[2 * STR], true, xl & 1u);
-                t1 = node_packed(v2[STR], v2[3 * STR], true, (xl >> 1) & 1u);
+        for (int half = 0; half < 2; ++half) {
+            const uint32_t mH = (fm >> (H * half)) & HM, fH = (fv >> (H * half)) & HM;
+            uint32_t uH = fH, xH = xf_bits<L - 1>(fH);
+            if (mH != HM) {  // not all-frozen: f (first half) or g with the first half's codeword, then the half's own sub-tree
+                if (half == 0) {
+#pragma unroll 4
+                    for (int h = 0; h < H; ++h) vl[h * STR] = node_packed(vL[h * STR], vL[(h + H) * STR], false, 0u);
+                } else {
+#pragma unroll 4
+                    for (int h = 0; h < H; ++h) vl[h * STR] = node_packed(vL[h * STR], vL[(h + H) * STR], true, (xl >> h) & 1u);
+                }
+                LeafBlock<L - 1, STR>::run(sv, mH, fH, uH, xH);
             }
-            decode2(t0, t1, m2, f2, u2, x2);
+            uu |= uH << (H * half);
+            if (half == 0)
+                xl = xH;
+            else
+                xr = xH;
         }
-        uu |= u2 << (2 * half);
-        if (half == 0)
-            xl = x2;
-        else
-            xr = x2;
+        u = uu;
+        x = (xl ^ xr) | (xr << H);
     }
-    u = uu;
-    x = (xl ^ xr) | (xr << 2);
-}
-// v3: the thread's level-3 vector, element h at v3[h * STR]; v2: its level-2 slots (written here, as the walk does)
+};
 template <int STR>
-__device__ __forceinline__ void decode_block8(const double *v3, double *v2, uint32_t fm, uint32_t fv, uint32_t &u, uint32_t &x) {
-    uint32_t uu = 0, xl = 0, xr = 0;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        const uint32_t m4 = (fm >> (4 * half)) & 15u, f4 = (fv >> (4 * half)) & 15u;
-        uint32_t u4 = f4, x4 = xf4(f4);
-        if (m4 != 15u) {
-            if (half == 0) {
-#pragma unroll
-                for (int h = 0; h < 4; ++h) v2[h * STR] = node_packed(v3[h * STR], v3[(h + 4) * STR], false, 0u);
-            } else {
-#pragma unroll
-                for (int h = 0; h < 4; ++h) v2[h * STR] = node_packed(v3[h * STR], v3[(h + 4) * STR], true, (xl >> h) & 1u);
-            }
-            decode4<STR>(v2, m4, f4, u4, x4);
-        }
-        uu |= u4 << (4 * half);
-        if (half == 0)
-            xl = x4;
-        else
-            xr = x4;
+struct LeafBlock<1, STR> {  // two leaves from their level-1 vector
+    static __device__ __forceinline__ void run(double *sv, uint32_t fm, uint32_t fv, uint32_t &u, uint32_t &x) {
+        const double v0 = sv[2 * STR], v1 = sv[3 * STR];
+        uint32_t u0 = fv & 1u, u1 = (fv >> 1) & 1u;
+        if (!(fm & 1u)) u0 = d_sign(node_packed(v0, v1, false, 0u));  // level 0: p0 >= p1 -> 0 (ties and (0,0) -> 0)
+        if (!(fm & 2u)) u1 = d_sign(node_packed(v0, v1, true, u0));
+        u = u0 | (u1 << 1);
+        x = (u0 ^ u1) | (u1 << 1);
     }
-    u = uu;
-    x = (xl ^ xr) | (xr << 4);
-}
+};
 
 // Elements [0, size) of a level from the level above (size >= 4), batches of 4: every load of a batch is issued before the
 // first division.  SSTR / DSTR: element strides (doubles) of the source and destination levels -- SC_THREADS for the
@@ -553,9 +541,10 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
                 }
                 cwreg |= bit << (i & 31);
             } else if (!R1 && e.kind == NODE_BLOCK) {
+                constexpr uint32_t BM = (1u << (1 << SC_LB)) - 1u;
                 uint32_t u8, x8;
-                decode_block8<SC_THREADS>(sv + (SC_THREADS << SC_LB), sv + (SC_THREADS << (SC_LB - 1)), e.bits & 255u, (e.bits >> 8) & 255u, u8, x8);
-                uint32_t m = ~e.bits & 255u, packed = 0;  // the block's information bits, in u order
+                LeafBlock<SC_LB, SC_THREADS>::run(sv, e.bits & BM, (e.bits >> (1 << SC_LB)) & BM, u8, x8);
+                uint32_t m = ~e.bits & BM, packed = 0;  // the block's information bits, in u order
                 int cnt = 0;
                 while (m) {
                     packed |= ((u8 >> (__ffs(m) - 1)) & 1u) << cnt;
