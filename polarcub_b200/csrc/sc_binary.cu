@@ -1572,6 +1572,11 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
                 p.n_sched = T->r1_len[j];
                 sc_decode_kernel<SC_INPUT_PACKED, MODE_DECODE, true><<<grid, SC_THREADS, smem, st>>>(p);
             } else {
+                const char *bl = getenv("PC_SC_BLOCK");
+                if (sp->d_sched_b && !(bl && atoi(bl) == 0)) {  // leaf blocks, as in sc_decode_common
+                    p.sched = sp->d_sched_b;
+                    p.n_sched = (int)sp->sched_b.size();
+                }
                 sc_decode_kernel<SC_INPUT_PACKED><<<grid, SC_THREADS, smem, st>>>(p);
             }
             PC_LAUNCH_CHECK();
