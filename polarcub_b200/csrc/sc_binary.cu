@@ -239,6 +239,53 @@ __device__ __forceinline__ void level_batches(const double *sp, double *dp, int 
     }
 }
 
+// Levels lev and lev-1 from level lev+1 in ONE sweep over the global scratch: the two level-lev elements an element of level lev-1
+// needs are produced (and stored: the g pass of level lev reads them a sub-tree later) and combined while still in registers, so
+// level lev is not re-read for the f pass below it.  Two elements of level lev-1 per iteration: eight loads in flight, four + two node
+// updates.  sp: level lev+1 (global, pitch 32), d0: level lev (global), d1: level lev-1 (pitch DSTR1: global or shared memory).
+#ifndef SC_FUSE2
+#define SC_FUSE2 1
+#endif
+template <int DSTR1>
+__device__ __forceinline__ void fused2_levels(const double *sp, double *d0, double *d1, int lev, bool isg, const uint32_t *uw, int64_t Bpad) {
+    const int S = 1 << (lev - 1);  // elements of level lev-1 (>= 16); level lev has 2 S, the source 4 S
+    uint32_t ub0 = 0, ub1 = 0;     // decision words of the level-lev elements h .. and h + S ..
+    if (isg && S < 32) {           // S == 16: level lev is one word
+        ub0 = uw[0];
+        ub1 = ub0 >> S;
+    }
+    const double *s0 = sp, *s1 = sp + (int64_t)S * 32, *s2 = s1 + (int64_t)S * 32, *s3 = s2 + (int64_t)S * 32;
+    double *e0 = d0, *e1 = d0 + (int64_t)S * 32;
+#pragma unroll 1
+    for (int h = 0; h < S; h += 2) {
+        if (isg && S >= 32 && (h & 31) == 0) {
+            ub0 = uw[(int64_t)(h >> 5) * Bpad];
+            ub1 = uw[(int64_t)((h + S) >> 5) * Bpad];
+        }
+        double a[2], b[2], c[2], d[2], pq[2], qq[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            a[u] = s0[u * 32];
+            b[u] = s2[u * 32];
+            c[u] = s1[u * 32];
+            d[u] = s3[u * 32];
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            pq[u] = node_packed(a[u], b[u], isg, (ub0 >> ((h + u) & 31)) & 1u);
+            qq[u] = node_packed(c[u], d[u], isg, (ub1 >> ((h + u) & 31)) & 1u);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            e0[u * 32] = pq[u];
+            e1[u * 32] = qq[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) d1[u * DSTR1] = node_packed(pq[u], qq[u], false, 0u);
+        s0 += 64, s1 += 64, s2 += 64, s3 += 64, e0 += 64, e1 += 64, d1 += 2 * DSTR1;
+    }
+}
+
 // MODE 0: the decoder.  The other modes walk the UNPRUNED schedule (one NODE_GENIE entry per leaf):
 //   MODE_GENIE  every leaf bit is known (u_t); leaf probabilities are captured (marg_t)
 //   MODE_DUAL   non-uniform a-priori distribution: lanes 2j / 2j+1 hold the a-posteriori (xy) and a-priori (x) trees of ONE
@@ -364,8 +411,10 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
                 isg = false;
                 resume = -1;
             }
+            int step = 1;  // levels produced by this iteration
 #pragma unroll 1
-            for (; lev >= stop; --lev, isg = false) {
+            for (; lev >= stop; lev -= step, isg = false) {
+                step = 1;
                 const int size = 1 << lev;
                 if (lut && lev == n - 1) {  // looked up on demand by the level below
                     top_mode = isg ? 1 : 0;
@@ -375,6 +424,15 @@ __global__ void __launch_bounds__(SC_THREADS, R1 ? 1 : SC_BLOCKS_PER_SM) sc_deco
                 const uint32_t ureg = cwreg >> ((i - size) & 31);               // g: decision bits of levels below 32
                 double *dp = lvl_ptr(lev);
                 const int dstr = lvl_stride(lev);
+                if (SC_FUSE2 && !R1 && MODE == MODE_DECODE && lev > stop && lev > LS && lev + 1 < n && !(lut && lev == n - 2)) {
+                    // source (level lev+1) and level lev in the global scratch, level lev-1 there or (lev - 1 == LS) in shared memory
+                    if (lev - 1 > LS)
+                        fused2_levels<32>(lvl_ptr(lev + 1), dp, lvl_ptr(lev - 1), lev, isg, uw, p.Bpad);
+                    else
+                        fused2_levels<SC_THREADS>(lvl_ptr(lev + 1), dp, lvl_ptr(lev - 1), lev, isg, uw, p.Bpad);
+                    step = 2;
+                    continue;
+                }
                 if (KIND == SC_INPUT_PACKED && lev + 1 == n) {
                     // the top level is a packed vector [2^n][Bpad] produced by the element-parallel upper stages (sc hybrid)
                     const double *sp = (const double *)p.in_t + col, *sp2 = sp + (int64_t)size * p.Bpad;
