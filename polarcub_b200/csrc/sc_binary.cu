@@ -22,6 +22,7 @@
 #include <map>
 #include <mutex>
 
+#include "async_copy.cuh"
 #include "sc_arith.cuh"
 
 namespace pc {
@@ -1319,6 +1320,75 @@ __global__ void __launch_bounds__(256) hy_level8_kernel(int64_t size, int64_t Bp
     }
 }
 
+// The same level update with the input rows staged by BULK ASYNCHRONOUS COPIES (cp.async.bulk completing on mbarriers, async_copy.cuh).
+// With plain loads the bytes in flight are bounded by the register file (one register per 4-byte load: ~64 KB per SM at 50 %
+// occupancy, long_scoreboard 26 warps per issue, 69 % of the copy peak in ncu); staged rows cost no registers.  A block owns 32
+// consecutive elements x 256 frame quads (1 KB per row): one thread arms four barriers (8 rows of both operands each, 16 KB) and
+// issues all 64 row copies at once; the block consumes stage after stage.  64 KB of shared memory per block, three blocks per SM.
+template <bool PACK4>
+__global__ void __launch_bounds__(256) hy_level8_bulk_kernel(int64_t size, int64_t Bpad, const uint8_t *__restrict__ in,
+                                                             const uint32_t *__restrict__ xw, int isg, uint8_t *__restrict__ out) {
+    extern __shared__ __align__(128) uint32_t sm_rows[];  // [2][32][256]: rows of operand a, then of operand b
+    __shared__ uint64_t bars[4];
+    const int64_t Bq = Bpad >> 2;
+    const int64_t hb = blockIdx.y, fq0 = (int64_t)blockIdx.x * 256;
+    const int cnt = (int)((Bq - fq0) < 256 ? (Bq - fq0) : 256);  // frame quads of this tile (a multiple of 8: Bpad is a multiple of 32)
+    const uint32_t bytes = (uint32_t)cnt * 4u;
+    const int t = threadIdx.x;
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (t == 0) {
+        const uint8_t *a = in + (hb * 32) * Bpad + fq0 * 4, *b = a + size * Bpad;
+#pragma unroll 1
+        for (int s = 0; s < 4; ++s) {
+            mbar_expect_tx(&bars[s], 16u * bytes);
+#pragma unroll 1
+            for (int r = 8 * s; r < 8 * s + 8; ++r) {
+                bulk_g2s(sm_rows + r * 256, a + (int64_t)r * Bpad, bytes, &bars[s]);
+                bulk_g2s(sm_rows + (32 + r) * 256, b + (int64_t)r * Bpad, bytes, &bars[s]);
+            }
+        }
+    }
+    const bool act = t < cnt;
+    const int64_t fq = fq0 + t;
+    uint4 wu = make_uint4(0, 0, 0, 0);
+    if (isg && act) wu = *(const uint4 *)(xw + hb * Bpad + 4 * fq);
+    uint32_t *o = (uint32_t *)out + hb * 32 * Bq + fq;
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+        mbar_wait(&bars[s], 0);
+        if (!act) continue;
+#pragma unroll
+        for (int k0 = 8 * s; k0 < 8 * s + 8; k0 += 4) {
+            uint32_t r[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = k0 + kk;
+                const uint32_t av = sm_rows[k * 256 + t], bv = sm_rows[(32 + k) * 256 + t];
+                const uint32_t u = ((wu.x >> k) & 1u) | (((wu.y >> k) & 1u) << 8) | (((wu.z >> k) & 1u) << 16) | (((wu.w >> k) & 1u) << 24);
+                r[kk] = isg ? g8(av, bv, u) : f8(av, bv);
+            }
+            if (PACK4) {
+                const uint32_t lo01 = __byte_perm(r[0], r[1], 0x5140), hi01 = __byte_perm(r[0], r[1], 0x7362);
+                const uint32_t lo23 = __byte_perm(r[2], r[3], 0x5140), hi23 = __byte_perm(r[2], r[3], 0x7362);
+                uint4 tt;
+                tt.x = __byte_perm(lo01, lo23, 0x5410);
+                tt.y = __byte_perm(lo01, lo23, 0x7632);
+                tt.z = __byte_perm(hi01, hi23, 0x5410);
+                tt.w = __byte_perm(hi01, hi23, 0x7632);
+                *(uint4 *)((uint32_t *)out + (hb * 8 + (k0 >> 2)) * Bpad + 4 * fq) = tt;
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) o[(k0 + kk) * Bq] = r[kk];
+            }
+        }
+    }
+}
+
 // out[h][f], h < quarter = N/4: node(L[h], L[h + quarter]) with L[e] = lut[mode(e)][sym[e]][sym[e + N/2]];
 // top_g: level n-1 is in its g phase, its decision bits are x[0, N/2) = the words at x0; xw: this level's decision words
 __global__ void __launch_bounds__(256) hy_level_sym_kernel(int64_t quarter, int64_t Bpad, const uint8_t *__restrict__ sym, int Y,
@@ -1528,6 +1598,12 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
     for (int y = 0; y < Y; ++y) r1 = r1 || ((h_table[2 * y] == 0.0) != (h_table[2 * y + 1] == 0.0));
     if (const char *s = getenv("PC_SC_R1")) r1 = r1 && atoi(s) != 0;
     const bool et = r1 && plan->n >= HY_L0 + 3 && hy_erasure_type(h_table, Y);
+    const char *bk = getenv("PC_HY_BULK");  // 0: the plain-load level kernel (kept for comparison)
+    const bool bulk8 = et && !(bk && atoi(bk) == 0);
+    if (bulk8) {
+        PC_CUDA(cudaFuncSetAttribute(hy_level8_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        PC_CUDA(cudaFuncSetAttribute(hy_level8_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    }
     int64_t chunk = round_up(B, 32);
     if (chunk > hy_frames_cap(et)) chunk = hy_frames_cap(et);
     while (chunk > 32 && hy_layout(plan, T, chunk, et).total > ws_bytes) chunk = round_up(chunk / 2, 32);
@@ -1574,7 +1650,13 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
             if (et && lev == n - 2)
                 hy_level_sym8_kernel<<<blocks_of((size >> 5) * (Bp / 4)), 256, 0, st>>>(size, Bp, sym, Y, (const uint8_t *)(lut + 768), cw_t,
                                                                               i >= N / 2 ? 1 : 0, xw, isg ? 1 : 0, V8(lev));
-            else if (et && lev == HY_L0)
+            else if (et && bulk8 && (size >> 5) <= 65535) {
+                const dim3 g((unsigned)((Bp / 4 + 255) / 256), (unsigned)(size >> 5));
+                if (lev == HY_L0)
+                    hy_level8_bulk_kernel<true><<<g, 256, 65536, st>>>(size, Bp, V8(lev + 1), xw, isg ? 1 : 0, V8(lev));
+                else
+                    hy_level8_bulk_kernel<false><<<g, 256, 65536, st>>>(size, Bp, V8(lev + 1), xw, isg ? 1 : 0, V8(lev));
+            } else if (et && lev == HY_L0)
                 hy_level8_kernel<true><<<blocks_of((size >> 5) * (Bp / 4)), 256, 0, st>>>(size, Bp, V8(lev + 1), xw, isg ? 1 : 0, V8(lev));
             else if (et)
                 hy_level8_kernel<false><<<blocks_of((size >> 5) * (Bp / 4)), 256, 0, st>>>(size, Bp, V8(lev + 1), xw, isg ? 1 : 0, V8(lev));
