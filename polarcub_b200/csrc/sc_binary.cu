@@ -1320,6 +1320,84 @@ __global__ void __launch_bounds__(256) hy_level8_kernel(int64_t size, int64_t Bp
     }
 }
 
+// Level n-2 from the channel symbols with the four symbol rows of every element staged by bulk asynchronous copies: a ring of two
+// slots (8 elements x 4 rows x 1 KB = 32 KB each); the slot an 8-element step has consumed is re-armed for the step after next.
+__global__ void __launch_bounds__(256) hy_level_sym8_bulk_kernel(int64_t quarter, int64_t Bpad, const uint8_t *__restrict__ sym, int Y,
+                                                                 const uint8_t *__restrict__ lut8, const uint32_t *__restrict__ x0,
+                                                                 int top_g, const uint32_t *__restrict__ xw, int isg,
+                                                                 uint8_t *__restrict__ out) {
+    extern __shared__ __align__(128) uint32_t sm_rows[];  // [slot][stream][row][256]
+    __shared__ uint64_t bars[2];
+    __shared__ uint8_t s_lut[768];
+    const int t = threadIdx.x;
+    for (int i = t; i < 3 * Y * Y; i += blockDim.x) s_lut[i] = lut8[i];
+    if (t == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int64_t Bq = Bpad >> 2, half = 2 * quarter;
+    const int64_t hb = blockIdx.y, fq0 = (int64_t)blockIdx.x * 256;
+    const int cnt = (int)((Bq - fq0) < 256 ? (Bq - fq0) : 256);
+    const uint32_t bytes = (uint32_t)cnt * 4u;
+    const uint8_t *b0 = sym + (hb * 32) * Bpad + fq0 * 4;
+    auto issue = [&](int s) {  // rows 8 s .. 8 s + 7 of the four streams into slot s & 1
+        const int slot = s & 1;
+        mbar_expect_tx(&bars[slot], 32u * bytes);
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const uint8_t *src = b0 + ((j & 1) ? half : 0) * Bpad + ((j & 2) ? quarter : 0) * Bpad + (int64_t)(8 * s) * Bpad;
+#pragma unroll 1
+            for (int r = 0; r < 8; ++r) bulk_g2s(sm_rows + ((slot * 4 + j) * 8 + r) * 256, src + (int64_t)r * Bpad, bytes, &bars[slot]);
+        }
+    };
+    if (t == 0) {
+        issue(0);
+        issue(1);
+    }
+    const bool act = t < cnt;
+    const int64_t fq = fq0 + t;
+    uint4 wa = make_uint4(0, 0, 0, 0), wb = wa, wu = wa;
+    if (act && top_g) {
+        wa = *(const uint4 *)(x0 + hb * Bpad + 4 * fq);
+        wb = *(const uint4 *)(x0 + (hb + (quarter >> 5)) * Bpad + 4 * fq);
+    }
+    if (act && isg) wu = *(const uint4 *)(xw + hb * Bpad + 4 * fq);
+    const uint32_t wav[4] = {wa.x, wa.y, wa.z, wa.w}, wbv[4] = {wb.x, wb.y, wb.z, wb.w}, wuv[4] = {wu.x, wu.y, wu.z, wu.w};
+    const uint32_t YY = (uint32_t)(Y * Y);
+    uint32_t *o = (uint32_t *)out + hb * 32 * Bq + fq;
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+        const int slot = s & 1;
+        mbar_wait(&bars[slot], (uint32_t)((s >> 1) & 1));
+        if (act) {
+#pragma unroll 4
+            for (int r = 0; r < 8; ++r) {
+                const int k = 8 * s + r;
+                const uint32_t *row = sm_rows + (slot * 4 * 8 + r) * 256 + t;  // stream j at row[j * 8 * 256]
+                const uint32_t y0 = row[0], y1 = row[8 * 256], y2 = row[16 * 256], y3 = row[24 * 256];  // streams: h, h + half, h + quarter, h + quarter + half
+                uint32_t A = 0, Bv = 0, U = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t ma = top_g ? YY + YY * ((wav[j] >> k) & 1u) : 0u, mb = top_g ? YY + YY * ((wbv[j] >> k) & 1u) : 0u;
+                    A |= (uint32_t)s_lut[ma + ((y0 >> (8 * j)) & 255u) * Y + ((y1 >> (8 * j)) & 255u)] << (8 * j);
+                    Bv |= (uint32_t)s_lut[mb + ((y2 >> (8 * j)) & 255u) * Y + ((y3 >> (8 * j)) & 255u)] << (8 * j);
+                    U |= ((wuv[j] >> k) & 1u) << (8 * j);
+                }
+                o[k * Bq] = isg ? g8(A, Bv, U) : f8(A, Bv);
+            }
+        }
+        if (s + 2 < 4) {
+            __syncthreads();  // every thread has read the slot
+            if (t == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(s + 2);
+            }
+        }
+    }
+}
+
 // The same level update with the input rows staged by BULK ASYNCHRONOUS COPIES (cp.async.bulk completing on mbarriers, async_copy.cuh).
 // With plain loads the bytes in flight are bounded by the register file (one register per 4-byte load: ~64 KB per SM at 50 %
 // occupancy, long_scoreboard 26 warps per issue, 69 % of the copy peak in ncu); staged rows cost no registers.  A block owns 32
@@ -1603,6 +1681,7 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
     if (bulk8) {
         PC_CUDA(cudaFuncSetAttribute(hy_level8_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         PC_CUDA(cudaFuncSetAttribute(hy_level8_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        PC_CUDA(cudaFuncSetAttribute(hy_level_sym8_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     }
     int64_t chunk = round_up(B, 32);
     if (chunk > hy_frames_cap(et)) chunk = hy_frames_cap(et);
@@ -1647,7 +1726,10 @@ static int sc_hybrid_decode(const pc_plan *plan, const uint8_t *d_y, int64_t B, 
             const int64_t size = (int64_t)1 << lev;
             const uint32_t *xw = isg ? cw_t + ((i - size) >> 5) * Bp : cw_t;
             if (lev == n - 1) return PC_OK;  // looked up on demand by the level below
-            if (et && lev == n - 2)
+            if (et && lev == n - 2 && bulk8 && (size >> 5) <= 65535)
+                hy_level_sym8_bulk_kernel<<<dim3((unsigned)((Bp / 4 + 255) / 256), (unsigned)(size >> 5)), 256, 65536, st>>>(
+                    size, Bp, sym, Y, (const uint8_t *)(lut + 768), cw_t, i >= N / 2 ? 1 : 0, xw, isg ? 1 : 0, V8(lev));
+            else if (et && lev == n - 2)
                 hy_level_sym8_kernel<<<blocks_of((size >> 5) * (Bp / 4)), 256, 0, st>>>(size, Bp, sym, Y, (const uint8_t *)(lut + 768), cw_t,
                                                                               i >= N / 2 ? 1 : 0, xw, isg ? 1 : 0, V8(lev));
             else if (et && bulk8 && (size >> 5) <= 65535) {
